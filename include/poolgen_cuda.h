@@ -1,0 +1,155 @@
+/*
+ * poolgen_cuda.h -- C ABI of the B200 (sm_100a) per-locus GWAS scan library (libpoolgen_cuda.so).
+ *
+ * This is the drop-in boundary for ONE hot path of jeffersonfparil/poolgen: the per-locus
+ * callbacks that `ChunkyReadAnalyseWrite::read_analyse_write` invokes for every line of a sync
+ * file (reference: src/base/structs_and_traits.rs:245-265, impls src/base/sync.rs:606-786 and
+ * 788-970), i.e.
+ *      gwas::ols_iterate          src/gwas/ols.rs:201-276            PG_KIND_OLS
+ *      gwas::correlation          src/gwas/correlation_test.rs:73-129 PG_KIND_CORR
+ *      tables::chisq              src/tables/chisq_test.rs:5-47       PG_KIND_CHISQ
+ *      tables::fisher             src/tables/fisher_exact_test.rs:32-130 PG_KIND_FISHER
+ * and the whole-matrix entry `ols_with_covariate` (src/gwas/ols.rs:278-436) through the pg_kinship_*
+ * functions.  The per-locus callback `Fn(&mut T, &FilterStats) -> Option<String>` becomes a
+ * per-BATCH call: the reader threads parse their byte range (src/base/sync.rs:827-868) into a slab
+ * of counts, hand the slab over, and format the returned numeric records with the reference's own
+ * rounding rules (src/base/helpers.rs:103-117).  INTEGRATION.md shows the Rust `extern "C"` stub.
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions cross this boundary; every function returns an int
+ *     (PG_OK = 0, negative = error class); the message is available from pg_last_error().
+ *   - one pg_ctx per GPU (one process or one thread per GPU); all functions taking the same
+ *     pg_batch must be called from one thread at a time; different batches are independent.
+ *   - allele codes follow the sync column order A:T:C:G:N:D = 0..5 (src/base/sync.rs:134-137).
+ *   - per-locus failures are DATA (status codes), never errors.
+ *   - there is no CPU fallback: every entry point fails with PG_ERR_CUDA when no sm_100 device
+ *     is usable.
+ */
+#ifndef POOLGEN_CUDA_H
+#define POOLGEN_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_ABI_VERSION 1
+
+enum { PG_OK = 0, PG_ERR_ARG = -1, PG_ERR_CUDA = -2, PG_ERR_STATE = -3, PG_ERR_UNSUPPORTED = -4, PG_ERR_NCCL = -5 };
+
+/* the four per-locus analyses (callbacks) */
+enum { PG_KIND_OLS = 0, PG_KIND_CORR = 1, PG_KIND_CHISQ = 2, PG_KIND_FISHER = 3 };
+
+/* per-locus status, = what the reference callback returned */
+enum {
+    PG_LOCUS_FILTERED = 0,    /* None: LocusCounts::filter dropped the locus (src/base/sync.rs:195-303) */
+    PG_LOCUS_OK = 1,          /* Some(line) */
+    PG_LOCUS_FAILED = 2,      /* None: the regression could not be solved (src/gwas/ols.rs:250-253) */
+    PG_LOCUS_UNSUPPORTED = 3, /* shape the device path does not implement (n_pools < n coefficients) */
+    PG_LOCUS_PANIC = 4        /* the reference would panic on this locus (assert / unwrap) */
+};
+
+#define PG_MAX_ALLELES 6
+#define PG_MAX_SLOTS 5 /* output rows per locus = kept alleles - 1 <= 5 */
+
+typedef struct pg_ctx pg_ctx;
+typedef struct pg_scan pg_scan;
+typedef struct pg_batch pg_batch;
+
+/* FilterStats (src/base/structs_and_traits.rs:69-78); only the fields the sync path reads.
+ * pool_sizes are taken as handed over by the phenotype loader, i.e. already normalised to sum 1
+ * (src/base/phen.rs:82-84); the library re-derives s_i / sum(s) exactly as src/base/sync.rs:262-270. */
+typedef struct {
+    int32_t remove_ns;             /* !--keep-ns */
+    uint64_t min_coverage_depth;   /* --min-coverage-depth */
+    double min_allele_frequency;   /* --min-allele-frequency */
+    double max_missingness_rate;   /* --max-missingness-rate */
+    int32_t n_pool_sizes;
+    const double *pool_sizes;
+} pg_filter;
+
+/* Numeric records of one batch, host pointers owned by the library (pinned), valid until the next
+ * download/destroy of that batch.  L = n_loci, S = n_slots (= n_alleles_dev - 1), k = n_phen.
+ *   meta[l]      byte0 status, byte1 n_out (rows for this locus), byte 2+s allele code of row s
+ *   freq_mean[l*S+s]            mean frequency of that allele            (ols.rs:265-268 / correlation_test.rs:119)
+ *   stats[((l*S+s)*k+j)*4 + c]  c=0 statistic (beta | r rounded to 7 digits, correlation_test.rs:70)
+ *                               c=1 standard error of beta | unrounded r
+ *                               c=2 t
+ *                               c=3 p-value
+ * CHISQ / FISHER: S = 1, k = 1, n_out = number of kept alleles, allele codes of ALL kept alleles in
+ * bytes 2.., stats[l*4+0] = chi2 | p_observed, stats[l*4+3] = p-value, freq_mean unused. */
+typedef struct {
+    int64_t n_loci;
+    int32_t n_slots;
+    int32_t n_phen;
+    const uint64_t *meta;
+    const double *freq_mean;
+    const double *stats;
+} pg_results;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int pg_abi_version(void);
+int pg_init(int device, pg_ctx **out);
+void pg_destroy(pg_ctx *ctx);
+const char *pg_last_error(const pg_ctx *ctx); /* ctx may be NULL: last error of a failed pg_init */
+int pg_device_info(pg_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
+/* pinned host slabs the reader threads parse into */
+int pg_pinned_alloc(pg_ctx *ctx, size_t bytes, void **out);
+int pg_pinned_free(pg_ctx *ctx, void *p);
+
+/* ---- scan configuration = (callback, FilterStats, phenotypes) --------------------------------
+ * n_alleles / allele_codes name the count columns the caller ships per pool (a subset of the six
+ * sync columns, in sync order).  When filter->remove_ns is set a column coded N(4) is dropped on
+ * the device exactly like src/base/sync.rs:200-213.
+ * phen: n_pools x k row-major f64 (Phen.phen_matrix, src/base/phen.rs:86-97); NULL/0 for the table tests. */
+int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, int n_alleles,
+                 const uint8_t *allele_codes, const double *phen, int k, pg_scan **out);
+int pg_scan_close(pg_scan *scan);
+
+/* ---- batches: a device-resident block of loci + its results ---------------------------------- */
+int pg_batch_create(pg_scan *scan, int64_t capacity_loci, pg_batch **out);
+int pg_batch_destroy(pg_batch *b);
+/* host -> device, asynchronous on the batch's stream.
+ * counts: u32 [locus][allele][pool] (pool fastest), the parsed LocusCounts.matrix transposed. */
+int pg_batch_upload_counts(pg_batch *b, const uint32_t *counts, int64_t n_loci);
+/* same, 16-bit counts (every count < 65536): half the PCIe bytes */
+int pg_batch_upload_counts_u16(pg_batch *b, const uint16_t *counts, int64_t n_loci);
+/* f64 first-stage frequency matrix, column-major n_pools x n_alleles per locus ([locus][allele][pool],
+ * N column already removed, NaN where the pool has no coverage) + per-pool depth [locus][pool].
+ * OLS / CORR only. */
+int pg_batch_upload_freq(pg_batch *b, const double *freq, const uint32_t *depth, int64_t n_loci);
+/* synthetic counts generated on the device (integer hash; pg_synth_counts_host replays it bit for bit) */
+int pg_batch_synth(pg_batch *b, uint64_t seed, int64_t first_locus, int64_t n_loci);
+/* launch the scan kernel over the loci resident in the batch (asynchronous) */
+int pg_batch_run(pg_batch *b);
+/* device -> pinned host copy of the result records (asynchronous), then pg_batch_sync + pg_batch_results */
+int pg_batch_download(pg_batch *b);
+int pg_batch_sync(pg_batch *b);
+int pg_batch_results(pg_batch *b, pg_results *out);
+/* timing helper: `iters` back-to-back pg_batch_run launches bracketed by CUDA events on the batch's
+ * stream; returns the total milliseconds and how many kernels were launched */
+int pg_batch_time_runs(pg_batch *b, int iters, float *ms_total, int *n_launches);
+/* device bytes one launch reads as input and writes as results (for traffic accounting) */
+int pg_batch_bytes(pg_batch *b, size_t *input_bytes, size_t *result_bytes);
+
+/* ---- streaming convenience used by the reader threads (src/base/sync.rs:917-939): submit a slab,
+ * get a ticket, collect the records later; up to PG_STREAM_DEPTH slabs are in flight so the H2D
+ * copy of slab i+1 overlaps the scan of slab i and the D2H copy of slab i-1. ---------------------- */
+#define PG_STREAM_DEPTH 3
+int pg_scan_stream_begin(pg_scan *scan, int64_t max_loci_per_slab);
+int pg_scan_submit_counts(pg_scan *scan, const uint32_t *counts, int64_t n_loci, int *ticket);
+int pg_scan_submit_counts_u16(pg_scan *scan, const uint16_t *counts, int64_t n_loci, int *ticket);
+int pg_scan_submit_freq(pg_scan *scan, const double *freq, const uint32_t *depth, int64_t n_loci, int *ticket);
+int pg_scan_collect(pg_scan *scan, int ticket, pg_results *out);
+
+/* ---- synthetic workload, host side: identical bits to pg_batch_synth ------------ */
+int pg_synth_counts_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int n_pools, int n_alleles,
+                         uint32_t *counts_out);
+int pg_synth_phen_host(uint64_t seed, int n_pools, int k, double *phen_out /* n_pools x k row-major */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

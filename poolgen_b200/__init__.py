@@ -1,0 +1,45 @@
+"""poolgen_b200 -- B200 (sm_100a) implementation of poolgen's per-locus GWAS scan.
+
+Host-side mirror of the reference's callback interface for the hot path only:
+`ols_iterate` (src/gwas/ols.rs:201-276), `correlation` (src/gwas/correlation_test.rs:73-129),
+`chisq` (src/tables/chisq_test.rs:5-47), `fisher` (src/tables/fisher_exact_test.rs:32-130), each taking a
+BATCH of parsed loci instead of one.  All arithmetic runs in libpoolgen_cuda.so (hand-written CUDA);
+nothing here computes on the CPU.
+"""
+from .capi import (ALLELE_NAMES, KIND_CHISQ, KIND_CORR, KIND_FISHER, KIND_OLS, LOCUS_FAILED, LOCUS_FILTERED,
+                   LOCUS_OK, LOCUS_PANIC, LOCUS_UNSUPPORTED, Batch, Context, FilterStats, PgError, Scan,
+                   ScanResults, synth_counts_host, synth_phen_host)
+
+__all__ = ["ALLELE_NAMES", "KIND_CHISQ", "KIND_CORR", "KIND_FISHER", "KIND_OLS", "LOCUS_FAILED", "LOCUS_FILTERED",
+           "LOCUS_OK", "LOCUS_PANIC", "LOCUS_UNSUPPORTED", "Batch", "Context", "FilterStats", "PgError", "Scan",
+           "ScanResults", "synth_counts_host", "synth_phen_host", "ols_iterate", "correlation", "chisq", "fisher"]
+
+_SYNC_CODES = (0, 1, 2, 3, 4, 5)
+
+
+def _run(kind, ctx, counts, filter_stats, phen, allele_codes):
+    scan = Scan(ctx, kind, filter_stats, counts.shape[2], allele_codes, phen)
+    try:
+        return scan.run_counts(counts)
+    finally:
+        scan.close()
+
+
+def ols_iterate(ctx, counts, phen, filter_stats, allele_codes=_SYNC_CODES):
+    """gwas::ols_iterate over a batch: counts uint32 [L, A, n_pools], phen [n_pools, k]."""
+    return _run(KIND_OLS, ctx, counts, filter_stats, phen, allele_codes)
+
+
+def correlation(ctx, counts, phen, filter_stats, allele_codes=_SYNC_CODES):
+    """gwas::correlation over a batch."""
+    return _run(KIND_CORR, ctx, counts, filter_stats, phen, allele_codes)
+
+
+def chisq(ctx, counts, filter_stats, allele_codes=_SYNC_CODES):
+    """tables::chisq over a batch."""
+    return _run(KIND_CHISQ, ctx, counts, filter_stats, None, allele_codes)
+
+
+def fisher(ctx, counts, filter_stats, allele_codes=_SYNC_CODES):
+    """tables::fisher over a batch."""
+    return _run(KIND_FISHER, ctx, counts, filter_stats, None, allele_codes)

@@ -1,0 +1,339 @@
+"""ctypes binding of libpoolgen_cuda.so (include/poolgen_cuda.h).
+
+This is the host-side mirror of the reference's per-locus callback interface
+(`ChunkyReadAnalyseWrite::read_analyse_write(&FilterStats, out, n_threads, function)`,
+src/base/structs_and_traits.rs:245-265) for the four analyses `ols_iterate`, `correlation`,
+`chisq`, `fisher`.  There is no CPU fallback: without the shared library or without a B200 every
+call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from .build import LIB_PATH
+
+PG_OK = 0
+KIND_OLS, KIND_CORR, KIND_CHISQ, KIND_FISHER = 0, 1, 2, 3
+LOCUS_FILTERED, LOCUS_OK, LOCUS_FAILED, LOCUS_UNSUPPORTED, LOCUS_PANIC = 0, 1, 2, 3, 4
+MAX_ALLELES = 6
+MAX_SLOTS = 5
+ALLELE_NAMES = "ATCGND"  # sync column order, src/base/sync.rs:134-137
+
+# every symbol include/poolgen_cuda.h declares (tests check the library exports each of them)
+ABI_SYMBOLS = [
+    "pg_abi_version", "pg_init", "pg_destroy", "pg_last_error", "pg_device_info", "pg_pinned_alloc",
+    "pg_pinned_free", "pg_scan_open", "pg_scan_close", "pg_batch_create", "pg_batch_destroy",
+    "pg_batch_upload_counts", "pg_batch_upload_counts_u16", "pg_batch_upload_freq", "pg_batch_synth",
+    "pg_batch_run", "pg_batch_download", "pg_batch_sync", "pg_batch_results", "pg_batch_time_runs",
+    "pg_batch_bytes", "pg_scan_stream_begin", "pg_scan_submit_counts", "pg_scan_submit_counts_u16",
+    "pg_scan_submit_freq", "pg_scan_collect", "pg_synth_counts_host", "pg_synth_phen_host",
+]
+
+
+class PgError(RuntimeError):
+    pass
+
+
+class _Filter(C.Structure):
+    _fields_ = [
+        ("remove_ns", C.c_int32),
+        ("min_coverage_depth", C.c_uint64),
+        ("min_allele_frequency", C.c_double),
+        ("max_missingness_rate", C.c_double),
+        ("n_pool_sizes", C.c_int32),
+        ("pool_sizes", C.POINTER(C.c_double)),
+    ]
+
+
+class _Results(C.Structure):
+    _fields_ = [
+        ("n_loci", C.c_int64),
+        ("n_slots", C.c_int32),
+        ("n_phen", C.c_int32),
+        ("meta", C.POINTER(C.c_uint64)),
+        ("freq_mean", C.POINTER(C.c_double)),
+        ("stats", C.POINTER(C.c_double)),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PgError(f"{LIB_PATH} is missing: run `python -m poolgen_b200.build` (nvcc, sm_100a); "
+                          "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+        pvp = C.POINTER(C.c_void_p)
+        sig = {
+            "pg_abi_version": (i, []),
+            "pg_init": (i, [i, pvp]),
+            "pg_destroy": (None, [vp]),
+            "pg_last_error": (C.c_char_p, [vp]),
+            "pg_device_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(C.c_size_t)]),
+            "pg_pinned_alloc": (i, [vp, C.c_size_t, pvp]),
+            "pg_pinned_free": (i, [vp, vp]),
+            "pg_scan_open": (i, [vp, i, C.POINTER(_Filter), i, i, C.POINTER(C.c_uint8), C.POINTER(C.c_double), i, pvp]),
+            "pg_scan_close": (i, [vp]),
+            "pg_batch_create": (i, [vp, i64, pvp]),
+            "pg_batch_destroy": (i, [vp]),
+            "pg_batch_upload_counts": (i, [vp, vp, i64]),
+            "pg_batch_upload_counts_u16": (i, [vp, vp, i64]),
+            "pg_batch_upload_freq": (i, [vp, vp, vp, i64]),
+            "pg_batch_synth": (i, [vp, u64, i64, i64]),
+            "pg_batch_run": (i, [vp]),
+            "pg_batch_download": (i, [vp]),
+            "pg_batch_sync": (i, [vp]),
+            "pg_batch_results": (i, [vp, C.POINTER(_Results)]),
+            "pg_batch_time_runs": (i, [vp, i, C.POINTER(C.c_float), C.POINTER(i)]),
+            "pg_batch_bytes": (i, [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+            "pg_scan_stream_begin": (i, [vp, i64]),
+            "pg_scan_submit_counts": (i, [vp, vp, i64, C.POINTER(i)]),
+            "pg_scan_submit_counts_u16": (i, [vp, vp, i64, C.POINTER(i)]),
+            "pg_scan_submit_freq": (i, [vp, vp, vp, i64, C.POINTER(i)]),
+            "pg_scan_collect": (i, [vp, i, C.POINTER(_Results)]),
+            "pg_synth_counts_host": (i, [u64, i64, i64, i, i, vp]),
+            "pg_synth_phen_host": (i, [u64, i, i, vp]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+@dataclass
+class FilterStats:
+    """FilterStats of the reference (src/base/structs_and_traits.rs:69-78), sync-path fields only.
+    pool_sizes as the phenotype loader hands them over (normalised to sum 1, src/base/phen.rs:82-84)."""
+    pool_sizes: np.ndarray
+    remove_ns: bool = True
+    min_coverage_depth: int = 1
+    min_allele_frequency: float = 0.001
+    max_missingness_rate: float = 0.0
+
+
+@dataclass
+class ScanResults:
+    """Numeric records of a batch (see pg_results in include/poolgen_cuda.h)."""
+    status: np.ndarray     # uint8 [L]
+    n_out: np.ndarray      # uint8 [L]
+    alleles: np.ndarray    # uint8 [L, 6] allele codes of the output rows (0xff = unused)
+    freq_mean: np.ndarray  # f64 [L, S]
+    stats: np.ndarray      # f64 [L, S, k, 4] = (statistic, se | raw r, t, p)
+
+    @staticmethod
+    def from_c(r: _Results) -> "ScanResults":
+        L, S, k = int(r.n_loci), int(r.n_slots), int(r.n_phen)
+        if L == 0:
+            return ScanResults(np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros((0, 6), np.uint8),
+                               np.zeros((0, S)), np.zeros((0, S, k, 4)))
+        meta = np.ctypeslib.as_array(r.meta, shape=(L,)).copy()
+        fm = np.ctypeslib.as_array(r.freq_mean, shape=(L, S)).copy()
+        st = np.ctypeslib.as_array(r.stats, shape=(L, S, k, 4)).copy()
+        status = (meta & 0xFF).astype(np.uint8)
+        n_out = ((meta >> 8) & 0xFF).astype(np.uint8)
+        alle = np.full((L, 6), 0xFF, dtype=np.uint8)
+        for s in range(6):
+            code = ((meta >> (16 + 8 * s)) & 0xFF).astype(np.uint8)
+            alle[:, s] = np.where(s < n_out, code, 0xFF)
+        return ScanResults(status, n_out, alle, fm, st)
+
+
+def _check(rc: int, ctx=None, what: str = ""):
+    if rc != PG_OK:
+        msg = lib().pg_last_error(ctx)
+        raise PgError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+class Context:
+    """One context per GPU (pg_init)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().pg_init(int(device), C.byref(self._h))
+        if rc != PG_OK:
+            raise PgError(f"pg_init({device}) failed ({rc}): {lib().pg_last_error(None).decode()}")
+        self.device = device
+
+    def info(self):
+        sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        _check(lib().pg_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)), self._h, "pg_device_info")
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+
+    def pinned_empty(self, shape, dtype):
+        """numpy array over a library-owned pinned host slab (freed with the returned handle's .free())."""
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dt.itemsize
+        p = C.c_void_p()
+        _check(lib().pg_pinned_alloc(self._h, nbytes, C.byref(p)), self._h, "pg_pinned_alloc")
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        return arr, p
+
+    def pinned_free(self, p):
+        _check(lib().pg_pinned_free(self._h, p), self._h, "pg_pinned_free")
+
+    def close(self):
+        if self._h:
+            lib().pg_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class Scan:
+    """A configured per-locus analysis = (callback kind, FilterStats, phenotypes)."""
+
+    def __init__(self, ctx: Context, kind: int, fs: FilterStats, n_pools: int, allele_codes, phen=None):
+        self.ctx = ctx
+        self.kind = kind
+        codes = np.ascontiguousarray(allele_codes, dtype=np.uint8)
+        ps = np.ascontiguousarray(fs.pool_sizes, dtype=np.float64)
+        self._keep = (codes, ps)
+        f = _Filter(int(fs.remove_ns), int(fs.min_coverage_depth), float(fs.min_allele_frequency),
+                    float(fs.max_missingness_rate), int(ps.size), ps.ctypes.data_as(C.POINTER(C.c_double)))
+        if phen is not None:
+            y = np.ascontiguousarray(phen, dtype=np.float64)
+            if y.ndim == 1:
+                y = y[:, None].copy()
+            k = y.shape[1]
+            yp = y.ctypes.data_as(C.POINTER(C.c_double))
+        else:
+            y, k, yp = None, 0, None
+        self.n_pools, self.n_alleles, self.k = int(n_pools), int(codes.size), k
+        self._h = C.c_void_p()
+        _check(lib().pg_scan_open(ctx._h, int(kind), C.byref(f), int(n_pools), int(codes.size),
+                                  codes.ctypes.data_as(C.POINTER(C.c_uint8)), yp, int(k), C.byref(self._h)),
+               ctx._h, "pg_scan_open")
+
+    def batch(self, capacity: int) -> "Batch":
+        return Batch(self, capacity)
+
+    def run_counts(self, counts) -> ScanResults:
+        """counts: uint32 (or uint16) [L, A, n_pools] -> records, synchronously."""
+        c = np.ascontiguousarray(counts)
+        b = self.batch(max(1, c.shape[0]))
+        try:
+            b.upload_counts(c)
+            b.run()
+            return b.fetch()
+        finally:
+            b.close()
+
+    # streaming: pg_scan_stream_begin / submit / collect
+    def stream_begin(self, max_loci: int):
+        _check(lib().pg_scan_stream_begin(self._h, int(max_loci)), self.ctx._h, "pg_scan_stream_begin")
+
+    def submit_counts(self, counts) -> int:
+        t = C.c_int()
+        c = counts
+        assert c.flags["C_CONTIGUOUS"]
+        fn = lib().pg_scan_submit_counts if c.dtype == np.uint32 else lib().pg_scan_submit_counts_u16
+        assert c.dtype in (np.uint32, np.uint16)
+        _check(fn(self._h, c.ctypes.data, int(c.shape[0]), C.byref(t)), self.ctx._h, "pg_scan_submit_counts")
+        return t.value
+
+    def submit_freq(self, freq, depth) -> int:
+        t = C.c_int()
+        assert freq.dtype == np.float64 and depth.dtype == np.uint32
+        assert freq.flags["C_CONTIGUOUS"] and depth.flags["C_CONTIGUOUS"]
+        _check(lib().pg_scan_submit_freq(self._h, freq.ctypes.data, depth.ctypes.data, int(freq.shape[0]), C.byref(t)),
+               self.ctx._h, "pg_scan_submit_freq")
+        return t.value
+
+    def collect(self, ticket: int, copy: bool = True):
+        r = _Results()
+        _check(lib().pg_scan_collect(self._h, int(ticket), C.byref(r)), self.ctx._h, "pg_scan_collect")
+        return ScanResults.from_c(r) if copy else r
+
+    def close(self):
+        if self._h:
+            lib().pg_scan_close(self._h)
+            self._h = C.c_void_p()
+
+
+class Batch:
+    def __init__(self, scan: Scan, capacity: int):
+        self.scan = scan
+        self._h = C.c_void_p()
+        self._keep = None
+        _check(lib().pg_batch_create(scan._h, int(capacity), C.byref(self._h)), scan.ctx._h, "pg_batch_create")
+
+    def _ck(self, rc, what):
+        _check(rc, self.scan.ctx._h, what)
+
+    def upload_counts(self, counts):
+        c = np.ascontiguousarray(counts)
+        if c.dtype not in (np.uint32, np.uint16):
+            c = c.astype(np.uint32)
+        assert c.ndim == 3 and c.shape[1] == self.scan.n_alleles and c.shape[2] == self.scan.n_pools, c.shape
+        self._keep = c
+        fn = lib().pg_batch_upload_counts if c.dtype == np.uint32 else lib().pg_batch_upload_counts_u16
+        self._ck(fn(self._h, c.ctypes.data, int(c.shape[0])), "pg_batch_upload_counts")
+
+    def upload_freq(self, freq, depth):
+        f = np.ascontiguousarray(freq, dtype=np.float64)
+        d = np.ascontiguousarray(depth, dtype=np.uint32)
+        self._keep = (f, d)
+        self._ck(lib().pg_batch_upload_freq(self._h, f.ctypes.data, d.ctypes.data, int(f.shape[0])), "pg_batch_upload_freq")
+
+    def synth(self, seed: int, first_locus: int, n_loci: int):
+        self._ck(lib().pg_batch_synth(self._h, int(seed), int(first_locus), int(n_loci)), "pg_batch_synth")
+
+    def run(self):
+        self._ck(lib().pg_batch_run(self._h), "pg_batch_run")
+
+    def sync(self):
+        self._ck(lib().pg_batch_sync(self._h), "pg_batch_sync")
+
+    def time_runs(self, iters: int):
+        ms, nl = C.c_float(), C.c_int()
+        self._ck(lib().pg_batch_time_runs(self._h, int(iters), C.byref(ms), C.byref(nl)), "pg_batch_time_runs")
+        return float(ms.value), int(nl.value)
+
+    def bytes(self):
+        a, b = C.c_size_t(), C.c_size_t()
+        self._ck(lib().pg_batch_bytes(self._h, C.byref(a), C.byref(b)), "pg_batch_bytes")
+        return int(a.value), int(b.value)
+
+    def download(self):
+        self._ck(lib().pg_batch_download(self._h), "pg_batch_download")
+
+    def results_view(self) -> _Results:
+        r = _Results()
+        self._ck(lib().pg_batch_results(self._h, C.byref(r)), "pg_batch_results")
+        return r
+
+    def fetch(self) -> ScanResults:
+        self.download()
+        self.sync()
+        return ScanResults.from_c(self.results_view())
+
+    def close(self):
+        if self._h:
+            lib().pg_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def synth_counts_host(seed: int, first_locus: int, n_loci: int, n_pools: int, n_alleles: int) -> np.ndarray:
+    out = np.empty((n_loci, n_alleles, n_pools), dtype=np.uint32)
+    rc = lib().pg_synth_counts_host(int(seed), int(first_locus), int(n_loci), int(n_pools), int(n_alleles), out.ctypes.data)
+    if rc != PG_OK:
+        raise PgError(f"pg_synth_counts_host failed ({rc})")
+    return out
+
+
+def synth_phen_host(seed: int, n_pools: int, k: int) -> np.ndarray:
+    out = np.empty((n_pools, k), dtype=np.float64)
+    rc = lib().pg_synth_phen_host(int(seed), int(n_pools), int(k), out.ctypes.data)
+    if rc != PG_OK:
+        raise PgError(f"pg_synth_phen_host failed ({rc})")
+    return out

@@ -1,0 +1,624 @@
+// pg_api.cu -- the C ABI of include/poolgen_cuda.h: context, scan configuration, batches, streaming.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "pg_internal.h"
+
+namespace pg {
+cudaError_t launch_scan_a2(const ScanParams &, int, cudaStream_t);
+cudaError_t launch_scan_a3(const ScanParams &, int, cudaStream_t);
+cudaError_t launch_scan_a4(const ScanParams &, int, cudaStream_t);
+cudaError_t launch_scan_a5(const ScanParams &, int, cudaStream_t);
+cudaError_t launch_scan_a6(const ScanParams &, int, cudaStream_t);
+
+cudaError_t launch_scan(const ScanParams &p, int sm_count, cudaStream_t s) {
+    switch (p.lay.A) {
+        case 2: return launch_scan_a2(p, sm_count, s);
+        case 3: return launch_scan_a3(p, sm_count, s);
+        case 4: return launch_scan_a4(p, sm_count, s);
+        case 5: return launch_scan_a5(p, sm_count, s);
+        case 6: return launch_scan_a6(p, sm_count, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+}  // namespace pg
+
+static thread_local std::string g_init_err;
+
+static int fail(pg_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_init_err = buf;
+    return code;
+}
+
+#define PG_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail((ctx), PG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                        \
+    } while (0)
+
+extern "C" {
+
+int pg_abi_version(void) { return PG_ABI_VERSION; }
+
+int pg_init(int device, pg_ctx **out) {
+    if (!out) return fail(nullptr, PG_ERR_ARG, "pg_init: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, PG_ERR_CUDA, "pg_init: no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, PG_ERR_ARG, "pg_init: device %d of %d", device, ndev);
+    cudaDeviceProp prop;
+    PG_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, PG_ERR_CUDA, "pg_init: device %d is sm_%d%d; the kernels are built for sm_100a only",
+                    device, prop.major, prop.minor);
+    PG_CUDA(nullptr, cudaSetDevice(device));
+    pg_ctx *c = new (std::nothrow) pg_ctx();
+    if (!c) return fail(nullptr, PG_ERR_ARG, "pg_init: out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->total_mem = prop.totalGlobalMem;
+    *out = c;
+    return PG_OK;
+}
+
+void pg_destroy(pg_ctx *ctx) { delete ctx; }
+
+const char *pg_last_error(const pg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
+
+int pg_device_info(pg_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
+    if (!ctx) return PG_ERR_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (total_mem) *total_mem = ctx->total_mem;
+    return PG_OK;
+}
+
+int pg_pinned_alloc(pg_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return PG_ERR_ARG;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    PG_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return PG_OK;
+}
+
+int pg_pinned_free(pg_ctx *ctx, void *p) {
+    if (!ctx) return PG_ERR_ARG;
+    if (p) PG_CUDA(ctx, cudaFreeHost(p));
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, int n_alleles,
+                 const uint8_t *allele_codes, const double *phen, int k, pg_scan **out) {
+    if (!ctx || !out || !filter || !allele_codes) return fail(ctx, PG_ERR_ARG, "pg_scan_open: NULL argument");
+    *out = nullptr;
+    if (kind < PG_KIND_OLS || kind > PG_KIND_FISHER) return fail(ctx, PG_ERR_ARG, "pg_scan_open: kind %d", kind);
+    if (n_pools < 1) return fail(ctx, PG_ERR_ARG, "pg_scan_open: n_pools %d", n_pools);
+    if (n_alleles < 1 || n_alleles > PG_MAX_ALLELES)
+        return fail(ctx, PG_ERR_ARG, "pg_scan_open: n_alleles %d not in 1..6", n_alleles);
+    for (int j = 0; j < n_alleles; j++) {
+        if (allele_codes[j] > 5) return fail(ctx, PG_ERR_ARG, "pg_scan_open: allele code %d", allele_codes[j]);
+        if (j && allele_codes[j] <= allele_codes[j - 1])
+            return fail(ctx, PG_ERR_ARG, "pg_scan_open: allele codes must be strictly increasing (sync column order)");
+    }
+    // assert!(n == filter_stats.pool_sizes.len()) src/base/sync.rs:254-257
+    if (filter->n_pool_sizes != n_pools || !filter->pool_sizes)
+        return fail(ctx, PG_ERR_ARG, "pg_scan_open: %d pool sizes for %d pools (the reference asserts equality)",
+                    filter->n_pool_sizes, n_pools);
+    const bool regression = (kind == PG_KIND_OLS || kind == PG_KIND_CORR);
+    if (regression && (!phen || k < 1)) return fail(ctx, PG_ERR_ARG, "pg_scan_open: phenotypes required");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    pg_scan *s = new (std::nothrow) pg_scan();
+    if (!s) return fail(ctx, PG_ERR_ARG, "out of host memory");
+    s->ctx = ctx;
+    s->kind = kind;
+    s->n = n_pools;
+    s->A_in = n_alleles;
+    s->k = regression ? k : 1;
+    s->remove_ns = filter->remove_ns != 0;
+    s->min_depth = filter->min_coverage_depth;
+    s->maf = filter->min_allele_frequency;
+    s->max_miss = filter->max_missingness_rate;
+    s->drop_col = -1;
+    int jj = 0;
+    for (int j = 0; j < n_alleles; j++) {
+        s->codes_in[j] = allele_codes[j];
+        if (s->remove_ns && allele_codes[j] == 4) {
+            s->drop_col = j;  // src/base/sync.rs:200-213
+            continue;
+        }
+        s->codes_dev[jj++] = allele_codes[j];
+    }
+    s->A_dev = jj;
+    if (regression && (s->A_dev < 2 || s->A_dev > 6)) {
+        delete s;
+        return fail(ctx, PG_ERR_ARG, "pg_scan_open: %d usable allele columns, need 2..6", jj);
+    }
+    s->lay = pg::make_layout(n_pools, s->A_dev);
+    s->n_slots = regression ? s->A_dev - 1 : 1;
+    // pool weights exactly as src/base/sync.rs:262-270: s_i / (sequential sum of s)
+    double S = 0.0;
+    for (int i = 0; i < n_pools; i++) S = S + filter->pool_sizes[i];
+    s->w_host.assign(s->lay.n_pad, 0.0);
+    for (int i = 0; i < n_pools; i++) s->w_host[i] = filter->pool_sizes[i] / S;
+    s->weighted = 0;
+    for (int i = 1; i < n_pools; i++)
+        if (s->w_host[i] != s->w_host[0]) s->weighted = 1;
+    s->w_uniform = s->w_host[0];
+
+    if (regression) {
+        const int n = n_pools, np = s->lay.n_pad;
+        s->yc_host.assign((size_t)k * np, 0.0);
+        s->ysum.assign(k, 0.0);
+        s->syy.assign(k, 0.0);
+        for (int j = 0; j < k; j++) {
+            double sum = 0.0;
+            for (int i = 0; i < n; i++) {
+                const double v = phen[(size_t)i * k + j];
+                if (v != v) s->y_has_nan = 1;
+                sum += v;
+            }
+            const double mean = sum / n;
+            double s1 = 0.0, s2 = 0.0;
+            for (int i = 0; i < n; i++) {
+                const double c = phen[(size_t)i * k + j] - mean;
+                s->yc_host[(size_t)j * np + i] = c;
+                s1 += c;
+                s2 += c * c;
+            }
+            s->ysum[j] = s1;
+            s->syy[j] = s2 - s1 * s1 / n;
+        }
+        if (s->y_has_nan) {
+            // ols_iterate: remove_missing() shrinks the pools but not FilterStats.pool_sizes, so the reference
+            // panics at src/base/sync.rs:254-257; correlation drops NaN pairs per phenotype (not implemented).
+            delete s;
+            return fail(ctx, PG_ERR_UNSUPPORTED,
+                        "pg_scan_open: missing phenotype values (the reference's ols_iter panics on them; "
+                        "pearson_corr pairwise deletion is not implemented on the device)");
+        }
+        s->df = (kind == PG_KIND_OLS) ? (double)n - 1.0 : (double)n - 2.0;
+        if (kind == PG_KIND_OLS && !(s->df > 0.0)) {
+            delete s;  // StudentsT::new(0,1,0).unwrap() panics (src/gwas/ols.rs:139)
+            return fail(ctx, PG_ERR_UNSUPPORTED, "pg_scan_open: ols_iter needs at least 2 pools");
+        }
+        s->ln_beta = s->df > 0.0 ? lgamma(s->df / 2.0 + 0.5) - lgamma(s->df / 2.0) - lgamma(0.5) : 0.0;
+        size_t smem_common = ((size_t)(std::min(k, pg::kMaxPhenPerPass) + 1) * np * 8);
+        if (smem_common > 160 * 1024) {
+            delete s;
+            return fail(ctx, PG_ERR_UNSUPPORTED, "pg_scan_open: %d pools exceed the shared-memory resident phenotype budget", n);
+        }
+        cudaError_t e = cudaMalloc(&s->d_yc, s->yc_host.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(s->d_yc, s->yc_host.data(), s->yc_host.size() * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            delete s;
+            return fail(ctx, PG_ERR_CUDA, "pg_scan_open: phenotype upload: %s", cudaGetErrorString(e));
+        }
+    }
+    {
+        cudaError_t e = cudaMalloc(&s->d_w, s->w_host.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(s->d_w, s->w_host.data(), s->w_host.size() * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            if (s->d_yc) cudaFree(s->d_yc);
+            delete s;
+            return fail(ctx, PG_ERR_CUDA, "pg_scan_open: weight upload: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = s;
+    return PG_OK;
+}
+
+int pg_scan_close(pg_scan *s) {
+    if (!s) return PG_OK;
+    for (int i = 0; i < PG_STREAM_DEPTH; i++)
+        if (s->slabs[i]) pg_batch_destroy(s->slabs[i]);
+    if (s->d_yc) cudaFree(s->d_yc);
+    if (s->d_w) cudaFree(s->d_w);
+    delete s;
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static bool is_regression(const pg_scan *s) { return s->kind == PG_KIND_OLS || s->kind == PG_KIND_CORR; }
+
+int pg_batch_create(pg_scan *s, int64_t cap, pg_batch **out) {
+    if (!s || !out || cap < 1) return fail(s ? s->ctx : nullptr, PG_ERR_ARG, "pg_batch_create: bad argument");
+    pg_ctx *ctx = s->ctx;
+    *out = nullptr;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    pg_batch *b = new (std::nothrow) pg_batch();
+    if (!b) return fail(ctx, PG_ERR_ARG, "out of host memory");
+    b->scan = s;
+    b->cap = cap;
+    cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    if (e == cudaSuccess && is_regression(s)) {
+        e = cudaMalloc(&b->d_freq, (size_t)cap * s->lay.freq_stride() * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_depth, (size_t)cap * s->lay.depth_stride() * 4);
+    }
+    const size_t S = s->n_slots, K = s->k;
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_meta, (size_t)cap * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_fmean, (size_t)cap * S * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_stats, (size_t)cap * S * K * 32);
+    if (e != cudaSuccess) {
+        pg_batch_destroy(b);
+        return fail(ctx, PG_ERR_CUDA, "pg_batch_create(%lld loci): %s", (long long)cap, cudaGetErrorString(e));
+    }
+    *out = b;
+    return PG_OK;
+}
+
+int pg_batch_destroy(pg_batch *b) {
+    if (!b) return PG_OK;
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_freq);
+    cudaFree(b->d_depth);
+    cudaFree(b->d_stage);
+    cudaFree(b->d_meta);
+    cudaFree(b->d_fmean);
+    cudaFree(b->d_stats);
+    if (b->h_meta) cudaFreeHost(b->h_meta);
+    if (b->h_fmean) cudaFreeHost(b->h_fmean);
+    if (b->h_stats) cudaFreeHost(b->h_stats);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    return PG_OK;
+}
+
+static int ensure_stage(pg_batch *b, size_t bytes) {
+    pg_ctx *ctx = b->scan->ctx;
+    if (b->stage_bytes >= bytes) return PG_OK;
+    if (b->d_stage) {
+        PG_CUDA(ctx, cudaStreamSynchronize(b->stream));
+        PG_CUDA(ctx, cudaFree(b->d_stage));
+        b->d_stage = nullptr;
+        b->stage_bytes = 0;
+    }
+    PG_CUDA(ctx, cudaMalloc(&b->d_stage, bytes));
+    b->stage_bytes = bytes;
+    return PG_OK;
+}
+
+}  // extern "C"
+
+template <typename CT>
+static int upload_counts_t(pg_batch *b, const CT *counts, int64_t n_loci) {
+    if (!b || (!counts && n_loci > 0)) return PG_ERR_ARG;
+    pg_scan *s = b->scan;
+    pg_ctx *ctx = s->ctx;
+    if (n_loci < 0 || n_loci > b->cap) return fail(ctx, PG_ERR_ARG, "upload: %lld loci > capacity %lld", (long long)n_loci, (long long)b->cap);
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    b->n_loci = n_loci;
+    b->have_input = 1;
+    if (n_loci == 0) return PG_OK;
+    const size_t bytes = (size_t)n_loci * s->A_in * s->n * sizeof(CT);
+    const bool reg = is_regression(s);
+    int rc = ensure_stage(b, (size_t)b->cap * s->A_in * s->n * sizeof(CT));
+    if (rc) return rc;
+    if (reg) {
+        PG_CUDA(ctx, cudaMemcpyAsync(b->d_stage, counts, bytes, cudaMemcpyHostToDevice, b->stream));
+        if (sizeof(CT) == 4)
+            PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
+                                               b->d_freq, b->d_depth, b->stream));
+        else
+            PG_CUDA(ctx, pg::launch_ingest_u16((const uint16_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
+                                               b->d_freq, b->d_depth, b->stream));
+    } else {
+        if (sizeof(CT) == 2) return fail(ctx, PG_ERR_UNSUPPORTED, "16-bit counts are not wired for the table tests yet");
+        PG_CUDA(ctx, cudaMemcpyAsync(b->d_stage, counts, bytes, cudaMemcpyHostToDevice, b->stream));
+    }
+    b->input_is_counts = 1;
+    return PG_OK;
+}
+
+extern "C" {
+
+int pg_batch_upload_counts(pg_batch *b, const uint32_t *counts, int64_t n_loci) {
+    return upload_counts_t<uint32_t>(b, counts, n_loci);
+}
+int pg_batch_upload_counts_u16(pg_batch *b, const uint16_t *counts, int64_t n_loci) {
+    return upload_counts_t<uint16_t>(b, counts, n_loci);
+}
+
+int pg_batch_upload_freq(pg_batch *b, const double *freq, const uint32_t *depth, int64_t n_loci) {
+    if (!b || ((!freq || !depth) && n_loci > 0)) return PG_ERR_ARG;
+    pg_scan *s = b->scan;
+    pg_ctx *ctx = s->ctx;
+    if (!is_regression(s)) return fail(ctx, PG_ERR_UNSUPPORTED, "upload_freq: the table tests need counts");
+    if (s->drop_col >= 0)
+        return fail(ctx, PG_ERR_ARG, "upload_freq: the frequency matrix must not contain the N column when remove_ns is set");
+    if (n_loci < 0 || n_loci > b->cap) return fail(ctx, PG_ERR_ARG, "upload: %lld loci > capacity %lld", (long long)n_loci, (long long)b->cap);
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    b->n_loci = n_loci;
+    b->have_input = 1;
+    if (n_loci == 0) return PG_OK;
+    const size_t fbytes_cap = (size_t)b->cap * s->A_dev * s->n * 8, dbytes_cap = (size_t)b->cap * s->n * 4;
+    int rc = ensure_stage(b, fbytes_cap + dbytes_cap);
+    if (rc) return rc;
+    double *sf = (double *)b->d_stage;
+    uint32_t *sd = (uint32_t *)((char *)b->d_stage + fbytes_cap);
+    PG_CUDA(ctx, cudaMemcpyAsync(sf, freq, (size_t)n_loci * s->A_dev * s->n * 8, cudaMemcpyHostToDevice, b->stream));
+    PG_CUDA(ctx, cudaMemcpyAsync(sd, depth, (size_t)n_loci * s->n * 4, cudaMemcpyHostToDevice, b->stream));
+    PG_CUDA(ctx, pg::launch_ingest_freq(sf, sd, n_loci, s->n, s->lay, b->d_freq, b->d_depth, b->stream));
+    b->input_is_counts = 0;
+    return PG_OK;
+}
+
+int pg_batch_synth(pg_batch *b, uint64_t seed, int64_t first_locus, int64_t n_loci) {
+    if (!b) return PG_ERR_ARG;
+    pg_scan *s = b->scan;
+    pg_ctx *ctx = s->ctx;
+    if (n_loci < 0 || n_loci > b->cap) return fail(ctx, PG_ERR_ARG, "synth: %lld loci > capacity %lld", (long long)n_loci, (long long)b->cap);
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    b->n_loci = n_loci;
+    b->have_input = 1;
+    if (n_loci == 0) return PG_OK;
+    const size_t per_locus = (size_t)s->A_in * s->n * 4;
+    if (!is_regression(s)) {
+        int rc = ensure_stage(b, (size_t)b->cap * per_locus);
+        if (rc) return rc;
+        PG_CUDA(ctx, pg::launch_synth(seed, first_locus, n_loci, s->n, s->A_in, (uint32_t *)b->d_stage, b->stream));
+        b->input_is_counts = 1;
+        return PG_OK;
+    }
+    // generate in slices so that the staging buffer stays small next to the resident frequency matrix
+    int64_t slice = (int64_t)((size_t)256 << 20) / (int64_t)per_locus;
+    if (slice < 1) slice = 1;
+    if (slice > n_loci) slice = n_loci;
+    if (b->stage_bytes < (size_t)slice * per_locus) {
+        int rc = ensure_stage(b, (size_t)slice * per_locus);
+        if (rc) return rc;
+    } else {
+        slice = (int64_t)(b->stage_bytes / per_locus);
+        if (slice > n_loci) slice = n_loci;
+    }
+    for (int64_t l0 = 0; l0 < n_loci; l0 += slice) {
+        const int64_t m = (n_loci - l0 < slice) ? n_loci - l0 : slice;
+        PG_CUDA(ctx, pg::launch_synth(seed, first_locus + l0, m, s->n, s->A_in, (uint32_t *)b->d_stage, b->stream));
+        PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, m, s->n, s->A_in, s->drop_col, s->lay,
+                                           b->d_freq + (size_t)l0 * s->lay.freq_stride(),
+                                           b->d_depth + (size_t)l0 * s->lay.depth_stride(), b->stream));
+    }
+    b->input_is_counts = 1;
+    return PG_OK;
+}
+
+static int run_once(pg_batch *b, int *launches) {
+    pg_scan *s = b->scan;
+    pg_ctx *ctx = s->ctx;
+    if (!b->have_input) return fail(ctx, PG_ERR_STATE, "pg_batch_run: no input uploaded");
+    if (b->n_loci == 0) return PG_OK;
+    if (is_regression(s)) {
+        for (int base = 0; base < s->k; base += pg::kMaxPhenPerPass) {
+            pg::ScanParams p;
+            memset(&p, 0, sizeof p);
+            p.lay = s->lay;
+            p.freq = b->d_freq;
+            p.depth = b->d_depth;
+            p.n_loci = b->n_loci;
+            p.kind = s->kind;
+            p.weighted = s->weighted;
+            p.maf = s->maf;
+            p.one_minus_maf = 1.00 - s->maf;
+            p.max_miss = s->max_miss;
+            p.min_depth_f = (double)s->min_depth;
+            p.w_uniform = s->w_uniform;
+            p.df = s->df;
+            p.ln_beta = s->ln_beta;
+            p.K = std::min(pg::kMaxPhenPerPass, s->k - base);
+            p.yc = s->d_yc + (size_t)base * s->lay.n_pad;
+            p.w = s->d_w;
+            for (int j = 0; j < p.K; j++) {
+                p.ysum[j] = s->ysum[base + j];
+                p.syy[j] = s->syy[base + j];
+            }
+            for (int j = 0; j < s->A_dev; j++) p.codes[j] = s->codes_dev[j];
+            p.meta = b->d_meta;
+            p.freq_mean = b->d_fmean;
+            p.stats = b->d_stats;
+            p.k_total = s->k;
+            p.phen_base = base;
+            p.write_meta = base == 0;
+            PG_CUDA(ctx, pg::launch_scan(p, ctx->sm_count, b->stream));
+            if (launches) (*launches)++;
+        }
+    } else {
+        pg::TableParams p;
+        memset(&p, 0, sizeof p);
+        p.counts = (const uint32_t *)b->d_stage;
+        p.n_loci = b->n_loci;
+        p.n = s->n;
+        p.A_in = s->A_in;
+        p.kind = s->kind;
+        p.drop_col = s->drop_col;
+        p.maf = s->maf;
+        p.one_minus_maf = 1.00 - s->maf;
+        p.max_miss = s->max_miss;
+        p.min_depth_f = (double)s->min_depth;
+        p.w = s->d_w;
+        for (int j = 0; j < s->A_in; j++) p.codes[j] = s->codes_in[j];
+        p.meta = b->d_meta;
+        p.stats = b->d_stats;
+        PG_CUDA(ctx, pg::launch_tables(p, ctx->sm_count, b->stream));
+        if (launches) (*launches)++;
+    }
+    return PG_OK;
+}
+
+int pg_batch_run(pg_batch *b) {
+    if (!b) return PG_ERR_ARG;
+    PG_CUDA(b->scan->ctx, cudaSetDevice(b->scan->ctx->device));
+    return run_once(b, nullptr);
+}
+
+int pg_batch_time_runs(pg_batch *b, int iters, float *ms_total, int *n_launches) {
+    if (!b || iters < 1 || !ms_total) return PG_ERR_ARG;
+    pg_ctx *ctx = b->scan->ctx;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    int launches = 0;
+    PG_CUDA(ctx, cudaStreamSynchronize(b->stream));
+    PG_CUDA(ctx, cudaEventRecord(b->ev0, b->stream));
+    for (int i = 0; i < iters; i++) {
+        int rc = run_once(b, &launches);
+        if (rc) return rc;
+    }
+    PG_CUDA(ctx, cudaEventRecord(b->ev1, b->stream));
+    PG_CUDA(ctx, cudaEventSynchronize(b->ev1));
+    PG_CUDA(ctx, cudaEventElapsedTime(ms_total, b->ev0, b->ev1));
+    if (n_launches) *n_launches = launches;
+    return PG_OK;
+}
+
+int pg_batch_bytes(pg_batch *b, size_t *input_bytes, size_t *result_bytes) {
+    if (!b) return PG_ERR_ARG;
+    pg_scan *s = b->scan;
+    const size_t L = (size_t)b->n_loci;
+    if (input_bytes)
+        *input_bytes = is_regression(s) ? L * (s->lay.freq_stride() * 8 + s->lay.depth_stride() * 4)
+                                        : L * (size_t)s->A_in * s->n * 4;
+    if (result_bytes) *result_bytes = L * (8 + (size_t)s->n_slots * 8 + (size_t)s->n_slots * s->k * 32);
+    return PG_OK;
+}
+
+int pg_batch_download(pg_batch *b) {
+    if (!b) return PG_ERR_ARG;
+    pg_scan *s = b->scan;
+    pg_ctx *ctx = s->ctx;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t S = s->n_slots, K = s->k;
+    if (!b->h_meta) {
+        PG_CUDA(ctx, cudaHostAlloc((void **)&b->h_meta, (size_t)b->cap * 8, cudaHostAllocDefault));
+        PG_CUDA(ctx, cudaHostAlloc((void **)&b->h_fmean, (size_t)b->cap * S * 8, cudaHostAllocDefault));
+        PG_CUDA(ctx, cudaHostAlloc((void **)&b->h_stats, (size_t)b->cap * S * K * 32, cudaHostAllocDefault));
+    }
+    const size_t L = (size_t)b->n_loci;
+    if (L == 0) return PG_OK;
+    PG_CUDA(ctx, cudaMemcpyAsync(b->h_meta, b->d_meta, L * 8, cudaMemcpyDeviceToHost, b->stream));
+    PG_CUDA(ctx, cudaMemcpyAsync(b->h_fmean, b->d_fmean, L * S * 8, cudaMemcpyDeviceToHost, b->stream));
+    PG_CUDA(ctx, cudaMemcpyAsync(b->h_stats, b->d_stats, L * S * K * 32, cudaMemcpyDeviceToHost, b->stream));
+    return PG_OK;
+}
+
+int pg_batch_sync(pg_batch *b) {
+    if (!b) return PG_ERR_ARG;
+    PG_CUDA(b->scan->ctx, cudaStreamSynchronize(b->stream));
+    return PG_OK;
+}
+
+int pg_batch_results(pg_batch *b, pg_results *out) {
+    if (!b || !out) return PG_ERR_ARG;
+    if (!b->h_meta && b->n_loci > 0) return fail(b->scan->ctx, PG_ERR_STATE, "pg_batch_results before pg_batch_download");
+    out->n_loci = b->n_loci;
+    out->n_slots = b->scan->n_slots;
+    out->n_phen = b->scan->k;
+    out->meta = b->h_meta;
+    out->freq_mean = b->h_fmean;
+    out->stats = b->h_stats;
+    return PG_OK;
+}
+
+// ---- streaming ------------------------------------------------------------------------------
+int pg_scan_stream_begin(pg_scan *s, int64_t max_loci) {
+    if (!s || max_loci < 1) return PG_ERR_ARG;
+    for (int i = 0; i < PG_STREAM_DEPTH; i++) {
+        if (s->slabs[i]) {
+            pg_batch_destroy(s->slabs[i]);
+            s->slabs[i] = nullptr;
+        }
+        int rc = pg_batch_create(s, max_loci, &s->slabs[i]);
+        if (rc) return rc;
+    }
+    s->slab_cap = max_loci;
+    s->next_slab = 0;
+    return PG_OK;
+}
+
+static int submit_common(pg_scan *s, int *ticket, pg_batch **b) {
+    if (!s || !ticket) return PG_ERR_ARG;
+    if (!s->slabs[0]) return fail(s->ctx, PG_ERR_STATE, "pg_scan_submit before pg_scan_stream_begin");
+    *ticket = s->next_slab;
+    *b = s->slabs[s->next_slab];
+    s->next_slab = (s->next_slab + 1) % PG_STREAM_DEPTH;
+    return pg_batch_sync(*b);  // the slab's previous results must have been collected by now
+}
+
+int pg_scan_submit_counts(pg_scan *s, const uint32_t *counts, int64_t n_loci, int *ticket) {
+    pg_batch *b = nullptr;
+    int rc = submit_common(s, ticket, &b);
+    if (rc) return rc;
+    if ((rc = pg_batch_upload_counts(b, counts, n_loci))) return rc;
+    if ((rc = pg_batch_run(b))) return rc;
+    return pg_batch_download(b);
+}
+int pg_scan_submit_counts_u16(pg_scan *s, const uint16_t *counts, int64_t n_loci, int *ticket) {
+    pg_batch *b = nullptr;
+    int rc = submit_common(s, ticket, &b);
+    if (rc) return rc;
+    if ((rc = pg_batch_upload_counts_u16(b, counts, n_loci))) return rc;
+    if ((rc = pg_batch_run(b))) return rc;
+    return pg_batch_download(b);
+}
+int pg_scan_submit_freq(pg_scan *s, const double *freq, const uint32_t *depth, int64_t n_loci, int *ticket) {
+    pg_batch *b = nullptr;
+    int rc = submit_common(s, ticket, &b);
+    if (rc) return rc;
+    if ((rc = pg_batch_upload_freq(b, freq, depth, n_loci))) return rc;
+    if ((rc = pg_batch_run(b))) return rc;
+    return pg_batch_download(b);
+}
+int pg_scan_collect(pg_scan *s, int ticket, pg_results *out) {
+    if (!s || ticket < 0 || ticket >= PG_STREAM_DEPTH || !s->slabs[ticket]) return PG_ERR_ARG;
+    int rc = pg_batch_sync(s->slabs[ticket]);
+    if (rc) return rc;
+    return pg_batch_results(s->slabs[ticket], out);
+}
+
+// ---- synthetic workload, host replay -----------------------------------------------------------
+int pg_synth_counts_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int n_pools, int n_alleles,
+                         uint32_t *out) {
+    if (!out || n_pools < 1 || n_alleles < 1 || n_alleles > PG_MAX_ALLELES || n_loci < 0) return PG_ERR_ARG;
+    for (int64_t l = 0; l < n_loci; l++)
+        for (int i = 0; i < n_pools; i++) {
+            uint32_t c[PG_MAX_ALLELES];
+            pg::synth_counts(seed, first_locus + l, i, n_alleles, c);
+            for (int a = 0; a < n_alleles; a++) out[((size_t)l * n_alleles + a) * n_pools + i] = c[a];
+        }
+    return PG_OK;
+}
+
+int pg_synth_phen_host(uint64_t seed, int n_pools, int k, double *out) {
+    if (!out || n_pools < 1 || k < 1) return PG_ERR_ARG;
+    for (int i = 0; i < n_pools; i++)
+        for (int j = 0; j < k; j++) {
+            const uint64_t h = pg::splitmix64(seed ^ 0x9E11E5ull ^ ((uint64_t)(i + 1) << 24) ^ (uint64_t)j);
+            // 53 uniform bits -> [-3, 3)
+            out[(size_t)i * k + j] = ((double)(h >> 11) * (1.0 / 9007199254740992.0)) * 6.0 - 3.0;
+        }
+    return PG_OK;
+}
+
+}  // extern "C"

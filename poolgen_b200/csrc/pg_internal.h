@@ -1,0 +1,225 @@
+// pg_internal.h -- shared declarations of libpoolgen_cuda (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "poolgen_cuda.h"
+
+namespace pg {
+
+// ---- device data layout of one batch --------------------------------------------------------
+// Per locus the first-stage frequency matrix (n_pools x A, reference LocusFrequencies.matrix of
+// src/base/sync.rs:166-192 before the MAF filter) is stored allele-major ("column-major n x A"),
+// split into row chunks of RC pools so that a chunk [A][rc] is one contiguous block a single
+// cp.async.bulk can fetch:
+//   freq  : [locus][chunk][A][rc_chunk] f64     locus stride = A * n_pad doubles
+//   depth : [locus][chunk][rc_chunk]    u32     locus stride = n_pad
+// n_pad = n rounded up to a multiple of 4 (16-byte granules for bulk copies); padding rows hold
+// freq = 0, depth = 0xFFFFFFFF.  When n_pad <= kChunkRows there is one chunk and consecutive loci
+// are contiguous, so several loci travel in one bulk copy.
+constexpr int kChunkRows = 128;
+
+struct Layout {
+    int n;         // pools
+    int n_pad;     // rounded up to 4
+    int A;         // allele columns on the device (N already dropped when remove_ns)
+    int rc;        // rows of a full chunk
+    int n_chunks;  // chunks per locus
+    int rc_last;   // rows of the last chunk (multiple of 4)
+    __host__ __device__ size_t freq_stride() const { return (size_t)A * n_pad; }
+    __host__ __device__ size_t depth_stride() const { return (size_t)n_pad; }
+    // element offset of (row i, allele j) inside one locus
+    __host__ __device__ size_t freq_off(int i, int j) const {
+        int c = i / rc, r = i - c * rc;
+        int rcc = (c == n_chunks - 1) ? rc_last : rc;
+        return (size_t)c * A * rc + (size_t)j * rcc + r;
+    }
+};
+
+inline Layout make_layout(int n, int A) {
+    Layout l;
+    l.n = n;
+    l.n_pad = (n + 3) & ~3;
+    l.A = A;
+    if (l.n_pad <= kChunkRows) {
+        l.rc = l.n_pad;
+        l.n_chunks = 1;
+        l.rc_last = l.n_pad;
+    } else {
+        l.rc = kChunkRows;
+        l.n_chunks = (l.n_pad + kChunkRows - 1) / kChunkRows;
+        l.rc_last = l.n_pad - (l.n_chunks - 1) * kChunkRows;
+    }
+    return l;
+}
+
+constexpr int kMaxPhenPerPass = 4;
+
+// parameters of one ols/corr scan launch (passed by value)
+struct ScanParams {
+    Layout lay;
+    const double *freq;
+    const uint32_t *depth;
+    int64_t n_loci;
+    int kind;
+    int weighted;         // pool weights differ
+    double maf, one_minus_maf, max_miss;
+    double min_depth_f;   // (min_coverage_depth as f64)
+    double w_uniform;     // s_0 / sum(s) when all weights are equal
+    double df;            // Student-t degrees of freedom (n-1 ols, n-2 corr)
+    double ln_beta;       // lnG(df/2 + 1/2) - lnG(df/2) - lnG(1/2)
+    const double *yc;     // [K][n_pad] centred phenotypes of this pass (device)
+    const double *w;      // [n_pad] s_i / sum(s) (device)
+    double ysum[kMaxPhenPerPass];  // sum of the centred phenotype (rounding residue)
+    double syy[kMaxPhenPerPass];   // centred sum of squares
+    int y_has_nan;
+    uint8_t codes[8];     // allele code of device column j
+    uint64_t *meta;
+    double *freq_mean;
+    double *stats;
+    int k_total, phen_base, K;  // output indexing when k > kMaxPhenPerPass
+    int write_meta;             // only the first phenotype pass writes meta / freq_mean
+};
+
+struct TableParams {
+    const uint32_t *counts;  // [locus][A_in][n]
+    int64_t n_loci;
+    int n, A_in;
+    int kind;
+    int drop_col;  // column index coded N to drop (-1 none)
+    double maf, one_minus_maf, max_miss, min_depth_f;
+    const double *w;
+    uint8_t codes[8];
+    uint64_t *meta;
+    double *stats;
+};
+
+// launchers implemented in the kernel translation units
+cudaError_t launch_scan(const ScanParams &p, int sm_count, cudaStream_t s);
+cudaError_t launch_tables(const TableParams &p, int sm_count, cudaStream_t s);
+cudaError_t launch_ingest_u32(const uint32_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
+                              const Layout &lay, double *freq, uint32_t *depth, cudaStream_t s);
+cudaError_t launch_ingest_u16(const uint16_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
+                              const Layout &lay, double *freq, uint32_t *depth, cudaStream_t s);
+cudaError_t launch_ingest_freq(const double *freq_in, const uint32_t *depth_in, int64_t n_loci, int n,
+                               const Layout &lay, double *freq, uint32_t *depth, cudaStream_t s);
+cudaError_t launch_synth(uint64_t seed, int64_t first_locus, int64_t n_loci, int n, int A_in,
+                         uint32_t *counts, cudaStream_t s);
+
+// synthetic generator shared by host and device (pure integer arithmetic)
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// counts of one (locus, pool): c[0..A_in-1].  Locus classes (by the locus hash): 5 % monomorphic
+// (fails a < 2), 2 % with pools at depth 0 (fails the depth filter), 3 % with one rare allele whose
+// pooled frequency straddles 0.1 % (exercises the MAF threshold and the renormalisation of the kept
+// alleles), the rest polymorphic in all of A,T,C,G.  Depth 20..100 per pool.
+__host__ __device__ inline void synth_counts(uint64_t seed, int64_t locus, int pool, int A_in, uint32_t *c) {
+    const uint64_t hl = splitmix64(seed ^ ((uint64_t)locus * 0x9E3779B97F4A7C15ull));
+    const uint64_t hp = splitmix64(hl ^ ((uint64_t)(pool + 1) << 20));
+    const uint32_t cls = (uint32_t)(hl % 100u);
+    const int n_real = A_in < 4 ? A_in : 4;  // N and D columns stay empty
+    uint32_t depth = 20u + (uint32_t)(hp % 81u);
+    if (cls >= 5 && cls < 7 && (uint32_t)((hl >> 32) % 61u) == (uint32_t)(pool % 61)) depth = 0;
+    int rare = -1;
+    uint32_t c_rare = 0;
+    if (cls >= 7 && cls < 10) {
+        rare = (int)((hl >> 44) % (uint64_t)n_real);
+        const uint32_t thr = 30u + (uint32_t)((hl >> 50) % 93u);
+        if (depth > 0 && (uint32_t)(splitmix64(hp ^ 0xBADA55ull) % 1024u) < thr) c_rare = 1;
+    }
+    const uint32_t rem = depth - c_rare;
+    uint64_t wgt[6];
+    uint64_t wsum = 0;
+    for (int a = 0; a < A_in; a++) {
+        const uint64_t ha = splitmix64(hl ^ (0xA11E1E00ull + (uint64_t)a));
+        uint64_t base = 1 + (ha % 997u);
+        if (a >= n_real || a == rare) base = 0;
+        if (cls < 5) base = (a == (int)((hl >> 40) % (uint64_t)n_real)) ? 1000 : 0;  // monomorphic
+        const uint64_t pa = splitmix64(hp ^ (0xC0FFEEull + (uint64_t)a));
+        const uint64_t w = base * (70u + (pa % 61u));  // +-30 % per (pool, allele)
+        wgt[a] = w;
+        wsum += w;
+    }
+    uint32_t used = 0;
+    int last = -1;
+    for (int a = 0; a < A_in; a++) {
+        const uint32_t v = wsum ? (uint32_t)(((uint64_t)rem * wgt[a]) / wsum) : 0u;
+        c[a] = v;
+        used += v;
+        if (wgt[a]) last = a;
+    }
+    if (last >= 0) c[last] += rem - used;  // the remainder goes to the last allele with weight
+    if (rare >= 0) c[rare] = c_rare;
+}
+
+struct Ctx;
+struct Scan;
+struct Batch;
+
+}  // namespace pg
+
+// opaque ABI types
+struct pg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    std::string err;
+};
+
+struct pg_scan {
+    pg_ctx *ctx = nullptr;
+    int kind = 0;
+    int n = 0, A_in = 0, A_dev = 0, k = 0;
+    int drop_col = -1;
+    uint8_t codes_in[8] = {0};
+    uint8_t codes_dev[8] = {0};
+    pg::Layout lay;
+    // filter
+    int remove_ns = 1;
+    uint64_t min_depth = 1;
+    double maf = 0, max_miss = 0;
+    int weighted = 0;
+    double w_uniform = 0;
+    std::vector<double> w_host;
+    // phenotypes
+    std::vector<double> yc_host;  // [k][n_pad]
+    std::vector<double> ysum, syy;
+    int y_has_nan = 0;
+    double df = 0, ln_beta = 0;
+    double *d_yc = nullptr;
+    double *d_w = nullptr;
+    int n_slots = 0;
+    // streaming
+    pg_batch *slabs[PG_STREAM_DEPTH] = {nullptr, nullptr, nullptr};
+    int next_slab = 0;
+    int64_t slab_cap = 0;
+};
+
+struct pg_batch {
+    pg_scan *scan = nullptr;
+    int64_t cap = 0, n_loci = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // device
+    double *d_freq = nullptr;
+    uint32_t *d_depth = nullptr;
+    void *d_stage = nullptr;  // raw uploaded slab (counts u32/u16 or unpadded freq+depth)
+    size_t stage_bytes = 0;
+    uint64_t *d_meta = nullptr;
+    double *d_fmean = nullptr;
+    double *d_stats = nullptr;
+    // pinned host results
+    uint64_t *h_meta = nullptr;
+    double *h_fmean = nullptr;
+    double *h_stats = nullptr;
+    int have_input = 0;
+    int input_is_counts = 0;
+};

@@ -1,0 +1,700 @@
+// pg_scan.cuh -- the per-locus OLS / Pearson scan kernel (ols_iterate: src/gwas/ols.rs:201-276,
+// correlation: src/gwas/correlation_test.rs:73-129) for sm_100a.
+//
+// One persistent CTA per SM.  Every warp owns a private ring of kNBuf shared-memory buffers fed by
+// 1-D bulk copies (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier), so there is no CTA-wide
+// synchronisation in the steady state.  A warp works on groups of G consecutive loci:
+//   phase 1 (per locus)  stream the [A][rows] frequency chunks, lane = pool, accumulate the column
+//                        sums, the A(A+1)/2 products and the A*K cross products with the centred
+//                        phenotypes (kept in shared memory), reduce 32 accumulators with 31 shuffles,
+//                        then evaluate the reference's keep-mask (LocusCounts::filter,
+//                        src/base/sync.rs:195-303) and allele order (src/base/sync.rs:478-505).
+//                        Decisions that land within a rounding bound of a threshold are re-evaluated
+//                        in the reference's exact sequential order (bit-exact mask).
+//   phase 2 (per group)  lane = locus: centred normal equations, Cholesky, beta, residual variance;
+//   phase 3 (per group)  lane = (locus, allele, phenotype): t and the Student-t two-sided p-value.
+#pragma once
+#include "pg_device.cuh"
+#include "pg_internal.h"
+
+namespace pg {
+
+constexpr int kNBuf = 3;
+constexpr int kBufRows = kChunkRows;
+
+template <int A, int K, bool W>
+struct Acc {
+    static constexpr int S0 = 0;
+    static constexpr int P0 = S0 + A;
+    static constexpr int C0 = P0 + A * (A + 1) / 2;
+    static constexpr int Q0 = C0 + A * K;
+    static constexpr int N = Q0 + (W ? A : 0);
+    static constexpr int NB = (N + 31) / 32;
+    static constexpr int NP = NB * 32;
+    __host__ __device__ static constexpr int tri(int j, int l) {  // j <= l
+        return P0 + j * A - j * (j - 1) / 2 + (l - j);
+    }
+};
+
+// loci per warp group: fill the 32 lanes of phase 3 as well as possible
+__host__ __device__ constexpr int group_size(int T) {
+    int best = 1;
+    int best_num = 0, best_den = 1;
+    for (int g = 1; g <= 16; g++) {
+        const int tasks = g * T;
+        const int passes = (tasks + 31) / 32;
+        // efficiency tasks / (32 * passes); prefer larger g on ties
+        if ((long long)tasks * best_den >= (long long)best_num * (32 * passes)) {
+            best = g;
+            best_num = tasks;
+            best_den = 32 * passes;
+        }
+    }
+    return best;
+}
+
+template <int A, int K, bool W>
+struct WarpSmem {
+    using AC = Acc<A, K, W>;
+    static constexpr int T = (A - 1) * K;
+    static constexpr int G = group_size(T);
+    static constexpr int bar_bytes = 32;
+    static constexpr int fbuf_bytes = A * kBufRows * 8;
+    static constexpr int dbuf_bytes = kBufRows * 4;
+    static constexpr int tot_bytes = G * AC::NP * 8;
+    static constexpr int sel_bytes = ((G * 8 + 15) / 16) * 16;
+    static constexpr int tb_bytes = G * T * 16;
+    static constexpr int off_f = bar_bytes;
+    static constexpr int off_d = off_f + kNBuf * fbuf_bytes;
+    static constexpr int off_tot = off_d + kNBuf * dbuf_bytes;
+    static constexpr int off_sel = off_tot + tot_bytes;
+    static constexpr int off_tb = off_sel + sel_bytes;
+    static constexpr int bytes = ((off_tb + tb_bytes + 127) / 128) * 128;
+};
+
+__host__ __device__ inline size_t scan_common_bytes(int K, int n_pad, bool weighted) {
+    size_t b = (size_t)(K + (weighted ? 1 : 0)) * n_pad * 8;
+    return (b + 127) / 128 * 128;
+}
+
+template <int A, int K, bool W, bool NANAWARE>
+__device__ __forceinline__ void accum_row(double (&acc)[Acc<A, K, W>::NP], const double (&f)[A],
+                                          const double (&y)[K], double w) {
+    using AC = Acc<A, K, W>;
+#pragma unroll
+    for (int j = 0; j < A; j++) {
+        if (NANAWARE)
+            acc[AC::S0 + j] += (f[j] != f[j]) ? 0.0 : f[j];  // column sums ignore NaN (sync.rs:483-489)
+        else
+            acc[AC::S0 + j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < A; j++)
+#pragma unroll
+        for (int l = j; l < A; l++) acc[AC::tri(j, l)] = fma(f[j], f[l], acc[AC::tri(j, l)]);
+#pragma unroll
+    for (int j = 0; j < A; j++)
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[AC::C0 + j * K + k] = fma(f[j], y[k], acc[AC::C0 + j * K + k]);
+    if (W) {
+#pragma unroll
+        for (int j = 0; j < A; j++) acc[AC::Q0 + j] = fma(f[j], w, acc[AC::Q0 + j]);
+    }
+}
+
+template <int NP>
+__device__ __forceinline__ void reduce_store(double (&acc)[NP], double *tot, int lane) {
+#pragma unroll
+    for (int b = 0; b < NP / 32; b++) {
+        double v[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = acc[b * 32 + i];
+        warp_reduce32(v, lane);
+        tot[b * 32 + lane] = v[0];
+    }
+}
+
+// q_j = sum_i f_ij * (s_i / S), accumulated in pool order with separately rounded multiply and add,
+// NaN frequencies contribute 0 -- the exact arithmetic of src/base/sync.rs:258-271.
+static __device__ __noinline__ double exact_q(const ScanParams &p, int64_t locus, int j, const double *ws) {
+    const Layout &lay = p.lay;
+    const double *fl = p.freq + (size_t)locus * lay.freq_stride();
+    double q = 0.0;
+    int i0 = 0;
+    for (int c = 0; c < lay.n_chunks; c++) {
+        const int rcc = (c == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
+        const double *col = fl + (size_t)c * lay.A * lay.rc + (size_t)j * rcc;
+        const int rows = min(rcc, lay.n - i0);
+        for (int r = 0; r < rows; r++) {
+            const double f = col[r];
+            const double w = ws ? ws[i0 + r] : p.w_uniform;
+            const double term = (f != f) ? 0.0 : __dmul_rn(f, w);
+            q = __dadd_rn(q, term);
+        }
+        i0 += rcc;
+    }
+    return q;
+}
+
+// renormalised frequency of (pool i, column j) over the kept columns:
+// c_ij / sum_{kept} c_i.  (LocusCounts::to_frequencies after the filter, src/base/sync.rs:166-192),
+// with c_ij = rint(f_ij * depth_i) recovering the integer count exactly.
+template <int A>
+__device__ __forceinline__ void renorm_row(const double (&f)[A], uint32_t d, unsigned kept, double (&F)[A]) {
+    double c[A];
+    double dk = 0.0;
+#pragma unroll
+    for (int j = 0; j < A; j++) {
+        c[j] = (d == 0u) ? 0.0 : rint(f[j] * (double)d);
+        if ((kept >> j) & 1u) dk += c[j];
+    }
+#pragma unroll
+    for (int j = 0; j < A; j++) {
+        if ((kept >> j) & 1u)
+            F[j] = (dk == 0.0) ? nan("") : c[j] / dk;
+        else
+            F[j] = 0.0;
+    }
+}
+
+// column sum of the renormalised frequencies in pool order, NaN ignored (src/base/sync.rs:483-489)
+template <int A>
+__device__ __noinline__ double exact_colsum(const ScanParams &p, int64_t locus, int jsel, unsigned kept) {
+    const Layout &lay = p.lay;
+    const double *fl = p.freq + (size_t)locus * lay.freq_stride();
+    const uint32_t *dl = p.depth + (size_t)locus * lay.depth_stride();
+    double s = 0.0;
+    int i0 = 0;
+    for (int c = 0; c < lay.n_chunks; c++) {
+        const int rcc = (c == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
+        const double *blk = fl + (size_t)c * lay.A * lay.rc;
+        const int rows = min(rcc, lay.n - i0);
+        for (int r = 0; r < rows; r++) {
+            double f[A], F[A];
+#pragma unroll
+            for (int j = 0; j < A; j++) f[j] = blk[(size_t)j * rcc + r];
+            renorm_row<A>(f, dl[i0 + r], kept, F);
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < A; j++)
+                if (j == jsel) v = F[j];
+            if (v == v) s = __dadd_rn(s, v);
+        }
+        i0 += rcc;
+    }
+    return s;
+}
+
+// Full reference pipeline for one locus straight from global memory: exact q with NaN handling,
+// missingness, renormalisation over the kept alleles.  Used when a pool has no coverage or when a
+// removed allele carries reads (both rare).  Leaves the re-accumulated totals in tot[].
+template <int A, int K, bool W>
+__device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const double *ys, const double *ws,
+                                       double *tot, int lane, unsigned &kept_out) {
+    using AC = Acc<A, K, W>;
+    const Layout &lay = p.lay;
+    const double *fl = p.freq + (size_t)locus * lay.freq_stride();
+    const uint32_t *dl = p.depth + (size_t)locus * lay.depth_stride();
+    // 1. keep-mask of the alleles (lane j evaluates column j sequentially)
+    bool keep_j = false;
+    if (lane < A) {
+        const double q = exact_q(p, locus, lane, ws);
+        keep_j = !((q < p.maf) | (q > p.one_minus_maf));
+    }
+    const unsigned kept = __ballot_sync(PG_FULL_MASK, keep_j) & ((1u << A) - 1u);
+    kept_out = kept;
+    if (__popc(kept) < 2) return PG_LOCUS_FILTERED;
+    // 2. missingness on the first kept column: NaN <=> the pool has no coverage (sync.rs:287-299)
+    int miss = 0;
+    for (int i = lane; i < lay.n; i += 32) {
+        const int c = i / lay.rc;
+        miss += (dl[(size_t)c * lay.rc + (i - c * lay.rc)] == 0u) ? 1 : 0;
+    }
+    miss = __reduce_add_sync(PG_FULL_MASK, miss);
+    if (miss == lay.n) return PG_LOCUS_FILTERED;
+    if (((double)miss / (double)lay.n) > p.max_miss) return PG_LOCUS_FILTERED;
+    // 3. re-accumulate over the renormalised frequencies
+    double acc[AC::NP];
+#pragma unroll
+    for (int i = 0; i < AC::NP; i++) acc[i] = 0.0;
+    int i0 = 0;
+    for (int c = 0; c < lay.n_chunks; c++) {
+        const int rcc = (c == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
+        const double *blk = fl + (size_t)c * lay.A * lay.rc;
+        const int rows = min(rcc, lay.n - i0);
+        for (int r = lane; r < rows; r += 32) {
+            double f[A], F[A], y[K];
+#pragma unroll
+            for (int j = 0; j < A; j++) f[j] = blk[(size_t)j * rcc + r];
+            renorm_row<A>(f, dl[i0 + r], kept, F);
+#pragma unroll
+            for (int k = 0; k < K; k++) y[k] = ys[k * lay.n_pad + i0 + r];
+            accum_row<A, K, W, true>(acc, F, y, 0.0);
+        }
+        i0 += rcc;
+    }
+    reduce_store<AC::NP>(acc, tot, lane);
+    __syncwarp();
+    return PG_LOCUS_OK;
+}
+
+__device__ __forceinline__ uint64_t pack_sel(int status, int nslots, const int *cols) {
+    uint64_t v = (uint64_t)(status & 0xff) | ((uint64_t)(nslots & 0xff) << 8);
+    for (int s = 0; s < PG_MAX_SLOTS; s++) v |= (uint64_t)(cols[s] & 0xf) << (16 + 4 * s);
+    return v;
+}
+
+template <int A, int K, bool W>
+__global__ void __launch_bounds__((Acc<A, K, W>::NB == 1 ? 12 : 8) * 32, 1) scan_kernel(const ScanParams p) {
+    using AC = Acc<A, K, W>;
+    using WS = WarpSmem<A, K, W>;
+    constexpr int T = WS::T;
+    constexpr int G = WS::G;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const Layout lay = p.lay;
+    const int n_pad = lay.n_pad;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    double *ys = reinterpret_cast<double *>(smem);
+    double *ws = W ? ys + (size_t)K * n_pad : nullptr;
+    unsigned char *wb = smem + scan_common_bytes(K, n_pad, W) + (size_t)warp * WS::bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wb);
+    double *fbuf = reinterpret_cast<double *>(wb + WS::off_f);
+    uint32_t *dbuf = reinterpret_cast<uint32_t *>(wb + WS::off_d);
+    double *tot = reinterpret_cast<double *>(wb + WS::off_tot);
+    uint64_t *sel = reinterpret_cast<uint64_t *>(wb + WS::off_sel);
+    double *tb = reinterpret_cast<double *>(wb + WS::off_tb);
+
+    for (int i = threadIdx.x; i < K * n_pad; i += blockDim.x) ys[i] = p.yc[i];
+    if (W)
+        for (int i = threadIdx.x; i < n_pad; i += blockDim.x) ws[i] = p.w[i];
+    if (lane == 0) {
+        for (int b = 0; b < kNBuf; b++) mbar_init(&bars[b], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int64_t L = p.n_loci;
+    const int64_t NG = (L + G - 1) / G;
+    const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;  // consecutive warps of a CTA take consecutive groups
+    const int64_t TW = (int64_t)gridDim.x * nwarps;
+    if (gw >= NG) return;
+    const int64_t my_groups = (NG - gw + TW - 1) / TW;
+    const bool small = lay.n_chunks == 1;
+    const int TL = small ? max(1, min(G, kBufRows / n_pad)) : 1;
+    const int TPG = small ? (G + TL - 1) / TL : G * lay.n_chunks;
+    const int64_t total_tiles = my_groups * TPG;
+    const size_t fstride = lay.freq_stride(), dstride = lay.depth_stride();
+    const double nn = (double)lay.n;
+    const double tol_rel = 2.0 * (nn + 8.0) * kEps;
+
+    // tile t of this warp -> (group, first locus slot, loci, chunk)
+    auto issue = [&](int64_t gs, int ti, int buf) {
+        const int64_t group = gw + gs * TW;
+        int li, chunk, nl;
+        if (small) {
+            li = ti * TL;
+            chunk = 0;
+            nl = min(TL, G - li);
+        } else {
+            li = ti / lay.n_chunks;
+            chunk = ti - li * lay.n_chunks;
+            nl = 1;
+        }
+        const int64_t l0 = group * G + li;
+        const int nlv = (int)max((int64_t)0, min((int64_t)nl, L - l0));
+        if (nlv <= 0) return;
+        const int rcc = (chunk == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
+        const uint32_t fbytes = (uint32_t)(small ? (size_t)nlv * A * n_pad * 8 : (size_t)A * rcc * 8);
+        const uint32_t dbytes = (uint32_t)(small ? (size_t)nlv * n_pad * 4 : (size_t)rcc * 4);
+        const double *fsrc = p.freq + (size_t)l0 * fstride + (size_t)chunk * A * lay.rc;
+        const uint32_t *dsrc = p.depth + (size_t)l0 * dstride + (size_t)chunk * lay.rc;
+        mbar_expect_tx(&bars[buf], fbytes + dbytes);
+        bulk_g2s(fbuf + (size_t)buf * (WS::fbuf_bytes / 8), fsrc, fbytes, &bars[buf]);
+        bulk_g2s(dbuf + (size_t)buf * (WS::dbuf_bytes / 4), dsrc, dbytes, &bars[buf]);
+    };
+
+    // prologue: fill the ring
+    {
+        int64_t gs = 0;
+        int ti = 0;
+        for (int b = 0; b < kNBuf && b < total_tiles; b++) {
+            if (lane == 0) issue(gs, ti, b);
+            if (++ti == TPG) {
+                ti = 0;
+                gs++;
+            }
+        }
+    }
+    // iterator of the tile to issue next: always kNBuf tiles ahead of the consumer
+    int64_t igs = kNBuf / TPG;
+    int iti = kNBuf % TPG;
+
+    double acc[AC::NP];
+    unsigned dmin = 0xFFFFFFFFu;
+    uint32_t phase_bits = 0;  // bit b = parity to wait for on buffer b
+    int buf = 0;
+    int64_t cgs = 0;
+    int cti = 0;
+
+    for (int64_t t = 0; t < total_tiles; t++) {
+        const int64_t group = gw + cgs * TW;
+        int li, chunk, nl;
+        if (small) {
+            li = cti * TL;
+            chunk = 0;
+            nl = min(TL, G - li);
+        } else {
+            li = cti / lay.n_chunks;
+            chunk = cti - li * lay.n_chunks;
+            nl = 1;
+        }
+        const int64_t l0 = group * G + li;
+        const int nlv = (int)max((int64_t)0, min((int64_t)nl, L - l0));
+        const int rcc = (chunk == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
+        const int row0 = chunk * lay.rc;
+        if (nlv > 0) {
+            mbar_wait(&bars[buf], (phase_bits >> buf) & 1u);
+            phase_bits ^= (1u << buf);
+            const double *fb0 = fbuf + (size_t)buf * (WS::fbuf_bytes / 8);
+            const uint32_t *db0 = dbuf + (size_t)buf * (WS::dbuf_bytes / 4);
+            for (int q = 0; q < nlv; q++) {
+                const double *fb = fb0 + (size_t)q * A * n_pad;
+                const uint32_t *db = db0 + (size_t)q * n_pad;
+                if (chunk == 0) {
+#pragma unroll
+                    for (int i = 0; i < AC::NP; i++) acc[i] = 0.0;
+                    dmin = 0xFFFFFFFFu;
+                }
+                // ---- phase 1: lane handles rows 2*lane, 2*lane+1 (+64 ...) with 128-bit loads
+                for (int r = 2 * lane; r < rcc; r += 64) {
+                    double2 f2[A];
+#pragma unroll
+                    for (int j = 0; j < A; j++) f2[j] = *reinterpret_cast<const double2 *>(fb + (size_t)j * rcc + r);
+                    const uint2 d2 = *reinterpret_cast<const uint2 *>(db + r);
+                    double2 y2[K];
+#pragma unroll
+                    for (int k = 0; k < K; k++)
+                        y2[k] = *reinterpret_cast<const double2 *>(ys + (size_t)k * n_pad + row0 + r);
+                    double2 w2 = make_double2(0.0, 0.0);
+                    if (W) w2 = *reinterpret_cast<const double2 *>(ws + row0 + r);
+                    dmin = min(dmin, min(d2.x, d2.y));
+                    double fa[A], ya[K];
+#pragma unroll
+                    for (int j = 0; j < A; j++) fa[j] = f2[j].x;
+#pragma unroll
+                    for (int k = 0; k < K; k++) ya[k] = y2[k].x;
+                    accum_row<A, K, W, false>(acc, fa, ya, w2.x);
+#pragma unroll
+                    for (int j = 0; j < A; j++) fa[j] = f2[j].y;
+#pragma unroll
+                    for (int k = 0; k < K; k++) ya[k] = y2[k].y;
+                    accum_row<A, K, W, false>(acc, fa, ya, w2.y);
+                }
+                if (chunk == lay.n_chunks - 1) {
+                    // ---- end of locus: reduce, keep-mask, allele order
+                    const int g = li + q;
+                    const int64_t locus = l0 + q;
+                    double *tg = tot + (size_t)g * AC::NP;
+                    const unsigned dm = __reduce_min_sync(PG_FULL_MASK, dmin);
+                    reduce_store<AC::NP>(acc, tg, lane);
+                    __syncwarp();
+                    int status = PG_LOCUS_OK;
+                    unsigned kept = 0;
+                    bool slow = false;
+                    if ((double)dm < p.min_depth_f) {
+                        status = PG_LOCUS_FILTERED;  // sync.rs:217-229
+                    } else if (dm == 0u) {
+                        slow = true;  // a pool without coverage: NaN frequencies
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < A; j++) {
+                            double qj = W ? tg[AC::Q0 + j] : tg[AC::S0 + j] * p.w_uniform;
+                            const double tl = tol_rel * fmax(fabs(qj), 1.0);
+                            if (fabs(qj - p.maf) <= tl || fabs(qj - p.one_minus_maf) <= tl)
+                                qj = exact_q(p, locus, j, ws);
+                            if (!((qj < p.maf) | (qj > p.one_minus_maf))) kept |= 1u << j;
+                        }
+                        if (__popc(kept) < 2) {
+                            status = PG_LOCUS_FILTERED;  // sync.rs:284-286
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < A; j++)
+                                if (!((kept >> j) & 1u) && tg[AC::S0 + j] > 0.0) slow = true;  // renormalise
+                        }
+                    }
+                    if (slow) status = slow_locus<A, K, W>(p, locus, ys, ws, tg, lane, kept);
+                    int cols[PG_MAX_SLOTS] = {0, 0, 0, 0, 0};
+                    int nslots = 0;
+                    if (status == PG_LOCUS_OK) {
+                        const int a = __popc(kept);
+                        nslots = a - 1;
+                        if (p.kind == PG_KIND_OLS) {
+                            // stable sort by decreasing column sum, drop the first (major) allele
+                            double cs[A];
+                            bool tie = false;
+#pragma unroll
+                            for (int j = 0; j < A; j++) cs[j] = tg[AC::S0 + j];
+#pragma unroll
+                            for (int j = 0; j < A; j++)
+#pragma unroll
+                                for (int l = j + 1; l < A; l++)
+                                    if (((kept >> j) & 1u) && ((kept >> l) & 1u) &&
+                                        fabs(cs[j] - cs[l]) <= tol_rel * fmax(fabs(cs[j]), fabs(cs[l])))
+                                        tie = true;
+                            if (tie) {
+                                double mine = 0.0;
+                                if (lane < A && ((kept >> lane) & 1u)) mine = exact_colsum<A>(p, locus, lane, kept);
+#pragma unroll
+                                for (int j = 0; j < A; j++) cs[j] = __shfl_sync(PG_FULL_MASK, mine, j);
+                            }
+#pragma unroll
+                            for (int j = 0; j < A; j++) {
+                                if (!((kept >> j) & 1u)) continue;
+                                int rank = 0;
+#pragma unroll
+                                for (int l = 0; l < A; l++) {
+                                    if (l == j || !((kept >> l) & 1u)) continue;
+                                    if (cs[l] > cs[j] || (cs[l] == cs[j] && l < j)) rank++;
+                                }
+#pragma unroll
+                                for (int s = 0; s < PG_MAX_SLOTS; s++)
+                                    if (rank == s + 1) cols[s] = j;
+                            }
+                        } else {
+                            // kept columns in file order, the last one is dropped (correlation_test.rs:94-98)
+                            int s = 0;
+#pragma unroll
+                            for (int j = 0; j < A; j++) {
+                                if (!((kept >> j) & 1u)) continue;
+#pragma unroll
+                                for (int ss = 0; ss < PG_MAX_SLOTS; ss++)
+                                    if (ss == s && s < nslots) cols[ss] = j;
+                                s++;
+                            }
+                        }
+                    }
+                    if (lane == 0) sel[g] = pack_sel(status, nslots, cols);
+                }
+            }
+        }
+        __syncwarp();
+        // refill this buffer with the tile kNBuf ahead
+        if (t + kNBuf < total_tiles) {
+            if (lane == 0) issue(igs, iti, buf);
+            if (++iti == TPG) {
+                iti = 0;
+                igs++;
+            }
+        }
+        buf = (buf + 1 == kNBuf) ? 0 : buf + 1;
+        const bool group_done = (cti + 1 == TPG);
+        if (++cti == TPG) {
+            cti = 0;
+            cgs++;
+        }
+        if (!group_done) continue;
+
+        // ---- phase 2: lane = locus of the group
+        __syncwarp();
+        const int64_t gl0 = group * G;
+        if (lane < G && gl0 + lane < L) {
+            const int g = lane;
+            const int64_t locus = gl0 + g;
+            const double *tg = tot + (size_t)g * AC::NP;
+            uint64_t sv = sel[g];
+            int status = (int)(sv & 0xff);
+            const int m = (int)((sv >> 8) & 0xff);
+            int cols[PG_MAX_SLOTS];
+#pragma unroll
+            for (int s = 0; s < PG_MAX_SLOTS; s++) cols[s] = (int)((sv >> (16 + 4 * s)) & 0xf);
+            double *tbg = tb + (size_t)g * T * 2;
+            double fmean[PG_MAX_SLOTS];
+            if (status == PG_LOCUS_OK) {
+                double sx[PG_MAX_SLOTS];
+                bool has_nan = false;
+                for (int a = 0; a < m; a++) {
+                    sx[a] = tg[AC::S0 + cols[a]];
+                    const double pjj = tg[AC::tri(cols[a], cols[a])];
+                    has_nan |= (pjj != pjj);
+                    fmean[a] = (pjj != pjj) ? nan("") : sx[a] / nn;
+                }
+                if (p.kind == PG_KIND_OLS) {
+                    if (lay.n < m + 1) {
+                        status = PG_LOCUS_UNSUPPORTED;
+                    } else if (has_nan) {
+                        for (int i = 0; i < m * K * 2; i++) tbg[i] = nan("");
+                    } else {
+                        double Lm[PG_MAX_SLOTS][PG_MAX_SLOTS];
+                        bool ok = true;
+                        for (int a = 0; a < m; a++)
+                            for (int b = 0; b <= a; b++) {
+                                const int ca = cols[a], cb = cols[b];
+                                const int lo = ca < cb ? ca : cb, hi = ca < cb ? cb : ca;
+                                double s = tg[AC::tri(lo, hi)] - sx[a] * sx[b] / nn;
+                                for (int c = 0; c < b; c++) s -= Lm[a][c] * Lm[b][c];
+                                if (a == b) {
+                                    if (!(s > 0.0)) {
+                                        ok = false;
+                                        s = 1.0;
+                                    }
+                                    Lm[a][a] = sqrt(s);
+                                } else {
+                                    Lm[a][b] = s / Lm[b][b];
+                                }
+                            }
+                        if (!ok) {
+                            status = PG_LOCUS_FAILED;
+                        } else {
+                            // inverse of L (lower), diag of Sxx^-1 = column sums of squares of L^-1
+                            double Li[PG_MAX_SLOTS][PG_MAX_SLOTS];
+                            for (int a = 0; a < m; a++) {
+                                Li[a][a] = 1.0 / Lm[a][a];
+                                for (int b = 0; b < a; b++) {
+                                    double s = 0.0;
+                                    for (int c = b; c < a; c++) s -= Lm[a][c] * Li[c][b];
+                                    Li[a][b] = s / Lm[a][a];
+                                }
+                            }
+                            double dg[PG_MAX_SLOTS];
+                            for (int b = 0; b < m; b++) {
+                                double s = 0.0;
+                                for (int a = b; a < m; a++) s += Li[a][b] * Li[a][b];
+                                dg[b] = s;
+                            }
+                            const double dfe = nn - (double)(m + 1);
+                            for (int k = 0; k < K; k++) {
+                                double z[PG_MAX_SLOTS];
+                                double zz = 0.0;
+                                for (int a = 0; a < m; a++) {
+                                    double s = 0.0;
+                                    for (int b = 0; b <= a; b++) {
+                                        const double sxy = tg[AC::C0 + cols[b] * K + k] - sx[b] * p.ysum[k] / nn;
+                                        s += Li[a][b] * sxy;
+                                    }
+                                    z[a] = s;
+                                    zz += s * s;
+                                }
+                                double rss = p.syy[k] - zz;
+                                if (rss < 0.0) rss = 0.0;
+                                const double ve = rss / dfe;
+                                for (int b = 0; b < m; b++) {
+                                    double s = 0.0;
+                                    for (int a = b; a < m; a++) s += Li[a][b] * z[a];
+                                    tbg[(b * K + k) * 2 + 0] = s;
+                                    tbg[(b * K + k) * 2 + 1] = ve * dg[b];
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    for (int a = 0; a < m; a++) {
+                        const double sxx = tg[AC::tri(cols[a], cols[a])] - sx[a] * sx[a] / nn;
+                        for (int k = 0; k < K; k++) {
+                            const double sxy = tg[AC::C0 + cols[a] * K + k] - sx[a] * p.ysum[k] / nn;
+                            tbg[(a * K + k) * 2 + 0] = sxy / (sqrt(sxx) * sqrt(p.syy[k]));
+                            tbg[(a * K + k) * 2 + 1] = 0.0;
+                        }
+                    }
+                }
+                if (status != PG_LOCUS_OK) sel[g] = (sv & ~(uint64_t)0xff) | (uint64_t)status;
+            }
+            if (p.write_meta) {
+                uint64_t mv = (uint64_t)status;
+                if (status == PG_LOCUS_OK) {
+                    mv |= (uint64_t)m << 8;
+                    for (int s = 0; s < m; s++) mv |= (uint64_t)p.codes[cols[s]] << (16 + 8 * s);
+                }
+                p.meta[locus] = mv;
+                for (int s = 0; s < A - 1; s++)
+                    p.freq_mean[(size_t)locus * (A - 1) + s] = (status == PG_LOCUS_OK && s < m) ? fmean[s] : nan("");
+            }
+        }
+        __syncwarp();
+        // ---- phase 3: lane = (locus, allele slot, phenotype)
+        for (int task = lane; task < G * T; task += 32) {
+            const int g = task / T, rem = task - g * T;
+            const int slot = rem / K, kk = rem - slot * K;
+            const int64_t locus = gl0 + g;
+            if (locus >= L) continue;
+            const uint64_t sv = sel[g];
+            const int status = (int)(sv & 0xff);
+            const int m = (int)((sv >> 8) & 0xff);
+            double o0 = nan(""), o1 = nan(""), o2 = nan(""), o3 = nan("");
+            if (status == PG_LOCUS_OK && slot < m) {
+                const double v0 = tb[((size_t)g * T + slot * K + kk) * 2 + 0];
+                const double v1 = tb[((size_t)g * T + slot * K + kk) * 2 + 1];
+                if (p.kind == PG_KIND_OLS) {
+                    // estimate_significance, src/gwas/ols.rs:139-154
+                    const double se = sqrt(v1);
+                    const double tt = (fabs(v0) <= kEps) ? 0.0 : v0 / se;
+                    double pv;
+                    if (fabs(tt) <= kEps || tt != tt)
+                        pv = 1.0;
+                    else
+                        pv = student_two_sided(fabs(tt), p.df, p.ln_beta);
+                    o0 = v0;
+                    o1 = se;
+                    o2 = tt;
+                    o3 = pv;
+                } else {
+                    // pearsons_correlation, src/gwas/correlation_test.rs:52-70
+                    const double r = v0;
+                    if (r == r) {
+                        const double s2 = (1.0 - r * r) / (nn - 2.0);
+                        o1 = r;
+                        if (s2 <= 0.0) {
+                            o0 = r;
+                            o3 = kEps;
+                        } else {
+                            const double tt = r / sqrt(s2);
+                            o2 = tt;
+                            o3 = (lay.n > 2) ? student_two_sided(fabs(tt), p.df, p.ln_beta) : nan("");
+                            o0 = round(r * 1e7) / 1e7;
+                        }
+                    }
+                }
+            }
+            double *o = p.stats + (((size_t)locus * (A - 1) + slot) * p.k_total + p.phen_base + kk) * 4;
+            *reinterpret_cast<double2 *>(o) = make_double2(o0, o1);
+            *reinterpret_cast<double2 *>(o + 2) = make_double2(o2, o3);
+        }
+        __syncwarp();
+    }
+}
+
+template <int A, int K, bool W>
+cudaError_t launch_scan_t(const ScanParams &p, int sm_count, cudaStream_t s) {
+    using WS = WarpSmem<A, K, W>;
+    using AC = Acc<A, K, W>;
+    const size_t common = scan_common_bytes(K, p.lay.n_pad, W);
+    const size_t avail = 227 * 1024;
+    if (common + WS::bytes > avail) return cudaErrorInvalidConfiguration;
+    int max_warps = AC::NB == 1 ? 12 : 8;
+    int nwarps = (int)((avail - common) / WS::bytes);
+    if (nwarps > max_warps) nwarps = max_warps;
+    if (nwarps > 4) nwarps &= ~3;  // keep the four SM sub-partitions balanced
+    const size_t smem = common + (size_t)nwarps * WS::bytes;
+    auto kern = scan_kernel<A, K, W>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t NG = (p.n_loci + WS::G - 1) / WS::G;
+    int64_t ctas = (NG + nwarps - 1) / nwarps;
+    if (ctas > sm_count) ctas = sm_count;
+    if (ctas < 1) ctas = 1;
+    kern<<<(unsigned)ctas, nwarps * 32, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int A>
+cudaError_t launch_scan_a(const ScanParams &p, int sm_count, cudaStream_t s) {
+    const bool w = p.weighted != 0;
+    switch (p.K) {
+        case 1: return w ? launch_scan_t<A, 1, true>(p, sm_count, s) : launch_scan_t<A, 1, false>(p, sm_count, s);
+        case 2: return w ? launch_scan_t<A, 2, true>(p, sm_count, s) : launch_scan_t<A, 2, false>(p, sm_count, s);
+        case 3: return w ? launch_scan_t<A, 3, true>(p, sm_count, s) : launch_scan_t<A, 3, false>(p, sm_count, s);
+        case 4: return w ? launch_scan_t<A, 4, true>(p, sm_count, s) : launch_scan_t<A, 4, false>(p, sm_count, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace pg

@@ -1,0 +1,239 @@
+// pg_tables.cu -- the count-table callbacks: tables::chisq (src/tables/chisq_test.rs:5-47) and
+// tables::fisher (src/tables/fisher_exact_test.rs:32-130), one thread per locus.  The raw u32 counts
+// [locus][allele][pool] of a CTA's loci are staged through shared memory with coalesced 128-bit loads;
+// each thread then walks its own locus in the reference's exact sequential order, so the keep-mask
+// needs no rounding analysis here.
+#include "pg_device.cuh"
+#include "pg_internal.h"
+
+namespace pg {
+
+constexpr int kTabThreads = 128;
+constexpr int kTabMaxPools = 16;
+constexpr int kTabMaxCells = kTabMaxPools * PG_MAX_ALLELES;
+
+__constant__ double c_lf10[36];  // log10(x!) accumulated like factorial_log10 (fisher_exact_test.rs:6-18)
+
+// LocusCounts::filter on one locus held as cnt[j*n + i]; returns status and the kept column list
+__device__ int table_filter(const uint32_t *cnt, const TableParams &p, int *cols, int &pk) {
+    const int n = p.n;
+    int col[PG_MAX_ALLELES];
+    int pc = 0;
+    for (int j = 0; j < p.A_in; j++)
+        if (j != p.drop_col) col[pc++] = j;
+    // depth per pool = sequential f64 sum over the remaining columns (exact: integers)
+    double dmin = 0.0;
+    for (int i = 0; i < n; i++) {
+        double d = 0.0;
+        for (int a = 0; a < pc; a++) d += (double)cnt[col[a] * n + i];
+        if (i == 0 || d < dmin) dmin = d;
+    }
+    pk = 0;
+    if (dmin < p.min_depth_f) return PG_LOCUS_FILTERED;
+    for (int a = 0; a < pc; a++) {
+        double q = 0.0;
+        for (int i = 0; i < n; i++) {
+            double d = 0.0;
+            for (int b = 0; b < pc; b++) d += (double)cnt[col[b] * n + i];
+            const double f = (d == 0.0) ? nan("") : (double)cnt[col[a] * n + i] / d;
+            const double term = (f != f) ? 0.0 : __dmul_rn(f, p.w[i]);
+            q = __dadd_rn(q, term);
+        }
+        if (!((q < p.maf) | (q > p.one_minus_maf))) cols[pk++] = col[a];
+    }
+    if (pk < 2) return PG_LOCUS_FILTERED;
+    int miss = 0;
+    for (int i = 0; i < n; i++) {
+        double d = 0.0;
+        for (int b = 0; b < pc; b++) d += (double)cnt[col[b] * n + i];
+        if (d == 0.0) miss++;
+    }
+    if (miss == n) return PG_LOCUS_FILTERED;
+    if (((double)miss / (double)n) > p.max_miss) return PG_LOCUS_FILTERED;
+    return PG_LOCUS_OK;
+}
+
+__device__ __forceinline__ double as_usize_f64(double v) {  // `(x) as usize as f64`
+    if (v != v || v <= 0.0) return 0.0;
+    if (v >= 18446744073709551615.0) return 18446744073709551615.0;
+    return (double)(unsigned long long)v;
+}
+
+__device__ double hypergeom_ratio_dev(const double *c, int cells, double lp) {
+    double s = 0.0, total = 0.0;
+    for (int i = 0; i < cells; i++) s = s + c_lf10[(int)c[i]];
+    for (int i = 0; i < cells; i++) total = total + c[i];
+    s = s + c_lf10[(int)total];
+    return pow(10.0, lp - s);
+}
+
+__global__ void __launch_bounds__(kTabThreads) tables_kernel(const TableParams p) {
+    extern __shared__ __align__(16) uint32_t sm_counts[];
+    const int per_locus = p.A_in * p.n;  // u32 words
+    const int64_t tiles = (p.n_loci + kTabThreads - 1) / kTabThreads;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t l0 = tile * kTabThreads;
+        const int nl = (int)min((int64_t)kTabThreads, p.n_loci - l0);
+        const size_t words = (size_t)nl * per_locus;
+        const uint32_t *src = p.counts + (size_t)l0 * per_locus;
+        __syncthreads();
+        // the tile start is 16-byte aligned when per_locus * kTabThreads * 4 is (always: 128 loci)
+        const size_t w4 = words / 4;
+        for (size_t i = threadIdx.x; i < w4; i += kTabThreads)
+            reinterpret_cast<uint4 *>(sm_counts)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+        for (size_t i = w4 * 4 + threadIdx.x; i < words; i += kTabThreads) sm_counts[i] = src[i];
+        __syncthreads();
+        if ((int)threadIdx.x >= nl) continue;
+        const int64_t locus = l0 + threadIdx.x;
+        const uint32_t *cnt = sm_counts + (size_t)threadIdx.x * per_locus;
+        const int n = p.n;
+        int cols[PG_MAX_ALLELES];
+        int pk = 0;
+        int status = table_filter(cnt, p, cols, pk);
+        double stat = nan(""), pval = nan("");
+        if (status == PG_LOCUS_OK) {
+            const int cells = n * pk;
+            double c[kTabMaxCells];  // row-major n x pk
+            double rs[kTabMaxPools], cs[PG_MAX_ALLELES];
+            if (p.kind == PG_KIND_CHISQ) {
+                // frequencies renormalised over the kept alleles (sync.rs:166-192)
+                for (int i = 0; i < n; i++) {
+                    double d = 0.0;
+                    for (int a = 0; a < pk; a++) d = d + (double)cnt[cols[a] * n + i];
+                    for (int a = 0; a < pk; a++) c[i * pk + a] = (d == 0.0) ? nan("") : (double)cnt[cols[a] * n + i] / d;
+                }
+                double total = 0.0;
+                for (int i = 0; i < cells; i++) total = total + c[i];
+                for (int i = 0; i < n; i++) {
+                    rs[i] = 0.0;
+                    for (int a = 0; a < pk; a++) rs[i] = rs[i] + c[i * pk + a];
+                }
+                for (int a = 0; a < pk; a++) {
+                    cs[a] = 0.0;
+                    for (int i = 0; i < n; i++) cs[a] = cs[a] + c[i * pk + a];
+                }
+                double chi2 = 0.0;
+                for (int i = 0; i < n; i++)
+                    for (int a = 0; a < pk; a++) {
+                        const double e = (rs[i] * cs[a]) / total;
+                        const double d = c[i * pk + a] - e;
+                        chi2 += (d * d) / e;
+                    }
+                stat = chi2;
+                const double df = (double)cells - 1.0;
+                double cdf;
+                if (chi2 <= 0.0)
+                    cdf = 0.0;
+                else if (isinf(chi2))
+                    cdf = 1.0;
+                else
+                    cdf = gamma_lr_dev(df / 2.0, chi2 * 0.5);
+                pval = 1.00 - cdf;
+            } else {
+                for (int i = 0; i < n; i++)
+                    for (int a = 0; a < pk; a++) c[i * pk + a] = (double)cnt[cols[a] * n + i];
+                double total = 0.0;
+                for (int i = 0; i < cells; i++) total = total + c[i];
+                if (total > 34.0) {
+                    const double coef = 34.0 / total;
+                    for (int i = 0; i < cells; i++) c[i] = floor(c[i] * coef);
+                }
+                for (int i = 0; i < n; i++) {
+                    rs[i] = 0.0;
+                    for (int a = 0; a < pk; a++) rs[i] = rs[i] + c[i * pk + a];
+                }
+                for (int a = 0; a < pk; a++) {
+                    cs[a] = 0.0;
+                    for (int i = 0; i < n; i++) cs[a] = cs[a] + c[i * pk + a];
+                }
+                double lp = 0.0;
+                for (int i = 0; i < n; i++) lp = lp + c_lf10[(int)rs[i]];
+                for (int a = 0; a < pk; a++) lp = lp + c_lf10[(int)cs[a]];
+                const double p_obs = hypergeom_ratio_dev(c, cells, lp);
+                double p_ext = 0.0;
+                bool panic = false;
+                for (int mi = 0; mi < n && !panic; mi++)
+                    for (int mj = 0; mj < pk && !panic; mj++) {
+                        for (int i = 0; i < n; i++)
+                            for (int j = 0; j < pk; j++) {
+                                double r = 0.0, s = 0.0;
+                                for (int jj = 0; jj < j; jj++) r = r + c[i * pk + jj];
+                                for (int ii = 0; ii < i; ii++) s = s + c[ii * pk + j];
+                                const double a = as_usize_f64(rs[i] - r), b = as_usize_f64(cs[j] - s);
+                                const double mx = a < b ? a : b;
+                                if ((i == n - 1) | (j == pk - 1))
+                                    c[i * pk + j] = mx;
+                                else if ((i < mi) | (j < mj))
+                                    c[i * pk + j] = 0.0;
+                                else
+                                    c[i * pk + j] = mx;
+                            }
+                        for (int ij = 0; ij < pk; ij++)
+                            for (int ii2 = 0; ii2 < n; ii2++) {
+                                const int j = pk - (ij + 1), i = n - (ii2 + 1);
+                                double r = 0.0, s = 0.0;
+                                for (int jj = 0; jj < pk; jj++) r = r + c[i * pk + jj];
+                                for (int ii = 0; ii < n; ii++) s = s + c[ii * pk + j];
+                                const double a = as_usize_f64(rs[i] - r), b = as_usize_f64(cs[j] - s);
+                                const double mx = a < b ? a : b;
+                                if (mx > 0.0) c[i * pk + j] = mx;
+                            }
+                        for (int i = 0; i < n; i++) {
+                            double r = 0.0;
+                            for (int j = 0; j < pk; j++) r = r + c[i * pk + j];
+                            if (r != rs[i]) panic = true;
+                        }
+                        for (int j = 0; j < pk; j++) {
+                            double s = 0.0;
+                            for (int i = 0; i < n; i++) s = s + c[i * pk + j];
+                            if (s != cs[j]) panic = true;
+                        }
+                        if (!panic) p_ext += hypergeom_ratio_dev(c, cells, lp);
+                    }
+                if (panic) {
+                    status = PG_LOCUS_PANIC;  // assert! at fisher_exact_test.rs:113-114
+                } else {
+                    stat = p_obs;
+                    pval = p_obs + p_ext;
+                }
+            }
+        }
+        uint64_t mv = (uint64_t)status;
+        if (status == PG_LOCUS_OK) {
+            mv |= (uint64_t)pk << 8;
+            for (int a = 0; a < pk; a++) mv |= (uint64_t)p.codes[cols[a]] << (16 + 8 * a);
+        }
+        p.meta[locus] = mv;
+        double *o = p.stats + (size_t)locus * 4;
+        *reinterpret_cast<double2 *>(o) = make_double2(stat, nan(""));
+        *reinterpret_cast<double2 *>(o + 2) = make_double2(nan(""), pval);
+    }
+}
+
+cudaError_t launch_tables(const TableParams &p, int sm_count, cudaStream_t s) {
+    if (p.n > kTabMaxPools) return cudaErrorInvalidConfiguration;
+    static bool lf_ready[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!lf_ready[dev & 63]) {
+        double lf[36];
+        for (int x = 0; x < 36; x++) {
+            double out = 0.0;
+            for (int i = 2; i < x + 1; i++) out = out + log10((double)i);
+            lf[x] = out;
+        }
+        cudaError_t e = cudaMemcpyToSymbol(c_lf10, lf, sizeof lf);
+        if (e != cudaSuccess) return e;
+        lf_ready[dev & 63] = true;
+    }
+    const size_t smem = (size_t)kTabThreads * p.A_in * p.n * 4;
+    cudaError_t e = cudaFuncSetAttribute(tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t tiles = (p.n_loci + kTabThreads - 1) / kTabThreads;
+    int64_t grid = tiles < (int64_t)sm_count * 8 ? tiles : (int64_t)sm_count * 8;
+    if (grid < 1) grid = 1;
+    tables_kernel<<<(unsigned)grid, kTabThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace pg

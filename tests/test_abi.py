@@ -1,0 +1,68 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports exactly what include/poolgen_cuda.h
+declares, and fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import poolgen_b200 as pb
+from poolgen_b200 import capi
+from poolgen_b200.build import LIB_PATH, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    if not os.path.exists(LIB_PATH):
+        build()
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "poolgen_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = _header_functions()
+    assert sorted(capi.ABI_SYMBOLS) == declared
+    L = ctypes.CDLL(LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert capi.lib().pg_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pb.PgError) as e:
+        pb.Context(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "poolgen_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("no CPU oracle", ""), os.path.join(dirpath, f)
+
+
+def test_host_generator_is_deterministic_and_well_formed():
+    a = pb.synth_counts_host(0x5EED0002, 10, 2000, 100, 4)
+    b = pb.synth_counts_host(0x5EED0002, 10, 2000, 100, 4)
+    assert np.array_equal(a, b)
+    # shifting the window reproduces the same loci
+    c = pb.synth_counts_host(0x5EED0002, 510, 100, 100, 4)
+    assert np.array_equal(a[500:600], c)
+    depth = a.sum(axis=1)
+    assert depth.max() <= 100 and ((depth == 0) | (depth >= 20)).all()
+    zero_loci = (depth == 0).any(axis=1).mean()
+    mono = ((a > 0).any(axis=2).sum(axis=1) == 1).mean()
+    assert 0.005 < zero_loci < 0.04 and 0.03 < mono < 0.08
+    y = pb.synth_phen_host(1, 100, 3)
+    assert y.shape == (100, 3) and (np.abs(y) <= 3).all() and y.std() > 1.0

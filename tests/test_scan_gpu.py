@@ -1,0 +1,218 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+
+import poolgen_b200 as pb
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+C1_FILTERS = [
+    dict(),                                                        # CLI defaults (main.rs:80-93)
+    dict(min_coverage_depth=10, min_allele_frequency=0.01),        # the CI flag set (.github/workflows/rust.yml)
+    dict(min_allele_frequency=0.05),                               # q lands exactly on the threshold
+    dict(min_allele_frequency=0.1),
+    dict(min_coverage_depth=0, max_missingness_rate=0.5),          # NaN frequencies survive the depth filter
+]
+
+
+def _fs(pool_sizes, **kw):
+    return pb.FilterStats(pool_sizes=pool_sizes, **kw)
+
+
+@pytest.mark.parametrize("fkw", C1_FILTERS)
+@pytest.mark.parametrize("kind", [pb.KIND_OLS, pb.KIND_CORR])
+def test_c1_regression(ctx, kind, fkw):
+    c1 = H.load_c1()
+    fs = _fs(c1["pool_sizes"], **fkw)
+    scan = pb.Scan(ctx, kind, fs, 5, c1["codes"], c1["phen"])
+    dev = scan.run_counts(c1["counts"])
+    scan.close()
+    st = H.compare_regression(kind, c1["counts"], c1["codes"], c1["phen"], fs, dev, label=f"C1 {kind} {fkw}")
+    if not fkw:
+        assert st["kept"] == 6556  # SURVEY.md 8a F2 (restated filter on tests/test.sync)
+    if fkw == dict(min_coverage_depth=10, min_allele_frequency=0.01):
+        assert st["kept"] == 2032
+    print(st)
+
+
+@pytest.mark.parametrize("fkw", C1_FILTERS[:4])
+@pytest.mark.parametrize("kind", [pb.KIND_CHISQ, pb.KIND_FISHER])
+def test_c1_tables(ctx, kind, fkw):
+    c1 = H.load_c1()
+    fs = _fs(c1["pool_sizes"], **fkw)
+    scan = pb.Scan(ctx, kind, fs, 5, c1["codes"])
+    dev = scan.run_counts(c1["counts"])
+    scan.close()
+    print(H.compare_tables(kind, c1["counts"], c1["codes"], fs, dev, label=f"C1 tables {kind} {fkw}"))
+
+
+SHAPES = [
+    # n_pools, n_alleles, k, loci, weighted
+    (100, 4, 1, 20000, False),   # C2 shape
+    (1000, 4, 3, 1500, False),   # C3 shape
+    (37, 4, 2, 4000, True),      # odd pool count, unequal pool sizes
+    (129, 5, 4, 1500, False),    # one row past a chunk boundary, D column present
+    (257, 6, 5, 600, True),      # N column dropped on the device, k > 4 (two phenotype passes)
+    (8, 2, 1, 3000, False),      # biallelic
+    (64, 3, 3, 3000, False),
+]
+
+
+@pytest.mark.parametrize("n,A,k,L,weighted", SHAPES)
+@pytest.mark.parametrize("kind", [pb.KIND_OLS, pb.KIND_CORR])
+def test_synthetic_regression(ctx, kind, n, A, k, L, weighted):
+    seed = 0x5EED0000 + n * 7 + A
+    counts = pb.synth_counts_host(seed, 0, L, n, A)
+    phen = pb.synth_phen_host(seed, n, k)
+    ps = np.ones(n)
+    if weighted:
+        ps = 10.0 + (np.arange(n) % 7)
+    tot = 0.0
+    for v in ps:
+        tot = tot + v
+    ps = np.array([v / tot for v in ps])
+    fs = _fs(ps)
+    codes = np.arange(A, dtype=np.uint8)
+    scan = pb.Scan(ctx, kind, fs, n, codes, phen)
+    dev = scan.run_counts(counts)
+    scan.close()
+    st = H.compare_regression(kind, counts, codes, phen, fs, dev, label=f"synth n={n} A={A} k={k}")
+    assert st["ok"] > 0.8 * L * (0.5 if A < 4 else 1.0) or A < 4
+    print(st)
+
+
+def test_device_generator_matches_host(ctx):
+    n, A, k, L = 100, 4, 1, 5000
+    seed = 0x5EED0002
+    phen = pb.synth_phen_host(seed, n, k)
+    fs = _fs(np.full(n, 1.0 / n))
+    scan = pb.Scan(ctx, pb.KIND_OLS, fs, n, np.arange(A, dtype=np.uint8), phen)
+    b = scan.batch(L)
+    b.synth(seed, 123, L)
+    b.run()
+    dev_synth = b.fetch()
+    counts = pb.synth_counts_host(seed, 123, L, n, A)
+    b.upload_counts(counts)
+    b.run()
+    dev_host = b.fetch()
+    b.close()
+    scan.close()
+    assert (dev_synth.status == dev_host.status).all()
+    assert np.array_equal(dev_synth.stats, dev_host.stats, equal_nan=True)
+
+
+def test_upload_formats_agree(ctx):
+    """u32 counts, u16 counts and the host-built f64 frequency matrix give identical records."""
+    n, A, k, L = 100, 4, 2, 3000
+    seed = 77
+    counts = pb.synth_counts_host(seed, 0, L, n, A)
+    phen = pb.synth_phen_host(seed, n, k)
+    fs = _fs(np.full(n, 1.0 / n))
+    scan = pb.Scan(ctx, pb.KIND_OLS, fs, n, np.arange(A, dtype=np.uint8), phen)
+    b = scan.batch(L)
+    b.upload_counts(counts)
+    b.run()
+    r32 = b.fetch()
+    b.upload_counts(counts.astype(np.uint16))
+    b.run()
+    r16 = b.fetch()
+    depth = counts.sum(axis=1).astype(np.uint32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        freq = counts.astype(np.float64) / depth[:, None, :].astype(np.float64)
+    b.upload_freq(freq, depth)
+    b.run()
+    rf = b.fetch()
+    b.close()
+    scan.close()
+    for r in (r16, rf):
+        assert (r.status == r32.status).all()
+        assert np.array_equal(r.stats, r32.stats, equal_nan=True)
+        assert np.array_equal(r.freq_mean, r32.freq_mean, equal_nan=True)
+
+
+def test_streaming_matches_batch(ctx):
+    n, A, k, L = 64, 4, 1, 9000
+    counts = pb.synth_counts_host(5, 0, L, n, A)
+    phen = pb.synth_phen_host(5, n, k)
+    fs = _fs(np.full(n, 1.0 / n))
+    scan = pb.Scan(ctx, pb.KIND_CORR, fs, n, np.arange(A, dtype=np.uint8), phen)
+    whole = scan.run_counts(counts)
+    scan.stream_begin(2048)
+    tickets, parts = [], []
+    for i, l0 in enumerate(range(0, L, 2048)):
+        slab = np.ascontiguousarray(counts[l0:l0 + 2048])
+        tickets.append((scan.submit_counts(slab), slab))
+        if len(tickets) == 3:
+            t, _ = tickets.pop(0)
+            parts.append(scan.collect(t))
+    for t, _ in tickets:
+        parts.append(scan.collect(t))
+    scan.close()
+    status = np.concatenate([p.status for p in parts])
+    stats = np.concatenate([p.stats for p in parts])
+    assert (status == whole.status).all()
+    assert np.array_equal(stats, whole.stats, equal_nan=True)
+
+
+def test_empty_and_tiny_batches(ctx):
+    n, A = 10, 4
+    phen = pb.synth_phen_host(1, n, 1)
+    fs = _fs(np.full(n, 1.0 / n))
+    scan = pb.Scan(ctx, pb.KIND_OLS, fs, n, np.arange(A, dtype=np.uint8), phen)
+    r0 = scan.run_counts(np.zeros((0, A, n), dtype=np.uint32))
+    assert r0.status.size == 0
+    counts = pb.synth_counts_host(9, 0, 1, n, A)
+    r1 = scan.run_counts(counts)
+    H.compare_regression(pb.KIND_OLS, counts, np.arange(A, dtype=np.uint8), phen, fs, r1, label="single locus")
+    # all-zero counts: every pool has no coverage
+    z = np.zeros((3, A, n), dtype=np.uint32)
+    rz = scan.run_counts(z)
+    assert (rz.status == pb.LOCUS_FILTERED).all()
+    scan.close()
+
+
+def test_c5_tables_synthetic(ctx):
+    """config C5 shape: 2 pools, count path, depth 20..100 so Fisher's > 34 rescale is exercised."""
+    n, A, L = 2, 4, 20000
+    counts = pb.synth_counts_host(0x5EED0005, 0, L, n, A)
+    fs = _fs(np.full(n, 0.5))
+    codes = np.arange(A, dtype=np.uint8)
+    for kind in (pb.KIND_CHISQ, pb.KIND_FISHER):
+        scan = pb.Scan(ctx, kind, fs, n, codes)
+        dev = scan.run_counts(counts)
+        scan.close()
+        print(H.compare_tables(kind, counts, codes, fs, dev, label=f"C5 {kind}"))
+
+
+def test_full_size_c2_properties(ctx):
+    """C2 at full size (100 pools x 1M loci): sampled loci against the oracle (host replay of the integer
+    generator) and a split-invariance property: scanning two halves gives the bits of the whole."""
+    n, A, k, L = 100, 4, 1, 1_000_000
+    seed = 0x5EED0002
+    phen = pb.synth_phen_host(seed, n, k)
+    fs = _fs(np.full(n, 1.0 / n))
+    codes = np.arange(A, dtype=np.uint8)
+    scan = pb.Scan(ctx, pb.KIND_OLS, fs, n, codes, phen)
+    b = scan.batch(L)
+    b.synth(seed, 0, L)
+    b.run()
+    whole = b.fetch()
+    # sampled windows against the oracle
+    for l0 in (0, 333_333, L - 4096):
+        counts = pb.synth_counts_host(seed, l0, 4096, n, A)
+        sub = pb.ScanResults(whole.status[l0:l0 + 4096], whole.n_out[l0:l0 + 4096], whole.alleles[l0:l0 + 4096],
+                             whole.freq_mean[l0:l0 + 4096], whole.stats[l0:l0 + 4096])
+        H.compare_regression(pb.KIND_OLS, counts, codes, phen, fs, sub, label=f"C2 window {l0}")
+    # split invariance
+    half = L // 2
+    b.synth(seed, half, half)
+    b.run()
+    second = b.fetch()
+    assert (second.status == whole.status[half:]).all()
+    assert np.array_equal(second.stats, whole.stats[half:], equal_nan=True)
+    # sanity of the class mix of the generator: ~5 % monomorphic + ~2 % zero-depth loci are filtered
+    frac = (whole.status == pb.LOCUS_FILTERED).mean()
+    assert 0.04 < frac < 0.12, frac
+    b.close()
+    scan.close()
