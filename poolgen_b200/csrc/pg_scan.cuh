@@ -238,10 +238,144 @@ __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const
     return PG_LOCUS_OK;
 }
 
-__device__ __forceinline__ uint64_t pack_sel(int status, int nslots, const int *cols) {
-    uint64_t v = (uint64_t)(status & 0xff) | ((uint64_t)(nslots & 0xff) << 8);
+__device__ __forceinline__ uint64_t pack_sel(int status, int nslots, const int *cols, unsigned kept) {
+    uint64_t v = (uint64_t)(status & 0xff) | ((uint64_t)(nslots & 0xff) << 8) | ((uint64_t)(kept & 0x3f) << 40);
     for (int s = 0; s < PG_MAX_SLOTS; s++) v |= (uint64_t)(cols[s] & 0xf) << (16 + 4 * s);
     return v;
+}
+
+// Cholesky of the m x m SPD matrix S (lower triangle filled) -> Li = L^-1 (lower), dg = diag(S^-1)
+__device__ __forceinline__ bool chol_inv(int m, const double (&S)[PG_MAX_SLOTS][PG_MAX_SLOTS],
+                                         double (&Li)[PG_MAX_SLOTS][PG_MAX_SLOTS], double (&dg)[PG_MAX_SLOTS]) {
+    double Lm[PG_MAX_SLOTS][PG_MAX_SLOTS];
+    bool ok = true;
+    for (int a = 0; a < m; a++)
+        for (int b = 0; b <= a; b++) {
+            double s = S[a][b];
+            for (int c = 0; c < b; c++) s -= Lm[a][c] * Lm[b][c];
+            if (a == b) {
+                if (!(s > 0.0)) {
+                    ok = false;
+                    s = 1.0;
+                }
+                Lm[a][a] = sqrt(s);
+            } else {
+                Lm[a][b] = s / Lm[b][b];
+            }
+        }
+    for (int a = 0; a < m; a++) {
+        Li[a][a] = 1.0 / Lm[a][a];
+        for (int b = 0; b < a; b++) {
+            double s = 0.0;
+            for (int c = b; c < a; c++) s -= Lm[a][c] * Li[c][b];
+            Li[a][b] = s / Lm[a][a];
+        }
+    }
+    for (int b = 0; b < m; b++) {
+        double s = 0.0;
+        for (int a = b; a < m; a++) s += Li[a][b] * Li[a][b];
+        dg[b] = s;
+    }
+    return ok;
+}
+
+// beta_k = S^-1 sxy_k through Li; returns z'z (= beta' sxy)
+__device__ __forceinline__ double solve_rhs(int m, const double (&Li)[PG_MAX_SLOTS][PG_MAX_SLOTS],
+                                            const double (&sxy)[PG_MAX_SLOTS], double (&beta)[PG_MAX_SLOTS]) {
+    double z[PG_MAX_SLOTS];
+    double zz = 0.0;
+    for (int a = 0; a < m; a++) {
+        double s = 0.0;
+        for (int b = 0; b <= a; b++) s += Li[a][b] * sxy[b];
+        z[a] = s;
+        zz += s * s;
+    }
+    for (int b = 0; b < m; b++) {
+        double s = 0.0;
+        for (int a = b; a < m; a++) s += Li[a][b] * z[a];
+        beta[b] = s;
+    }
+    return zz;
+}
+
+// Reference-style two-pass evaluation of one locus straight from global memory (explicit centred moments, explicit
+// residuals e = y - Xb as src/gwas/ols.rs:98-104): used when the single-pass Gram form would lose digits to
+// cancellation (near-perfect fits, nearly constant or nearly collinear allele columns).  One lane per locus.
+template <int A, int K>
+__device__ __noinline__ int explicit_locus(const ScanParams &p, int64_t locus, unsigned kept, int m, const int *cols,
+                                           const double *xbar, const double *ys, double *tbg) {
+    const Layout &lay = p.lay;
+    const double *fl = p.freq + (size_t)locus * lay.freq_stride();
+    const uint32_t *dl = p.depth + (size_t)locus * lay.depth_stride();
+    const double nn = (double)lay.n;
+    double S[PG_MAX_SLOTS][PG_MAX_SLOTS], sxy[K][PG_MAX_SLOTS], ybar[K];
+    for (int a = 0; a < PG_MAX_SLOTS; a++) {
+        for (int b = 0; b < PG_MAX_SLOTS; b++) S[a][b] = 0.0;
+        for (int k = 0; k < K; k++) sxy[k][a] = 0.0;
+    }
+    for (int k = 0; k < K; k++) ybar[k] = p.ysum[k] / nn;
+    for (int pass = 0; pass < 2; pass++) {
+        double Li[PG_MAX_SLOTS][PG_MAX_SLOTS], dg[PG_MAX_SLOTS], beta[K][PG_MAX_SLOTS], rss[K];
+        if (pass == 1) {
+            if (p.kind == PG_KIND_OLS) {
+                if (!chol_inv(m, S, Li, dg)) return PG_LOCUS_FAILED;
+                for (int k = 0; k < K; k++) {
+                    solve_rhs(m, Li, sxy[k], beta[k]);
+                    rss[k] = 0.0;
+                }
+            } else {
+                for (int a = 0; a < m; a++)
+                    for (int k = 0; k < K; k++) {
+                        tbg[(a * K + k) * 2 + 0] = sxy[k][a] / (sqrt(S[a][a]) * sqrt(p.syy[k]));
+                        tbg[(a * K + k) * 2 + 1] = 0.0;
+                    }
+                return PG_LOCUS_OK;
+            }
+        }
+        int i0 = 0;
+        for (int c = 0; c < lay.n_chunks; c++) {
+            const int rcc = (c == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
+            const double *blk = fl + (size_t)c * lay.A * lay.rc;
+            const int rows = min(rcc, lay.n - i0);
+            for (int r = 0; r < rows; r++) {
+                double f[A], F[A], x[PG_MAX_SLOTS];
+#pragma unroll
+                for (int j = 0; j < A; j++) f[j] = blk[(size_t)j * rcc + r];
+                renorm_row<A>(f, dl[i0 + r], kept, F);
+                for (int a = 0; a < m; a++) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int j = 0; j < A; j++)
+                        if (j == cols[a]) v = F[j];
+                    x[a] = v - xbar[a];
+                }
+                if (pass == 0) {
+                    for (int a = 0; a < m; a++) {
+                        for (int b = 0; b <= a; b++) S[a][b] = fma(x[a], x[b], S[a][b]);
+                        for (int k = 0; k < K; k++) sxy[k][a] = fma(x[a], ys[k * lay.n_pad + i0 + r] - ybar[k], sxy[k][a]);
+                    }
+                } else {
+                    for (int k = 0; k < K; k++) {
+                        double e = ys[k * lay.n_pad + i0 + r] - ybar[k];
+                        for (int a = 0; a < m; a++) e -= beta[k][a] * x[a];
+                        rss[k] = fma(e, e, rss[k]);
+                    }
+                }
+            }
+            i0 += rcc;
+        }
+        if (pass == 1) {
+            const double dfe = nn - (double)(m + 1);
+            for (int k = 0; k < K; k++) {
+                const double ve = rss[k] / dfe;
+                for (int b = 0; b < m; b++) {
+                    tbg[(b * K + k) * 2 + 0] = beta[k][b];
+                    tbg[(b * K + k) * 2 + 1] = ve * dg[b];
+                }
+            }
+        }
+    }
+    return PG_LOCUS_OK;
 }
 
 template <int A, int K, bool W>
@@ -473,7 +607,7 @@ __global__ void __launch_bounds__((Acc<A, K, W>::NB == 1 ? 12 : 8) * 32, 1) scan
                             }
                         }
                     }
-                    if (lane == 0) sel[g] = pack_sel(status, nslots, cols);
+                    if (lane == 0) sel[g] = pack_sel(status, nslots, cols, kept);
                 }
             }
         }
@@ -518,83 +652,62 @@ __global__ void __launch_bounds__((Acc<A, K, W>::NB == 1 ? 12 : 8) * 32, 1) scan
                     has_nan |= (pjj != pjj);
                     fmean[a] = (pjj != pjj) ? nan("") : sx[a] / nn;
                 }
+                const unsigned keptm = (unsigned)((sv >> 40) & 0x3f);
+                double xbar[PG_MAX_SLOTS];
+                for (int a = 0; a < m; a++) xbar[a] = sx[a] / nn;
                 if (p.kind == PG_KIND_OLS) {
                     if (lay.n < m + 1) {
                         status = PG_LOCUS_UNSUPPORTED;
                     } else if (has_nan) {
                         for (int i = 0; i < m * K * 2; i++) tbg[i] = nan("");
                     } else {
-                        double Lm[PG_MAX_SLOTS][PG_MAX_SLOTS];
-                        bool ok = true;
+                        double S[PG_MAX_SLOTS][PG_MAX_SLOTS], Li[PG_MAX_SLOTS][PG_MAX_SLOTS], dg[PG_MAX_SLOTS];
+                        double amp = 1.0;
                         for (int a = 0; a < m; a++)
                             for (int b = 0; b <= a; b++) {
                                 const int ca = cols[a], cb = cols[b];
                                 const int lo = ca < cb ? ca : cb, hi = ca < cb ? cb : ca;
-                                double s = tg[AC::tri(lo, hi)] - sx[a] * sx[b] / nn;
-                                for (int c = 0; c < b; c++) s -= Lm[a][c] * Lm[b][c];
-                                if (a == b) {
-                                    if (!(s > 0.0)) {
-                                        ok = false;
-                                        s = 1.0;
-                                    }
-                                    Lm[a][a] = sqrt(s);
-                                } else {
-                                    Lm[a][b] = s / Lm[b][b];
-                                }
+                                const double raw = tg[AC::tri(lo, hi)];
+                                S[a][b] = raw - sx[a] * sx[b] / nn;
+                                if (a == b) amp = fmax(amp, raw / S[a][a]);
                             }
-                        if (!ok) {
-                            status = PG_LOCUS_FAILED;
-                        } else {
-                            // inverse of L (lower), diag of Sxx^-1 = column sums of squares of L^-1
-                            double Li[PG_MAX_SLOTS][PG_MAX_SLOTS];
-                            for (int a = 0; a < m; a++) {
-                                Li[a][a] = 1.0 / Lm[a][a];
-                                for (int b = 0; b < a; b++) {
-                                    double s = 0.0;
-                                    for (int c = b; c < a; c++) s -= Lm[a][c] * Li[c][b];
-                                    Li[a][b] = s / Lm[a][a];
-                                }
-                            }
-                            double dg[PG_MAX_SLOTS];
-                            for (int b = 0; b < m; b++) {
-                                double s = 0.0;
-                                for (int a = b; a < m; a++) s += Li[a][b] * Li[a][b];
-                                dg[b] = s;
-                            }
+                        bool ok = chol_inv(m, S, Li, dg);
+                        bool redo = !ok || !(amp > 0.0);
+                        if (ok) {
+                            double vif = 1.0;
+                            for (int a = 0; a < m; a++) vif = fmax(vif, S[a][a] * dg[a]);
                             const double dfe = nn - (double)(m + 1);
                             for (int k = 0; k < K; k++) {
-                                double z[PG_MAX_SLOTS];
-                                double zz = 0.0;
-                                for (int a = 0; a < m; a++) {
-                                    double s = 0.0;
-                                    for (int b = 0; b <= a; b++) {
-                                        const double sxy = tg[AC::C0 + cols[b] * K + k] - sx[b] * p.ysum[k] / nn;
-                                        s += Li[a][b] * sxy;
-                                    }
-                                    z[a] = s;
-                                    zz += s * s;
-                                }
+                                double sxy[PG_MAX_SLOTS], beta[PG_MAX_SLOTS];
+                                for (int b = 0; b < m; b++)
+                                    sxy[b] = tg[AC::C0 + cols[b] * K + k] - sx[b] * p.ysum[k] / nn;
+                                const double zz = solve_rhs(m, Li, sxy, beta);
                                 double rss = p.syy[k] - zz;
+                                // digits lost by the single-pass form: centring (amp), collinearity (vif) and syy - zz
+                                if (!(64.0 * kEps * (amp * vif * zz + p.syy[k]) <= 1e-10 * rss)) redo = true;
                                 if (rss < 0.0) rss = 0.0;
                                 const double ve = rss / dfe;
                                 for (int b = 0; b < m; b++) {
-                                    double s = 0.0;
-                                    for (int a = b; a < m; a++) s += Li[a][b] * z[a];
-                                    tbg[(b * K + k) * 2 + 0] = s;
+                                    tbg[(b * K + k) * 2 + 0] = beta[b];
                                     tbg[(b * K + k) * 2 + 1] = ve * dg[b];
                                 }
                             }
                         }
+                        if (redo) status = explicit_locus<A, K>(p, locus, keptm, m, cols, xbar, ys, tbg);
                     }
                 } else {
+                    bool redo = false;
                     for (int a = 0; a < m; a++) {
-                        const double sxx = tg[AC::tri(cols[a], cols[a])] - sx[a] * sx[a] / nn;
+                        const double raw = tg[AC::tri(cols[a], cols[a])];
+                        const double sxx = raw - sx[a] * sx[a] / nn;
+                        if (!(raw <= 1e4 * sxx)) redo = true;
                         for (int k = 0; k < K; k++) {
                             const double sxy = tg[AC::C0 + cols[a] * K + k] - sx[a] * p.ysum[k] / nn;
                             tbg[(a * K + k) * 2 + 0] = sxy / (sqrt(sxx) * sqrt(p.syy[k]));
                             tbg[(a * K + k) * 2 + 1] = 0.0;
                         }
                     }
+                    if (redo && !has_nan) explicit_locus<A, K>(p, locus, keptm, m, cols, xbar, ys, tbg);
                 }
                 if (status != PG_LOCUS_OK) sel[g] = (sv & ~(uint64_t)0xff) | (uint64_t)status;
             }
