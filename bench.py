@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- loci/s of the `ols_iter` per-locus scan (f64) on 1..8 B200, with its HBM roofline.
+
+Workload (BASELINE.json configs[2], "C3"): synthetic sync counts, 1,000 pools x 10,000,000 loci x 4 alleles,
+3 phenotypes, sharded over 8 GPUs = 1,250,000 loci per GPU.  The full matrix (323 GB of f64) does not fit one GPU,
+so the bench is WEAK-scaled: every rank holds one 1.25M-locus shard (45 GB resident in HBM, generated on the
+device by the integer-hash generator the CPU oracle can replay); at --gpus 8 the job is exactly C3.
+A step = one pass of the scan kernel over the rank's resident shard (inputs 45 GB >> 126 MB L2, so no flush).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--loci-per-gpu L]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POOLS, N_ALLELES, N_PHEN = 1000, 4, 3
+LOCI_PER_GPU = 1_250_000
+SEED = 0x5EED0003
+ALG_BYTES_PER_LOCUS = 8 * N_POOLS * N_ALLELES + 32 * (N_ALLELES - 1) * N_PHEN  # 32,288 B
+METRIC = "loci/sec for ols_iter (f64)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 9:
+                self.rows.append(f)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for f in self.rows:
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def cpu_reference_rate(seconds_target: float, n_threads: int, warm: bool = True):
+    """The reference's CPU path restated (oracle/poolgen_oracle.c, per-locus allocation structure and one OS thread
+    per contiguous locus range like src/base/sync.rs:917-939) timed on a bounded sample of the SAME workload."""
+    from oracle import pgo
+    import poolgen_b200 as pb
+    phen = pb.synth_phen_host(SEED, N_POOLS, N_PHEN)
+    fs = pgo.FilterStats(pool_sizes=np.full(N_POOLS, 1.0 / N_POOLS))
+    codes = np.arange(N_ALLELES, dtype=np.uint8)
+    probe = 256 * n_threads
+    counts = pb.synth_counts_host(SEED, 0, probe, N_POOLS, N_ALLELES)
+    t0 = time.perf_counter()
+    pgo.scan_batch(pgo.SCAN_OLS, counts, codes, phen, fs, n_threads)
+    dt = time.perf_counter() - t0
+    rate = probe / dt
+    sample = int(max(probe, min(400_000, rate * seconds_target)))
+    sample -= sample % n_threads
+    counts = pb.synth_counts_host(SEED, 0, sample, N_POOLS, N_ALLELES)
+
+    def step():
+        t0 = time.perf_counter()
+        pgo.scan_batch(pgo.SCAN_OLS, counts, codes, phen, fs, n_threads)
+        return time.perf_counter() - t0
+    return step, sample
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    n_threads = os.cpu_count() or 1
+    step, sample = cpu_reference_rate(4.0, n_threads)
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    total = sum(times)
+    value = sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C3 ols_iter: {N_POOLS} pools x 4 alleles x {N_PHEN} phenotypes; CPU arm times a "
+                               f"bounded sample of {sample} loci per step (in-memory counts, parsing and CSV excluded)"},
+        "cpu_baseline": {"value": value, "unit": "loci/s", "cores": n_threads, "kind": "port",
+                         "sample": f"{sample} loci of the C3 shape per step, {n_threads} OS threads over contiguous locus ranges"},
+        "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_cuda(args):
+    import torch
+    import poolgen_b200 as pb
+    rank, local, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+        torch.cuda.set_device(local)
+    ctx = pb.Context(local)
+    L = args.loci_per_gpu
+    phen = pb.synth_phen_host(SEED, N_POOLS, N_PHEN)
+    fs = pb.FilterStats(pool_sizes=np.full(N_POOLS, 1.0 / N_POOLS))
+    codes = np.arange(N_ALLELES, dtype=np.uint8)
+    scan = pb.Scan(ctx, pb.KIND_OLS, fs, N_POOLS, codes, phen)
+    batch = scan.batch(L)
+    batch.synth(SEED, rank * L, L)  # this rank's contiguous locus range of the 10M-locus job
+    batch.sync()
+    in_bytes, out_bytes = batch.bytes()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch.time_runs(max(3, args.warmup))  # warm-up (>= 3 passes)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ms, launches = batch.time_runs(args.steps)  # CUDA events on the stream the kernels are launched on
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * L * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers: pinned counts -> H2D -> ingest -> scan -> D2H records
+    slab = args.e2e_slab
+    n_slabs = args.e2e_slabs
+    host, hptr = ctx.pinned_empty((3, slab, N_ALLELES, N_POOLS), np.uint16)
+    for i in range(3):
+        host[i] = pb.synth_counts_host(SEED, rank * L + i * slab, slab, N_POOLS, N_ALLELES).astype(np.uint16)
+    scan.stream_begin(slab)
+    for i in range(3):  # warm-up
+        scan.collect(scan.submit_counts(host[i]), copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    pending = []
+    kept = 0
+    for i in range(n_slabs):
+        pending.append(scan.submit_counts(host[i % 3]))
+        if len(pending) == 3:
+            r = scan.collect(pending.pop(0), copy=False)
+            kept += int(r.n_loci)
+    while pending:
+        r = scan.collect(pending.pop(0), copy=False)
+        kept += int(r.n_loci)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * slab * n_slabs / float(te.item())
+    h2d = slab * N_ALLELES * N_POOLS * 2
+    d2h = slab * (8 + 8 * (N_ALLELES - 1) + 32 * (N_ALLELES - 1) * N_PHEN)
+    ctx.pinned_free(hptr)
+
+    # sanity on the results of the timed scan (not a parity test: tests/ does that)
+    batch.download()
+    batch.sync()
+    rv = batch.results_view()
+    meta = np.ctypeslib.as_array(rv.meta, shape=(L,))
+    ok_frac = float(((meta & 0xFF) == pb.LOCUS_OK).mean())
+
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        extras = c2_numbers(ctx, pb)
+    batch.close()
+    scan.close()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        per_launch_ms = ms / launches
+        achieved = ALG_BYTES_PER_LOCUS * L / (per_launch_ms * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            n_threads = os.cpu_count() or 1
+            step, sample = cpu_reference_rate(12.0, n_threads)
+            dt = step()
+            cpu = {"value": sample / dt, "unit": "loci/s", "cores": n_threads, "kind": "port",
+                   "sample": f"{sample} loci of the C3 shape (1000 pools x 4 alleles, 3 phenotypes), in-memory counts, "
+                             f"{n_threads} OS threads over contiguous locus ranges, {dt:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3 ols_iter shard: {N_POOLS} pools x {L} loci/GPU x {N_ALLELES} alleles, "
+                                   f"{N_PHEN} phenotypes (8 GPUs = the 10M-locus job)",
+                       "l2": f"inputs {in_bytes / 1e9:.1f} GB per pass >> 126 MB L2, no flush needed",
+                       "filters": "CLI defaults: min depth 1, MAF 0.001, missingness 0", "ok_fraction": ok_frac,
+                       "e2e_format": f"u16 counts, slabs of {slab} loci, depth-3 pipeline, {n_slabs} slabs"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_locus": ALG_BYTES_PER_LOCUS,
+                         "resident_input_bytes_per_locus": in_bytes / L, "kernel_ms": per_launch_ms},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "extras": extras,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def c2_numbers(ctx, pb):
+    """BASELINE.json configs[1] (C2): 100 pools x 1M loci x 4 alleles, 1 phenotype, ols_iter + pearson_corr."""
+    out = {}
+    n, A, k, L = 100, 4, 1, 1_000_000
+    phen = pb.synth_phen_host(0x5EED0002, n, k)
+    fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n))
+    peak, _ = measured_peaks()
+    alg = 8 * n * A + 32 * (A - 1) * k
+    for name, kind in (("c2_ols_iter", pb.KIND_OLS), ("c2_pearson_corr", pb.KIND_CORR)):
+        scan = pb.Scan(ctx, kind, fs, n, np.arange(A, dtype=np.uint8), phen)
+        b = scan.batch(L)
+        b.synth(0x5EED0002, 0, L)
+        b.time_runs(5)
+        ms, nl = b.time_runs(20)
+        per = ms / nl
+        out[name] = {"loci_per_s": L / (per * 1e-3), "kernel_ms": per,
+                     "roofline_frac": alg * L / (per * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_locus": alg,
+                     "note": "3.3 GB input > L2 (126 MB)"}
+        b.close()
+        scan.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--loci-per-gpu", type=int, default=LOCI_PER_GPU)
+    ap.add_argument("--e2e-slab", type=int, default=16384)
+    ap.add_argument("--e2e-slabs", type=int, default=24)
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

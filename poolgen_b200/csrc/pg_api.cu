@@ -2,12 +2,14 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <new>
 
 #include "pg_internal.h"
+#include "pg_ptable.h"
 
 namespace pg {
 cudaError_t launch_scan_a2(const ScanParams &, int, cudaStream_t);
@@ -209,6 +211,23 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
             delete s;
             return fail(ctx, PG_ERR_UNSUPPORTED, "pg_scan_open: %d pools exceed the shared-memory resident phenotype budget", n);
         }
+        const char *pv_mode = getenv("PG_PVALUE");
+        if (s->df > 0.0 && !(pv_mode && strcmp(pv_mode, "cf") == 0)) {
+            pg::PTable tab = pg::build_ptable(s->df);
+            if (tab.max_err < 2e-9) {  // otherwise keep the continued fraction
+                cudaError_t et = cudaMalloc(&s->d_ptab, tab.coef.size() * 8);
+                if (et == cudaSuccess)
+                    et = cudaMemcpy(s->d_ptab, tab.coef.data(), tab.coef.size() * 8, cudaMemcpyHostToDevice);
+                if (et != cudaSuccess) {
+                    delete s;
+                    return fail(ctx, PG_ERR_CUDA, "pg_scan_open: p-value table upload: %s", cudaGetErrorString(et));
+                }
+                s->ptab_M = tab.M;
+                s->ptab_vmax = tab.v_max;
+                s->ptab_inv_h = tab.inv_h;
+                s->ptab_err = tab.max_err;
+            }
+        }
         cudaError_t e = cudaMalloc(&s->d_yc, s->yc_host.size() * 8);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_yc, s->yc_host.data(), s->yc_host.size() * 8, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
@@ -235,6 +254,7 @@ int pg_scan_close(pg_scan *s) {
         if (s->slabs[i]) pg_batch_destroy(s->slabs[i]);
     if (s->d_yc) cudaFree(s->d_yc);
     if (s->d_w) cudaFree(s->d_w);
+    if (s->d_ptab) cudaFree(s->d_ptab);
     delete s;
     return PG_OK;
 }
@@ -429,6 +449,10 @@ static int run_once(pg_batch *b, int *launches) {
             p.w_uniform = s->w_uniform;
             p.df = s->df;
             p.ln_beta = s->ln_beta;
+            p.ptab = s->d_ptab;
+            p.ptab_vmax = s->ptab_vmax;
+            p.ptab_inv_h = s->ptab_inv_h;
+            p.ptab_M = s->ptab_M;
             p.K = std::min(pg::kMaxPhenPerPass, s->k - base);
             p.yc = s->d_yc + (size_t)base * s->lay.n_pad;
             p.w = s->d_w;

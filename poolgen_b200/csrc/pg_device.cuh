@@ -122,6 +122,31 @@ __device__ __forceinline__ double student_two_sided(double t_abs, double df, dou
     return 2.0 * (1.0 - cdf);
 }
 
+// Same quantity through the per-scan table of ln p(v), v = sqrt(log1p(t^2/df)) (pg_ptable.h).  The final
+// 2 * (1 - (1 - ib)) reproduces the reference's quantisation of small p-values.
+struct PTableDev {
+    const double4 *coef;
+    double v_max, inv_h;
+    int M;
+};
+__device__ __forceinline__ double student_two_sided_tab(double t_abs, double df, const PTableDev &tb) {
+    const double z = t_abs * t_abs / df;
+    const double v = sqrt(log1p(z));
+    double ptrue = 0.0;
+    if (v < tb.v_max) {
+        const double pos = v * tb.inv_h;
+        int i = (int)pos;
+        if (i > tb.M - 1) i = tb.M - 1;
+        const double s = pos - (double)i;
+        const double2 *cp = reinterpret_cast<const double2 *>(tb.coef + i);
+        const double2 c01 = __ldg(cp), c23 = __ldg(cp + 1);
+        ptrue = exp(fma(s, fma(s, fma(s, c23.y, c23.x), c01.y), c01.x));
+    }
+    const double ib = 0.5 * ptrue;
+    const double cdf = t_abs <= 0.0 ? ib : 1.0 - ib;
+    return 2.0 * (1.0 - cdf);
+}
+
 // statrs ln_gamma (Lanczos g = 10.900511, 11 terms), needed on the device only for chi-square
 __device__ inline double ln_gamma_dev(double x) {
     const double dk[11] = {2.48574089138753565546e-5,  1.05142378581721974210,     -3.45687097222016235469,

@@ -70,6 +70,9 @@ struct ScanParams {
     double w_uniform;     // s_0 / sum(s) when all weights are equal
     double df;            // Student-t degrees of freedom (n-1 ols, n-2 corr)
     double ln_beta;       // lnG(df/2 + 1/2) - lnG(df/2) - lnG(1/2)
+    const void *ptab;     // per-scan table of ln p(v) (double4 per interval), NULL = continued fraction on the device
+    double ptab_vmax, ptab_inv_h;
+    int ptab_M;
     const double *yc;     // [K][n_pad] centred phenotypes of this pass (device)
     const double *w;      // [n_pad] s_i / sum(s) (device)
     double ysum[kMaxPhenPerPass];  // sum of the centred phenotype (rounding residue)
@@ -196,6 +199,9 @@ struct pg_scan {
     double df = 0, ln_beta = 0;
     double *d_yc = nullptr;
     double *d_w = nullptr;
+    double *d_ptab = nullptr;
+    double ptab_vmax = 0, ptab_inv_h = 0, ptab_err = 0;
+    int ptab_M = 0;
     int n_slots = 0;
     // streaming
     pg_batch *slabs[PG_STREAM_DEPTH] = {nullptr, nullptr, nullptr};

@@ -20,6 +20,7 @@
 namespace pg {
 
 constexpr int kNBuf = 3;
+constexpr int kRedPitchDecl = 33;
 constexpr int kBufRows = kChunkRows;
 
 template <int A, int K, bool W>
@@ -64,12 +65,14 @@ struct WarpSmem {
     static constexpr int tot_bytes = G * AC::NP * 8;
     static constexpr int sel_bytes = ((G * 8 + 15) / 16) * 16;
     static constexpr int tb_bytes = G * T * 16;
+    static constexpr int red_bytes = (AC::N < 32 ? AC::N : 32) * kRedPitchDecl * 8;
     static constexpr int off_f = bar_bytes;
     static constexpr int off_d = off_f + kNBuf * fbuf_bytes;
     static constexpr int off_tot = off_d + kNBuf * dbuf_bytes;
     static constexpr int off_sel = off_tot + tot_bytes;
     static constexpr int off_tb = off_sel + sel_bytes;
-    static constexpr int bytes = ((off_tb + tb_bytes + 127) / 128) * 128;
+    static constexpr int off_red = off_tb + tb_bytes;
+    static constexpr int bytes = ((off_red + red_bytes + 127) / 128) * 128;
 };
 
 __host__ __device__ inline size_t scan_common_bytes(int K, int n_pad, bool weighted) {
@@ -102,15 +105,31 @@ __device__ __forceinline__ void accum_row(double (&acc)[Acc<A, K, W>::NP], const
     }
 }
 
-template <int NP>
-__device__ __forceinline__ void reduce_store(double (&acc)[NP], double *tot, int lane) {
+// Warp reduction of the N accumulators through shared memory: every lane stores its partial sums into a
+// [accumulator][lane] tile (row pitch 33 doubles, conflict free both ways), then lane a adds up row a.  ~3x fewer
+// instructions than a shuffle tree and it keeps the accumulators in aligned 64-bit register pairs.
+constexpr int kRedPitch = 33;
+template <int N, int NP>
+__device__ __forceinline__ void reduce_store(const double (&acc)[NP], double *red, double *tot, int lane) {
 #pragma unroll
-    for (int b = 0; b < NP / 32; b++) {
-        double v[32];
+    for (int b = 0; b < (N + 31) / 32; b++) {
+        if (b) __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] = acc[b * 32 + i];
-        warp_reduce32(v, lane);
-        tot[b * 32 + lane] = v[0];
+        for (int i = 0; i < 32; i++)
+            if (b * 32 + i < N) red[i * kRedPitch + lane] = acc[b * 32 + i];
+        __syncwarp();
+        if (b * 32 + lane < N) {
+            const double *row = red + lane * kRedPitch;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                s0 += row[i];
+                s1 += row[i + 1];
+                s2 += row[i + 2];
+                s3 += row[i + 3];
+            }
+            tot[b * 32 + lane] = (s0 + s1) + (s2 + s3);
+        }
     }
 }
 
@@ -190,29 +209,31 @@ __device__ __noinline__ double exact_colsum(const ScanParams &p, int64_t locus, 
 // removed allele carries reads (both rare).  Leaves the re-accumulated totals in tot[].
 template <int A, int K, bool W>
 __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const double *ys, const double *ws,
-                                       double *tot, int lane, unsigned &kept_out) {
+                                       double *red, double *tot, int lane, bool decide, unsigned &kept_out) {
     using AC = Acc<A, K, W>;
     const Layout &lay = p.lay;
     const double *fl = p.freq + (size_t)locus * lay.freq_stride();
     const uint32_t *dl = p.depth + (size_t)locus * lay.depth_stride();
     // 1. keep-mask of the alleles (lane j evaluates column j sequentially)
-    bool keep_j = false;
-    if (lane < A) {
-        const double q = exact_q(p, locus, lane, ws);
-        keep_j = !((q < p.maf) | (q > p.one_minus_maf));
+    unsigned kept = kept_out;
+    if (decide) {  // a pool without coverage poisoned the fast sums: redo the MAF decision exactly
+        bool keep_j = false;
+        if (lane < A) {
+            const double q = exact_q(p, locus, lane, ws);
+            keep_j = !((q < p.maf) | (q > p.one_minus_maf));
+        }
+        kept = __ballot_sync(PG_FULL_MASK, keep_j) & ((1u << A) - 1u);
+        kept_out = kept;
+        if (__popc(kept) < 2) return PG_LOCUS_FILTERED;
     }
-    const unsigned kept = __ballot_sync(PG_FULL_MASK, keep_j) & ((1u << A) - 1u);
-    kept_out = kept;
-    if (__popc(kept) < 2) return PG_LOCUS_FILTERED;
     // 2. missingness on the first kept column: NaN <=> the pool has no coverage (sync.rs:287-299)
-    int miss = 0;
-    for (int i = lane; i < lay.n; i += 32) {
-        const int c = i / lay.rc;
-        miss += (dl[(size_t)c * lay.rc + (i - c * lay.rc)] == 0u) ? 1 : 0;
+    if (decide) {
+        int miss = 0;
+        for (int i = lane; i < lay.n; i += 32) miss += (dl[i] == 0u) ? 1 : 0;
+        miss = __reduce_add_sync(PG_FULL_MASK, miss);
+        if (miss == lay.n) return PG_LOCUS_FILTERED;
+        if (((double)miss / (double)lay.n) > p.max_miss) return PG_LOCUS_FILTERED;
     }
-    miss = __reduce_add_sync(PG_FULL_MASK, miss);
-    if (miss == lay.n) return PG_LOCUS_FILTERED;
-    if (((double)miss / (double)lay.n) > p.max_miss) return PG_LOCUS_FILTERED;
     // 3. re-accumulate over the renormalised frequencies
     double acc[AC::NP];
 #pragma unroll
@@ -233,7 +254,8 @@ __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const
         }
         i0 += rcc;
     }
-    reduce_store<AC::NP>(acc, tot, lane);
+    __syncwarp();
+    reduce_store<AC::N, AC::NP>(acc, red, tot, lane);
     __syncwarp();
     return PG_LOCUS_OK;
 }
@@ -378,8 +400,72 @@ __device__ __noinline__ int explicit_locus(const ScanParams &p, int64_t locus, u
     return PG_LOCUS_OK;
 }
 
+// pearsons_correlation with missing frequencies (src/gwas/correlation_test.rs:21-31): pools whose frequency is NaN
+// are dropped pairwise, the means and centred sums run over the remaining pools, n stays the full pool count.
+template <int A, int K>
+__device__ __noinline__ void explicit_corr_nan(const ScanParams &p, int64_t locus, unsigned kept, int m, const int *cols,
+                                               const double *ys, double *tbg) {
+    const Layout &lay = p.lay;
+    const double *fl = p.freq + (size_t)locus * lay.freq_stride();
+    const uint32_t *dl = p.depth + (size_t)locus * lay.depth_stride();
+    double sx[PG_MAX_SLOTS], sy[K], sxx[PG_MAX_SLOTS], syy[K], sxy[K][PG_MAX_SLOTS];
+    double cnt = 0.0;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int a = 0; a < PG_MAX_SLOTS; a++) {
+            if (pass == 0) sx[a] = 0.0; else sx[a] = sx[a] / cnt;
+            sxx[a] = 0.0;
+            for (int k = 0; k < K; k++) sxy[k][a] = 0.0;
+        }
+        for (int k = 0; k < K; k++) {
+            if (pass == 0) sy[k] = 0.0; else sy[k] = sy[k] / cnt;
+            syy[k] = 0.0;
+        }
+        int i0 = 0;
+        for (int c = 0; c < lay.n_chunks; c++) {
+            const int rcc = (c == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
+            const double *blk = fl + (size_t)c * lay.A * lay.rc;
+            const int rows = min(rcc, lay.n - i0);
+            for (int r = 0; r < rows; r++) {
+                double f[A], F[A];
+#pragma unroll
+                for (int j = 0; j < A; j++) f[j] = blk[(size_t)j * rcc + r];
+                renorm_row<A>(f, dl[i0 + r], kept, F);
+                double x[PG_MAX_SLOTS];
+                bool valid = true;
+                for (int a = 0; a < m; a++) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int j = 0; j < A; j++)
+                        if (j == cols[a]) v = F[j];
+                    x[a] = v;
+                    valid &= (v == v);
+                }
+                if (!valid) continue;
+                if (pass == 0) {
+                    cnt += 1.0;
+                    for (int a = 0; a < m; a++) sx[a] += x[a];
+                    for (int k = 0; k < K; k++) sy[k] += ys[k * lay.n_pad + i0 + r];
+                } else {
+                    for (int k = 0; k < K; k++) {
+                        const double dy = ys[k * lay.n_pad + i0 + r] - sy[k];
+                        syy[k] = fma(dy, dy, syy[k]);
+                        for (int a = 0; a < m; a++) sxy[k][a] = fma(x[a] - sx[a], dy, sxy[k][a]);
+                    }
+                    for (int a = 0; a < m; a++) sxx[a] = fma(x[a] - sx[a], x[a] - sx[a], sxx[a]);
+                }
+            }
+            i0 += rcc;
+        }
+    }
+    for (int a = 0; a < m; a++)
+        for (int k = 0; k < K; k++) {
+            tbg[(a * K + k) * 2 + 0] = sxy[k][a] / (sqrt(sxx[a]) * sqrt(syy[k]));
+            tbg[(a * K + k) * 2 + 1] = 0.0;
+        }
+}
+
 template <int A, int K, bool W>
-__global__ void __launch_bounds__((Acc<A, K, W>::NB == 1 ? 12 : 8) * 32, 1) scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(8 * 32, 1) scan_kernel(const ScanParams p) {
     using AC = Acc<A, K, W>;
     using WS = WarpSmem<A, K, W>;
     constexpr int T = WS::T;
@@ -397,6 +483,7 @@ __global__ void __launch_bounds__((Acc<A, K, W>::NB == 1 ? 12 : 8) * 32, 1) scan
     double *tot = reinterpret_cast<double *>(wb + WS::off_tot);
     uint64_t *sel = reinterpret_cast<uint64_t *>(wb + WS::off_sel);
     double *tb = reinterpret_cast<double *>(wb + WS::off_tb);
+    double *red = reinterpret_cast<double *>(wb + WS::off_red);
 
     for (int i = threadIdx.x; i < K * n_pad; i += blockDim.x) ys[i] = p.yc[i];
     if (W)
@@ -420,6 +507,7 @@ __global__ void __launch_bounds__((Acc<A, K, W>::NB == 1 ? 12 : 8) * 32, 1) scan
     const size_t fstride = lay.freq_stride(), dstride = lay.depth_stride();
     const double nn = (double)lay.n;
     const double tol_rel = 2.0 * (nn + 8.0) * kEps;
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
 
     // tile t of this warp -> (group, first locus slot, loci, chunk)
     auto issue = [&](int64_t gs, int ti, int buf) {
@@ -530,7 +618,7 @@ __global__ void __launch_bounds__((Acc<A, K, W>::NB == 1 ? 12 : 8) * 32, 1) scan
                     const int64_t locus = l0 + q;
                     double *tg = tot + (size_t)g * AC::NP;
                     const unsigned dm = __reduce_min_sync(PG_FULL_MASK, dmin);
-                    reduce_store<AC::NP>(acc, tg, lane);
+                    reduce_store<AC::N, AC::NP>(acc, red, tg, lane);
                     __syncwarp();
                     int status = PG_LOCUS_OK;
                     unsigned kept = 0;
@@ -556,7 +644,7 @@ __global__ void __launch_bounds__((Acc<A, K, W>::NB == 1 ? 12 : 8) * 32, 1) scan
                                 if (!((kept >> j) & 1u) && tg[AC::S0 + j] > 0.0) slow = true;  // renormalise
                         }
                     }
-                    if (slow) status = slow_locus<A, K, W>(p, locus, ys, ws, tg, lane, kept);
+                    if (slow) status = slow_locus<A, K, W>(p, locus, ys, ws, red, tg, lane, dm == 0u, kept);
                     int cols[PG_MAX_SLOTS] = {0, 0, 0, 0, 0};
                     int nslots = 0;
                     if (status == PG_LOCUS_OK) {
@@ -707,7 +795,10 @@ __global__ void __launch_bounds__((Acc<A, K, W>::NB == 1 ? 12 : 8) * 32, 1) scan
                             tbg[(a * K + k) * 2 + 1] = 0.0;
                         }
                     }
-                    if (redo && !has_nan) explicit_locus<A, K>(p, locus, keptm, m, cols, xbar, ys, tbg);
+                    if (has_nan)
+                        explicit_corr_nan<A, K>(p, locus, keptm, m, cols, ys, tbg);
+                    else if (redo)
+                        explicit_locus<A, K>(p, locus, keptm, m, cols, xbar, ys, tbg);
                 }
                 if (status != PG_LOCUS_OK) sel[g] = (sv & ~(uint64_t)0xff) | (uint64_t)status;
             }
@@ -744,7 +835,8 @@ __global__ void __launch_bounds__((Acc<A, K, W>::NB == 1 ? 12 : 8) * 32, 1) scan
                     if (fabs(tt) <= kEps || tt != tt)
                         pv = 1.0;
                     else
-                        pv = student_two_sided(fabs(tt), p.df, p.ln_beta);
+                        pv = p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab)
+                                    : student_two_sided(fabs(tt), p.df, p.ln_beta);
                     o0 = v0;
                     o1 = se;
                     o2 = tt;
@@ -761,7 +853,9 @@ __global__ void __launch_bounds__((Acc<A, K, W>::NB == 1 ? 12 : 8) * 32, 1) scan
                         } else {
                             const double tt = r / sqrt(s2);
                             o2 = tt;
-                            o3 = (lay.n > 2) ? student_two_sided(fabs(tt), p.df, p.ln_beta) : nan("");
+                            o3 = (lay.n > 2) ? (p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab)
+                                                       : student_two_sided(fabs(tt), p.df, p.ln_beta))
+                                             : nan("");
                             o0 = round(r * 1e7) / 1e7;
                         }
                     }
@@ -782,7 +876,7 @@ cudaError_t launch_scan_t(const ScanParams &p, int sm_count, cudaStream_t s) {
     const size_t common = scan_common_bytes(K, p.lay.n_pad, W);
     const size_t avail = 227 * 1024;
     if (common + WS::bytes > avail) return cudaErrorInvalidConfiguration;
-    int max_warps = AC::NB == 1 ? 12 : 8;
+    int max_warps = 8;
     int nwarps = (int)((avail - common) / WS::bytes);
     if (nwarps > max_warps) nwarps = max_warps;
     if (nwarps > 4) nwarps &= ~3;  // keep the four SM sub-partitions balanced
