@@ -467,6 +467,7 @@ static int run_once(pg_batch *b, int *launches) {
             p.k_total = s->k;
             p.phen_base = base;
             p.write_meta = base == 0;
+            { const char *dbg = getenv("PG_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
             PG_CUDA(ctx, pg::launch_scan(p, ctx->sm_count, b->stream));
             if (launches) (*launches)++;
         }

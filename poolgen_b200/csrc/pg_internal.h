@@ -84,6 +84,7 @@ struct ScanParams {
     double *stats;
     int k_total, phen_base, K;  // output indexing when k > kMaxPhenPerPass
     int write_meta;             // only the first phenotype pass writes meta / freq_mean
+    int debug;                  // PG_DEBUG bit mask (kernel bisection, never set in production)
 };
 
 struct TableParams {

@@ -19,7 +19,7 @@
 
 namespace pg {
 
-constexpr int kNBuf = 3;
+constexpr int kNBuf = 2;
 constexpr int kRedPitchDecl = 33;
 constexpr int kBufRows = kChunkRows;
 
@@ -44,8 +44,8 @@ __host__ __device__ constexpr int group_size(int T) {
     for (int g = 1; g <= 16; g++) {
         const int tasks = g * T;
         const int passes = (tasks + 31) / 32;
-        // efficiency tasks / (32 * passes); prefer larger g on ties
-        if ((long long)tasks * best_den >= (long long)best_num * (32 * passes)) {
+        // efficiency tasks / (32 * passes); the smaller g wins ties (less shared memory per warp)
+        if ((long long)tasks * best_den > (long long)best_num * (32 * passes)) {
             best = g;
             best_num = tasks;
             best_den = 32 * passes;
@@ -65,14 +65,15 @@ struct WarpSmem {
     static constexpr int tot_bytes = G * AC::NP * 8;
     static constexpr int sel_bytes = ((G * 8 + 15) / 16) * 16;
     static constexpr int tb_bytes = G * T * 16;
-    static constexpr int red_bytes = (AC::N < 32 ? AC::N : 32) * kRedPitchDecl * 8;
+    // the chunk buffer that was consumed last doubles as the reduction scratch: rows of 33 doubles
+    static constexpr int RED_ROWS_CAP = fbuf_bytes / (kRedPitchDecl * 8);
+    static constexpr int RED_ROWS = RED_ROWS_CAP < 32 ? RED_ROWS_CAP : 32;
     static constexpr int off_f = bar_bytes;
     static constexpr int off_d = off_f + kNBuf * fbuf_bytes;
     static constexpr int off_tot = off_d + kNBuf * dbuf_bytes;
     static constexpr int off_sel = off_tot + tot_bytes;
     static constexpr int off_tb = off_sel + sel_bytes;
-    static constexpr int off_red = off_tb + tb_bytes;
-    static constexpr int bytes = ((off_red + red_bytes + 127) / 128) * 128;
+    static constexpr int bytes = ((off_tb + tb_bytes + 127) / 128) * 128;
 };
 
 __host__ __device__ inline size_t scan_common_bytes(int K, int n_pad, bool weighted) {
@@ -109,16 +110,16 @@ __device__ __forceinline__ void accum_row(double (&acc)[Acc<A, K, W>::NP], const
 // [accumulator][lane] tile (row pitch 33 doubles, conflict free both ways), then lane a adds up row a.  ~3x fewer
 // instructions than a shuffle tree and it keeps the accumulators in aligned 64-bit register pairs.
 constexpr int kRedPitch = 33;
-template <int N, int NP>
+template <int N, int NP, int R>
 __device__ __forceinline__ void reduce_store(const double (&acc)[NP], double *red, double *tot, int lane) {
 #pragma unroll
-    for (int b = 0; b < (N + 31) / 32; b++) {
+    for (int b = 0; b < (N + R - 1) / R; b++) {
         if (b) __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 32; i++)
-            if (b * 32 + i < N) red[i * kRedPitch + lane] = acc[b * 32 + i];
+        for (int i = 0; i < R; i++)
+            if (b * R + i < N) red[i * kRedPitch + lane] = acc[b * R + i];
         __syncwarp();
-        if (b * 32 + lane < N) {
+        if (lane < R && b * R + lane < N) {
             const double *row = red + lane * kRedPitch;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
@@ -128,7 +129,7 @@ __device__ __forceinline__ void reduce_store(const double (&acc)[NP], double *re
                 s2 += row[i + 2];
                 s3 += row[i + 3];
             }
-            tot[b * 32 + lane] = (s0 + s1) + (s2 + s3);
+            tot[b * R + lane] = (s0 + s1) + (s2 + s3);
         }
     }
 }
@@ -255,7 +256,7 @@ __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const
         i0 += rcc;
     }
     __syncwarp();
-    reduce_store<AC::N, AC::NP>(acc, red, tot, lane);
+    reduce_store<AC::N, AC::NP, WarpSmem<A, K, W>::RED_ROWS>(acc, red, tot, lane);
     __syncwarp();
     return PG_LOCUS_OK;
 }
@@ -464,8 +465,311 @@ __device__ __noinline__ void explicit_corr_nan(const ScanParams &p, int64_t locu
         }
 }
 
+// ---- end of a locus (all lanes, warp uniform): keep-mask and allele order from the reduced sums ---------------
 template <int A, int K, bool W>
-__global__ void __launch_bounds__(8 * 32, 1) scan_kernel(const ScanParams p) {
+__device__ __noinline__ uint64_t decide_locus(const ScanParams &p, int64_t locus, double *tg, double *red, unsigned dm,
+                                              const double *ys, const double *ws, int lane, double tol_rel) {
+    using AC = Acc<A, K, W>;
+    int status = PG_LOCUS_OK;
+    unsigned kept = 0;
+    bool slow = false;
+    if ((double)dm < p.min_depth_f) {
+        status = PG_LOCUS_FILTERED;  // sync.rs:217-229
+    } else if (dm == 0u) {
+        slow = true;  // a pool without coverage: NaN frequencies
+    } else {
+#pragma unroll
+        for (int j = 0; j < A; j++) {
+            double qj = W ? tg[AC::Q0 + j] : tg[AC::S0 + j] * p.w_uniform;
+            const double tl = tol_rel * fmax(fabs(qj), 1.0);
+            if (fabs(qj - p.maf) <= tl || fabs(qj - p.one_minus_maf) <= tl) qj = exact_q(p, locus, j, ws);
+            if (!((qj < p.maf) | (qj > p.one_minus_maf))) kept |= 1u << j;
+        }
+        if (__popc(kept) < 2) {
+            status = PG_LOCUS_FILTERED;  // sync.rs:284-286
+        } else {
+#pragma unroll
+            for (int j = 0; j < A; j++)
+                if (!((kept >> j) & 1u) && tg[AC::S0 + j] > 0.0) slow = true;  // a removed allele carries reads
+        }
+    }
+    if (slow) status = slow_locus<A, K, W>(p, locus, ys, ws, red, tg, lane, dm == 0u, kept);
+    int cols[PG_MAX_SLOTS] = {0, 0, 0, 0, 0};
+    int nslots = 0;
+    if (status == PG_LOCUS_OK) {
+        nslots = __popc(kept) - 1;
+        if (p.kind == PG_KIND_OLS) {
+            // stable sort by decreasing column sum, drop the first (major) allele (sync.rs:478-505, ols.rs:227-230)
+            double cs[A];
+            bool tie = false;
+#pragma unroll
+            for (int j = 0; j < A; j++) cs[j] = tg[AC::S0 + j];
+#pragma unroll
+            for (int j = 0; j < A; j++)
+#pragma unroll
+                for (int l = j + 1; l < A; l++)
+                    if (((kept >> j) & 1u) && ((kept >> l) & 1u) &&
+                        fabs(cs[j] - cs[l]) <= tol_rel * fmax(fabs(cs[j]), fabs(cs[l])))
+                        tie = true;
+            if (tie) {
+                double mine = 0.0;
+                if (lane < A && ((kept >> lane) & 1u)) mine = exact_colsum<A>(p, locus, lane, kept);
+#pragma unroll
+                for (int j = 0; j < A; j++) cs[j] = __shfl_sync(PG_FULL_MASK, mine, j);
+            }
+#pragma unroll
+            for (int j = 0; j < A; j++) {
+                if (!((kept >> j) & 1u)) continue;
+                int rank = 0;
+#pragma unroll
+                for (int l = 0; l < A; l++) {
+                    if (l == j || !((kept >> l) & 1u)) continue;
+                    if (cs[l] > cs[j] || (cs[l] == cs[j] && l < j)) rank++;
+                }
+#pragma unroll
+                for (int s = 0; s < PG_MAX_SLOTS; s++)
+                    if (rank == s + 1) cols[s] = j;
+            }
+        } else {
+            // kept columns in file order, the last one is dropped (correlation_test.rs:94-98)
+            int sidx = 0;
+#pragma unroll
+            for (int j = 0; j < A; j++) {
+                if (!((kept >> j) & 1u)) continue;
+#pragma unroll
+                for (int ss = 0; ss < PG_MAX_SLOTS; ss++)
+                    if (ss == sidx && sidx < nslots) cols[ss] = j;
+                sidx++;
+            }
+        }
+    }
+    return pack_sel(status, nslots, cols, kept);
+}
+
+// Single-pass OLS from the reduced sums for M regressors, fully unrolled so that every matrix lives in registers
+// (the generic chol_inv / solve_rhs above index local arrays dynamically and are kept for the two-pass fallback).
+// Returns false when the centred X'X is not positive definite; sets redo when the single-pass form loses digits.
+template <int M, int A, int K, bool W>
+__device__ __forceinline__ bool ols_gram_m(const ScanParams &p, const double *tg, const int *cols, double nn,
+                                           double *tbg, bool &redo) {
+    using AC = Acc<A, K, W>;
+    double sx[M], S[M][M], Lm[M][M], Li[M][M], dg[M], rinv[M];
+    int c[M];
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+        c[a] = cols[a];
+        sx[a] = tg[AC::S0 + c[a]];
+    }
+    const double inv_n = 1.0 / nn;
+    double amp = 1.0;
+#pragma unroll
+    for (int a = 0; a < M; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+            const int lo = c[a] < c[b] ? c[a] : c[b], hi = c[a] < c[b] ? c[b] : c[a];
+            const double raw = tg[AC::tri(lo, hi)];
+            S[a][b] = raw - sx[a] * sx[b] * inv_n;
+            if (a == b) amp = fmax(amp, raw / S[a][a]);
+        }
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < M; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+            double v = S[a][b];
+#pragma unroll
+            for (int q = 0; q < b; q++) v -= Lm[a][q] * Lm[b][q];
+            if (a == b) {
+                if (!(v > 0.0)) {
+                    ok = false;
+                    v = 1.0;
+                }
+                Lm[a][a] = sqrt(v);
+                rinv[a] = 1.0 / Lm[a][a];
+            } else {
+                Lm[a][b] = v * rinv[b];
+            }
+        }
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+        Li[a][a] = rinv[a];
+#pragma unroll
+        for (int b = 0; b < a; b++) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = b; q < a; q++) v -= Lm[a][q] * Li[q][b];
+            Li[a][b] = v * rinv[a];
+        }
+    }
+    double vif = 1.0;
+#pragma unroll
+    for (int b = 0; b < M; b++) {
+        double v = 0.0;
+#pragma unroll
+        for (int a = b; a < M; a++) v += Li[a][b] * Li[a][b];
+        dg[b] = v;
+        vif = fmax(vif, S[b][b] * v);
+    }
+    redo = !ok || !(amp > 0.0);
+    if (!ok) return false;
+    const double inv_dfe = 1.0 / (nn - (double)(M + 1));
+    const bool saturated = !(nn - (double)(M + 1) > 0.0);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double z[M], zz = 0.0;
+        const double ys_n = p.ysum[k] * inv_n;
+#pragma unroll
+        for (int a = 0; a < M; a++) {
+            double v = 0.0;
+#pragma unroll
+            for (int b = 0; b <= a; b++) v += Li[a][b] * (tg[AC::C0 + c[b] * K + k] - sx[b] * ys_n);
+            z[a] = v;
+            zz += v * v;
+        }
+        double rss = p.syy[k] - zz;
+        // digits lost by the single-pass form: centring (amp), collinearity (vif) and syy - zz
+        if (!(64.0 * kEps * (amp * vif * zz + p.syy[k]) <= 1e-10 * rss)) redo = true;
+        if (rss < 0.0) rss = 0.0;
+        const double ve = saturated ? rss / (nn - (double)(M + 1)) : rss * inv_dfe;
+#pragma unroll
+        for (int b = 0; b < M; b++) {
+            double v = 0.0;
+#pragma unroll
+            for (int a = b; a < M; a++) v += Li[a][b] * z[a];
+            tbg[(b * K + k) * 2 + 0] = v;
+            tbg[(b * K + k) * 2 + 1] = ve * dg[b];
+        }
+    }
+    return true;
+}
+
+// ---- phase 2 (one lane per locus): centred normal equations -> (beta | r, var) per (allele slot, phenotype) -------
+template <int A, int K, bool W>
+__device__ __noinline__ uint64_t solve_locus(const ScanParams &p, int64_t locus, const double *tg, uint64_t sv,
+                                             const double *ys, double *tbg) {
+    using AC = Acc<A, K, W>;
+    const Layout &lay = p.lay;
+    const double nn = (double)lay.n;
+    int status = (int)(sv & 0xff);
+    const int m = (int)((sv >> 8) & 0xff);
+    int cols[PG_MAX_SLOTS];
+#pragma unroll
+    for (int s = 0; s < PG_MAX_SLOTS; s++) cols[s] = (int)((sv >> (16 + 4 * s)) & 0xf);
+    double fmean[PG_MAX_SLOTS];
+    if (status == PG_LOCUS_OK) {
+        double sx[PG_MAX_SLOTS], xbar[PG_MAX_SLOTS];
+        bool has_nan = false;
+        for (int a = 0; a < m; a++) {
+            sx[a] = tg[AC::S0 + cols[a]];
+            const double pjj = tg[AC::tri(cols[a], cols[a])];
+            has_nan |= (pjj != pjj);
+            xbar[a] = sx[a] / nn;
+            fmean[a] = (pjj != pjj) ? nan("") : xbar[a];
+        }
+        const unsigned keptm = (unsigned)((sv >> 40) & 0x3f);
+        if (p.kind == PG_KIND_OLS) {
+            if (lay.n < m + 1) {
+                status = PG_LOCUS_UNSUPPORTED;
+            } else if (has_nan) {
+                for (int i = 0; i < m * K * 2; i++) tbg[i] = nan("");
+            } else {
+                bool redo = false;
+                switch (m) {
+                    case 1: ols_gram_m<1, A, K, W>(p, tg, cols, nn, tbg, redo); break;
+                    case 2:
+                        if constexpr (A >= 3) ols_gram_m<2, A, K, W>(p, tg, cols, nn, tbg, redo);
+                        break;
+                    case 3:
+                        if constexpr (A >= 4) ols_gram_m<3, A, K, W>(p, tg, cols, nn, tbg, redo);
+                        break;
+                    case 4:
+                        if constexpr (A >= 5) ols_gram_m<4, A, K, W>(p, tg, cols, nn, tbg, redo);
+                        break;
+                    default:
+                        if constexpr (A >= 6) ols_gram_m<5, A, K, W>(p, tg, cols, nn, tbg, redo);
+                        break;
+                }
+                if (redo) status = explicit_locus<A, K>(p, locus, keptm, m, cols, xbar, ys, tbg);
+            }
+        } else {
+            bool redo = false;
+            for (int a = 0; a < m; a++) {
+                const double raw = tg[AC::tri(cols[a], cols[a])];
+                const double sxx = raw - sx[a] * sx[a] / nn;
+                if (!(raw <= 1e4 * sxx)) redo = true;
+                for (int k = 0; k < K; k++) {
+                    const double sxy = tg[AC::C0 + cols[a] * K + k] - sx[a] * p.ysum[k] / nn;
+                    tbg[(a * K + k) * 2 + 0] = sxy / (sqrt(sxx) * sqrt(p.syy[k]));
+                    tbg[(a * K + k) * 2 + 1] = 0.0;
+                }
+            }
+            if (has_nan)
+                explicit_corr_nan<A, K>(p, locus, keptm, m, cols, ys, tbg);
+            else if (redo)
+                explicit_locus<A, K>(p, locus, keptm, m, cols, xbar, ys, tbg);
+        }
+        if (status != PG_LOCUS_OK) sv = (sv & ~(uint64_t)0xff) | (uint64_t)status;
+    }
+    if (p.write_meta) {
+        uint64_t mv = (uint64_t)status;
+        if (status == PG_LOCUS_OK) {
+            mv |= (uint64_t)m << 8;
+            for (int s = 0; s < m; s++) mv |= (uint64_t)p.codes[cols[s]] << (16 + 8 * s);
+        }
+        p.meta[locus] = mv;
+        for (int s = 0; s < A - 1; s++)
+            p.freq_mean[(size_t)locus * (A - 1) + s] = (status == PG_LOCUS_OK && s < m) ? fmean[s] : nan("");
+    }
+    return sv;
+}
+
+// ---- phase 3 (one lane per (locus, allele slot, phenotype)): t and p --------------------------------------------
+static __device__ __noinline__ void finish_task(const ScanParams &p, const PTableDev &ptab, bool valid, double v0, double v1,
+                                         double *o) {
+    const double nn = (double)p.lay.n;
+    double o0 = nan(""), o1 = nan(""), o2 = nan(""), o3 = nan("");
+    if (valid) {
+        if (p.kind == PG_KIND_OLS) {
+            // estimate_significance, src/gwas/ols.rs:139-154
+            const double se = sqrt(v1);
+            const double tt = (fabs(v0) <= kEps) ? 0.0 : v0 / se;
+            double pv;
+            if (fabs(tt) <= kEps || tt != tt)
+                pv = 1.0;
+            else
+                pv = p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab) : student_two_sided(fabs(tt), p.df, p.ln_beta);
+            o0 = v0;
+            o1 = se;
+            o2 = tt;
+            o3 = pv;
+        } else {
+            // pearsons_correlation, src/gwas/correlation_test.rs:52-70
+            const double r = v0;
+            if (r == r) {
+                const double s2 = (1.0 - r * r) / (nn - 2.0);
+                o1 = r;
+                if (s2 <= 0.0) {
+                    o0 = r;
+                    o3 = kEps;
+                } else {
+                    const double tt = r / sqrt(s2);
+                    o2 = tt;
+                    o3 = (p.lay.n > 2) ? (p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab)
+                                                 : student_two_sided(fabs(tt), p.df, p.ln_beta))
+                                       : nan("");
+                    o0 = round(r * 1e7) / 1e7;
+                }
+            }
+        }
+    }
+    *reinterpret_cast<double2 *>(o) = make_double2(o0, o1);
+    *reinterpret_cast<double2 *>(o + 2) = make_double2(o2, o3);
+}
+
+constexpr int kMaxWarps = 16;
+
+template <int A, int K, bool W>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) scan_kernel(const ScanParams p) {
     using AC = Acc<A, K, W>;
     using WS = WarpSmem<A, K, W>;
     constexpr int T = WS::T;
@@ -483,7 +787,6 @@ __global__ void __launch_bounds__(8 * 32, 1) scan_kernel(const ScanParams p) {
     double *tot = reinterpret_cast<double *>(wb + WS::off_tot);
     uint64_t *sel = reinterpret_cast<uint64_t *>(wb + WS::off_sel);
     double *tb = reinterpret_cast<double *>(wb + WS::off_tb);
-    double *red = reinterpret_cast<double *>(wb + WS::off_red);
 
     for (int i = threadIdx.x; i < K * n_pad; i += blockDim.x) ys[i] = p.yc[i];
     if (W)
@@ -496,99 +799,70 @@ __global__ void __launch_bounds__(8 * 32, 1) scan_kernel(const ScanParams p) {
 
     const int64_t L = p.n_loci;
     const int64_t NG = (L + G - 1) / G;
-    const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;  // consecutive warps of a CTA take consecutive groups
+    const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;  // consecutive warps take consecutive groups
     const int64_t TW = (int64_t)gridDim.x * nwarps;
     if (gw >= NG) return;
-    const int64_t my_groups = (NG - gw + TW - 1) / TW;
-    const bool small = lay.n_chunks == 1;
-    const int TL = small ? max(1, min(G, kBufRows / n_pad)) : 1;
-    const int TPG = small ? (G + TL - 1) / TL : G * lay.n_chunks;
-    const int64_t total_tiles = my_groups * TPG;
+    const int n_chunks = lay.n_chunks;
     const size_t fstride = lay.freq_stride(), dstride = lay.depth_stride();
-    const double nn = (double)lay.n;
-    const double tol_rel = 2.0 * (nn + 8.0) * kEps;
+    const double tol_rel = 2.0 * ((double)lay.n + 8.0) * kEps;
     const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
 
-    // tile t of this warp -> (group, first locus slot, loci, chunk)
-    auto issue = [&](int64_t gs, int ti, int buf) {
-        const int64_t group = gw + gs * TW;
-        int li, chunk, nl;
-        if (small) {
-            li = ti * TL;
-            chunk = 0;
-            nl = min(TL, G - li);
-        } else {
-            li = ti / lay.n_chunks;
-            chunk = ti - li * lay.n_chunks;
-            nl = 1;
-        }
-        const int64_t l0 = group * G + li;
-        const int nlv = (int)max((int64_t)0, min((int64_t)nl, L - l0));
-        if (nlv <= 0) return;
-        const int rcc = (chunk == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
-        const uint32_t fbytes = (uint32_t)(small ? (size_t)nlv * A * n_pad * 8 : (size_t)A * rcc * 8);
-        const uint32_t dbytes = (uint32_t)(small ? (size_t)nlv * n_pad * 4 : (size_t)rcc * 4);
-        const double *fsrc = p.freq + (size_t)l0 * fstride + (size_t)chunk * A * lay.rc;
-        const uint32_t *dsrc = p.depth + (size_t)l0 * dstride + (size_t)chunk * lay.rc;
-        mbar_expect_tx(&bars[buf], fbytes + dbytes);
-        bulk_g2s(fbuf + (size_t)buf * (WS::fbuf_bytes / 8), fsrc, fbytes, &bars[buf]);
-        bulk_g2s(dbuf + (size_t)buf * (WS::dbuf_bytes / 4), dsrc, dbytes, &bars[buf]);
-    };
+    // producer side of the warp's private ring: the tile stream is (group, locus in group, chunk), and only the
+    // last group of the job can be short, so the stream of a warp simply ends at the first locus >= L.  All of the
+    // iterator state is plain scalars so that it stays in registers.
+    int64_t i_group = gw, i_locus = gw * G;
+    int i_li = 0, i_chunk = 0;
+    bool i_done = false;
+#define PG_ISSUE_NEXT(BUF)                                                                                  \
+    do {                                                                                                    \
+        if (!i_done) {                                                                                      \
+            if (lane == 0) {                                                                                \
+                const int rcc_ = (i_chunk == n_chunks - 1) ? lay.rc_last : lay.rc;                          \
+                const uint32_t fbytes_ = (uint32_t)(A * rcc_ * 8), dbytes_ = (uint32_t)(rcc_ * 4);          \
+                const double *fsrc_ = p.freq + (size_t)i_locus * fstride + (size_t)i_chunk * A * lay.rc;    \
+                const uint32_t *dsrc_ = p.depth + (size_t)i_locus * dstride + (size_t)i_chunk * lay.rc;     \
+                fence_proxy_async(); /* the buffer may have served as reduction scratch (generic writes) */ \
+                mbar_expect_tx(&bars[BUF], fbytes_ + dbytes_);                                              \
+                bulk_g2s(fbuf + (size_t)(BUF) * (WS::fbuf_bytes / 8), fsrc_, fbytes_, &bars[BUF]);          \
+                bulk_g2s(dbuf + (size_t)(BUF) * (WS::dbuf_bytes / 4), dsrc_, dbytes_, &bars[BUF]);          \
+            }                                                                                               \
+            if (++i_chunk == n_chunks) {                                                                    \
+                i_chunk = 0;                                                                                \
+                i_locus++;                                                                                  \
+                if (++i_li == G) {                                                                          \
+                    i_li = 0;                                                                               \
+                    i_group += TW;                                                                          \
+                    i_locus = i_group * G;                                                                  \
+                    if (i_group >= NG) i_done = true;                                                       \
+                }                                                                                           \
+                if (i_locus >= L) i_done = true;                                                            \
+            }                                                                                               \
+        }                                                                                                   \
+    } while (0)
+#pragma unroll
+    for (int b = 0; b < kNBuf; b++) PG_ISSUE_NEXT(b);
 
-    // prologue: fill the ring
-    {
-        int64_t gs = 0;
-        int ti = 0;
-        for (int b = 0; b < kNBuf && b < total_tiles; b++) {
-            if (lane == 0) issue(gs, ti, b);
-            if (++ti == TPG) {
-                ti = 0;
-                gs++;
-            }
-        }
-    }
-    // iterator of the tile to issue next: always kNBuf tiles ahead of the consumer
-    int64_t igs = kNBuf / TPG;
-    int iti = kNBuf % TPG;
-
-    double acc[AC::NP];
-    unsigned dmin = 0xFFFFFFFFu;
     uint32_t phase_bits = 0;  // bit b = parity to wait for on buffer b
     int buf = 0;
-    int64_t cgs = 0;
-    int cti = 0;
-
-    for (int64_t t = 0; t < total_tiles; t++) {
-        const int64_t group = gw + cgs * TW;
-        int li, chunk, nl;
-        if (small) {
-            li = cti * TL;
-            chunk = 0;
-            nl = min(TL, G - li);
-        } else {
-            li = cti / lay.n_chunks;
-            chunk = cti - li * lay.n_chunks;
-            nl = 1;
-        }
-        const int64_t l0 = group * G + li;
-        const int nlv = (int)max((int64_t)0, min((int64_t)nl, L - l0));
-        const int rcc = (chunk == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
-        const int row0 = chunk * lay.rc;
-        if (nlv > 0) {
-            mbar_wait(&bars[buf], (phase_bits >> buf) & 1u);
-            phase_bits ^= (1u << buf);
-            const double *fb0 = fbuf + (size_t)buf * (WS::fbuf_bytes / 8);
-            const uint32_t *db0 = dbuf + (size_t)buf * (WS::dbuf_bytes / 4);
-            for (int q = 0; q < nlv; q++) {
-                const double *fb = fb0 + (size_t)q * A * n_pad;
-                const uint32_t *db = db0 + (size_t)q * n_pad;
-                if (chunk == 0) {
+    for (int64_t group = gw; group < NG; group += TW) {
+        const int64_t gl0 = group * G;
+        const int gn = (int)min((int64_t)G, L - gl0);  // loci of this group
+        for (int g = 0; g < gn; g++) {
+            const int64_t locus = gl0 + g;
+            double acc[AC::NP];
 #pragma unroll
-                    for (int i = 0; i < AC::NP; i++) acc[i] = 0.0;
-                    dmin = 0xFFFFFFFFu;
-                }
-                // ---- phase 1: lane handles rows 2*lane, 2*lane+1 (+64 ...) with 128-bit loads
-                for (int r = 2 * lane; r < rcc; r += 64) {
+            for (int i = 0; i < AC::NP; i++) acc[i] = 0.0;
+            unsigned dmin = 0xFFFFFFFFu;
+            double *red = nullptr;
+            for (int chunk = 0; chunk < n_chunks; chunk++) {
+                const int rcc = (chunk == n_chunks - 1) ? lay.rc_last : lay.rc;
+                const int row0 = chunk * lay.rc;
+                mbar_wait(&bars[buf], (phase_bits >> buf) & 1u);
+                phase_bits ^= (1u << buf);
+                const double *fb = fbuf + (size_t)buf * (WS::fbuf_bytes / 8);
+                const uint32_t *db = dbuf + (size_t)buf * (WS::dbuf_bytes / 4);
+                // ---- phase 1: lane handles rows 2*lane, 2*lane+1 (+64 ...) with 128-bit shared loads
+                for (int r = 2 * lane; r < ((p.debug & 1) ? 0 : rcc); r += 64) {
                     double2 f2[A];
 #pragma unroll
                     for (int j = 0; j < A; j++) f2[j] = *reinterpret_cast<const double2 *>(fb + (size_t)j * rcc + r);
@@ -612,274 +886,55 @@ __global__ void __launch_bounds__(8 * 32, 1) scan_kernel(const ScanParams p) {
                     for (int k = 0; k < K; k++) ya[k] = y2[k].y;
                     accum_row<A, K, W, false>(acc, fa, ya, w2.y);
                 }
-                if (chunk == lay.n_chunks - 1) {
-                    // ---- end of locus: reduce, keep-mask, allele order
-                    const int g = li + q;
-                    const int64_t locus = l0 + q;
+                __syncwarp();
+                if (chunk == n_chunks - 1 && !(p.debug & 2)) {
+                    // the buffer just consumed doubles as the reduction scratch before it is refilled
+                    red = const_cast<double *>(fb);
                     double *tg = tot + (size_t)g * AC::NP;
                     const unsigned dm = __reduce_min_sync(PG_FULL_MASK, dmin);
-                    reduce_store<AC::N, AC::NP>(acc, red, tg, lane);
+                    reduce_store<AC::N, AC::NP, WS::RED_ROWS>(acc, red, tg, lane);
                     __syncwarp();
-                    int status = PG_LOCUS_OK;
-                    unsigned kept = 0;
-                    bool slow = false;
-                    if ((double)dm < p.min_depth_f) {
-                        status = PG_LOCUS_FILTERED;  // sync.rs:217-229
-                    } else if (dm == 0u) {
-                        slow = true;  // a pool without coverage: NaN frequencies
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < A; j++) {
-                            double qj = W ? tg[AC::Q0 + j] : tg[AC::S0 + j] * p.w_uniform;
-                            const double tl = tol_rel * fmax(fabs(qj), 1.0);
-                            if (fabs(qj - p.maf) <= tl || fabs(qj - p.one_minus_maf) <= tl)
-                                qj = exact_q(p, locus, j, ws);
-                            if (!((qj < p.maf) | (qj > p.one_minus_maf))) kept |= 1u << j;
-                        }
-                        if (__popc(kept) < 2) {
-                            status = PG_LOCUS_FILTERED;  // sync.rs:284-286
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < A; j++)
-                                if (!((kept >> j) & 1u) && tg[AC::S0 + j] > 0.0) slow = true;  // renormalise
-                        }
-                    }
-                    if (slow) status = slow_locus<A, K, W>(p, locus, ys, ws, red, tg, lane, dm == 0u, kept);
-                    int cols[PG_MAX_SLOTS] = {0, 0, 0, 0, 0};
-                    int nslots = 0;
-                    if (status == PG_LOCUS_OK) {
-                        const int a = __popc(kept);
-                        nslots = a - 1;
-                        if (p.kind == PG_KIND_OLS) {
-                            // stable sort by decreasing column sum, drop the first (major) allele
-                            double cs[A];
-                            bool tie = false;
-#pragma unroll
-                            for (int j = 0; j < A; j++) cs[j] = tg[AC::S0 + j];
-#pragma unroll
-                            for (int j = 0; j < A; j++)
-#pragma unroll
-                                for (int l = j + 1; l < A; l++)
-                                    if (((kept >> j) & 1u) && ((kept >> l) & 1u) &&
-                                        fabs(cs[j] - cs[l]) <= tol_rel * fmax(fabs(cs[j]), fabs(cs[l])))
-                                        tie = true;
-                            if (tie) {
-                                double mine = 0.0;
-                                if (lane < A && ((kept >> lane) & 1u)) mine = exact_colsum<A>(p, locus, lane, kept);
-#pragma unroll
-                                for (int j = 0; j < A; j++) cs[j] = __shfl_sync(PG_FULL_MASK, mine, j);
-                            }
-#pragma unroll
-                            for (int j = 0; j < A; j++) {
-                                if (!((kept >> j) & 1u)) continue;
-                                int rank = 0;
-#pragma unroll
-                                for (int l = 0; l < A; l++) {
-                                    if (l == j || !((kept >> l) & 1u)) continue;
-                                    if (cs[l] > cs[j] || (cs[l] == cs[j] && l < j)) rank++;
-                                }
-#pragma unroll
-                                for (int s = 0; s < PG_MAX_SLOTS; s++)
-                                    if (rank == s + 1) cols[s] = j;
-                            }
-                        } else {
-                            // kept columns in file order, the last one is dropped (correlation_test.rs:94-98)
-                            int s = 0;
-#pragma unroll
-                            for (int j = 0; j < A; j++) {
-                                if (!((kept >> j) & 1u)) continue;
-#pragma unroll
-                                for (int ss = 0; ss < PG_MAX_SLOTS; ss++)
-                                    if (ss == s && s < nslots) cols[ss] = j;
-                                s++;
-                            }
-                        }
-                    }
-                    if (lane == 0) sel[g] = pack_sel(status, nslots, cols, kept);
+                    const uint64_t sv = decide_locus<A, K, W>(p, locus, tg, red, dm, ys, ws, lane, tol_rel);
+                    if (lane == 0) sel[g] = sv;
+                    __syncwarp();
                 }
+                PG_ISSUE_NEXT(buf);  // refill this buffer with the tile kNBuf ahead
+                buf = (buf + 1 == kNBuf) ? 0 : buf + 1;
             }
         }
-        __syncwarp();
-        // refill this buffer with the tile kNBuf ahead
-        if (t + kNBuf < total_tiles) {
-            if (lane == 0) issue(igs, iti, buf);
-            if (++iti == TPG) {
-                iti = 0;
-                igs++;
-            }
-        }
-        buf = (buf + 1 == kNBuf) ? 0 : buf + 1;
-        const bool group_done = (cti + 1 == TPG);
-        if (++cti == TPG) {
-            cti = 0;
-            cgs++;
-        }
-        if (!group_done) continue;
-
         // ---- phase 2: lane = locus of the group
         __syncwarp();
-        const int64_t gl0 = group * G;
-        if (lane < G && gl0 + lane < L) {
-            const int g = lane;
-            const int64_t locus = gl0 + g;
-            const double *tg = tot + (size_t)g * AC::NP;
-            uint64_t sv = sel[g];
-            int status = (int)(sv & 0xff);
-            const int m = (int)((sv >> 8) & 0xff);
-            int cols[PG_MAX_SLOTS];
-#pragma unroll
-            for (int s = 0; s < PG_MAX_SLOTS; s++) cols[s] = (int)((sv >> (16 + 4 * s)) & 0xf);
-            double *tbg = tb + (size_t)g * T * 2;
-            double fmean[PG_MAX_SLOTS];
-            if (status == PG_LOCUS_OK) {
-                double sx[PG_MAX_SLOTS];
-                bool has_nan = false;
-                for (int a = 0; a < m; a++) {
-                    sx[a] = tg[AC::S0 + cols[a]];
-                    const double pjj = tg[AC::tri(cols[a], cols[a])];
-                    has_nan |= (pjj != pjj);
-                    fmean[a] = (pjj != pjj) ? nan("") : sx[a] / nn;
-                }
-                const unsigned keptm = (unsigned)((sv >> 40) & 0x3f);
-                double xbar[PG_MAX_SLOTS];
-                for (int a = 0; a < m; a++) xbar[a] = sx[a] / nn;
-                if (p.kind == PG_KIND_OLS) {
-                    if (lay.n < m + 1) {
-                        status = PG_LOCUS_UNSUPPORTED;
-                    } else if (has_nan) {
-                        for (int i = 0; i < m * K * 2; i++) tbg[i] = nan("");
-                    } else {
-                        double S[PG_MAX_SLOTS][PG_MAX_SLOTS], Li[PG_MAX_SLOTS][PG_MAX_SLOTS], dg[PG_MAX_SLOTS];
-                        double amp = 1.0;
-                        for (int a = 0; a < m; a++)
-                            for (int b = 0; b <= a; b++) {
-                                const int ca = cols[a], cb = cols[b];
-                                const int lo = ca < cb ? ca : cb, hi = ca < cb ? cb : ca;
-                                const double raw = tg[AC::tri(lo, hi)];
-                                S[a][b] = raw - sx[a] * sx[b] / nn;
-                                if (a == b) amp = fmax(amp, raw / S[a][a]);
-                            }
-                        bool ok = chol_inv(m, S, Li, dg);
-                        bool redo = !ok || !(amp > 0.0);
-                        if (ok) {
-                            double vif = 1.0;
-                            for (int a = 0; a < m; a++) vif = fmax(vif, S[a][a] * dg[a]);
-                            const double dfe = nn - (double)(m + 1);
-                            for (int k = 0; k < K; k++) {
-                                double sxy[PG_MAX_SLOTS], beta[PG_MAX_SLOTS];
-                                for (int b = 0; b < m; b++)
-                                    sxy[b] = tg[AC::C0 + cols[b] * K + k] - sx[b] * p.ysum[k] / nn;
-                                const double zz = solve_rhs(m, Li, sxy, beta);
-                                double rss = p.syy[k] - zz;
-                                // digits lost by the single-pass form: centring (amp), collinearity (vif) and syy - zz
-                                if (!(64.0 * kEps * (amp * vif * zz + p.syy[k]) <= 1e-10 * rss)) redo = true;
-                                if (rss < 0.0) rss = 0.0;
-                                const double ve = rss / dfe;
-                                for (int b = 0; b < m; b++) {
-                                    tbg[(b * K + k) * 2 + 0] = beta[b];
-                                    tbg[(b * K + k) * 2 + 1] = ve * dg[b];
-                                }
-                            }
-                        }
-                        if (redo) status = explicit_locus<A, K>(p, locus, keptm, m, cols, xbar, ys, tbg);
-                    }
-                } else {
-                    bool redo = false;
-                    for (int a = 0; a < m; a++) {
-                        const double raw = tg[AC::tri(cols[a], cols[a])];
-                        const double sxx = raw - sx[a] * sx[a] / nn;
-                        if (!(raw <= 1e4 * sxx)) redo = true;
-                        for (int k = 0; k < K; k++) {
-                            const double sxy = tg[AC::C0 + cols[a] * K + k] - sx[a] * p.ysum[k] / nn;
-                            tbg[(a * K + k) * 2 + 0] = sxy / (sqrt(sxx) * sqrt(p.syy[k]));
-                            tbg[(a * K + k) * 2 + 1] = 0.0;
-                        }
-                    }
-                    if (has_nan)
-                        explicit_corr_nan<A, K>(p, locus, keptm, m, cols, ys, tbg);
-                    else if (redo)
-                        explicit_locus<A, K>(p, locus, keptm, m, cols, xbar, ys, tbg);
-                }
-                if (status != PG_LOCUS_OK) sel[g] = (sv & ~(uint64_t)0xff) | (uint64_t)status;
-            }
-            if (p.write_meta) {
-                uint64_t mv = (uint64_t)status;
-                if (status == PG_LOCUS_OK) {
-                    mv |= (uint64_t)m << 8;
-                    for (int s = 0; s < m; s++) mv |= (uint64_t)p.codes[cols[s]] << (16 + 8 * s);
-                }
-                p.meta[locus] = mv;
-                for (int s = 0; s < A - 1; s++)
-                    p.freq_mean[(size_t)locus * (A - 1) + s] = (status == PG_LOCUS_OK && s < m) ? fmean[s] : nan("");
-            }
+        if (p.debug & 4) continue;
+        if (lane < gn) {
+            const uint64_t sv = solve_locus<A, K, W>(p, gl0 + lane, tot + (size_t)lane * AC::NP, sel[lane], ys,
+                                                     tb + (size_t)lane * T * 2);
+            sel[lane] = sv;
         }
         __syncwarp();
         // ---- phase 3: lane = (locus, allele slot, phenotype)
-        for (int task = lane; task < G * T; task += 32) {
+        for (int task = lane; task < ((p.debug & 8) ? 0 : gn * T); task += 32) {
             const int g = task / T, rem = task - g * T;
             const int slot = rem / K, kk = rem - slot * K;
-            const int64_t locus = gl0 + g;
-            if (locus >= L) continue;
             const uint64_t sv = sel[g];
-            const int status = (int)(sv & 0xff);
-            const int m = (int)((sv >> 8) & 0xff);
-            double o0 = nan(""), o1 = nan(""), o2 = nan(""), o3 = nan("");
-            if (status == PG_LOCUS_OK && slot < m) {
-                const double v0 = tb[((size_t)g * T + slot * K + kk) * 2 + 0];
-                const double v1 = tb[((size_t)g * T + slot * K + kk) * 2 + 1];
-                if (p.kind == PG_KIND_OLS) {
-                    // estimate_significance, src/gwas/ols.rs:139-154
-                    const double se = sqrt(v1);
-                    const double tt = (fabs(v0) <= kEps) ? 0.0 : v0 / se;
-                    double pv;
-                    if (fabs(tt) <= kEps || tt != tt)
-                        pv = 1.0;
-                    else
-                        pv = p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab)
-                                    : student_two_sided(fabs(tt), p.df, p.ln_beta);
-                    o0 = v0;
-                    o1 = se;
-                    o2 = tt;
-                    o3 = pv;
-                } else {
-                    // pearsons_correlation, src/gwas/correlation_test.rs:52-70
-                    const double r = v0;
-                    if (r == r) {
-                        const double s2 = (1.0 - r * r) / (nn - 2.0);
-                        o1 = r;
-                        if (s2 <= 0.0) {
-                            o0 = r;
-                            o3 = kEps;
-                        } else {
-                            const double tt = r / sqrt(s2);
-                            o2 = tt;
-                            o3 = (lay.n > 2) ? (p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab)
-                                                       : student_two_sided(fabs(tt), p.df, p.ln_beta))
-                                             : nan("");
-                            o0 = round(r * 1e7) / 1e7;
-                        }
-                    }
-                }
-            }
-            double *o = p.stats + (((size_t)locus * (A - 1) + slot) * p.k_total + p.phen_base + kk) * 4;
-            *reinterpret_cast<double2 *>(o) = make_double2(o0, o1);
-            *reinterpret_cast<double2 *>(o + 2) = make_double2(o2, o3);
+            const bool valid = ((int)(sv & 0xff) == PG_LOCUS_OK) && slot < (int)((sv >> 8) & 0xff);
+            const double v0 = tb[((size_t)g * T + slot * K + kk) * 2 + 0];
+            const double v1 = tb[((size_t)g * T + slot * K + kk) * 2 + 1];
+            double *o = p.stats + (((size_t)(gl0 + g) * (A - 1) + slot) * p.k_total + p.phen_base + kk) * 4;
+            finish_task(p, ptab, valid, v0, v1, o);
         }
         __syncwarp();
     }
+#undef PG_ISSUE_NEXT
 }
 
 template <int A, int K, bool W>
 cudaError_t launch_scan_t(const ScanParams &p, int sm_count, cudaStream_t s) {
     using WS = WarpSmem<A, K, W>;
-    using AC = Acc<A, K, W>;
     const size_t common = scan_common_bytes(K, p.lay.n_pad, W);
     const size_t avail = 227 * 1024;
     if (common + WS::bytes > avail) return cudaErrorInvalidConfiguration;
-    int max_warps = 8;
     int nwarps = (int)((avail - common) / WS::bytes);
-    if (nwarps > max_warps) nwarps = max_warps;
-    if (nwarps > 4) nwarps &= ~3;  // keep the four SM sub-partitions balanced
+    if (nwarps > kMaxWarps) nwarps = kMaxWarps;
     const size_t smem = common + (size_t)nwarps * WS::bytes;
     auto kern = scan_kernel<A, K, W>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
