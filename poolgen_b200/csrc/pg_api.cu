@@ -277,6 +277,7 @@ int pg_batch_create(pg_scan *s, int64_t cap, pg_batch **out) {
     if (e == cudaSuccess && is_regression(s)) {
         e = cudaMalloc(&b->d_freq, (size_t)cap * s->lay.freq_stride() * 8);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_depth, (size_t)cap * s->lay.depth_stride() * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_dmin, (size_t)cap * 4);
     }
     const size_t S = s->n_slots, K = s->k;
     if (e == cudaSuccess) e = cudaMalloc(&b->d_meta, (size_t)cap * 8);
@@ -295,6 +296,7 @@ int pg_batch_destroy(pg_batch *b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->d_freq);
     cudaFree(b->d_depth);
+    cudaFree(b->d_dmin);
     cudaFree(b->d_stage);
     cudaFree(b->d_meta);
     cudaFree(b->d_fmean);
@@ -343,10 +345,10 @@ static int upload_counts_t(pg_batch *b, const CT *counts, int64_t n_loci) {
         PG_CUDA(ctx, cudaMemcpyAsync(b->d_stage, counts, bytes, cudaMemcpyHostToDevice, b->stream));
         if (sizeof(CT) == 4)
             PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
-                                               b->d_freq, b->d_depth, b->stream));
+                                               b->d_freq, b->d_depth, b->d_dmin, b->stream));
         else
             PG_CUDA(ctx, pg::launch_ingest_u16((const uint16_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
-                                               b->d_freq, b->d_depth, b->stream));
+                                               b->d_freq, b->d_depth, b->d_dmin, b->stream));
     } else {
         if (sizeof(CT) == 2) return fail(ctx, PG_ERR_UNSUPPORTED, "16-bit counts are not wired for the table tests yet");
         PG_CUDA(ctx, cudaMemcpyAsync(b->d_stage, counts, bytes, cudaMemcpyHostToDevice, b->stream));
@@ -383,7 +385,7 @@ int pg_batch_upload_freq(pg_batch *b, const double *freq, const uint32_t *depth,
     uint32_t *sd = (uint32_t *)((char *)b->d_stage + fbytes_cap);
     PG_CUDA(ctx, cudaMemcpyAsync(sf, freq, (size_t)n_loci * s->A_dev * s->n * 8, cudaMemcpyHostToDevice, b->stream));
     PG_CUDA(ctx, cudaMemcpyAsync(sd, depth, (size_t)n_loci * s->n * 4, cudaMemcpyHostToDevice, b->stream));
-    PG_CUDA(ctx, pg::launch_ingest_freq(sf, sd, n_loci, s->n, s->lay, b->d_freq, b->d_depth, b->stream));
+    PG_CUDA(ctx, pg::launch_ingest_freq(sf, sd, n_loci, s->n, s->lay, b->d_freq, b->d_depth, b->d_dmin, b->stream));
     b->input_is_counts = 0;
     return PG_OK;
 }
@@ -421,7 +423,7 @@ int pg_batch_synth(pg_batch *b, uint64_t seed, int64_t first_locus, int64_t n_lo
         PG_CUDA(ctx, pg::launch_synth(seed, first_locus + l0, m, s->n, s->A_in, (uint32_t *)b->d_stage, b->stream));
         PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, m, s->n, s->A_in, s->drop_col, s->lay,
                                            b->d_freq + (size_t)l0 * s->lay.freq_stride(),
-                                           b->d_depth + (size_t)l0 * s->lay.depth_stride(), b->stream));
+                                           b->d_depth + (size_t)l0 * s->lay.depth_stride(), b->d_dmin + l0, b->stream));
     }
     b->input_is_counts = 1;
     return PG_OK;
@@ -433,12 +435,16 @@ static int run_once(pg_batch *b, int *launches) {
     if (!b->have_input) return fail(ctx, PG_ERR_STATE, "pg_batch_run: no input uploaded");
     if (b->n_loci == 0) return PG_OK;
     if (is_regression(s)) {
-        for (int base = 0; base < s->k; base += pg::kMaxPhenPerPass) {
+        const int kpass = pg::max_phen_per_pass(s->A_dev);
+        static const int nbuf_env = getenv("PG_NBUF") ? atoi(getenv("PG_NBUF")) : 0;
+        static const int warps_env = getenv("PG_WARPS") ? atoi(getenv("PG_WARPS")) : 0;
+        for (int base = 0; base < s->k; base += kpass) {
             pg::ScanParams p;
             memset(&p, 0, sizeof p);
             p.lay = s->lay;
             p.freq = b->d_freq;
             p.depth = b->d_depth;
+            p.dmin = b->d_dmin;
             p.n_loci = b->n_loci;
             p.kind = s->kind;
             p.weighted = s->weighted;
@@ -453,7 +459,7 @@ static int run_once(pg_batch *b, int *launches) {
             p.ptab_vmax = s->ptab_vmax;
             p.ptab_inv_h = s->ptab_inv_h;
             p.ptab_M = s->ptab_M;
-            p.K = std::min(pg::kMaxPhenPerPass, s->k - base);
+            p.K = std::min(kpass, s->k - base);
             p.yc = s->d_yc + (size_t)base * s->lay.n_pad;
             p.w = s->d_w;
             for (int j = 0; j < p.K; j++) {
@@ -467,7 +473,8 @@ static int run_once(pg_batch *b, int *launches) {
             p.k_total = s->k;
             p.phen_base = base;
             p.write_meta = base == 0;
-            { const char *dbg = getenv("PG_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+            p.nbuf_override = nbuf_env;
+            p.warps_override = warps_env;
             PG_CUDA(ctx, pg::launch_scan(p, ctx->sm_count, b->stream));
             if (launches) (*launches)++;
         }
@@ -523,7 +530,7 @@ int pg_batch_bytes(pg_batch *b, size_t *input_bytes, size_t *result_bytes) {
     pg_scan *s = b->scan;
     const size_t L = (size_t)b->n_loci;
     if (input_bytes)
-        *input_bytes = is_regression(s) ? L * (s->lay.freq_stride() * 8 + s->lay.depth_stride() * 4)
+        *input_bytes = is_regression(s) ? L * (s->lay.freq_stride() * 8 + 4)  // frequency matrix + dmin
                                         : L * (size_t)s->A_in * s->n * 4;
     if (result_bytes) *result_bytes = L * (8 + (size_t)s->n_slots * 8 + (size_t)s->n_slots * s->k * 32);
     return PG_OK;

@@ -16,10 +16,13 @@ namespace pg {
 // cp.async.bulk can fetch:
 //   freq  : [locus][chunk][A][rc_chunk] f64     locus stride = A * n_pad doubles
 //   depth : [locus][chunk][rc_chunk]    u32     locus stride = n_pad
+//   dmin  : [locus]                    u32     min over the pools of depth (the min-depth filter and the
+//                                               "a pool has no coverage" test need nothing else on the fast path;
+//                                               the per-pool depths are only read by the rare renormalisation paths)
 // n_pad = n rounded up to a multiple of 4 (16-byte granules for bulk copies); padding rows hold
-// freq = 0, depth = 0xFFFFFFFF.  When n_pad <= kChunkRows there is one chunk and consecutive loci
-// are contiguous, so several loci travel in one bulk copy.
-constexpr int kChunkRows = 128;
+// freq = 0, depth = 0xFFFFFFFF.  When n_pad <= chunk_rows(A) there is one chunk and consecutive loci
+// are contiguous, so several loci travel in one bulk copy.  A full chunk is 4..6 KB for every A.
+__host__ __device__ constexpr int chunk_rows(int A) { return A <= 2 ? 256 : (A == 3 ? 192 : 128); }
 
 struct Layout {
     int n;         // pools
@@ -43,25 +46,29 @@ inline Layout make_layout(int n, int A) {
     l.n = n;
     l.n_pad = (n + 3) & ~3;
     l.A = A;
-    if (l.n_pad <= kChunkRows) {
+    const int cr = chunk_rows(A);
+    if (l.n_pad <= cr) {
         l.rc = l.n_pad;
         l.n_chunks = 1;
         l.rc_last = l.n_pad;
     } else {
-        l.rc = kChunkRows;
-        l.n_chunks = (l.n_pad + kChunkRows - 1) / kChunkRows;
-        l.rc_last = l.n_pad - (l.n_chunks - 1) * kChunkRows;
+        l.rc = cr;
+        l.n_chunks = (l.n_pad + cr - 1) / cr;
+        l.rc_last = l.n_pad - (l.n_chunks - 1) * cr;
     }
     return l;
 }
 
 constexpr int kMaxPhenPerPass = 4;
+// phenotypes per kernel pass: bounded by the accumulator registers (A + A(A+1)/2 + A*K doubles per lane)
+inline int max_phen_per_pass(int A) { return A <= 4 ? 4 : (A == 5 ? 3 : 2); }
 
 // parameters of one ols/corr scan launch (passed by value)
 struct ScanParams {
     Layout lay;
     const double *freq;
     const uint32_t *depth;
+    const uint32_t *dmin;
     int64_t n_loci;
     int kind;
     int weighted;         // pool weights differ
@@ -84,7 +91,10 @@ struct ScanParams {
     double *stats;
     int k_total, phen_base, K;  // output indexing when k > kMaxPhenPerPass
     int write_meta;             // only the first phenotype pass writes meta / freq_mean
-    int debug;                  // PG_DEBUG bit mask (kernel bisection, never set in production)
+    // launch geometry, filled in by the launcher
+    uint32_t common_bytes, warp_bytes, stage_bytes;
+    int nbuf;
+    int nbuf_override, warps_override;  // tuning knobs (PG_NBUF / PG_WARPS), 0 = automatic
 };
 
 struct TableParams {
@@ -104,11 +114,11 @@ struct TableParams {
 cudaError_t launch_scan(const ScanParams &p, int sm_count, cudaStream_t s);
 cudaError_t launch_tables(const TableParams &p, int sm_count, cudaStream_t s);
 cudaError_t launch_ingest_u32(const uint32_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
-                              const Layout &lay, double *freq, uint32_t *depth, cudaStream_t s);
+                              const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s);
 cudaError_t launch_ingest_u16(const uint16_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
-                              const Layout &lay, double *freq, uint32_t *depth, cudaStream_t s);
+                              const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s);
 cudaError_t launch_ingest_freq(const double *freq_in, const uint32_t *depth_in, int64_t n_loci, int n,
-                               const Layout &lay, double *freq, uint32_t *depth, cudaStream_t s);
+                               const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s);
 cudaError_t launch_synth(uint64_t seed, int64_t first_locus, int64_t n_loci, int n, int A_in,
                          uint32_t *counts, cudaStream_t s);
 
@@ -218,6 +228,7 @@ struct pg_batch {
     // device
     double *d_freq = nullptr;
     uint32_t *d_depth = nullptr;
+    uint32_t *d_dmin = nullptr;
     void *d_stage = nullptr;  // raw uploaded slab (counts u32/u16 or unpadded freq+depth)
     size_t stage_bytes = 0;
     uint64_t *d_meta = nullptr;

@@ -1,89 +1,49 @@
 // pg_scan.cuh -- the per-locus OLS / Pearson scan kernel (ols_iterate: src/gwas/ols.rs:201-276,
 // correlation: src/gwas/correlation_test.rs:73-129) for sm_100a.
 //
-// One persistent CTA per SM.  Every warp owns a private ring of kNBuf shared-memory buffers fed by
-// 1-D bulk copies (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier), so there is no CTA-wide
-// synchronisation in the steady state.  A warp works on groups of G consecutive loci:
-//   phase 1 (per locus)  stream the [A][rows] frequency chunks, lane = pool, accumulate the column
-//                        sums, the A(A+1)/2 products and the A*K cross products with the centred
-//                        phenotypes (kept in shared memory), reduce 32 accumulators with 31 shuffles,
-//                        then evaluate the reference's keep-mask (LocusCounts::filter,
-//                        src/base/sync.rs:195-303) and allele order (src/base/sync.rs:478-505).
-//                        Decisions that land within a rounding bound of a threshold are re-evaluated
-//                        in the reference's exact sequential order (bit-exact mask).
-//   phase 2 (per group)  lane = locus: centred normal equations, Cholesky, beta, residual variance;
-//   phase 3 (per group)  lane = (locus, allele, phenotype): t and the Student-t two-sided p-value.
+// One persistent CTA per SM.  Every warp owns a private ring of shared-memory stage buffers fed by 1-D bulk copies
+// (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier), so there is no CTA-wide synchronisation in the steady
+// state.  A warp works on blocks of G consecutive loci:
+//   phase 1  stream the frequency matrix.  P lanes share one locus (P = 32: one locus per stage, row chunks of
+//            Layout::rc pools; P = 8: four whole loci per stage, for pool counts that fit one chunk), each lane owns
+//            row pairs (128-bit shared loads) and accumulates the column sums, the A(A+1)/2 products and the A*K
+//            cross products with the centred phenotypes (resident in shared memory).  The partial sums are reduced
+//            through a [accumulator][lane] transposition in the stage buffer that was just consumed and parked in
+//            the warp's totals area.
+//   phase 2  lane = locus, once per block: keep-mask (LocusCounts::filter, src/base/sync.rs:195-303) and allele
+//            order (src/base/sync.rs:478-505) from the totals, centred normal equations, Cholesky, beta, residual
+//            variance, t and the Student-t two-sided p-value, records written straight to global memory.
+// Decisions that land within a rounding bound of a threshold are re-evaluated in the reference's exact sequential
+// order (bit-exact mask); loci that need the renormalised frequencies (a removed allele carries reads, a pool has no
+// coverage) are re-accumulated by the whole warp from global memory.
 #pragma once
 #include "pg_device.cuh"
 #include "pg_internal.h"
 
 namespace pg {
 
-constexpr int kNBuf = 2;
-constexpr int kRedPitchDecl = 33;
-constexpr int kBufRows = kChunkRows;
+constexpr int kScanWarps = 12;  // 384 threads -> up to 168 registers per thread
+constexpr int kRedPitch = 33;   // row pitch (doubles) of the reduction scratch: conflict free both ways
 
 template <int A, int K, bool W>
 struct Acc {
-    static constexpr int S0 = 0;
-    static constexpr int P0 = S0 + A;
-    static constexpr int C0 = P0 + A * (A + 1) / 2;
-    static constexpr int Q0 = C0 + A * K;
+    static constexpr int S0 = 0;                        // column sums
+    static constexpr int P0 = S0 + A;                   // products f_j f_l, j <= l
+    static constexpr int C0 = P0 + A * (A + 1) / 2;     // cross products f_j y_k
+    static constexpr int Q0 = C0 + A * K;               // weighted column sums (unequal pool sizes only)
     static constexpr int N = Q0 + (W ? A : 0);
-    static constexpr int NB = (N + 31) / 32;
-    static constexpr int NP = NB * 32;
+    static constexpr int NP = N | 1;                    // odd pitch of a totals row: lane = locus reads are conflict free
     __host__ __device__ static constexpr int tri(int j, int l) {  // j <= l
         return P0 + j * A - j * (j - 1) / 2 + (l - j);
     }
 };
 
-// loci per warp group: fill the 32 lanes of phase 3 as well as possible
-__host__ __device__ constexpr int group_size(int T) {
-    int best = 1;
-    int best_num = 0, best_den = 1;
-    for (int g = 1; g <= 16; g++) {
-        const int tasks = g * T;
-        const int passes = (tasks + 31) / 32;
-        // efficiency tasks / (32 * passes); the smaller g wins ties (less shared memory per warp)
-        if ((long long)tasks * best_den > (long long)best_num * (32 * passes)) {
-            best = g;
-            best_num = tasks;
-            best_den = 32 * passes;
-        }
-    }
-    return best;
-}
-
-template <int A, int K, bool W>
-struct WarpSmem {
-    using AC = Acc<A, K, W>;
-    static constexpr int T = (A - 1) * K;
-    static constexpr int G = group_size(T);
-    static constexpr int bar_bytes = 32;
-    static constexpr int fbuf_bytes = A * kBufRows * 8;
-    static constexpr int dbuf_bytes = kBufRows * 4;
-    static constexpr int tot_bytes = G * AC::NP * 8;
-    static constexpr int sel_bytes = ((G * 8 + 15) / 16) * 16;
-    static constexpr int tb_bytes = G * T * 16;
-    // the chunk buffer that was consumed last doubles as the reduction scratch: rows of 33 doubles
-    static constexpr int RED_ROWS_CAP = fbuf_bytes / (kRedPitchDecl * 8);
-    static constexpr int RED_ROWS = RED_ROWS_CAP < 32 ? RED_ROWS_CAP : 32;
-    static constexpr int off_f = bar_bytes;
-    static constexpr int off_d = off_f + kNBuf * fbuf_bytes;
-    static constexpr int off_tot = off_d + kNBuf * dbuf_bytes;
-    static constexpr int off_sel = off_tot + tot_bytes;
-    static constexpr int off_tb = off_sel + sel_bytes;
-    static constexpr int bytes = ((off_tb + tb_bytes + 127) / 128) * 128;
-};
-
-__host__ __device__ inline size_t scan_common_bytes(int K, int n_pad, bool weighted) {
-    size_t b = (size_t)(K + (weighted ? 1 : 0)) * n_pad * 8;
-    return (b + 127) / 128 * 128;
-}
+// loci per epilogue block: with one locus per stage the totals area is kept small, otherwise fill the 32 lanes
+__host__ __device__ constexpr int block_loci(int P) { return P == 32 ? 16 : 32; }
 
 template <int A, int K, bool W, bool NANAWARE>
-__device__ __forceinline__ void accum_row(double (&acc)[Acc<A, K, W>::NP], const double (&f)[A],
-                                          const double (&y)[K], double w) {
+__device__ __forceinline__ void accum_row(double (&acc)[Acc<A, K, W>::N], const double (&f)[A], const double (&y)[K],
+                                          double w) {
     using AC = Acc<A, K, W>;
 #pragma unroll
     for (int j = 0; j < A; j++) {
@@ -106,32 +66,54 @@ __device__ __forceinline__ void accum_row(double (&acc)[Acc<A, K, W>::NP], const
     }
 }
 
-// Warp reduction of the N accumulators through shared memory: every lane stores its partial sums into a
-// [accumulator][lane] tile (row pitch 33 doubles, conflict free both ways), then lane a adds up row a.  ~3x fewer
-// instructions than a shuffle tree and it keeps the accumulators in aligned 64-bit register pairs.
-constexpr int kRedPitch = 33;
-template <int N, int NP, int R>
-__device__ __forceinline__ void reduce_store(const double (&acc)[NP], double *red, double *tot, int lane) {
+// two consecutive rows held as double2 per column
+template <int A, int K, bool W>
+__device__ __forceinline__ void accum_pair(double (&acc)[Acc<A, K, W>::N], const double2 (&f2)[A],
+                                           const double2 (&y2)[K], double2 w2) {
+    double fa[A], ya[K];
 #pragma unroll
-    for (int b = 0; b < (N + R - 1) / R; b++) {
-        if (b) __syncwarp();
+    for (int j = 0; j < A; j++) fa[j] = f2[j].x;
 #pragma unroll
-        for (int i = 0; i < R; i++)
-            if (b * R + i < N) red[i * kRedPitch + lane] = acc[b * R + i];
+    for (int k = 0; k < K; k++) ya[k] = y2[k].x;
+    accum_row<A, K, W, false>(acc, fa, ya, w2.x);
+#pragma unroll
+    for (int j = 0; j < A; j++) fa[j] = f2[j].y;
+#pragma unroll
+    for (int k = 0; k < K; k++) ya[k] = y2[k].y;
+    accum_row<A, K, W, false>(acc, fa, ya, w2.y);
+}
+
+// Reduction of the per-lane partial sums: every lane stores its N accumulators into a [accumulator][lane] tile, then
+// the totals of the 32/P loci of this step are formed by summing P consecutive entries of a row in a fixed order
+// (so a locus gets the same bits wherever it lands) and written to tot[u * NP + a].  The scratch holds red_rows
+// accumulators at a time.
+template <int N, int NP, int P>
+__device__ __forceinline__ void reduce_to_tot(const double (&acc)[N], double *red, int red_rows, double *tot,
+                                              int lane) {
+    constexpr int LPS = 32 / P;
+    for (int b0 = 0; b0 < N; b0 += red_rows) {
+        if (b0) __syncwarp();
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            if (i >= b0 && i < b0 + red_rows) red[(i - b0) * kRedPitch + lane] = acc[i];
         __syncwarp();
-        if (lane < R && b * R + lane < N) {
-            const double *row = red + lane * kRedPitch;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const int nb = min(red_rows, N - b0);
+        for (int t = lane; t < nb * LPS; t += 32) {
+            const int u = (LPS == 1) ? 0 : t / nb;
+            const int a = t - u * nb;
+            const double *row = red + a * kRedPitch + u * P;
+            double s0 = row[0], s1 = row[1], s2 = row[2], s3 = row[3];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 4; i < P; i += 4) {
                 s0 += row[i];
                 s1 += row[i + 1];
                 s2 += row[i + 2];
                 s3 += row[i + 3];
             }
-            tot[b * R + lane] = (s0 + s1) + (s2 + s3);
+            tot[u * NP + b0 + a] = (s0 + s1) + (s2 + s3);
         }
     }
+    __syncwarp();
 }
 
 // q_j = sum_i f_ij * (s_i / S), accumulated in pool order with separately rounded multiply and add,
@@ -205,19 +187,18 @@ __device__ __noinline__ double exact_colsum(const ScanParams &p, int64_t locus, 
     return s;
 }
 
-// Full reference pipeline for one locus straight from global memory: exact q with NaN handling,
-// missingness, renormalisation over the kept alleles.  Used when a pool has no coverage or when a
-// removed allele carries reads (both rare).  Leaves the re-accumulated totals in tot[].
+// Full reference pipeline for one locus straight from global memory, executed by the whole warp (lane = pool):
+// exact q with NaN handling, missingness, renormalisation over the kept alleles.  Used when a pool has no coverage
+// or when a removed allele carries reads (both rare).  Leaves the re-accumulated totals in tot[0..N).
 template <int A, int K, bool W>
 __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const double *ys, const double *ws,
-                                       double *red, double *tot, int lane, bool decide, unsigned &kept_out) {
+                                       double *tot, int lane, bool decide, unsigned &kept_out) {
     using AC = Acc<A, K, W>;
     const Layout &lay = p.lay;
     const double *fl = p.freq + (size_t)locus * lay.freq_stride();
     const uint32_t *dl = p.depth + (size_t)locus * lay.depth_stride();
-    // 1. keep-mask of the alleles (lane j evaluates column j sequentially)
     unsigned kept = kept_out;
-    if (decide) {  // a pool without coverage poisoned the fast sums: redo the MAF decision exactly
+    if (decide) {  // a pool without coverage poisoned the fast sums: redo the MAF decision exactly (lane j = column j)
         bool keep_j = false;
         if (lane < A) {
             const double q = exact_q(p, locus, lane, ws);
@@ -226,19 +207,16 @@ __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const
         kept = __ballot_sync(PG_FULL_MASK, keep_j) & ((1u << A) - 1u);
         kept_out = kept;
         if (__popc(kept) < 2) return PG_LOCUS_FILTERED;
-    }
-    // 2. missingness on the first kept column: NaN <=> the pool has no coverage (sync.rs:287-299)
-    if (decide) {
+        // missingness on the first kept column: NaN <=> the pool has no coverage (sync.rs:287-299)
         int miss = 0;
         for (int i = lane; i < lay.n; i += 32) miss += (dl[i] == 0u) ? 1 : 0;
         miss = __reduce_add_sync(PG_FULL_MASK, miss);
         if (miss == lay.n) return PG_LOCUS_FILTERED;
         if (((double)miss / (double)lay.n) > p.max_miss) return PG_LOCUS_FILTERED;
     }
-    // 3. re-accumulate over the renormalised frequencies
-    double acc[AC::NP];
+    double acc[AC::N];
 #pragma unroll
-    for (int i = 0; i < AC::NP; i++) acc[i] = 0.0;
+    for (int i = 0; i < AC::N; i++) acc[i] = 0.0;
     int i0 = 0;
     for (int c = 0; c < lay.n_chunks; c++) {
         const int rcc = (c == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
@@ -255,16 +233,16 @@ __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const
         }
         i0 += rcc;
     }
-    __syncwarp();
-    reduce_store<AC::N, AC::NP, WarpSmem<A, K, W>::RED_ROWS>(acc, red, tot, lane);
+    // fixed-order butterfly: every lane ends up with the same total
+#pragma unroll
+    for (int i = 0; i < AC::N; i++) {
+        double v = acc[i];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(PG_FULL_MASK, v, off);
+        if (lane == 0) tot[i] = v;
+    }
     __syncwarp();
     return PG_LOCUS_OK;
-}
-
-__device__ __forceinline__ uint64_t pack_sel(int status, int nslots, const int *cols, unsigned kept) {
-    uint64_t v = (uint64_t)(status & 0xff) | ((uint64_t)(nslots & 0xff) << 8) | ((uint64_t)(kept & 0x3f) << 40);
-    for (int s = 0; s < PG_MAX_SLOTS; s++) v |= (uint64_t)(cols[s] & 0xf) << (16 + 4 * s);
-    return v;
 }
 
 // Cholesky of the m x m SPD matrix S (lower triangle filled) -> Li = L^-1 (lower), dg = diag(S^-1)
@@ -465,87 +443,6 @@ __device__ __noinline__ void explicit_corr_nan(const ScanParams &p, int64_t locu
         }
 }
 
-// ---- end of a locus (all lanes, warp uniform): keep-mask and allele order from the reduced sums ---------------
-template <int A, int K, bool W>
-__device__ __noinline__ uint64_t decide_locus(const ScanParams &p, int64_t locus, double *tg, double *red, unsigned dm,
-                                              const double *ys, const double *ws, int lane, double tol_rel) {
-    using AC = Acc<A, K, W>;
-    int status = PG_LOCUS_OK;
-    unsigned kept = 0;
-    bool slow = false;
-    if ((double)dm < p.min_depth_f) {
-        status = PG_LOCUS_FILTERED;  // sync.rs:217-229
-    } else if (dm == 0u) {
-        slow = true;  // a pool without coverage: NaN frequencies
-    } else {
-#pragma unroll
-        for (int j = 0; j < A; j++) {
-            double qj = W ? tg[AC::Q0 + j] : tg[AC::S0 + j] * p.w_uniform;
-            const double tl = tol_rel * fmax(fabs(qj), 1.0);
-            if (fabs(qj - p.maf) <= tl || fabs(qj - p.one_minus_maf) <= tl) qj = exact_q(p, locus, j, ws);
-            if (!((qj < p.maf) | (qj > p.one_minus_maf))) kept |= 1u << j;
-        }
-        if (__popc(kept) < 2) {
-            status = PG_LOCUS_FILTERED;  // sync.rs:284-286
-        } else {
-#pragma unroll
-            for (int j = 0; j < A; j++)
-                if (!((kept >> j) & 1u) && tg[AC::S0 + j] > 0.0) slow = true;  // a removed allele carries reads
-        }
-    }
-    if (slow) status = slow_locus<A, K, W>(p, locus, ys, ws, red, tg, lane, dm == 0u, kept);
-    int cols[PG_MAX_SLOTS] = {0, 0, 0, 0, 0};
-    int nslots = 0;
-    if (status == PG_LOCUS_OK) {
-        nslots = __popc(kept) - 1;
-        if (p.kind == PG_KIND_OLS) {
-            // stable sort by decreasing column sum, drop the first (major) allele (sync.rs:478-505, ols.rs:227-230)
-            double cs[A];
-            bool tie = false;
-#pragma unroll
-            for (int j = 0; j < A; j++) cs[j] = tg[AC::S0 + j];
-#pragma unroll
-            for (int j = 0; j < A; j++)
-#pragma unroll
-                for (int l = j + 1; l < A; l++)
-                    if (((kept >> j) & 1u) && ((kept >> l) & 1u) &&
-                        fabs(cs[j] - cs[l]) <= tol_rel * fmax(fabs(cs[j]), fabs(cs[l])))
-                        tie = true;
-            if (tie) {
-                double mine = 0.0;
-                if (lane < A && ((kept >> lane) & 1u)) mine = exact_colsum<A>(p, locus, lane, kept);
-#pragma unroll
-                for (int j = 0; j < A; j++) cs[j] = __shfl_sync(PG_FULL_MASK, mine, j);
-            }
-#pragma unroll
-            for (int j = 0; j < A; j++) {
-                if (!((kept >> j) & 1u)) continue;
-                int rank = 0;
-#pragma unroll
-                for (int l = 0; l < A; l++) {
-                    if (l == j || !((kept >> l) & 1u)) continue;
-                    if (cs[l] > cs[j] || (cs[l] == cs[j] && l < j)) rank++;
-                }
-#pragma unroll
-                for (int s = 0; s < PG_MAX_SLOTS; s++)
-                    if (rank == s + 1) cols[s] = j;
-            }
-        } else {
-            // kept columns in file order, the last one is dropped (correlation_test.rs:94-98)
-            int sidx = 0;
-#pragma unroll
-            for (int j = 0; j < A; j++) {
-                if (!((kept >> j) & 1u)) continue;
-#pragma unroll
-                for (int ss = 0; ss < PG_MAX_SLOTS; ss++)
-                    if (ss == sidx && sidx < nslots) cols[ss] = j;
-                sidx++;
-            }
-        }
-    }
-    return pack_sel(status, nslots, cols, kept);
-}
-
 // Single-pass OLS from the reduced sums for M regressors, fully unrolled so that every matrix lives in registers
 // (the generic chol_inv / solve_rhs above index local arrays dynamically and are kept for the two-pass fallback).
 // Returns false when the centred X'X is not positive definite; sets redo when the single-pass form loses digits.
@@ -567,7 +464,7 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, const double *tg
 #pragma unroll
         for (int b = 0; b <= a; b++) {
             const int lo = c[a] < c[b] ? c[a] : c[b], hi = c[a] < c[b] ? c[b] : c[a];
-            const double raw = tg[AC::tri(lo, hi)];
+            const double raw = tg[AC::P0 + lo * A - lo * (lo - 1) / 2 + (hi - lo)];
             S[a][b] = raw - sx[a] * sx[b] * inv_n;
             if (a == b) amp = fmax(amp, raw / S[a][a]);
         }
@@ -643,89 +540,9 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, const double *tg
     return true;
 }
 
-// ---- phase 2 (one lane per locus): centred normal equations -> (beta | r, var) per (allele slot, phenotype) -------
-template <int A, int K, bool W>
-__device__ __noinline__ uint64_t solve_locus(const ScanParams &p, int64_t locus, const double *tg, uint64_t sv,
-                                             const double *ys, double *tbg) {
-    using AC = Acc<A, K, W>;
-    const Layout &lay = p.lay;
-    const double nn = (double)lay.n;
-    int status = (int)(sv & 0xff);
-    const int m = (int)((sv >> 8) & 0xff);
-    int cols[PG_MAX_SLOTS];
-#pragma unroll
-    for (int s = 0; s < PG_MAX_SLOTS; s++) cols[s] = (int)((sv >> (16 + 4 * s)) & 0xf);
-    double fmean[PG_MAX_SLOTS];
-    if (status == PG_LOCUS_OK) {
-        double sx[PG_MAX_SLOTS], xbar[PG_MAX_SLOTS];
-        bool has_nan = false;
-        for (int a = 0; a < m; a++) {
-            sx[a] = tg[AC::S0 + cols[a]];
-            const double pjj = tg[AC::tri(cols[a], cols[a])];
-            has_nan |= (pjj != pjj);
-            xbar[a] = sx[a] / nn;
-            fmean[a] = (pjj != pjj) ? nan("") : xbar[a];
-        }
-        const unsigned keptm = (unsigned)((sv >> 40) & 0x3f);
-        if (p.kind == PG_KIND_OLS) {
-            if (lay.n < m + 1) {
-                status = PG_LOCUS_UNSUPPORTED;
-            } else if (has_nan) {
-                for (int i = 0; i < m * K * 2; i++) tbg[i] = nan("");
-            } else {
-                bool redo = false;
-                switch (m) {
-                    case 1: ols_gram_m<1, A, K, W>(p, tg, cols, nn, tbg, redo); break;
-                    case 2:
-                        if constexpr (A >= 3) ols_gram_m<2, A, K, W>(p, tg, cols, nn, tbg, redo);
-                        break;
-                    case 3:
-                        if constexpr (A >= 4) ols_gram_m<3, A, K, W>(p, tg, cols, nn, tbg, redo);
-                        break;
-                    case 4:
-                        if constexpr (A >= 5) ols_gram_m<4, A, K, W>(p, tg, cols, nn, tbg, redo);
-                        break;
-                    default:
-                        if constexpr (A >= 6) ols_gram_m<5, A, K, W>(p, tg, cols, nn, tbg, redo);
-                        break;
-                }
-                if (redo) status = explicit_locus<A, K>(p, locus, keptm, m, cols, xbar, ys, tbg);
-            }
-        } else {
-            bool redo = false;
-            for (int a = 0; a < m; a++) {
-                const double raw = tg[AC::tri(cols[a], cols[a])];
-                const double sxx = raw - sx[a] * sx[a] / nn;
-                if (!(raw <= 1e4 * sxx)) redo = true;
-                for (int k = 0; k < K; k++) {
-                    const double sxy = tg[AC::C0 + cols[a] * K + k] - sx[a] * p.ysum[k] / nn;
-                    tbg[(a * K + k) * 2 + 0] = sxy / (sqrt(sxx) * sqrt(p.syy[k]));
-                    tbg[(a * K + k) * 2 + 1] = 0.0;
-                }
-            }
-            if (has_nan)
-                explicit_corr_nan<A, K>(p, locus, keptm, m, cols, ys, tbg);
-            else if (redo)
-                explicit_locus<A, K>(p, locus, keptm, m, cols, xbar, ys, tbg);
-        }
-        if (status != PG_LOCUS_OK) sv = (sv & ~(uint64_t)0xff) | (uint64_t)status;
-    }
-    if (p.write_meta) {
-        uint64_t mv = (uint64_t)status;
-        if (status == PG_LOCUS_OK) {
-            mv |= (uint64_t)m << 8;
-            for (int s = 0; s < m; s++) mv |= (uint64_t)p.codes[cols[s]] << (16 + 8 * s);
-        }
-        p.meta[locus] = mv;
-        for (int s = 0; s < A - 1; s++)
-            p.freq_mean[(size_t)locus * (A - 1) + s] = (status == PG_LOCUS_OK && s < m) ? fmean[s] : nan("");
-    }
-    return sv;
-}
-
-// ---- phase 3 (one lane per (locus, allele slot, phenotype)): t and p --------------------------------------------
-static __device__ __noinline__ void finish_task(const ScanParams &p, const PTableDev &ptab, bool valid, double v0, double v1,
-                                         double *o) {
+// t and the two-sided p-value of one (allele slot, phenotype) record; o -> 4 doubles
+static __device__ __noinline__ void finish_task(const ScanParams &p, const PTableDev &ptab, bool valid, double v0,
+                                                double v1, double *o) {
     const double nn = (double)p.lay.n;
     double o0 = nan(""), o1 = nan(""), o2 = nan(""), o3 = nan("");
     if (valid) {
@@ -766,185 +583,419 @@ static __device__ __noinline__ void finish_task(const ScanParams &p, const PTabl
     *reinterpret_cast<double2 *>(o + 2) = make_double2(o2, o3);
 }
 
-constexpr int kMaxWarps = 16;
-
+// ---- phase 2, second half (one lane per locus): allele order, centred normal equations, records ----------------
 template <int A, int K, bool W>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) scan_kernel(const ScanParams p) {
+__device__ __noinline__ void finish_locus(const ScanParams &p, const PTableDev &ptab, int64_t locus, const double *tg,
+                                          int status, unsigned kept, const double *ys) {
     using AC = Acc<A, K, W>;
-    using WS = WarpSmem<A, K, W>;
-    constexpr int T = WS::T;
-    constexpr int G = WS::G;
+    constexpr int T = (A - 1) * K;
+    const Layout &lay = p.lay;
+    const double nn = (double)lay.n;
+    const double tol_rel = 2.0 * (nn + 8.0) * kEps;
+    int cols[PG_MAX_SLOTS] = {0, 0, 0, 0, 0};
+    int m = 0;
+    double tb[T * 2];
+#pragma unroll
+    for (int i = 0; i < T * 2; i++) tb[i] = nan("");
+    double fmean[A - 1];
+#pragma unroll
+    for (int s = 0; s < A - 1; s++) fmean[s] = nan("");
+    if (status == PG_LOCUS_OK) {
+        m = __popc(kept) - 1;
+        if (p.kind == PG_KIND_OLS) {
+            // stable sort by decreasing column sum, drop the first (major) allele (sync.rs:478-505, ols.rs:227-230)
+            double cs[A];
+            bool tie = false;
+#pragma unroll
+            for (int j = 0; j < A; j++) cs[j] = tg[AC::S0 + j];
+#pragma unroll
+            for (int j = 0; j < A; j++)
+#pragma unroll
+                for (int l = j + 1; l < A; l++)
+                    if (((kept >> j) & 1u) && ((kept >> l) & 1u) &&
+                        fabs(cs[j] - cs[l]) <= tol_rel * fmax(fabs(cs[j]), fabs(cs[l])))
+                        tie = true;
+            if (tie) {
+#pragma unroll
+                for (int j = 0; j < A; j++)
+                    if ((kept >> j) & 1u) cs[j] = exact_colsum<A>(p, locus, j, kept);
+            }
+#pragma unroll
+            for (int j = 0; j < A; j++) {
+                if (!((kept >> j) & 1u)) continue;
+                int rank = 0;
+#pragma unroll
+                for (int l = 0; l < A; l++) {
+                    if (l == j || !((kept >> l) & 1u)) continue;
+                    if (cs[l] > cs[j] || (cs[l] == cs[j] && l < j)) rank++;
+                }
+#pragma unroll
+                for (int s = 0; s < PG_MAX_SLOTS; s++)
+                    if (rank == s + 1) cols[s] = j;
+            }
+        } else {
+            // kept columns in file order, the last one is dropped (correlation_test.rs:94-98)
+            int sidx = 0;
+#pragma unroll
+            for (int j = 0; j < A; j++) {
+                if (!((kept >> j) & 1u)) continue;
+#pragma unroll
+                for (int ss = 0; ss < PG_MAX_SLOTS; ss++)
+                    if (ss == sidx && sidx < m) cols[ss] = j;
+                sidx++;
+            }
+        }
+        double sx[PG_MAX_SLOTS], xbar[PG_MAX_SLOTS];
+        bool has_nan = false;
+#pragma unroll
+        for (int a = 0; a < A - 1; a++) {
+            if (a < m) {
+                sx[a] = tg[AC::S0 + cols[a]];
+                const double pjj = tg[AC::P0 + cols[a] * A - cols[a] * (cols[a] - 1) / 2];
+                has_nan |= (pjj != pjj);
+                xbar[a] = sx[a] / nn;
+                fmean[a] = (pjj != pjj) ? nan("") : xbar[a];
+            }
+        }
+        if (p.kind == PG_KIND_OLS) {
+            if (lay.n < m + 1) {
+                status = PG_LOCUS_UNSUPPORTED;
+            } else if (!has_nan) {
+                bool redo = false;
+                switch (m) {
+                    case 1: ols_gram_m<1, A, K, W>(p, tg, cols, nn, tb, redo); break;
+                    case 2:
+                        if constexpr (A >= 3) ols_gram_m<2, A, K, W>(p, tg, cols, nn, tb, redo);
+                        break;
+                    case 3:
+                        if constexpr (A >= 4) ols_gram_m<3, A, K, W>(p, tg, cols, nn, tb, redo);
+                        break;
+                    case 4:
+                        if constexpr (A >= 5) ols_gram_m<4, A, K, W>(p, tg, cols, nn, tb, redo);
+                        break;
+                    default:
+                        if constexpr (A >= 6) ols_gram_m<5, A, K, W>(p, tg, cols, nn, tb, redo);
+                        break;
+                }
+                if (redo) status = explicit_locus<A, K>(p, locus, kept, m, cols, xbar, ys, tb);
+            }
+        } else {
+            bool redo = false;
+#pragma unroll
+            for (int a = 0; a < A - 1; a++) {
+                if (a < m) {
+                    const double raw = tg[AC::P0 + cols[a] * A - cols[a] * (cols[a] - 1) / 2];
+                    const double sxx = raw - sx[a] * sx[a] / nn;
+                    if (!(raw <= 1e4 * sxx)) redo = true;
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        const double sxy = tg[AC::C0 + cols[a] * K + k] - sx[a] * p.ysum[k] / nn;
+                        tb[(a * K + k) * 2 + 0] = sxy / (sqrt(sxx) * sqrt(p.syy[k]));
+                        tb[(a * K + k) * 2 + 1] = 0.0;
+                    }
+                }
+            }
+            if (has_nan)
+                explicit_corr_nan<A, K>(p, locus, kept, m, cols, ys, tb);
+            else if (redo)
+                explicit_locus<A, K>(p, locus, kept, m, cols, xbar, ys, tb);
+        }
+    }
+    if (p.write_meta) {
+        uint64_t mv = (uint64_t)status;
+        if (status == PG_LOCUS_OK) {
+            mv |= (uint64_t)m << 8;
+#pragma unroll
+            for (int s = 0; s < A - 1; s++)
+                if (s < m) mv |= (uint64_t)p.codes[cols[s]] << (16 + 8 * s);
+        }
+        p.meta[locus] = mv;
+#pragma unroll
+        for (int s = 0; s < A - 1; s++)
+            p.freq_mean[(size_t)locus * (A - 1) + s] = (status == PG_LOCUS_OK && s < m) ? fmean[s] : nan("");
+    }
+#pragma unroll
+    for (int s = 0; s < A - 1; s++)
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double *o = p.stats + (((size_t)locus * (A - 1) + s) * p.k_total + p.phen_base + k) * 4;
+            finish_task(p, ptab, status == PG_LOCUS_OK && s < m, tb[(s * K + k) * 2 + 0], tb[(s * K + k) * 2 + 1], o);
+        }
+}
+
+// ---- phase 2 (lane = locus of the block): keep-mask from the totals, cooperative exact / slow paths, records ----
+template <int A, int K, bool W>
+__device__ __noinline__ void epilogue(const ScanParams &p, int64_t l0, int cnt, double *tot, const double *ys,
+                                      const double *ws, int lane) {
+    using AC = Acc<A, K, W>;
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
+    const bool act = lane < cnt;
+    const int64_t locus = l0 + lane;
+    double *tg = tot + (size_t)lane * AC::NP;
+    const double tol_rel = 2.0 * ((double)p.lay.n + 8.0) * kEps;
+    int status = PG_LOCUS_FILTERED;
+    unsigned kept = 0, exact_bits = 0;
+    bool slow = false, slow_decide = false;
+    double q[A];
+#pragma unroll
+    for (int j = 0; j < A; j++) q[j] = 0.0;
+    if (act) {
+        const unsigned dm = p.dmin[locus];
+        if ((double)dm < p.min_depth_f) {
+            status = PG_LOCUS_FILTERED;  // sync.rs:217-229
+        } else if (dm == 0u) {
+            status = PG_LOCUS_OK;  // a pool without coverage: NaN frequencies, decided on the slow path
+            slow = slow_decide = true;
+        } else {
+            status = PG_LOCUS_OK;
+#pragma unroll
+            for (int j = 0; j < A; j++) {
+                q[j] = W ? tg[AC::Q0 + j] : tg[AC::S0 + j] * p.w_uniform;
+                const double tl = tol_rel * fmax(fabs(q[j]), 1.0);
+                if (fabs(q[j] - p.maf) <= tl || fabs(q[j] - p.one_minus_maf) <= tl) exact_bits |= 1u << j;
+            }
+        }
+    }
+    // thresholds hit within rounding: lane j re-evaluates q_j of that locus in the reference's order
+    unsigned need = __ballot_sync(PG_FULL_MASK, exact_bits != 0u);
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const unsigned bits = __shfl_sync(PG_FULL_MASK, exact_bits, src);
+        double qe = 0.0;
+        if (lane < A && ((bits >> lane) & 1u)) qe = exact_q(p, l0 + src, lane, ws);
+#pragma unroll
+        for (int j = 0; j < A; j++) {
+            const double v = __shfl_sync(PG_FULL_MASK, qe, j);
+            if (lane == src && ((bits >> j) & 1u)) q[j] = v;
+        }
+    }
+    if (act && status == PG_LOCUS_OK && !slow) {
+#pragma unroll
+        for (int j = 0; j < A; j++)
+            if (!((q[j] < p.maf) | (q[j] > p.one_minus_maf))) kept |= 1u << j;
+        if (__popc(kept) < 2) {
+            status = PG_LOCUS_FILTERED;  // sync.rs:284-286
+        } else {
+#pragma unroll
+            for (int j = 0; j < A; j++)
+                if (!((kept >> j) & 1u) && tg[AC::S0 + j] > 0.0) slow = true;  // a removed allele carries reads
+        }
+    }
+    need = __ballot_sync(PG_FULL_MASK, act && slow && status == PG_LOCUS_OK);
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const bool dec = __shfl_sync(PG_FULL_MASK, (int)slow_decide, src) != 0;
+        unsigned kk = __shfl_sync(PG_FULL_MASK, kept, src);
+        const int st = slow_locus<A, K, W>(p, l0 + src, ys, ws, tot + (size_t)src * AC::NP, lane, dec, kk);
+        if (lane == src) {
+            status = st;
+            kept = kk;
+        }
+    }
+    __syncwarp();
+    if (act) finish_locus<A, K, W>(p, ptab, locus, tg, status, kept, ys);
+    __syncwarp();
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------
+template <int A, int K, bool W, int P>
+__global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const ScanParams p) {
+    using AC = Acc<A, K, W>;
+    constexpr int G = block_loci(P);
+    constexpr int LPS = 32 / P;  // loci per stage
     extern __shared__ __align__(128) unsigned char smem[];
     const Layout lay = p.lay;
     const int n_pad = lay.n_pad;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     double *ys = reinterpret_cast<double *>(smem);
     double *ws = W ? ys + (size_t)K * n_pad : nullptr;
-    unsigned char *wb = smem + scan_common_bytes(K, n_pad, W) + (size_t)warp * WS::bytes;
+    unsigned char *wb = smem + p.common_bytes + (size_t)warp * p.warp_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(wb);
-    double *fbuf = reinterpret_cast<double *>(wb + WS::off_f);
-    uint32_t *dbuf = reinterpret_cast<uint32_t *>(wb + WS::off_d);
-    double *tot = reinterpret_cast<double *>(wb + WS::off_tot);
-    uint64_t *sel = reinterpret_cast<uint64_t *>(wb + WS::off_sel);
-    double *tb = reinterpret_cast<double *>(wb + WS::off_tb);
+    unsigned char *stage0 = wb + 64;
+    double *tot = reinterpret_cast<double *>(stage0 + (size_t)p.nbuf * p.stage_bytes);
+    const int nbuf = p.nbuf;
+    const int red_rows = min((int)(p.stage_bytes / (kRedPitch * 8)), AC::N);
 
     for (int i = threadIdx.x; i < K * n_pad; i += blockDim.x) ys[i] = p.yc[i];
     if (W)
         for (int i = threadIdx.x; i < n_pad; i += blockDim.x) ws[i] = p.w[i];
     if (lane == 0) {
-        for (int b = 0; b < kNBuf; b++) mbar_init(&bars[b], 1);
+        for (int b = 0; b < nbuf; b++) mbar_init(&bars[b], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
     const int64_t L = p.n_loci;
-    const int64_t NG = (L + G - 1) / G;
-    const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;  // consecutive warps take consecutive groups
+    const int64_t NB = (L + G - 1) / G;
+    const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;  // consecutive warps take consecutive blocks
     const int64_t TW = (int64_t)gridDim.x * nwarps;
-    if (gw >= NG) return;
+    if (gw >= NB) return;
     const int n_chunks = lay.n_chunks;
-    const size_t fstride = lay.freq_stride(), dstride = lay.depth_stride();
-    const double tol_rel = 2.0 * ((double)lay.n + 8.0) * kEps;
-    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
+    const size_t fstride = lay.freq_stride();
 
-    // producer side of the warp's private ring: the tile stream is (group, locus in group, chunk), and only the
-    // last group of the job can be short, so the stream of a warp simply ends at the first locus >= L.  All of the
-    // iterator state is plain scalars so that it stays in registers.
-    int64_t i_group = gw, i_locus = gw * G;
-    int i_li = 0, i_chunk = 0;
+    // producer side of the ring: the stage stream of this warp in consumption order, nbuf stages ahead
+    int64_t i_blk = gw;
+    int i_sub = 0, i_chunk = 0;  // P = 32: locus in block, chunk;  P < 32: stage in block
     bool i_done = false;
-#define PG_ISSUE_NEXT(BUF)                                                                                  \
-    do {                                                                                                    \
-        if (!i_done) {                                                                                      \
-            if (lane == 0) {                                                                                \
-                const int rcc_ = (i_chunk == n_chunks - 1) ? lay.rc_last : lay.rc;                          \
-                const uint32_t fbytes_ = (uint32_t)(A * rcc_ * 8), dbytes_ = (uint32_t)(rcc_ * 4);          \
-                const double *fsrc_ = p.freq + (size_t)i_locus * fstride + (size_t)i_chunk * A * lay.rc;    \
-                const uint32_t *dsrc_ = p.depth + (size_t)i_locus * dstride + (size_t)i_chunk * lay.rc;     \
-                fence_proxy_async(); /* the buffer may have served as reduction scratch (generic writes) */ \
-                mbar_expect_tx(&bars[BUF], fbytes_ + dbytes_);                                              \
-                bulk_g2s(fbuf + (size_t)(BUF) * (WS::fbuf_bytes / 8), fsrc_, fbytes_, &bars[BUF]);          \
-                bulk_g2s(dbuf + (size_t)(BUF) * (WS::dbuf_bytes / 4), dsrc_, dbytes_, &bars[BUF]);          \
-            }                                                                                               \
-            if (++i_chunk == n_chunks) {                                                                    \
-                i_chunk = 0;                                                                                \
-                i_locus++;                                                                                  \
-                if (++i_li == G) {                                                                          \
-                    i_li = 0;                                                                               \
-                    i_group += TW;                                                                          \
-                    i_locus = i_group * G;                                                                  \
-                    if (i_group >= NG) i_done = true;                                                       \
-                }                                                                                           \
-                if (i_locus >= L) i_done = true;                                                            \
-            }                                                                                               \
-        }                                                                                                   \
-    } while (0)
-#pragma unroll
-    for (int b = 0; b < kNBuf; b++) PG_ISSUE_NEXT(b);
+    auto issue_next = [&](int b) {
+        if (i_done) return;
+        const int64_t bl0 = i_blk * G;
+        const int bcnt = (int)min((int64_t)G, L - bl0);
+        const double *src;
+        uint32_t bytes;
+        if (P == 32) {
+            const int rcc = (i_chunk == n_chunks - 1) ? lay.rc_last : lay.rc;
+            src = p.freq + (size_t)(bl0 + i_sub) * fstride + (size_t)i_chunk * A * lay.rc;
+            bytes = (uint32_t)(A * rcc * 8);
+        } else {
+            const int nl = min(LPS, bcnt - i_sub * LPS);
+            src = p.freq + (size_t)(bl0 + i_sub * LPS) * fstride;
+            bytes = (uint32_t)(nl * (int)fstride * 8);
+        }
+        if (lane == 0) {
+            fence_proxy_async();  // the buffer served as reduction scratch (generic-proxy writes)
+            mbar_expect_tx(&bars[b], bytes);
+            bulk_g2s(stage0 + (size_t)b * p.stage_bytes, src, bytes, &bars[b]);
+        }
+        bool next_block = false;
+        if (P == 32) {
+            if (++i_chunk == n_chunks) {
+                i_chunk = 0;
+                if (++i_sub == bcnt) next_block = true;
+            }
+        } else {
+            if (++i_sub * LPS >= bcnt) next_block = true;
+        }
+        if (next_block) {
+            i_sub = 0;
+            i_blk += TW;
+            if (i_blk >= NB) i_done = true;
+        }
+    };
+    for (int b = 0; b < nbuf; b++) issue_next(b);
 
-    uint32_t phase_bits = 0;  // bit b = parity to wait for on buffer b
     int buf = 0;
-    for (int64_t group = gw; group < NG; group += TW) {
-        const int64_t gl0 = group * G;
-        const int gn = (int)min((int64_t)G, L - gl0);  // loci of this group
-        for (int g = 0; g < gn; g++) {
-            const int64_t locus = gl0 + g;
-            double acc[AC::NP];
+    uint32_t parity = 0;
+    for (int64_t blk = gw; blk < NB; blk += TW) {
+        const int64_t l0 = blk * G;
+        const int cnt = (int)min((int64_t)G, L - l0);
+        if (P == 32) {
+            for (int g = 0; g < cnt; g++) {
+                double acc[AC::N];
 #pragma unroll
-            for (int i = 0; i < AC::NP; i++) acc[i] = 0.0;
-            unsigned dmin = 0xFFFFFFFFu;
-            double *red = nullptr;
-            for (int chunk = 0; chunk < n_chunks; chunk++) {
-                const int rcc = (chunk == n_chunks - 1) ? lay.rc_last : lay.rc;
-                const int row0 = chunk * lay.rc;
-                mbar_wait(&bars[buf], (phase_bits >> buf) & 1u);
-                phase_bits ^= (1u << buf);
-                const double *fb = fbuf + (size_t)buf * (WS::fbuf_bytes / 8);
-                const uint32_t *db = dbuf + (size_t)buf * (WS::dbuf_bytes / 4);
-                // ---- phase 1: lane handles rows 2*lane, 2*lane+1 (+64 ...) with 128-bit shared loads
-                for (int r = 2 * lane; r < ((p.debug & 1) ? 0 : rcc); r += 64) {
-                    double2 f2[A];
+                for (int i = 0; i < AC::N; i++) acc[i] = 0.0;
+                for (int chunk = 0; chunk < n_chunks; chunk++) {
+                    const int rcc = (chunk == n_chunks - 1) ? lay.rc_last : lay.rc;
+                    const double *yrow = ys + chunk * lay.rc;
+                    mbar_wait(&bars[buf], parity);
+                    double *fb = reinterpret_cast<double *>(stage0 + (size_t)buf * p.stage_bytes);
+#pragma unroll 2
+                    for (int r = 2 * lane; r < rcc; r += 64) {
+                        double2 f2[A], y2[K];
 #pragma unroll
-                    for (int j = 0; j < A; j++) f2[j] = *reinterpret_cast<const double2 *>(fb + (size_t)j * rcc + r);
-                    const uint2 d2 = *reinterpret_cast<const uint2 *>(db + r);
-                    double2 y2[K];
+                        for (int j = 0; j < A; j++) f2[j] = *reinterpret_cast<const double2 *>(fb + (size_t)j * rcc + r);
 #pragma unroll
-                    for (int k = 0; k < K; k++)
-                        y2[k] = *reinterpret_cast<const double2 *>(ys + (size_t)k * n_pad + row0 + r);
-                    double2 w2 = make_double2(0.0, 0.0);
-                    if (W) w2 = *reinterpret_cast<const double2 *>(ws + row0 + r);
-                    dmin = min(dmin, min(d2.x, d2.y));
-                    double fa[A], ya[K];
+                        for (int k = 0; k < K; k++) y2[k] = *reinterpret_cast<const double2 *>(yrow + (size_t)k * n_pad + r);
+                        double2 w2 = make_double2(0.0, 0.0);
+                        if (W) w2 = *reinterpret_cast<const double2 *>(ws + chunk * lay.rc + r);
+                        accum_pair<A, K, W>(acc, f2, y2, w2);
+                    }
+                    __syncwarp();
+                    if (chunk == n_chunks - 1)
+                        reduce_to_tot<AC::N, AC::NP, 32>(acc, fb, red_rows, tot + (size_t)g * AC::NP, lane);
+                    issue_next(buf);  // refill this buffer with the stage nbuf ahead
+                    if (++buf == nbuf) {
+                        buf = 0;
+                        parity ^= 1u;
+                    }
+                }
+            }
+        } else {
+            const int u = lane / P, q0 = lane % P;
+            const int nsteps = (cnt + LPS - 1) / LPS;
+            for (int s = 0; s < nsteps; s++) {
+                double acc[AC::N];
 #pragma unroll
-                    for (int j = 0; j < A; j++) fa[j] = f2[j].x;
+                for (int i = 0; i < AC::N; i++) acc[i] = 0.0;
+                mbar_wait(&bars[buf], parity);
+                double *fb = reinterpret_cast<double *>(stage0 + (size_t)buf * p.stage_bytes);
+                if (s * LPS + u < cnt) {  // the stage holds only the loci that exist
+                    const double *fl = fb + (size_t)u * fstride;
+#pragma unroll 2
+                    for (int r = 2 * q0; r < n_pad; r += 2 * P) {
+                        double2 f2[A], y2[K];
 #pragma unroll
-                    for (int k = 0; k < K; k++) ya[k] = y2[k].x;
-                    accum_row<A, K, W, false>(acc, fa, ya, w2.x);
+                        for (int j = 0; j < A; j++) f2[j] = *reinterpret_cast<const double2 *>(fl + (size_t)j * n_pad + r);
 #pragma unroll
-                    for (int j = 0; j < A; j++) fa[j] = f2[j].y;
-#pragma unroll
-                    for (int k = 0; k < K; k++) ya[k] = y2[k].y;
-                    accum_row<A, K, W, false>(acc, fa, ya, w2.y);
+                        for (int k = 0; k < K; k++) y2[k] = *reinterpret_cast<const double2 *>(ys + (size_t)k * n_pad + r);
+                        double2 w2 = make_double2(0.0, 0.0);
+                        if (W) w2 = *reinterpret_cast<const double2 *>(ws + r);
+                        accum_pair<A, K, W>(acc, f2, y2, w2);
+                    }
                 }
                 __syncwarp();
-                if (chunk == n_chunks - 1 && !(p.debug & 2)) {
-                    // the buffer just consumed doubles as the reduction scratch before it is refilled
-                    red = const_cast<double *>(fb);
-                    double *tg = tot + (size_t)g * AC::NP;
-                    const unsigned dm = __reduce_min_sync(PG_FULL_MASK, dmin);
-                    reduce_store<AC::N, AC::NP, WS::RED_ROWS>(acc, red, tg, lane);
-                    __syncwarp();
-                    const uint64_t sv = decide_locus<A, K, W>(p, locus, tg, red, dm, ys, ws, lane, tol_rel);
-                    if (lane == 0) sel[g] = sv;
-                    __syncwarp();
+                reduce_to_tot<AC::N, AC::NP, P>(acc, fb, red_rows, tot + (size_t)(s * LPS) * AC::NP, lane);
+                issue_next(buf);
+                if (++buf == nbuf) {
+                    buf = 0;
+                    parity ^= 1u;
                 }
-                PG_ISSUE_NEXT(buf);  // refill this buffer with the tile kNBuf ahead
-                buf = (buf + 1 == kNBuf) ? 0 : buf + 1;
             }
         }
-        // ---- phase 2: lane = locus of the group
-        __syncwarp();
-        if (p.debug & 4) continue;
-        if (lane < gn) {
-            const uint64_t sv = solve_locus<A, K, W>(p, gl0 + lane, tot + (size_t)lane * AC::NP, sel[lane], ys,
-                                                     tb + (size_t)lane * T * 2);
-            sel[lane] = sv;
-        }
-        __syncwarp();
-        // ---- phase 3: lane = (locus, allele slot, phenotype)
-        for (int task = lane; task < ((p.debug & 8) ? 0 : gn * T); task += 32) {
-            const int g = task / T, rem = task - g * T;
-            const int slot = rem / K, kk = rem - slot * K;
-            const uint64_t sv = sel[g];
-            const bool valid = ((int)(sv & 0xff) == PG_LOCUS_OK) && slot < (int)((sv >> 8) & 0xff);
-            const double v0 = tb[((size_t)g * T + slot * K + kk) * 2 + 0];
-            const double v1 = tb[((size_t)g * T + slot * K + kk) * 2 + 1];
-            double *o = p.stats + (((size_t)(gl0 + g) * (A - 1) + slot) * p.k_total + p.phen_base + kk) * 4;
-            finish_task(p, ptab, valid, v0, v1, o);
-        }
-        __syncwarp();
+        epilogue<A, K, W>(p, l0, cnt, tot, ys, ws, lane);
     }
-#undef PG_ISSUE_NEXT
 }
 
-template <int A, int K, bool W>
-cudaError_t launch_scan_t(const ScanParams &p, int sm_count, cudaStream_t s) {
-    using WS = WarpSmem<A, K, W>;
-    const size_t common = scan_common_bytes(K, p.lay.n_pad, W);
+template <int A, int K, bool W, int P>
+cudaError_t launch_scan_p(ScanParams p, int sm_count, cudaStream_t s) {
+    using AC = Acc<A, K, W>;
+    constexpr int G = block_loci(P);
+    const Layout &lay = p.lay;
     const size_t avail = 227 * 1024;
-    if (common + WS::bytes > avail) return cudaErrorInvalidConfiguration;
-    int nwarps = (int)((avail - common) / WS::bytes);
-    if (nwarps > kMaxWarps) nwarps = kMaxWarps;
-    const size_t smem = common + (size_t)nwarps * WS::bytes;
-    auto kern = scan_kernel<A, K, W>;
+    size_t common = (size_t)(K + (W ? 1 : 0)) * lay.n_pad * 8;
+    common = (common + 127) / 128 * 128;
+    size_t stage = (P == 32) ? (size_t)A * lay.rc * 8 : (size_t)(32 / P) * lay.freq_stride() * 8;
+    stage = (stage + 127) / 128 * 128;
+    const size_t tot_bytes = ((size_t)G * AC::NP * 8 + 127) / 128 * 128;
+    // ring depth: 3 stages unless that leaves too few warps to keep the FP64 pipe and the copy engine busy
+    int nbuf = 3, nwarps = 0;
+    size_t wbytes = 0;
+    for (;; nbuf--) {
+        wbytes = 64 + (size_t)nbuf * stage + tot_bytes;
+        nwarps = common + wbytes <= avail ? (int)((avail - common) / wbytes) : 0;
+        if (nwarps > kScanWarps) nwarps = kScanWarps;
+        if (nwarps >= 8 || nbuf == 2) break;
+    }
+    if (p.nbuf_override >= 1 && p.nbuf_override <= 8) {
+        nbuf = p.nbuf_override;
+        wbytes = 64 + (size_t)nbuf * stage + tot_bytes;
+        nwarps = common + wbytes <= avail ? (int)((avail - common) / wbytes) : 0;
+        if (nwarps > kScanWarps) nwarps = kScanWarps;
+    }
+    if (p.warps_override >= 1 && p.warps_override < nwarps) nwarps = p.warps_override;
+    if (nwarps < 1) return cudaErrorInvalidConfiguration;
+    p.common_bytes = (uint32_t)common;
+    p.warp_bytes = (uint32_t)wbytes;
+    p.stage_bytes = (uint32_t)stage;
+    p.nbuf = nbuf;
+    const size_t smem = common + (size_t)nwarps * wbytes;
+    auto kern = scan_kernel<A, K, W, P>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int64_t NG = (p.n_loci + WS::G - 1) / WS::G;
-    int64_t ctas = (NG + nwarps - 1) / nwarps;
+    const int64_t NB = (p.n_loci + G - 1) / G;
+    int64_t ctas = (NB + nwarps - 1) / nwarps;
     if (ctas > sm_count) ctas = sm_count;
     if (ctas < 1) ctas = 1;
     kern<<<(unsigned)ctas, nwarps * 32, smem, s>>>(p);
     return cudaGetLastError();
+}
+
+template <int A, int K, bool W>
+cudaError_t launch_scan_t(const ScanParams &p, int sm_count, cudaStream_t s) {
+    if (p.lay.n_chunks == 1) return launch_scan_p<A, K, W, 8>(p, sm_count, s);
+    return launch_scan_p<A, K, W, 32>(p, sm_count, s);
 }
 
 template <int A>
@@ -953,8 +1004,12 @@ cudaError_t launch_scan_a(const ScanParams &p, int sm_count, cudaStream_t s) {
     switch (p.K) {
         case 1: return w ? launch_scan_t<A, 1, true>(p, sm_count, s) : launch_scan_t<A, 1, false>(p, sm_count, s);
         case 2: return w ? launch_scan_t<A, 2, true>(p, sm_count, s) : launch_scan_t<A, 2, false>(p, sm_count, s);
-        case 3: return w ? launch_scan_t<A, 3, true>(p, sm_count, s) : launch_scan_t<A, 3, false>(p, sm_count, s);
-        case 4: return w ? launch_scan_t<A, 4, true>(p, sm_count, s) : launch_scan_t<A, 4, false>(p, sm_count, s);
+        case 3:
+            if constexpr (A <= 5) return w ? launch_scan_t<A, 3, true>(p, sm_count, s) : launch_scan_t<A, 3, false>(p, sm_count, s);
+            else return cudaErrorInvalidValue;
+        case 4:
+            if constexpr (A <= 4) return w ? launch_scan_t<A, 4, true>(p, sm_count, s) : launch_scan_t<A, 4, false>(p, sm_count, s);
+            else return cudaErrorInvalidValue;
         default: return cudaErrorInvalidValue;
     }
 }
