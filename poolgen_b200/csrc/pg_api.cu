@@ -438,6 +438,7 @@ static int run_once(pg_batch *b, int *launches) {
         const int kpass = pg::max_phen_per_pass(s->A_dev);
         static const int nbuf_env = getenv("PG_NBUF") ? atoi(getenv("PG_NBUF")) : 0;
         static const int warps_env = getenv("PG_WARPS") ? atoi(getenv("PG_WARPS")) : 0;
+        static const int g_env = getenv("PG_G") ? atoi(getenv("PG_G")) : 0;
         for (int base = 0; base < s->k; base += kpass) {
             pg::ScanParams p;
             memset(&p, 0, sizeof p);
@@ -475,6 +476,7 @@ static int run_once(pg_batch *b, int *launches) {
             p.write_meta = base == 0;
             p.nbuf_override = nbuf_env;
             p.warps_override = warps_env;
+            p.g_override = g_env;
             PG_CUDA(ctx, pg::launch_scan(p, ctx->sm_count, b->stream));
             if (launches) (*launches)++;
         }

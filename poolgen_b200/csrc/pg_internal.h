@@ -93,8 +93,8 @@ struct ScanParams {
     int write_meta;             // only the first phenotype pass writes meta / freq_mean
     // launch geometry, filled in by the launcher
     uint32_t common_bytes, warp_bytes, stage_bytes;
-    int nbuf;
-    int nbuf_override, warps_override;  // tuning knobs (PG_NBUF / PG_WARPS), 0 = automatic
+    int nbuf, block_loci;
+    int nbuf_override, warps_override, g_override;  // tuning knobs (PG_NBUF / PG_WARPS / PG_G), 0 = automatic
 };
 
 struct TableParams {

@@ -38,9 +38,6 @@ struct Acc {
     }
 };
 
-// loci per epilogue block: with one locus per stage the totals area is kept small, otherwise fill the 32 lanes
-__host__ __device__ constexpr int block_loci(int P) { return P == 32 ? 16 : 32; }
-
 template <int A, int K, bool W, bool NANAWARE>
 __device__ __forceinline__ void accum_row(double (&acc)[Acc<A, K, W>::N], const double (&f)[A], const double (&y)[K],
                                           double w) {
@@ -187,6 +184,45 @@ __device__ __noinline__ double exact_colsum(const ScanParams &p, int64_t locus, 
     return s;
 }
 
+// Rows i = lane, lane + 32, ... of one locus straight from global memory, four rows per lane in flight:
+// fn(i, f[A], depth_i).  The building block of the warp-cooperative slow paths.
+template <int A, typename Fn>
+__device__ __forceinline__ void for_rows_coop(const ScanParams &p, int64_t locus, int lane, Fn &&fn) {
+    const Layout &lay = p.lay;
+    const double *fl = p.freq + (size_t)locus * lay.freq_stride();
+    const uint32_t *dl = p.depth + (size_t)locus * lay.depth_stride();
+    int i0 = 0;
+    for (int c = 0; c < lay.n_chunks; c++) {
+        const int rcc = (c == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
+        const double *blk = fl + (size_t)c * lay.A * lay.rc;
+        const int rows = min(rcc, lay.n - i0);
+        for (int r0 = 0; r0 < rows; r0 += 128) {
+            double f[4][A];
+            uint32_t d[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int r = r0 + lane + 32 * i;
+                const bool ok = r < rows;
+#pragma unroll
+                for (int j = 0; j < A; j++) f[i][j] = ok ? blk[(size_t)j * rcc + r] : 0.0;
+                d[i] = ok ? dl[i0 + r] : 1u;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int r = r0 + lane + 32 * i;
+                if (r < rows) fn(i0 + r, f[i], d[i]);
+            }
+        }
+        i0 += rcc;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {  // fixed-order butterfly: every lane gets the same bits
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(PG_FULL_MASK, v, off);
+    return v;
+}
+
 // Full reference pipeline for one locus straight from global memory, executed by the whole warp (lane = pool):
 // exact q with NaN handling, missingness, renormalisation over the kept alleles.  Used when a pool has no coverage
 // or when a removed allele carries reads (both rare).  Leaves the re-accumulated totals in tot[0..N).
@@ -195,7 +231,6 @@ __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const
                                        double *tot, int lane, bool decide, unsigned &kept_out) {
     using AC = Acc<A, K, W>;
     const Layout &lay = p.lay;
-    const double *fl = p.freq + (size_t)locus * lay.freq_stride();
     const uint32_t *dl = p.depth + (size_t)locus * lay.depth_stride();
     unsigned kept = kept_out;
     if (decide) {  // a pool without coverage poisoned the fast sums: redo the MAF decision exactly (lane j = column j)
@@ -217,28 +252,17 @@ __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const
     double acc[AC::N];
 #pragma unroll
     for (int i = 0; i < AC::N; i++) acc[i] = 0.0;
-    int i0 = 0;
-    for (int c = 0; c < lay.n_chunks; c++) {
-        const int rcc = (c == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
-        const double *blk = fl + (size_t)c * lay.A * lay.rc;
-        const int rows = min(rcc, lay.n - i0);
-        for (int r = lane; r < rows; r += 32) {
-            double f[A], F[A], y[K];
+    const int n_pad = lay.n_pad;
+    for_rows_coop<A>(p, locus, lane, [&](int i, const double(&f)[A], uint32_t d) {
+        double F[A], y[K];
+        renorm_row<A>(f, d, kept, F);
 #pragma unroll
-            for (int j = 0; j < A; j++) f[j] = blk[(size_t)j * rcc + r];
-            renorm_row<A>(f, dl[i0 + r], kept, F);
-#pragma unroll
-            for (int k = 0; k < K; k++) y[k] = ys[k * lay.n_pad + i0 + r];
-            accum_row<A, K, W, true>(acc, F, y, 0.0);
-        }
-        i0 += rcc;
-    }
-    // fixed-order butterfly: every lane ends up with the same total
+        for (int k = 0; k < K; k++) y[k] = ys[k * n_pad + i];
+        accum_row<A, K, W, true>(acc, F, y, 0.0);
+    });
 #pragma unroll
     for (int i = 0; i < AC::N; i++) {
-        double v = acc[i];
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(PG_FULL_MASK, v, off);
+        const double v = warp_sum(acc[i]);
         if (lane == 0) tot[i] = v;
     }
     __syncwarp();
@@ -299,162 +323,182 @@ __device__ __forceinline__ double solve_rhs(int m, const double (&Li)[PG_MAX_SLO
     return zz;
 }
 
-// Reference-style two-pass evaluation of one locus straight from global memory (explicit centred moments, explicit
-// residuals e = y - Xb as src/gwas/ols.rs:98-104): used when the single-pass Gram form would lose digits to
-// cancellation (near-perfect fits, nearly constant or nearly collinear allele columns).  One lane per locus.
+__device__ __forceinline__ int slot_col(unsigned cb, int s) { return (int)((cb >> (4 * s)) & 0xfu); }
+
+enum { REDO_NONE = 0, REDO_OLS = 1, REDO_CORR = 2, REDO_CORR_NAN = 3 };
+
+// Reference-style two-pass evaluation of one locus straight from global memory by the whole warp (lane = pool):
+// explicit centred moments and explicit residuals e = y - Xb as src/gwas/ols.rs:98-104.  Used when the single-pass
+// Gram form would lose digits to cancellation (near-perfect fits, nearly constant or nearly collinear allele
+// columns), and for pearsons_correlation with missing frequencies (src/gwas/correlation_test.rs:21-31: pools whose
+// frequency is NaN are dropped pairwise, the means and centred sums run over the remaining pools).  Every lane ends
+// up with the same numbers; lane 0 leaves (beta | r, var) per (slot, phenotype) in out[0 .. 2 (A-1) K).
 template <int A, int K>
-__device__ __noinline__ int explicit_locus(const ScanParams &p, int64_t locus, unsigned kept, int m, const int *cols,
-                                           const double *xbar, const double *ys, double *tbg) {
+__device__ __noinline__ int redo_locus(const ScanParams &p, int64_t locus, unsigned kept, int m, unsigned cb, int mode,
+                                       const double *ys, double *out, int lane) {
+    constexpr int MS = A - 1;
     const Layout &lay = p.lay;
-    const double *fl = p.freq + (size_t)locus * lay.freq_stride();
-    const uint32_t *dl = p.depth + (size_t)locus * lay.depth_stride();
+    const int n_pad = lay.n_pad;
     const double nn = (double)lay.n;
-    double S[PG_MAX_SLOTS][PG_MAX_SLOTS], sxy[K][PG_MAX_SLOTS], ybar[K];
-    for (int a = 0; a < PG_MAX_SLOTS; a++) {
-        for (int b = 0; b < PG_MAX_SLOTS; b++) S[a][b] = 0.0;
-        for (int k = 0; k < K; k++) sxy[k][a] = 0.0;
+    double xbar[MS], ybar[K];
+    double cntv = nn;
+    // pass 0: means (the totals of the fast path are not trusted here)
+    {
+        double sx[MS], sy[K], cnt = 0.0;
+#pragma unroll
+        for (int a = 0; a < MS; a++) sx[a] = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; k++) sy[k] = 0.0;
+        for_rows_coop<A>(p, locus, lane, [&](int i, const double(&f)[A], uint32_t d) {
+            double F[A], x[MS];
+            renorm_row<A>(f, d, kept, F);
+            bool valid = true;
+#pragma unroll
+            for (int a = 0; a < MS; a++) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < A; j++)
+                    if (a < m && j == slot_col(cb, a)) v = F[j];
+                x[a] = v;
+                valid &= (v == v);
+            }
+            if (mode == REDO_CORR_NAN && !valid) return;
+            cnt += 1.0;
+#pragma unroll
+            for (int a = 0; a < MS; a++) sx[a] += x[a];
+#pragma unroll
+            for (int k = 0; k < K; k++) sy[k] += ys[k * n_pad + i];
+        });
+        cntv = warp_sum(cnt);
+#pragma unroll
+        for (int a = 0; a < MS; a++) xbar[a] = warp_sum(sx[a]) / cntv;
+#pragma unroll
+        for (int k = 0; k < K; k++) ybar[k] = warp_sum(sy[k]) / cntv;
     }
-    for (int k = 0; k < K; k++) ybar[k] = p.ysum[k] / nn;
-    for (int pass = 0; pass < 2; pass++) {
-        double Li[PG_MAX_SLOTS][PG_MAX_SLOTS], dg[PG_MAX_SLOTS], beta[K][PG_MAX_SLOTS], rss[K];
-        if (pass == 1) {
-            if (p.kind == PG_KIND_OLS) {
-                if (!chol_inv(m, S, Li, dg)) return PG_LOCUS_FAILED;
-                for (int k = 0; k < K; k++) {
-                    solve_rhs(m, Li, sxy[k], beta[k]);
-                    rss[k] = 0.0;
-                }
-            } else {
-                for (int a = 0; a < m; a++)
-                    for (int k = 0; k < K; k++) {
-                        tbg[(a * K + k) * 2 + 0] = sxy[k][a] / (sqrt(S[a][a]) * sqrt(p.syy[k]));
-                        tbg[(a * K + k) * 2 + 1] = 0.0;
-                    }
-                return PG_LOCUS_OK;
-            }
-        }
-        int i0 = 0;
-        for (int c = 0; c < lay.n_chunks; c++) {
-            const int rcc = (c == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
-            const double *blk = fl + (size_t)c * lay.A * lay.rc;
-            const int rows = min(rcc, lay.n - i0);
-            for (int r = 0; r < rows; r++) {
-                double f[A], F[A], x[PG_MAX_SLOTS];
+    // pass 1: centred moments
+    double S[PG_MAX_SLOTS][PG_MAX_SLOTS], sxy[K][PG_MAX_SLOTS], syy[K];
+    {
+        double Sa[MS * (MS + 1) / 2], sxya[K][MS], syya[K];
 #pragma unroll
-                for (int j = 0; j < A; j++) f[j] = blk[(size_t)j * rcc + r];
-                renorm_row<A>(f, dl[i0 + r], kept, F);
-                for (int a = 0; a < m; a++) {
-                    double v = 0.0;
+        for (int i = 0; i < MS * (MS + 1) / 2; i++) Sa[i] = 0.0;
 #pragma unroll
-                    for (int j = 0; j < A; j++)
-                        if (j == cols[a]) v = F[j];
-                    x[a] = v - xbar[a];
-                }
-                if (pass == 0) {
-                    for (int a = 0; a < m; a++) {
-                        for (int b = 0; b <= a; b++) S[a][b] = fma(x[a], x[b], S[a][b]);
-                        for (int k = 0; k < K; k++) sxy[k][a] = fma(x[a], ys[k * lay.n_pad + i0 + r] - ybar[k], sxy[k][a]);
-                    }
-                } else {
-                    for (int k = 0; k < K; k++) {
-                        double e = ys[k * lay.n_pad + i0 + r] - ybar[k];
-                        for (int a = 0; a < m; a++) e -= beta[k][a] * x[a];
-                        rss[k] = fma(e, e, rss[k]);
-                    }
-                }
-            }
-            i0 += rcc;
+        for (int k = 0; k < K; k++) {
+            syya[k] = 0.0;
+#pragma unroll
+            for (int a = 0; a < MS; a++) sxya[k][a] = 0.0;
         }
-        if (pass == 1) {
-            const double dfe = nn - (double)(m + 1);
+        for_rows_coop<A>(p, locus, lane, [&](int i, const double(&f)[A], uint32_t d) {
+            double F[A], x[MS];
+            renorm_row<A>(f, d, kept, F);
+            bool valid = true;
+#pragma unroll
+            for (int a = 0; a < MS; a++) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < A; j++)
+                    if (a < m && j == slot_col(cb, a)) v = F[j];
+                valid &= (v == v);
+                x[a] = v - xbar[a];
+            }
+            if (mode == REDO_CORR_NAN && !valid) return;
+#pragma unroll
+            for (int a = 0; a < MS; a++)
+#pragma unroll
+                for (int b = 0; b <= a; b++) Sa[a * (a + 1) / 2 + b] = fma(x[a], x[b], Sa[a * (a + 1) / 2 + b]);
+#pragma unroll
             for (int k = 0; k < K; k++) {
-                const double ve = rss[k] / dfe;
-                for (int b = 0; b < m; b++) {
-                    tbg[(b * K + k) * 2 + 0] = beta[k][b];
-                    tbg[(b * K + k) * 2 + 1] = ve * dg[b];
+                const double dy = ys[k * n_pad + i] - ybar[k];
+                syya[k] = fma(dy, dy, syya[k]);
+#pragma unroll
+                for (int a = 0; a < MS; a++) sxya[k][a] = fma(x[a], dy, sxya[k][a]);
+            }
+        });
+#pragma unroll
+        for (int a = 0; a < PG_MAX_SLOTS; a++)
+#pragma unroll
+            for (int b = 0; b < PG_MAX_SLOTS; b++) S[a][b] = 0.0;
+#pragma unroll
+        for (int a = 0; a < MS; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++) S[a][b] = warp_sum(Sa[a * (a + 1) / 2 + b]);
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            syy[k] = warp_sum(syya[k]);
+#pragma unroll
+            for (int a = 0; a < PG_MAX_SLOTS; a++) sxy[k][a] = 0.0;
+#pragma unroll
+            for (int a = 0; a < MS; a++) sxy[k][a] = warp_sum(sxya[k][a]);
+        }
+    }
+    if (mode != REDO_OLS) {
+        if (lane == 0)
+            for (int a = 0; a < m; a++)
+                for (int k = 0; k < K; k++) {
+                    const double den = (mode == REDO_CORR_NAN) ? sqrt(S[a][a]) * sqrt(syy[k])
+                                                                : sqrt(S[a][a]) * sqrt(p.syy[k]);
+                    out[(a * K + k) * 2 + 0] = sxy[k][a] / den;
+                    out[(a * K + k) * 2 + 1] = 0.0;
                 }
+        __syncwarp();
+        return PG_LOCUS_OK;
+    }
+    double Li[PG_MAX_SLOTS][PG_MAX_SLOTS], dg[PG_MAX_SLOTS], beta[K][PG_MAX_SLOTS];
+    if (!chol_inv(m, S, Li, dg)) return PG_LOCUS_FAILED;
+    for (int k = 0; k < K; k++) solve_rhs(m, Li, sxy[k], beta[k]);
+    // pass 2: explicit residuals
+    double rss[K];
+    {
+        double ra[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) ra[k] = 0.0;
+        for_rows_coop<A>(p, locus, lane, [&](int i, const double(&f)[A], uint32_t d) {
+            double F[A], x[MS];
+            renorm_row<A>(f, d, kept, F);
+#pragma unroll
+            for (int a = 0; a < MS; a++) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < A; j++)
+                    if (a < m && j == slot_col(cb, a)) v = F[j];
+                x[a] = v - xbar[a];
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                double e = ys[k * n_pad + i] - ybar[k];
+#pragma unroll
+                for (int a = 0; a < MS; a++)
+                    if (a < m) e -= beta[k][a] * x[a];
+                ra[k] = fma(e, e, ra[k]);
+            }
+        });
+#pragma unroll
+        for (int k = 0; k < K; k++) rss[k] = warp_sum(ra[k]);
+    }
+    if (lane == 0) {
+        const double dfe = nn - (double)(m + 1);
+        for (int k = 0; k < K; k++) {
+            const double ve = rss[k] / dfe;
+            for (int b = 0; b < m; b++) {
+                out[(b * K + k) * 2 + 0] = beta[k][b];
+                out[(b * K + k) * 2 + 1] = ve * dg[b];
             }
         }
     }
+    __syncwarp();
     return PG_LOCUS_OK;
 }
 
-// pearsons_correlation with missing frequencies (src/gwas/correlation_test.rs:21-31): pools whose frequency is NaN
-// are dropped pairwise, the means and centred sums run over the remaining pools, n stays the full pool count.
-template <int A, int K>
-__device__ __noinline__ void explicit_corr_nan(const ScanParams &p, int64_t locus, unsigned kept, int m, const int *cols,
-                                               const double *ys, double *tbg) {
-    const Layout &lay = p.lay;
-    const double *fl = p.freq + (size_t)locus * lay.freq_stride();
-    const uint32_t *dl = p.depth + (size_t)locus * lay.depth_stride();
-    double sx[PG_MAX_SLOTS], sy[K], sxx[PG_MAX_SLOTS], syy[K], sxy[K][PG_MAX_SLOTS];
-    double cnt = 0.0;
-    for (int pass = 0; pass < 2; pass++) {
-        for (int a = 0; a < PG_MAX_SLOTS; a++) {
-            if (pass == 0) sx[a] = 0.0; else sx[a] = sx[a] / cnt;
-            sxx[a] = 0.0;
-            for (int k = 0; k < K; k++) sxy[k][a] = 0.0;
-        }
-        for (int k = 0; k < K; k++) {
-            if (pass == 0) sy[k] = 0.0; else sy[k] = sy[k] / cnt;
-            syy[k] = 0.0;
-        }
-        int i0 = 0;
-        for (int c = 0; c < lay.n_chunks; c++) {
-            const int rcc = (c == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
-            const double *blk = fl + (size_t)c * lay.A * lay.rc;
-            const int rows = min(rcc, lay.n - i0);
-            for (int r = 0; r < rows; r++) {
-                double f[A], F[A];
-#pragma unroll
-                for (int j = 0; j < A; j++) f[j] = blk[(size_t)j * rcc + r];
-                renorm_row<A>(f, dl[i0 + r], kept, F);
-                double x[PG_MAX_SLOTS];
-                bool valid = true;
-                for (int a = 0; a < m; a++) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int j = 0; j < A; j++)
-                        if (j == cols[a]) v = F[j];
-                    x[a] = v;
-                    valid &= (v == v);
-                }
-                if (!valid) continue;
-                if (pass == 0) {
-                    cnt += 1.0;
-                    for (int a = 0; a < m; a++) sx[a] += x[a];
-                    for (int k = 0; k < K; k++) sy[k] += ys[k * lay.n_pad + i0 + r];
-                } else {
-                    for (int k = 0; k < K; k++) {
-                        const double dy = ys[k * lay.n_pad + i0 + r] - sy[k];
-                        syy[k] = fma(dy, dy, syy[k]);
-                        for (int a = 0; a < m; a++) sxy[k][a] = fma(x[a] - sx[a], dy, sxy[k][a]);
-                    }
-                    for (int a = 0; a < m; a++) sxx[a] = fma(x[a] - sx[a], x[a] - sx[a], sxx[a]);
-                }
-            }
-            i0 += rcc;
-        }
-    }
-    for (int a = 0; a < m; a++)
-        for (int k = 0; k < K; k++) {
-            tbg[(a * K + k) * 2 + 0] = sxy[k][a] / (sqrt(sxx[a]) * sqrt(syy[k]));
-            tbg[(a * K + k) * 2 + 1] = 0.0;
-        }
-}
-
-// Single-pass OLS from the reduced sums for M regressors, fully unrolled so that every matrix lives in registers
-// (the generic chol_inv / solve_rhs above index local arrays dynamically and are kept for the two-pass fallback).
+// Single-pass OLS from the reduced sums for M regressors, fully unrolled so that every matrix lives in registers.
 // Returns false when the centred X'X is not positive definite; sets redo when the single-pass form loses digits.
 template <int M, int A, int K, bool W>
-__device__ __forceinline__ bool ols_gram_m(const ScanParams &p, const double *tg, const int *cols, double nn,
-                                           double *tbg, bool &redo) {
+__device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsigned cb, double nn, bool &redo) {
     using AC = Acc<A, K, W>;
+    double tbg[2 * M * K];
     double sx[M], S[M][M], Lm[M][M], Li[M][M], dg[M], rinv[M];
     int c[M];
 #pragma unroll
     for (int a = 0; a < M; a++) {
-        c[a] = cols[a];
+        c[a] = slot_col(cb, a);
         sx[a] = tg[AC::S0 + c[a]];
     }
     const double inv_n = 1.0 / nn;
@@ -537,196 +581,252 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, const double *tg
             tbg[(b * K + k) * 2 + 1] = ve * dg[b];
         }
     }
+#pragma unroll
+    for (int i = 0; i < 2 * M * K; i++) tg[i] = tbg[i];  // every total has been read: the row now holds the results
     return true;
 }
 
-// t and the two-sided p-value of one (allele slot, phenotype) record; o -> 4 doubles
-static __device__ __noinline__ void finish_task(const ScanParams &p, const PTableDev &ptab, bool valid, double v0,
-                                                double v1, double *o) {
-    const double nn = (double)p.lay.n;
-    double o0 = nan(""), o1 = nan(""), o2 = nan(""), o3 = nan("");
-    if (valid) {
-        if (p.kind == PG_KIND_OLS) {
-            // estimate_significance, src/gwas/ols.rs:139-154
-            const double se = sqrt(v1);
-            const double tt = (fabs(v0) <= kEps) ? 0.0 : v0 / se;
-            double pv;
-            if (fabs(tt) <= kEps || tt != tt)
-                pv = 1.0;
-            else
-                pv = p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab) : student_two_sided(fabs(tt), p.df, p.ln_beta);
-            o0 = v0;
-            o1 = se;
-            o2 = tt;
-            o3 = pv;
-        } else {
-            // pearsons_correlation, src/gwas/correlation_test.rs:52-70
-            const double r = v0;
-            if (r == r) {
-                const double s2 = (1.0 - r * r) / (nn - 2.0);
-                o1 = r;
-                if (s2 <= 0.0) {
-                    o0 = r;
-                    o3 = kEps;
-                } else {
-                    const double tt = r / sqrt(s2);
-                    o2 = tt;
-                    o3 = (p.lay.n > 2) ? (p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab)
-                                                 : student_two_sided(fabs(tt), p.df, p.ln_beta))
-                                       : nan("");
-                    o0 = round(r * 1e7) / 1e7;
-                }
-            }
-        }
-    }
-    *reinterpret_cast<double2 *>(o) = make_double2(o0, o1);
-    *reinterpret_cast<double2 *>(o + 2) = make_double2(o2, o3);
-}
-
-// ---- phase 2, second half (one lane per locus): allele order, centred normal equations, records ----------------
+// ---- phase 2b (one lane per locus): allele order and the single-pass solve, everything in registers ------------
+// in: the totals row tg of the locus.  out: m (rows), cb (allele column of each row, 4 bits per slot), redo (REDO_*)
+// and, in place of the totals, tg[(s*K+k)*2 + {0,1}] = (beta | r, var) and tg[2(A-1)K + s] = mean frequency.
 template <int A, int K, bool W>
-__device__ __noinline__ void finish_locus(const ScanParams &p, const PTableDev &ptab, int64_t locus, const double *tg,
-                                          int status, unsigned kept, const double *ys) {
+__device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, double *tg, int &status, unsigned kept,
+                                         int &m, unsigned &cb, int &redo_mode) {
     using AC = Acc<A, K, W>;
-    constexpr int T = (A - 1) * K;
+    constexpr int T2 = 2 * (A - 1) * K;
+    static_assert(T2 + A - 1 <= AC::NP, "the results of a locus must fit its totals row");
+    double fmean[A - 1];
+#pragma unroll
+    for (int a = 0; a < A - 1; a++) fmean[a] = nan("");
     const Layout &lay = p.lay;
     const double nn = (double)lay.n;
     const double tol_rel = 2.0 * (nn + 8.0) * kEps;
-    int cols[PG_MAX_SLOTS] = {0, 0, 0, 0, 0};
-    int m = 0;
-    double tb[T * 2];
+    m = __popc(kept) - 1;
+    cb = 0;
+    if (p.kind == PG_KIND_OLS) {
+        // stable sort by decreasing column sum, drop the first (major) allele (sync.rs:478-505, ols.rs:227-230)
+        double cs[A];
+        bool tie = false;
 #pragma unroll
-    for (int i = 0; i < T * 2; i++) tb[i] = nan("");
-    double fmean[A - 1];
+        for (int j = 0; j < A; j++) cs[j] = tg[AC::S0 + j];
 #pragma unroll
-    for (int s = 0; s < A - 1; s++) fmean[s] = nan("");
-    if (status == PG_LOCUS_OK) {
-        m = __popc(kept) - 1;
-        if (p.kind == PG_KIND_OLS) {
-            // stable sort by decreasing column sum, drop the first (major) allele (sync.rs:478-505, ols.rs:227-230)
-            double cs[A];
-            bool tie = false;
+        for (int j = 0; j < A; j++)
 #pragma unroll
-            for (int j = 0; j < A; j++) cs[j] = tg[AC::S0 + j];
+            for (int l = j + 1; l < A; l++)
+                if (((kept >> j) & 1u) && ((kept >> l) & 1u) &&
+                    fabs(cs[j] - cs[l]) <= tol_rel * fmax(fabs(cs[j]), fabs(cs[l])))
+                    tie = true;
+        if (tie) {
 #pragma unroll
             for (int j = 0; j < A; j++)
-#pragma unroll
-                for (int l = j + 1; l < A; l++)
-                    if (((kept >> j) & 1u) && ((kept >> l) & 1u) &&
-                        fabs(cs[j] - cs[l]) <= tol_rel * fmax(fabs(cs[j]), fabs(cs[l])))
-                        tie = true;
-            if (tie) {
-#pragma unroll
-                for (int j = 0; j < A; j++)
-                    if ((kept >> j) & 1u) cs[j] = exact_colsum<A>(p, locus, j, kept);
-            }
-#pragma unroll
-            for (int j = 0; j < A; j++) {
-                if (!((kept >> j) & 1u)) continue;
-                int rank = 0;
-#pragma unroll
-                for (int l = 0; l < A; l++) {
-                    if (l == j || !((kept >> l) & 1u)) continue;
-                    if (cs[l] > cs[j] || (cs[l] == cs[j] && l < j)) rank++;
-                }
-#pragma unroll
-                for (int s = 0; s < PG_MAX_SLOTS; s++)
-                    if (rank == s + 1) cols[s] = j;
-            }
-        } else {
-            // kept columns in file order, the last one is dropped (correlation_test.rs:94-98)
-            int sidx = 0;
-#pragma unroll
-            for (int j = 0; j < A; j++) {
-                if (!((kept >> j) & 1u)) continue;
-#pragma unroll
-                for (int ss = 0; ss < PG_MAX_SLOTS; ss++)
-                    if (ss == sidx && sidx < m) cols[ss] = j;
-                sidx++;
-            }
+                if ((kept >> j) & 1u) cs[j] = exact_colsum<A>(p, locus, j, kept);
         }
-        double sx[PG_MAX_SLOTS], xbar[PG_MAX_SLOTS];
-        bool has_nan = false;
+#pragma unroll
+        for (int j = 0; j < A; j++) {
+            if (!((kept >> j) & 1u)) continue;
+            int rank = 0;
+#pragma unroll
+            for (int l = 0; l < A; l++) {
+                if (l == j || !((kept >> l) & 1u)) continue;
+                if (cs[l] > cs[j] || (cs[l] == cs[j] && l < j)) rank++;
+            }
+            if (rank >= 1) cb |= (unsigned)j << (4 * (rank - 1));
+        }
+    } else {
+        // kept columns in file order, the last one is dropped (correlation_test.rs:94-98)
+        int sidx = 0;
+#pragma unroll
+        for (int j = 0; j < A; j++) {
+            if (!((kept >> j) & 1u)) continue;
+            if (sidx < m) cb |= (unsigned)j << (4 * sidx);
+            sidx++;
+        }
+    }
+    bool has_nan = false;
+#pragma unroll
+    for (int a = 0; a < A - 1; a++) {
+        if (a < m) {
+            const int c = slot_col(cb, a);
+            const double pjj = tg[AC::P0 + c * A - c * (c - 1) / 2];
+            has_nan |= (pjj != pjj);
+            fmean[a] = (pjj != pjj) ? nan("") : tg[AC::S0 + c] / nn;
+        }
+    }
+    if (p.kind == PG_KIND_OLS) {
+        if (lay.n < m + 1) {
+            status = PG_LOCUS_UNSUPPORTED;
+        } else if (!has_nan) {
+            bool redo = false;
+            switch (m) {
+                case 1: ols_gram_m<1, A, K, W>(p, tg, cb, nn, redo); break;
+                case 2:
+                    if constexpr (A >= 3) ols_gram_m<2, A, K, W>(p, tg, cb, nn, redo);
+                    break;
+                case 3:
+                    if constexpr (A >= 4) ols_gram_m<3, A, K, W>(p, tg, cb, nn, redo);
+                    break;
+                case 4:
+                    if constexpr (A >= 5) ols_gram_m<4, A, K, W>(p, tg, cb, nn, redo);
+                    break;
+                default:
+                    if constexpr (A >= 6) ols_gram_m<5, A, K, W>(p, tg, cb, nn, redo);
+                    break;
+            }
+            if (redo) redo_mode = REDO_OLS;
+        } else {
+            for (int i = 0; i < T2; i++) tg[i] = nan("");
+        }
+    } else {
+        double tb[T2];
+#pragma unroll
+        for (int i = 0; i < T2; i++) tb[i] = nan("");
+        bool redo = false;
 #pragma unroll
         for (int a = 0; a < A - 1; a++) {
             if (a < m) {
-                sx[a] = tg[AC::S0 + cols[a]];
-                const double pjj = tg[AC::P0 + cols[a] * A - cols[a] * (cols[a] - 1) / 2];
-                has_nan |= (pjj != pjj);
-                xbar[a] = sx[a] / nn;
-                fmean[a] = (pjj != pjj) ? nan("") : xbar[a];
-            }
-        }
-        if (p.kind == PG_KIND_OLS) {
-            if (lay.n < m + 1) {
-                status = PG_LOCUS_UNSUPPORTED;
-            } else if (!has_nan) {
-                bool redo = false;
-                switch (m) {
-                    case 1: ols_gram_m<1, A, K, W>(p, tg, cols, nn, tb, redo); break;
-                    case 2:
-                        if constexpr (A >= 3) ols_gram_m<2, A, K, W>(p, tg, cols, nn, tb, redo);
-                        break;
-                    case 3:
-                        if constexpr (A >= 4) ols_gram_m<3, A, K, W>(p, tg, cols, nn, tb, redo);
-                        break;
-                    case 4:
-                        if constexpr (A >= 5) ols_gram_m<4, A, K, W>(p, tg, cols, nn, tb, redo);
-                        break;
-                    default:
-                        if constexpr (A >= 6) ols_gram_m<5, A, K, W>(p, tg, cols, nn, tb, redo);
-                        break;
-                }
-                if (redo) status = explicit_locus<A, K>(p, locus, kept, m, cols, xbar, ys, tb);
-            }
-        } else {
-            bool redo = false;
+                const int c = slot_col(cb, a);
+                const double sxa = tg[AC::S0 + c];
+                const double raw = tg[AC::P0 + c * A - c * (c - 1) / 2];
+                const double sxx = raw - sxa * sxa / nn;
+                if (!(raw <= 1e4 * sxx)) redo = true;
 #pragma unroll
-            for (int a = 0; a < A - 1; a++) {
-                if (a < m) {
-                    const double raw = tg[AC::P0 + cols[a] * A - cols[a] * (cols[a] - 1) / 2];
-                    const double sxx = raw - sx[a] * sx[a] / nn;
-                    if (!(raw <= 1e4 * sxx)) redo = true;
-#pragma unroll
-                    for (int k = 0; k < K; k++) {
-                        const double sxy = tg[AC::C0 + cols[a] * K + k] - sx[a] * p.ysum[k] / nn;
-                        tb[(a * K + k) * 2 + 0] = sxy / (sqrt(sxx) * sqrt(p.syy[k]));
-                        tb[(a * K + k) * 2 + 1] = 0.0;
-                    }
+                for (int k = 0; k < K; k++) {
+                    const double sxy = tg[AC::C0 + c * K + k] - sxa * p.ysum[k] / nn;
+                    tb[(a * K + k) * 2 + 0] = sxy / (sqrt(sxx) * sqrt(p.syy[k]));
+                    tb[(a * K + k) * 2 + 1] = 0.0;
                 }
             }
-            if (has_nan)
-                explicit_corr_nan<A, K>(p, locus, kept, m, cols, ys, tb);
-            else if (redo)
-                explicit_locus<A, K>(p, locus, kept, m, cols, xbar, ys, tb);
         }
+        if (has_nan)
+            redo_mode = REDO_CORR_NAN;
+        else if (redo)
+            redo_mode = REDO_CORR;
+#pragma unroll
+        for (int i = 0; i < T2; i++) tg[i] = tb[i];
     }
+#pragma unroll
+    for (int a = 0; a < A - 1; a++) tg[T2 + a] = fmean[a];
+}
+
+// two-sided Student-t p-values of K statistics at once: the table loads of all K are in flight together
+template <int K>
+__device__ __forceinline__ void student_batch(const ScanParams &p, const PTableDev &tab, const double (&t_abs)[K],
+                                              const bool (&need)[K], double (&pv)[K]) {
+    if (!tab.coef) {
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (need[k]) pv[k] = student_two_sided(t_abs[k], p.df, p.ln_beta);
+        return;
+    }
+    double s[K];
+    const double2 *cp[K];
+    bool in[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const double ta = need[k] ? t_abs[k] : 0.0;
+        const double v = sqrt(log1p(ta * ta / p.df));
+        in[k] = need[k] && (v < tab.v_max);
+        const double pos = in[k] ? v * tab.inv_h : 0.0;
+        int i = (int)pos;
+        if (i > tab.M - 1) i = tab.M - 1;
+        s[k] = pos - (double)i;
+        cp[k] = reinterpret_cast<const double2 *>(tab.coef + i);
+    }
+    double2 c01[K], c23[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        c01[k] = __ldg(cp[k]);
+        c23[k] = __ldg(cp[k] + 1);
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const double ptrue = in[k] ? exp(fma(s[k], fma(s[k], fma(s[k], c23[k].y, c23[k].x), c01[k].y), c01[k].x)) : 0.0;
+        const double ib = 0.5 * ptrue;
+        const double cdf = t_abs[k] <= 0.0 ? ib : 1.0 - ib;  // the reference's 2 * (1 - (1 - ib)) quantisation
+        if (need[k]) pv[k] = 2.0 * (1.0 - cdf);
+    }
+}
+
+// ---- phase 2c (one lane per locus): t, p and the records ----------------------------------------------------------
+template <int A, int K>
+__device__ __noinline__ void write_records(const ScanParams &p, const PTableDev &tab, int64_t locus, int status,
+                                           int m, unsigned cb, const double *tb) {
+    constexpr int T2 = 2 * (A - 1) * K;
+    const double nn = (double)p.lay.n;
     if (p.write_meta) {
         uint64_t mv = (uint64_t)status;
         if (status == PG_LOCUS_OK) {
             mv |= (uint64_t)m << 8;
 #pragma unroll
             for (int s = 0; s < A - 1; s++)
-                if (s < m) mv |= (uint64_t)p.codes[cols[s]] << (16 + 8 * s);
+                if (s < m) mv |= (uint64_t)p.codes[slot_col(cb, s)] << (16 + 8 * s);
         }
         p.meta[locus] = mv;
 #pragma unroll
         for (int s = 0; s < A - 1; s++)
-            p.freq_mean[(size_t)locus * (A - 1) + s] = (status == PG_LOCUS_OK && s < m) ? fmean[s] : nan("");
+            p.freq_mean[(size_t)locus * (A - 1) + s] = (status == PG_LOCUS_OK && s < m) ? tb[T2 + s] : nan("");
     }
+#pragma unroll 1
+    for (int s = 0; s < A - 1; s++) {
+        const bool valid = status == PG_LOCUS_OK && s < m;
+        double o0[K], o1[K], o2[K], o3[K], ta[K];
+        bool need[K];
 #pragma unroll
-    for (int s = 0; s < A - 1; s++)
+        for (int k = 0; k < K; k++) {
+            const double v0 = valid ? tb[(s * K + k) * 2 + 0] : 0.0, v1 = valid ? tb[(s * K + k) * 2 + 1] : 0.0;
+            o0[k] = o1[k] = o2[k] = o3[k] = nan("");
+            need[k] = false;
+            ta[k] = 0.0;
+            if (valid) {
+                if (p.kind == PG_KIND_OLS) {
+                    // estimate_significance, src/gwas/ols.rs:139-154
+                    const double se = sqrt(v1);
+                    const double tt = (fabs(v0) <= kEps) ? 0.0 : v0 / se;
+                    o0[k] = v0;
+                    o1[k] = se;
+                    o2[k] = tt;
+                    if (fabs(tt) <= kEps || tt != tt) {
+                        o3[k] = 1.0;
+                    } else {
+                        need[k] = true;
+                        ta[k] = fabs(tt);
+                    }
+                } else {
+                    // pearsons_correlation, src/gwas/correlation_test.rs:52-70
+                    const double r = v0;
+                    if (r == r) {
+                        const double s2 = (1.0 - r * r) / (nn - 2.0);
+                        o1[k] = r;
+                        if (s2 <= 0.0) {
+                            o0[k] = r;
+                            o3[k] = kEps;
+                        } else {
+                            const double tt = r / sqrt(s2);
+                            o2[k] = tt;
+                            o0[k] = round(r * 1e7) / 1e7;
+                            if (p.lay.n > 2) {
+                                need[k] = true;
+                                ta[k] = fabs(tt);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        student_batch<K>(p, tab, ta, need, o3);
 #pragma unroll
         for (int k = 0; k < K; k++) {
             double *o = p.stats + (((size_t)locus * (A - 1) + s) * p.k_total + p.phen_base + k) * 4;
-            finish_task(p, ptab, status == PG_LOCUS_OK && s < m, tb[(s * K + k) * 2 + 0], tb[(s * K + k) * 2 + 1], o);
+            *reinterpret_cast<double2 *>(o) = make_double2(o0[k], o1[k]);
+            *reinterpret_cast<double2 *>(o + 2) = make_double2(o2[k], o3[k]);
         }
+    }
 }
 
 // ---- phase 2 (lane = locus of the block): keep-mask from the totals, cooperative exact / slow paths, records ----
 template <int A, int K, bool W>
 __device__ __noinline__ void epilogue(const ScanParams &p, int64_t l0, int cnt, double *tot, const double *ys,
-                                      const double *ws, int lane) {
+                                      const double *ws, int lane, unsigned dm) {
     using AC = Acc<A, K, W>;
     const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
     const bool act = lane < cnt;
@@ -740,7 +840,6 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t l0, int cnt, 
 #pragma unroll
     for (int j = 0; j < A; j++) q[j] = 0.0;
     if (act) {
-        const unsigned dm = p.dmin[locus];
         if ((double)dm < p.min_depth_f) {
             status = PG_LOCUS_FILTERED;  // sync.rs:217-229
         } else if (dm == 0u) {
@@ -795,19 +894,43 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t l0, int cnt, 
         }
     }
     __syncwarp();
-    if (act) finish_locus<A, K, W>(p, ptab, locus, tg, status, kept, ys);
+    int m = 0, redo_mode = REDO_NONE;
+    unsigned cb = 0;
+    if (act && status == PG_LOCUS_OK) solve_locus<A, K, W>(p, locus, tg, status, kept, m, cb, redo_mode);
+    // loci whose single-pass form is not trustworthy: explicit two-pass evaluation by the whole warp
+    need = __ballot_sync(PG_FULL_MASK, redo_mode != REDO_NONE);
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int md = __shfl_sync(PG_FULL_MASK, redo_mode, src);
+        const unsigned kk = __shfl_sync(PG_FULL_MASK, kept, src);
+        const int mm = __shfl_sync(PG_FULL_MASK, m, src);
+        const unsigned cc = __shfl_sync(PG_FULL_MASK, cb, src);
+        __syncwarp();
+        const int st = redo_locus<A, K>(p, l0 + src, kk, mm, cc, md, ys, tot + (size_t)src * AC::NP, lane);
+        if (lane == src) status = st;
+    }
+    __syncwarp();
+    if (act) write_records<A, K>(p, ptab, locus, status, m, cb, tg);
     __syncwarp();
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
 template <int A, int K, bool W, int P>
-__global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const __grid_constant__ ScanParams p) {
     using AC = Acc<A, K, W>;
-    constexpr int G = block_loci(P);
     constexpr int LPS = 32 / P;  // loci per stage
+    constexpr int RC = chunk_rows(A);
     extern __shared__ __align__(128) unsigned char smem[];
+    // the out-of-line phase-2 functions take the parameter block by reference: give them a shared-memory copy
+    // (a reference to the kernel parameter itself would be spilled to per-thread local memory)
+    __shared__ __align__(16) ScanParams sp_storage;
+    for (int i = threadIdx.x; i < (int)(sizeof(ScanParams) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t *>(&sp_storage)[i] = reinterpret_cast<const uint32_t *>(&p)[i];
+    const ScanParams &sp = sp_storage;
     const Layout lay = p.lay;
     const int n_pad = lay.n_pad;
+    const int G = p.block_loci;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     double *ys = reinterpret_cast<double *>(smem);
     double *ws = W ? ys + (size_t)K * n_pad : nullptr;
@@ -834,78 +957,99 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const ScanPara
     if (gw >= NB) return;
     const int n_chunks = lay.n_chunks;
     const size_t fstride = lay.freq_stride();
+    const uint32_t full_bytes = (uint32_t)(A * lay.rc * 8), last_bytes = (uint32_t)(A * lay.rc_last * 8);
+    const uint32_t locus_bytes = (uint32_t)(fstride * 8);
 
-    // producer side of the ring: the stage stream of this warp in consumption order, nbuf stages ahead
+    // producer side of the ring: the stages of a block are one contiguous walk through the frequency matrix
     int64_t i_blk = gw;
-    int i_sub = 0, i_chunk = 0;  // P = 32: locus in block, chunk;  P < 32: stage in block
+    const unsigned char *i_src = reinterpret_cast<const unsigned char *>(p.freq + (size_t)(gw * G) * fstride);
+    int i_left = (int)min((int64_t)G, L - gw * G);  // loci of the block not yet requested
+    int i_chunk = 0;
     bool i_done = false;
-    auto issue_next = [&](int b) {
+    auto issue_next = [&](int b, bool scratch_used) {
         if (i_done) return;
-        const int64_t bl0 = i_blk * G;
-        const int bcnt = (int)min((int64_t)G, L - bl0);
-        const double *src;
         uint32_t bytes;
+        int nl = 1;
         if (P == 32) {
-            const int rcc = (i_chunk == n_chunks - 1) ? lay.rc_last : lay.rc;
-            src = p.freq + (size_t)(bl0 + i_sub) * fstride + (size_t)i_chunk * A * lay.rc;
-            bytes = (uint32_t)(A * rcc * 8);
+            bytes = (i_chunk == n_chunks - 1) ? last_bytes : full_bytes;
         } else {
-            const int nl = min(LPS, bcnt - i_sub * LPS);
-            src = p.freq + (size_t)(bl0 + i_sub * LPS) * fstride;
-            bytes = (uint32_t)(nl * (int)fstride * 8);
+            nl = min(LPS, i_left);
+            bytes = (uint32_t)nl * locus_bytes;
         }
         if (lane == 0) {
-            fence_proxy_async();  // the buffer served as reduction scratch (generic-proxy writes)
+            if (scratch_used) fence_proxy_async();  // generic-proxy writes of the reduction before the async-proxy refill
             mbar_expect_tx(&bars[b], bytes);
-            bulk_g2s(stage0 + (size_t)b * p.stage_bytes, src, bytes, &bars[b]);
+            bulk_g2s(stage0 + (size_t)b * p.stage_bytes, i_src, bytes, &bars[b]);
         }
-        bool next_block = false;
+        i_src += bytes;
         if (P == 32) {
             if (++i_chunk == n_chunks) {
                 i_chunk = 0;
-                if (++i_sub == bcnt) next_block = true;
+                i_left--;
             }
         } else {
-            if (++i_sub * LPS >= bcnt) next_block = true;
+            i_left -= nl;
         }
-        if (next_block) {
-            i_sub = 0;
+        if (i_left == 0) {
             i_blk += TW;
-            if (i_blk >= NB) i_done = true;
+            if (i_blk >= NB) {
+                i_done = true;
+            } else {
+                i_src = reinterpret_cast<const unsigned char *>(p.freq + (size_t)(i_blk * G) * fstride);
+                i_left = (int)min((int64_t)G, L - i_blk * G);
+            }
         }
     };
-    for (int b = 0; b < nbuf; b++) issue_next(b);
+    for (int b = 0; b < nbuf; b++) issue_next(b, false);
 
     int buf = 0;
     uint32_t parity = 0;
     for (int64_t blk = gw; blk < NB; blk += TW) {
         const int64_t l0 = blk * G;
         const int cnt = (int)min((int64_t)G, L - l0);
+        const unsigned dm = (lane < cnt) ? __ldg(p.dmin + l0 + lane) : 0xFFFFFFFFu;  // consumed by the epilogue
         if (P == 32) {
             for (int g = 0; g < cnt; g++) {
                 double acc[AC::N];
 #pragma unroll
                 for (int i = 0; i < AC::N; i++) acc[i] = 0.0;
                 for (int chunk = 0; chunk < n_chunks; chunk++) {
-                    const int rcc = (chunk == n_chunks - 1) ? lay.rc_last : lay.rc;
-                    const double *yrow = ys + chunk * lay.rc;
+                    const double *yrow = ys + chunk * RC + 2 * lane;
+                    const double *wrow = W ? ws + chunk * RC + 2 * lane : nullptr;
                     mbar_wait(&bars[buf], parity);
                     double *fb = reinterpret_cast<double *>(stage0 + (size_t)buf * p.stage_bytes);
-#pragma unroll 2
-                    for (int r = 2 * lane; r < rcc; r += 64) {
-                        double2 f2[A], y2[K];
+                    if (chunk < n_chunks - 1 || lay.rc_last == RC) {
+                        const double *fl = fb + 2 * lane;
 #pragma unroll
-                        for (int j = 0; j < A; j++) f2[j] = *reinterpret_cast<const double2 *>(fb + (size_t)j * rcc + r);
+                        for (int it = 0; it < RC / 64; it++) {
+                            double2 f2[A], y2[K];
 #pragma unroll
-                        for (int k = 0; k < K; k++) y2[k] = *reinterpret_cast<const double2 *>(yrow + (size_t)k * n_pad + r);
-                        double2 w2 = make_double2(0.0, 0.0);
-                        if (W) w2 = *reinterpret_cast<const double2 *>(ws + chunk * lay.rc + r);
-                        accum_pair<A, K, W>(acc, f2, y2, w2);
+                            for (int j = 0; j < A; j++) f2[j] = *reinterpret_cast<const double2 *>(fl + j * RC + it * 64);
+#pragma unroll
+                            for (int k = 0; k < K; k++)
+                                y2[k] = *reinterpret_cast<const double2 *>(yrow + (size_t)k * n_pad + it * 64);
+                            double2 w2 = make_double2(0.0, 0.0);
+                            if (W) w2 = *reinterpret_cast<const double2 *>(wrow + it * 64);
+                            accum_pair<A, K, W>(acc, f2, y2, w2);
+                        }
+                    } else {
+                        const int rcc = lay.rc_last;
+                        for (int r = 2 * lane; r < rcc; r += 64) {
+                            double2 f2[A], y2[K];
+#pragma unroll
+                            for (int j = 0; j < A; j++) f2[j] = *reinterpret_cast<const double2 *>(fb + (size_t)j * rcc + r);
+#pragma unroll
+                            for (int k = 0; k < K; k++)
+                                y2[k] = *reinterpret_cast<const double2 *>(ys + chunk * RC + (size_t)k * n_pad + r);
+                            double2 w2 = make_double2(0.0, 0.0);
+                            if (W) w2 = *reinterpret_cast<const double2 *>(ws + chunk * RC + r);
+                            accum_pair<A, K, W>(acc, f2, y2, w2);
+                        }
                     }
                     __syncwarp();
                     if (chunk == n_chunks - 1)
                         reduce_to_tot<AC::N, AC::NP, 32>(acc, fb, red_rows, tot + (size_t)g * AC::NP, lane);
-                    issue_next(buf);  // refill this buffer with the stage nbuf ahead
+                    issue_next(buf, chunk == n_chunks - 1);  // refill this buffer with the stage nbuf ahead
                     if (++buf == nbuf) {
                         buf = 0;
                         parity ^= 1u;
@@ -937,42 +1081,51 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const ScanPara
                 }
                 __syncwarp();
                 reduce_to_tot<AC::N, AC::NP, P>(acc, fb, red_rows, tot + (size_t)(s * LPS) * AC::NP, lane);
-                issue_next(buf);
+                issue_next(buf, true);
                 if (++buf == nbuf) {
                     buf = 0;
                     parity ^= 1u;
                 }
             }
         }
-        epilogue<A, K, W>(p, l0, cnt, tot, ys, ws, lane);
+        epilogue<A, K, W>(sp, l0, cnt, tot, ys, ws, lane, dm);
     }
 }
 
 template <int A, int K, bool W, int P>
 cudaError_t launch_scan_p(ScanParams p, int sm_count, cudaStream_t s) {
     using AC = Acc<A, K, W>;
-    constexpr int G = block_loci(P);
     const Layout &lay = p.lay;
-    const size_t avail = 227 * 1024;
+    const size_t avail = 227 * 1024 - 512;  // 512 B of static shared memory hold the parameter copy
     size_t common = (size_t)(K + (W ? 1 : 0)) * lay.n_pad * 8;
     common = (common + 127) / 128 * 128;
     size_t stage = (P == 32) ? (size_t)A * lay.rc * 8 : (size_t)(32 / P) * lay.freq_stride() * 8;
     stage = (stage + 127) / 128 * 128;
-    const size_t tot_bytes = ((size_t)G * AC::NP * 8 + 127) / 128 * 128;
-    // ring depth: 3 stages unless that leaves too few warps to keep the FP64 pipe and the copy engine busy
-    int nbuf = 3, nwarps = 0;
+    // loci per epilogue block (= lanes busy in phase 2) and ring depth: prefer 32 loci and 3 stages, give way in
+    // that order until the full set of warps fits (the scan is bound by the number of resident warps)
+    int G = 32, nbuf = 3, nwarps = 0;
     size_t wbytes = 0;
-    for (;; nbuf--) {
-        wbytes = 64 + (size_t)nbuf * stage + tot_bytes;
+    auto fit = [&](int g, int nb) {
+        const size_t tot_bytes = ((size_t)g * AC::NP * 8 + 127) / 128 * 128;
+        wbytes = 64 + (size_t)nb * stage + tot_bytes;
         nwarps = common + wbytes <= avail ? (int)((avail - common) / wbytes) : 0;
         if (nwarps > kScanWarps) nwarps = kScanWarps;
-        if (nwarps >= 8 || nbuf == 2) break;
-    }
-    if (p.nbuf_override >= 1 && p.nbuf_override <= 8) {
-        nbuf = p.nbuf_override;
-        wbytes = 64 + (size_t)nbuf * stage + tot_bytes;
-        nwarps = common + wbytes <= avail ? (int)((avail - common) / wbytes) : 0;
-        if (nwarps > kScanWarps) nwarps = kScanWarps;
+        return nwarps;
+    };
+    const int g_min = (P == 32) ? 16 : 32;
+    if (p.nbuf_override >= 1 || p.g_override >= 1) {
+        G = (p.g_override == 16 || p.g_override == 32) && P == 32 ? p.g_override : 32;
+        nbuf = (p.nbuf_override >= 1 && p.nbuf_override <= 8) ? p.nbuf_override : 2;
+        fit(G, nbuf);
+    } else if (fit(32, 3) >= kScanWarps) {
+        G = 32, nbuf = 3;
+    } else if (fit(32, 2) >= kScanWarps) {
+        G = 32, nbuf = 2;
+    } else if (fit(g_min, 2) >= kScanWarps) {
+        G = g_min, nbuf = 2;
+    } else {
+        G = 32, nbuf = 2;
+        fit(G, nbuf);
     }
     if (p.warps_override >= 1 && p.warps_override < nwarps) nwarps = p.warps_override;
     if (nwarps < 1) return cudaErrorInvalidConfiguration;
@@ -980,6 +1133,7 @@ cudaError_t launch_scan_p(ScanParams p, int sm_count, cudaStream_t s) {
     p.warp_bytes = (uint32_t)wbytes;
     p.stage_bytes = (uint32_t)stage;
     p.nbuf = nbuf;
+    p.block_loci = G;
     const size_t smem = common + (size_t)nwarps * wbytes;
     auto kern = scan_kernel<A, K, W, P>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
