@@ -144,6 +144,44 @@ int pg_scan_submit_counts_u16(pg_scan *scan, const uint16_t *counts, int64_t n_l
 int pg_scan_submit_freq(pg_scan *scan, const double *freq, const uint32_t *depth, int64_t n_loci, int *ticket);
 int pg_scan_collect(pg_scan *scan, int ticket, pg_results *out);
 
+/* ---- ols_iter_with_kinship: ols_with_covariate (src/gwas/ols.rs:278-436) over a device-resident block of allele
+ * columns of GenotypesAndPhenotypes.intercept_and_allele_frequencies[:, 1..] (src/base/sync.rs:1106-1179).
+ * One pg_kin per GPU holds that GPU's column shard.  Sequence: append columns -> pg_kin_gram (partial G G') ->
+ * [sum the partials over the GPUs: pg_kin_partial hands out the device pointer for an NCCL all-reduce] ->
+ * pg_kin_eig_select (K = sum / P_total, eigen-decomposition, number of PCs by the reference's rule) ->
+ * pg_kin_covar_scan (beta, var(beta), p of the allele coefficient with X = [1 | PCs | g], one record per column
+ * and phenotype; the caller writes them phenotype-outer / column-inner like src/gwas/ols.rs:410-433). ----------- */
+typedef struct pg_kin pg_kin;
+int pg_kin_open(pg_ctx *ctx, int n_pools, int64_t max_columns, pg_kin **out);
+int pg_kin_close(pg_kin *kin);
+int pg_kin_reset(pg_kin *kin);
+int64_t pg_kin_columns(pg_kin *kin);
+/* host f64 allele columns, column-major [P_add][n_pools] */
+int pg_kin_append_columns(pg_kin *kin, const double *cols, int64_t P_add);
+/* a slab of parsed loci (u32 [locus][allele][pool]) through LoadAll::load semantics (src/base/sync.rs:973-1104): filter,
+ * renormalised frequencies of the kept alleles, with keep_p_minus_1 the sort by column sum and the drop of the major
+ * allele; every kept allele becomes one column.  pg_kin_last_labels returns (locus ordinal in the slab, allele code)
+ * of the columns the last call appended. */
+int pg_kin_append_counts(pg_kin *kin, const pg_filter *filter, int n_alleles, const uint8_t *allele_codes,
+                         const uint32_t *counts, int64_t n_loci, int keep_p_minus_1, int64_t *n_cols_added);
+int pg_kin_last_labels(pg_kin *kin, int64_t n_cols, int64_t *col_locus, uint8_t *col_allele);
+/* synthetic biallelic columns (two per locus) generated on the device from the integer-hash workload */
+int pg_kin_synth(pg_kin *kin, uint64_t seed, int64_t first_locus, int64_t n_loci);
+int pg_kin_get_columns(pg_kin *kin, int64_t first, int64_t count, double *out /* [count][n_pools] */);
+/* partial Gram matrix of the resident columns (FP64 tensor cores), asynchronous */
+int pg_kin_gram(pg_kin *kin);
+int pg_kin_gram_time(pg_kin *kin, int iters, float *ms_total);
+int pg_kin_partial(pg_kin *kin, double **device_ptr, size_t *n_elems); /* n_pools x n_pools, synchronises */
+int pg_kin_partial_get(pg_kin *kin, double *out_host);
+int pg_kin_partial_set(pg_kin *kin, const double *in_host);
+int pg_kin_eig_select(pg_kin *kin, int64_t P_total, double variance_explained, int *n_eigenvecs);
+int pg_kin_eigvals(pg_kin *kin, double *out, int count); /* K's eigenvalues, high to low */
+int pg_kin_set_covariates(pg_kin *kin, const double *cov /* n_pools x m row-major */, int m);
+/* phen n_pools x k row-major; results host pointers (library-owned, pinned), each [k][columns];
+ * iters > 0 additionally times `iters` back-to-back launches with CUDA events */
+int pg_kin_covar_scan(pg_kin *kin, const double *phen, int k, int iters, float *ms_total, const double **beta,
+                      const double **var, const double **pval);
+
 /* ---- synthetic workload, host side: identical bits to pg_batch_synth ------------ */
 int pg_synth_counts_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int n_pools, int n_alleles,
                          uint32_t *counts_out);

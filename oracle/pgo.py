@@ -356,3 +356,66 @@ def scan_batch(kind, counts_packed, allele_codes, phen, fs: FilterStats, n_threa
                               _dp(fm), _dp(stat), _dp(var), _dp(t), _dp(pval))
     assert rc == 0
     return BatchResult(status, n_out, allele, fm, stat, var, t, pval)
+
+
+# ---- ols_iter_with_kinship: LoadAll (sync.rs:973-1179) + ols_with_covariate (gwas/ols.rs:278-436) -------------------
+def load_columns(counts, alleles, fs: FilterStats, keep_p_minus_1: bool = False):
+    """LoadAll::per_chunk_load + into_genotypes_and_phenotypes for a list of loci (counts [L, n, A] u64):
+    returns (G [P, n] allele columns = intercept_and_allele_frequencies[:, 1..] transposed, labels [(locus, allele)])."""
+    cols, labels = [], []
+    for l in range(len(counts)):
+        st, ck, ak = filter_locus(counts[l], alleles, fs)
+        if st != OK:
+            continue
+        f = to_frequencies(ck)
+        if keep_p_minus_1:
+            f, ak = sort_by_allele_freq(f, ak, True)
+            f, ak = f[:, 1:], ak[1:]
+        for j in range(f.shape[1]):
+            cols.append(f[:, j].copy())
+            labels.append((l, int(ak[j])))
+    n = counts.shape[1]
+    return (np.array(cols) if cols else np.zeros((0, n))), labels
+
+
+def select_eigenvectors(eigvals_desc, threshold):
+    """the PC-count rule of gwas/ols.rs:297-311 on eigenvalues sorted from high to low (the reference's assumption)"""
+    n = len(eigvals_desc)
+    s = 0.0
+    for v in eigvals_desc:
+        s = s + v
+    cum = [v / s for v in eigvals_desc]
+    m = n
+    for i in range(1, n):
+        cum[i] = cum[i - 1] + cum[i]
+        if cum[i - 1] >= threshold and (i - 1) < m:
+            m = i - 1
+    return m
+
+
+def ols_with_covariate(G_cols, phen, threshold):
+    """G_cols [P, n] allele columns, phen [n, k].  Returns (m, beta [P, k], var [P, k], pval [P, k]) where each entry is
+    the LAST coefficient of ols([1 | PCs | g], y) (gwas/ols.rs:340-370); NaN where the regression fails.
+    The eigen-decomposition uses numpy's symmetric solver with eigenvalues sorted from high to low; the reference calls
+    MKL dgeev and ASSUMES that order (gwas/ols.rs:296) -- parity unpinned for the order, pinned for everything else by
+    the invariance of the last coefficient to the basis of span(PCs)."""
+    G = np.ascontiguousarray(G_cols, dtype=np.float64)
+    P, n = G.shape
+    y = np.ascontiguousarray(phen, dtype=np.float64)
+    if y.ndim == 1:
+        y = y[:, None].copy()
+    k = y.shape[1]
+    K = (G.T @ G) / float(P)
+    w, V = np.linalg.eigh(K)
+    w, V = w[::-1], V[:, ::-1]
+    m = select_eigenvectors(list(w), threshold)
+    cov = V[:, :m]
+    beta, var, pval = (np.full((P, k), np.nan) for _ in range(3))
+    for c in range(P):
+        x = np.ones((n, 2 + m))
+        x[:, 1:1 + m] = cov
+        x[:, 1 + m] = G[c]
+        rc, b, v, p, _ = ols(x, y)
+        if rc == 0:
+            beta[c], var[c], pval[c] = b[1 + m], v[1 + m], p[1 + m]
+    return m, beta, var, pval

@@ -7,12 +7,13 @@ BATCH of parsed loci instead of one.  All arithmetic runs in libpoolgen_cuda.so 
 nothing here computes on the CPU.
 """
 from .capi import (ALLELE_NAMES, KIND_CHISQ, KIND_CORR, KIND_FISHER, KIND_OLS, LOCUS_FAILED, LOCUS_FILTERED,
-                   LOCUS_OK, LOCUS_PANIC, LOCUS_UNSUPPORTED, Batch, Context, FilterStats, PgError, Scan,
+                   LOCUS_OK, LOCUS_PANIC, LOCUS_UNSUPPORTED, Batch, Context, FilterStats, Kinship, PgError, Scan,
                    ScanResults, synth_counts_host, synth_phen_host)
 
 __all__ = ["ALLELE_NAMES", "KIND_CHISQ", "KIND_CORR", "KIND_FISHER", "KIND_OLS", "LOCUS_FAILED", "LOCUS_FILTERED",
-           "LOCUS_OK", "LOCUS_PANIC", "LOCUS_UNSUPPORTED", "Batch", "Context", "FilterStats", "PgError", "Scan",
-           "ScanResults", "synth_counts_host", "synth_phen_host", "ols_iterate", "correlation", "chisq", "fisher"]
+           "LOCUS_OK", "LOCUS_PANIC", "LOCUS_UNSUPPORTED", "Batch", "Context", "FilterStats", "Kinship", "PgError", "Scan",
+           "ScanResults", "synth_counts_host", "synth_phen_host", "ols_iterate", "correlation", "chisq", "fisher",
+           "ols_with_covariate"]
 
 _SYNC_CODES = (0, 1, 2, 3, 4, 5)
 
@@ -43,3 +44,19 @@ def chisq(ctx, counts, filter_stats, allele_codes=_SYNC_CODES):
 def fisher(ctx, counts, filter_stats, allele_codes=_SYNC_CODES):
     """tables::fisher over a batch."""
     return _run(KIND_FISHER, ctx, counts, filter_stats, None, allele_codes)
+
+
+def ols_with_covariate(ctx, columns, phen, xxt_eigen_variance_explained=0.75):
+    """gwas::ols_with_covariate (src/gwas/ols.rs:278-436) on one GPU: columns f64 [P, n_pools] (the allele columns of
+    intercept_and_allele_frequencies[:, 1..]), phen [n_pools, k].  Returns (n_eigenvecs, beta, var, pval) with the
+    records as [k, P] arrays."""
+    cols = columns
+    kin = Kinship(ctx, cols.shape[1], max(1, cols.shape[0]))
+    try:
+        kin.append_columns(cols)
+        kin.gram()
+        m = kin.eig_select(cols.shape[0], xxt_eigen_variance_explained)
+        beta, var, pval = kin.covar_scan(phen)
+        return m, beta, var, pval
+    finally:
+        kin.close()

@@ -31,6 +31,10 @@ ABI_SYMBOLS = [
     "pg_batch_run", "pg_batch_download", "pg_batch_sync", "pg_batch_results", "pg_batch_time_runs",
     "pg_batch_bytes", "pg_scan_stream_begin", "pg_scan_submit_counts", "pg_scan_submit_counts_u16",
     "pg_scan_submit_freq", "pg_scan_collect", "pg_synth_counts_host", "pg_synth_phen_host",
+    "pg_kin_open", "pg_kin_close", "pg_kin_reset", "pg_kin_columns", "pg_kin_append_columns", "pg_kin_append_counts",
+    "pg_kin_last_labels", "pg_kin_synth", "pg_kin_get_columns", "pg_kin_gram", "pg_kin_gram_time", "pg_kin_partial",
+    "pg_kin_partial_get", "pg_kin_partial_set", "pg_kin_eig_select", "pg_kin_eigvals", "pg_kin_set_covariates",
+    "pg_kin_covar_scan",
 ]
 
 
@@ -102,6 +106,24 @@ def lib():
             "pg_scan_collect": (i, [vp, i, C.POINTER(_Results)]),
             "pg_synth_counts_host": (i, [u64, i64, i64, i, i, vp]),
             "pg_synth_phen_host": (i, [u64, i, i, vp]),
+            "pg_kin_open": (i, [vp, i, i64, pvp]),
+            "pg_kin_close": (i, [vp]),
+            "pg_kin_reset": (i, [vp]),
+            "pg_kin_columns": (i64, [vp]),
+            "pg_kin_append_columns": (i, [vp, vp, i64]),
+            "pg_kin_append_counts": (i, [vp, C.POINTER(_Filter), i, C.POINTER(C.c_uint8), vp, i64, i, C.POINTER(i64)]),
+            "pg_kin_last_labels": (i, [vp, i64, vp, vp]),
+            "pg_kin_synth": (i, [vp, u64, i64, i64]),
+            "pg_kin_get_columns": (i, [vp, i64, i64, vp]),
+            "pg_kin_gram": (i, [vp]),
+            "pg_kin_gram_time": (i, [vp, i, C.POINTER(C.c_float)]),
+            "pg_kin_partial": (i, [vp, pvp, C.POINTER(C.c_size_t)]),
+            "pg_kin_partial_get": (i, [vp, vp]),
+            "pg_kin_partial_set": (i, [vp, vp]),
+            "pg_kin_eig_select": (i, [vp, i64, C.c_double, C.POINTER(i)]),
+            "pg_kin_eigvals": (i, [vp, vp, i]),
+            "pg_kin_set_covariates": (i, [vp, vp, i]),
+            "pg_kin_covar_scan": (i, [vp, vp, i, i, C.POINTER(C.c_float), pvp, pvp, pvp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -320,6 +342,118 @@ class Batch:
     def close(self):
         if self._h:
             lib().pg_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class Kinship:
+    """ols_with_covariate (src/gwas/ols.rs:278-436) over this GPU's shard of allele columns (pg_kin_*)."""
+
+    def __init__(self, ctx: Context, n_pools: int, max_columns: int):
+        self.ctx, self.n = ctx, int(n_pools)
+        self._h = C.c_void_p()
+        _check(lib().pg_kin_open(ctx._h, int(n_pools), int(max_columns), C.byref(self._h)), ctx._h, "pg_kin_open")
+
+    def _ck(self, rc, what):
+        _check(rc, self.ctx._h, what)
+
+    @property
+    def columns(self) -> int:
+        return int(lib().pg_kin_columns(self._h))
+
+    def reset(self):
+        self._ck(lib().pg_kin_reset(self._h), "pg_kin_reset")
+
+    def append_columns(self, cols):
+        """cols: f64 [P_add, n_pools] (one allele column per row)."""
+        c = np.ascontiguousarray(cols, dtype=np.float64)
+        assert c.ndim == 2 and c.shape[1] == self.n, c.shape
+        self._ck(lib().pg_kin_append_columns(self._h, c.ctypes.data, int(c.shape[0])), "pg_kin_append_columns")
+
+    def append_counts(self, counts, allele_codes, fs: FilterStats, keep_p_minus_1: bool = False):
+        """counts: uint32 [L, A, n_pools]; returns (col_locus int64 [P_add], col_allele uint8 [P_add])."""
+        c = np.ascontiguousarray(counts, dtype=np.uint32)
+        codes = np.ascontiguousarray(allele_codes, dtype=np.uint8)
+        ps = np.ascontiguousarray(fs.pool_sizes, dtype=np.float64)
+        f = _Filter(int(fs.remove_ns), int(fs.min_coverage_depth), float(fs.min_allele_frequency),
+                    float(fs.max_missingness_rate), int(ps.size), ps.ctypes.data_as(C.POINTER(C.c_double)))
+        added = C.c_int64()
+        self._ck(lib().pg_kin_append_counts(self._h, C.byref(f), int(codes.size),
+                                            codes.ctypes.data_as(C.POINTER(C.c_uint8)), c.ctypes.data, int(c.shape[0]),
+                                            int(keep_p_minus_1), C.byref(added)), "pg_kin_append_counts")
+        n_add = int(added.value)
+        loc = np.empty(n_add, dtype=np.int64)
+        alle = np.empty(n_add, dtype=np.uint8)
+        self._ck(lib().pg_kin_last_labels(self._h, n_add, loc.ctypes.data, alle.ctypes.data), "pg_kin_last_labels")
+        return loc, alle
+
+    def synth(self, seed: int, first_locus: int, n_loci: int):
+        self._ck(lib().pg_kin_synth(self._h, int(seed), int(first_locus), int(n_loci)), "pg_kin_synth")
+
+    def get_columns(self, first: int, count: int) -> np.ndarray:
+        out = np.empty((count, self.n), dtype=np.float64)
+        self._ck(lib().pg_kin_get_columns(self._h, int(first), int(count), out.ctypes.data), "pg_kin_get_columns")
+        return out
+
+    def gram(self):
+        self._ck(lib().pg_kin_gram(self._h), "pg_kin_gram")
+
+    def gram_time(self, iters: int) -> float:
+        ms = C.c_float()
+        self._ck(lib().pg_kin_gram_time(self._h, int(iters), C.byref(ms)), "pg_kin_gram_time")
+        return float(ms.value)
+
+    def partial_device_ptr(self):
+        """(device pointer, element count) of the n x n partial Gram matrix, for an NCCL all-reduce by the caller."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(lib().pg_kin_partial(self._h, C.byref(p), C.byref(n)), "pg_kin_partial")
+        return int(p.value), int(n.value)
+
+    def partial_get(self) -> np.ndarray:
+        out = np.empty((self.n, self.n), dtype=np.float64)
+        self._ck(lib().pg_kin_partial_get(self._h, out.ctypes.data), "pg_kin_partial_get")
+        return out
+
+    def partial_set(self, K):
+        k = np.ascontiguousarray(K, dtype=np.float64)
+        assert k.shape == (self.n, self.n)
+        self._ck(lib().pg_kin_partial_set(self._h, k.ctypes.data), "pg_kin_partial_set")
+
+    def eig_select(self, P_total: int, variance_explained: float) -> int:
+        m = C.c_int()
+        self._ck(lib().pg_kin_eig_select(self._h, int(P_total), float(variance_explained), C.byref(m)), "pg_kin_eig_select")
+        return int(m.value)
+
+    def eigvals(self, count: int) -> np.ndarray:
+        out = np.empty(count, dtype=np.float64)
+        self._ck(lib().pg_kin_eigvals(self._h, out.ctypes.data, int(count)), "pg_kin_eigvals")
+        return out
+
+    def set_covariates(self, cov):
+        c = np.ascontiguousarray(cov, dtype=np.float64).reshape(self.n, -1)
+        self._ck(lib().pg_kin_set_covariates(self._h, c.ctypes.data if c.size else None, int(c.shape[1])), "pg_kin_set_covariates")
+
+    def covar_scan(self, phen, iters: int = 0):
+        """phen [n_pools, k] -> (beta, var, pval) each [k, columns] (+ milliseconds of `iters` launches if iters > 0)."""
+        y = np.ascontiguousarray(phen, dtype=np.float64)
+        if y.ndim == 1:
+            y = y[:, None].copy()
+        k = y.shape[1]
+        ms = C.c_float()
+        pb, pv, pp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(lib().pg_kin_covar_scan(self._h, y.ctypes.data, int(k), int(iters), C.byref(ms), C.byref(pb), C.byref(pv),
+                                         C.byref(pp)), "pg_kin_covar_scan")
+        P = self.columns
+
+        def arr(p):
+            if P == 0:
+                return np.zeros((k, 0))
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(k, P)).copy()
+        out = (arr(pb), arr(pv), arr(pp))
+        return out + (float(ms.value),) if iters > 0 else out
+
+    def close(self):
+        if self._h:
+            lib().pg_kin_close(self._h)
             self._h = C.c_void_p()
 
 

@@ -64,6 +64,13 @@ __device__ __forceinline__ void warp_reduce32(double (&v)[32], int lane) {
     }
 }
 
+// fixed-order butterfly sum: every lane ends up with the same bits
+__device__ __forceinline__ double warp_sum_fixed(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(PG_FULL_MASK, v, off);
+    return v;
+}
+
 // ---- statrs 0.16 compatible tails -------------------------------------
 // beta_reg(a, b, x) with ln_beta = lnG(a+b) - lnG(a) - lnG(b) supplied by the host (it only depends on
 // the degrees of freedom, which are constant for a scan).

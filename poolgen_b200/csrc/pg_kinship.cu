@@ -1,3 +1,1147 @@
-// pg_kinship.cu -- ols_iter_with_kinship (src/gwas/ols.rs:278-436): placeholder translation unit,
-// the FP64 DMMA kinship GEMM and the covariate scan are built in a later milestone.
+// pg_kinship.cu -- ols_iter_with_kinship (ols_with_covariate, src/gwas/ols.rs:278-436) on sm_100a:
+//   load_*        LoadAll::load + into_genotypes_and_phenotypes (src/base/sync.rs:973-1179): a slab of parsed loci ->
+//                 filter -> renormalised frequencies of the kept alleles -> allele columns G[:, c] (column-major,
+//                 one column contiguous), i.e. intercept_and_allele_frequencies[:, 1..]
+//   gram_kernel   K_partial = G G' (src/gwas/ols.rs:295), FP64 tensor cores (mma.sync m8n8k4 f64 -> SASS DMMA),
+//                 operands staged through shared memory by bulk copies, split over column slices and the upper
+//                 triangle of 128 x 128 tiles; the slices are summed in a fixed order (bit-reproducible)
+//   eig_select    kinship.eig() + PC selection (ols.rs:296-315): cuSOLVER syevd, eigenvalues taken from high to low
+//                 as the reference assumes, covariates = the first m eigenvectors
+//   covar_kernel  the per-column regression with X = [1 | PCs | g] (ols.rs:340-370) in its Frisch-Waugh form: with Q
+//                 an orthonormal basis of [1 | PCs] and y~ = y - QQ'y,  b = g'y~ / (g'g - |Q'g|^2),
+//                 RSS = y~'y~ - b g'y~, var = RSS / (n - (2+m)) / (g'g - |Q'g|^2), p from Student-t(n-1) -- identical to
+//                 the last coefficient of the reference's normal equations up to rounding
+#include <cub/device/device_scan.cuh>
+#include <cusolverDn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "pg_device.cuh"
 #include "pg_internal.h"
+#include "pg_ptable.h"
+
+namespace pg {
+
+// ================================================================================================================
+// 1. column loader
+// ================================================================================================================
+struct LoadParams {
+    const uint32_t *counts;  // [locus][A_in][n]
+    int64_t n_loci;
+    int n, A_in, drop_col, ldg;
+    int keep_p_minus_1;
+    double maf, one_minus_maf, max_miss, min_depth_f;
+    const double *w;  // [n] s_i / sum(s)
+    uint8_t codes[8];
+    uint32_t *sel;      // [locus] number of columns | 4-bit input column index per emitted column << (4 + 4 s)
+    int64_t *offsets;   // [locus] exclusive scan of the column counts
+    double *G;          // [column][ldg]
+    int64_t col_base;
+    int64_t *col_locus;  // [column] locus ordinal inside the slab
+    uint8_t *col_allele; // [column] allele code
+};
+
+// pass 1: one warp per locus, lane = pool (stride 32): the reference's keep-mask and, with keep_p_minus_1, its order
+__global__ void __launch_bounds__(256) load_decide_kernel(const LoadParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int A = p.A_in - (p.drop_col >= 0 ? 1 : 0);
+    for (int64_t locus = warp; locus < p.n_loci; locus += nwarps) {
+        const uint32_t *cl = p.counts + (size_t)locus * p.A_in * p.n;
+        int col_of[PG_MAX_ALLELES];
+        {
+            int jj = 0;
+            for (int j = 0; j < p.A_in; j++)
+                if (j != p.drop_col) col_of[jj++] = j;
+        }
+        // depth filter and first-stage pooled frequencies q_j (parallel sums, exact re-evaluation near a threshold)
+        double qs[PG_MAX_ALLELES];
+        for (int j = 0; j < PG_MAX_ALLELES; j++) qs[j] = 0.0;
+        uint32_t dmin = 0xFFFFFFFFu;
+        int miss = 0;
+        for (int i = lane; i < p.n; i += 32) {
+            uint64_t d = 0;
+            uint32_t c[PG_MAX_ALLELES];
+            for (int j = 0; j < A; j++) {
+                c[j] = cl[(size_t)col_of[j] * p.n + i];
+                d += c[j];
+            }
+            if (d > 0xFFFFFFFEull) d = 0xFFFFFFFEull;
+            dmin = min(dmin, (uint32_t)d);
+            if (d == 0) {
+                miss++;
+            } else {
+                const double dd = (double)d, wi = p.w[i];
+                for (int j = 0; j < A; j++) qs[j] = fma((double)c[j] / dd, wi, qs[j]);
+            }
+        }
+        dmin = __reduce_min_sync(PG_FULL_MASK, dmin);
+        miss = __reduce_add_sync(PG_FULL_MASK, miss);
+        uint32_t sel = 0;
+        bool keep = !((double)dmin < p.min_depth_f);
+        unsigned kept = 0;
+        if (keep) {
+            const double tol = 2.0 * ((double)p.n + 8.0) * kEps;
+            for (int j = 0; j < A; j++) {
+                double q = qs[j];
+                for (int off = 16; off >= 1; off >>= 1) q += __shfl_xor_sync(PG_FULL_MASK, q, off);
+                const double tl = tol * fmax(fabs(q), 1.0);
+                if (fabs(q - p.maf) <= tl || fabs(q - p.one_minus_maf) <= tl) {
+                    // the reference's order: sequential over the pools, separately rounded multiply and add
+                    double qe = 0.0;
+                    if (lane == 0) {
+                        for (int i = 0; i < p.n; i++) {
+                            uint64_t d = 0;
+                            for (int l = 0; l < A; l++) d += cl[(size_t)col_of[l] * p.n + i];
+                            if (d == 0) continue;
+                            const double f = (double)cl[(size_t)col_of[j] * p.n + i] / (double)d;
+                            qe = __dadd_rn(qe, __dmul_rn(f, p.w[i]));
+                        }
+                    }
+                    q = __shfl_sync(PG_FULL_MASK, qe, 0);
+                }
+                if (!((q < p.maf) | (q > p.one_minus_maf))) kept |= 1u << j;
+            }
+            if (__popc(kept) < 2) keep = false;
+            // missingness on the first kept column (sync.rs:287-299)
+            if (keep && (miss == p.n || ((double)miss / (double)p.n) > p.max_miss)) keep = false;
+        }
+        if (keep) {
+            int order[PG_MAX_ALLELES], no = 0;
+            for (int j = 0; j < A; j++)
+                if ((kept >> j) & 1u) order[no++] = j;
+            if (p.keep_p_minus_1) {
+                // sort_by_allele_freq(true) then drop the first column (sync.rs:1017-1027, 478-505): column sums of the
+                // renormalised frequencies, sequential over the pools (lane j sums column j)
+                double cs = 0.0;
+                if (lane < A && ((kept >> lane) & 1u)) {
+                    for (int i = 0; i < p.n; i++) {
+                        uint64_t dk = 0;
+                        for (int l = 0; l < A; l++)
+                            if ((kept >> l) & 1u) dk += cl[(size_t)col_of[l] * p.n + i];
+                        if (dk == 0) continue;
+                        cs = __dadd_rn(cs, (double)cl[(size_t)col_of[lane] * p.n + i] / (double)dk);
+                    }
+                }
+                double csj[PG_MAX_ALLELES];
+                for (int j = 0; j < A; j++) csj[j] = __shfl_sync(PG_FULL_MASK, cs, j);
+                int sorted[PG_MAX_ALLELES];
+                for (int a = 0; a < no; a++) {
+                    const int j = order[a];
+                    int rank = 0;
+                    for (int b = 0; b < no; b++) {
+                        const int l = order[b];
+                        if (l != j && (csj[l] > csj[j] || (csj[l] == csj[j] && l < j))) rank++;
+                    }
+                    sorted[rank] = j;
+                }
+                no -= 1;
+                for (int a = 0; a < no; a++) order[a] = sorted[a + 1];
+            }
+            sel = (uint32_t)no;
+            for (int a = 0; a < no; a++) sel |= (uint32_t)order[a] << (4 + 4 * a);
+            sel |= kept << 24;
+        }
+        if (lane == 0) {
+            p.sel[locus] = sel;
+            p.offsets[locus] = (int64_t)(sel & 0xf);
+        }
+    }
+}
+
+// pass 2: renormalised frequencies of the emitted columns (to_frequencies after the filter, sync.rs:166-192)
+__global__ void __launch_bounds__(256) load_emit_kernel(const LoadParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int A = p.A_in - (p.drop_col >= 0 ? 1 : 0);
+    for (int64_t locus = warp; locus < p.n_loci; locus += nwarps) {
+        const uint32_t sel = p.sel[locus];
+        const int no = (int)(sel & 0xf);
+        if (no == 0) continue;
+        const unsigned kept = sel >> 24;
+        const int64_t c0 = p.col_base + p.offsets[locus];
+        const uint32_t *cl = p.counts + (size_t)locus * p.A_in * p.n;
+        int col_of[PG_MAX_ALLELES];
+        {
+            int jj = 0;
+            for (int j = 0; j < p.A_in; j++)
+                if (j != p.drop_col) col_of[jj++] = j;
+        }
+        for (int i = lane; i < p.ldg; i += 32) {
+            uint64_t dk = 0;
+            if (i < p.n)
+                for (int l = 0; l < A; l++)
+                    if ((kept >> l) & 1u) dk += cl[(size_t)col_of[l] * p.n + i];
+            for (int a = 0; a < no; a++) {
+                const int j = (int)((sel >> (4 + 4 * a)) & 0xf);
+                double v = 0.0;
+                if (i < p.n) v = dk ? (double)cl[(size_t)col_of[j] * p.n + i] / (double)dk : nan("");
+                p.G[(size_t)(c0 + a) * p.ldg + i] = v;
+            }
+        }
+        if (lane < no) {
+            const int j = (int)((sel >> (4 + 4 * lane)) & 0xf);
+            p.col_locus[c0 + lane - p.col_base] = locus;
+            p.col_allele[c0 + lane - p.col_base] = p.codes[col_of[j]];
+        }
+    }
+}
+
+// synthetic biallelic columns for the C4 workload: locus l contributes two columns f and 1 - f over the pools, built
+// from the same integer-hash counts as the scan workload (alleles A and T only)
+__global__ void __launch_bounds__(256) kin_synth_kernel(uint64_t seed, int64_t first_locus, int64_t n_loci, int n,
+                                                        int ldg, double *G) {
+    const int64_t total = n_loci * ldg;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = idx / ldg;
+        const int i = (int)(idx - l * ldg);
+        double f0 = 0.0, f1 = 0.0;
+        if (i < n) {
+            uint32_t c[PG_MAX_ALLELES];
+            synth_counts(seed, first_locus + l, i, 4, c);
+            const uint32_t a = c[0] + c[2], b = c[1] + c[3];  // fold to two alleles, depth 20..100 (or 0)
+            const uint32_t d = a + b;
+            f0 = d ? (double)a / (double)d : 0.5;
+            f1 = d ? (double)b / (double)d : 0.5;
+        }
+        G[(size_t)(2 * l) * ldg + i] = f0;
+        G[(size_t)(2 * l + 1) * ldg + i] = f1;
+    }
+}
+
+// ================================================================================================================
+// 2. kinship Gram matrix: FP64 DMMA SYRK
+// ================================================================================================================
+constexpr int kTile = 128;           // C tile edge
+constexpr int kKC = 16;              // columns of G (the contraction index) per stage
+constexpr int kPitch = kTile + 4;    // shared row pitch: 132 = 4 (mod 16) doubles -> conflict-free fragment loads
+constexpr int kStages = 4;
+constexpr int kGramWarps = 8;        // consumer warps: 2 (rows) x 4 (columns), warp tile 64 x 32
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct GramParams {
+    const double *G;   // [P_pad][ldg]
+    int64_t P_pad;     // multiple of kKC, the pad columns are zero
+    int ldg, n;
+    int nt;            // tiles per edge
+    int n_slices;
+    int64_t slice_cols;  // multiple of kKC
+    double *ws;        // [slice][tile][kTile*kTile]
+};
+
+__global__ void __launch_bounds__((kGramWarps + 1) * 32, 1) gram_kernel(const GramParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + kStages;
+    double *tiles = reinterpret_cast<double *>(smem + 128);  // [stage][2][kKC][kPitch]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kGramWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int ntiles = p.nt * (p.nt + 1) / 2;
+    const int64_t n_items = (int64_t)ntiles * p.n_slices;
+    uint32_t it_stage = 0;  // running stage counter (same sequence on the producer and the consumers)
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int slice = (int)(item / ntiles);
+        int tile = (int)(item - (int64_t)slice * ntiles);
+        int ti = 0;
+        while (tile >= p.nt - ti) {  // row ti of the upper triangle holds nt - ti tiles
+            tile -= p.nt - ti;
+            ti++;
+        }
+        const int tj = ti + tile;
+        const bool diag = ti == tj;
+        const int64_t k_begin = (int64_t)slice * p.slice_cols;
+        const int64_t k_end = min(p.P_pad, k_begin + p.slice_cols);
+        const int n_steps = (int)((k_end - k_begin + kKC - 1) / kKC);
+        if (warp == kGramWarps) {
+            // ---- producer warp: lane r < 16 copies row r of the A tile, lane 16 + r row r of the B tile
+            for (int st = 0; st < n_steps; st++) {
+                const uint32_t s = (it_stage + st) % kStages, use = (it_stage + st) / kStages;
+                if (use > 0) mbar_wait(&empty[s], (use - 1) & 1u);
+                if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(kKC * kTile * 8 * (diag ? 1 : 2)));
+                __syncwarp();
+                const int r = lane & 15, which = lane >> 4;
+                if (which == 0 || !diag) {
+                    const int64_t k = k_begin + (int64_t)st * kKC + r;
+                    const double *src = p.G + (size_t)k * p.ldg + (size_t)(which ? tj : ti) * kTile;
+                    double *dst = tiles + ((size_t)(s * 2 + which) * kKC + r) * kPitch;
+                    bulk_g2s(dst, src, kTile * 8, &full[s]);
+                }
+            }
+        } else {
+            // ---- consumer warps
+            const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
+            double acc[8][4][2];
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int st = 0; st < n_steps; st++) {
+                const uint32_t s = (it_stage + st) % kStages, use = (it_stage + st) / kStages;
+                mbar_wait(&full[s], use & 1u);
+                const double *As = tiles + (size_t)(s * 2) * kKC * kPitch + wm * 64 + g;
+                const double *Bs = tiles + (size_t)(s * 2 + (diag ? 0 : 1)) * kKC * kPitch + wn * 32 + g;
+#pragma unroll
+                for (int kk = 0; kk < kKC / 4; kk++) {
+                    double a[8], b[4];
+#pragma unroll
+                    for (int mi = 0; mi < 8; mi++) a[mi] = As[(kk * 4 + t) * kPitch + mi * 8];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) b[ni] = Bs[(kk * 4 + t) * kPitch + ni * 8];
+#pragma unroll
+                    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+            // partial tile of this (slice, tile) -> workspace
+            double *out = p.ws + ((size_t)slice * ntiles + (item - (int64_t)slice * ntiles)) * (kTile * kTile);
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    const int row = wm * 64 + mi * 8 + g, col = wn * 32 + ni * 8 + 2 * t;
+                    *reinterpret_cast<double2 *>(out + (size_t)row * kTile + col) =
+                        make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                }
+        }
+        it_stage += (uint32_t)n_steps;
+    }
+}
+
+// K[i][j] = K[j][i] = sum over the slices (fixed order) of the partial tiles
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const double *ws, int nt, int n_slices, int n, double *K) {
+    const int ntiles = nt * (nt + 1) / 2;
+    const int64_t total = (int64_t)ntiles * kTile * kTile;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int tile = (int)(idx / (kTile * kTile));
+        const int e = (int)(idx - (int64_t)tile * kTile * kTile);
+        const int tile_id = tile;
+        int ti = 0;
+        while (tile >= nt - ti) {
+            tile -= nt - ti;
+            ti++;
+        }
+        const int tj = ti + tile;
+        const int i = ti * kTile + e / kTile, j = tj * kTile + e % kTile;
+        if (i >= n || j >= n || j < i) continue;
+        double s = 0.0;
+        for (int sl = 0; sl < n_slices; sl++) s += ws[((size_t)sl * ntiles + tile_id) * (kTile * kTile) + e];
+        K[(size_t)i * n + j] = s;
+        K[(size_t)j * n + i] = s;
+    }
+}
+
+// ================================================================================================================
+// 3. covariate scan
+// ================================================================================================================
+struct CovarParams {
+    const double *G;
+    int64_t P;
+    int ldg, n;
+    int nq;            // columns of Q = 1 + m
+    int k;             // phenotypes
+    const double *V;   // [nq + k][ldg]: Q columns then y~ columns (device)
+    double yy[kMaxPhenPerPass * 4];  // y~'y~ per phenotype (k <= 16)
+    double dfe;        // n - (2 + m)
+    double df;         // n - 1
+    const void *ptab;
+    double ptab_vmax, ptab_inv_h;
+    int ptab_M;
+    double ln_beta;
+    double *beta, *var, *pval;  // [k][P]
+};
+
+constexpr int kCovarMaxVec = 12;  // nq + k vectors resident in shared memory (templated on the count)
+
+template <int NV>
+__global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
+    extern __shared__ __align__(16) double vs[];  // [NV][ldg]
+    const int ldg = p.ldg;
+    for (int i = threadIdx.x; i < NV * ldg; i += blockDim.x) vs[i] = p.V[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
+    const int nq = p.nq, k = p.k;
+    for (int64_t c = warp; c < p.P; c += nwarps) {
+        const double *g = p.G + (size_t)c * ldg;
+        double acc[NV], gg = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[v] = 0.0;
+#pragma unroll 4
+        for (int r = 2 * lane; r < ldg; r += 64) {
+            const double2 g2 = __ldcs(reinterpret_cast<const double2 *>(g + r));
+            gg = fma(g2.x, g2.x, gg);
+            gg = fma(g2.y, g2.y, gg);
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                const double2 q2 = *reinterpret_cast<const double2 *>(vs + (size_t)v * ldg + r);
+                acc[v] = fma(g2.x, q2.x, acc[v]);
+                acc[v] = fma(g2.y, q2.y, acc[v]);
+            }
+        }
+        gg = warp_sum_fixed(gg);
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[v] = warp_sum_fixed(acc[v]);
+        double uu = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+            if (v < nq) uu = fma(acc[v], acc[v], uu);
+        double ggc = gg - uu;
+        double gy[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) gy[v] = acc[v];
+        if (!(gg <= 1e4 * ggc)) {
+            // cancellation: second pass with explicit residuals g - Q u (the column is still in L2)
+            double s2 = 0.0, sy[NV];
+#pragma unroll
+            for (int v = 0; v < NV; v++) sy[v] = 0.0;
+            for (int r = lane; r < p.n; r += 32) {
+                double e = g[r];
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+                    if (v < nq) e = fma(-acc[v], vs[(size_t)v * ldg + r], e);
+                s2 = fma(e, e, s2);
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+                    if (v >= nq) sy[v] = fma(e, vs[(size_t)v * ldg + r], sy[v]);
+            }
+            ggc = warp_sum_fixed(s2);
+#pragma unroll
+            for (int v = 0; v < NV; v++)
+                if (v >= nq) gy[v] = warp_sum_fixed(sy[v]);
+        }
+        // lane j < k finishes phenotype j
+        double b = nan(""), vb = nan(""), pv = nan("");
+        double gyj = 0.0, yyj = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+            if (v - nq == lane) gyj = gy[v];
+#pragma unroll
+        for (int j = 0; j < kMaxPhenPerPass * 4; j++)
+            if (j == lane) yyj = p.yy[j];
+        if (lane < k) {
+            if (ggc > 0.0 && p.dfe > 0.0) {
+                b = gyj / ggc;
+                double rss = yyj - b * gyj;
+                if (rss < 0.0) rss = 0.0;
+                vb = rss / p.dfe / ggc;
+                // estimate_significance, src/gwas/ols.rs:139-154
+                const double tt = (fabs(b) <= kEps) ? 0.0 : b / sqrt(vb);
+                if (fabs(tt) <= kEps || tt != tt)
+                    pv = 1.0;
+                else
+                    pv = p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab) : student_two_sided(fabs(tt), p.df, p.ln_beta);
+            } else if (gg != gg) {
+                pv = 1.0;  // NaN frequencies: the reference's t is NaN and its p is forced to 1 (ols.rs:150-151)
+            }
+            p.beta[(size_t)lane * p.P + c] = b;
+            p.var[(size_t)lane * p.P + c] = vb;
+            p.pval[(size_t)lane * p.P + c] = pv;
+        }
+    }
+}
+
+// Any number of covariates: the column is staged in shared memory (one slot per warp), the 1 + m + k vectors stream
+// from global memory (L2 resident), u = Q'g goes to the warp's shared slot.  O(n (m + k)) per column like the fast
+// kernel, without its register / shared-memory limits.
+__global__ void __launch_bounds__(256) covar_generic_kernel(const CovarParams p) {
+    extern __shared__ __align__(16) double gs[];  // [warps][ldg + nv]
+    const int ldg = p.ldg, nq = p.nq, k = p.k, nv = nq + k;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *gcol = gs + (size_t)wib * (ldg + nv);
+    double *u = gcol + ldg;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
+    for (int64_t c = warp; c < p.P; c += nwarps) {
+        const double *g = p.G + (size_t)c * ldg;
+        double gg = 0.0;
+        for (int r = lane; r < ldg; r += 32) {
+            const double v = g[r];
+            gcol[r] = v;
+            gg = fma(v, v, gg);
+        }
+        gg = warp_sum_fixed(gg);
+        __syncwarp();
+        double uu = 0.0;
+        for (int v = 0; v < nv; v++) {
+            const double *q = p.V + (size_t)v * ldg;
+            double a = 0.0;
+            for (int r = lane; r < ldg; r += 32) a = fma(gcol[r], q[r], a);
+            a = warp_sum_fixed(a);
+            if (lane == 0) u[v] = a;
+            if (v < nq) uu = fma(a, a, uu);
+        }
+        __syncwarp();
+        double ggc = gg - uu;
+        const bool redo = !(gg <= 1e4 * ggc);
+        if (redo) {  // explicit residual e = g - Q u, then e'e and e'y~
+            for (int r = lane; r < ldg; r += 32) {
+                double e = gcol[r];
+                for (int v = 0; v < nq; v++) e = fma(-u[v], p.V[(size_t)v * ldg + r], e);
+                gcol[r] = e;
+            }
+            __syncwarp();
+            double s2 = 0.0;
+            for (int r = lane; r < p.n; r += 32) s2 = fma(gcol[r], gcol[r], s2);
+            ggc = warp_sum_fixed(s2);
+            for (int j = 0; j < k; j++) {
+                const double *yt = p.V + (size_t)(nq + j) * ldg;
+                double a = 0.0;
+                for (int r = lane; r < p.n; r += 32) a = fma(gcol[r], yt[r], a);
+                a = warp_sum_fixed(a);
+                if (lane == 0) u[nq + j] = a;
+            }
+            __syncwarp();
+        }
+        if (lane < k) {
+            double b = nan(""), vb = nan(""), pv = nan("");
+            const double gyj = u[nq + lane], yyj = p.yy[lane];
+            if (ggc > 0.0 && p.dfe > 0.0) {
+                b = gyj / ggc;
+                double rss = yyj - b * gyj;
+                if (rss < 0.0) rss = 0.0;
+                vb = rss / p.dfe / ggc;
+                const double tt = (fabs(b) <= kEps) ? 0.0 : b / sqrt(vb);
+                if (fabs(tt) <= kEps || tt != tt)
+                    pv = 1.0;
+                else
+                    pv = p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab) : student_two_sided(fabs(tt), p.df, p.ln_beta);
+            } else if (gg != gg) {
+                pv = 1.0;
+            }
+            p.beta[(size_t)lane * p.P + c] = b;
+            p.var[(size_t)lane * p.P + c] = vb;
+            p.pval[(size_t)lane * p.P + c] = pv;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace pg
+
+// ================================================================================================================
+// C ABI
+// ================================================================================================================
+struct pg_kin {
+    pg_ctx *ctx = nullptr;
+    int n = 0, ldg = 0;
+    int64_t cap = 0, P = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double *d_G = nullptr;
+    double *d_K = nullptr;    // [n][n] partial Gram matrix (sum over the resident columns)
+    double *d_ws = nullptr;   // split-K workspace
+    size_t ws_bytes = 0;
+    int nt = 0, n_slices = 0;
+    // covariates
+    int m = -1;
+    std::vector<double> eigvals;  // descending
+    std::vector<double> Q;        // [1+m][ldg] orthonormal basis of [1 | PCs] (host)
+    double *d_V = nullptr;        // [(1+m) + k][ldg]
+    size_t V_bytes = 0;
+    double *d_ptab = nullptr;
+    double ptab_vmax = 0, ptab_inv_h = 0;
+    int ptab_M = 0;
+    // results
+    int k = 0;
+    double *d_res = nullptr;  // [3][k][P]
+    double *h_res = nullptr;  // pinned
+    size_t res_elems = 0;
+    // loader scratch
+    uint32_t *d_sel = nullptr;
+    int64_t *d_off = nullptr;
+    int64_t *d_col_locus = nullptr;
+    uint8_t *d_col_allele = nullptr;
+    void *d_scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+    int64_t load_cap = 0;
+    void *d_counts = nullptr;
+    size_t counts_bytes = 0;
+    double *d_w = nullptr;
+};
+
+static int kfail(pg_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+#define KCUDA(ctx, call)                                                                                  \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return kfail((ctx), PG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+extern "C" {
+
+int pg_kin_open(pg_ctx *ctx, int n_pools, int64_t max_columns, pg_kin **out) {
+    if (!ctx || !out || n_pools < 2 || max_columns < 1) return kfail(ctx, PG_ERR_ARG, "pg_kin_open: bad argument");
+    *out = nullptr;
+    KCUDA(ctx, cudaSetDevice(ctx->device));
+    pg_kin *h = new (std::nothrow) pg_kin();
+    if (!h) return kfail(ctx, PG_ERR_ARG, "out of host memory");
+    h->ctx = ctx;
+    h->n = n_pools;
+    h->ldg = (n_pools + 3) & ~3;
+    h->cap = round_up(max_columns, pg::kKC);
+    h->nt = (h->ldg + pg::kTile - 1) / pg::kTile;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    // + one tile of slack: the last tile of a row reads past ldg into the next column
+    const size_t g_bytes = ((size_t)h->cap * h->ldg + pg::kTile) * 8;
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_G, g_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->d_G, 0, g_bytes, h->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_K, (size_t)n_pools * n_pools * 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->d_K, 0, (size_t)n_pools * n_pools * 8, h->stream);
+    if (e != cudaSuccess) {
+        pg_kin_close(h);
+        return kfail(ctx, PG_ERR_CUDA, "pg_kin_open(%d pools, %lld columns): %s", n_pools, (long long)max_columns,
+                     cudaGetErrorString(e));
+    }
+    *out = h;
+    return PG_OK;
+}
+
+int pg_kin_close(pg_kin *h) {
+    if (!h) return PG_OK;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_G);
+    cudaFree(h->d_K);
+    cudaFree(h->d_ws);
+    cudaFree(h->d_V);
+    cudaFree(h->d_ptab);
+    cudaFree(h->d_res);
+    if (h->h_res) cudaFreeHost(h->h_res);
+    cudaFree(h->d_sel);
+    cudaFree(h->d_off);
+    cudaFree(h->d_col_locus);
+    cudaFree(h->d_col_allele);
+    cudaFree(h->d_scan_tmp);
+    cudaFree(h->d_counts);
+    cudaFree(h->d_w);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PG_OK;
+}
+
+int pg_kin_reset(pg_kin *h) {
+    if (!h) return PG_ERR_ARG;
+    KCUDA(h->ctx, cudaSetDevice(h->ctx->device));
+    KCUDA(h->ctx, cudaMemsetAsync(h->d_G, 0, ((size_t)h->cap * h->ldg + pg::kTile) * 8, h->stream));
+    h->P = 0;
+    return PG_OK;
+}
+
+int64_t pg_kin_columns(pg_kin *h) { return h ? h->P : -1; }
+
+int pg_kin_append_columns(pg_kin *h, const double *cols, int64_t P_add) {
+    if (!h || (!cols && P_add > 0) || P_add < 0) return PG_ERR_ARG;
+    pg_ctx *ctx = h->ctx;
+    if (h->P + P_add > h->cap) return kfail(ctx, PG_ERR_ARG, "pg_kin_append_columns: %lld + %lld columns > capacity %lld",
+                                            (long long)h->P, (long long)P_add, (long long)h->cap);
+    KCUDA(ctx, cudaSetDevice(ctx->device));
+    if (P_add == 0) return PG_OK;
+    KCUDA(ctx, cudaMemcpy2DAsync(h->d_G + (size_t)h->P * h->ldg, (size_t)h->ldg * 8, cols, (size_t)h->n * 8,
+                                 (size_t)h->n * 8, (size_t)P_add, cudaMemcpyHostToDevice, h->stream));
+    h->P += P_add;
+    return PG_OK;
+}
+
+int pg_kin_append_counts(pg_kin *h, const pg_filter *filter, int n_alleles, const uint8_t *codes,
+                         const uint32_t *counts, int64_t n_loci, int keep_p_minus_1, int64_t *n_cols_added) {
+    if (!h || !filter || !codes || (!counts && n_loci > 0) || n_loci < 0 || n_alleles < 1 || n_alleles > PG_MAX_ALLELES)
+        return PG_ERR_ARG;
+    pg_ctx *ctx = h->ctx;
+    if (filter->n_pool_sizes != h->n || !filter->pool_sizes)
+        return kfail(ctx, PG_ERR_ARG, "pg_kin_append_counts: %d pool sizes for %d pools", filter->n_pool_sizes, h->n);
+    KCUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_cols_added) *n_cols_added = 0;
+    if (n_loci == 0) return PG_OK;
+    if (h->load_cap < n_loci) {
+        KCUDA(ctx, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_sel);
+        cudaFree(h->d_off);
+        cudaFree(h->d_col_locus);
+        cudaFree(h->d_col_allele);
+        cudaFree(h->d_scan_tmp);
+        h->d_sel = nullptr, h->d_off = nullptr, h->d_col_locus = nullptr, h->d_col_allele = nullptr, h->d_scan_tmp = nullptr;
+        KCUDA(ctx, cudaMalloc(&h->d_sel, (size_t)n_loci * 4));
+        KCUDA(ctx, cudaMalloc(&h->d_off, (size_t)(n_loci + 1) * 8));
+        KCUDA(ctx, cudaMalloc(&h->d_col_locus, (size_t)n_loci * PG_MAX_SLOTS * 8));
+        KCUDA(ctx, cudaMalloc(&h->d_col_allele, (size_t)n_loci * PG_MAX_SLOTS));
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, h->d_off, h->d_off, (int)(n_loci + 1), h->stream);
+        KCUDA(ctx, cudaMalloc(&h->d_scan_tmp, tmp));
+        h->scan_tmp_bytes = tmp;
+        h->load_cap = n_loci;
+    }
+    const size_t cbytes = (size_t)n_loci * n_alleles * h->n * 4;
+    if (h->counts_bytes < cbytes) {
+        KCUDA(ctx, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_counts);
+        h->d_counts = nullptr;
+        KCUDA(ctx, cudaMalloc(&h->d_counts, cbytes));
+        h->counts_bytes = cbytes;
+    }
+    if (!h->d_w) KCUDA(ctx, cudaMalloc(&h->d_w, (size_t)h->n * 8));
+    {
+        std::vector<double> w(h->n);
+        double S = 0.0;
+        for (int i = 0; i < h->n; i++) S = S + filter->pool_sizes[i];
+        for (int i = 0; i < h->n; i++) w[i] = filter->pool_sizes[i] / S;  // sync.rs:262-270
+        KCUDA(ctx, cudaMemcpyAsync(h->d_w, w.data(), (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
+        KCUDA(ctx, cudaStreamSynchronize(h->stream));
+    }
+    KCUDA(ctx, cudaMemcpyAsync(h->d_counts, counts, cbytes, cudaMemcpyHostToDevice, h->stream));
+    pg::LoadParams lp;
+    memset(&lp, 0, sizeof lp);
+    lp.counts = (const uint32_t *)h->d_counts;
+    lp.n_loci = n_loci;
+    lp.n = h->n;
+    lp.A_in = n_alleles;
+    lp.drop_col = -1;
+    for (int j = 0; j < n_alleles; j++) {
+        lp.codes[j] = codes[j];
+        if (filter->remove_ns && codes[j] == 4) lp.drop_col = j;
+    }
+    lp.ldg = h->ldg;
+    lp.keep_p_minus_1 = keep_p_minus_1 != 0;
+    lp.maf = filter->min_allele_frequency;
+    lp.one_minus_maf = 1.00 - filter->min_allele_frequency;
+    lp.max_miss = filter->max_missingness_rate;
+    lp.min_depth_f = (double)filter->min_coverage_depth;
+    lp.w = h->d_w;
+    lp.sel = h->d_sel;
+    lp.offsets = h->d_off;
+    lp.G = h->d_G;
+    lp.col_base = h->P;
+    lp.col_locus = h->d_col_locus;
+    lp.col_allele = h->d_col_allele;
+    const int grid = (int)std::min<int64_t>((n_loci * 32 + 255) / 256, (int64_t)ctx->sm_count * 8);
+    pg::load_decide_kernel<<<grid, 256, 0, h->stream>>>(lp);
+    KCUDA(ctx, cudaGetLastError());
+    KCUDA(ctx, cudaMemsetAsync(h->d_off + n_loci, 0, 8, h->stream));
+    size_t tmp = h->scan_tmp_bytes;
+    KCUDA(ctx, cub::DeviceScan::ExclusiveSum(h->d_scan_tmp, tmp, h->d_off, h->d_off, (int)(n_loci + 1), h->stream));
+    int64_t added = 0;
+    KCUDA(ctx, cudaMemcpyAsync(&added, h->d_off + n_loci, 8, cudaMemcpyDeviceToHost, h->stream));
+    KCUDA(ctx, cudaStreamSynchronize(h->stream));
+    if (h->P + added > h->cap)
+        return kfail(ctx, PG_ERR_ARG, "pg_kin_append_counts: %lld + %lld columns > capacity %lld", (long long)h->P,
+                     (long long)added, (long long)h->cap);
+    pg::load_emit_kernel<<<grid, 256, 0, h->stream>>>(lp);
+    KCUDA(ctx, cudaGetLastError());
+    h->P += added;
+    if (n_cols_added) *n_cols_added = added;
+    return PG_OK;
+}
+
+int pg_kin_last_labels(pg_kin *h, int64_t n_cols, int64_t *col_locus, uint8_t *col_allele) {
+    if (!h || n_cols < 0) return PG_ERR_ARG;
+    if (n_cols == 0) return PG_OK;
+    KCUDA(h->ctx, cudaMemcpyAsync(col_locus, h->d_col_locus, (size_t)n_cols * 8, cudaMemcpyDeviceToHost, h->stream));
+    KCUDA(h->ctx, cudaMemcpyAsync(col_allele, h->d_col_allele, (size_t)n_cols, cudaMemcpyDeviceToHost, h->stream));
+    KCUDA(h->ctx, cudaStreamSynchronize(h->stream));
+    return PG_OK;
+}
+
+int pg_kin_synth(pg_kin *h, uint64_t seed, int64_t first_locus, int64_t n_loci) {
+    if (!h || n_loci < 0) return PG_ERR_ARG;
+    pg_ctx *ctx = h->ctx;
+    if (h->P + 2 * n_loci > h->cap) return kfail(ctx, PG_ERR_ARG, "pg_kin_synth: capacity");
+    KCUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_loci == 0) return PG_OK;
+    const int grid = (int)std::min<int64_t>((n_loci * h->ldg + 255) / 256, (int64_t)ctx->sm_count * 16);
+    pg::kin_synth_kernel<<<grid, 256, 0, h->stream>>>(seed, first_locus, n_loci, h->n, h->ldg,
+                                                      h->d_G + (size_t)h->P * h->ldg);
+    KCUDA(ctx, cudaGetLastError());
+    h->P += 2 * n_loci;
+    return PG_OK;
+}
+
+int pg_kin_get_columns(pg_kin *h, int64_t first, int64_t count, double *out) {
+    if (!h || first < 0 || count < 0 || first + count > h->P || (!out && count)) return PG_ERR_ARG;
+    if (!count) return PG_OK;
+    KCUDA(h->ctx, cudaMemcpy2DAsync(out, (size_t)h->n * 8, h->d_G + (size_t)first * h->ldg, (size_t)h->ldg * 8,
+                                    (size_t)h->n * 8, (size_t)count, cudaMemcpyDeviceToHost, h->stream));
+    KCUDA(h->ctx, cudaStreamSynchronize(h->stream));
+    return PG_OK;
+}
+
+static int gram_launch(pg_kin *h) {
+    pg_ctx *ctx = h->ctx;
+    const int ntiles = h->nt * (h->nt + 1) / 2;
+    const int64_t P_pad = round_up(std::max<int64_t>(h->P, 1), pg::kKC);
+    // column slices: enough (slice, tile) items for ~8 waves over the SMs, each slice a multiple of kKC columns
+    int n_slices = (int)std::max<int64_t>(1, std::min<int64_t>((8LL * ctx->sm_count + ntiles - 1) / ntiles, P_pad / pg::kKC));
+    int64_t slice_cols = round_up((P_pad + n_slices - 1) / n_slices, pg::kKC);
+    n_slices = (int)((P_pad + slice_cols - 1) / slice_cols);
+    const size_t ws = (size_t)n_slices * ntiles * pg::kTile * pg::kTile * 8;
+    if (h->ws_bytes < ws) {
+        KCUDA(ctx, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_ws);
+        h->d_ws = nullptr;
+        KCUDA(ctx, cudaMalloc(&h->d_ws, ws));
+        h->ws_bytes = ws;
+    }
+    h->n_slices = n_slices;
+    pg::GramParams gp;
+    gp.G = h->d_G;
+    gp.P_pad = P_pad;
+    gp.ldg = h->ldg;
+    gp.n = h->n;
+    gp.nt = h->nt;
+    gp.n_slices = n_slices;
+    gp.slice_cols = slice_cols;
+    gp.ws = h->d_ws;
+    const size_t smem = 128 + (size_t)pg::kStages * 2 * pg::kKC * pg::kPitch * 8;
+    KCUDA(ctx, cudaFuncSetAttribute(pg::gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t items = (int64_t)ntiles * n_slices;
+    const int grid = (int)std::min<int64_t>(items, ctx->sm_count);
+    pg::gram_kernel<<<grid, (pg::kGramWarps + 1) * 32, smem, h->stream>>>(gp);
+    KCUDA(ctx, cudaGetLastError());
+    pg::gram_reduce_kernel<<<ctx->sm_count * 4, 256, 0, h->stream>>>(h->d_ws, h->nt, n_slices, h->n, h->d_K);
+    KCUDA(ctx, cudaGetLastError());
+    return PG_OK;
+}
+
+int pg_kin_gram(pg_kin *h) {
+    if (!h) return PG_ERR_ARG;
+    KCUDA(h->ctx, cudaSetDevice(h->ctx->device));
+    return gram_launch(h);
+}
+
+int pg_kin_gram_time(pg_kin *h, int iters, float *ms_total) {
+    if (!h || iters < 1 || !ms_total) return PG_ERR_ARG;
+    pg_ctx *ctx = h->ctx;
+    KCUDA(ctx, cudaSetDevice(ctx->device));
+    KCUDA(ctx, cudaStreamSynchronize(h->stream));
+    KCUDA(ctx, cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < iters; i++) {
+        int rc = gram_launch(h);
+        if (rc) return rc;
+    }
+    KCUDA(ctx, cudaEventRecord(h->ev1, h->stream));
+    KCUDA(ctx, cudaEventSynchronize(h->ev1));
+    KCUDA(ctx, cudaEventElapsedTime(ms_total, h->ev0, h->ev1));
+    return PG_OK;
+}
+
+int pg_kin_partial(pg_kin *h, double **dev_ptr, size_t *n_elems) {
+    if (!h || !dev_ptr) return PG_ERR_ARG;
+    KCUDA(h->ctx, cudaStreamSynchronize(h->stream));
+    *dev_ptr = h->d_K;
+    if (n_elems) *n_elems = (size_t)h->n * h->n;
+    return PG_OK;
+}
+
+int pg_kin_partial_get(pg_kin *h, double *out) {
+    if (!h || !out) return PG_ERR_ARG;
+    KCUDA(h->ctx, cudaMemcpyAsync(out, h->d_K, (size_t)h->n * h->n * 8, cudaMemcpyDeviceToHost, h->stream));
+    KCUDA(h->ctx, cudaStreamSynchronize(h->stream));
+    return PG_OK;
+}
+
+int pg_kin_partial_set(pg_kin *h, const double *in) {
+    if (!h || !in) return PG_ERR_ARG;
+    KCUDA(h->ctx, cudaMemcpyAsync(h->d_K, in, (size_t)h->n * h->n * 8, cudaMemcpyHostToDevice, h->stream));
+    KCUDA(h->ctx, cudaStreamSynchronize(h->stream));
+    return PG_OK;
+}
+
+// K = (sum of the partial Gram matrices) / P_total; eigen-decomposition; number of PCs by the reference's rule
+int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) {
+    if (!h || P_total < 1) return PG_ERR_ARG;
+    pg_ctx *ctx = h->ctx;
+    const int n = h->n;
+    KCUDA(ctx, cudaSetDevice(ctx->device));
+    KCUDA(ctx, cudaStreamSynchronize(h->stream));
+    double *dA = nullptr, *dW = nullptr, *dwork = nullptr;
+    int *dinfo = nullptr;
+    cusolverDnHandle_t cs = nullptr;
+    int rc = PG_OK;
+    std::vector<double> A((size_t)n * n), W(n);
+    do {
+        if (cusolverDnCreate(&cs) != CUSOLVER_STATUS_SUCCESS) { rc = kfail(ctx, PG_ERR_CUDA, "cusolverDnCreate failed"); break; }
+        cusolverDnSetStream(cs, h->stream);
+        if (cudaMalloc(&dA, (size_t)n * n * 8) != cudaSuccess || cudaMalloc(&dW, (size_t)n * 8) != cudaSuccess ||
+            cudaMalloc(&dinfo, 4) != cudaSuccess) { rc = kfail(ctx, PG_ERR_CUDA, "pg_kin_eig_select: out of device memory"); break; }
+        // scale on the host path is avoided: eigenvectors do not depend on the scale, eigenvalue SHARES neither
+        cudaMemcpyAsync(dA, h->d_K, (size_t)n * n * 8, cudaMemcpyDeviceToDevice, h->stream);
+        int lwork = 0;
+        if (cusolverDnDsyevd_bufferSize(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dA, n, dW, &lwork) !=
+            CUSOLVER_STATUS_SUCCESS) { rc = kfail(ctx, PG_ERR_CUDA, "Dsyevd_bufferSize failed"); break; }
+        if (cudaMalloc(&dwork, (size_t)lwork * 8) != cudaSuccess) { rc = kfail(ctx, PG_ERR_CUDA, "syevd workspace"); break; }
+        if (cusolverDnDsyevd(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dA, n, dW, dwork, lwork, dinfo) !=
+            CUSOLVER_STATUS_SUCCESS) { rc = kfail(ctx, PG_ERR_CUDA, "Dsyevd failed"); break; }
+        int info = 0;
+        cudaMemcpyAsync(&info, dinfo, 4, cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(A.data(), dA, (size_t)n * n * 8, cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(W.data(), dW, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess || info != 0) { rc = kfail(ctx, PG_ERR_CUDA, "Dsyevd info %d", info); break; }
+    } while (0);
+    cudaFree(dA);
+    cudaFree(dW);
+    cudaFree(dwork);
+    cudaFree(dinfo);
+    if (cs) cusolverDnDestroy(cs);
+    if (rc) return rc;
+    // syevd returns ascending eigenvalues, column j of A (column-major) = eigenvector j; the reference walks them
+    // "sorted from high to low" (ols.rs:296)
+    h->eigvals.resize(n);
+    for (int i = 0; i < n; i++) h->eigvals[i] = W[n - 1 - i] / (double)P_total;
+    double sum = 0.0;
+    for (int i = 0; i < n; i++) sum = sum + h->eigvals[i];
+    std::vector<double> cum(n);
+    for (int i = 0; i < n; i++) cum[i] = h->eigvals[i] / sum;
+    int m = n;
+    for (int i = 1; i < n; i++) {  // ols.rs:303-311
+        cum[i] = cum[i - 1] + cum[i];
+        if (cum[i - 1] >= threshold && (i - 1) < m) m = i - 1;
+    }
+    h->m = m;
+    if (m_out) *m_out = m;
+    if (m + 2 > n) return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_eig_select: %d covariates for %d pools (the reference's n < p branch is not built)", m, n);
+    // Q = orthonormal basis of [1 | v_1 .. v_m] (modified Gram-Schmidt, twice)
+    const int nq = 1 + m, ldg = h->ldg;
+    h->Q.assign((size_t)nq * ldg, 0.0);
+    for (int i = 0; i < n; i++) h->Q[i] = 1.0;
+    for (int l = 0; l < m; l++)
+        for (int i = 0; i < n; i++) h->Q[(size_t)(1 + l) * ldg + i] = A[(size_t)(n - 1 - l) * n + i];
+    for (int c = 0; c < nq; c++) {
+        double *qc = &h->Q[(size_t)c * ldg];
+        for (int pass = 0; pass < 2; pass++)
+            for (int b = 0; b < c; b++) {
+                const double *qb = &h->Q[(size_t)b * ldg];
+                double d = 0.0;
+                for (int i = 0; i < n; i++) d += qb[i] * qc[i];
+                for (int i = 0; i < n; i++) qc[i] -= d * qb[i];
+            }
+        double nn = 0.0;
+        for (int i = 0; i < n; i++) nn += qc[i] * qc[i];
+        nn = sqrt(nn);
+        if (!(nn > 1e-12)) return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_eig_select: covariate %d is collinear with the intercept", c);
+        for (int i = 0; i < n; i++) qc[i] /= nn;
+    }
+    return PG_OK;
+}
+
+int pg_kin_eigvals(pg_kin *h, double *out, int count) {
+    if (!h || !out || count < 0 || (size_t)count > h->eigvals.size()) return PG_ERR_ARG;
+    for (int i = 0; i < count; i++) out[i] = h->eigvals[i];
+    return PG_OK;
+}
+
+// explicit covariates instead of the eigen step (tests; a caller that already holds the PCs): cov is n x m row-major
+int pg_kin_set_covariates(pg_kin *h, const double *cov, int m) {
+    if (!h || m < 0 || (m > 0 && !cov)) return PG_ERR_ARG;
+    pg_ctx *ctx = h->ctx;
+    const int n = h->n, ldg = h->ldg, nq = 1 + m;
+    if (m + 2 > n) return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_set_covariates: %d covariates for %d pools", m, n);
+    h->m = m;
+    h->Q.assign((size_t)nq * ldg, 0.0);
+    for (int i = 0; i < n; i++) h->Q[i] = 1.0;
+    for (int l = 0; l < m; l++)
+        for (int i = 0; i < n; i++) h->Q[(size_t)(1 + l) * ldg + i] = cov[(size_t)i * m + l];
+    for (int c = 0; c < nq; c++) {
+        double *qc = &h->Q[(size_t)c * ldg];
+        for (int pass = 0; pass < 2; pass++)
+            for (int b = 0; b < c; b++) {
+                const double *qb = &h->Q[(size_t)b * ldg];
+                double d = 0.0;
+                for (int i = 0; i < n; i++) d += qb[i] * qc[i];
+                for (int i = 0; i < n; i++) qc[i] -= d * qb[i];
+            }
+        double nn = 0.0;
+        for (int i = 0; i < n; i++) nn += qc[i] * qc[i];
+        nn = sqrt(nn);
+        if (!(nn > 1e-12)) return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_set_covariates: covariate %d is collinear", c);
+        for (int i = 0; i < n; i++) qc[i] /= nn;
+    }
+    return PG_OK;
+}
+
+}  // extern "C"
+
+template <int NV>
+static cudaError_t covar_launch_nv(const pg::CovarParams &cp, int sm_count, cudaStream_t s) {
+    const size_t smem = (size_t)NV * cp.ldg * 8;
+    auto kern = pg::covar_kernel<NV>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int ctas_per_sm = (int)std::min<size_t>(4, (227 * 1024) / std::max<size_t>(smem, 1));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    kern<<<sm_count * ctas_per_sm, 512, smem, s>>>(cp);
+    return cudaGetLastError();
+}
+
+static int covar_launch(pg_kin *h, const pg::CovarParams &cp) {
+    pg_ctx *ctx = h->ctx;
+    const int nv = cp.nq + cp.k;
+    cudaError_t e;
+    switch (nv) {
+        case 2: e = covar_launch_nv<2>(cp, ctx->sm_count, h->stream); break;
+        case 3: e = covar_launch_nv<3>(cp, ctx->sm_count, h->stream); break;
+        case 4: e = covar_launch_nv<4>(cp, ctx->sm_count, h->stream); break;
+        case 5: e = covar_launch_nv<5>(cp, ctx->sm_count, h->stream); break;
+        case 6: e = covar_launch_nv<6>(cp, ctx->sm_count, h->stream); break;
+        case 7: e = covar_launch_nv<7>(cp, ctx->sm_count, h->stream); break;
+        case 8: e = covar_launch_nv<8>(cp, ctx->sm_count, h->stream); break;
+        case 9: e = covar_launch_nv<9>(cp, ctx->sm_count, h->stream); break;
+        case 10: e = covar_launch_nv<10>(cp, ctx->sm_count, h->stream); break;
+        case 11: e = covar_launch_nv<11>(cp, ctx->sm_count, h->stream); break;
+        case 12: e = covar_launch_nv<12>(cp, ctx->sm_count, h->stream); break;
+        default: {
+            const size_t per_warp = (size_t)(cp.ldg + nv) * 8;
+            int warps = (int)std::min<size_t>(8, (200 * 1024) / per_warp);
+            if (warps < 1) return kfail(ctx, PG_ERR_UNSUPPORTED, "covariate scan: %d pools x %d vectors exceed shared memory", cp.n, nv);
+            const size_t smem = per_warp * warps;
+            e = cudaFuncSetAttribute(pg::covar_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) {
+                pg::covar_generic_kernel<<<ctx->sm_count, warps * 32, smem, h->stream>>>(cp);
+                e = cudaGetLastError();
+            }
+            break;
+        }
+    }
+    if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covar_kernel: %s", cudaGetErrorString(e));
+    return PG_OK;
+}
+
+extern "C" {
+
+// per-column regression; phen n x k row-major.  Results (host, pinned, valid until the next call / close):
+// beta, var, pval each [k][P].  iters > 0: time `iters` launches (ms_total), results from the last one.
+int pg_kin_covar_scan(pg_kin *h, const double *phen, int k, int iters, float *ms_total, const double **beta,
+                      const double **var, const double **pval) {
+    if (!h || !phen || k < 1) return PG_ERR_ARG;
+    pg_ctx *ctx = h->ctx;
+    if (h->m < 0) return kfail(ctx, PG_ERR_STATE, "pg_kin_covar_scan before pg_kin_eig_select / pg_kin_set_covariates");
+    const int n = h->n, ldg = h->ldg, nq = 1 + h->m;
+    if (k > pg::kMaxPhenPerPass * 4)
+        return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_covar_scan: %d phenotypes > %d per call", k, pg::kMaxPhenPerPass * 4);
+    KCUDA(ctx, cudaSetDevice(ctx->device));
+    // y~ = y - Q Q'y on the host (n x k, tiny)
+    std::vector<double> V((size_t)(nq + k) * ldg, 0.0);
+    std::copy(h->Q.begin(), h->Q.end(), V.begin());
+    pg::CovarParams cp;
+    memset(&cp, 0, sizeof cp);
+    for (int j = 0; j < k; j++) {
+        double *yt = &V[(size_t)(nq + j) * ldg];
+        for (int i = 0; i < n; i++) yt[i] = phen[(size_t)i * k + j];
+        for (int pass = 0; pass < 2; pass++)
+            for (int b = 0; b < nq; b++) {
+                const double *qb = &h->Q[(size_t)b * ldg];
+                double d = 0.0;
+                for (int i = 0; i < n; i++) d += qb[i] * yt[i];
+                for (int i = 0; i < n; i++) yt[i] -= d * qb[i];
+            }
+        double yy = 0.0;
+        for (int i = 0; i < n; i++) yy += yt[i] * yt[i];
+        cp.yy[j] = yy;
+    }
+    const size_t vb = V.size() * 8;
+    if (h->V_bytes < vb) {
+        KCUDA(ctx, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_V);
+        h->d_V = nullptr;
+        KCUDA(ctx, cudaMalloc(&h->d_V, vb));
+        h->V_bytes = vb;
+    }
+    KCUDA(ctx, cudaMemcpyAsync(h->d_V, V.data(), vb, cudaMemcpyHostToDevice, h->stream));
+    KCUDA(ctx, cudaStreamSynchronize(h->stream));
+    const double df = (double)n - 1.0;
+    if (!h->d_ptab) {
+        pg::PTable tab = pg::build_ptable(df);
+        if (tab.max_err < 2e-9) {
+            KCUDA(ctx, cudaMalloc(&h->d_ptab, tab.coef.size() * 8));
+            KCUDA(ctx, cudaMemcpy(h->d_ptab, tab.coef.data(), tab.coef.size() * 8, cudaMemcpyHostToDevice));
+            h->ptab_M = tab.M;
+            h->ptab_vmax = tab.v_max;
+            h->ptab_inv_h = tab.inv_h;
+        }
+    }
+    const size_t elems = (size_t)3 * k * std::max<int64_t>(h->P, 1);
+    if (h->res_elems < elems) {
+        KCUDA(ctx, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_res);
+        if (h->h_res) cudaFreeHost(h->h_res);
+        h->d_res = nullptr, h->h_res = nullptr;
+        KCUDA(ctx, cudaMalloc(&h->d_res, elems * 8));
+        KCUDA(ctx, cudaHostAlloc((void **)&h->h_res, elems * 8, cudaHostAllocDefault));
+        h->res_elems = elems;
+    }
+    h->k = k;
+    cp.G = h->d_G;
+    cp.P = h->P;
+    cp.ldg = ldg;
+    cp.n = n;
+    cp.nq = nq;
+    cp.k = k;
+    cp.V = h->d_V;
+    cp.dfe = (double)n - (double)(2 + h->m);
+    cp.df = df;
+    cp.ptab = h->d_ptab;
+    cp.ptab_vmax = h->ptab_vmax;
+    cp.ptab_inv_h = h->ptab_inv_h;
+    cp.ptab_M = h->ptab_M;
+    cp.ln_beta = lgamma(df / 2.0 + 0.5) - lgamma(df / 2.0) - lgamma(0.5);
+    cp.beta = h->d_res;
+    cp.var = h->d_res + (size_t)k * h->P;
+    cp.pval = h->d_res + (size_t)2 * k * h->P;
+    const int reps = iters > 0 ? iters : 1;
+    if (iters > 0) KCUDA(ctx, cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < reps; i++) {
+        int rc = covar_launch(h, cp);
+        if (rc) return rc;
+    }
+    if (iters > 0) KCUDA(ctx, cudaEventRecord(h->ev1, h->stream));
+    KCUDA(ctx, cudaMemcpyAsync(h->h_res, h->d_res, (size_t)3 * k * h->P * 8, cudaMemcpyDeviceToHost, h->stream));
+    KCUDA(ctx, cudaStreamSynchronize(h->stream));
+    if (iters > 0 && ms_total) KCUDA(ctx, cudaEventElapsedTime(ms_total, h->ev0, h->ev1));
+    if (beta) *beta = h->h_res;
+    if (var) *var = h->h_res + (size_t)k * h->P;
+    if (pval) *pval = h->h_res + (size_t)2 * k * h->P;
+    return PG_OK;
+}
+
+}  // extern "C"

@@ -217,12 +217,6 @@ __device__ __forceinline__ void for_rows_coop(const ScanParams &p, int64_t locus
     }
 }
 
-__device__ __forceinline__ double warp_sum(double v) {  // fixed-order butterfly: every lane gets the same bits
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(PG_FULL_MASK, v, off);
-    return v;
-}
-
 // Full reference pipeline for one locus straight from global memory, executed by the whole warp (lane = pool):
 // exact q with NaN handling, missingness, renormalisation over the kept alleles.  Used when a pool has no coverage
 // or when a removed allele carries reads (both rare).  Leaves the re-accumulated totals in tot[0..N).
@@ -262,7 +256,7 @@ __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const
     });
 #pragma unroll
     for (int i = 0; i < AC::N; i++) {
-        const double v = warp_sum(acc[i]);
+        const double v = warp_sum_fixed(acc[i]);
         if (lane == 0) tot[i] = v;
     }
     __syncwarp();
@@ -369,11 +363,11 @@ __device__ __noinline__ int redo_locus(const ScanParams &p, int64_t locus, unsig
 #pragma unroll
             for (int k = 0; k < K; k++) sy[k] += ys[k * n_pad + i];
         });
-        cntv = warp_sum(cnt);
+        cntv = warp_sum_fixed(cnt);
 #pragma unroll
-        for (int a = 0; a < MS; a++) xbar[a] = warp_sum(sx[a]) / cntv;
+        for (int a = 0; a < MS; a++) xbar[a] = warp_sum_fixed(sx[a]) / cntv;
 #pragma unroll
-        for (int k = 0; k < K; k++) ybar[k] = warp_sum(sy[k]) / cntv;
+        for (int k = 0; k < K; k++) ybar[k] = warp_sum_fixed(sy[k]) / cntv;
     }
     // pass 1: centred moments
     double S[PG_MAX_SLOTS][PG_MAX_SLOTS], sxy[K][PG_MAX_SLOTS], syy[K];
@@ -420,14 +414,14 @@ __device__ __noinline__ int redo_locus(const ScanParams &p, int64_t locus, unsig
 #pragma unroll
         for (int a = 0; a < MS; a++)
 #pragma unroll
-            for (int b = 0; b <= a; b++) S[a][b] = warp_sum(Sa[a * (a + 1) / 2 + b]);
+            for (int b = 0; b <= a; b++) S[a][b] = warp_sum_fixed(Sa[a * (a + 1) / 2 + b]);
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            syy[k] = warp_sum(syya[k]);
+            syy[k] = warp_sum_fixed(syya[k]);
 #pragma unroll
             for (int a = 0; a < PG_MAX_SLOTS; a++) sxy[k][a] = 0.0;
 #pragma unroll
-            for (int a = 0; a < MS; a++) sxy[k][a] = warp_sum(sxya[k][a]);
+            for (int a = 0; a < MS; a++) sxy[k][a] = warp_sum_fixed(sxya[k][a]);
         }
     }
     if (mode != REDO_OLS) {
@@ -472,7 +466,7 @@ __device__ __noinline__ int redo_locus(const ScanParams &p, int64_t locus, unsig
             }
         });
 #pragma unroll
-        for (int k = 0; k < K; k++) rss[k] = warp_sum(ra[k]);
+        for (int k = 0; k < K; k++) rss[k] = warp_sum_fixed(ra[k]);
     }
     if (lane == 0) {
         const double dfe = nn - (double)(m + 1);

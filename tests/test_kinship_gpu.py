@@ -1,0 +1,163 @@
+"""GPU parity tests of the ols_iter_with_kinship path (pg_kin_*): column loader, DMMA Gram matrix, PC selection and
+the covariate scan against the CPU oracle (oracle/pgo.py: load_columns, ols_with_covariate)."""
+import numpy as np
+import pytest
+
+import poolgen_b200 as pb
+from oracle import pgo
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9   # beta, var
+PTOL = 1e-6   # p-values (absolute floor 2.3e-16, tests/helpers.py)
+
+
+def _arbiter(G, cov, phen, c, j):
+    """QR least squares of column c / phenotype j (accurate to cond(X) eps, unlike the normal equations the reference
+    and the oracle invert): (beta, var) of the allele coefficient."""
+    n = G.shape[1]
+    x = np.ones((n, 2 + cov.shape[1]))
+    x[:, 1:1 + cov.shape[1]] = cov
+    x[:, -1] = G[c]
+    q, r = np.linalg.qr(x)
+    b = np.linalg.solve(r, q.T @ phen[:, j])
+    e = phen[:, j] - x @ b
+    rinv = np.linalg.inv(r)
+    return b[-1], (e @ e) / (n - x.shape[1]) * (rinv[-1] @ rinv[-1])
+
+
+def _cmp_records(dev, orc, label, arb=None):
+    """dev / orc: (beta, var, pval) as [k, P].  Entries outside the tolerance are arbitrated: the device
+    passes if it is at least as close to the QR solution as 4x the oracle's own error."""
+    beta, var, pval = dev
+    ob, ov, op = orc
+    assert beta.shape == ob.shape, (beta.shape, ob.shape)
+    nan_o = np.isnan(ob)
+    assert (np.isnan(beta) == nan_o).all(), label
+    ok = ~nan_o
+    se = np.sqrt(np.where(ok, ov, 1.0))
+    bad_b = ok & ~(np.abs(beta - ob) <= RTOL * np.maximum(np.abs(ob), se))
+    bad_v = ok & ~(np.abs(var - ov) <= 4 * RTOL * np.abs(ov))
+    bad_p = ok & ~(np.abs(pval - op) <= PTOL * np.abs(op) + H.P_FLOOR)
+    bad = bad_b | bad_v | bad_p
+    if bad.any():
+        assert arb is not None, (label, int(bad.sum()))
+        G, cov, phen = arb
+        for j, c in zip(*np.nonzero(bad)):
+            xb, xv = _arbiter(G, cov, phen, c, j)
+            eb_o, eb_d = abs(ob[j, c] - xb), abs(beta[j, c] - xb)
+            ev_o, ev_d = abs(ov[j, c] - xv), abs(var[j, c] - xv)
+            assert eb_d <= max(4 * eb_o, RTOL * max(abs(xb), np.sqrt(xv))), (label, j, c, beta[j, c], ob[j, c], xb)
+            assert ev_d <= max(4 * ev_o, 4 * RTOL * abs(xv)), (label, j, c, var[j, c], ov[j, c], xv)
+    return int(bad.sum())
+
+
+@pytest.mark.parametrize("keep_p_minus_1", [False, True])
+@pytest.mark.parametrize("fkw", [dict(), dict(min_coverage_depth=10, min_allele_frequency=0.01),
+                                 dict(min_allele_frequency=0.05)])
+def test_loader_c1_bit_exact(ctx, fkw, keep_p_minus_1):
+    """LoadAll over the reference's tests/test.sync: same columns, same labels, same bits."""
+    c1 = H.load_c1()
+    fs = pb.FilterStats(pool_sizes=c1["pool_sizes"], **fkw)
+    counts = c1["counts"]  # [L, 6, n]
+    L = counts.shape[0]
+    kin = pb.Kinship(ctx, 5, 5 * L)
+    loc, alle = kin.append_counts(counts, c1["codes"], fs, keep_p_minus_1)
+    G = kin.get_columns(0, kin.columns)
+    kin.close()
+    ocols, olabels = pgo.load_columns(counts.transpose(0, 2, 1).astype(np.uint64), c1["codes"], H.oracle_fs(fs),
+                                      keep_p_minus_1)
+    assert len(olabels) == G.shape[0]
+    assert [l for l, _ in olabels] == list(loc)
+    assert [a for _, a in olabels] == list(alle)
+    assert np.array_equal(G, ocols, equal_nan=True)
+
+
+@pytest.mark.parametrize("n,P", [(40, 333), (130, 1000), (257, 64)])
+def test_gram_matches_numpy(ctx, n, P):
+    rng = np.random.default_rng(n * 1000 + P)
+    G = rng.random((P, n))
+    kin = pb.Kinship(ctx, n, P)
+    kin.append_columns(G)
+    kin.gram()
+    K = kin.partial_get()
+    kin.gram()
+    K2 = kin.partial_get()
+    kin.close()
+    ref = G.T @ G
+    assert np.allclose(K, ref, rtol=1e-12, atol=1e-12 * P)
+    assert np.array_equal(K, K.T)
+    assert np.array_equal(K, K2)  # fixed summation order
+
+
+@pytest.mark.parametrize("n,L,k,thr", [(24, 150, 2, 0.75), (60, 200, 1, 0.999), (100, 120, 3, 0.9999)])
+def test_ols_with_covariate_synthetic(ctx, n, L, k, thr):
+    seed = 0x5EED0004 + n
+    counts = pb.synth_counts_host(seed, 0, L, n, 4)
+    codes = np.arange(4, dtype=np.uint8)
+    fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n))
+    phen = pb.synth_phen_host(seed, n, k)
+    kin = pb.Kinship(ctx, n, 4 * L)
+    kin.append_counts(counts, codes, fs)
+    P = kin.columns
+    G = kin.get_columns(0, P)
+    kin.gram()
+    m = kin.eig_select(P, thr)
+    ev = kin.eigvals(n)
+    beta, var, pval = kin.covar_scan(phen)
+    kin.close()
+    om, ob, ov, op = pgo.ols_with_covariate(G, phen, thr)
+    w, V = np.linalg.eigh((G.T @ G) / P)
+    w, V = w[::-1], V[:, ::-1]
+    assert np.allclose(ev, w, rtol=1e-9, atol=1e-12 * w[0])
+    assert m == om
+    n_arb = _cmp_records((beta, var, pval), (ob.T, ov.T, op.T), f"kinship n={n} m={m}", arb=(G, V[:, :m], phen))
+    print(f"kinship n={n} P={P} m={m}: {n_arb} of {P * k} records arbitrated")
+
+
+def test_explicit_covariates_and_c1(ctx):
+    """config C1 columns with two hand-made covariates (no eigen step): the Frisch-Waugh form against the oracle's
+    normal equations for every column."""
+    c1 = H.load_c1()
+    fs = pb.FilterStats(pool_sizes=c1["pool_sizes"], min_coverage_depth=10, min_allele_frequency=0.01)
+    kin = pb.Kinship(ctx, 5, 5 * c1["counts"].shape[0])
+    kin.append_counts(c1["counts"], c1["codes"], fs)
+    P = kin.columns
+    G = kin.get_columns(0, P)
+    cov = np.array([[0.3], [-1.2], [0.8], [2.0], [-0.4]])
+    kin.set_covariates(cov)
+    beta, var, pval = kin.covar_scan(c1["phen"])
+    kin.close()
+    k = c1["phen"].shape[1]
+    ob, ov, op = (np.full((P, k), np.nan) for _ in range(3))
+    for c in range(P):
+        x = np.ones((5, 3))
+        x[:, 1] = cov[:, 0]
+        x[:, 2] = G[c]
+        rc, b, v, p, _ = pgo.ols(x, c1["phen"])
+        if rc == 0:
+            ob[c], ov[c], op[c] = b[2], v[2], p[2]
+    good = ~np.isnan(ob[:, 0]) & (np.abs(ob[:, 0]) < 1e8)
+    assert good.sum() > 0.5 * P
+    _cmp_records((beta[:, good], var[:, good], pval[:, good]), (ob[good].T, ov[good].T, op[good].T), "C1 covariates")
+
+
+def test_partial_sum_equals_whole(ctx):
+    """two column shards: the sum of the partial Gram matrices equals the Gram matrix of the whole (the all-reduce step)"""
+    n, P = 64, 900
+    rng = np.random.default_rng(7)
+    G = rng.random((P, n))
+    whole = pb.Kinship(ctx, n, P)
+    whole.append_columns(G)
+    whole.gram()
+    K = whole.partial_get()
+    whole.close()
+    parts = []
+    for sl in (slice(0, 400), slice(400, P)):
+        kin = pb.Kinship(ctx, n, P)
+        kin.append_columns(G[sl])
+        kin.gram()
+        parts.append(kin.partial_get())
+        kin.close()
+    assert np.allclose(parts[0] + parts[1], K, rtol=1e-13, atol=1e-10)
