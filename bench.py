@@ -227,11 +227,16 @@ def run_cuda(args):
     meta = np.ctypeslib.as_array(rv.meta, shape=(L,))
     ok_frac = float(((meta & 0xFF) == pb.LOCUS_OK).mean())
 
-    extras = {}
-    if rank == 0 and not args.no_extras:
-        extras = c2_numbers(ctx, pb)
     batch.close()
     scan.close()
+    extras = {}
+    if not args.no_extras:
+        if rank == 0:
+            extras = c2_numbers(ctx, pb)
+            extras.update(c5_numbers(ctx, pb))
+        kin = c4_numbers(ctx, pb, dist, rank, world)  # every rank takes part (column shards + all-reduce)
+        if rank == 0:
+            extras.update(kin)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -293,6 +298,78 @@ def c2_numbers(ctx, pb):
         b.close()
         scan.close()
     return out
+
+
+def c5_numbers(ctx, pb):
+    """BASELINE.json configs[4] (C5): chisq_test + fisher_exact_test on 2 pools x L loci of synthetic counts
+    (count path: u32 [locus][allele][pool] in, 2 f64 + status out; 4*n*6 + 16 = 64 algorithmic bytes per locus)."""
+    out = {}
+    n, A, L = 2, 6, 20_000_000
+    fs = pb.FilterStats(pool_sizes=np.full(n, 0.5))
+    peak, _ = measured_peaks()
+    alg = 4 * n * 6 + 16
+    for name, kind in (("c5_chisq_test", pb.KIND_CHISQ), ("c5_fisher_exact_test", pb.KIND_FISHER)):
+        scan = pb.Scan(ctx, kind, fs, n, np.arange(A, dtype=np.uint8))
+        b = scan.batch(L)
+        b.synth(0x5EED0005, 0, L)
+        b.time_runs(3)
+        ms, nl = b.time_runs(5)
+        per = ms / nl
+        out[name] = {"loci_per_s": L / (per * 1e-3), "kernel_ms": per, "loci": L,
+                     "roofline_frac": alg * L / (per * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_locus": alg,
+                     "note": "960 MB of counts per pass > L2 (126 MB); Fisher is compute-bound (O((n a)^2 (n+a)) log10/pow per locus)"}
+        b.close()
+        scan.close()
+    return out
+
+
+FP64_DMMA_PEAK_TFLOPS = 37.1  # tools/fp64_probe.cu on this pool's B200 (profiles/fp64_probe_r1.txt): mma.sync m8n8k4 f64
+
+
+def c4_numbers(ctx, pb, dist, rank, world):
+    """BASELINE.json configs[3] (C4): ols_iter_with_kinship, 2,000 pools x 5M biallelic loci = 10M allele columns
+    (160 GB of f64) column-sharded over 8 GPUs = 1.25M columns (20 GB) per rank: FP64 DMMA Gram matrix, all-reduce of
+    the n x n partials, eigen step, covariate scan."""
+    import torch
+    from poolgen_b200 import shard
+    n, L_rank, k = 2000, 625_000, 1
+    kin = pb.Kinship(ctx, n, 2 * L_rank)
+    kin.synth(0x5EED0004, rank * L_rank, L_rank)
+    P = kin.columns
+    kin.gram_time(1)
+    gram_ms = kin.gram_time(3) / 3
+    t0 = time.perf_counter()
+    shard.allreduce_partial_gram(kin, dist)
+    torch.cuda.synchronize()
+    ar_ms = 1e3 * (time.perf_counter() - t0)
+    P_total = shard.total_columns(P, dist)
+    t0 = time.perf_counter()
+    m = kin.eig_select(P_total, 0.75)
+    eig_ms = 1e3 * (time.perf_counter() - t0)
+    phen = pb.synth_phen_host(0x5EED0004, n, k)
+    kin.covar_scan(phen, 1)
+    *_, covar_ms = kin.covar_scan(phen, 5)
+    covar_ms /= 5
+    kin.close()
+    t = torch.tensor([gram_ms, covar_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gram_ms, covar_ms = (float(v) for v in t.tolist())
+    peak, _ = measured_peaks()
+    nt = (n + 127) // 128
+    hw_flops = 2.0 * (nt * (nt + 1) // 2) * 128 * 128 * P       # the upper triangle of 128 x 128 tiles that is computed
+    alg_flops = 2.0 * n * n * P                                  # what g.dot(&g.t()) does (ols.rs:295)
+    alg_bytes = (8.0 * n + 24 * k) * P
+    return {"c4_kinship": {
+        "columns_per_gpu": P, "n_pools": n, "n_eigenvecs": m,
+        "gram_ms": gram_ms, "gram_algorithmic_tflops_per_gpu": alg_flops / gram_ms / 1e9,
+        "gram_hardware_tflops_per_gpu": hw_flops / gram_ms / 1e9,
+        "gram_frac_of_fp64_tensor_peak": hw_flops / gram_ms / 1e9 / FP64_DMMA_PEAK_TFLOPS,
+        "fp64_tensor_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+        "allreduce_ms": ar_ms if world > 1 else None, "eig_select_ms": eig_ms,
+        "covar_scan_ms": covar_ms, "covar_columns_per_s": world * P / (covar_ms * 1e-3),
+        "covar_roofline_frac": alg_bytes / (covar_ms * 1e-3) / 1e9 / peak,
+        "note": "symmetric Gram: the algorithmic rate counts 2 n^2 P flops, the hardware rate the DMMA work issued"}}
 
 
 def main():
