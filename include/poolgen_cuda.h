@@ -116,6 +116,8 @@ int pg_batch_destroy(pg_batch *b);
 int pg_batch_upload_counts(pg_batch *b, const uint32_t *counts, int64_t n_loci);
 /* same, 16-bit counts (every count < 65536): half the PCIe bytes */
 int pg_batch_upload_counts_u16(pg_batch *b, const uint16_t *counts, int64_t n_loci);
+/* same, 8-bit counts (every count < 256, typical for pool-seq depths below 255): a quarter of the PCIe bytes */
+int pg_batch_upload_counts_u8(pg_batch *b, const uint8_t *counts, int64_t n_loci);
 /* f64 first-stage frequency matrix, column-major n_pools x n_alleles per locus ([locus][allele][pool],
  * N column already removed, NaN where the pool has no coverage) + per-pool depth [locus][pool].
  * OLS / CORR only. */
@@ -141,6 +143,7 @@ int pg_batch_bytes(pg_batch *b, size_t *input_bytes, size_t *result_bytes);
 int pg_scan_stream_begin(pg_scan *scan, int64_t max_loci_per_slab);
 int pg_scan_submit_counts(pg_scan *scan, const uint32_t *counts, int64_t n_loci, int *ticket);
 int pg_scan_submit_counts_u16(pg_scan *scan, const uint16_t *counts, int64_t n_loci, int *ticket);
+int pg_scan_submit_counts_u8(pg_scan *scan, const uint8_t *counts, int64_t n_loci, int *ticket);
 int pg_scan_submit_freq(pg_scan *scan, const double *freq, const uint32_t *depth, int64_t n_loci, int *ticket);
 int pg_scan_collect(pg_scan *scan, int ticket, pg_results *out);
 

@@ -27,10 +27,10 @@ ALLELE_NAMES = "ATCGND"  # sync column order, src/base/sync.rs:134-137
 ABI_SYMBOLS = [
     "pg_abi_version", "pg_init", "pg_destroy", "pg_last_error", "pg_device_info", "pg_pinned_alloc",
     "pg_pinned_free", "pg_scan_open", "pg_scan_close", "pg_batch_create", "pg_batch_destroy",
-    "pg_batch_upload_counts", "pg_batch_upload_counts_u16", "pg_batch_upload_freq", "pg_batch_synth",
+    "pg_batch_upload_counts", "pg_batch_upload_counts_u16", "pg_batch_upload_counts_u8", "pg_batch_upload_freq", "pg_batch_synth",
     "pg_batch_run", "pg_batch_download", "pg_batch_sync", "pg_batch_results", "pg_batch_time_runs",
     "pg_batch_bytes", "pg_scan_stream_begin", "pg_scan_submit_counts", "pg_scan_submit_counts_u16",
-    "pg_scan_submit_freq", "pg_scan_collect", "pg_synth_counts_host", "pg_synth_phen_host",
+    "pg_scan_submit_counts_u8", "pg_scan_submit_freq", "pg_scan_collect", "pg_synth_counts_host", "pg_synth_phen_host",
     "pg_kin_open", "pg_kin_close", "pg_kin_reset", "pg_kin_columns", "pg_kin_append_columns", "pg_kin_append_counts",
     "pg_kin_last_labels", "pg_kin_synth", "pg_kin_get_columns", "pg_kin_gram", "pg_kin_gram_time", "pg_kin_partial",
     "pg_kin_partial_get", "pg_kin_partial_set", "pg_kin_eig_select", "pg_kin_eigvals", "pg_kin_set_covariates",
@@ -91,6 +91,7 @@ def lib():
             "pg_batch_destroy": (i, [vp]),
             "pg_batch_upload_counts": (i, [vp, vp, i64]),
             "pg_batch_upload_counts_u16": (i, [vp, vp, i64]),
+            "pg_batch_upload_counts_u8": (i, [vp, vp, i64]),
             "pg_batch_upload_freq": (i, [vp, vp, vp, i64]),
             "pg_batch_synth": (i, [vp, u64, i64, i64]),
             "pg_batch_run": (i, [vp]),
@@ -102,6 +103,7 @@ def lib():
             "pg_scan_stream_begin": (i, [vp, i64]),
             "pg_scan_submit_counts": (i, [vp, vp, i64, C.POINTER(i)]),
             "pg_scan_submit_counts_u16": (i, [vp, vp, i64, C.POINTER(i)]),
+            "pg_scan_submit_counts_u8": (i, [vp, vp, i64, C.POINTER(i)]),
             "pg_scan_submit_freq": (i, [vp, vp, vp, i64, C.POINTER(i)]),
             "pg_scan_collect": (i, [vp, i, C.POINTER(_Results)]),
             "pg_synth_counts_host": (i, [u64, i64, i64, i, i, vp]),
@@ -258,8 +260,8 @@ class Scan:
         t = C.c_int()
         c = counts
         assert c.flags["C_CONTIGUOUS"]
-        fn = lib().pg_scan_submit_counts if c.dtype == np.uint32 else lib().pg_scan_submit_counts_u16
-        assert c.dtype in (np.uint32, np.uint16)
+        assert c.dtype in (np.uint32, np.uint16, np.uint8)
+        fn = {4: lib().pg_scan_submit_counts, 2: lib().pg_scan_submit_counts_u16, 1: lib().pg_scan_submit_counts_u8}[c.dtype.itemsize]
         _check(fn(self._h, c.ctypes.data, int(c.shape[0]), C.byref(t)), self.ctx._h, "pg_scan_submit_counts")
         return t.value
 
@@ -294,11 +296,11 @@ class Batch:
 
     def upload_counts(self, counts):
         c = np.ascontiguousarray(counts)
-        if c.dtype not in (np.uint32, np.uint16):
+        if c.dtype not in (np.uint32, np.uint16, np.uint8):
             c = c.astype(np.uint32)
         assert c.ndim == 3 and c.shape[1] == self.scan.n_alleles and c.shape[2] == self.scan.n_pools, c.shape
         self._keep = c
-        fn = lib().pg_batch_upload_counts if c.dtype == np.uint32 else lib().pg_batch_upload_counts_u16
+        fn = {4: lib().pg_batch_upload_counts, 2: lib().pg_batch_upload_counts_u16, 1: lib().pg_batch_upload_counts_u8}[c.dtype.itemsize]
         self._ck(fn(self._h, c.ctypes.data, int(c.shape[0])), "pg_batch_upload_counts")
 
     def upload_freq(self, freq, depth):

@@ -346,11 +346,14 @@ static int upload_counts_t(pg_batch *b, const CT *counts, int64_t n_loci) {
         if (sizeof(CT) == 4)
             PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
                                                b->d_freq, b->d_depth, b->d_dmin, b->stream));
+        else if (sizeof(CT) == 1)
+            PG_CUDA(ctx, pg::launch_ingest_u8((const uint8_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
+                                              b->d_freq, b->d_depth, b->d_dmin, b->stream));
         else
             PG_CUDA(ctx, pg::launch_ingest_u16((const uint16_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
                                                b->d_freq, b->d_depth, b->d_dmin, b->stream));
     } else {
-        if (sizeof(CT) == 2) return fail(ctx, PG_ERR_UNSUPPORTED, "16-bit counts are not wired for the table tests yet");
+        if (sizeof(CT) != 4) return fail(ctx, PG_ERR_UNSUPPORTED, "narrow counts are not wired for the table tests yet");
         PG_CUDA(ctx, cudaMemcpyAsync(b->d_stage, counts, bytes, cudaMemcpyHostToDevice, b->stream));
     }
     b->input_is_counts = 1;
@@ -364,6 +367,9 @@ int pg_batch_upload_counts(pg_batch *b, const uint32_t *counts, int64_t n_loci) 
 }
 int pg_batch_upload_counts_u16(pg_batch *b, const uint16_t *counts, int64_t n_loci) {
     return upload_counts_t<uint16_t>(b, counts, n_loci);
+}
+int pg_batch_upload_counts_u8(pg_batch *b, const uint8_t *counts, int64_t n_loci) {
+    return upload_counts_t<uint8_t>(b, counts, n_loci);
 }
 
 int pg_batch_upload_freq(pg_batch *b, const double *freq, const uint32_t *depth, int64_t n_loci) {
@@ -613,6 +619,14 @@ int pg_scan_submit_counts_u16(pg_scan *s, const uint16_t *counts, int64_t n_loci
     int rc = submit_common(s, ticket, &b);
     if (rc) return rc;
     if ((rc = pg_batch_upload_counts_u16(b, counts, n_loci))) return rc;
+    if ((rc = pg_batch_run(b))) return rc;
+    return pg_batch_download(b);
+}
+int pg_scan_submit_counts_u8(pg_scan *s, const uint8_t *counts, int64_t n_loci, int *ticket) {
+    pg_batch *b = nullptr;
+    int rc = submit_common(s, ticket, &b);
+    if (rc) return rc;
+    if ((rc = pg_batch_upload_counts_u8(b, counts, n_loci))) return rc;
     if ((rc = pg_batch_run(b))) return rc;
     return pg_batch_download(b);
 }

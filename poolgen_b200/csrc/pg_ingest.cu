@@ -106,6 +106,15 @@ cudaError_t launch_ingest_u16(const uint16_t *counts, int64_t n_loci, int n, int
                                                                                lay, freq, depth, dmin);
     return cudaGetLastError();
 }
+cudaError_t launch_ingest_u8(const uint8_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
+                             const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s) {
+    if (n_loci <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(dmin, 0xFF, (size_t)n_loci * 4, s);
+    if (e != cudaSuccess) return e;
+    ingest_counts_kernel<uint8_t><<<grid_for(n_loci * lay.n_pad), 256, 0, s>>>(counts, n_loci, n, A_in, drop_col,
+                                                                              lay, freq, depth, dmin);
+    return cudaGetLastError();
+}
 cudaError_t launch_ingest_freq(const double *fin, const uint32_t *din, int64_t n_loci, int n, const Layout &lay,
                                double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s) {
     if (n_loci <= 0) return cudaSuccess;

@@ -117,6 +117,8 @@ cudaError_t launch_ingest_u32(const uint32_t *counts, int64_t n_loci, int n, int
                               const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s);
 cudaError_t launch_ingest_u16(const uint16_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
                               const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s);
+cudaError_t launch_ingest_u8(const uint8_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
+                             const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s);
 cudaError_t launch_ingest_freq(const double *freq_in, const uint32_t *depth_in, int64_t n_loci, int n,
                                const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s);
 cudaError_t launch_synth(uint64_t seed, int64_t first_locus, int64_t n_loci, int n, int A_in,

@@ -103,7 +103,7 @@ def test_device_generator_matches_host(ctx):
 
 
 def test_upload_formats_agree(ctx):
-    """u32 counts, u16 counts and the host-built f64 frequency matrix give identical records."""
+    """u32, u16 and u8 counts and the host-built f64 frequency matrix give identical records."""
     n, A, k, L = 100, 4, 2, 3000
     seed = 77
     counts = pb.synth_counts_host(seed, 0, L, n, A)
@@ -117,6 +117,10 @@ def test_upload_formats_agree(ctx):
     b.upload_counts(counts.astype(np.uint16))
     b.run()
     r16 = b.fetch()
+    assert counts.max() < 256
+    b.upload_counts(counts.astype(np.uint8))
+    b.run()
+    r8 = b.fetch()
     depth = counts.sum(axis=1).astype(np.uint32)
     with np.errstate(invalid="ignore", divide="ignore"):
         freq = counts.astype(np.float64) / depth[:, None, :].astype(np.float64)
@@ -125,7 +129,7 @@ def test_upload_formats_agree(ctx):
     rf = b.fetch()
     b.close()
     scan.close()
-    for r in (r16, rf):
+    for r in (r16, r8, rf):
         assert (r.status == r32.status).all()
         assert np.array_equal(r.stats, r32.stats, equal_nan=True)
         assert np.array_equal(r.freq_mean, r32.freq_mean, equal_nan=True)
