@@ -263,7 +263,7 @@ int pg_scan_close(pg_scan *s) {
 static bool is_regression(const pg_scan *s) { return s->kind == PG_KIND_OLS || s->kind == PG_KIND_CORR; }
 
 int pg_batch_create(pg_scan *s, int64_t cap, pg_batch **out) {
-    if (!s || !out || cap < 1) return fail(s ? s->ctx : nullptr, PG_ERR_ARG, "pg_batch_create: bad argument");
+    if (!s || !out || cap < 1 || cap > 0x7FFFFFFFLL) return fail(s ? s->ctx : nullptr, PG_ERR_ARG, "pg_batch_create: bad argument (1 <= capacity < 2^31 loci)");
     pg_ctx *ctx = s->ctx;
     *out = nullptr;
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -278,6 +278,7 @@ int pg_batch_create(pg_scan *s, int64_t cap, pg_batch **out) {
         e = cudaMalloc(&b->d_freq, (size_t)cap * s->lay.freq_stride() * 8);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_depth, (size_t)cap * s->lay.depth_stride() * 4);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_dmin, (size_t)cap * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_defer, (size_t)(cap + 1) * 8);
     }
     const size_t S = s->n_slots, K = s->k;
     if (e == cudaSuccess) e = cudaMalloc(&b->d_meta, (size_t)cap * 8);
@@ -297,6 +298,7 @@ int pg_batch_destroy(pg_batch *b) {
     cudaFree(b->d_freq);
     cudaFree(b->d_depth);
     cudaFree(b->d_dmin);
+    cudaFree(b->d_defer);
     cudaFree(b->d_stage);
     cudaFree(b->d_meta);
     cudaFree(b->d_fmean);
@@ -445,6 +447,7 @@ static int run_once(pg_batch *b, int *launches) {
         static const int nbuf_env = getenv("PG_NBUF") ? atoi(getenv("PG_NBUF")) : 0;
         static const int warps_env = getenv("PG_WARPS") ? atoi(getenv("PG_WARPS")) : 0;
         static const int g_env = getenv("PG_G") ? atoi(getenv("PG_G")) : 0;
+        static const int p_env = getenv("PG_P") ? atoi(getenv("PG_P")) : 0;
         for (int base = 0; base < s->k; base += kpass) {
             pg::ScanParams p;
             memset(&p, 0, sizeof p);
@@ -477,14 +480,17 @@ static int run_once(pg_batch *b, int *launches) {
             p.meta = b->d_meta;
             p.freq_mean = b->d_fmean;
             p.stats = b->d_stats;
+            p.defer_list = b->d_defer;
+            p.defer_count = reinterpret_cast<uint32_t *>(b->d_defer + b->cap);
             p.k_total = s->k;
             p.phen_base = base;
             p.write_meta = base == 0;
             p.nbuf_override = nbuf_env;
             p.warps_override = warps_env;
             p.g_override = g_env;
+            p.p_override = p_env;
             PG_CUDA(ctx, pg::launch_scan(p, ctx->sm_count, b->stream));
-            if (launches) (*launches)++;
+            if (launches) (*launches) += 2;  // streaming kernel + fix-up kernel
         }
     } else {
         pg::TableParams p;

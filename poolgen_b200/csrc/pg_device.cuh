@@ -121,7 +121,7 @@ __device__ __forceinline__ double beta_reg_dev(double a, double b, double x, dou
 
 // two-sided p-value exactly as the reference forms it: 2 * (1 - StudentsT(0,1,df).cdf(|t|))
 // (src/gwas/ols.rs:153, src/gwas/correlation_test.rs:66) including the cancellation 1 - (1 - ib).
-__device__ __forceinline__ double student_two_sided(double t_abs, double df, double ln_beta) {
+static __device__ __noinline__ double student_two_sided(double t_abs, double df, double ln_beta) {
     if (isinf(df)) return 2.0 * (1.0 - 0.5 * erfc(-t_abs / sqrt(2.0)));
     const double h = df / (df + t_abs * t_abs);
     const double ib = 0.5 * beta_reg_dev(df / 2.0, 0.5, h, ln_beta);

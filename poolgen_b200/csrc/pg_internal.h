@@ -89,12 +89,14 @@ struct ScanParams {
     uint64_t *meta;
     double *freq_mean;
     double *stats;
+    uint64_t *defer_list;   // [n_loci] loci left to the fix-up kernel: locus | kept set << 40 (0 = undecided)
+    uint32_t *defer_count;  // [1]
     int k_total, phen_base, K;  // output indexing when k > kMaxPhenPerPass
     int write_meta;             // only the first phenotype pass writes meta / freq_mean
     // launch geometry, filled in by the launcher
     uint32_t common_bytes, warp_bytes, stage_bytes;
     int nbuf, block_loci;
-    int nbuf_override, warps_override, g_override;  // tuning knobs (PG_NBUF / PG_WARPS / PG_G), 0 = automatic
+    int nbuf_override, warps_override, g_override, p_override;  // tuning knobs (PG_NBUF / PG_WARPS / PG_G), 0 = automatic
 };
 
 struct TableParams {
@@ -231,6 +233,7 @@ struct pg_batch {
     double *d_freq = nullptr;
     uint32_t *d_depth = nullptr;
     uint32_t *d_dmin = nullptr;
+    uint64_t *d_defer = nullptr;  // [cap + 1]: list then its counter
     void *d_stage = nullptr;  // raw uploaded slab (counts u32/u16 or unpadded freq+depth)
     size_t stage_bytes = 0;
     uint64_t *d_meta = nullptr;

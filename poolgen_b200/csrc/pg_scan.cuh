@@ -156,6 +156,22 @@ __device__ __forceinline__ void renorm_row(const double (&f)[A], uint32_t d, uns
     }
 }
 
+// the same with one division per row (c_ij * (1 / sum_kept c_i.)): within 1.5 ulp of the reference's quotient, used
+// where only the regression sums are formed (every order- or threshold-sensitive decision has its own exact path)
+template <int A>
+__device__ __forceinline__ void renorm_row_fast(const double (&f)[A], uint32_t d, unsigned kept, double (&F)[A]) {
+    double c[A];
+    double dk = 0.0;
+#pragma unroll
+    for (int j = 0; j < A; j++) {
+        c[j] = (d == 0u) ? 0.0 : rint(f[j] * (double)d);
+        if ((kept >> j) & 1u) dk += c[j];
+    }
+    const double inv = (dk == 0.0) ? nan("") : 1.0 / dk;
+#pragma unroll
+    for (int j = 0; j < A; j++) F[j] = ((kept >> j) & 1u) ? c[j] * inv : 0.0;
+}
+
 // column sum of the renormalised frequencies in pool order, NaN ignored (src/base/sync.rs:483-489)
 template <int A>
 __device__ __noinline__ double exact_colsum(const ScanParams &p, int64_t locus, int jsel, unsigned kept) {
@@ -249,7 +265,7 @@ __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const
     const int n_pad = lay.n_pad;
     for_rows_coop<A>(p, locus, lane, [&](int i, const double(&f)[A], uint32_t d) {
         double F[A], y[K];
-        renorm_row<A>(f, d, kept, F);
+        renorm_row_fast<A>(f, d, kept, F);
 #pragma unroll
         for (int k = 0; k < K; k++) y[k] = ys[k * n_pad + i];
         accum_row<A, K, W, true>(acc, F, y, 0.0);
@@ -319,7 +335,7 @@ __device__ __forceinline__ double solve_rhs(int m, const double (&Li)[PG_MAX_SLO
 
 __device__ __forceinline__ int slot_col(unsigned cb, int s) { return (int)((cb >> (4 * s)) & 0xfu); }
 
-enum { REDO_NONE = 0, REDO_OLS = 1, REDO_CORR = 2, REDO_CORR_NAN = 3 };
+enum { REDO_NONE = 0, REDO_OLS = 1, REDO_CORR = 2, REDO_CORR_NAN = 3, REDO_DEFER = 4 };
 
 // Reference-style two-pass evaluation of one locus straight from global memory by the whole warp (lane = pool):
 // explicit centred moments and explicit residuals e = y - Xb as src/gwas/ols.rs:98-104.  Used when the single-pass
@@ -583,7 +599,7 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsi
 // ---- phase 2b (one lane per locus): allele order and the single-pass solve, everything in registers ------------
 // in: the totals row tg of the locus.  out: m (rows), cb (allele column of each row, 4 bits per slot), redo (REDO_*)
 // and, in place of the totals, tg[(s*K+k)*2 + {0,1}] = (beta | r, var) and tg[2(A-1)K + s] = mean frequency.
-template <int A, int K, bool W>
+template <int A, int K, bool W, bool DEFER>
 __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, double *tg, int &status, unsigned kept,
                                          int &m, unsigned &cb, int &redo_mode) {
     using AC = Acc<A, K, W>;
@@ -611,6 +627,10 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
                     fabs(cs[j] - cs[l]) <= tol_rel * fmax(fabs(cs[j]), fabs(cs[l])))
                     tie = true;
         if (tie) {
+            if (DEFER) {  // the streaming kernel leaves exact evaluations to the fix-up kernel
+                redo_mode = REDO_DEFER;
+                return;
+            }
 #pragma unroll
             for (int j = 0; j < A; j++)
                 if ((kept >> j) & 1u) cs[j] = exact_colsum<A>(p, locus, j, kept);
@@ -817,14 +837,19 @@ __device__ __noinline__ void write_records(const ScanParams &p, const PTableDev 
     }
 }
 
-// ---- phase 2 (lane = locus of the block): keep-mask from the totals, cooperative exact / slow paths, records ----
-template <int A, int K, bool W>
-__device__ __noinline__ void epilogue(const ScanParams &p, int64_t l0, int cnt, double *tot, const double *ys,
-                                      const double *ws, int lane, unsigned dm) {
+// ---- phase 2 (lane = locus of the block): keep-mask from the totals, solve, records -----------------------------
+// DEFER = true (the streaming kernel): loci that need an exact re-evaluation (a threshold hit within rounding, tied
+// column sums), the renormalised frequencies (a removed allele carries reads, a pool has no coverage) or the two-pass
+// form are appended to the batch's fix-up list and left to fixup_kernel -- none of that code is linked into the
+// streaming kernel, whose instruction footprint has to stay inside the instruction cache.
+// DEFER = false (the fix-up kernel): the whole warp works on those paths.
+// locus / act / dm are per lane; pre_kept != 0 (fix-up kernel only) says that the row already holds the totals of the
+// renormalised frequencies over that kept set.
+template <int A, int K, bool W, bool DEFER>
+__device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool act, double *tot, const double *ys,
+                                      const double *ws, int lane, unsigned dm, unsigned pre_kept) {
     using AC = Acc<A, K, W>;
     const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
-    const bool act = lane < cnt;
-    const int64_t locus = l0 + lane;
     double *tg = tot + (size_t)lane * AC::NP;
     const double tol_rel = 2.0 * ((double)p.lay.n + 8.0) * kEps;
     int status = PG_LOCUS_FILTERED;
@@ -833,7 +858,10 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t l0, int cnt, 
     double q[A];
 #pragma unroll
     for (int j = 0; j < A; j++) q[j] = 0.0;
-    if (act) {
+    if (act && pre_kept) {
+        status = PG_LOCUS_OK;
+        kept = pre_kept;
+    } else if (act) {
         if ((double)dm < p.min_depth_f) {
             status = PG_LOCUS_FILTERED;  // sync.rs:217-229
         } else if (dm == 0u) {
@@ -849,21 +877,27 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t l0, int cnt, 
             }
         }
     }
-    // thresholds hit within rounding: lane j re-evaluates q_j of that locus in the reference's order
-    unsigned need = __ballot_sync(PG_FULL_MASK, exact_bits != 0u);
-    while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const unsigned bits = __shfl_sync(PG_FULL_MASK, exact_bits, src);
-        double qe = 0.0;
-        if (lane < A && ((bits >> lane) & 1u)) qe = exact_q(p, l0 + src, lane, ws);
+    bool deferred = false;
+    if (DEFER) {
+        if (exact_bits != 0u) deferred = true;
+    } else {
+        // thresholds hit within rounding: lane j re-evaluates q_j of that locus in the reference's order
+        unsigned need = __ballot_sync(PG_FULL_MASK, exact_bits != 0u);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const unsigned bits = __shfl_sync(PG_FULL_MASK, exact_bits, src);
+            const int64_t lsrc = __shfl_sync(PG_FULL_MASK, locus, src);
+            double qe = 0.0;
+            if (lane < A && ((bits >> lane) & 1u)) qe = exact_q(p, lsrc, lane, ws);
 #pragma unroll
-        for (int j = 0; j < A; j++) {
-            const double v = __shfl_sync(PG_FULL_MASK, qe, j);
-            if (lane == src && ((bits >> j) & 1u)) q[j] = v;
+            for (int j = 0; j < A; j++) {
+                const double v = __shfl_sync(PG_FULL_MASK, qe, j);
+                if (lane == src && ((bits >> j) & 1u)) q[j] = v;
+            }
         }
     }
-    if (act && status == PG_LOCUS_OK && !slow) {
+    if (act && status == PG_LOCUS_OK && !slow && !deferred && !pre_kept) {
 #pragma unroll
         for (int j = 0; j < A; j++)
             if (!((q[j] < p.maf) | (q[j] > p.one_minus_maf))) kept |= 1u << j;
@@ -875,38 +909,119 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t l0, int cnt, 
                 if (!((kept >> j) & 1u) && tg[AC::S0 + j] > 0.0) slow = true;  // a removed allele carries reads
         }
     }
-    need = __ballot_sync(PG_FULL_MASK, act && slow && status == PG_LOCUS_OK);
-    while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const bool dec = __shfl_sync(PG_FULL_MASK, (int)slow_decide, src) != 0;
-        unsigned kk = __shfl_sync(PG_FULL_MASK, kept, src);
-        const int st = slow_locus<A, K, W>(p, l0 + src, ys, ws, tot + (size_t)src * AC::NP, lane, dec, kk);
-        if (lane == src) {
-            status = st;
-            kept = kk;
+    bool kept_known = false;
+    if (DEFER) {
+        if (act && slow && status == PG_LOCUS_OK) {
+            kept_known = !deferred && !slow_decide;  // the fix-up kernel can renormalise right away
+            deferred = true;
         }
+    } else {
+        unsigned need = __ballot_sync(PG_FULL_MASK, act && slow && status == PG_LOCUS_OK);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const bool dec = __shfl_sync(PG_FULL_MASK, (int)slow_decide, src) != 0;
+            unsigned kk = __shfl_sync(PG_FULL_MASK, kept, src);
+            const int64_t lsrc = __shfl_sync(PG_FULL_MASK, locus, src);
+            const int st = slow_locus<A, K, W>(p, lsrc, ys, ws, tot + (size_t)src * AC::NP, lane, dec, kk);
+            if (lane == src) {
+                status = st;
+                kept = kk;
+            }
+        }
+        __syncwarp();
     }
-    __syncwarp();
     int m = 0, redo_mode = REDO_NONE;
     unsigned cb = 0;
-    if (act && status == PG_LOCUS_OK) solve_locus<A, K, W>(p, locus, tg, status, kept, m, cb, redo_mode);
-    // loci whose single-pass form is not trustworthy: explicit two-pass evaluation by the whole warp
-    need = __ballot_sync(PG_FULL_MASK, redo_mode != REDO_NONE);
-    while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const int md = __shfl_sync(PG_FULL_MASK, redo_mode, src);
-        const unsigned kk = __shfl_sync(PG_FULL_MASK, kept, src);
-        const int mm = __shfl_sync(PG_FULL_MASK, m, src);
-        const unsigned cc = __shfl_sync(PG_FULL_MASK, cb, src);
+    if (act && status == PG_LOCUS_OK && !deferred)
+        solve_locus<A, K, W, DEFER>(p, locus, tg, status, kept, m, cb, redo_mode);
+    if (DEFER) {
+        if (redo_mode != REDO_NONE) deferred = true;
+        if (deferred)
+            p.defer_list[atomicAdd(p.defer_count, 1u)] = (uint64_t)locus | (kept_known ? ((uint64_t)kept << 40) : 0ull);
+    } else {
+        // loci whose single-pass form is not trustworthy: explicit two-pass evaluation by the whole warp
+        unsigned need = __ballot_sync(PG_FULL_MASK, redo_mode != REDO_NONE);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int md = __shfl_sync(PG_FULL_MASK, redo_mode, src);
+            const unsigned kk = __shfl_sync(PG_FULL_MASK, kept, src);
+            const int mm = __shfl_sync(PG_FULL_MASK, m, src);
+            const unsigned cc = __shfl_sync(PG_FULL_MASK, cb, src);
+            const int64_t lsrc = __shfl_sync(PG_FULL_MASK, locus, src);
+            __syncwarp();
+            const int st = redo_locus<A, K>(p, lsrc, kk, mm, cc, md, ys, tot + (size_t)src * AC::NP, lane);
+            if (lane == src) status = st;
+        }
         __syncwarp();
-        const int st = redo_locus<A, K>(p, l0 + src, kk, mm, cc, md, ys, tot + (size_t)src * AC::NP, lane);
-        if (lane == src) status = st;
     }
+    if (act && !deferred) write_records<A, K>(p, ptab, locus, status, m, cb, tg);
     __syncwarp();
-    if (act) write_records<A, K>(p, ptab, locus, status, m, cb, tg);
-    __syncwarp();
+}
+
+// ---- the fix-up kernel: a warp takes 32 deferred loci, accumulates each straight from global memory (lane = pool:
+// the renormalised frequencies when the kept set is already known, else the first-stage frequencies like phase 1) and
+// runs the full phase 2 with lane = locus -----------------------------------------------------------------------
+constexpr int kFixWarps = 8;
+
+template <int A, int K, bool W>
+__global__ void __launch_bounds__(kFixWarps * 32) fixup_kernel(const __grid_constant__ ScanParams p) {
+    using AC = Acc<A, K, W>;
+    extern __shared__ __align__(16) unsigned char fsm[];  // totals [2][32][NP]: accumulate block i+1 during phase 2 of i
+    __shared__ __align__(16) ScanParams sp_storage;
+    for (int i = threadIdx.x; i < (int)(sizeof(ScanParams) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t *>(&sp_storage)[i] = reinterpret_cast<const uint32_t *>(&p)[i];
+    __syncthreads();
+    const ScanParams &sp = sp_storage;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t count = *p.defer_count;
+    const int n_pad = p.lay.n_pad;
+    const double *ys = p.yc;  // the slow paths index [k * n_pad + pool]: global memory serves as well as shared
+    const double *ws = W ? p.w : nullptr;
+    const uint32_t n_blocks = (count + 31) / 32;
+    int it = 0;
+    for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
+        double *tot = reinterpret_cast<double *>(fsm) + (size_t)(it & 1) * 32 * AC::NP;
+        const uint32_t e0 = blk * 32;
+        const int cnt = (int)min(32u, count - e0);
+        for (int g = warp; g < cnt; g += kFixWarps) {  // the loci of the block are dealt over the warps
+            const uint64_t e = p.defer_list[e0 + g];
+            const int64_t locus = (int64_t)(e & 0xFFFFFFFFFFull);
+            const unsigned kept = (unsigned)(e >> 40) & 0x3fu;
+            double acc[AC::N];
+#pragma unroll
+            for (int a = 0; a < AC::N; a++) acc[a] = 0.0;
+            if (kept) {
+                for_rows_coop<A>(sp, locus, lane, [&](int r, const double(&f)[A], uint32_t d) {
+                    double F[A], y[K];
+                    renorm_row_fast<A>(f, d, kept, F);
+#pragma unroll
+                    for (int k = 0; k < K; k++) y[k] = ys[k * n_pad + r];
+                    accum_row<A, K, W, true>(acc, F, y, 0.0);
+                });
+            } else {
+                for_rows_coop<A>(sp, locus, lane, [&](int r, const double(&f)[A], uint32_t) {
+                    double y[K];
+#pragma unroll
+                    for (int k = 0; k < K; k++) y[k] = ys[k * n_pad + r];
+                    accum_row<A, K, W, false>(acc, f, y, W ? ws[r] : 0.0);
+                });
+            }
+#pragma unroll
+            for (int a = 0; a < AC::N; a++) {
+                const double v = warp_sum_fixed(acc[a]);
+                if (lane == 0) tot[(size_t)g * AC::NP + a] = v;
+            }
+        }
+        __syncthreads();  // the block's rows are complete; phase 2 of the block two back (same buffer) has finished
+        if (warp == (it % kFixWarps)) {
+            const uint64_t mine = (lane < cnt) ? p.defer_list[e0 + lane] : 0ull;
+            const int64_t locus = (int64_t)(mine & 0xFFFFFFFFFFull);
+            const unsigned dm = (lane < cnt) ? __ldg(p.dmin + locus) : 0xFFFFFFFFu;
+            epilogue<A, K, W, false>(sp, locus, lane < cnt, tot, ys, ws, lane, dm, (unsigned)(mine >> 40) & 0x3fu);
+        }
+    }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
@@ -1082,7 +1197,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const __grid_c
                 }
             }
         }
-        epilogue<A, K, W>(sp, l0, cnt, tot, ys, ws, lane, dm);
+        epilogue<A, K, W, true>(sp, l0 + lane, lane < cnt, tot, ys, ws, lane, dm, 0u);
     }
 }
 
@@ -1136,13 +1251,28 @@ cudaError_t launch_scan_p(ScanParams p, int sm_count, cudaStream_t s) {
     int64_t ctas = (NB + nwarps - 1) / nwarps;
     if (ctas > sm_count) ctas = sm_count;
     if (ctas < 1) ctas = 1;
+    e = cudaMemsetAsync(p.defer_count, 0, 4, s);
+    if (e != cudaSuccess) return e;
     kern<<<(unsigned)ctas, nwarps * 32, smem, s>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // deferred loci (count read on the device; an empty list costs one tiny launch)
+    auto fix = fixup_kernel<A, K, W>;
+    const size_t fsmem = (size_t)2 * 32 * AC::NP * 8;
+    e = cudaFuncSetAttribute(fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    if (e != cudaSuccess) return e;
+    fix<<<sm_count * 8, kFixWarps * 32, fsmem, s>>>(p);
     return cudaGetLastError();
 }
 
 template <int A, int K, bool W>
 cudaError_t launch_scan_t(const ScanParams &p, int sm_count, cudaStream_t s) {
-    if (p.lay.n_chunks == 1) return launch_scan_p<A, K, W, 8>(p, sm_count, s);
+    if (p.lay.n_chunks == 1) {
+        // 16 lanes per locus keep the stage at two loci (more resident warps); tiny pool counts use 8
+        const int P = p.p_override ? p.p_override : (p.lay.n_pad > 64 ? 16 : 8);
+        if (P == 16) return launch_scan_p<A, K, W, 16>(p, sm_count, s);
+        return launch_scan_p<A, K, W, 8>(p, sm_count, s);
+    }
     return launch_scan_p<A, K, W, 32>(p, sm_count, s);
 }
 

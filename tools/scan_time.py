@@ -17,7 +17,7 @@ b = scan.batch(L)
 b.synth(0x5EED0003, 0, L)
 b.time_runs(3)
 ms, nl = b.time_runs(iters)
-per = ms / nl
+per = ms / iters  # one run = the streaming kernel + the fix-up kernel
 alg = 8 * n * A + 32 * (A - 1) * k
 print(f"n={n} A={A} k={k} L={L} kind={kind} NBUF={os.environ.get('PG_NBUF','-')} WARPS={os.environ.get('PG_WARPS','-')}: "
       f"{per:.3f} ms  {L / per / 1e3:.1f} Mloci/s  {alg * L / per / 1e6:.0f} GB/s alg  frac {alg * L / per / 1e6 / 6551.4:.3f}")
