@@ -220,3 +220,101 @@ def test_full_size_c2_properties(ctx):
     assert 0.04 < frac < 0.12, frac
     b.close()
     scan.close()
+
+
+MORE_SHAPES = [
+    # n_pools, n_alleles, k, loci, weighted
+    (300, 3, 2, 1500, False),    # A=3: chunks of 192 pools, two chunks
+    (600, 2, 1, 1500, True),     # A=2: chunks of 256 pools, three chunks, unequal pool sizes
+    (1000, 6, 3, 400, True),     # N dropped on the device -> 5 columns, 3 phenotypes in one pass, weighted, 8 chunks
+    (130, 4, 4, 1500, False),    # one row pair past a chunk boundary, 4 phenotypes
+    (20, 4, 2, 4000, False),     # 8 lanes per locus (tiny pool count)
+    (128, 4, 1, 3000, False),    # exactly one chunk, 16 lanes per locus
+]
+
+
+@pytest.mark.parametrize("n,A,k,L,weighted", MORE_SHAPES)
+@pytest.mark.parametrize("kind", [pb.KIND_OLS, pb.KIND_CORR])
+def test_more_shapes(ctx, kind, n, A, k, L, weighted):
+    seed = 0xABCD0000 + n * 11 + A
+    counts = pb.synth_counts_host(seed, 0, L, n, A)
+    phen = pb.synth_phen_host(seed, n, k)
+    ps = (10.0 + (np.arange(n) % 7)) if weighted else np.ones(n)
+    tot = 0.0
+    for v in ps:
+        tot = tot + v
+    fs = _fs(np.array([v / tot for v in ps]))
+    codes = np.arange(A, dtype=np.uint8)
+    scan = pb.Scan(ctx, kind, fs, n, codes, phen)
+    dev = scan.run_counts(counts)
+    scan.close()
+    print(H.compare_regression(kind, counts, codes, phen, fs, dev, label=f"more n={n} A={A} k={k}"))
+
+
+@pytest.mark.parametrize("n,L", [(100, 6000), (1000, 600)])
+@pytest.mark.parametrize("kind", [pb.KIND_OLS, pb.KIND_CORR])
+def test_error_reads_defer_most_loci(ctx, kind, n, L):
+    """real pool-seq data: stray reads on a third / fourth allele in a few pools.  Those alleles fail the MAF filter
+    but carry reads, so nearly every locus takes the renormalising fix-up path."""
+    seed = 0xE44 + n
+    counts = pb.synth_counts_host(seed, 0, L, n, 2)  # biallelic A/T
+    full = np.zeros((L, 5, n), dtype=np.uint32)       # A T C G D
+    full[:, :2] = counts
+    rng = np.random.default_rng(seed)
+    for col in (2, 3, 4):
+        hit = rng.random((L, n)) < (0.02 if col < 4 else 0.005)
+        full[:, col] = hit.astype(np.uint32)
+    phen = pb.synth_phen_host(seed, n, 2)
+    fs = _fs(np.full(n, 1.0 / n), min_allele_frequency=0.001)
+    codes = np.array([0, 1, 2, 3, 5], dtype=np.uint8)
+    scan = pb.Scan(ctx, kind, fs, n, codes, phen)
+    dev = scan.run_counts(full)
+    scan.close()
+    st = H.compare_regression(kind, full, codes, phen, fs, dev, label=f"error reads n={n}")
+    assert st["ok"] > 0.8 * L
+    print(st)
+
+
+def test_missing_coverage_at_scale(ctx):
+    """--min-coverage-depth 0 with pools without coverage at 300 pools: NaN frequencies, exact q, missingness"""
+    n, A, k, L = 300, 4, 2, 1500
+    seed = 0x5EED0303
+    counts = pb.synth_counts_host(seed, 0, L, n, A)   # 2 % of the loci have a pool at depth 0
+    phen = pb.synth_phen_host(seed, n, k)
+    fs = _fs(np.full(n, 1.0 / n), min_coverage_depth=0, max_missingness_rate=0.25)
+    codes = np.arange(A, dtype=np.uint8)
+    for kind in (pb.KIND_OLS, pb.KIND_CORR):
+        scan = pb.Scan(ctx, kind, fs, n, codes, phen)
+        dev = scan.run_counts(counts)
+        scan.close()
+        print(H.compare_regression(kind, counts, codes, phen, fs, dev, label="missing coverage"))
+
+
+def test_full_size_c3_shard_properties(ctx):
+    """C3 shape at 300,000 loci (10 GB resident): sampled windows against the oracle and split invariance."""
+    n, A, k, L = 1000, 4, 3, 300_000
+    seed = 0x5EED0003
+    phen = pb.synth_phen_host(seed, n, k)
+    fs = _fs(np.full(n, 1.0 / n))
+    codes = np.arange(A, dtype=np.uint8)
+    scan = pb.Scan(ctx, pb.KIND_OLS, fs, n, codes, phen)
+    b = scan.batch(L)
+    b.synth(seed, 0, L)
+    b.run()
+    whole = b.fetch()
+    for l0 in (0, 123_456, L - 384):
+        counts = pb.synth_counts_host(seed, l0, 384, n, A)
+        sub = pb.ScanResults(whole.status[l0:l0 + 384], whole.n_out[l0:l0 + 384], whole.alleles[l0:l0 + 384],
+                             whole.freq_mean[l0:l0 + 384], whole.stats[l0:l0 + 384])
+        H.compare_regression(pb.KIND_OLS, counts, codes, phen, fs, sub, label=f"C3 window {l0}")
+    third = L // 3
+    b.synth(seed, third, third)
+    b.run()
+    part = b.fetch()
+    assert (part.status == whole.status[third:2 * third]).all()
+    assert np.array_equal(part.stats, whole.stats[third:2 * third], equal_nan=True)
+    assert np.array_equal(part.freq_mean, whole.freq_mean[third:2 * third], equal_nan=True)
+    frac = (whole.status == pb.LOCUS_FILTERED).mean()
+    assert 0.04 < frac < 0.12, frac
+    b.close()
+    scan.close()
