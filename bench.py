@@ -127,7 +127,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     n_threads = os.cpu_count() or 1
-    step, sample = cpu_reference_rate(4.0, n_threads)
+    step, sample = cpu_reference_rate(args.cpu_seconds, n_threads)
     for _ in range(args.warmup):
         step()
     times = [step() for _ in range(args.steps)]
@@ -137,8 +137,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3 ols_iter: {N_POOLS} pools x 4 alleles x {N_PHEN} phenotypes; CPU arm times a "
-                               f"bounded sample of {sample} loci per step (in-memory counts, parsing and CSV excluded)"},
+        "config": {"workload": f"C3 ols_iter shard: {N_POOLS} pools x {LOCI_PER_GPU} loci/GPU x {N_ALLELES} alleles, "
+                               f"{N_PHEN} phenotypes (8 GPUs = the 10M-locus job)",
+                   "reference_arm": f"the CPU path times a bounded sample of {sample} loci of that workload per step "
+                                    "(in-memory counts, parsing and CSV writing excluded) and scales linearly in loci",
+                   "filters": "CLI defaults: min depth 1, MAF 0.001, missingness 0"},
         "cpu_baseline": {"value": value, "unit": "loci/s", "cores": n_threads, "kind": "port",
                          "sample": f"{sample} loci of the C3 shape per step, {n_threads} OS threads over contiguous locus ranges"},
         "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -397,6 +400,7 @@ def main():
     ap.add_argument("--e2e-slabs", type=int, default=24)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--cpu-seconds", type=float, default=4.0, help="target seconds per step of the --impl reference arm")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
