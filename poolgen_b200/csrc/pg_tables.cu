@@ -67,6 +67,307 @@ __device__ double hypergeom_ratio_dev(const double *c, int cells, double lp) {
     return pow(10.0, lp - s);
 }
 
+
+// ---- register-resident variant for the common small tables (NP pools x NA stored alleles, C5: 2 x 4..6) ------------
+// Same arithmetic in the same order as the generic kernel below, but the table lives in registers (every index is a
+// compile-time constant, removed alleles stay in place as zero cells under a kept mask, which preserves the order of
+// every sum over the kept columns), the chi-square tail uses the finite closed forms of the regularised gamma function
+// for integer and half-integer shape, and 10^x is exp10.
+
+// upper tail Q(a, x) of the regularised gamma function for 2a = df integer:
+//   a = m      : Q = e^-x sum_{j<m} x^j / j!
+//   a = m + 1/2: Q = erfc(sqrt x) + e^-x sum_{j<m} x^(j+1/2) / Gamma(j + 3/2)
+// (finite sums of positive terms: accurate to a few ulp; statrs reaches the same value through its series / continued
+// fraction to 1e-15).  The caller forms p = 1 - (1 - Q) like the reference's 1 - cdf.
+__device__ __forceinline__ double gamma_q_halfint(int df, double x) {
+    const double ex = exp(-x);
+    if (df & 1) {
+        const int m = df >> 1;
+        const double sx = sqrt(x);
+        double term = 1.1283791670955125738961589031215 * sx;  // 2 sqrt(x) / sqrt(pi) = x^(1/2) / Gamma(3/2)
+        double sum = 0.0;
+        for (int j = 0; j < m; j++) {
+            sum += term;
+            term *= x / ((double)j + 1.5);
+        }
+        return erfc(sx) + ex * sum;
+    }
+    const int m = df >> 1;
+    double term = 1.0, sum = 0.0;
+    for (int j = 0; j < m; j++) {
+        sum += term;
+        term *= x / (double)(j + 1);
+    }
+    return ex * sum;
+}
+
+template <int NP, int NA>
+__device__ __forceinline__ double ratio_t(const double (&c)[NP][NA], unsigned km, double lp) {
+    double s = 0.0, total = 0.0;
+#pragma unroll
+    for (int i = 0; i < NP; i++)
+#pragma unroll
+        for (int j = 0; j < NA; j++)
+            if ((km >> j) & 1u) s = s + c_lf10[(int)c[i][j]];
+#pragma unroll
+    for (int i = 0; i < NP; i++)
+#pragma unroll
+        for (int j = 0; j < NA; j++)
+            if ((km >> j) & 1u) total = total + c[i][j];
+    s = s + c_lf10[(int)total];
+    return exp10(lp - s);
+}
+
+template <int NP, int NA>
+__global__ void __launch_bounds__(kTabThreads) tables_kernel_t(const TableParams p) {
+    extern __shared__ __align__(16) uint32_t sm_counts[];
+    constexpr int per_locus = NA * NP;
+    const int64_t tiles = (p.n_loci + kTabThreads - 1) / kTabThreads;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t l0 = tile * kTabThreads;
+        const int nl = (int)min((int64_t)kTabThreads, p.n_loci - l0);
+        const size_t words = (size_t)nl * per_locus;
+        const uint32_t *src = p.counts + (size_t)l0 * per_locus;
+        __syncthreads();
+        const size_t w4 = words / 4;
+        for (size_t i = threadIdx.x; i < w4; i += kTabThreads)
+            reinterpret_cast<uint4 *>(sm_counts)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+        for (size_t i = w4 * 4 + threadIdx.x; i < words; i += kTabThreads) sm_counts[i] = src[i];
+        __syncthreads();
+        if ((int)threadIdx.x >= nl) continue;
+        const int64_t locus = l0 + threadIdx.x;
+        double cnt[NP][NA];  // cnt[i][j] = count of pool i, stored allele j (0 for the dropped N column)
+        unsigned present = 0;  // stored columns that take part (N dropped when remove_ns)
+#pragma unroll
+        for (int j = 0; j < NA; j++) {
+            const bool on = j != p.drop_col;
+            if (on) present |= 1u << j;
+#pragma unroll
+            for (int i = 0; i < NP; i++) cnt[i][j] = on ? (double)sm_counts[(size_t)threadIdx.x * per_locus + j * NP + i] : 0.0;
+        }
+        // LocusCounts::filter (src/base/sync.rs:195-303), sequential sums in the reference's order
+        double dep[NP];
+        double dmin = 0.0;
+        int miss = 0;
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            double d = 0.0;
+#pragma unroll
+            for (int j = 0; j < NA; j++)
+                if ((present >> j) & 1u) d += cnt[i][j];
+            dep[i] = d;
+            if (i == 0 || d < dmin) dmin = d;
+            if (d == 0.0) miss++;
+        }
+        int status = PG_LOCUS_OK;
+        unsigned km = 0;
+        if (dmin < p.min_depth_f) {
+            status = PG_LOCUS_FILTERED;
+        } else {
+#pragma unroll
+            for (int j = 0; j < NA; j++) {
+                if (!((present >> j) & 1u)) continue;
+                double q = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; i++) {
+                    const double f = (dep[i] == 0.0) ? nan("") : cnt[i][j] / dep[i];
+                    const double term = (f != f) ? 0.0 : __dmul_rn(f, p.w[i]);
+                    q = __dadd_rn(q, term);
+                }
+                if (!((q < p.maf) | (q > p.one_minus_maf))) km |= 1u << j;
+            }
+            if (__popc(km) < 2)
+                status = PG_LOCUS_FILTERED;
+            else if (miss == NP || ((double)miss / (double)NP) > p.max_miss)
+                status = PG_LOCUS_FILTERED;
+        }
+        const int pk = __popc(km);
+        double stat = nan(""), pval = nan("");
+        if (status == PG_LOCUS_OK) {
+            double c[NP][NA], rs[NP], cs[NA];
+            if (p.kind == PG_KIND_CHISQ) {
+#pragma unroll
+                for (int i = 0; i < NP; i++) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NA; j++)
+                        if ((km >> j) & 1u) d = d + cnt[i][j];
+#pragma unroll
+                    for (int j = 0; j < NA; j++) c[i][j] = ((km >> j) & 1u) ? ((d == 0.0) ? nan("") : cnt[i][j] / d) : 0.0;
+                }
+                double total = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; i++)
+#pragma unroll
+                    for (int j = 0; j < NA; j++)
+                        if ((km >> j) & 1u) total = total + c[i][j];
+#pragma unroll
+                for (int i = 0; i < NP; i++) {
+                    rs[i] = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NA; j++)
+                        if ((km >> j) & 1u) rs[i] = rs[i] + c[i][j];
+                }
+#pragma unroll
+                for (int j = 0; j < NA; j++) {
+                    cs[j] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NP; i++) cs[j] = cs[j] + c[i][j];
+                }
+                double chi2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; i++)
+#pragma unroll
+                    for (int j = 0; j < NA; j++)
+                        if ((km >> j) & 1u) {
+                            const double e = (rs[i] * cs[j]) / total;
+                            const double d = c[i][j] - e;
+                            chi2 += (d * d) / e;
+                        }
+                stat = chi2;
+                const int df = NP * pk - 1;
+                double cdf;
+                if (chi2 != chi2)
+                    cdf = nan("");
+                else if (chi2 <= 0.0)
+                    cdf = 0.0;
+                else if (isinf(chi2))
+                    cdf = 1.0;
+                else
+                    cdf = 1.0 - gamma_q_halfint(df, chi2 * 0.5);
+                pval = 1.00 - cdf;
+            } else {
+                double total = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; i++)
+#pragma unroll
+                    for (int j = 0; j < NA; j++) {
+                        c[i][j] = ((km >> j) & 1u) ? cnt[i][j] : 0.0;
+                        if ((km >> j) & 1u) total = total + c[i][j];
+                    }
+                if (total > 34.0) {
+                    const double coef = 34.0 / total;
+#pragma unroll
+                    for (int i = 0; i < NP; i++)
+#pragma unroll
+                        for (int j = 0; j < NA; j++)
+                            if ((km >> j) & 1u) c[i][j] = floor(c[i][j] * coef);
+                }
+#pragma unroll
+                for (int i = 0; i < NP; i++) {
+                    rs[i] = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NA; j++) rs[i] = rs[i] + c[i][j];
+                }
+#pragma unroll
+                for (int j = 0; j < NA; j++) {
+                    cs[j] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NP; i++) cs[j] = cs[j] + c[i][j];
+                }
+                double lp = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; i++) lp = lp + c_lf10[(int)rs[i]];
+#pragma unroll
+                for (int j = 0; j < NA; j++)
+                    if ((km >> j) & 1u) lp = lp + c_lf10[(int)cs[j]];
+                const double p_obs = ratio_t<NP, NA>(c, km, lp);
+                const int jlast = 31 - __clz(km);  // the last kept column
+                double p_ext = 0.0;
+                bool panic = false;
+                for (int mi = 0; mi < NP && !panic; mi++)
+                    for (int mj = 0; mj < NA && !panic; mj++) {
+                        if (!((km >> mj) & 1u)) continue;
+                        // forward fill (fisher_exact_test.rs:78-92)
+#pragma unroll
+                        for (int i = 0; i < NP; i++)
+#pragma unroll
+                            for (int j = 0; j < NA; j++) {
+                                if (!((km >> j) & 1u)) continue;
+                                double r = 0.0, sdown = 0.0;
+#pragma unroll
+                                for (int jj = 0; jj < j; jj++) r = r + c[i][jj];
+#pragma unroll
+                                for (int ii = 0; ii < i; ii++) sdown = sdown + c[ii][j];
+                                const double a = as_usize_f64(rs[i] - r), b = as_usize_f64(cs[j] - sdown);
+                                const double mx = a < b ? a : b;
+                                if ((i == NP - 1) | (j == jlast))
+                                    c[i][j] = mx;
+                                else if ((i < mi) | (j < mj))
+                                    c[i][j] = 0.0;
+                                else
+                                    c[i][j] = mx;
+                            }
+                        // reverse fill (fisher_exact_test.rs:96-111)
+#pragma unroll
+                        for (int j = NA - 1; j >= 0; j--)
+#pragma unroll
+                            for (int i = NP - 1; i >= 0; i--) {
+                                if (!((km >> j) & 1u)) continue;
+                                double r = 0.0, sdown = 0.0;
+#pragma unroll
+                                for (int jj = 0; jj < NA; jj++) r = r + c[i][jj];
+#pragma unroll
+                                for (int ii = 0; ii < NP; ii++) sdown = sdown + c[ii][j];
+                                const double a = as_usize_f64(rs[i] - r), b = as_usize_f64(cs[j] - sdown);
+                                const double mx = a < b ? a : b;
+                                if (mx > 0.0) c[i][j] = mx;
+                            }
+#pragma unroll
+                        for (int i = 0; i < NP; i++) {
+                            double r = 0.0;
+#pragma unroll
+                            for (int j = 0; j < NA; j++) r = r + c[i][j];
+                            if (r != rs[i]) panic = true;
+                        }
+#pragma unroll
+                        for (int j = 0; j < NA; j++) {
+                            double sdown = 0.0;
+#pragma unroll
+                            for (int i = 0; i < NP; i++) sdown = sdown + c[i][j];
+                            if (sdown != cs[j]) panic = true;
+                        }
+                        if (!panic) p_ext += ratio_t<NP, NA>(c, km, lp);
+                    }
+                if (panic) {
+                    status = PG_LOCUS_PANIC;  // assert! at fisher_exact_test.rs:113-114
+                } else {
+                    stat = p_obs;
+                    pval = p_obs + p_ext;
+                }
+            }
+        }
+        uint64_t mv = (uint64_t)status;
+        if (status == PG_LOCUS_OK) {
+            mv |= (uint64_t)pk << 8;
+            int a = 0;
+#pragma unroll
+            for (int j = 0; j < NA; j++)
+                if ((km >> j) & 1u) {
+                    mv |= (uint64_t)p.codes[j] << (16 + 8 * a);
+                    a++;
+                }
+        }
+        p.meta[locus] = mv;
+        double *o = p.stats + (size_t)locus * 4;
+        *reinterpret_cast<double2 *>(o) = make_double2(stat, nan(""));
+        *reinterpret_cast<double2 *>(o + 2) = make_double2(nan(""), pval);
+    }
+}
+
+template <int NP, int NA>
+static cudaError_t launch_tables_t(const TableParams &p, int sm_count, cudaStream_t s) {
+    const size_t smem = (size_t)kTabThreads * NA * NP * 4;
+    auto kern = tables_kernel_t<NP, NA>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t tiles = (p.n_loci + kTabThreads - 1) / kTabThreads;
+    int64_t grid = tiles < (int64_t)sm_count * 8 ? tiles : (int64_t)sm_count * 8;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kTabThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(kTabThreads) tables_kernel(const TableParams p) {
     extern __shared__ __align__(16) uint32_t sm_counts[];
     const int per_locus = p.A_in * p.n;  // u32 words
@@ -225,6 +526,18 @@ cudaError_t launch_tables(const TableParams &p, int sm_count, cudaStream_t s) {
         cudaError_t e = cudaMemcpyToSymbol(c_lf10, lf, sizeof lf);
         if (e != cudaSuccess) return e;
         lf_ready[dev & 63] = true;
+    }
+    // register-resident kernels for the common small tables; everything else takes the generic kernel
+    if (p.n == 2) {
+        if (p.A_in == 4) return launch_tables_t<2, 4>(p, sm_count, s);
+        if (p.A_in == 5) return launch_tables_t<2, 5>(p, sm_count, s);
+        if (p.A_in == 6) return launch_tables_t<2, 6>(p, sm_count, s);
+    } else if (p.n == 3) {
+        if (p.A_in == 4) return launch_tables_t<3, 4>(p, sm_count, s);
+        if (p.A_in == 6) return launch_tables_t<3, 6>(p, sm_count, s);
+    } else if (p.n == 4) {
+        if (p.A_in == 4) return launch_tables_t<4, 4>(p, sm_count, s);
+        if (p.A_in == 6) return launch_tables_t<4, 6>(p, sm_count, s);
     }
     const size_t smem = (size_t)kTabThreads * p.A_in * p.n * 4;
     cudaError_t e = cudaFuncSetAttribute(tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -318,3 +318,23 @@ def test_full_size_c3_shard_properties(ctx):
     assert 0.04 < frac < 0.12, frac
     b.close()
     scan.close()
+
+
+@pytest.mark.parametrize("n,A", [(2, 4), (2, 5), (2, 6), (3, 4), (3, 6), (4, 4), (4, 6), (3, 5), (6, 4)])
+@pytest.mark.parametrize("kind", [pb.KIND_CHISQ, pb.KIND_FISHER])
+def test_small_tables(ctx, kind, n, A):
+    """register-resident table kernels (2-4 pools) and the generic kernel (other shapes) against the oracle; the N
+    column (code 4) is dropped on the device when present"""
+    L = 6000
+    counts = pb.synth_counts_host(0x7AB1E + n * 10 + A, 0, L, n, A)
+    if A >= 5:  # put a few reads on the N / D columns so that they matter
+        rng = np.random.default_rng(n * 100 + A)
+        counts[:, 4:] = (rng.random((L, A - 4, n)) < 0.3).astype(np.uint32) * rng.integers(1, 4, (L, A - 4, n), dtype=np.uint32)
+    fs = _fs(np.full(n, 1.0 / n), min_allele_frequency=0.01)
+    codes = np.arange(A, dtype=np.uint8)
+    scan = pb.Scan(ctx, kind, fs, n, codes)
+    dev = scan.run_counts(counts)
+    scan.close()
+    st = H.compare_tables(kind, counts, codes, fs, dev, label=f"tables n={n} A={A}")
+    assert st["ok"] > 0.5 * L
+    print(st)
