@@ -338,3 +338,19 @@ def test_small_tables(ctx, kind, n, A):
     st = H.compare_tables(kind, counts, codes, fs, dev, label=f"tables n={n} A={A}")
     assert st["ok"] > 0.5 * L
     print(st)
+
+
+def test_many_pools_split_phenotype_passes(ctx):
+    """4,000 pools x 3 phenotypes: the resident phenotype vectors of one pass are capped at 96 KB of shared memory, so
+    the scan runs 3 phenotypes as passes of two and one"""
+    n, A, k, L = 4000, 4, 3, 96
+    seed = 0x4000
+    counts = pb.synth_counts_host(seed, 0, L, n, A)
+    phen = pb.synth_phen_host(seed, n, k)
+    fs = _fs(np.full(n, 1.0 / n))
+    codes = np.arange(A, dtype=np.uint8)
+    for kind in (pb.KIND_OLS, pb.KIND_CORR):
+        scan = pb.Scan(ctx, kind, fs, n, codes, phen)
+        dev = scan.run_counts(counts)
+        scan.close()
+        print(H.compare_regression(kind, counts, codes, phen, fs, dev, label="4000 pools"))
