@@ -176,12 +176,17 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
         s->syy.assign(k, 0.0);
         for (int j = 0; j < k; j++) {
             double sum = 0.0;
+            int n_valid = 0;
             for (int i = 0; i < n; i++) {
                 const double v = phen[(size_t)i * k + j];
-                if (v != v) s->y_has_nan = 1;
+                if (v != v) {
+                    s->y_has_nan = 1;  // NA phenotype (src/base/phen.rs:68-75)
+                    continue;
+                }
                 sum += v;
+                n_valid++;
             }
-            const double mean = sum / n;
+            const double mean = n_valid ? sum / n_valid : 0.0;  // = sum / n without missing values
             double s1 = 0.0, s2 = 0.0;
             for (int i = 0; i < n; i++) {
                 const double c = phen[(size_t)i * k + j] - mean;
@@ -192,13 +197,14 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
             s->ysum[j] = s1;
             s->syy[j] = s2 - s1 * s1 / n;
         }
-        if (s->y_has_nan) {
+        if (s->y_has_nan && kind == PG_KIND_OLS) {
             // ols_iterate: remove_missing() shrinks the pools but not FilterStats.pool_sizes, so the reference
-            // panics at src/base/sync.rs:254-257; correlation drops NaN pairs per phenotype (not implemented).
+            // panics at src/base/sync.rs:254-257.  pearson_corr drops NaN pairs per phenotype
+            // (correlation_test.rs:21-31): every locus of such a scan takes the pairwise path of the fix-up kernel.
             delete s;
             return fail(ctx, PG_ERR_UNSUPPORTED,
-                        "pg_scan_open: missing phenotype values (the reference's ols_iter panics on them; "
-                        "pearson_corr pairwise deletion is not implemented on the device)");
+                        "pg_scan_open: missing phenotype values (the reference's ols_iter panics on them, "
+                        "src/base/sync.rs:254-257)");
         }
         s->df = (kind == PG_KIND_OLS) ? (double)n - 1.0 : (double)n - 2.0;
         if (kind == PG_KIND_OLS && !(s->df > 0.0)) {
@@ -477,6 +483,7 @@ static int run_once(pg_batch *b, int *launches) {
             p.ptab_inv_h = s->ptab_inv_h;
             p.ptab_M = s->ptab_M;
             p.K = std::min(kpass, s->k - base);
+            p.y_has_nan = s->y_has_nan;
             p.yc = s->d_yc + (size_t)base * s->lay.n_pad;
             p.w = s->d_w;
             for (int j = 0; j < p.K; j++) {

@@ -498,6 +498,106 @@ __device__ __noinline__ int redo_locus(const ScanParams &p, int64_t locus, unsig
     return PG_LOCUS_OK;
 }
 
+// pearsons_correlation with missing values (src/gwas/correlation_test.rs:21-31) by the whole warp: for every
+// phenotype the pools whose frequency OR phenotype is NaN are dropped pairwise, means and centred sums run over the
+// remaining pools (so they differ per phenotype), n in the t statistic stays the full pool count.
+template <int A, int K>
+__device__ __noinline__ int corr_pairwise_locus(const ScanParams &p, int64_t locus, unsigned kept, int m, unsigned cb,
+                                                const double *ys, double *out, int lane) {
+    constexpr int MS = A - 1;
+    const int n_pad = p.lay.n_pad;
+    double xbar[K][MS], ybar[K];
+    {
+        double cnt[K], sx[K][MS], sy[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            cnt[k] = sy[k] = 0.0;
+#pragma unroll
+            for (int a = 0; a < MS; a++) sx[k][a] = 0.0;
+        }
+        for_rows_coop<A>(p, locus, lane, [&](int i, const double(&f)[A], uint32_t d) {
+            double F[A], x[MS];
+            renorm_row<A>(f, d, kept, F);
+            bool xv = true;
+#pragma unroll
+            for (int a = 0; a < MS; a++) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < A; j++)
+                    if (a < m && j == slot_col(cb, a)) v = F[j];
+                x[a] = v;
+                xv &= (v == v);
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const double y = ys[k * n_pad + i];
+                if (xv && y == y) {
+                    cnt[k] += 1.0;
+                    sy[k] += y;
+#pragma unroll
+                    for (int a = 0; a < MS; a++) sx[k][a] += x[a];
+                }
+            }
+        });
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const double c = warp_sum_fixed(cnt[k]);
+            ybar[k] = warp_sum_fixed(sy[k]) / c;
+#pragma unroll
+            for (int a = 0; a < MS; a++) xbar[k][a] = warp_sum_fixed(sx[k][a]) / c;
+        }
+    }
+    double sxx[K][MS], sxy[K][MS], syy[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        syy[k] = 0.0;
+#pragma unroll
+        for (int a = 0; a < MS; a++) sxx[k][a] = sxy[k][a] = 0.0;
+    }
+    for_rows_coop<A>(p, locus, lane, [&](int i, const double(&f)[A], uint32_t d) {
+        double F[A], x[MS];
+        renorm_row<A>(f, d, kept, F);
+        bool xv = true;
+#pragma unroll
+        for (int a = 0; a < MS; a++) {
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < A; j++)
+                if (a < m && j == slot_col(cb, a)) v = F[j];
+            x[a] = v;
+            xv &= (v == v);
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const double y = ys[k * n_pad + i];
+            if (xv && y == y) {
+                const double dy = y - ybar[k];
+                syy[k] = fma(dy, dy, syy[k]);
+#pragma unroll
+                for (int a = 0; a < MS; a++) {
+                    const double dx = x[a] - xbar[k][a];
+                    sxx[k][a] = fma(dx, dx, sxx[k][a]);
+                    sxy[k][a] = fma(dx, dy, sxy[k][a]);
+                }
+            }
+        }
+    });
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const double yy = warp_sum_fixed(syy[k]);
+#pragma unroll
+        for (int a = 0; a < MS; a++) {
+            const double xx = warp_sum_fixed(sxx[k][a]), xy = warp_sum_fixed(sxy[k][a]);
+            if (lane == 0 && a < m) {
+                out[(a * K + k) * 2 + 0] = xy / (sqrt(xx) * sqrt(yy));
+                out[(a * K + k) * 2 + 1] = 0.0;
+            }
+        }
+    }
+    __syncwarp();
+    return PG_LOCUS_OK;
+}
+
 // Single-pass OLS from the reduced sums for M regressors, fully unrolled so that every matrix lives in registers.
 // Returns false when the centred X'X is not positive definite; sets redo when the single-pass form loses digits.
 template <int M, int A, int K, bool W>
@@ -711,7 +811,7 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
                 }
             }
         }
-        if (has_nan)
+        if (has_nan || p.y_has_nan)
             redo_mode = REDO_CORR_NAN;
         else if (redo)
             redo_mode = REDO_CORR;
@@ -951,7 +1051,9 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool a
             const unsigned cc = __shfl_sync(PG_FULL_MASK, cb, src);
             const int64_t lsrc = __shfl_sync(PG_FULL_MASK, locus, src);
             __syncwarp();
-            const int st = redo_locus<A, K>(p, lsrc, kk, mm, cc, md, ys, tot + (size_t)src * AC::NP, lane);
+            const int st = (md == REDO_CORR_NAN)
+                               ? corr_pairwise_locus<A, K>(p, lsrc, kk, mm, cc, ys, tot + (size_t)src * AC::NP, lane)
+                               : redo_locus<A, K>(p, lsrc, kk, mm, cc, md, ys, tot + (size_t)src * AC::NP, lane);
             if (lane == src) status = st;
         }
         __syncwarp();

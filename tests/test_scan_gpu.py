@@ -354,3 +354,25 @@ def test_many_pools_split_phenotype_passes(ctx):
         dev = scan.run_counts(counts)
         scan.close()
         print(H.compare_regression(kind, counts, codes, phen, fs, dev, label="4000 pools"))
+
+
+@pytest.mark.parametrize("n,L", [(40, 3000), (300, 800)])
+def test_pearson_with_missing_phenotypes(ctx, n, L):
+    """NA phenotype values (src/base/phen.rs:68-75): pearson_corr drops the pairs per phenotype
+    (correlation_test.rs:21-31); ols_iter panics in the reference, so the scan refuses to open"""
+    seed = 0x9A9 + n
+    counts = pb.synth_counts_host(seed, 0, L, n, 4)
+    phen = pb.synth_phen_host(seed, n, 3)
+    phen[3, 0] = np.nan
+    phen[7, 0] = np.nan
+    phen[n - 1, 2] = np.nan
+    fs = _fs(np.full(n, 1.0 / n))
+    codes = np.arange(4, dtype=np.uint8)
+    scan = pb.Scan(ctx, pb.KIND_CORR, fs, n, codes, phen)
+    dev = scan.run_counts(counts)
+    scan.close()
+    st = H.compare_regression(pb.KIND_CORR, counts, codes, phen, fs, dev, label=f"missing phenotypes n={n}")
+    assert st["ok"] > 0.8 * L
+    print(st)
+    with pytest.raises(pb.PgError):
+        pb.Scan(ctx, pb.KIND_OLS, fs, n, codes, phen)
