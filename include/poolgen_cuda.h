@@ -122,6 +122,15 @@ int pg_batch_upload_counts_u8(pg_batch *b, const uint8_t *counts, int64_t n_loci
  * N column already removed, NaN where the pool has no coverage) + per-pool depth [locus][pool].
  * OLS / CORR only. */
 int pg_batch_upload_freq(pg_batch *b, const double *freq, const uint32_t *depth, int64_t n_loci);
+/* sync TEXT on the fast path: a line-aligned chunk of a sync file (chr \t pos \t ref \t A:T:C:G:N:D per pool, as the
+ * chunk readers hand lines to `lparse`, src/base/sync.rs:100-156, 827-868) is copied to the device as it is and parsed
+ * there.  Commented lines and lines whose position is not an integer are skipped like the reference skips them; a pool
+ * count that differs from the scan's, or a malformed pool field (the reference panics), is PG_ERR_ARG with the byte
+ * offset in the message.  The scan must have been opened with the six sync columns (codes 0..5).  Synchronises the
+ * batch's stream.  pg_batch_text_labels: per parsed locus the byte offset of its line in the chunk (chromosome and
+ * position text for the writer) and the parsed position, host pointers valid until the next text upload. */
+int pg_batch_upload_sync_text(pg_batch *b, const char *text, size_t n_bytes, int64_t *n_loci);
+int pg_batch_text_labels(pg_batch *b, const uint64_t **line_offsets, const uint64_t **positions);
 /* synthetic counts generated on the device (integer hash; pg_synth_counts_host replays it bit for bit) */
 int pg_batch_synth(pg_batch *b, uint64_t seed, int64_t first_locus, int64_t n_loci);
 /* launch the scan kernel over the loci resident in the batch (asynchronous) */
@@ -145,6 +154,7 @@ int pg_scan_submit_counts(pg_scan *scan, const uint32_t *counts, int64_t n_loci,
 int pg_scan_submit_counts_u16(pg_scan *scan, const uint16_t *counts, int64_t n_loci, int *ticket);
 int pg_scan_submit_counts_u8(pg_scan *scan, const uint8_t *counts, int64_t n_loci, int *ticket);
 int pg_scan_submit_freq(pg_scan *scan, const double *freq, const uint32_t *depth, int64_t n_loci, int *ticket);
+int pg_scan_submit_sync_text(pg_scan *scan, const char *text, size_t n_bytes, int *ticket, int64_t *n_loci);
 int pg_scan_collect(pg_scan *scan, int ticket, pg_results *out);
 
 /* ---- ols_iter_with_kinship: ols_with_covariate (src/gwas/ols.rs:278-436) over a device-resident block of allele

@@ -6,6 +6,7 @@ Host-side mirror of the reference's callback interface for the hot path only:
 BATCH of parsed loci instead of one.  All arithmetic runs in libpoolgen_cuda.so (hand-written CUDA);
 nothing here computes on the CPU.
 """
+from . import capi  # noqa: F401
 from .capi import (ALLELE_NAMES, KIND_CHISQ, KIND_CORR, KIND_FISHER, KIND_OLS, LOCUS_FAILED, LOCUS_FILTERED,
                    LOCUS_OK, LOCUS_PANIC, LOCUS_UNSUPPORTED, Batch, Context, FilterStats, Kinship, PgError, Scan,
                    ScanResults, synth_counts_host, synth_phen_host)

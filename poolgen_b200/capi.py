@@ -27,7 +27,8 @@ ALLELE_NAMES = "ATCGND"  # sync column order, src/base/sync.rs:134-137
 ABI_SYMBOLS = [
     "pg_abi_version", "pg_init", "pg_destroy", "pg_last_error", "pg_device_info", "pg_pinned_alloc",
     "pg_pinned_free", "pg_scan_open", "pg_scan_close", "pg_batch_create", "pg_batch_destroy",
-    "pg_batch_upload_counts", "pg_batch_upload_counts_u16", "pg_batch_upload_counts_u8", "pg_batch_upload_freq", "pg_batch_synth",
+    "pg_batch_upload_counts", "pg_batch_upload_counts_u16", "pg_batch_upload_counts_u8", "pg_batch_upload_freq", "pg_batch_upload_sync_text", "pg_batch_text_labels",
+    "pg_scan_submit_sync_text", "pg_batch_synth",
     "pg_batch_run", "pg_batch_download", "pg_batch_sync", "pg_batch_results", "pg_batch_time_runs",
     "pg_batch_bytes", "pg_scan_stream_begin", "pg_scan_submit_counts", "pg_scan_submit_counts_u16",
     "pg_scan_submit_counts_u8", "pg_scan_submit_freq", "pg_scan_collect", "pg_synth_counts_host", "pg_synth_phen_host",
@@ -93,6 +94,9 @@ def lib():
             "pg_batch_upload_counts_u16": (i, [vp, vp, i64]),
             "pg_batch_upload_counts_u8": (i, [vp, vp, i64]),
             "pg_batch_upload_freq": (i, [vp, vp, vp, i64]),
+            "pg_batch_upload_sync_text": (i, [vp, vp, C.c_size_t, C.POINTER(i64)]),
+            "pg_batch_text_labels": (i, [vp, pvp, pvp]),
+            "pg_scan_submit_sync_text": (i, [vp, vp, C.c_size_t, C.POINTER(i), C.POINTER(i64)]),
             "pg_batch_synth": (i, [vp, u64, i64, i64]),
             "pg_batch_run": (i, [vp]),
             "pg_batch_download": (i, [vp]),
@@ -312,6 +316,21 @@ class Batch:
     def synth(self, seed: int, first_locus: int, n_loci: int):
         self._ck(lib().pg_batch_synth(self._h, int(seed), int(first_locus), int(n_loci)), "pg_batch_synth")
 
+    def upload_sync_text(self, text: bytes):
+        """a line-aligned chunk of a sync file, parsed on the device; returns (n_loci, line byte offsets, positions)"""
+        buf = bytes(text)
+        self._keep = buf
+        n = C.c_int64()
+        self._ck(lib().pg_batch_upload_sync_text(self._h, buf, len(buf), C.byref(n)), "pg_batch_upload_sync_text")
+        L = int(n.value)
+        po, pp = C.c_void_p(), C.c_void_p()
+        self._ck(lib().pg_batch_text_labels(self._h, C.byref(po), C.byref(pp)), "pg_batch_text_labels")
+        if L == 0:
+            return 0, np.zeros(0, np.uint64), np.zeros(0, np.uint64)
+        off = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(L,)).copy()
+        pos = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_uint64)), shape=(L,)).copy()
+        return L, off, pos
+
     def run(self):
         self._ck(lib().pg_batch_run(self._h), "pg_batch_run")
 
@@ -457,6 +476,15 @@ class Kinship:
         if self._h:
             lib().pg_kin_close(self._h)
             self._h = C.c_void_p()
+
+
+def submit_sync_text(scan: "Scan", text: bytes):
+    """pg_scan_submit_sync_text: parse + scan + download of one text slab; returns (ticket, n_loci)"""
+    t, n = C.c_int(), C.c_int64()
+    buf = bytes(text)
+    scan._keep_text = buf
+    _check(lib().pg_scan_submit_sync_text(scan._h, buf, len(buf), C.byref(t), C.byref(n)), scan.ctx._h, "pg_scan_submit_sync_text")
+    return t.value, int(n.value)
 
 
 def synth_counts_host(seed: int, first_locus: int, n_loci: int, n_pools: int, n_alleles: int) -> np.ndarray:

@@ -306,6 +306,7 @@ int pg_batch_destroy(pg_batch *b) {
     cudaFree(b->d_depth);
     cudaFree(b->d_dmin);
     cudaFree(b->d_defer);
+    pg::text_scratch_free(b->text);
     cudaFree(b->d_stage);
     cudaFree(b->d_meta);
     cudaFree(b->d_fmean);
@@ -402,6 +403,44 @@ int pg_batch_upload_freq(pg_batch *b, const double *freq, const uint32_t *depth,
     PG_CUDA(ctx, cudaMemcpyAsync(sd, depth, (size_t)n_loci * s->n * 4, cudaMemcpyHostToDevice, b->stream));
     PG_CUDA(ctx, pg::launch_ingest_freq(sf, sd, n_loci, s->n, s->lay, b->d_freq, b->d_depth, b->d_dmin, b->stream));
     b->input_is_counts = 0;
+    return PG_OK;
+}
+
+int pg_batch_upload_sync_text(pg_batch *b, const char *text, size_t n_bytes, int64_t *n_loci_out) {
+    if (!b || (!text && n_bytes > 0)) return PG_ERR_ARG;
+    pg_scan *s = b->scan;
+    pg_ctx *ctx = s->ctx;
+    if (s->A_in != 6) return fail(ctx, PG_ERR_ARG, "upload_sync_text: the scan must be opened with the six sync columns A:T:C:G:N:D");
+    for (int j = 0; j < 6; j++)
+        if (s->codes_in[j] != j) return fail(ctx, PG_ERR_ARG, "upload_sync_text: allele codes must be 0..5 in sync order");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_loci_out) *n_loci_out = 0;
+    b->n_loci = 0;
+    b->have_input = 1;
+    b->input_is_counts = 1;
+    int rc = ensure_stage(b, (size_t)b->cap * 6 * s->n * 4);
+    if (rc) return rc;
+    cudaError_t ce = cudaSuccess;
+    uint64_t at = 0;
+    const int64_t L = pg::text_to_counts(&b->text, text, n_bytes, s->n, (uint32_t *)b->d_stage, b->cap, ctx->sm_count,
+                                         b->stream, &ce, &at);
+    if (L == -1) return fail(ctx, PG_ERR_CUDA, "upload_sync_text: %s", cudaGetErrorString(ce));
+    if (L == -2) return fail(ctx, PG_ERR_ARG, "upload_sync_text: more loci in the chunk than the batch capacity %lld", (long long)b->cap);
+    if (L == -3) return fail(ctx, PG_ERR_ARG, "upload_sync_text: the line at byte %llu does not hold %d pools (the reference asserts the pool count, src/base/sync.rs:254-257)", (unsigned long long)at, s->n);
+    if (L == -4) return fail(ctx, PG_ERR_ARG, "upload_sync_text: malformed pool field at byte %llu (the reference panics: allele counts are not valid integers, src/base/sync.rs:146)", (unsigned long long)at);
+    b->n_loci = L;
+    if (n_loci_out) *n_loci_out = L;
+    if (L > 0 && is_regression(s))
+        PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, L, s->n, s->A_in, s->drop_col, s->lay, b->d_freq,
+                                           b->d_depth, b->d_dmin, b->stream));
+    return PG_OK;
+}
+
+int pg_batch_text_labels(pg_batch *b, const uint64_t **line_offsets, const uint64_t **positions) {
+    if (!b) return PG_ERR_ARG;
+    if (!b->text) return fail(b->scan->ctx, PG_ERR_STATE, "pg_batch_text_labels before pg_batch_upload_sync_text");
+    if (line_offsets) *line_offsets = pg::text_offsets(b->text);
+    if (positions) *positions = pg::text_positions(b->text);
     return PG_OK;
 }
 
@@ -655,6 +694,14 @@ int pg_scan_submit_freq(pg_scan *s, const double *freq, const uint32_t *depth, i
     int rc = submit_common(s, ticket, &b);
     if (rc) return rc;
     if ((rc = pg_batch_upload_freq(b, freq, depth, n_loci))) return rc;
+    if ((rc = pg_batch_run(b))) return rc;
+    return pg_batch_download(b);
+}
+int pg_scan_submit_sync_text(pg_scan *s, const char *text, size_t n_bytes, int *ticket, int64_t *n_loci) {
+    pg_batch *b = nullptr;
+    int rc = submit_common(s, ticket, &b);
+    if (rc) return rc;
+    if ((rc = pg_batch_upload_sync_text(b, text, n_bytes, n_loci))) return rc;
     if ((rc = pg_batch_run(b))) return rc;
     return pg_batch_download(b);
 }

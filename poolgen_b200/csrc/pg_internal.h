@@ -126,6 +126,14 @@ cudaError_t launch_ingest_freq(const double *freq_in, const uint32_t *depth_in, 
 cudaError_t launch_synth(uint64_t seed, int64_t first_locus, int64_t n_loci, int n, int A_in,
                          uint32_t *counts, cudaStream_t s);
 
+// sync text -> counts[locus][6][n_pools] on the device (pg_text.cu)
+struct TextScratch;
+int64_t text_to_counts(TextScratch **scratch, const char *text, size_t n_bytes, int n_pools, uint32_t *d_counts,
+                       int64_t max_loci, int sm_count, cudaStream_t s, cudaError_t *cuda_err, uint64_t *err_offset);
+void text_scratch_free(TextScratch *t);
+const uint64_t *text_offsets(const TextScratch *t);
+const uint64_t *text_positions(const TextScratch *t);
+
 // synthetic generator shared by host and device (pure integer arithmetic)
 __host__ __device__ inline uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -245,4 +253,5 @@ struct pg_batch {
     double *h_stats = nullptr;
     int have_input = 0;
     int input_is_counts = 0;
+    pg::TextScratch *text = nullptr;
 };

@@ -1,0 +1,117 @@
+"""Sync text parsed on the device (pg_batch_upload_sync_text) against the count path and the oracle's line parser."""
+import numpy as np
+import pytest
+
+import poolgen_b200 as pb
+from oracle import pgo
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _sync_text(counts, chroms, positions, crlf=False, extra=()):
+    """counts [L, 6, n] -> sync text (src/base/sync.rs:100-156 format); `extra` = (line index, raw line) insertions"""
+    eol = "\r\n" if crlf else "\n"
+    lines = ["#chr\tpos\tref\t" + "\t".join(f"pool{i}" for i in range(counts.shape[2]))]
+    ins = dict(extra)
+    for l in range(counts.shape[0]):
+        if l in ins:
+            lines.append(ins[l])
+        pools = "\t".join(":".join(str(int(v)) for v in counts[l, :, i]) for i in range(counts.shape[2]))
+        lines.append(f"{chroms[l]}\t{positions[l]}\tN\t{pools}")
+    return (eol.join(lines) + eol).encode()
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+def test_c1_text_matches_counts(ctx, crlf):
+    c1 = H.load_c1()
+    counts = c1["counts"]
+    L = counts.shape[0]
+    chroms = [str(c1["chrom_names"][i]) for i in c1["chrom_idx"]]
+    pos = [int(p) for p in c1["pos"]]
+    text = _sync_text(counts, chroms, pos, crlf, extra=[(5, "Chromosome1\tnot_a_number\tC\t" + "\t".join(["1:2:3:4:5:6"] * 5)),
+                                                       (9, "#a comment in the middle")])
+    # the oracle's restatement of lparse agrees with the generated text line by line
+    body = [ln for ln in text.decode().replace("\r\n", "\n").split("\n") if ln and not ln.startswith("#") and "not_a_number" not in ln]
+    for l in (0, 1, 77, L - 1):
+        n, ch, p, oc = pgo.parse_sync_line(body[l] + "\n")
+        assert n == 5 and ch == chroms[l] and p == pos[l] and (oc.T == counts[l]).all()
+    fs = pb.FilterStats(pool_sizes=c1["pool_sizes"])
+    for kind, phen in ((pb.KIND_CHISQ, None), (pb.KIND_FISHER, None), (pb.KIND_OLS, c1["phen"]), (pb.KIND_CORR, c1["phen"])):
+        scan = pb.Scan(ctx, kind, fs, 5, c1["codes"], phen)
+        b = scan.batch(L)
+        nl, off, p = b.upload_sync_text(text)
+        assert nl == L
+        assert list(p) == pos
+        for l in (0, 5, 6, 9, 10, L - 1):  # the line offsets point at the chromosome names
+            assert text[int(off[l]):].startswith((chroms[l] + "\t" + str(pos[l])).encode())
+        b.run()
+        from_text = b.fetch()
+        b.upload_counts(counts)
+        b.run()
+        from_counts = b.fetch()
+        b.close()
+        scan.close()
+        assert (from_text.status == from_counts.status).all()
+        assert np.array_equal(from_text.stats, from_counts.stats, equal_nan=True)
+        assert (from_text.alleles == from_counts.alleles).all()
+
+
+def test_synthetic_text_and_streaming(ctx):
+    n, L, k = 100, 3000, 2
+    counts4 = pb.synth_counts_host(0x7E47, 0, L, n, 4)
+    counts = np.zeros((L, 6, n), dtype=np.uint32)
+    counts[:, :4] = counts4
+    counts[:, 5] = (np.arange(L)[:, None] + np.arange(n)[None, :]) % 3 == 0  # a few deletions
+    chroms = ["chr%d" % (1 + l // 1000) for l in range(L)]
+    pos = [1000 + 7 * l for l in range(L)]
+    phen = pb.synth_phen_host(0x7E47, n, k)
+    fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n))
+    codes = np.arange(6, dtype=np.uint8)
+    scan = pb.Scan(ctx, pb.KIND_OLS, fs, n, codes, phen)
+    whole = scan.run_counts(counts)
+    scan.stream_begin(1024)
+    parts = []
+    pending = []
+    for l0 in range(0, L, 1000):
+        text = _sync_text(counts[l0:l0 + 1000], chroms[l0:l0 + 1000], pos[l0:l0 + 1000])
+        t, nl = pb.capi.submit_sync_text(scan, text)
+        assert nl == min(1000, L - l0)
+        pending.append(t)
+    for t in pending:
+        parts.append(scan.collect(t))
+    scan.close()
+    status = np.concatenate([p.status for p in parts])
+    stats = np.concatenate([p.stats for p in parts])
+    assert (status == whole.status).all()
+    assert np.array_equal(stats, whole.stats, equal_nan=True)
+    H.compare_regression(pb.KIND_OLS, counts, codes, phen, fs, whole, label="synthetic text")
+
+
+def test_text_errors(ctx):
+    n = 3
+    fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n))
+    scan = pb.Scan(ctx, pb.KIND_CHISQ, fs, n, np.arange(6, dtype=np.uint8))
+    b = scan.batch(16)
+    good = b"c\t1\tA\t1:2:3:4:0:0\t1:2:3:4:0:0\t4:3:2:1:0:0\n"
+    assert b.upload_sync_text(good)[0] == 1
+    assert b.upload_sync_text(good[:-1])[0] == 1                      # last line without its newline
+    assert b.upload_sync_text(b"# only a comment\n")[0] == 0
+    assert b.upload_sync_text(b"")[0] == 0
+    assert b.upload_sync_text(b"c\t+12\tA\t1:2:3:4:0:0:9\t1:2:3:4:0:0\t4:3:2:1:0:0\n")[0] == 1   # extra numbers ignored
+    with pytest.raises(pb.PgError):   # two pools where the scan has three
+        b.upload_sync_text(b"c\t1\tA\t1:2:3:4:0:0\t1:2:3:4:0:0\n")
+    with pytest.raises(pb.PgError):   # five numbers in a pool field
+        b.upload_sync_text(b"c\t1\tA\t1:2:3:4:0\t1:2:3:4:0:0\t4:3:2:1:0:0\n")
+    with pytest.raises(pb.PgError):   # not an integer
+        b.upload_sync_text(b"c\t1\tA\t1:2:x:4:0:0\t1:2:3:4:0:0\t4:3:2:1:0:0\n")
+    with pytest.raises(pb.PgError):   # more loci than the batch holds
+        b.upload_sync_text(good * 17)
+    b.close()
+    scan.close()
+    scan4 = pb.Scan(ctx, pb.KIND_CHISQ, fs, n, np.arange(4, dtype=np.uint8))
+    b4 = scan4.batch(4)
+    with pytest.raises(pb.PgError):   # sync text needs the six sync columns
+        b4.upload_sync_text(good)
+    b4.close()
+    scan4.close()
