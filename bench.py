@@ -242,6 +242,7 @@ def run_cuda(args):
         if rank == 0:
             extras = c2_numbers(ctx, pb)
             extras.update(c5_numbers(ctx, pb))
+            extras.update(text_numbers(ctx, pb))
         kin = c4_numbers(ctx, pb, dist, rank, world)  # every rank takes part (column shards + all-reduce)
         if rank == 0:
             extras.update(kin)
@@ -332,6 +333,47 @@ def c5_numbers(ctx, pb):
         b.close()
         scan.close()
     return out
+
+
+def text_numbers(ctx, pb):
+    """end to end from sync TEXT in pinned host memory (what the reference's reader threads start from) to
+    records on the host: H2D of the raw text, device-side parse, ingest, scan, D2H.  C3 shape, slabs of 4,096 loci."""
+    slab, n_slabs = 4096, 12
+    per_locus_cap = 16 + N_POOLS * 24
+    host, hptr = ctx.pinned_empty((2, slab * per_locus_cap), np.uint8)
+    nbytes = [pb.synth_sync_text_host(SEED, i * slab, slab, N_POOLS, N_ALLELES, host[i]) for i in range(2)]
+    phen = pb.synth_phen_host(SEED, N_POOLS, N_PHEN)
+    fs = pb.FilterStats(pool_sizes=np.full(N_POOLS, 1.0 / N_POOLS))
+    scan = pb.Scan(ctx, pb.KIND_OLS, fs, N_POOLS, np.arange(6, dtype=np.uint8), phen)
+    scan.stream_begin(slab)
+    import ctypes as C
+    lib = pb.capi.lib()
+
+    def submit(i):
+        t, n = C.c_int(), C.c_int64()
+        rc = lib.pg_scan_submit_sync_text(scan._h, host[i % 2].ctypes.data, nbytes[i % 2], C.byref(t), C.byref(n))
+        assert rc == 0 and n.value == slab, (rc, n.value)
+        return t.value
+    for i in range(3):
+        scan.collect(submit(i), copy=False)
+    import torch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pending = []
+    for i in range(n_slabs):
+        pending.append(submit(i))
+        if len(pending) == 3:
+            scan.collect(pending.pop(0), copy=False)
+    while pending:
+        scan.collect(pending.pop(0), copy=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    scan.close()
+    ctx.pinned_free(hptr)
+    return {"e2e_sync_text": {"loci_per_s": slab * n_slabs / dt, "text_bytes_per_locus": nbytes[0] / slab,
+                              "text_gb_per_s": sum(nbytes[i % 2] for i in range(n_slabs)) / dt / 1e9,
+                              "note": "pinned sync text -> H2D -> device parse -> ingest -> scan -> D2H records, "
+                                      f"{N_POOLS} pools, slabs of {slab} loci"}}
 
 
 FP64_DMMA_PEAK_TFLOPS = 37.1  # tools/fp64_probe.cu on this pool's B200 (profiles/fp64_probe_r1.txt): mma.sync m8n8k4 f64

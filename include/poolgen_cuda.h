@@ -199,6 +199,10 @@ int pg_kin_covar_scan(pg_kin *kin, const double *phen, int k, int iters, float *
 int pg_synth_counts_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int n_pools, int n_alleles,
                          uint32_t *counts_out);
 int pg_synth_phen_host(uint64_t seed, int n_pools, int k, double *phen_out /* n_pools x k row-major */);
+/* the same counts as sync text (six columns, N = D = 0 beyond n_alleles): chr<1 + locus / 1000000> \t <locus + 1> \t N ...;
+ * returns the bytes written (or needed, when capacity is too small) in *n_bytes */
+int pg_synth_sync_text_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int n_pools, int n_alleles,
+                            char *out, size_t capacity, size_t *n_bytes);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "pg_scan_submit_sync_text", "pg_batch_synth",
     "pg_batch_run", "pg_batch_download", "pg_batch_sync", "pg_batch_results", "pg_batch_time_runs",
     "pg_batch_bytes", "pg_scan_stream_begin", "pg_scan_submit_counts", "pg_scan_submit_counts_u16",
-    "pg_scan_submit_counts_u8", "pg_scan_submit_freq", "pg_scan_collect", "pg_synth_counts_host", "pg_synth_phen_host",
+    "pg_scan_submit_counts_u8", "pg_scan_submit_freq", "pg_scan_collect", "pg_synth_counts_host", "pg_synth_phen_host", "pg_synth_sync_text_host",
     "pg_kin_open", "pg_kin_close", "pg_kin_reset", "pg_kin_columns", "pg_kin_append_columns", "pg_kin_append_counts",
     "pg_kin_last_labels", "pg_kin_synth", "pg_kin_get_columns", "pg_kin_gram", "pg_kin_gram_time", "pg_kin_partial",
     "pg_kin_partial_get", "pg_kin_partial_set", "pg_kin_eig_select", "pg_kin_eigvals", "pg_kin_set_covariates",
@@ -112,6 +112,7 @@ def lib():
             "pg_scan_collect": (i, [vp, i, C.POINTER(_Results)]),
             "pg_synth_counts_host": (i, [u64, i64, i64, i, i, vp]),
             "pg_synth_phen_host": (i, [u64, i, i, vp]),
+            "pg_synth_sync_text_host": (i, [u64, i64, i64, i, i, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
             "pg_kin_open": (i, [vp, i, i64, pvp]),
             "pg_kin_close": (i, [vp]),
             "pg_kin_reset": (i, [vp]),
@@ -493,6 +494,16 @@ def synth_counts_host(seed: int, first_locus: int, n_loci: int, n_pools: int, n_
     if rc != PG_OK:
         raise PgError(f"pg_synth_counts_host failed ({rc})")
     return out
+
+
+def synth_sync_text_host(seed: int, first_locus: int, n_loci: int, n_pools: int, n_alleles: int, out: np.ndarray) -> int:
+    """writes the synthetic counts as sync text into `out` (uint8 array, e.g. over pinned memory); returns the bytes"""
+    nb = C.c_size_t()
+    rc = lib().pg_synth_sync_text_host(int(seed), int(first_locus), int(n_loci), int(n_pools), int(n_alleles),
+                                       out.ctypes.data, int(out.size), C.byref(nb))
+    if rc != PG_OK:
+        raise PgError(f"pg_synth_sync_text_host failed ({rc}): needs {nb.value} bytes, has {out.size}")
+    return int(nb.value)
 
 
 def synth_phen_host(seed: int, n_pools: int, k: int) -> np.ndarray:

@@ -129,6 +129,8 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
                     filter->n_pool_sizes, n_pools);
     const bool regression = (kind == PG_KIND_OLS || kind == PG_KIND_CORR);
     if (regression && (!phen || k < 1)) return fail(ctx, PG_ERR_ARG, "pg_scan_open: phenotypes required");
+    if (!regression && n_pools > 16)
+        return fail(ctx, PG_ERR_UNSUPPORTED, "pg_scan_open: the count tests hold one table per thread and are built for up to 16 pools (got %d)", n_pools);
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
 
     pg_scan *s = new (std::nothrow) pg_scan();
@@ -723,6 +725,31 @@ int pg_synth_counts_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int
             for (int a = 0; a < n_alleles; a++) out[((size_t)l * n_alleles + a) * n_pools + i] = c[a];
         }
     return PG_OK;
+}
+
+int pg_synth_sync_text_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int n_pools, int n_alleles, char *out,
+                            size_t capacity, size_t *n_bytes) {
+    if (!n_bytes || n_pools < 1 || n_alleles < 1 || n_alleles > PG_MAX_ALLELES || n_loci < 0) return PG_ERR_ARG;
+    size_t w = 0;
+    char tmp[64];
+    auto put = [&](const char *p, size_t len) {
+        if (out && w + len <= capacity) memcpy(out + w, p, len);
+        w += len;
+    };
+    for (int64_t l = 0; l < n_loci; l++) {
+        const int64_t locus = first_locus + l;
+        int len = snprintf(tmp, sizeof tmp, "chr%lld\t%lld\tN", (long long)(1 + locus / 1000000), (long long)(locus + 1));
+        put(tmp, (size_t)len);
+        for (int i = 0; i < n_pools; i++) {
+            uint32_t c[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
+            pg::synth_counts(seed, locus, i, n_alleles, c);
+            len = snprintf(tmp, sizeof tmp, "\t%u:%u:%u:%u:%u:%u", c[0], c[1], c[2], c[3], c[4], c[5]);
+            put(tmp, (size_t)len);
+        }
+        put("\n", 1);
+    }
+    *n_bytes = w;
+    return (out && w <= capacity) ? PG_OK : PG_ERR_ARG;
 }
 
 int pg_synth_phen_host(uint64_t seed, int n_pools, int k, double *out) {

@@ -376,3 +376,9 @@ def test_pearson_with_missing_phenotypes(ctx, n, L):
     print(st)
     with pytest.raises(pb.PgError):
         pb.Scan(ctx, pb.KIND_OLS, fs, n, codes, phen)
+
+
+def test_count_tests_refuse_more_than_16_pools(ctx):
+    fs = _fs(np.full(17, 1.0 / 17))
+    with pytest.raises(pb.PgError):
+        pb.Scan(ctx, pb.KIND_FISHER, fs, 17, np.arange(4, dtype=np.uint8))

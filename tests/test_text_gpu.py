@@ -115,3 +115,29 @@ def test_text_errors(ctx):
         b4.upload_sync_text(good)
     b4.close()
     scan4.close()
+
+
+def test_host_text_generator_round_trip(ctx):
+    """pg_synth_sync_text_host writes the synthetic counts as sync text: parsing it on the device gives the records of
+    the count path"""
+    n, A, L = 12, 4, 500
+    out = np.empty(L * (16 + n * 24), dtype=np.uint8)
+    nb = pb.synth_sync_text_host(0xBEEF, 10, L, n, A, out)
+    text = out[:nb].tobytes()
+    assert text.count(b"\n") == L and text.startswith(b"chr1\t11\tN\t")
+    counts4 = pb.synth_counts_host(0xBEEF, 10, L, n, A)
+    counts = np.zeros((L, 6, n), dtype=np.uint32)
+    counts[:, :A] = counts4
+    fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n))
+    scan = pb.Scan(ctx, pb.KIND_FISHER, fs, n, np.arange(6, dtype=np.uint8))
+    b = scan.batch(L)
+    nl, off, pos = b.upload_sync_text(text)
+    assert nl == L and list(pos) == list(range(11, 11 + L))
+    b.run()
+    rt = b.fetch()
+    b.upload_counts(counts)
+    b.run()
+    rc = b.fetch()
+    b.close()
+    scan.close()
+    assert (rt.status == rc.status).all() and np.array_equal(rt.stats, rc.stats, equal_nan=True)
