@@ -288,6 +288,8 @@ int pg_batch_create(pg_scan *s, int64_t cap, pg_batch **out) {
         if (e == cudaSuccess) e = cudaMalloc(&b->d_depth, (size_t)cap * s->lay.depth_stride() * 4);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_dmin, (size_t)cap * 4);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_defer, (size_t)(cap + 1) * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_qbuf, (size_t)cap * s->A_dev * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_hint, (size_t)cap);
     }
     const size_t S = s->n_slots, K = s->k;
     if (e == cudaSuccess) e = cudaMalloc(&b->d_meta, (size_t)cap * 8);
@@ -308,6 +310,8 @@ int pg_batch_destroy(pg_batch *b) {
     cudaFree(b->d_depth);
     cudaFree(b->d_dmin);
     cudaFree(b->d_defer);
+    cudaFree(b->d_qbuf);
+    cudaFree(b->d_hint);
     pg::text_scratch_free(b->text);
     cudaFree(b->d_stage);
     cudaFree(b->d_meta);
@@ -321,6 +325,21 @@ int pg_batch_destroy(pg_batch *b) {
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
     return PG_OK;
+}
+
+static pg::IngestOut ingest_out(pg_batch *b, int64_t first_locus) {
+    pg_scan *s = b->scan;
+    pg::IngestOut o;
+    o.freq = b->d_freq + (size_t)first_locus * s->lay.freq_stride();
+    o.depth = b->d_depth + (size_t)first_locus * s->lay.depth_stride();
+    o.dmin = b->d_dmin + first_locus;
+    o.qbuf = b->d_qbuf + (size_t)first_locus * s->A_dev;
+    o.hint = b->d_hint + first_locus;
+    o.w = s->d_w;
+    o.maf = s->maf;
+    o.one_minus_maf = 1.00 - s->maf;
+    o.min_depth_f = (double)s->min_depth;
+    return o;
 }
 
 static int ensure_stage(pg_batch *b, size_t bytes) {
@@ -357,13 +376,13 @@ static int upload_counts_t(pg_batch *b, const CT *counts, int64_t n_loci) {
         PG_CUDA(ctx, cudaMemcpyAsync(b->d_stage, counts, bytes, cudaMemcpyHostToDevice, b->stream));
         if (sizeof(CT) == 4)
             PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
-                                               b->d_freq, b->d_depth, b->d_dmin, b->stream));
+                                               ingest_out(b, 0), b->stream));
         else if (sizeof(CT) == 1)
             PG_CUDA(ctx, pg::launch_ingest_u8((const uint8_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
-                                              b->d_freq, b->d_depth, b->d_dmin, b->stream));
+                                              ingest_out(b, 0), b->stream));
         else
             PG_CUDA(ctx, pg::launch_ingest_u16((const uint16_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
-                                               b->d_freq, b->d_depth, b->d_dmin, b->stream));
+                                               ingest_out(b, 0), b->stream));
     } else {
         if (sizeof(CT) != 4) return fail(ctx, PG_ERR_UNSUPPORTED, "narrow counts are not wired for the table tests yet");
         PG_CUDA(ctx, cudaMemcpyAsync(b->d_stage, counts, bytes, cudaMemcpyHostToDevice, b->stream));
@@ -403,7 +422,7 @@ int pg_batch_upload_freq(pg_batch *b, const double *freq, const uint32_t *depth,
     uint32_t *sd = (uint32_t *)((char *)b->d_stage + fbytes_cap);
     PG_CUDA(ctx, cudaMemcpyAsync(sf, freq, (size_t)n_loci * s->A_dev * s->n * 8, cudaMemcpyHostToDevice, b->stream));
     PG_CUDA(ctx, cudaMemcpyAsync(sd, depth, (size_t)n_loci * s->n * 4, cudaMemcpyHostToDevice, b->stream));
-    PG_CUDA(ctx, pg::launch_ingest_freq(sf, sd, n_loci, s->n, s->lay, b->d_freq, b->d_depth, b->d_dmin, b->stream));
+    PG_CUDA(ctx, pg::launch_ingest_freq(sf, sd, n_loci, s->n, s->lay, ingest_out(b, 0), b->stream));
     b->input_is_counts = 0;
     return PG_OK;
 }
@@ -433,8 +452,8 @@ int pg_batch_upload_sync_text(pg_batch *b, const char *text, size_t n_bytes, int
     b->n_loci = L;
     if (n_loci_out) *n_loci_out = L;
     if (L > 0 && is_regression(s))
-        PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, L, s->n, s->A_in, s->drop_col, s->lay, b->d_freq,
-                                           b->d_depth, b->d_dmin, b->stream));
+        PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, L, s->n, s->A_in, s->drop_col, s->lay,
+                                           ingest_out(b, 0), b->stream));
     return PG_OK;
 }
 
@@ -478,8 +497,7 @@ int pg_batch_synth(pg_batch *b, uint64_t seed, int64_t first_locus, int64_t n_lo
         const int64_t m = (n_loci - l0 < slice) ? n_loci - l0 : slice;
         PG_CUDA(ctx, pg::launch_synth(seed, first_locus + l0, m, s->n, s->A_in, (uint32_t *)b->d_stage, b->stream));
         PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, m, s->n, s->A_in, s->drop_col, s->lay,
-                                           b->d_freq + (size_t)l0 * s->lay.freq_stride(),
-                                           b->d_depth + (size_t)l0 * s->lay.depth_stride(), b->d_dmin + l0, b->stream));
+                                           ingest_out(b, l0), b->stream));
     }
     b->input_is_counts = 1;
     return PG_OK;
@@ -509,6 +527,7 @@ static int run_once(pg_batch *b, int *launches) {
             p.freq = b->d_freq;
             p.depth = b->d_depth;
             p.dmin = b->d_dmin;
+            p.hint = b->d_hint;
             p.n_loci = b->n_loci;
             p.kind = s->kind;
             p.weighted = s->weighted;

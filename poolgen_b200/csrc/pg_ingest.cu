@@ -3,6 +3,9 @@
 // generator.  Frequencies are one IEEE division of exactly representable integers, i.e. bit-identical
 // to LocusCounts::to_frequencies (src/base/sync.rs:166-192).  Every ingest also leaves dmin[locus] = the smallest
 // pool depth of the locus (the caller presets dmin to 0xFFFFFFFF).
+#include <stdlib.h>
+
+#include "pg_device.cuh"
 #include "pg_internal.h"
 
 namespace pg {
@@ -15,11 +18,58 @@ __device__ __forceinline__ void fold_dmin(uint32_t *dmin, int64_t locus, uint32_
     if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicMin(dmin + locus, m);
 }
 
+// per-locus pooled frequencies q_j = sum_i f_ij w_i (NaN skipped), accumulated with one atomic per (warp, locus,
+// allele) where a warp holds one locus; they only feed the renormalisation HINT of the scan, never a decision
+__device__ __forceinline__ void fold_q(double *qbuf, int64_t locus, int A, const double *fw) {
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, (unsigned long long)locus);
+    if (peers == 0xFFFFFFFFu) {
+        for (int j = 0; j < A; j++) {
+            double v = fw[j];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+            if ((threadIdx.x & 31) == 0) atomicAdd(qbuf + (size_t)locus * A + j, v);
+        }
+    } else {
+        for (int j = 0; j < A; j++)
+            if (fw[j] != 0.0) atomicAdd(qbuf + (size_t)locus * A + j, fw[j]);
+    }
+}
+
+// hint of a locus: bit 7 = "renormalise over the alleles in bits 0..5": every pool has coverage, the depth filter
+// passes, at least two alleles survive the MAF filter, a removed allele carries reads (the regression then runs on
+// c_ij / sum_kept c_i., src/base/sync.rs:166-192 after the filter) and every pooled frequency is further from both
+// thresholds than twice the rounding bound of ANY summation order -- so the keep-mask in the hint is the reference's.
+// The streaming scan renormalises such loci on the fly; every other locus gets 0 and takes the scan's own decision
+// path (which defers what it cannot settle to the fix-up kernel).
+__global__ void __launch_bounds__(256) hint_kernel(const double *__restrict__ qbuf, const uint32_t *__restrict__ dmin,
+                                                   int64_t n_loci, int A, int n, double maf, double one_minus_maf,
+                                                   double min_depth_f, uint8_t *__restrict__ hint) {
+    const double tol_rel = 4.0 * ((double)n + 8.0) * kEps;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n_loci; l += (int64_t)gridDim.x * blockDim.x) {
+        unsigned kept = 0;
+        bool removed_with_reads = false, safe = true;
+        for (int j = 0; j < A; j++) {
+            const double q = qbuf[(size_t)l * A + j];
+            const double tl = tol_rel * fmax(fabs(q), 1.0);
+            if (fabs(q - maf) <= tl || fabs(q - one_minus_maf) <= tl) safe = false;
+            if (!((q < maf) | (q > one_minus_maf)))
+                kept |= 1u << j;
+            else if (q > 0.0)
+                removed_with_reads = true;
+        }
+        const uint32_t dm = dmin[l];
+        const bool depth_ok = dm != 0u && !((double)dm < min_depth_f);
+        hint[l] = (safe && depth_ok && removed_with_reads && __popc(kept) >= 2) ? (uint8_t)(0x80u | kept) : (uint8_t)0;
+    }
+}
+
 template <typename CT>
 __global__ void __launch_bounds__(256) ingest_counts_kernel(const CT *__restrict__ counts, int64_t n_loci, int n,
                                                             int A_in, int drop_col, Layout lay,
                                                             double *__restrict__ freq, uint32_t *__restrict__ depth,
-                                                            uint32_t *__restrict__ dmin) {
+                                                            uint32_t *__restrict__ dmin, double *__restrict__ qbuf,
+                                                            const double *__restrict__ w) {
     const int64_t total = n_loci * lay.n_pad;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
@@ -30,6 +80,8 @@ __global__ void __launch_bounds__(256) ingest_counts_kernel(const CT *__restrict
             for (int j = 0; j < lay.A; j++) fl[lay.freq_off(i, j)] = 0.0;
             depth[(size_t)locus * lay.n_pad + i] = 0xFFFFFFFFu;
             fold_dmin(dmin, locus, 0xFFFFFFFFu);
+            double zero[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
+            fold_q(qbuf, locus, lay.A, zero);
             continue;
         }
         const CT *cl = counts + (size_t)locus * A_in * n + i;
@@ -43,17 +95,24 @@ __global__ void __launch_bounds__(256) ingest_counts_kernel(const CT *__restrict
             jj++;
         }
         if (d > 0xFFFFFFFEull) d = 0xFFFFFFFEull;  // documented limit: per-pool depth < 2^32 - 1
-        const double dd = (double)d;
-        for (int j = 0; j < lay.A; j++) fl[lay.freq_off(i, j)] = (d == 0) ? nan("") : (double)c[j] / dd;
+        const double dd = (double)d, wi = w[i];
+        double fw[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < lay.A; j++) {
+            const double f = (d == 0) ? nan("") : (double)c[j] / dd;
+            fl[lay.freq_off(i, j)] = f;
+            fw[j] = (d == 0) ? 0.0 : f * wi;
+        }
         depth[(size_t)locus * lay.n_pad + i] = (uint32_t)d;
         fold_dmin(dmin, locus, (uint32_t)d);
+        fold_q(qbuf, locus, lay.A, fw);
     }
 }
 
 __global__ void __launch_bounds__(256) ingest_freq_kernel(const double *__restrict__ fin, const uint32_t *__restrict__ din,
                                                           int64_t n_loci, int n, Layout lay,
                                                           double *__restrict__ freq, uint32_t *__restrict__ depth,
-                                                          uint32_t *__restrict__ dmin) {
+                                                          uint32_t *__restrict__ dmin, double *__restrict__ qbuf,
+                                                          const double *__restrict__ w) {
     const int64_t total = n_loci * lay.n_pad;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
@@ -61,11 +120,16 @@ __global__ void __launch_bounds__(256) ingest_freq_kernel(const double *__restri
         const int i = (int)(idx - locus * lay.n_pad);
         double *fl = freq + (size_t)locus * lay.freq_stride();
         const bool pad = i >= n;
-        for (int j = 0; j < lay.A; j++)
-            fl[lay.freq_off(i, j)] = pad ? 0.0 : fin[((size_t)locus * lay.A + j) * n + i];
+        double fw[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < lay.A; j++) {
+            const double f = pad ? 0.0 : fin[((size_t)locus * lay.A + j) * n + i];
+            fl[lay.freq_off(i, j)] = f;
+            fw[j] = (pad || f != f) ? 0.0 : f * w[i];
+        }
         const uint32_t d = pad ? 0xFFFFFFFFu : din[(size_t)locus * n + i];
         depth[(size_t)locus * lay.n_pad + i] = d;
         fold_dmin(dmin, locus, d);
+        fold_q(qbuf, locus, lay.A, fw);
     }
 }
 
@@ -88,40 +152,52 @@ static int grid_for(int64_t total) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-cudaError_t launch_ingest_u32(const uint32_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
-                              const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s) {
-    if (n_loci <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(dmin, 0xFF, (size_t)n_loci * 4, s);
-    if (e != cudaSuccess) return e;
-    ingest_counts_kernel<uint32_t><<<grid_for(n_loci * lay.n_pad), 256, 0, s>>>(counts, n_loci, n, A_in, drop_col,
-                                                                               lay, freq, depth, dmin);
+static cudaError_t ingest_prologue(int64_t n_loci, const Layout &lay, const IngestOut &o, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(o.dmin, 0xFF, (size_t)n_loci * 4, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(o.qbuf, 0, (size_t)n_loci * lay.A * 8, s);
+    return e;
+}
+static cudaError_t ingest_epilogue(int64_t n_loci, const Layout &lay, const IngestOut &o, cudaStream_t s) {
+    static const bool no_hint = getenv("PG_NOHINT") != nullptr;  // tuning knob: every locus takes the scan's own path
+    if (no_hint) return cudaMemsetAsync(o.hint, 0, (size_t)n_loci, s);
+    hint_kernel<<<grid_for(n_loci), 256, 0, s>>>(o.qbuf, o.dmin, n_loci, lay.A, lay.n, o.maf, o.one_minus_maf,
+                                                 o.min_depth_f, o.hint);
     return cudaGetLastError();
 }
-cudaError_t launch_ingest_u16(const uint16_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
-                              const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s) {
+template <typename CT>
+static cudaError_t launch_ingest_t(const CT *counts, int64_t n_loci, int n, int A_in, int drop_col, const Layout &lay,
+                                   const IngestOut &o, cudaStream_t s) {
     if (n_loci <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(dmin, 0xFF, (size_t)n_loci * 4, s);
+    cudaError_t e = ingest_prologue(n_loci, lay, o, s);
     if (e != cudaSuccess) return e;
-    ingest_counts_kernel<uint16_t><<<grid_for(n_loci * lay.n_pad), 256, 0, s>>>(counts, n_loci, n, A_in, drop_col,
-                                                                               lay, freq, depth, dmin);
-    return cudaGetLastError();
+    ingest_counts_kernel<CT><<<grid_for(n_loci * lay.n_pad), 256, 0, s>>>(counts, n_loci, n, A_in, drop_col, lay, o.freq,
+                                                                         o.depth, o.dmin, o.qbuf, o.w);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return ingest_epilogue(n_loci, lay, o, s);
 }
-cudaError_t launch_ingest_u8(const uint8_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
-                             const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s) {
-    if (n_loci <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(dmin, 0xFF, (size_t)n_loci * 4, s);
-    if (e != cudaSuccess) return e;
-    ingest_counts_kernel<uint8_t><<<grid_for(n_loci * lay.n_pad), 256, 0, s>>>(counts, n_loci, n, A_in, drop_col,
-                                                                              lay, freq, depth, dmin);
-    return cudaGetLastError();
+cudaError_t launch_ingest_u32(const uint32_t *counts, int64_t n_loci, int n, int A_in, int drop_col, const Layout &lay,
+                              const IngestOut &o, cudaStream_t s) {
+    return launch_ingest_t<uint32_t>(counts, n_loci, n, A_in, drop_col, lay, o, s);
+}
+cudaError_t launch_ingest_u16(const uint16_t *counts, int64_t n_loci, int n, int A_in, int drop_col, const Layout &lay,
+                              const IngestOut &o, cudaStream_t s) {
+    return launch_ingest_t<uint16_t>(counts, n_loci, n, A_in, drop_col, lay, o, s);
+}
+cudaError_t launch_ingest_u8(const uint8_t *counts, int64_t n_loci, int n, int A_in, int drop_col, const Layout &lay,
+                             const IngestOut &o, cudaStream_t s) {
+    return launch_ingest_t<uint8_t>(counts, n_loci, n, A_in, drop_col, lay, o, s);
 }
 cudaError_t launch_ingest_freq(const double *fin, const uint32_t *din, int64_t n_loci, int n, const Layout &lay,
-                               double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s) {
+                               const IngestOut &o, cudaStream_t s) {
     if (n_loci <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(dmin, 0xFF, (size_t)n_loci * 4, s);
+    cudaError_t e = ingest_prologue(n_loci, lay, o, s);
     if (e != cudaSuccess) return e;
-    ingest_freq_kernel<<<grid_for(n_loci * lay.n_pad), 256, 0, s>>>(fin, din, n_loci, n, lay, freq, depth, dmin);
-    return cudaGetLastError();
+    ingest_freq_kernel<<<grid_for(n_loci * lay.n_pad), 256, 0, s>>>(fin, din, n_loci, n, lay, o.freq, o.depth, o.dmin,
+                                                                    o.qbuf, o.w);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return ingest_epilogue(n_loci, lay, o, s);
 }
 cudaError_t launch_synth(uint64_t seed, int64_t first_locus, int64_t n_loci, int n, int A_in, uint32_t *counts,
                          cudaStream_t s) {

@@ -69,6 +69,7 @@ struct ScanParams {
     const double *freq;
     const uint32_t *depth;
     const uint32_t *dmin;
+    const uint8_t *hint;
     int64_t n_loci;
     int kind;
     int weighted;         // pool weights differ
@@ -115,14 +116,24 @@ struct TableParams {
 // launchers implemented in the kernel translation units
 cudaError_t launch_scan(const ScanParams &p, int sm_count, cudaStream_t s);
 cudaError_t launch_tables(const TableParams &p, int sm_count, cudaStream_t s);
-cudaError_t launch_ingest_u32(const uint32_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
-                              const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s);
-cudaError_t launch_ingest_u16(const uint16_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
-                              const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s);
-cudaError_t launch_ingest_u8(const uint8_t *counts, int64_t n_loci, int n, int A_in, int drop_col,
-                             const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s);
-cudaError_t launch_ingest_freq(const double *freq_in, const uint32_t *depth_in, int64_t n_loci, int n,
-                               const Layout &lay, double *freq, uint32_t *depth, uint32_t *dmin, cudaStream_t s);
+// what an ingest kernel produces for a slab of loci (device pointers already offset to the first locus of the slab)
+struct IngestOut {
+    double *freq;
+    uint32_t *depth;
+    uint32_t *dmin;
+    double *qbuf;    // [locus][A] scratch: pooled frequencies for the hint
+    uint8_t *hint;   // [locus] renormalisation hint of the scan (pg_ingest.cu:hint_kernel)
+    const double *w; // [n_pad] pool weights s_i / sum(s)
+    double maf, one_minus_maf, min_depth_f;
+};
+cudaError_t launch_ingest_u32(const uint32_t *counts, int64_t n_loci, int n, int A_in, int drop_col, const Layout &lay,
+                              const IngestOut &o, cudaStream_t s);
+cudaError_t launch_ingest_u16(const uint16_t *counts, int64_t n_loci, int n, int A_in, int drop_col, const Layout &lay,
+                              const IngestOut &o, cudaStream_t s);
+cudaError_t launch_ingest_u8(const uint8_t *counts, int64_t n_loci, int n, int A_in, int drop_col, const Layout &lay,
+                             const IngestOut &o, cudaStream_t s);
+cudaError_t launch_ingest_freq(const double *freq_in, const uint32_t *depth_in, int64_t n_loci, int n, const Layout &lay,
+                               const IngestOut &o, cudaStream_t s);
 cudaError_t launch_synth(uint64_t seed, int64_t first_locus, int64_t n_loci, int n, int A_in,
                          uint32_t *counts, cudaStream_t s);
 
@@ -242,6 +253,8 @@ struct pg_batch {
     uint32_t *d_depth = nullptr;
     uint32_t *d_dmin = nullptr;
     uint64_t *d_defer = nullptr;  // [cap + 1]: list then its counter
+    double *d_qbuf = nullptr;     // [cap][A] ingest scratch
+    uint8_t *d_hint = nullptr;    // [cap]
     void *d_stage = nullptr;  // raw uploaded slab (counts u32/u16 or unpadded freq+depth)
     size_t stage_bytes = 0;
     uint64_t *d_meta = nullptr;

@@ -172,6 +172,26 @@ __device__ __forceinline__ void renorm_row_fast(const double (&f)[A], uint32_t d
     for (int j = 0; j < A; j++) F[j] = ((kept >> j) & 1u) ? c[j] * inv : 0.0;
 }
 
+// the streaming form for loci whose ingest hint names the kept alleles: two rows (row, row + 1) of first-stage
+// frequencies f_ij = c_ij / depth_i become f_ij / sum_kept f_i. -- the depth cancels, so no depth load; within 3 ulp of
+// the reference's c_ij / sum_kept c_i. (only the regression sums are formed from it; a tie of column sums or a lost
+// digit still goes to the fix-up kernel).  A pool whose reads all sit on removed alleles gives NaN like the reference
+// (0 / 0), padding rows stay 0.
+template <int A>
+__device__ __forceinline__ void renorm_pair(double2 (&f2)[A], unsigned kept, int row, int n) {
+    double sx = 0.0, sy = 0.0;
+#pragma unroll
+    for (int j = 0; j < A; j++)
+        if ((kept >> j) & 1u) {
+            sx += f2[j].x;
+            sy += f2[j].y;
+        }
+    const double ix = (row < n) ? 1.0 / sx : 0.0, iy = (row + 1 < n) ? 1.0 / sy : 0.0;
+#pragma unroll
+    for (int j = 0; j < A; j++)
+        f2[j] = ((kept >> j) & 1u) ? make_double2(f2[j].x * ix, f2[j].y * iy) : make_double2(0.0, 0.0);
+}
+
 // column sum of the renormalised frequencies in pool order, NaN ignored (src/base/sync.rs:483-489)
 template <int A>
 __device__ __noinline__ double exact_colsum(const ScanParams &p, int64_t locus, int jsel, unsigned kept) {
@@ -958,9 +978,18 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool a
     double q[A];
 #pragma unroll
     for (int j = 0; j < A; j++) q[j] = 0.0;
+    bool deferred = false, kept_known = false;
     if (act && pre_kept) {
         status = PG_LOCUS_OK;
         kept = pre_kept;
+        if (DEFER) {
+            // streaming kernel under an ingest hint: the totals are those of the renormalised frequencies.  A pool
+            // without reads on the kept alleles made them NaN -- the NaN-aware accumulation is the fix-up kernel's
+            kept_known = true;
+#pragma unroll
+            for (int j = 0; j < A; j++)
+                if (((kept >> j) & 1u) && tg[AC::S0 + j] != tg[AC::S0 + j]) deferred = true;
+        }
     } else if (act) {
         if ((double)dm < p.min_depth_f) {
             status = PG_LOCUS_FILTERED;  // sync.rs:217-229
@@ -977,7 +1006,6 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool a
             }
         }
     }
-    bool deferred = false;
     if (DEFER) {
         if (exact_bits != 0u) deferred = true;
     } else {
@@ -1009,7 +1037,6 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool a
                 if (!((kept >> j) & 1u) && tg[AC::S0 + j] > 0.0) slow = true;  // a removed allele carries reads
         }
     }
-    bool kept_known = false;
     if (DEFER) {
         if (act && slow && status == PG_LOCUS_OK) {
             kept_known = !deferred && !slow_decide;  // the fix-up kernel can renormalise right away
@@ -1219,8 +1246,12 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const __grid_c
         const int64_t l0 = blk * G;
         const int cnt = (int)min((int64_t)G, L - l0);
         const unsigned dm = (lane < cnt) ? __ldg(p.dmin + l0 + lane) : 0xFFFFFFFFu;  // consumed by the epilogue
+        const unsigned hl = (lane < cnt) ? (unsigned)__ldg(p.hint + l0 + lane) : 0u;  // ingest hint (pg_ingest.cu)
         if (P == 32) {
             for (int g = 0; g < cnt; g++) {
+                const unsigned hk = __shfl_sync(PG_FULL_MASK, hl, g);
+                const bool hinted = (hk & 0x80u) != 0u;
+                const unsigned hkept = hk & 0x3fu;
                 double acc[AC::N];
 #pragma unroll
                 for (int i = 0; i < AC::N; i++) acc[i] = 0.0;
@@ -1241,6 +1272,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const __grid_c
                                 y2[k] = *reinterpret_cast<const double2 *>(yrow + (size_t)k * n_pad + it * 64);
                             double2 w2 = make_double2(0.0, 0.0);
                             if (W) w2 = *reinterpret_cast<const double2 *>(wrow + it * 64);
+                            if (hinted) renorm_pair<A>(f2, hkept, chunk * RC + it * 64 + 2 * lane, lay.n);
                             accum_pair<A, K, W>(acc, f2, y2, w2);
                         }
                     } else {
@@ -1254,6 +1286,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const __grid_c
                                 y2[k] = *reinterpret_cast<const double2 *>(ys + chunk * RC + (size_t)k * n_pad + r);
                             double2 w2 = make_double2(0.0, 0.0);
                             if (W) w2 = *reinterpret_cast<const double2 *>(ws + chunk * RC + r);
+                            if (hinted) renorm_pair<A>(f2, hkept, chunk * RC + r, lay.n);
                             accum_pair<A, K, W>(acc, f2, y2, w2);
                         }
                     }
@@ -1274,10 +1307,30 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const __grid_c
                 double acc[AC::N];
 #pragma unroll
                 for (int i = 0; i < AC::N; i++) acc[i] = 0.0;
+                const unsigned hk = __shfl_sync(PG_FULL_MASK, hl, min(s * LPS + u, 31));
+                const bool hinted = (hk & 0x80u) != 0u;
+                const unsigned hkept = hk & 0x3fu;
                 mbar_wait(&bars[buf], parity);
                 double *fb = reinterpret_cast<double *>(stage0 + (size_t)buf * p.stage_bytes);
-                if (s * LPS + u < cnt) {  // the stage holds only the loci that exist
-                    const double *fl = fb + (size_t)u * fstride;
+                const double *fl = fb + (size_t)u * fstride;
+                if (__any_sync(PG_FULL_MASK, hinted)) {  // rare: kept out of the steady-state loop below
+                    if (s * LPS + u < cnt) {
+#pragma unroll 1
+                        for (int r = 2 * q0; r < n_pad; r += 2 * P) {
+                            double2 f2[A], y2[K];
+#pragma unroll
+                            for (int j = 0; j < A; j++)
+                                f2[j] = *reinterpret_cast<const double2 *>(fl + (size_t)j * n_pad + r);
+#pragma unroll
+                            for (int k = 0; k < K; k++)
+                                y2[k] = *reinterpret_cast<const double2 *>(ys + (size_t)k * n_pad + r);
+                            double2 w2 = make_double2(0.0, 0.0);
+                            if (W) w2 = *reinterpret_cast<const double2 *>(ws + r);
+                            if (hinted) renorm_pair<A>(f2, hkept, r, lay.n);
+                            accum_pair<A, K, W>(acc, f2, y2, w2);
+                        }
+                    }
+                } else if (s * LPS + u < cnt) {  // the stage holds only the loci that exist
 #pragma unroll 2
                     for (int r = 2 * q0; r < n_pad; r += 2 * P) {
                         double2 f2[A], y2[K];
@@ -1299,7 +1352,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const __grid_c
                 }
             }
         }
-        epilogue<A, K, W, true>(sp, l0 + lane, lane < cnt, tot, ys, ws, lane, dm, 0u);
+        epilogue<A, K, W, true>(sp, l0 + lane, lane < cnt, tot, ys, ws, lane, dm, (hl & 0x80u) ? (hl & 0x3fu) : 0u);
     }
 }
 

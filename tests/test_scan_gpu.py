@@ -275,6 +275,37 @@ def test_error_reads_defer_most_loci(ctx, kind, n, L):
     print(st)
 
 
+@pytest.mark.parametrize("n,L,weighted", [(40, 4000, False), (100, 3000, True), (300, 1200, True), (1000, 400, False)])
+@pytest.mark.parametrize("kind", [pb.KIND_OLS, pb.KIND_CORR])
+def test_hinted_renormalisation(ctx, kind, n, L, weighted):
+    """the ingest hint lets the streaming kernel renormalise on the fly (8 / 16 / 32 lanes per locus, a partial last
+    row chunk at 300 pools, unequal pool sizes); a pool whose reads all sit on removed alleles makes the renormalised
+    frequencies NaN (0 / 0 in to_frequencies, src/base/sync.rs:166-192) and has to come out like the reference's."""
+    seed = 0x417 + n
+    counts = pb.synth_counts_host(seed, 0, L, n, 3)  # A/T/C
+    full = np.zeros((L, 5, n), dtype=np.uint32)
+    full[:, :3] = counts
+    rng = np.random.default_rng(seed)
+    full[:, 3] = (rng.random((L, n)) < 0.03).astype(np.uint32) * rng.integers(1, 3, (L, n)).astype(np.uint32)
+    full[:, 4] = (rng.random((L, n)) < 0.004).astype(np.uint32)
+    for l in range(7, L, 97):   # pool l % n keeps only stray reads on G
+        full[l, :, l % n] = 0
+        full[l, 3, l % n] = 4
+    phen = pb.synth_phen_host(seed, n, 2)
+    ps = (5.0 + (np.arange(n) % 5)) if weighted else np.ones(n)
+    tot = 0.0
+    for v in ps:
+        tot = tot + v
+    fs = _fs(np.array([v / tot for v in ps]), min_allele_frequency=0.002)
+    codes = np.array([0, 1, 2, 3, 5], dtype=np.uint8)
+    scan = pb.Scan(ctx, kind, fs, n, codes, phen)
+    dev = scan.run_counts(full)
+    scan.close()
+    st = H.compare_regression(kind, full, codes, phen, fs, dev, label=f"hinted n={n}")
+    assert st["ok"] > 0.7 * L
+    print(st)
+
+
 def test_missing_coverage_at_scale(ctx):
     """--min-coverage-depth 0 with pools without coverage at 300 pools: NaN frequencies, exact q, missingness"""
     n, A, k, L = 300, 4, 2, 1500
