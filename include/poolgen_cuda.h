@@ -195,6 +195,36 @@ int pg_kin_set_covariates(pg_kin *kin, const double *cov /* n_pools x m row-majo
 int pg_kin_covar_scan(pg_kin *kin, const double *phen, int k, int iters, float *ms_total, const double **beta,
                       const double **var, const double **pval);
 
+/* ---- the reference's CSV rows from the numeric records (host code, threads over locus ranges) -------
+ * Replaces the string building of the per-locus callbacks (src/gwas/ols.rs:255-275, src/gwas/correlation_test.rs:113-128,
+ * src/tables/chisq_test.rs:36-46, src/tables/fisher_exact_test.rs:118-129) and of ols_with_covariate
+ * (src/gwas/ols.rs:409-433): numbers as Rust's f64::to_string() prints them, rounded with
+ * parse_f64_roundup_and_own (src/base/helpers.rs:103-117) where the reference rounds.  Only loci with status
+ * PG_LOCUS_OK produce rows, in locus order (= file order within the chunk, src/base/sync.rs:953-967). */
+#define PG_KIND_OLS_KINSHIP 4 /* header selector only */
+typedef struct {
+    const uint64_t *positions;    /* [n_loci] */
+    const char *text;             /* the sync text chunk the loci were parsed from, or NULL */
+    const uint64_t *line_offsets; /* with text: [n_loci] byte offset of the locus' line (pg_batch_text_labels);
+                                     the chromosome is the text up to the first tab */
+    const char *const *chr_names; /* without text: table of NUL-terminated chromosome names ... */
+    const uint32_t *chr_index;    /* ... and [n_loci] indices into it */
+} pg_row_labels;
+/* the header line of the output file (src/base/sync.rs:766,950, src/gwas/ols.rs:409) */
+int pg_format_header(int kind, char *out, size_t capacity, size_t *n_bytes);
+/* rows of `res` (OLS / CORR / CHISQ / FISHER); *n_bytes = bytes written, or needed when capacity is too small
+ * (PG_ERR_ARG, nothing written) */
+int pg_format_rows(int kind, const pg_results *res, const pg_row_labels *labels, int n_threads, char *out,
+                   size_t capacity, size_t *n_bytes);
+/* rows of ols_iter_with_kinship: phenotype outer, column inner; beta / pval as pg_kin_covar_scan returns them
+ * ([k][n_columns]); chromosome / position / allele are indexed by the column ordinal exactly like
+ * src/gwas/ols.rs:421-424 indexes the label vectors of GenotypesAndPhenotypes (whose entry 0 is "intercept") */
+int pg_format_kinship_rows(int64_t n_columns, int k, const char *const *chromosome, const uint64_t *position,
+                           const char *const *allele, const double *beta, const double *pval, int n_threads,
+                           char *out, size_t capacity, size_t *n_bytes);
+/* one number: n_digits > 0 = parse_f64_roundup_and_own(x, n_digits), 0 = f64::to_string(); returns the length */
+int pg_format_f64(double x, int n_digits, char *out, size_t capacity);
+
 /* ---- synthetic workload, host side: identical bits to pg_batch_synth ------------ */
 int pg_synth_counts_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int n_pools, int n_alleles,
                          uint32_t *counts_out);

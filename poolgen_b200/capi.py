@@ -18,6 +18,7 @@ from .build import LIB_PATH
 
 PG_OK = 0
 KIND_OLS, KIND_CORR, KIND_CHISQ, KIND_FISHER = 0, 1, 2, 3
+KIND_OLS_KINSHIP = 4  # header selector of the writer only
 LOCUS_FILTERED, LOCUS_OK, LOCUS_FAILED, LOCUS_UNSUPPORTED, LOCUS_PANIC = 0, 1, 2, 3, 4
 MAX_ALLELES = 6
 MAX_SLOTS = 5
@@ -35,7 +36,7 @@ ABI_SYMBOLS = [
     "pg_kin_open", "pg_kin_close", "pg_kin_reset", "pg_kin_columns", "pg_kin_append_columns", "pg_kin_append_counts",
     "pg_kin_last_labels", "pg_kin_synth", "pg_kin_get_columns", "pg_kin_gram", "pg_kin_gram_time", "pg_kin_partial",
     "pg_kin_partial_get", "pg_kin_partial_set", "pg_kin_eig_select", "pg_kin_eigvals", "pg_kin_set_covariates",
-    "pg_kin_covar_scan",
+    "pg_kin_covar_scan", "pg_format_header", "pg_format_rows", "pg_format_kinship_rows", "pg_format_f64",
 ]
 
 
@@ -62,6 +63,16 @@ class _Results(C.Structure):
         ("meta", C.POINTER(C.c_uint64)),
         ("freq_mean", C.POINTER(C.c_double)),
         ("stats", C.POINTER(C.c_double)),
+    ]
+
+
+class _RowLabels(C.Structure):
+    _fields_ = [
+        ("positions", C.POINTER(C.c_uint64)),
+        ("text", C.c_char_p),
+        ("line_offsets", C.POINTER(C.c_uint64)),
+        ("chr_names", C.POINTER(C.c_char_p)),
+        ("chr_index", C.POINTER(C.c_uint32)),
     ]
 
 
@@ -131,6 +142,11 @@ def lib():
             "pg_kin_eigvals": (i, [vp, vp, i]),
             "pg_kin_set_covariates": (i, [vp, vp, i]),
             "pg_kin_covar_scan": (i, [vp, vp, i, i, C.POINTER(C.c_float), pvp, pvp, pvp]),
+            "pg_format_header": (i, [i, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+            "pg_format_rows": (i, [i, C.POINTER(_Results), C.POINTER(_RowLabels), i, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+            "pg_format_kinship_rows": (i, [i64, i, C.POINTER(C.c_char_p), vp, C.POINTER(C.c_char_p), vp, vp, i, vp,
+                                           C.c_size_t, C.POINTER(C.c_size_t)]),
+            "pg_format_f64": (i, [C.c_double, i, vp, C.c_size_t]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -176,6 +192,93 @@ class ScanResults:
             code = ((meta >> (16 + 8 * s)) & 0xFF).astype(np.uint8)
             alle[:, s] = np.where(s < n_out, code, 0xFF)
         return ScanResults(status, n_out, alle, fm, st)
+
+
+    def to_c(self):
+        """a pg_results over numpy copies of these records (for the writer); returns (struct, keep-alive tuple)"""
+        L = int(self.status.shape[0])
+        S = int(self.freq_mean.shape[1]) if self.freq_mean.ndim == 2 else 1
+        k = int(self.stats.shape[2]) if self.stats.ndim == 4 else 1
+        meta = self.status.astype(np.uint64) | (self.n_out.astype(np.uint64) << np.uint64(8))
+        for s in range(6):
+            code = np.where(s < self.n_out, self.alleles[:, s], 0).astype(np.uint64)
+            meta |= code << np.uint64(16 + 8 * s)
+        meta = np.ascontiguousarray(meta)
+        fm = np.ascontiguousarray(self.freq_mean, dtype=np.float64)
+        st = np.ascontiguousarray(self.stats, dtype=np.float64)
+        r = _Results(L, S, k, meta.ctypes.data_as(C.POINTER(C.c_uint64)), fm.ctypes.data_as(C.POINTER(C.c_double)),
+                     st.ctypes.data_as(C.POINTER(C.c_double)))
+        return r, (meta, fm, st)
+
+
+def format_header(kind: int) -> bytes:
+    """the header line of the reference's output file (src/base/sync.rs:766,950, src/gwas/ols.rs:409)"""
+    buf = C.create_string_buffer(128)
+    n = C.c_size_t()
+    _check(lib().pg_format_header(int(kind), buf, 128, C.byref(n)), None, "pg_format_header")
+    return buf.raw[:n.value]
+
+
+def format_f64(x: float, n_digits: int = 0) -> str:
+    """f64::to_string() (n_digits = 0) or parse_f64_roundup_and_own(x, n_digits) (src/base/helpers.rs:103-117)"""
+    buf = C.create_string_buffer(512)
+    n = lib().pg_format_f64(float(x), int(n_digits), buf, 512)
+    if n < 0:
+        raise PgError("pg_format_f64 failed")
+    return buf.raw[:n].decode()
+
+
+def format_rows(kind: int, results, positions, text: bytes | None = None, line_offsets=None, chr_names=None,
+                chr_index=None, n_threads: int = 0) -> bytes:
+    """CSV rows of the per-locus callbacks for a slab of records (`results`: ScanResults or the raw pg_results of
+    Scan.collect(copy=False)).  Chromosome names come from the sync text the loci were parsed from (text +
+    line_offsets, as Batch.upload_sync_text returns them) or from chr_names[chr_index[locus]]."""
+    keep = None
+    if isinstance(results, ScanResults):
+        results, keep = results.to_c()
+    pos = np.ascontiguousarray(positions, dtype=np.uint64)
+    lab = _RowLabels()
+    lab.positions = pos.ctypes.data_as(C.POINTER(C.c_uint64))
+    if text is not None:
+        off = np.ascontiguousarray(line_offsets, dtype=np.uint64)
+        lab.text = text
+        lab.line_offsets = off.ctypes.data_as(C.POINTER(C.c_uint64))
+    else:
+        names = (C.c_char_p * len(chr_names))(*[n.encode() if isinstance(n, str) else n for n in chr_names])
+        idx = np.ascontiguousarray(chr_index, dtype=np.uint32)
+        lab.chr_names = names
+        lab.chr_index = idx.ctypes.data_as(C.POINTER(C.c_uint32))
+    n_threads = n_threads or (os.cpu_count() or 1)
+    need = C.c_size_t()
+    rc = lib().pg_format_rows(int(kind), C.byref(results), C.byref(lab), n_threads, None, 0, C.byref(need))
+    if need.value == 0:
+        if rc != PG_OK:
+            raise PgError("pg_format_rows: bad arguments")
+        return b""
+    buf = C.create_string_buffer(need.value)
+    _check(lib().pg_format_rows(int(kind), C.byref(results), C.byref(lab), n_threads, buf, need.value, C.byref(need)),
+           None, "pg_format_rows")
+    del keep
+    return buf.raw[:need.value]
+
+
+def format_kinship_rows(chromosome, position, allele, beta, pval, n_threads: int = 0) -> bytes:
+    """rows of ols_with_covariate's writer (src/gwas/ols.rs:410-433): beta / pval [k, P]; the label sequences are
+    indexed by the column ordinal exactly like the reference indexes GenotypesAndPhenotypes' label vectors."""
+    b = np.ascontiguousarray(beta, dtype=np.float64)
+    p = np.ascontiguousarray(pval, dtype=np.float64)
+    k, P = b.shape
+    enc = lambda v: v.encode() if isinstance(v, str) else v
+    cn = (C.c_char_p * P)(*[enc(v) for v in chromosome[:P]])
+    an = (C.c_char_p * P)(*[enc(v) for v in allele[:P]])
+    pos = np.ascontiguousarray(position[:P], dtype=np.uint64)
+    n_threads = n_threads or (os.cpu_count() or 1)
+    need = C.c_size_t()
+    lib().pg_format_kinship_rows(P, k, cn, pos.ctypes.data, an, b.ctypes.data, p.ctypes.data, n_threads, None, 0, C.byref(need))
+    buf = C.create_string_buffer(max(1, need.value))
+    _check(lib().pg_format_kinship_rows(P, k, cn, pos.ctypes.data, an, b.ctypes.data, p.ctypes.data, n_threads, buf,
+                                        need.value, C.byref(need)), None, "pg_format_kinship_rows")
+    return buf.raw[:need.value]
 
 
 def _check(rc: int, ctx=None, what: str = ""):

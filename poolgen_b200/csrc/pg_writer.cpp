@@ -1,0 +1,333 @@
+// pg_writer.cpp -- the CSV rows of the reference's writers from the numeric records of a scan.
+// Host code (the text ends up in a host file either way; records are smaller than rows, so they cross PCIe):
+//   ols_iterate     src/gwas/ols.rs:255-275            chr,pos,allele,freq r8,Pheno_j,beta r6,p r12
+//   correlation     src/gwas/correlation_test.rs:113-128  chr,pos,allele,freq,Pheno_j,r r6,p
+//   chisq           src/tables/chisq_test.rs:36-46     chr,pos,alleles,chi2 r6,p
+//   fisher          src/tables/fisher_exact_test.rs:118-129  chr,pos,alleles,p_observed,p
+//   ols_with_covariate  src/gwas/ols.rs:409-433        chr,pos,allele,Pheno_j,beta,p  (phenotype outer, column inner)
+// Numbers follow Rust's `f64::to_string()` (shortest digits that round-trip, never an exponent, "NaN", "inf", "-0")
+// and src/base/helpers.rs:103-117 (`sensible_round`, `parse_f64_roundup_and_own`).  Loci are split over threads in
+// contiguous ranges; the pieces are concatenated in locus order, like the reference concatenates its chunk files
+// (src/base/sync.rs:953-967).
+#include <charconv>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "poolgen_cuda.h"
+
+namespace {
+
+const char kAlleleNames[6] = {'A', 'T', 'C', 'G', 'N', 'D'};  // src/base/sync.rs:134-137
+
+inline char *put_u64(uint64_t v, char *o) {
+    auto r = std::to_chars(o, o + 24, v);
+    return r.ptr;
+}
+
+// digits d[0..nd) with the decimal point after d[0] scaled by 10^e10 -> positional notation
+inline char *put_positional(bool neg, const char *d, int nd, int e10, char *o) {
+    if (neg) *o++ = '-';
+    if (e10 >= nd - 1) {
+        memcpy(o, d, (size_t)nd);
+        o += nd;
+        const int z = e10 - (nd - 1);
+        memset(o, '0', (size_t)z);
+        o += z;
+    } else if (e10 >= 0) {
+        memcpy(o, d, (size_t)e10 + 1);
+        o += e10 + 1;
+        *o++ = '.';
+        memcpy(o, d + e10 + 1, (size_t)(nd - e10 - 1));
+        o += nd - e10 - 1;
+    } else {
+        *o++ = '0';
+        *o++ = '.';
+        memset(o, '0', (size_t)(-e10 - 1));
+        o += -e10 - 1;
+        memcpy(o, d, (size_t)nd);
+        o += nd;
+    }
+    return o;
+}
+
+// Rust `Display for f64`: at most 1 + 1 + 324 + 17 characters
+char *put_f64(double x, char *o) {
+    if (x != x) {
+        memcpy(o, "NaN", 3);
+        return o + 3;
+    }
+    if (std::isinf(x)) {
+        if (x < 0) *o++ = '-';
+        memcpy(o, "inf", 3);
+        return o + 3;
+    }
+    if (x == 0.0) {
+        if (std::signbit(x)) *o++ = '-';
+        *o++ = '0';
+        return o;
+    }
+    char tmp[40];
+    auto r = std::to_chars(tmp, tmp + sizeof tmp, x, std::chars_format::scientific);  // shortest round-trip digits
+    const char *p = tmp;
+    bool neg = false;
+    if (*p == '-') {
+        neg = true;
+        p++;
+    }
+    char d[24];
+    int nd = 0;
+    for (; p < r.ptr && *p != 'e'; p++)
+        if (*p != '.') d[nd++] = *p;
+    p++;  // 'e'
+    bool eneg = false;
+    if (*p == '-') {
+        eneg = true;
+        p++;
+    } else if (*p == '+') {
+        p++;
+    }
+    int e10 = 0;
+    for (; p < r.ptr; p++) e10 = e10 * 10 + (*p - '0');
+    if (eneg) e10 = -e10;
+    while (nd > 1 && d[nd - 1] == '0') nd--;
+    return put_positional(neg, d, nd, e10, o);
+}
+
+struct Rounder {
+    int digits;
+    double factor;  // the correctly rounded parse of "1e<digits>" (helpers.rs:104-106)
+    explicit Rounder(int nd) : digits(nd) {
+        char f[16];
+        snprintf(f, sizeof f, "1e%d", nd);
+        factor = strtod(f, nullptr);
+    }
+    // parse_f64_roundup_and_own (helpers.rs:111-117)
+    char *put(double x, char *o) const {
+        const double y = x * factor;
+        if (std::fabs(y) < 9.0e14) {
+            // k = round(y) is an integer below 10^15: the shortest digits of k / factor ARE the decimal k / 10^digits
+            // (two different decimals of <= 15 significant digits never share a double), and an x whose own shortest
+            // form is shorter than `digits` characters has fewer than `digits` decimals, so rounding returns it
+            // unchanged -- the `s.len() < n_digits` shortcut of the reference cannot be observed in this range
+            const double kd = std::round(y);
+            if (kd == 0.0) {
+                // -0 survives the division (Rust prints "-0")
+                if (std::signbit(kd)) *o++ = '-';
+                *o++ = '0';
+                return o;
+            }
+            const bool neg = kd < 0;
+            uint64_t k = (uint64_t)(neg ? -kd : kd);
+            char d[24];
+            int nd = 0;
+            {
+                char rev[24];
+                int n = 0;
+                while (k) {
+                    rev[n++] = (char)('0' + k % 10);
+                    k /= 10;
+                }
+                while (n) d[nd++] = rev[--n];
+            }
+            const int e10 = nd - 1 - digits;
+            while (nd > 1 && d[nd - 1] == '0') nd--;
+            return put_positional(neg, d, nd, e10, o);
+        }
+        char tmp[400];
+        char *e = put_f64(x, tmp);
+        if ((int)(e - tmp) < digits) {
+            memcpy(o, tmp, (size_t)(e - tmp));
+            return o + (e - tmp);
+        }
+        return put_f64(std::round(y) / factor, o);
+    }
+};
+
+struct Labels {
+    const pg_row_labels *lab;
+    // chromosome text of locus l
+    inline void chr(int64_t l, const char *&s, size_t &n) const {
+        if (lab->text) {
+            s = lab->text + lab->line_offsets[l];
+            const char *t = s;
+            while (*t != '\t') t++;
+            n = (size_t)(t - s);
+        } else {
+            s = lab->chr_names[lab->chr_index[l]];
+            n = strlen(s);
+        }
+    }
+};
+
+void format_range(int kind, const pg_results *res, const pg_row_labels *lab, int64_t lo, int64_t hi, std::string &out) {
+    const Labels L{lab};
+    const int S = res->n_slots, k = res->n_phen;
+    const Rounder r6(6), r8(8), r12(12);
+    char line[1024];
+    out.reserve((size_t)(hi - lo) * 48);
+    for (int64_t l = lo; l < hi; l++) {
+        const uint64_t mv = res->meta[l];
+        if ((mv & 0xffu) != PG_LOCUS_OK) continue;  // None: no row (src/base/sync.rs:864-867)
+        const int n_out = (int)((mv >> 8) & 0xffu);
+        const char *cs;
+        size_t cn;
+        L.chr(l, cs, cn);
+        char head[320];
+        char *h = head;
+        if (cn > 256) cn = 256;
+        memcpy(h, cs, cn);
+        h += cn;
+        *h++ = ',';
+        h = put_u64(lab->positions[l], h);
+        *h++ = ',';
+        const size_t hn = (size_t)(h - head);
+        if (kind == PG_KIND_OLS || kind == PG_KIND_CORR) {
+            for (int s = 0; s < n_out && s < S; s++) {
+                const double fm = res->freq_mean[(size_t)l * S + s];
+                const char an = kAlleleNames[(mv >> (16 + 8 * s)) & 0xffu];
+                for (int j = 0; j < k; j++) {
+                    const double *st = res->stats + (((size_t)l * S + s) * k + j) * 4;
+                    char *o = line;
+                    memcpy(o, head, hn);
+                    o += hn;
+                    *o++ = an;
+                    *o++ = ',';
+                    o = (kind == PG_KIND_OLS) ? r8.put(fm, o) : put_f64(fm, o);
+                    memcpy(o, ",Pheno_", 7);
+                    o += 7;
+                    o = put_u64((uint64_t)j, o);
+                    *o++ = ',';
+                    o = r6.put(st[0], o);
+                    *o++ = ',';
+                    o = (kind == PG_KIND_OLS) ? r12.put(st[3], o) : put_f64(st[3], o);
+                    *o++ = '\n';
+                    out.append(line, (size_t)(o - line));
+                }
+            }
+        } else {
+            const double *st = res->stats + (size_t)l * 4;
+            char *o = line;
+            memcpy(o, head, hn);
+            o += hn;
+            for (int s = 0; s < n_out && s < PG_MAX_ALLELES; s++) *o++ = kAlleleNames[(mv >> (16 + 8 * s)) & 0xffu];
+            *o++ = ',';
+            o = (kind == PG_KIND_CHISQ) ? r6.put(st[0], o) : put_f64(st[0], o);
+            *o++ = ',';
+            o = put_f64(st[3], o);
+            *o++ = '\n';
+            out.append(line, (size_t)(o - line));
+        }
+    }
+}
+
+int emit(const std::vector<std::string> &parts, char *out, size_t capacity, size_t *n_bytes) {
+    size_t total = 0;
+    for (const auto &p : parts) total += p.size();
+    if (n_bytes) *n_bytes = total;
+    if (total > capacity || (!out && total)) return PG_ERR_ARG;
+    size_t o = 0;
+    for (const auto &p : parts) {
+        memcpy(out + o, p.data(), p.size());
+        o += p.size();
+    }
+    return PG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pg_format_header(int kind, char *out, size_t capacity, size_t *n_bytes) {
+    const char *h;
+    switch (kind) {
+        case PG_KIND_OLS:
+        case PG_KIND_CORR: h = "#chr,pos,alleles,freq,phenotype,statistic,pvalue\n"; break;  // src/base/sync.rs:950
+        case PG_KIND_CHISQ:
+        case PG_KIND_FISHER: h = "#chr,pos,alleles,statistic,pvalue\n"; break;               // src/base/sync.rs:766
+        case PG_KIND_OLS_KINSHIP: h = "#chr,pos,alleles,phenotype,statistic,pvalue\n"; break;  // src/gwas/ols.rs:409
+        default: return PG_ERR_ARG;
+    }
+    const size_t n = strlen(h);
+    if (n_bytes) *n_bytes = n;
+    if (n > capacity || !out) return PG_ERR_ARG;
+    memcpy(out, h, n);
+    return PG_OK;
+}
+
+int pg_format_rows(int kind, const pg_results *res, const pg_row_labels *labels, int n_threads, char *out,
+                   size_t capacity, size_t *n_bytes) {
+    if (!res || !labels || !labels->positions || kind < PG_KIND_OLS || kind > PG_KIND_FISHER) return PG_ERR_ARG;
+    if (labels->text ? !labels->line_offsets : (!labels->chr_names || !labels->chr_index)) return PG_ERR_ARG;
+    const int64_t L = res->n_loci;
+    if (L > 0 && (!res->meta || !res->stats)) return PG_ERR_ARG;
+    int T = n_threads < 1 ? 1 : n_threads;
+    if ((int64_t)T > (L + 4095) / 4096) T = (int)((L + 4095) / 4096);  // not worth a thread below 4,096 loci
+    if (T < 1) T = 1;
+    std::vector<std::string> parts((size_t)T);
+    if (T == 1) {
+        format_range(kind, res, labels, 0, L, parts[0]);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) {
+            const int64_t lo = L * t / T, hi = L * (t + 1) / T;
+            th.emplace_back([=, &parts] { format_range(kind, res, labels, lo, hi, parts[(size_t)t]); });
+        }
+        for (auto &x : th) x.join();
+    }
+    return emit(parts, out, capacity, n_bytes);
+}
+
+int pg_format_kinship_rows(int64_t n_columns, int k, const char *const *chromosome, const uint64_t *position,
+                           const char *const *allele, const double *beta, const double *pval, int n_threads,
+                           char *out, size_t capacity, size_t *n_bytes) {
+    if (n_columns < 0 || k < 0 || (n_columns > 0 && (!chromosome || !position || !allele || !beta || !pval)))
+        return PG_ERR_ARG;
+    const int64_t rows = n_columns * k;
+    int T = n_threads < 1 ? 1 : n_threads;
+    if ((int64_t)T > (rows + 8191) / 8192) T = (int)((rows + 8191) / 8192);
+    if (T < 1) T = 1;
+    std::vector<std::string> parts((size_t)T);
+    auto work = [&](int t) {
+        std::string &o = parts[(size_t)t];
+        const int64_t lo = rows * t / T, hi = rows * (t + 1) / T;
+        char num[420];
+        for (int64_t r = lo; r < hi; r++) {
+            const int64_t j = r / n_columns, i = r - j * n_columns;  // phenotype outer, column inner
+            o.append(chromosome[i]);
+            o.push_back(',');
+            o.append(num, (size_t)(put_u64(position[i], num) - num));
+            o.push_back(',');
+            o.append(allele[i]);
+            o.append(",Pheno_");
+            o.append(num, (size_t)(put_u64((uint64_t)j, num) - num));
+            o.push_back(',');
+            o.append(num, (size_t)(put_f64(beta[(size_t)j * n_columns + i], num) - num));
+            o.push_back(',');
+            o.append(num, (size_t)(put_f64(pval[(size_t)j * n_columns + i], num) - num));
+            o.push_back('\n');
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    return emit(parts, out, capacity, n_bytes);
+}
+
+int pg_format_f64(double x, int n_digits, char *out, size_t capacity) {
+    char tmp[420];
+    char *e = (n_digits > 0) ? Rounder(n_digits).put(x, tmp) : put_f64(x, tmp);
+    const size_t n = (size_t)(e - tmp);
+    if (!out || n + 1 > capacity) return PG_ERR_ARG;
+    memcpy(out, tmp, n);
+    out[n] = 0;
+    return (int)n;
+}
+
+}  // extern "C"

@@ -141,3 +141,63 @@ def test_host_text_generator_round_trip(ctx):
     b.close()
     scan.close()
     assert (rt.status == rc.status).all() and np.array_equal(rt.stats, rc.stats, equal_nan=True)
+
+
+@pytest.mark.parametrize("kind", [pb.KIND_OLS, pb.KIND_CORR, pb.KIND_CHISQ, pb.KIND_FISHER])
+def test_c1_text_in_csv_out(ctx, kind):
+    """the whole replaced stretch of `read_analyse_write` (src/base/sync.rs:788-970): sync text -> device parse -> scan
+    -> records -> pg_format_rows, against the lines the oracle's callbacks format for the same file.  Labels, row order
+    and row count are exact; Fisher rows are identical text; the other numbers agree within the parity tolerances
+    (a printed digit can differ where the device value sits within 1e-9 of a rounding boundary)."""
+    c1 = H.load_c1()
+    counts = c1["counts"]
+    L = counts.shape[0]
+    names = [str(s) for s in c1["chrom_names"]]
+    chroms = [names[i] for i in c1["chrom_idx"]]
+    pos = [int(p) for p in c1["pos"]]
+    text = _sync_text(counts, chroms, pos)
+    regression = kind in (pb.KIND_OLS, pb.KIND_CORR)
+    phen = c1["phen"] if regression else None
+    fs = pb.FilterStats(pool_sizes=c1["pool_sizes"])
+    scan = pb.Scan(ctx, kind, fs, 5, c1["codes"], phen)
+    b = scan.batch(L)
+    nl, off, p = b.upload_sync_text(text)
+    b.run()
+    rec = b.fetch()
+    b.close()
+    scan.close()
+    got = pb.format_rows(kind, rec, p, text=text, line_offsets=off, n_threads=4).decode()
+    ofs = H.oracle_fs(fs)
+    expect = []
+    for l in range(L):
+        c = counts[l].T.astype(np.uint64)
+        if kind == pb.KIND_OLS:
+            expect.append(pgo.format_ols_lines(chroms[l], pos[l], pgo.ols_iterate(c, c1["codes"], phen, ofs)))
+        elif kind == pb.KIND_CORR:
+            expect.append(pgo.format_corr_lines(chroms[l], pos[l], pgo.correlation(c, c1["codes"], phen, ofs)))
+        elif kind == pb.KIND_CHISQ:
+            expect.append(pgo.format_chisq_line(chroms[l], pos[l], pgo.chisq(c, c1["codes"], ofs)))
+        else:
+            expect.append(pgo.format_fisher_line(chroms[l], pos[l], pgo.fisher(c, c1["codes"], ofs)))
+    expect = "".join(expect)
+    if kind == pb.KIND_FISHER:
+        assert got == expect
+        return
+    gl, el = got.strip().split("\n"), expect.strip().split("\n")
+    assert len(gl) == len(el) > 6000
+    n_text = 3 if not regression else 3
+    same = 0
+    for g, e in zip(gl, el):
+        if g == e:
+            same += 1
+            continue
+        gf, ef = g.split(","), e.split(",")
+        assert len(gf) == len(ef)
+        for i, (a, b_) in enumerate(zip(gf, ef)):
+            if i < n_text or a.startswith("Pheno_"):
+                assert a == b_, (g, e)
+            else:
+                x, y = float(a), float(b_)
+                assert (x != x and y != y) or abs(x - y) <= 2e-6 * max(abs(x), abs(y)) + 1.1e-6, (g, e)
+    assert same >= 0.97 * len(el), (same, len(el))
+    print(f"kind {kind}: {same} of {len(el)} rows identical text")
