@@ -335,45 +335,89 @@ def c5_numbers(ctx, pb):
     return out
 
 
-def text_numbers(ctx, pb):
-    """end to end from sync TEXT in pinned host memory (what the reference's reader threads start from) to
-    records on the host: H2D of the raw text, device-side parse, ingest, scan, D2H.  C3 shape, slabs of 4,096 loci."""
-    slab, n_slabs = 4096, 12
+def text_numbers(ctx, pb, n_threads=2):
+    """SURVEY 8f-1 + 8f-2: the whole stretch of `read_analyse_write` the library replaces, end to end from sync TEXT in
+    pinned host memory (what the reference's reader threads start from) to (a) records on the host and (b) the CSV rows
+    of the reference's writer: H2D of the raw text, device-side parse, ingest, scan, D2H, pg_format_rows.  C3 shape,
+    slabs of 4,096 loci, `n_threads` reader threads with one scan handle each (the reference runs one reader per file
+    chunk, src/base/sync.rs:917-939) so that one thread's host synchronisation overlaps another's copy."""
+    import ctypes as C
+    import threading
+    import torch
+    slab, slabs_per_thread = 4096, 8
     per_locus_cap = 16 + N_POOLS * 24
     host, hptr = ctx.pinned_empty((2, slab * per_locus_cap), np.uint8)
     nbytes = [pb.synth_sync_text_host(SEED, i * slab, slab, N_POOLS, N_ALLELES, host[i]) for i in range(2)]
     phen = pb.synth_phen_host(SEED, N_POOLS, N_PHEN)
     fs = pb.FilterStats(pool_sizes=np.full(N_POOLS, 1.0 / N_POOLS))
-    scan = pb.Scan(ctx, pb.KIND_OLS, fs, N_POOLS, np.arange(6, dtype=np.uint8), phen)
-    scan.stream_begin(slab)
-    import ctypes as C
     lib = pb.capi.lib()
+    scans = [pb.Scan(ctx, pb.KIND_OLS, fs, N_POOLS, np.arange(6, dtype=np.uint8), phen) for _ in range(n_threads)]
+    for sc in scans:
+        sc.stream_begin(slab)
+    cap = slab * N_PHEN * 3 * 96
+    outs = [C.create_string_buffer(cap) for _ in range(n_threads)]
+    fmt_threads = max(1, (os.cpu_count() or 1) // n_threads)
+    rows = [0] * n_threads
 
-    def submit(i):
-        t, n = C.c_int(), C.c_int64()
-        rc = lib.pg_scan_submit_sync_text(scan._h, host[i % 2].ctypes.data, nbytes[i % 2], C.byref(t), C.byref(n))
-        assert rc == 0 and n.value == slab, (rc, n.value)
-        return t.value
-    for i in range(3):
-        scan.collect(submit(i), copy=False)
-    import torch
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    pending = []
-    for i in range(n_slabs):
-        pending.append(submit(i))
-        if len(pending) == 3:
-            scan.collect(pending.pop(0), copy=False)
-    while pending:
-        scan.collect(pending.pop(0), copy=False)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    scan.close()
+    def reader(t, n_slabs, to_csv):
+        sc = scans[t]
+        pending = []
+
+        def finish(item):
+            ticket, i = item
+            r = sc.collect(ticket, copy=False)
+            assert r.n_loci == slab, r.n_loci
+            if not to_csv:
+                return
+            po, pp = C.c_void_p(), C.c_void_p()
+            assert lib.pg_scan_text_labels(sc._h, int(ticket), C.byref(po), C.byref(pp)) == 0
+            lab = pb.capi._RowLabels()
+            lab.positions = C.cast(pp, C.POINTER(C.c_uint64))
+            lab.text = C.cast(host[i % 2].ctypes.data, C.c_char_p)
+            lab.line_offsets = C.cast(po, C.POINTER(C.c_uint64))
+            nb = C.c_size_t()
+            rc = lib.pg_format_rows(pb.KIND_OLS, C.byref(r), C.byref(lab), fmt_threads, outs[t], cap, C.byref(nb))
+            assert rc == 0, rc
+            rows[t] += nb.value
+
+        for i in range(n_slabs):
+            tk = C.c_int()
+            rc = lib.pg_scan_submit_sync_text(sc._h, host[i % 2].ctypes.data, nbytes[i % 2], C.byref(tk), None)
+            assert rc == 0, rc
+            pending.append((tk.value, i))
+            if len(pending) == 3:
+                finish(pending.pop(0))
+        while pending:
+            finish(pending.pop(0))
+
+    def timed(n_slabs, to_csv):
+        th = [threading.Thread(target=reader, args=(t, n_slabs, to_csv)) for t in range(n_threads)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    timed(3, True)
+    dt_rec = timed(slabs_per_thread, False)
+    rows[:] = [0] * n_threads
+    dt_csv = timed(slabs_per_thread, True)
+    for sc in scans:
+        sc.close()
     ctx.pinned_free(hptr)
-    return {"e2e_sync_text": {"loci_per_s": slab * n_slabs / dt, "text_bytes_per_locus": nbytes[0] / slab,
-                              "text_gb_per_s": sum(nbytes[i % 2] for i in range(n_slabs)) / dt / 1e9,
-                              "note": "pinned sync text -> H2D -> device parse -> ingest -> scan -> D2H records, "
-                                      f"{N_POOLS} pools, slabs of {slab} loci"}}
+    n_loci = slab * slabs_per_thread * n_threads
+    text_bytes = sum(nbytes[i % 2] for i in range(slabs_per_thread)) * n_threads
+    note = (f"{N_POOLS} pools, slabs of {slab} loci, {n_threads} reader threads x depth-3 pipeline; "
+            "pinned sync text -> H2D -> device parse -> ingest -> scan -> D2H records")
+    return {"e2e_sync_text": {"loci_per_s": n_loci / dt_rec, "text_bytes_per_locus": nbytes[0] / slab,
+                              "text_gb_per_s": text_bytes / dt_rec / 1e9, "note": note},
+            "e2e_text_to_csv": {"loci_per_s": n_loci / dt_csv, "text_gb_per_s": text_bytes / dt_csv / 1e9,
+                                "csv_bytes": int(sum(rows)), "csv_gb_per_s": sum(rows) / dt_csv / 1e9,
+                                "format_threads": fmt_threads * n_threads,
+                                "note": note + " -> pg_format_rows (the reference's CSV rows)"}}
 
 
 FP64_DMMA_PEAK_TFLOPS = 37.1  # tools/fp64_probe.cu on this pool's B200 (profiles/fp64_probe_r1.txt): mma.sync m8n8k4 f64

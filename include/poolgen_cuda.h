@@ -154,8 +154,15 @@ int pg_scan_submit_counts(pg_scan *scan, const uint32_t *counts, int64_t n_loci,
 int pg_scan_submit_counts_u16(pg_scan *scan, const uint16_t *counts, int64_t n_loci, int *ticket);
 int pg_scan_submit_counts_u8(pg_scan *scan, const uint8_t *counts, int64_t n_loci, int *ticket);
 int pg_scan_submit_freq(pg_scan *scan, const double *freq, const uint32_t *depth, int64_t n_loci, int *ticket);
+/* text slabs: the copy and the device-side parse are enqueued and the call returns; the scan of a slab is launched by
+ * the NEXT submit (or by its collect), once the parse has told the host how many loci the chunk holds -- so the copy of
+ * slab i+1 overlaps the parse of slab i.  `text` must stay valid and unchanged until the ticket has been collected.
+ * n_loci may be NULL; when it is not, the call waits for this slab's parse (no deferral).  Errors of a deferred slab
+ * (pool count, malformed field) surface from the call that finishes it. */
 int pg_scan_submit_sync_text(pg_scan *scan, const char *text, size_t n_bytes, int *ticket, int64_t *n_loci);
 int pg_scan_collect(pg_scan *scan, int ticket, pg_results *out);
+/* labels of a slab submitted as text (see pg_batch_text_labels), valid until the ticket's slab is submitted again */
+int pg_scan_text_labels(pg_scan *scan, int ticket, const uint64_t **line_offsets, const uint64_t **positions);
 
 /* ---- ols_iter_with_kinship: ols_with_covariate (src/gwas/ols.rs:278-436) over a device-resident block of allele
  * columns of GenotypesAndPhenotypes.intercept_and_allele_frequencies[:, 1..] (src/base/sync.rs:1106-1179).

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "pg_scan_submit_sync_text", "pg_batch_synth",
     "pg_batch_run", "pg_batch_download", "pg_batch_sync", "pg_batch_results", "pg_batch_time_runs",
     "pg_batch_bytes", "pg_scan_stream_begin", "pg_scan_submit_counts", "pg_scan_submit_counts_u16",
-    "pg_scan_submit_counts_u8", "pg_scan_submit_freq", "pg_scan_collect", "pg_synth_counts_host", "pg_synth_phen_host", "pg_synth_sync_text_host",
+    "pg_scan_submit_counts_u8", "pg_scan_submit_freq", "pg_scan_collect", "pg_scan_text_labels", "pg_synth_counts_host", "pg_synth_phen_host", "pg_synth_sync_text_host",
     "pg_kin_open", "pg_kin_close", "pg_kin_reset", "pg_kin_columns", "pg_kin_append_columns", "pg_kin_append_counts",
     "pg_kin_last_labels", "pg_kin_synth", "pg_kin_get_columns", "pg_kin_gram", "pg_kin_gram_time", "pg_kin_partial",
     "pg_kin_partial_get", "pg_kin_partial_set", "pg_kin_eig_select", "pg_kin_eigvals", "pg_kin_set_covariates",
@@ -121,6 +121,7 @@ def lib():
             "pg_scan_submit_counts_u8": (i, [vp, vp, i64, C.POINTER(i)]),
             "pg_scan_submit_freq": (i, [vp, vp, vp, i64, C.POINTER(i)]),
             "pg_scan_collect": (i, [vp, i, C.POINTER(_Results)]),
+            "pg_scan_text_labels": (i, [vp, i, pvp, pvp]),
             "pg_synth_counts_host": (i, [u64, i64, i64, i, i, vp]),
             "pg_synth_phen_host": (i, [u64, i, i, vp]),
             "pg_synth_sync_text_host": (i, [u64, i64, i64, i, i, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -582,13 +583,29 @@ class Kinship:
             self._h = C.c_void_p()
 
 
-def submit_sync_text(scan: "Scan", text: bytes):
-    """pg_scan_submit_sync_text: parse + scan + download of one text slab; returns (ticket, n_loci)"""
+def submit_sync_text(scan: "Scan", text: bytes, deferred: bool = False):
+    """pg_scan_submit_sync_text: parse + scan + download of one text slab; returns (ticket, n_loci).
+    deferred=True passes n_loci = NULL: the call only enqueues the copy and the parse (n_loci comes back as None, the
+    count is in the collected records) and the slab's scan is launched by the next submit or by its collect."""
     t, n = C.c_int(), C.c_int64()
     buf = bytes(text)
-    scan._keep_text = buf
-    _check(lib().pg_scan_submit_sync_text(scan._h, buf, len(buf), C.byref(t), C.byref(n)), scan.ctx._h, "pg_scan_submit_sync_text")
-    return t.value, int(n.value)
+    if not hasattr(scan, "_keep_text"):
+        scan._keep_text = {}
+    _check(lib().pg_scan_submit_sync_text(scan._h, buf, len(buf), C.byref(t), None if deferred else C.byref(n)),
+           scan.ctx._h, "pg_scan_submit_sync_text")
+    scan._keep_text[t.value] = buf  # the chunk must stay alive until its ticket is collected
+    return t.value, (None if deferred else int(n.value))
+
+
+def text_labels(scan: "Scan", ticket: int, n_loci: int):
+    """pg_scan_text_labels after the collect of `ticket`: (line byte offsets, positions) of its loci"""
+    po, pp = C.c_void_p(), C.c_void_p()
+    _check(lib().pg_scan_text_labels(scan._h, int(ticket), C.byref(po), C.byref(pp)), scan.ctx._h, "pg_scan_text_labels")
+    if n_loci == 0:
+        return np.zeros(0, np.uint64), np.zeros(0, np.uint64)
+    off = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(n_loci,)).copy()
+    pos = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_uint64)), shape=(n_loci,)).copy()
+    return off, pos
 
 
 def synth_counts_host(seed: int, first_locus: int, n_loci: int, n_pools: int, n_alleles: int) -> np.ndarray:

@@ -427,7 +427,8 @@ int pg_batch_upload_freq(pg_batch *b, const double *freq, const uint32_t *depth,
     return PG_OK;
 }
 
-int pg_batch_upload_sync_text(pg_batch *b, const char *text, size_t n_bytes, int64_t *n_loci_out) {
+// stage A of a text upload: copy + device parse, asynchronous (pg_text.cu)
+static int text_stage_a(pg_batch *b, const char *text, size_t n_bytes, size_t line_cap) {
     if (!b || (!text && n_bytes > 0)) return PG_ERR_ARG;
     pg_scan *s = b->scan;
     pg_ctx *ctx = s->ctx;
@@ -435,25 +436,51 @@ int pg_batch_upload_sync_text(pg_batch *b, const char *text, size_t n_bytes, int
     for (int j = 0; j < 6; j++)
         if (s->codes_in[j] != j) return fail(ctx, PG_ERR_ARG, "upload_sync_text: allele codes must be 0..5 in sync order");
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (n_loci_out) *n_loci_out = 0;
     b->n_loci = 0;
     b->have_input = 1;
     b->input_is_counts = 1;
+    b->text_src = text;
+    b->text_bytes = n_bytes;
     int rc = ensure_stage(b, (size_t)b->cap * 6 * s->n * 4);
     if (rc) return rc;
+    PG_CUDA(ctx, pg::text_parse_async(&b->text, text, n_bytes, s->n, (uint32_t *)b->d_stage, b->cap, line_cap,
+                                      ctx->sm_count, b->stream));
+    return PG_OK;
+}
+
+// stage B: wait for the parse, learn the number of loci, enqueue the label copy and the ingest
+static int text_stage_b(pg_batch *b, int64_t *n_loci_out) {
+    pg_scan *s = b->scan;
+    pg_ctx *ctx = s->ctx;
+    if (n_loci_out) *n_loci_out = 0;
     cudaError_t ce = cudaSuccess;
     uint64_t at = 0;
-    const int64_t L = pg::text_to_counts(&b->text, text, n_bytes, s->n, (uint32_t *)b->d_stage, b->cap, ctx->sm_count,
-                                         b->stream, &ce, &at);
+    int64_t L = pg::text_parse_finish(b->text, b->stream, &ce, &at);
+    if (L == -5) {  // more (comment / blank) lines than the default bound: repeat with the exact number
+        int rc = text_stage_a(b, b->text_src, b->text_bytes, (size_t)at + 1);
+        if (rc) return rc;
+        L = pg::text_parse_finish(b->text, b->stream, &ce, &at);
+    }
     if (L == -1) return fail(ctx, PG_ERR_CUDA, "upload_sync_text: %s", cudaGetErrorString(ce));
     if (L == -2) return fail(ctx, PG_ERR_ARG, "upload_sync_text: more loci in the chunk than the batch capacity %lld", (long long)b->cap);
     if (L == -3) return fail(ctx, PG_ERR_ARG, "upload_sync_text: the line at byte %llu does not hold %d pools (the reference asserts the pool count, src/base/sync.rs:254-257)", (unsigned long long)at, s->n);
     if (L == -4) return fail(ctx, PG_ERR_ARG, "upload_sync_text: malformed pool field at byte %llu (the reference panics: allele counts are not valid integers, src/base/sync.rs:146)", (unsigned long long)at);
+    if (L < 0) return fail(ctx, PG_ERR_ARG, "upload_sync_text: the chunk could not be parsed (%lld)", (long long)L);
     b->n_loci = L;
     if (n_loci_out) *n_loci_out = L;
     if (L > 0 && is_regression(s))
         PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, L, s->n, s->A_in, s->drop_col, s->lay,
                                            ingest_out(b, 0), b->stream));
+    return PG_OK;
+}
+
+int pg_batch_upload_sync_text(pg_batch *b, const char *text, size_t n_bytes, int64_t *n_loci_out) {
+    if (n_loci_out) *n_loci_out = 0;
+    int rc = text_stage_a(b, text, n_bytes, 0);
+    if (rc) return rc;
+    rc = text_stage_b(b, n_loci_out);
+    if (rc) return rc;
+    PG_CUDA(b->scan->ctx, cudaStreamSynchronize(b->stream));  // the labels are on the host when this returns
     return PG_OK;
 }
 
@@ -718,17 +745,38 @@ int pg_scan_submit_freq(pg_scan *s, const double *freq, const uint32_t *depth, i
     if ((rc = pg_batch_run(b))) return rc;
     return pg_batch_download(b);
 }
+// a slab submitted as text whose parse has been enqueued but whose scan has not: finish it (stage B, scan, download)
+static int finish_text_slab(pg_scan *s, int slab, int64_t *n_loci) {
+    pg_batch *b = s->slabs[slab];
+    if (!b || !pg::text_parse_pending(b->text)) return PG_OK;
+    int rc = text_stage_b(b, n_loci);
+    if (rc) return rc;
+    if ((rc = pg_batch_run(b))) return rc;
+    return pg_batch_download(b);
+}
 int pg_scan_submit_sync_text(pg_scan *s, const char *text, size_t n_bytes, int *ticket, int64_t *n_loci) {
     pg_batch *b = nullptr;
     int rc = submit_common(s, ticket, &b);
     if (rc) return rc;
-    if ((rc = pg_batch_upload_sync_text(b, text, n_bytes, n_loci))) return rc;
-    if ((rc = pg_batch_run(b))) return rc;
-    return pg_batch_download(b);
+    // the copy + parse of this slab is enqueued BEFORE the host waits for the previous slab's parse, so the copy
+    // engine never idles; the previous slab's scan is launched as soon as its locus count is known
+    if ((rc = text_stage_a(b, text, n_bytes, 0))) return rc;
+    for (int i = 1; i < PG_STREAM_DEPTH; i++) {
+        const int prev = (*ticket + i) % PG_STREAM_DEPTH;  // oldest first
+        if ((rc = finish_text_slab(s, prev, nullptr))) return rc;
+    }
+    if (n_loci) return finish_text_slab(s, *ticket, n_loci);  // the caller wants the count now: no deferral
+    return PG_OK;
+}
+int pg_scan_text_labels(pg_scan *s, int ticket, const uint64_t **line_offsets, const uint64_t **positions) {
+    if (!s || ticket < 0 || ticket >= PG_STREAM_DEPTH || !s->slabs[ticket]) return PG_ERR_ARG;
+    return pg_batch_text_labels(s->slabs[ticket], line_offsets, positions);
 }
 int pg_scan_collect(pg_scan *s, int ticket, pg_results *out) {
     if (!s || ticket < 0 || ticket >= PG_STREAM_DEPTH || !s->slabs[ticket]) return PG_ERR_ARG;
-    int rc = pg_batch_sync(s->slabs[ticket]);
+    int rc = finish_text_slab(s, ticket, nullptr);
+    if (rc) return rc;
+    rc = pg_batch_sync(s->slabs[ticket]);
     if (rc) return rc;
     return pg_batch_results(s->slabs[ticket], out);
 }

@@ -10,30 +10,44 @@
 
 namespace pg {
 
-// lanes of the warp that hold the same locus fold their depths, one atomic per (warp, locus)
-__device__ __forceinline__ void fold_dmin(uint32_t *dmin, int64_t locus, uint32_t d) {
-    const unsigned active = __activemask();
-    const unsigned peers = __match_any_sync(active, (unsigned long long)locus);
-    const unsigned m = __reduce_min_sync(peers, d);
-    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicMin(dmin + locus, m);
+// per-locus pooled frequencies q_j = sum_i f_ij w_i (NaN skipped): the lanes of a warp that hold the same locus are
+// contiguous, so a segmented shuffle reduction leaves the sum of every run in its first lane, which issues ONE atomic
+// per (warp, locus, allele).  Must be called by all 32 lanes at a convergent point (locus = -1 for lanes without a
+// row).  The sums only feed the renormalisation HINT of the scan, never a decision on their own.
+__device__ __forceinline__ void fold_q(double *qbuf, int64_t locus, int A, const double *fw) {
+    const int lane = threadIdx.x & 31;
+    const int64_t up = __shfl_up_sync(0xFFFFFFFFu, locus, 1);
+    const bool head = lane == 0 || up != locus;
+    bool same[5];
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int64_t other = __shfl_down_sync(0xFFFFFFFFu, locus, 1 << s);
+        same[s] = (lane + (1 << s) < 32) && other == locus;
+    }
+    for (int j = 0; j < A; j++) {
+        double v = fw[j];
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            const double t = __shfl_down_sync(0xFFFFFFFFu, v, 1 << s);
+            if (same[s]) v += t;
+        }
+        if (head && locus >= 0 && v != 0.0) atomicAdd(qbuf + (size_t)locus * A + j, v);
+    }
 }
 
-// per-locus pooled frequencies q_j = sum_i f_ij w_i (NaN skipped), accumulated with one atomic per (warp, locus,
-// allele) where a warp holds one locus; they only feed the renormalisation HINT of the scan, never a decision
-__device__ __forceinline__ void fold_q(double *qbuf, int64_t locus, int A, const double *fw) {
-    const unsigned active = __activemask();
-    const unsigned peers = __match_any_sync(active, (unsigned long long)locus);
-    if (peers == 0xFFFFFFFFu) {
-        for (int j = 0; j < A; j++) {
-            double v = fw[j];
+// the same for the smallest depth of the locus
+__device__ __forceinline__ void fold_dmin(uint32_t *dmin, int64_t locus, uint32_t d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t up = __shfl_up_sync(0xFFFFFFFFu, locus, 1);
+    const bool head = lane == 0 || up != locus;
+    uint32_t v = d;
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
-            if ((threadIdx.x & 31) == 0) atomicAdd(qbuf + (size_t)locus * A + j, v);
-        }
-    } else {
-        for (int j = 0; j < A; j++)
-            if (fw[j] != 0.0) atomicAdd(qbuf + (size_t)locus * A + j, fw[j]);
+    for (int s = 0; s < 5; s++) {
+        const int64_t other = __shfl_down_sync(0xFFFFFFFFu, locus, 1 << s);
+        const uint32_t t = __shfl_down_sync(0xFFFFFFFFu, v, 1 << s);
+        if ((lane + (1 << s) < 32) && other == locus) v = min(v, t);
     }
+    if (head && locus >= 0) atomicMin(dmin + locus, v);
 }
 
 // hint of a locus: bit 7 = "renormalise over the alleles in bits 0..5": every pool has coverage, the depth filter
@@ -71,39 +85,42 @@ __global__ void __launch_bounds__(256) ingest_counts_kernel(const CT *__restrict
                                                             uint32_t *__restrict__ dmin, double *__restrict__ qbuf,
                                                             const double *__restrict__ w) {
     const int64_t total = n_loci * lay.n_pad;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+    // the whole warp stays in the loop: the folds at the end shuffle across all 32 lanes
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx - (int64_t)(threadIdx.x & 31) < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t locus = idx / lay.n_pad;
-        const int i = (int)(idx - locus * lay.n_pad);
-        double *fl = freq + (size_t)locus * lay.freq_stride();
-        if (i >= n) {
-            for (int j = 0; j < lay.A; j++) fl[lay.freq_off(i, j)] = 0.0;
-            depth[(size_t)locus * lay.n_pad + i] = 0xFFFFFFFFu;
-            fold_dmin(dmin, locus, 0xFFFFFFFFu);
-            double zero[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
-            fold_q(qbuf, locus, lay.A, zero);
-            continue;
-        }
-        const CT *cl = counts + (size_t)locus * A_in * n + i;
-        uint32_t c[PG_MAX_ALLELES];
-        uint64_t d = 0;
-        int jj = 0;
-        for (int j = 0; j < A_in; j++) {
-            if (j == drop_col) continue;
-            c[jj] = (uint32_t)cl[(size_t)j * n];
-            d += c[jj];
-            jj++;
-        }
-        if (d > 0xFFFFFFFEull) d = 0xFFFFFFFEull;  // documented limit: per-pool depth < 2^32 - 1
-        const double dd = (double)d, wi = w[i];
+        int64_t locus = -1;
+        uint32_t dfold = 0xFFFFFFFFu;
         double fw[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < lay.A; j++) {
-            const double f = (d == 0) ? nan("") : (double)c[j] / dd;
-            fl[lay.freq_off(i, j)] = f;
-            fw[j] = (d == 0) ? 0.0 : f * wi;
+        if (idx < total) {
+            locus = idx / lay.n_pad;
+            const int i = (int)(idx - locus * lay.n_pad);
+            double *fl = freq + (size_t)locus * lay.freq_stride();
+            if (i >= n) {  // padding row
+                for (int j = 0; j < lay.A; j++) fl[lay.freq_off(i, j)] = 0.0;
+                depth[(size_t)locus * lay.n_pad + i] = 0xFFFFFFFFu;
+            } else {
+                const CT *cl = counts + (size_t)locus * A_in * n + i;
+                uint32_t c[PG_MAX_ALLELES];
+                uint64_t d = 0;
+                int jj = 0;
+                for (int j = 0; j < A_in; j++) {
+                    if (j == drop_col) continue;
+                    c[jj] = (uint32_t)cl[(size_t)j * n];
+                    d += c[jj];
+                    jj++;
+                }
+                if (d > 0xFFFFFFFEull) d = 0xFFFFFFFEull;  // documented limit: per-pool depth < 2^32 - 1
+                const double dd = (double)d, wi = w[i];
+                for (int j = 0; j < lay.A; j++) {
+                    const double f = (d == 0) ? nan("") : (double)c[j] / dd;
+                    fl[lay.freq_off(i, j)] = f;
+                    fw[j] = (d == 0) ? 0.0 : f * wi;
+                }
+                depth[(size_t)locus * lay.n_pad + i] = (uint32_t)d;
+                dfold = (uint32_t)d;
+            }
         }
-        depth[(size_t)locus * lay.n_pad + i] = (uint32_t)d;
-        fold_dmin(dmin, locus, (uint32_t)d);
+        fold_dmin(dmin, locus, dfold);
         fold_q(qbuf, locus, lay.A, fw);
     }
 }
@@ -114,21 +131,25 @@ __global__ void __launch_bounds__(256) ingest_freq_kernel(const double *__restri
                                                           uint32_t *__restrict__ dmin, double *__restrict__ qbuf,
                                                           const double *__restrict__ w) {
     const int64_t total = n_loci * lay.n_pad;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx - (int64_t)(threadIdx.x & 31) < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t locus = idx / lay.n_pad;
-        const int i = (int)(idx - locus * lay.n_pad);
-        double *fl = freq + (size_t)locus * lay.freq_stride();
-        const bool pad = i >= n;
+        int64_t locus = -1;
+        uint32_t dfold = 0xFFFFFFFFu;
         double fw[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < lay.A; j++) {
-            const double f = pad ? 0.0 : fin[((size_t)locus * lay.A + j) * n + i];
-            fl[lay.freq_off(i, j)] = f;
-            fw[j] = (pad || f != f) ? 0.0 : f * w[i];
+        if (idx < total) {
+            locus = idx / lay.n_pad;
+            const int i = (int)(idx - locus * lay.n_pad);
+            double *fl = freq + (size_t)locus * lay.freq_stride();
+            const bool pad = i >= n;
+            for (int j = 0; j < lay.A; j++) {
+                const double f = pad ? 0.0 : fin[((size_t)locus * lay.A + j) * n + i];
+                fl[lay.freq_off(i, j)] = f;
+                fw[j] = (pad || f != f) ? 0.0 : f * w[i];
+            }
+            dfold = pad ? 0xFFFFFFFFu : din[(size_t)locus * n + i];
+            depth[(size_t)locus * lay.n_pad + i] = dfold;
         }
-        const uint32_t d = pad ? 0xFFFFFFFFu : din[(size_t)locus * n + i];
-        depth[(size_t)locus * lay.n_pad + i] = d;
-        fold_dmin(dmin, locus, d);
+        fold_dmin(dmin, locus, dfold);
         fold_q(qbuf, locus, lay.A, fw);
     }
 }

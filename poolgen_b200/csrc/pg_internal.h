@@ -139,8 +139,10 @@ cudaError_t launch_synth(uint64_t seed, int64_t first_locus, int64_t n_loci, int
 
 // sync text -> counts[locus][6][n_pools] on the device (pg_text.cu)
 struct TextScratch;
-int64_t text_to_counts(TextScratch **scratch, const char *text, size_t n_bytes, int n_pools, uint32_t *d_counts,
-                       int64_t max_loci, int sm_count, cudaStream_t s, cudaError_t *cuda_err, uint64_t *err_offset);
+cudaError_t text_parse_async(TextScratch **scratch, const char *text, size_t n_bytes, int n_pools, uint32_t *d_counts,
+                             int64_t max_loci, size_t line_cap, int sm_count, cudaStream_t s);
+int64_t text_parse_finish(TextScratch *t, cudaStream_t s, cudaError_t *cuda_err, uint64_t *err_offset);
+bool text_parse_pending(const TextScratch *t);
 void text_scratch_free(TextScratch *t);
 const uint64_t *text_offsets(const TextScratch *t);
 const uint64_t *text_positions(const TextScratch *t);
@@ -267,4 +269,6 @@ struct pg_batch {
     int have_input = 0;
     int input_is_counts = 0;
     pg::TextScratch *text = nullptr;
+    const char *text_src = nullptr;  // the caller's chunk of the last text upload (valid until its slab is collected)
+    size_t text_bytes = 0;
 };

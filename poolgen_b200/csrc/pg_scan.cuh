@@ -1393,6 +1393,15 @@ cudaError_t launch_scan_p(ScanParams p, int sm_count, cudaStream_t s) {
     }
     if (p.warps_override >= 1 && p.warps_override < nwarps) nwarps = p.warps_override;
     if (nwarps < 1) return cudaErrorInvalidConfiguration;
+    // small slabs (the streaming submit path): shrink the block so that every warp of the grid gets loci -- phase 2
+    // then runs with few lanes, but on all warps at once instead of on a handful of them
+    if (p.g_override < 1) {
+        const int64_t per_warp = p.n_loci / ((int64_t)sm_count * nwarps * 2);
+        const int step = (P == 32) ? 1 : 32 / P;  // whole stages
+        int64_t g = per_warp / step * step;
+        if (g < step) g = step;
+        if (g < G) G = (int)g;
+    }
     p.common_bytes = (uint32_t)common;
     p.warp_bytes = (uint32_t)wbytes;
     p.stage_bytes = (uint32_t)stage;
