@@ -229,6 +229,18 @@ int pg_format_rows(int kind, const pg_results *res, const pg_row_labels *labels,
 int pg_format_kinship_rows(int64_t n_columns, int k, const char *const *chromosome, const uint64_t *position,
                            const char *const *allele, const double *beta, const double *pval, int n_threads,
                            char *out, size_t capacity, size_t *n_bytes);
+/* sync2csv (SaveCsv::write_csv, src/base/sync.rs:1182-1262) on top of the column loader (pg_kin_append_counts +
+ * pg_kin_get_columns + pg_kin_last_labels): one row per allele column, `chr,pos,allele,f_1,...,f_n` with every
+ * frequency through parse_f64_roundup_and_own(x, 6).  labels are indexed by the locus ordinal col_locus[c]; columns must
+ * be grouped by ascending locus ordinal (as the loader emits them).  locus_order (optional) lists the locus ordinals in
+ * output order -- pg_sort_loci gives the reference's order, a stable sort by (chromosome bytes, position)
+ * (src/base/sync.rs:1092-1101). */
+int pg_sort_loci(const pg_row_labels *labels, int64_t n_loci, int64_t *order_out);
+int pg_format_frequency_header(const char *const *pool_names, int n_pools, char *out, size_t capacity, size_t *n_bytes);
+int pg_format_frequency_rows(int64_t n_columns, int n_pools, const double *columns /* [n_columns][n_pools] */,
+                             const int64_t *col_locus, const uint8_t *col_allele, const pg_row_labels *labels,
+                             const int64_t *locus_order, int64_t n_order, int n_threads, char *out, size_t capacity,
+                             size_t *n_bytes);
 /* one number: n_digits > 0 = parse_f64_roundup_and_own(x, n_digits), 0 = f64::to_string(); returns the length */
 int pg_format_f64(double x, int n_digits, char *out, size_t capacity);
 

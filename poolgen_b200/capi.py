@@ -36,7 +36,8 @@ ABI_SYMBOLS = [
     "pg_kin_open", "pg_kin_close", "pg_kin_reset", "pg_kin_columns", "pg_kin_append_columns", "pg_kin_append_counts",
     "pg_kin_last_labels", "pg_kin_synth", "pg_kin_get_columns", "pg_kin_gram", "pg_kin_gram_time", "pg_kin_partial",
     "pg_kin_partial_get", "pg_kin_partial_set", "pg_kin_eig_select", "pg_kin_eigvals", "pg_kin_set_covariates",
-    "pg_kin_covar_scan", "pg_format_header", "pg_format_rows", "pg_format_kinship_rows", "pg_format_f64",
+    "pg_kin_covar_scan", "pg_format_header", "pg_format_rows", "pg_format_kinship_rows", "pg_format_f64", "pg_sort_loci",
+    "pg_format_frequency_header", "pg_format_frequency_rows",
 ]
 
 
@@ -148,6 +149,10 @@ def lib():
             "pg_format_kinship_rows": (i, [i64, i, C.POINTER(C.c_char_p), vp, C.POINTER(C.c_char_p), vp, vp, i, vp,
                                            C.c_size_t, C.POINTER(C.c_size_t)]),
             "pg_format_f64": (i, [C.c_double, i, vp, C.c_size_t]),
+            "pg_sort_loci": (i, [C.POINTER(_RowLabels), i64, vp]),
+            "pg_format_frequency_header": (i, [C.POINTER(C.c_char_p), i, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+            "pg_format_frequency_rows": (i, [i64, i, vp, vp, vp, C.POINTER(_RowLabels), vp, i64, i, vp, C.c_size_t,
+                                             C.POINTER(C.c_size_t)]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -259,6 +264,65 @@ def format_rows(kind: int, results, positions, text: bytes | None = None, line_o
     buf = C.create_string_buffer(need.value)
     _check(lib().pg_format_rows(int(kind), C.byref(results), C.byref(lab), n_threads, buf, need.value, C.byref(need)),
            None, "pg_format_rows")
+    del keep
+    return buf.raw[:need.value]
+
+
+def _row_labels(positions, text=None, line_offsets=None, chr_names=None, chr_index=None):
+    """pg_row_labels + the objects that must stay alive while it is used"""
+    pos = np.ascontiguousarray(positions, dtype=np.uint64)
+    lab = _RowLabels()
+    lab.positions = pos.ctypes.data_as(C.POINTER(C.c_uint64))
+    keep = [pos]
+    if text is not None:
+        off = np.ascontiguousarray(line_offsets, dtype=np.uint64)
+        lab.text = text
+        lab.line_offsets = off.ctypes.data_as(C.POINTER(C.c_uint64))
+        keep += [text, off]
+    else:
+        names = (C.c_char_p * len(chr_names))(*[n.encode() if isinstance(n, str) else n for n in chr_names])
+        idx = np.ascontiguousarray(chr_index, dtype=np.uint32)
+        lab.chr_names = names
+        lab.chr_index = idx.ctypes.data_as(C.POINTER(C.c_uint32))
+        keep += [names, idx]
+    return lab, keep
+
+
+def sort_loci(positions, **label_kw) -> np.ndarray:
+    """the order LoadAll::load leaves the loci in: stable sort by (chromosome bytes, position), src/base/sync.rs:1092-1101"""
+    lab, keep = _row_labels(positions, **label_kw)
+    n = len(keep[0])
+    order = np.empty(n, dtype=np.int64)
+    _check(lib().pg_sort_loci(C.byref(lab), n, order.ctypes.data), None, "pg_sort_loci")
+    return order
+
+
+def format_frequency_header(pool_names) -> bytes:
+    names = (C.c_char_p * len(pool_names))(*[n.encode() if isinstance(n, str) else n for n in pool_names])
+    need = C.c_size_t()
+    lib().pg_format_frequency_header(names, len(pool_names), None, 0, C.byref(need))
+    buf = C.create_string_buffer(need.value)
+    _check(lib().pg_format_frequency_header(names, len(pool_names), buf, need.value, C.byref(need)), None,
+           "pg_format_frequency_header")
+    return buf.raw[:need.value]
+
+
+def format_frequency_rows(columns, col_locus, col_allele, positions, locus_order=None, n_threads: int = 0, **label_kw) -> bytes:
+    """sync2csv rows (src/base/sync.rs:1243-1260): columns f64 [P, n_pools] with their (locus ordinal, allele code)
+    labels as the column loader returns them; locus_order from sort_loci for the reference's row order."""
+    cols = np.ascontiguousarray(columns, dtype=np.float64)
+    cl = np.ascontiguousarray(col_locus, dtype=np.int64)
+    ca = np.ascontiguousarray(col_allele, dtype=np.uint8)
+    lab, keep = _row_labels(positions, **label_kw)
+    order = None if locus_order is None else np.ascontiguousarray(locus_order, dtype=np.int64)
+    P, n = (cols.shape if cols.ndim == 2 else (0, 1))
+    n_threads = n_threads or (os.cpu_count() or 1)
+    args = (P, n, cols.ctypes.data, cl.ctypes.data, ca.ctypes.data, C.byref(lab),
+            None if order is None else order.ctypes.data, 0 if order is None else order.size, n_threads)
+    need = C.c_size_t()
+    lib().pg_format_frequency_rows(*args, None, 0, C.byref(need))
+    buf = C.create_string_buffer(max(1, need.value))
+    _check(lib().pg_format_frequency_rows(*args, buf, need.value, C.byref(need)), None, "pg_format_frequency_rows")
     del keep
     return buf.raw[:need.value]
 

@@ -5,10 +5,12 @@
 //   chisq           src/tables/chisq_test.rs:36-46     chr,pos,alleles,chi2 r6,p
 //   fisher          src/tables/fisher_exact_test.rs:118-129  chr,pos,alleles,p_observed,p
 //   ols_with_covariate  src/gwas/ols.rs:409-433        chr,pos,allele,Pheno_j,beta,p  (phenotype outer, column inner)
+//   sync2csv        src/base/sync.rs:1182-1262         chr,pos,allele,f_pool1 r6,...  (loci sorted by chromosome, position)
 // Numbers follow Rust's `f64::to_string()` (shortest digits that round-trip, never an exponent, "NaN", "inf", "-0")
 // and src/base/helpers.rs:103-117 (`sensible_round`, `parse_f64_roundup_and_own`).  Loci are split over threads in
 // contiguous ranges; the pieces are concatenated in locus order, like the reference concatenates its chunk files
 // (src/base/sync.rs:953-967).
+#include <algorithm>
 #include <charconv>
 #include <cmath>
 #include <cstring>
@@ -307,6 +309,118 @@ int pg_format_kinship_rows(int64_t n_columns, int k, const char *const *chromoso
             o.append(num, (size_t)(put_f64(beta[(size_t)j * n_columns + i], num) - num));
             o.push_back(',');
             o.append(num, (size_t)(put_f64(pval[(size_t)j * n_columns + i], num) - num));
+            o.push_back('\n');
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    return emit(parts, out, capacity, n_bytes);
+}
+
+// ---- sync2csv: the rows of SaveCsv::write_csv (src/base/sync.rs:1182-1262) -------------------------------------------
+int pg_sort_loci(const pg_row_labels *labels, int64_t n_loci, int64_t *order_out) {
+    if (!labels || !labels->positions || n_loci < 0 || (n_loci > 0 && !order_out)) return PG_ERR_ARG;
+    if (labels->text ? !labels->line_offsets : (!labels->chr_names || !labels->chr_index)) return PG_ERR_ARG;
+    const Labels L{labels};
+    struct Key {
+        const char *s;
+        size_t n;
+        uint64_t pos;
+        int64_t l;
+    };
+    std::vector<Key> keys((size_t)n_loci);
+    for (int64_t l = 0; l < n_loci; l++) {
+        Key &k = keys[(size_t)l];
+        L.chr(l, k.s, k.n);
+        k.pos = labels->positions[l];
+        k.l = l;
+    }
+    // `a.chromosome.cmp(&b.chromosome).then(a.position.cmp(&b.position))`, stable (src/base/sync.rs:1092-1101);
+    // Rust compares strings byte-wise
+    std::stable_sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
+        const int c = memcmp(a.s, b.s, a.n < b.n ? a.n : b.n);
+        if (c != 0) return c < 0;
+        if (a.n != b.n) return a.n < b.n;
+        return a.pos < b.pos;
+    });
+    for (int64_t i = 0; i < n_loci; i++) order_out[i] = keys[(size_t)i].l;
+    return PG_OK;
+}
+
+int pg_format_frequency_header(const char *const *pool_names, int n_pools, char *out, size_t capacity, size_t *n_bytes) {
+    if (n_pools < 0 || (n_pools > 0 && !pool_names)) return PG_ERR_ARG;
+    std::string h = "#chr,pos,allele,";  // src/base/sync.rs:1236-1240
+    for (int i = 0; i < n_pools; i++) {
+        if (i) h.push_back(',');
+        h.append(pool_names[i]);
+    }
+    h.push_back('\n');
+    if (n_bytes) *n_bytes = h.size();
+    if (h.size() > capacity || !out) return PG_ERR_ARG;
+    memcpy(out, h.data(), h.size());
+    return PG_OK;
+}
+
+int pg_format_frequency_rows(int64_t n_columns, int n_pools, const double *columns, const int64_t *col_locus,
+                             const uint8_t *col_allele, const pg_row_labels *labels, const int64_t *locus_order,
+                             int64_t n_order, int n_threads, char *out, size_t capacity, size_t *n_bytes) {
+    if (n_columns < 0 || n_pools < 1 || !labels || !labels->positions) return PG_ERR_ARG;
+    if (n_columns > 0 && (!columns || !col_locus || !col_allele)) return PG_ERR_ARG;
+    if (labels->text ? !labels->line_offsets : (!labels->chr_names || !labels->chr_index)) return PG_ERR_ARG;
+    // the sequence of columns to print: as stored, or locus by locus in `locus_order`
+    std::vector<int64_t> seq;
+    if (locus_order) {
+        int64_t max_l = -1;
+        for (int64_t c = 0; c < n_columns; c++) {
+            if (c && col_locus[c] < col_locus[c - 1]) return PG_ERR_ARG;  // columns must be grouped by ascending locus
+            if (col_locus[c] > max_l) max_l = col_locus[c];
+        }
+        std::vector<int64_t> first((size_t)(max_l + 2), -1), count((size_t)(max_l + 2), 0);
+        for (int64_t c = 0; c < n_columns; c++) {
+            if (first[(size_t)col_locus[c]] < 0) first[(size_t)col_locus[c]] = c;
+            count[(size_t)col_locus[c]]++;
+        }
+        seq.reserve((size_t)n_columns);
+        for (int64_t i = 0; i < n_order; i++) {
+            const int64_t l = locus_order[i];
+            if (l < 0 || l > max_l || first[(size_t)l] < 0) continue;
+            for (int64_t c = 0; c < count[(size_t)l]; c++) seq.push_back(first[(size_t)l] + c);
+        }
+    }
+    const int64_t rows = locus_order ? (int64_t)seq.size() : n_columns;
+    int T = n_threads < 1 ? 1 : n_threads;
+    const int64_t per = std::max<int64_t>(1, 65536 / n_pools);  // rows worth a thread
+    if ((int64_t)T > (rows + per - 1) / per) T = (int)((rows + per - 1) / per);
+    if (T < 1) T = 1;
+    std::vector<std::string> parts((size_t)T);
+    const Labels L{labels};
+    auto work = [&](int t) {
+        std::string &o = parts[(size_t)t];
+        const Rounder r6(6);
+        const int64_t lo = rows * t / T, hi = rows * (t + 1) / T;
+        o.reserve((size_t)(hi - lo) * (size_t)(24 + 9 * n_pools));
+        char num[420];
+        for (int64_t r = lo; r < hi; r++) {
+            const int64_t c = locus_order ? seq[(size_t)r] : r;
+            const int64_t l = col_locus[c];
+            const char *cs;
+            size_t cn;
+            L.chr(l, cs, cn);
+            o.append(cs, cn);
+            o.push_back(',');
+            o.append(num, (size_t)(put_u64(labels->positions[l], num) - num));
+            o.push_back(',');
+            o.push_back(kAlleleNames[col_allele[c] < 6 ? col_allele[c] : 4]);
+            const double *col = columns + (size_t)c * n_pools;
+            for (int i = 0; i < n_pools; i++) {
+                o.push_back(',');
+                o.append(num, (size_t)(r6.put(col[i], num) - num));  // parse_f64_roundup_and_own(x, 6), sync.rs:1247
+            }
             o.push_back('\n');
         }
     };

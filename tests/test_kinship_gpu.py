@@ -161,3 +161,25 @@ def test_partial_sum_equals_whole(ctx):
         parts.append(kin.partial_get())
         kin.close()
     assert np.allclose(parts[0] + parts[1], K, rtol=1e-13, atol=1e-10)
+
+
+def test_sync2csv_from_the_device_loader(ctx):
+    """sync2csv (SaveCsv::write_csv, src/base/sync.rs:1182-1262): device column loader -> pg_sort_loci ->
+    pg_format_frequency_rows equals the rows built from the oracle's loader, text for text"""
+    from tests.test_writer import _oracle_sync2csv_rows
+    c1 = H.load_c1()
+    fs = pb.FilterStats(pool_sizes=c1["pool_sizes"], min_coverage_depth=5, min_allele_frequency=0.01)
+    counts = c1["counts"]
+    L = counts.shape[0]
+    names = [str(s) for s in c1["chrom_names"]]
+    chroms = [names[i] for i in c1["chrom_idx"]]
+    pos = [int(p) for p in c1["pos"]]
+    kin = pb.Kinship(ctx, 5, 5 * L)
+    loc, alle = kin.append_counts(counts, c1["codes"], fs, True)
+    G = kin.get_columns(0, kin.columns)
+    kin.close()
+    order = pb.sort_loci(c1["pos"], chr_names=names, chr_index=c1["chrom_idx"])
+    got = pb.format_frequency_rows(G, loc, alle, c1["pos"], locus_order=order, chr_names=names,
+                                   chr_index=c1["chrom_idx"]).decode()
+    ocols, olabels = pgo.load_columns(counts.transpose(0, 2, 1).astype(np.uint64), c1["codes"], H.oracle_fs(fs), True)
+    assert got == _oracle_sync2csv_rows(ocols, olabels, chroms, pos) and got.count("\n") == len(olabels) > 1000

@@ -173,3 +173,43 @@ def test_kinship_rows():
     assert got[4] == "chr1,100,A,Pheno_1,0.30000000000000004,0.5"
     assert got[5] == "chr1,100,T,Pheno_1,1000000000000000000000,0.25"
     assert got[6] == "" and len(got) == 7
+
+
+def _oracle_sync2csv_rows(cols, labels, chroms, pos):
+    """rows of SaveCsv::write_csv (src/base/sync.rs:1243-1260) from the oracle's loader output, loci in the order of
+    LoadAll::load (stable sort by chromosome string, then position, src/base/sync.rs:1092-1101)"""
+    loci = sorted(range(len(chroms)), key=lambda l: (chroms[l].encode(), pos[l]))   # Python's sort is stable
+    by_locus = {}
+    for c, (l, a) in enumerate(labels):
+        by_locus.setdefault(l, []).append((c, a))
+    out = []
+    for l in loci:
+        for c, a in by_locus.get(l, []):
+            out.append(",".join([chroms[l], str(pos[l]), "ATCGND"[a]] + [pgo.round_to_string(v, 6) for v in cols[c]]) + "\n")
+    return "".join(out)
+
+
+@pytest.mark.parametrize("keep_p_minus_1", [False, True])
+def test_sync2csv_rows_c1(keep_p_minus_1):
+    """sync2csv over C1: the oracle's LoadAll columns through pg_sort_loci + pg_format_frequency_rows; the chromosome
+    order is scrambled first so that the sort does something"""
+    c1 = H.load_c1()
+    L = 1200
+    counts = c1["counts"][:L]
+    fs = pgo.FilterStats(pool_sizes=c1["pool_sizes"])
+    cols, labels = pgo.load_columns(counts.transpose(0, 2, 1).astype(np.uint64), c1["codes"], fs, keep_p_minus_1)
+    names = ["chr10", "chr2", "chr1", "Chr1", "chr1_b"]
+    idx = (np.arange(L) * 7) % len(names)
+    pos = (np.arange(L) * 7919) % 5000 + 1
+    chroms = [names[i] for i in idx]
+    order = pb.sort_loci(pos, chr_names=names, chr_index=idx)
+    assert sorted(order) == list(range(L))
+    got = pb.format_frequency_rows(cols, [l for l, _ in labels], [a for _, a in labels], pos, locus_order=order,
+                                   n_threads=3, chr_names=names, chr_index=idx).decode()
+    expect = _oracle_sync2csv_rows(cols, labels, chroms, [int(p) for p in pos])
+    assert got == expect and got.count("\n") == len(labels) > 1000
+    # as stored (no order): the loader's own sequence
+    plain = pb.format_frequency_rows(cols[:5], [l for l, _ in labels[:5]], [a for _, a in labels[:5]], pos,
+                                     chr_names=names, chr_index=idx).decode().split("\n")
+    assert plain[0].startswith(f"{chroms[labels[0][0]]},{pos[labels[0][0]]},{'ATCGND'[labels[0][1]]},")
+    assert pb.format_frequency_header(["Pop1", "Pop2", "Pop3"]) == b"#chr,pos,allele,Pop1,Pop2,Pop3\n"
