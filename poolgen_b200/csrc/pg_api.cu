@@ -288,7 +288,6 @@ int pg_batch_create(pg_scan *s, int64_t cap, pg_batch **out) {
         if (e == cudaSuccess) e = cudaMalloc(&b->d_depth, (size_t)cap * s->lay.depth_stride() * 4);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_dmin, (size_t)cap * 4);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_defer, (size_t)(cap + 1) * 8);
-        if (e == cudaSuccess) e = cudaMalloc(&b->d_qbuf, (size_t)cap * s->A_dev * 8);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_hint, (size_t)cap);
     }
     const size_t S = s->n_slots, K = s->k;
@@ -310,7 +309,6 @@ int pg_batch_destroy(pg_batch *b) {
     cudaFree(b->d_depth);
     cudaFree(b->d_dmin);
     cudaFree(b->d_defer);
-    cudaFree(b->d_qbuf);
     cudaFree(b->d_hint);
     pg::text_scratch_free(b->text);
     cudaFree(b->d_stage);
@@ -333,7 +331,6 @@ static pg::IngestOut ingest_out(pg_batch *b, int64_t first_locus) {
     o.freq = b->d_freq + (size_t)first_locus * s->lay.freq_stride();
     o.depth = b->d_depth + (size_t)first_locus * s->lay.depth_stride();
     o.dmin = b->d_dmin + first_locus;
-    o.qbuf = b->d_qbuf + (size_t)first_locus * s->A_dev;
     o.hint = b->d_hint + first_locus;
     o.w = s->d_w;
     o.maf = s->maf;

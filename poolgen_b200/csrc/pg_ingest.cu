@@ -2,7 +2,7 @@
 // f64 first-stage frequency matrix + depth vector the scan kernel streams, and the synthetic workload
 // generator.  Frequencies are one IEEE division of exactly representable integers, i.e. bit-identical
 // to LocusCounts::to_frequencies (src/base/sync.rs:166-192).  Every ingest also leaves dmin[locus] = the smallest
-// pool depth of the locus (the caller presets dmin to 0xFFFFFFFF).
+// pool depth of the locus and the renormalisation hint of the scan.
 #include <stdlib.h>
 
 #include "pg_device.cuh"
@@ -10,148 +10,112 @@
 
 namespace pg {
 
-// per-locus pooled frequencies q_j = sum_i f_ij w_i (NaN skipped): the lanes of a warp that hold the same locus are
-// contiguous, so a segmented shuffle reduction leaves the sum of every run in its first lane, which issues ONE atomic
-// per (warp, locus, allele).  Must be called by all 32 lanes at a convergent point (locus = -1 for lanes without a
-// row).  The sums only feed the renormalisation HINT of the scan, never a decision on their own.
-__device__ __forceinline__ void fold_q(double *qbuf, int64_t locus, int A, const double *fw) {
-    const int lane = threadIdx.x & 31;
-    const int64_t up = __shfl_up_sync(0xFFFFFFFFu, locus, 1);
-    const bool head = lane == 0 || up != locus;
-    bool same[5];
-#pragma unroll
-    for (int s = 0; s < 5; s++) {
-        const int64_t other = __shfl_down_sync(0xFFFFFFFFu, locus, 1 << s);
-        same[s] = (lane + (1 << s) < 32) && other == locus;
-    }
-    for (int j = 0; j < A; j++) {
-        double v = fw[j];
-#pragma unroll
-        for (int s = 0; s < 5; s++) {
-            const double t = __shfl_down_sync(0xFFFFFFFFu, v, 1 << s);
-            if (same[s]) v += t;
-        }
-        if (head && locus >= 0 && v != 0.0) atomicAdd(qbuf + (size_t)locus * A + j, v);
-    }
-}
-
-// the same for the smallest depth of the locus
-__device__ __forceinline__ void fold_dmin(uint32_t *dmin, int64_t locus, uint32_t d) {
-    const int lane = threadIdx.x & 31;
-    const int64_t up = __shfl_up_sync(0xFFFFFFFFu, locus, 1);
-    const bool head = lane == 0 || up != locus;
-    uint32_t v = d;
-#pragma unroll
-    for (int s = 0; s < 5; s++) {
-        const int64_t other = __shfl_down_sync(0xFFFFFFFFu, locus, 1 << s);
-        const uint32_t t = __shfl_down_sync(0xFFFFFFFFu, v, 1 << s);
-        if ((lane + (1 << s) < 32) && other == locus) v = min(v, t);
-    }
-    if (head && locus >= 0) atomicMin(dmin + locus, v);
-}
-
 // hint of a locus: bit 7 = "renormalise over the alleles in bits 0..5": every pool has coverage, the depth filter
 // passes, at least two alleles survive the MAF filter, a removed allele carries reads (the regression then runs on
 // c_ij / sum_kept c_i., src/base/sync.rs:166-192 after the filter) and every pooled frequency is further from both
 // thresholds than twice the rounding bound of ANY summation order -- so the keep-mask in the hint is the reference's.
 // The streaming scan renormalises such loci on the fly; every other locus gets 0 and takes the scan's own decision
 // path (which defers what it cannot settle to the fix-up kernel).
-__global__ void __launch_bounds__(256) hint_kernel(const double *__restrict__ qbuf, const uint32_t *__restrict__ dmin,
-                                                   int64_t n_loci, int A, int n, double maf, double one_minus_maf,
-                                                   double min_depth_f, uint8_t *__restrict__ hint) {
+struct HintParams {
+    double maf, one_minus_maf, min_depth_f;
+    int enabled;
+};
+__device__ __forceinline__ uint8_t locus_hint(const double *q, int A, int n, uint32_t dm, const HintParams &hp) {
+    if (!hp.enabled) return 0;
     const double tol_rel = 4.0 * ((double)n + 8.0) * kEps;
-    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n_loci; l += (int64_t)gridDim.x * blockDim.x) {
-        unsigned kept = 0;
-        bool removed_with_reads = false, safe = true;
-        for (int j = 0; j < A; j++) {
-            const double q = qbuf[(size_t)l * A + j];
-            const double tl = tol_rel * fmax(fabs(q), 1.0);
-            if (fabs(q - maf) <= tl || fabs(q - one_minus_maf) <= tl) safe = false;
-            if (!((q < maf) | (q > one_minus_maf)))
-                kept |= 1u << j;
-            else if (q > 0.0)
-                removed_with_reads = true;
+    unsigned kept = 0;
+    bool removed_with_reads = false, safe = true;
+    for (int j = 0; j < A; j++) {
+        const double tl = tol_rel * fmax(fabs(q[j]), 1.0);
+        if (fabs(q[j] - hp.maf) <= tl || fabs(q[j] - hp.one_minus_maf) <= tl) safe = false;
+        if (!((q[j] < hp.maf) | (q[j] > hp.one_minus_maf)))
+            kept |= 1u << j;
+        else if (q[j] > 0.0)
+            removed_with_reads = true;
+    }
+    const bool depth_ok = dm != 0u && !((double)dm < hp.min_depth_f);
+    return (safe && depth_ok && removed_with_reads && __popc(kept) >= 2) ? (uint8_t)(0x80u | kept) : (uint8_t)0;
+}
+
+// A group of P lanes (P = 32 for more than 16 pools, else the next power of two) owns a locus: every lane converts
+// the pools q0, q0 + P, ... and keeps the pooled frequencies q_j = sum_i f_ij w_i (NaN skipped) and the smallest
+// depth of its pools; a butterfly over the group completes them, its first lane stores dmin and the hint.  No
+// atomics, no scratch, and a locus gets the same bits wherever it lands.
+template <typename RowFn>
+__device__ __forceinline__ void ingest_loci(int64_t n_loci, const Layout &lay, int P, uint32_t *__restrict__ dmin,
+                                            uint8_t *__restrict__ hint, const HintParams &hp, RowFn &&row) {
+    const int lane = threadIdx.x & 31, sub = lane / P, q0 = lane % P, lpw = 32 / P;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t l0 = gw * lpw; l0 < n_loci; l0 += nw * lpw) {
+        const int64_t locus = l0 + sub;
+        double q[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
+        uint32_t dm = 0xFFFFFFFFu;
+        if (locus < n_loci)
+            for (int i = q0; i < lay.n_pad; i += P) row(locus, i, q, dm);
+        for (int off = P >> 1; off >= 1; off >>= 1) {
+            for (int j = 0; j < lay.A; j++) q[j] += __shfl_xor_sync(0xFFFFFFFFu, q[j], off);
+            dm = min(dm, __shfl_xor_sync(0xFFFFFFFFu, dm, off));
         }
-        const uint32_t dm = dmin[l];
-        const bool depth_ok = dm != 0u && !((double)dm < min_depth_f);
-        hint[l] = (safe && depth_ok && removed_with_reads && __popc(kept) >= 2) ? (uint8_t)(0x80u | kept) : (uint8_t)0;
+        if (locus < n_loci && q0 == 0) {
+            dmin[locus] = dm;
+            hint[locus] = locus_hint(q, lay.A, lay.n, dm, hp);
+        }
     }
 }
 
 template <typename CT>
 __global__ void __launch_bounds__(256) ingest_counts_kernel(const CT *__restrict__ counts, int64_t n_loci, int n,
-                                                            int A_in, int drop_col, Layout lay,
+                                                            int A_in, int drop_col, Layout lay, int P,
                                                             double *__restrict__ freq, uint32_t *__restrict__ depth,
-                                                            uint32_t *__restrict__ dmin, double *__restrict__ qbuf,
-                                                            const double *__restrict__ w) {
-    const int64_t total = n_loci * lay.n_pad;
-    // the whole warp stays in the loop: the folds at the end shuffle across all 32 lanes
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx - (int64_t)(threadIdx.x & 31) < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        int64_t locus = -1;
-        uint32_t dfold = 0xFFFFFFFFu;
-        double fw[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
-        if (idx < total) {
-            locus = idx / lay.n_pad;
-            const int i = (int)(idx - locus * lay.n_pad);
-            double *fl = freq + (size_t)locus * lay.freq_stride();
-            if (i >= n) {  // padding row
-                for (int j = 0; j < lay.A; j++) fl[lay.freq_off(i, j)] = 0.0;
-                depth[(size_t)locus * lay.n_pad + i] = 0xFFFFFFFFu;
-            } else {
-                const CT *cl = counts + (size_t)locus * A_in * n + i;
-                uint32_t c[PG_MAX_ALLELES];
-                uint64_t d = 0;
-                int jj = 0;
-                for (int j = 0; j < A_in; j++) {
-                    if (j == drop_col) continue;
-                    c[jj] = (uint32_t)cl[(size_t)j * n];
-                    d += c[jj];
-                    jj++;
-                }
-                if (d > 0xFFFFFFFEull) d = 0xFFFFFFFEull;  // documented limit: per-pool depth < 2^32 - 1
-                const double dd = (double)d, wi = w[i];
-                for (int j = 0; j < lay.A; j++) {
-                    const double f = (d == 0) ? nan("") : (double)c[j] / dd;
-                    fl[lay.freq_off(i, j)] = f;
-                    fw[j] = (d == 0) ? 0.0 : f * wi;
-                }
-                depth[(size_t)locus * lay.n_pad + i] = (uint32_t)d;
-                dfold = (uint32_t)d;
-            }
+                                                            uint32_t *__restrict__ dmin, uint8_t *__restrict__ hint,
+                                                            const double *__restrict__ w, HintParams hp) {
+    ingest_loci(n_loci, lay, P, dmin, hint, hp, [&](int64_t locus, int i, double *q, uint32_t &dm) {
+        double *fl = freq + (size_t)locus * lay.freq_stride();
+        if (i >= n) {  // padding row
+            for (int j = 0; j < lay.A; j++) fl[lay.freq_off(i, j)] = 0.0;
+            depth[(size_t)locus * lay.n_pad + i] = 0xFFFFFFFFu;
+            return;
         }
-        fold_dmin(dmin, locus, dfold);
-        fold_q(qbuf, locus, lay.A, fw);
-    }
+        const CT *cl = counts + (size_t)locus * A_in * n + i;
+        uint32_t c[PG_MAX_ALLELES];
+        uint64_t d = 0;
+        int jj = 0;
+        for (int j = 0; j < A_in; j++) {
+            if (j == drop_col) continue;
+            c[jj] = (uint32_t)cl[(size_t)j * n];
+            d += c[jj];
+            jj++;
+        }
+        if (d > 0xFFFFFFFEull) d = 0xFFFFFFFEull;  // documented limit: per-pool depth < 2^32 - 1
+        const double dd = (double)d, wi = w[i];
+        for (int j = 0; j < lay.A; j++) {
+            const double f = (d == 0) ? nan("") : (double)c[j] / dd;
+            fl[lay.freq_off(i, j)] = f;
+            if (d != 0) q[j] = fma(f, wi, q[j]);
+        }
+        depth[(size_t)locus * lay.n_pad + i] = (uint32_t)d;
+        dm = min(dm, (uint32_t)d);
+    });
 }
 
 __global__ void __launch_bounds__(256) ingest_freq_kernel(const double *__restrict__ fin, const uint32_t *__restrict__ din,
-                                                          int64_t n_loci, int n, Layout lay,
+                                                          int64_t n_loci, int n, Layout lay, int P,
                                                           double *__restrict__ freq, uint32_t *__restrict__ depth,
-                                                          uint32_t *__restrict__ dmin, double *__restrict__ qbuf,
-                                                          const double *__restrict__ w) {
-    const int64_t total = n_loci * lay.n_pad;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx - (int64_t)(threadIdx.x & 31) < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        int64_t locus = -1;
-        uint32_t dfold = 0xFFFFFFFFu;
-        double fw[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
-        if (idx < total) {
-            locus = idx / lay.n_pad;
-            const int i = (int)(idx - locus * lay.n_pad);
-            double *fl = freq + (size_t)locus * lay.freq_stride();
-            const bool pad = i >= n;
-            for (int j = 0; j < lay.A; j++) {
-                const double f = pad ? 0.0 : fin[((size_t)locus * lay.A + j) * n + i];
-                fl[lay.freq_off(i, j)] = f;
-                fw[j] = (pad || f != f) ? 0.0 : f * w[i];
-            }
-            dfold = pad ? 0xFFFFFFFFu : din[(size_t)locus * n + i];
-            depth[(size_t)locus * lay.n_pad + i] = dfold;
+                                                          uint32_t *__restrict__ dmin, uint8_t *__restrict__ hint,
+                                                          const double *__restrict__ w, HintParams hp) {
+    ingest_loci(n_loci, lay, P, dmin, hint, hp, [&](int64_t locus, int i, double *q, uint32_t &dm) {
+        double *fl = freq + (size_t)locus * lay.freq_stride();
+        const bool pad = i >= n;
+        for (int j = 0; j < lay.A; j++) {
+            const double f = pad ? 0.0 : fin[((size_t)locus * lay.A + j) * n + i];
+            fl[lay.freq_off(i, j)] = f;
+            if (!pad && f == f) q[j] = fma(f, w[i], q[j]);
         }
-        fold_dmin(dmin, locus, dfold);
-        fold_q(qbuf, locus, lay.A, fw);
-    }
+        const uint32_t d = pad ? 0xFFFFFFFFu : din[(size_t)locus * n + i];
+        depth[(size_t)locus * lay.n_pad + i] = d;
+        dm = min(dm, d);
+    });
 }
 
 __global__ void __launch_bounds__(256) synth_kernel(uint64_t seed, int64_t first_locus, int64_t n_loci, int n,
@@ -173,29 +137,29 @@ static int grid_for(int64_t total) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-static cudaError_t ingest_prologue(int64_t n_loci, const Layout &lay, const IngestOut &o, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(o.dmin, 0xFF, (size_t)n_loci * 4, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(o.qbuf, 0, (size_t)n_loci * lay.A * 8, s);
-    return e;
+// lanes per locus of the ingest kernels
+static int ingest_group(const Layout &lay) {
+    int P = 32;
+    while (P > 1 && (P >> 1) >= lay.n_pad) P >>= 1;
+    return P;
 }
-static cudaError_t ingest_epilogue(int64_t n_loci, const Layout &lay, const IngestOut &o, cudaStream_t s) {
+static HintParams hint_params(const IngestOut &o) {
     static const bool no_hint = getenv("PG_NOHINT") != nullptr;  // tuning knob: every locus takes the scan's own path
-    if (no_hint) return cudaMemsetAsync(o.hint, 0, (size_t)n_loci, s);
-    hint_kernel<<<grid_for(n_loci), 256, 0, s>>>(o.qbuf, o.dmin, n_loci, lay.A, lay.n, o.maf, o.one_minus_maf,
-                                                 o.min_depth_f, o.hint);
-    return cudaGetLastError();
+    HintParams hp;
+    hp.maf = o.maf;
+    hp.one_minus_maf = o.one_minus_maf;
+    hp.min_depth_f = o.min_depth_f;
+    hp.enabled = no_hint ? 0 : 1;
+    return hp;
 }
 template <typename CT>
 static cudaError_t launch_ingest_t(const CT *counts, int64_t n_loci, int n, int A_in, int drop_col, const Layout &lay,
                                    const IngestOut &o, cudaStream_t s) {
     if (n_loci <= 0) return cudaSuccess;
-    cudaError_t e = ingest_prologue(n_loci, lay, o, s);
-    if (e != cudaSuccess) return e;
-    ingest_counts_kernel<CT><<<grid_for(n_loci * lay.n_pad), 256, 0, s>>>(counts, n_loci, n, A_in, drop_col, lay, o.freq,
-                                                                         o.depth, o.dmin, o.qbuf, o.w);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    return ingest_epilogue(n_loci, lay, o, s);
+    const int P = ingest_group(lay);
+    ingest_counts_kernel<CT><<<grid_for(n_loci * P), 256, 0, s>>>(counts, n_loci, n, A_in, drop_col, lay, P, o.freq,
+                                                                 o.depth, o.dmin, o.hint, o.w, hint_params(o));
+    return cudaGetLastError();
 }
 cudaError_t launch_ingest_u32(const uint32_t *counts, int64_t n_loci, int n, int A_in, int drop_col, const Layout &lay,
                               const IngestOut &o, cudaStream_t s) {
@@ -212,13 +176,10 @@ cudaError_t launch_ingest_u8(const uint8_t *counts, int64_t n_loci, int n, int A
 cudaError_t launch_ingest_freq(const double *fin, const uint32_t *din, int64_t n_loci, int n, const Layout &lay,
                                const IngestOut &o, cudaStream_t s) {
     if (n_loci <= 0) return cudaSuccess;
-    cudaError_t e = ingest_prologue(n_loci, lay, o, s);
-    if (e != cudaSuccess) return e;
-    ingest_freq_kernel<<<grid_for(n_loci * lay.n_pad), 256, 0, s>>>(fin, din, n_loci, n, lay, o.freq, o.depth, o.dmin,
-                                                                    o.qbuf, o.w);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    return ingest_epilogue(n_loci, lay, o, s);
+    const int P = ingest_group(lay);
+    ingest_freq_kernel<<<grid_for(n_loci * P), 256, 0, s>>>(fin, din, n_loci, n, lay, P, o.freq, o.depth, o.dmin, o.hint,
+                                                            o.w, hint_params(o));
+    return cudaGetLastError();
 }
 cudaError_t launch_synth(uint64_t seed, int64_t first_locus, int64_t n_loci, int n, int A_in, uint32_t *counts,
                          cudaStream_t s) {

@@ -121,8 +121,7 @@ struct IngestOut {
     double *freq;
     uint32_t *depth;
     uint32_t *dmin;
-    double *qbuf;    // [locus][A] scratch: pooled frequencies for the hint
-    uint8_t *hint;   // [locus] renormalisation hint of the scan (pg_ingest.cu:hint_kernel)
+    uint8_t *hint;   // [locus] renormalisation hint of the scan (pg_ingest.cu:locus_hint)
     const double *w; // [n_pad] pool weights s_i / sum(s)
     double maf, one_minus_maf, min_depth_f;
 };
@@ -255,7 +254,6 @@ struct pg_batch {
     uint32_t *d_depth = nullptr;
     uint32_t *d_dmin = nullptr;
     uint64_t *d_defer = nullptr;  // [cap + 1]: list then its counter
-    double *d_qbuf = nullptr;     // [cap][A] ingest scratch
     uint8_t *d_hint = nullptr;    // [cap]
     void *d_stage = nullptr;  // raw uploaded slab (counts u32/u16 or unpadded freq+depth)
     size_t stage_bytes = 0;
