@@ -48,6 +48,7 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.rows = []
+        self.stamps = []
         self.proc = None
 
     def start(self):
@@ -65,11 +66,20 @@ class ClockSampler:
             f = [x.strip() for x in line.split(",")]
             if len(f) >= 9:
                 self.rows.append(f)
+                self.stamps.append(time.time())
+
+    def samples_since(self, t0: float) -> int:
+        return sum(1 for t in self.stamps if t >= t0)
+
+    def keep_since(self, t0: float):
+        """only the samples taken while the GPU was under load count"""
+        keep = [i for i, t in enumerate(self.stamps) if t >= t0]
+        self.rows = [self.rows[i] for i in keep]
+        self.stamps = [self.stamps[i] for i in keep]
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -151,10 +161,28 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """pin this process to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned host memory is allocated:
+    with 8 ranks on one box the slabs of the end-to-end leg otherwise sit on one socket and every copy crosses it"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001 -- a missing NVML binding only costs the binding
+        return None
+
+
 def run_cuda(args):
     import torch
     import poolgen_b200 as pb
     rank, local, world = dist_env()
+    # rank 0 prints ONE JSON line: everything else a library writes to fd 1 (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -181,12 +209,20 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    batch.time_runs(max(3, args.warmup))  # warm-up (>= 3 passes)
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
+    batch.time_runs(1)
+    t_load = time.time()
+    batch.time_runs(max(3, args.warmup))  # warm-up (>= 3 passes)
+    barrier()
     ms, launches = batch.time_runs(args.steps)  # CUDA events on the stream the kernels are launched on
     barrier()
+    # the timed region can be shorter than nvidia-smi's sampling period: keep the same kernel running (untimed) until
+    # at least three clock samples were taken under load
+    t_end = time.time() + 4.0
+    while sampler.proc and sampler.samples_since(t_load) < 3 and time.time() < t_end:
+        batch.time_runs(max(1, args.steps))
+    sampler.keep_since(t_load)
     clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -281,11 +317,15 @@ def run_cuda(args):
             "clocks": clocks,
             "extras": extras,
         }
-        print(json.dumps(line))
+        if cpus is not None:
+            line["config"]["cpu_affinity"] = f"each rank bound to the {len(cpus)} CPUs next to its GPU (NVML)"
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
     return 0
 
 

@@ -129,8 +129,8 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
                     filter->n_pool_sizes, n_pools);
     const bool regression = (kind == PG_KIND_OLS || kind == PG_KIND_CORR);
     if (regression && (!phen || k < 1)) return fail(ctx, PG_ERR_ARG, "pg_scan_open: phenotypes required");
-    if (!regression && n_pools > 16)
-        return fail(ctx, PG_ERR_UNSUPPORTED, "pg_scan_open: the count tests hold one table per thread and are built for up to 16 pools (got %d)", n_pools);
+    if (kind == PG_KIND_FISHER && n_pools > 16)
+        return fail(ctx, PG_ERR_UNSUPPORTED, "pg_scan_open: fisher holds one table per thread and is built for up to 16 pools (got %d); its enumeration grows with (pools x alleles)^2 (src/tables/fisher_exact_test.rs:68-117)", n_pools);
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
 
     pg_scan *s = new (std::nothrow) pg_scan();

@@ -511,8 +511,140 @@ __global__ void __launch_bounds__(kTabThreads) tables_kernel(const TableParams p
     }
 }
 
+// ---- tables::chisq for more than 16 pools: one warp per locus, lane = pool (stride 32), counts re-read from L1/L2 for
+// each of the three passes (depth + pooled frequencies, column sums, chi-square).  The keep-mask is the reference's:
+// a pooled frequency within the rounding bound of a threshold is re-evaluated by one lane in pool order with separately
+// rounded multiply and add (src/base/sync.rs:258-271).
+__global__ void __launch_bounds__(256) chisq_wide_kernel(const TableParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int n = p.n;
+    int col[PG_MAX_ALLELES];
+    int pc = 0;
+    for (int j = 0; j < p.A_in; j++)
+        if (j != p.drop_col) col[pc++] = j;
+    const double tol_rel = 2.0 * ((double)n + 8.0) * kEps;
+    for (int64_t locus = gw; locus < p.n_loci; locus += nw) {
+        const uint32_t *cnt = p.counts + (size_t)locus * p.A_in * n;
+        // pass 1: depth per pool, smallest depth, pools without coverage, pooled frequencies
+        double q[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
+        double dmin = 1.7976931348623157e308;
+        int miss = 0;
+        for (int i = lane; i < n; i += 32) {
+            double d = 0.0;
+            for (int a = 0; a < pc; a++) d += (double)cnt[col[a] * n + i];
+            dmin = fmin(dmin, d);
+            if (d == 0.0) {
+                miss++;
+            } else {
+                const double wi = p.w[i];
+                for (int a = 0; a < pc; a++) q[a] += ((double)cnt[col[a] * n + i] / d) * wi;
+            }
+        }
+        for (int off = 16; off >= 1; off >>= 1) {
+            dmin = fmin(dmin, __shfl_xor_sync(PG_FULL_MASK, dmin, off));
+            miss += __shfl_xor_sync(PG_FULL_MASK, miss, off);
+            for (int a = 0; a < pc; a++) q[a] += __shfl_xor_sync(PG_FULL_MASK, q[a], off);
+        }
+        int status = PG_LOCUS_OK;
+        int cols[PG_MAX_ALLELES];
+        int pk = 0;
+        if (dmin < p.min_depth_f) {
+            status = PG_LOCUS_FILTERED;
+        } else {
+            for (int a = 0; a < pc; a++) {
+                double qa = q[a];
+                const double tl = tol_rel * fmax(fabs(qa), 1.0);
+                if (fabs(qa - p.maf) <= tl || fabs(qa - p.one_minus_maf) <= tl) {
+                    if (lane == 0) {  // the reference's order decides
+                        double e = 0.0;
+                        for (int i = 0; i < n; i++) {
+                            double d = 0.0;
+                            for (int b = 0; b < pc; b++) d += (double)cnt[col[b] * n + i];
+                            const double f = (d == 0.0) ? nan("") : (double)cnt[col[a] * n + i] / d;
+                            const double term = (f != f) ? 0.0 : __dmul_rn(f, p.w[i]);
+                            e = __dadd_rn(e, term);
+                        }
+                        qa = e;
+                    }
+                    qa = __shfl_sync(PG_FULL_MASK, qa, 0);
+                }
+                if (!((qa < p.maf) | (qa > p.one_minus_maf))) cols[pk++] = col[a];
+            }
+            if (pk < 2) status = PG_LOCUS_FILTERED;
+            else if (miss == n) status = PG_LOCUS_FILTERED;
+            else if (((double)miss / (double)n) > p.max_miss) status = PG_LOCUS_FILTERED;
+        }
+        double stat = nan(""), pval = nan("");
+        if (status == PG_LOCUS_OK) {
+            // pass 2: column sums and the total of the frequencies renormalised over the kept alleles (sync.rs:166-192)
+            double cs[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
+            double total = 0.0;
+            for (int i = lane; i < n; i += 32) {
+                double d = 0.0;
+                for (int a = 0; a < pk; a++) d = d + (double)cnt[cols[a] * n + i];
+                for (int a = 0; a < pk; a++) {
+                    const double c = (d == 0.0) ? nan("") : (double)cnt[cols[a] * n + i] / d;
+                    cs[a] += c;
+                    total += c;
+                }
+            }
+            for (int off = 16; off >= 1; off >>= 1) {
+                total += __shfl_xor_sync(PG_FULL_MASK, total, off);
+                for (int a = 0; a < pk; a++) cs[a] += __shfl_xor_sync(PG_FULL_MASK, cs[a], off);
+            }
+            // pass 3: chi-square (chisq_test.rs:17-31)
+            double chi2 = 0.0;
+            for (int i = lane; i < n; i += 32) {
+                double d = 0.0;
+                for (int a = 0; a < pk; a++) d = d + (double)cnt[cols[a] * n + i];
+                double c[PG_MAX_ALLELES], rs = 0.0;
+                for (int a = 0; a < pk; a++) {
+                    c[a] = (d == 0.0) ? nan("") : (double)cnt[cols[a] * n + i] / d;
+                    rs = rs + c[a];
+                }
+                for (int a = 0; a < pk; a++) {
+                    const double e = (rs * cs[a]) / total;
+                    const double dd = c[a] - e;
+                    chi2 += (dd * dd) / e;
+                }
+            }
+            for (int off = 16; off >= 1; off >>= 1) chi2 += __shfl_xor_sync(PG_FULL_MASK, chi2, off);
+            stat = chi2;
+            const double df = (double)(n * pk) - 1.0;
+            double cdf;
+            if (chi2 <= 0.0)
+                cdf = 0.0;
+            else if (isinf(chi2))
+                cdf = 1.0;
+            else
+                cdf = gamma_lr_dev(df / 2.0, chi2 * 0.5);
+            pval = 1.00 - cdf;
+        }
+        if (lane == 0) {
+            uint64_t mv = (uint64_t)status;
+            if (status == PG_LOCUS_OK) {
+                mv |= (uint64_t)pk << 8;
+                for (int a = 0; a < pk; a++) mv |= (uint64_t)p.codes[cols[a]] << (16 + 8 * a);
+            }
+            p.meta[locus] = mv;
+            double *o = p.stats + (size_t)locus * 4;
+            *reinterpret_cast<double2 *>(o) = make_double2(stat, nan(""));
+            *reinterpret_cast<double2 *>(o + 2) = make_double2(nan(""), pval);
+        }
+    }
+}
+
 cudaError_t launch_tables(const TableParams &p, int sm_count, cudaStream_t s) {
-    if (p.n > kTabMaxPools) return cudaErrorInvalidConfiguration;
+    if (p.n > kTabMaxPools) {
+        if (p.kind != PG_KIND_CHISQ) return cudaErrorInvalidConfiguration;
+        int64_t grid = (p.n_loci * 32 + 255) / 256;
+        if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
+        if (grid < 1) grid = 1;
+        chisq_wide_kernel<<<(unsigned)grid, 256, 0, s>>>(p);
+        return cudaGetLastError();
+    }
     static bool lf_ready[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);

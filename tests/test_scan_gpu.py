@@ -409,7 +409,32 @@ def test_pearson_with_missing_phenotypes(ctx, n, L):
         pb.Scan(ctx, pb.KIND_OLS, fs, n, codes, phen)
 
 
-def test_count_tests_refuse_more_than_16_pools(ctx):
+def test_fisher_refuses_more_than_16_pools(ctx):
     fs = _fs(np.full(17, 1.0 / 17))
     with pytest.raises(pb.PgError):
         pb.Scan(ctx, pb.KIND_FISHER, fs, 17, np.arange(4, dtype=np.uint8))
+
+
+@pytest.mark.parametrize("n,A,L,kw", [(17, 4, 3000, {}), (100, 6, 1500, {}), (1000, 4, 300, {}),
+                                      (300, 5, 600, dict(min_coverage_depth=0, max_missingness_rate=0.3))])
+def test_chisq_many_pools(ctx, n, A, L, kw):
+    """tables::chisq beyond 16 pools: one warp per locus (df up to 3,999), unequal pool sizes, pools without coverage"""
+    seed = 0xC415 + n
+    counts = pb.synth_counts_host(seed, 0, L, n, min(A, 4))
+    full = np.zeros((L, A, n), dtype=np.uint32)
+    full[:, :min(A, 4)] = counts
+    if A > 4:
+        rng = np.random.default_rng(seed)
+        full[:, 4:] = (rng.random((L, A - 4, n)) < 0.05).astype(np.uint32)
+    ps = 3.0 + (np.arange(n) % 4)
+    tot = 0.0
+    for v in ps:
+        tot = tot + v
+    fs = _fs(np.array([v / tot for v in ps]), **kw)
+    codes = np.arange(A, dtype=np.uint8) if A <= 4 else np.array([0, 1, 2, 3, 4, 5][:A], dtype=np.uint8)
+    scan = pb.Scan(ctx, pb.KIND_CHISQ, fs, n, codes)
+    dev = scan.run_counts(full)
+    scan.close()
+    st = H.compare_tables(pb.KIND_CHISQ, full, codes, fs, dev, label=f"chisq n={n}")
+    assert st["ok"] > 0.5 * L
+    print(st)
