@@ -66,3 +66,21 @@ def test_host_generator_is_deterministic_and_well_formed():
     assert 0.005 < zero_loci < 0.04 and 0.03 < mono < 0.08
     y = pb.synth_phen_host(1, 100, 3)
     assert y.shape == (100, 3) and (np.abs(y) <= 3).all() and y.std() > 1.0
+
+
+def test_rust_ffi_crate_declares_the_same_functions():
+    """ffi/poolgen-cuda-sys/src/lib.rs (the binding poolgen would link; not compiled here: no cargo in the image) must
+    declare every function of the header with the same number of parameters, and nothing else"""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "poolgen_cuda.h")).read(), flags=re.S)
+    rs = re.sub(r"//.*", "", open(os.path.join(ROOT, "ffi", "poolgen-cuda-sys", "src", "lib.rs")).read())
+    ext = rs[rs.index('extern "C" {'):]
+    ext = ext[:ext.index("\n}\n")]
+
+    def arity(params: str) -> int:
+        p = params.strip()
+        return 0 if p in ("", "void") else p.count(",") + 1
+
+    c_fns = {m.group(1): arity(m.group(2)) for m in re.finditer(r"\b(pg_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", hdr)}
+    rs_fns = {m.group(1): arity(m.group(2)) for m in re.finditer(r"pub fn (pg_[a-z0-9_]+)\(([^()]*)\)", ext)}
+    assert sorted(c_fns) == _header_functions()
+    assert rs_fns == c_fns
