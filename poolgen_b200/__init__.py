@@ -12,7 +12,9 @@ from .capi import (ALLELE_NAMES, KIND_CHISQ, KIND_CORR, KIND_FISHER, KIND_OLS, L
                    ScanResults, format_f64, format_frequency_header, format_frequency_rows, format_header, format_kinship_rows,
                    format_rows, sort_loci, synth_counts_host, synth_phen_host, synth_sync_text_host)
 
-__all__ = ["ALLELE_NAMES", "KIND_CHISQ", "KIND_CORR", "KIND_FISHER", "KIND_OLS", "LOCUS_FAILED", "LOCUS_FILTERED",
+from .sync_io import FilePhen, FileSync, FileSyncPhen, Phen, find_file_splits  # noqa: E402
+
+__all__ = ["FilePhen", "FileSync", "FileSyncPhen", "Phen", "find_file_splits", "ALLELE_NAMES", "KIND_CHISQ", "KIND_CORR", "KIND_FISHER", "KIND_OLS", "LOCUS_FAILED", "LOCUS_FILTERED",
            "LOCUS_OK", "LOCUS_PANIC", "LOCUS_UNSUPPORTED", "Batch", "Context", "FilterStats", "Kinship", "PgError", "Scan",
            "ScanResults", "synth_counts_host", "synth_phen_host", "synth_sync_text_host", "ols_iterate", "correlation", "chisq", "fisher",
            "ols_with_covariate", "format_f64", "format_header", "format_kinship_rows", "format_rows", "format_frequency_header",
