@@ -88,6 +88,33 @@ template <int N, int NP, int P>
 __device__ __forceinline__ void reduce_to_tot(const double (&acc)[N], double *red, int red_rows, double *tot,
                                               int lane) {
     constexpr int LPS = 32 / P;
+    if (red_rows >= N) {
+        // the whole accumulator set fits the scratch (small loci: this runs once per stage, so it is kept free of
+        // run-time bounds -- constant store offsets, division by the constant N)
+#pragma unroll
+        for (int i = 0; i < N; i++) red[i * kRedPitch + lane] = acc[i];
+        __syncwarp();
+#pragma unroll
+        for (int t0 = 0; t0 < N * LPS; t0 += 32) {
+            const int t = t0 + lane;
+            if (t < N * LPS) {
+                const int u = (LPS == 1) ? 0 : t / N;
+                const int a = t - u * N;
+                const double *row = red + a * kRedPitch + u * P;
+                double s0 = row[0], s1 = row[1], s2 = row[2], s3 = row[3];
+#pragma unroll
+                for (int i = 4; i < P; i += 4) {
+                    s0 += row[i];
+                    s1 += row[i + 1];
+                    s2 += row[i + 2];
+                    s3 += row[i + 3];
+                }
+                tot[u * NP + a] = (s0 + s1) + (s2 + s3);
+            }
+        }
+        __syncwarp();
+        return;
+    }
     for (int b0 = 0; b0 < N; b0 += red_rows) {
         if (b0) __syncwarp();
 #pragma unroll
