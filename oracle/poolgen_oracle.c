@@ -407,24 +407,26 @@ int pgo_parse_sync_line(const char *line_in, char *chr, size_t chr_cap, uint64_t
                 rc = -2;
                 break;
             }
-            char *c = cur;
-            for (int j = 0; j < 6; j++) {
-                char *end = NULL;
-                if (*c < '0' || *c > '9') {
+            /* `.split(":").map(|x| x.parse::<u64>().expect(..))` (sync.rs:144-147): EVERY ':'-separated piece of the
+               pool field must parse (optional '+', then digits) or the reference panics; the first six are kept and
+               fewer than six is an index panic (sync.rs:148-150) */
+            const char *fend = tab ? tab : cur + strlen(cur);
+            const char *c = cur;
+            int j = 0;
+            for (;;) {
+                const char *d = (*c == '+') ? c + 1 : c;
+                const char *e = d;
+                while (e < fend && *e >= '0' && *e <= '9') e++;
+                if (e == d || (e < fend && *e != ':')) {
                     rc = -3;
                     break;
                 }
-                counts[(size_t)n * 6 + j] = strtoull(c, &end, 10);
-                if (j < 5) {
-                    if (*end != ':') {
-                        rc = -3;
-                        break;
-                    }
-                    c = end + 1;
-                } else {
-                    c = end; /* extra ':'-fields beyond the sixth are ignored by the reference (sync.rs:145-147) */
-                }
+                if (j < 6) counts[(size_t)n * 6 + j] = strtoull(d, NULL, 10);
+                j++;
+                if (e >= fend) break;
+                c = e + 1;
             }
+            if (!rc && j < 6) rc = -3;
             if (rc) break;
             n++;
         }

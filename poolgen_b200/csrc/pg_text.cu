@@ -8,7 +8,9 @@
 //     trip the pool-size assert of the filter, src/base/sync.rs:254-257): reported as an error;
 //   - every pool field holds at least six ':'-separated unsigned integers, the first six are A:T:C:G:N:D
 //     (src/base/sync.rs:134-137, 144-150); anything else makes the reference panic (`expect`): reported as an error;
-//   - a trailing '\r' before the newline is dropped (src/base/sync.rs:104-109).
+//   - a trailing '\r' before the newline is dropped (src/base/sync.rs:104-109);
+//   - an empty line or a line with fewer than three fields makes the reference panic (index out of bounds,
+//     src/base/sync.rs:112,121); such lines are skipped here.
 // Pipeline, every step asynchronous on the batch's stream (all counts stay on the device, so the host never waits
 // between the copy of the text and the parsed slab -- text_parse_async; text_parse_finish reads the outcome):
 //   tokenizer   16 bytes per thread: tok_count_kernel counts tabs + newlines and newlines per 4 KB block, an exclusive
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(256) text_parse_kernel(const TextParams p) {
             if (b > a && p.text[b - 1] == '\r') b--;  // Windows line end on the last pool field
             int j = 0;
             uint64_t v = 0;
-            bool digits = false, bad = false;
+            bool digits = false, bad = false, plus = false;
             for (uint32_t q = a; q <= b; q++) {
                 const char c = (q < b) ? p.text[q] : ':';
                 if (c == ':') {
@@ -227,6 +229,9 @@ __global__ void __launch_bounds__(256) text_parse_kernel(const TextParams p) {
                     j++;
                     v = 0;
                     digits = false;
+                    plus = false;
+                } else if (c == '+' && !digits && !plus) {
+                    plus = true;  // `parse::<u64>()` accepts one leading '+'
                 } else {
                     const unsigned d = (unsigned)(c - '0');
                     if (d > 9u) bad = true;

@@ -282,3 +282,66 @@ def test_deferred_text_stream(ctx):
     with pytest.raises(pb.PgError):
         scan.collect(t)
     scan.close()
+
+
+def test_text_fuzz_against_the_oracle_parser(ctx):
+    """random chunks (comment lines, CRLF, '+' signs, non-integer positions, extra numbers in a pool field, a last line
+    without its newline): the loci, positions and line offsets the device parser reports equal what the oracle's
+    restatement of `lparse` keeps, and the records equal those of the count path fed with the oracle-parsed counts"""
+    rng = np.random.default_rng(20261018)
+    n = 7
+    fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n), min_allele_frequency=0.01)
+    scan = pb.Scan(ctx, pb.KIND_CHISQ, fs, n, np.arange(6, dtype=np.uint8))
+    b = scan.batch(256)
+    for trial in range(40):
+        crlf = bool(rng.integers(0, 2))
+        eol = "\r\n" if crlf else "\n"
+        lines = []
+        for l in range(int(rng.integers(1, 200))):
+            r = rng.random()
+            if r < 0.08:
+                lines.append("#" + "x" * int(rng.integers(0, 30)))
+                continue
+            pos = str(int(rng.integers(0, 2 ** 40)))
+            if r < 0.14:
+                pos = rng.choice(["1e5", "12a", "-3", "", "0x10"])
+            elif r < 0.2:
+                pos = "+" + pos
+            fields = []
+            for i in range(n):
+                c = [str(int(v)) for v in rng.integers(0, 60, 6) * (rng.random(6) < 0.6)]
+                if rng.random() < 0.05:
+                    c[int(rng.integers(0, 6))] = "+" + c[0]
+                if rng.random() < 0.05:
+                    c.append("17")
+                fields.append(":".join(c))
+            lines.append(f"chr{int(rng.integers(1, 4))}\t{pos}\tN\t" + "\t".join(fields))
+        text = eol.join(lines) + (eol if rng.random() < 0.7 else "")
+        raw = text.encode()
+        kept, offs, cnts = [], [], []
+        cursor = 0
+        for ln in text.split(eol) if text else []:
+            start = cursor
+            cursor += len(ln.encode()) + len(eol)
+            if ln == "" or ln.startswith("#"):
+                continue
+            nn, ch, p, oc = pgo.parse_sync_line(ln + "\n")
+            if nn <= 0:
+                continue
+            assert nn == n
+            kept.append(p)
+            offs.append(start)
+            cnts.append(oc.T)
+        nl, off, p = b.upload_sync_text(raw)
+        assert nl == len(kept), (trial, nl, len(kept))
+        assert list(p) == kept and list(off) == offs
+        if nl == 0:
+            continue
+        b.run()
+        rt = b.fetch()
+        b.upload_counts(np.ascontiguousarray(np.array(cnts, dtype=np.uint32)))
+        b.run()
+        rc = b.fetch()
+        assert (rt.status == rc.status).all() and np.array_equal(rt.stats, rc.stats, equal_nan=True)
+    b.close()
+    scan.close()
