@@ -185,6 +185,12 @@ int pg_kin_append_columns(pg_kin *kin, const double *cols, int64_t P_add);
 int pg_kin_append_counts(pg_kin *kin, const pg_filter *filter, int n_alleles, const uint8_t *allele_codes,
                          const uint32_t *counts, int64_t n_loci, int keep_p_minus_1, int64_t *n_cols_added);
 int pg_kin_last_labels(pg_kin *kin, int64_t n_cols, int64_t *col_locus, uint8_t *col_allele);
+/* the same from a line-aligned chunk of sync TEXT (see pg_batch_upload_sync_text), parsed on the device straight into
+ * the loader's count slab; max_loci bounds the loci of a chunk.  pg_kin_text_labels: byte offset of each parsed locus'
+ * line and its position (host pointers valid until the next text append) -- col_locus of pg_kin_last_labels indexes them. */
+int pg_kin_append_sync_text(pg_kin *kin, const pg_filter *filter, const char *text, size_t n_bytes, int64_t max_loci,
+                            int keep_p_minus_1, int64_t *n_loci, int64_t *n_cols_added);
+int pg_kin_text_labels(pg_kin *kin, const uint64_t **line_offsets, const uint64_t **positions);
 /* synthetic biallelic columns (two per locus) generated on the device from the integer-hash workload */
 int pg_kin_synth(pg_kin *kin, uint64_t seed, int64_t first_locus, int64_t n_loci);
 int pg_kin_get_columns(pg_kin *kin, int64_t first, int64_t count, double *out /* [count][n_pools] */);

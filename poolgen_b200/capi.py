@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "pg_batch_bytes", "pg_scan_stream_begin", "pg_scan_submit_counts", "pg_scan_submit_counts_u16",
     "pg_scan_submit_counts_u8", "pg_scan_submit_freq", "pg_scan_collect", "pg_scan_text_labels", "pg_synth_counts_host", "pg_synth_phen_host", "pg_synth_sync_text_host",
     "pg_kin_open", "pg_kin_close", "pg_kin_reset", "pg_kin_columns", "pg_kin_append_columns", "pg_kin_append_counts",
-    "pg_kin_last_labels", "pg_kin_synth", "pg_kin_get_columns", "pg_kin_gram", "pg_kin_gram_time", "pg_kin_partial",
+    "pg_kin_last_labels", "pg_kin_append_sync_text", "pg_kin_text_labels", "pg_kin_synth", "pg_kin_get_columns", "pg_kin_gram", "pg_kin_gram_time", "pg_kin_partial",
     "pg_kin_partial_get", "pg_kin_partial_set", "pg_kin_eig_select", "pg_kin_eigvals", "pg_kin_set_covariates",
     "pg_kin_covar_scan", "pg_format_header", "pg_format_rows", "pg_format_kinship_rows", "pg_format_f64", "pg_sort_loci",
     "pg_format_frequency_header", "pg_format_frequency_rows",
@@ -133,6 +133,8 @@ def lib():
             "pg_kin_append_columns": (i, [vp, vp, i64]),
             "pg_kin_append_counts": (i, [vp, C.POINTER(_Filter), i, C.POINTER(C.c_uint8), vp, i64, i, C.POINTER(i64)]),
             "pg_kin_last_labels": (i, [vp, i64, vp, vp]),
+            "pg_kin_append_sync_text": (i, [vp, C.POINTER(_Filter), vp, C.c_size_t, i64, i, C.POINTER(i64), C.POINTER(i64)]),
+            "pg_kin_text_labels": (i, [vp, pvp, pvp]),
             "pg_kin_synth": (i, [vp, u64, i64, i64]),
             "pg_kin_get_columns": (i, [vp, i64, i64, vp]),
             "pg_kin_gram": (i, [vp]),
@@ -575,6 +577,29 @@ class Kinship:
         alle = np.empty(n_add, dtype=np.uint8)
         self._ck(lib().pg_kin_last_labels(self._h, n_add, loc.ctypes.data, alle.ctypes.data), "pg_kin_last_labels")
         return loc, alle
+
+    def append_sync_text(self, text: bytes, fs: FilterStats, max_loci: int, keep_p_minus_1: bool = False):
+        """a line-aligned chunk of sync text through the device parser and LoadAll: returns (n_loci, line offsets,
+        positions, col_locus, col_allele)"""
+        buf = bytes(text)
+        ps = np.ascontiguousarray(fs.pool_sizes, dtype=np.float64)
+        f = _Filter(int(fs.remove_ns), int(fs.min_coverage_depth), float(fs.min_allele_frequency),
+                    float(fs.max_missingness_rate), int(ps.size), ps.ctypes.data_as(C.POINTER(C.c_double)))
+        nl, added = C.c_int64(), C.c_int64()
+        self._ck(lib().pg_kin_append_sync_text(self._h, C.byref(f), buf, len(buf), int(max_loci), int(keep_p_minus_1),
+                                               C.byref(nl), C.byref(added)), "pg_kin_append_sync_text")
+        L, n_add = int(nl.value), int(added.value)
+        po, pp = C.c_void_p(), C.c_void_p()
+        self._ck(lib().pg_kin_text_labels(self._h, C.byref(po), C.byref(pp)), "pg_kin_text_labels")
+        if L:
+            off = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(L,)).copy()
+            pos = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_uint64)), shape=(L,)).copy()
+        else:
+            off, pos = np.zeros(0, np.uint64), np.zeros(0, np.uint64)
+        loc = np.empty(n_add, dtype=np.int64)
+        alle = np.empty(n_add, dtype=np.uint8)
+        self._ck(lib().pg_kin_last_labels(self._h, n_add, loc.ctypes.data, alle.ctypes.data), "pg_kin_last_labels")
+        return L, off, pos, loc, alle
 
     def synth(self, seed: int, first_locus: int, n_loci: int):
         self._ck(lib().pg_kin_synth(self._h, int(seed), int(first_locus), int(n_loci)), "pg_kin_synth")

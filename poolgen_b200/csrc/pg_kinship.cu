@@ -588,6 +588,7 @@ struct pg_kin {
     void *d_counts = nullptr;
     size_t counts_bytes = 0;
     double *d_w = nullptr;
+    pg::TextScratch *text = nullptr;  // sync text parsed on the device (pg_kin_append_sync_text)
 };
 
 static int kfail(pg_ctx *ctx, int code, const char *fmt, ...) {
@@ -656,6 +657,7 @@ int pg_kin_close(pg_kin *h) {
     cudaFree(h->d_scan_tmp);
     cudaFree(h->d_counts);
     cudaFree(h->d_w);
+    pg::text_scratch_free(h->text);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -686,16 +688,9 @@ int pg_kin_append_columns(pg_kin *h, const double *cols, int64_t P_add) {
     return PG_OK;
 }
 
-int pg_kin_append_counts(pg_kin *h, const pg_filter *filter, int n_alleles, const uint8_t *codes,
-                         const uint32_t *counts, int64_t n_loci, int keep_p_minus_1, int64_t *n_cols_added) {
-    if (!h || !filter || !codes || (!counts && n_loci > 0) || n_loci < 0 || n_alleles < 1 || n_alleles > PG_MAX_ALLELES)
-        return PG_ERR_ARG;
+// loader scratch for n_loci loci of n_alleles stored columns
+static int kin_reserve(pg_kin *h, int64_t n_loci, int n_alleles) {
     pg_ctx *ctx = h->ctx;
-    if (filter->n_pool_sizes != h->n || !filter->pool_sizes)
-        return kfail(ctx, PG_ERR_ARG, "pg_kin_append_counts: %d pool sizes for %d pools", filter->n_pool_sizes, h->n);
-    KCUDA(ctx, cudaSetDevice(ctx->device));
-    if (n_cols_added) *n_cols_added = 0;
-    if (n_loci == 0) return PG_OK;
     if (h->load_cap < n_loci) {
         KCUDA(ctx, cudaStreamSynchronize(h->stream));
         cudaFree(h->d_sel);
@@ -722,6 +717,13 @@ int pg_kin_append_counts(pg_kin *h, const pg_filter *filter, int n_alleles, cons
         KCUDA(ctx, cudaMalloc(&h->d_counts, cbytes));
         h->counts_bytes = cbytes;
     }
+    return PG_OK;
+}
+
+// LoadAll over the n_loci loci whose counts are in h->d_counts ([locus][allele][pool])
+static int kin_load_resident(pg_kin *h, const pg_filter *filter, int n_alleles, const uint8_t *codes, int64_t n_loci,
+                             int keep_p_minus_1, int64_t *n_cols_added, const char *who) {
+    pg_ctx *ctx = h->ctx;
     if (!h->d_w) KCUDA(ctx, cudaMalloc(&h->d_w, (size_t)h->n * 8));
     {
         std::vector<double> w(h->n);
@@ -731,7 +733,6 @@ int pg_kin_append_counts(pg_kin *h, const pg_filter *filter, int n_alleles, cons
         KCUDA(ctx, cudaMemcpyAsync(h->d_w, w.data(), (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
         KCUDA(ctx, cudaStreamSynchronize(h->stream));
     }
-    KCUDA(ctx, cudaMemcpyAsync(h->d_counts, counts, cbytes, cudaMemcpyHostToDevice, h->stream));
     pg::LoadParams lp;
     memset(&lp, 0, sizeof lp);
     lp.counts = (const uint32_t *)h->d_counts;
@@ -766,12 +767,73 @@ int pg_kin_append_counts(pg_kin *h, const pg_filter *filter, int n_alleles, cons
     KCUDA(ctx, cudaMemcpyAsync(&added, h->d_off + n_loci, 8, cudaMemcpyDeviceToHost, h->stream));
     KCUDA(ctx, cudaStreamSynchronize(h->stream));
     if (h->P + added > h->cap)
-        return kfail(ctx, PG_ERR_ARG, "pg_kin_append_counts: %lld + %lld columns > capacity %lld", (long long)h->P,
+        return kfail(ctx, PG_ERR_ARG, "%s: %lld + %lld columns > capacity %lld", who, (long long)h->P,
                      (long long)added, (long long)h->cap);
     pg::load_emit_kernel<<<grid, 256, 0, h->stream>>>(lp);
     KCUDA(ctx, cudaGetLastError());
     h->P += added;
     if (n_cols_added) *n_cols_added = added;
+    return PG_OK;
+}
+
+int pg_kin_append_counts(pg_kin *h, const pg_filter *filter, int n_alleles, const uint8_t *codes,
+                         const uint32_t *counts, int64_t n_loci, int keep_p_minus_1, int64_t *n_cols_added) {
+    if (!h || !filter || !codes || (!counts && n_loci > 0) || n_loci < 0 || n_alleles < 1 || n_alleles > PG_MAX_ALLELES)
+        return PG_ERR_ARG;
+    pg_ctx *ctx = h->ctx;
+    if (filter->n_pool_sizes != h->n || !filter->pool_sizes)
+        return kfail(ctx, PG_ERR_ARG, "pg_kin_append_counts: %d pool sizes for %d pools", filter->n_pool_sizes, h->n);
+    KCUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_cols_added) *n_cols_added = 0;
+    if (n_loci == 0) return PG_OK;
+    int rc = kin_reserve(h, n_loci, n_alleles);
+    if (rc) return rc;
+    KCUDA(ctx, cudaMemcpyAsync(h->d_counts, counts, (size_t)n_loci * n_alleles * h->n * 4, cudaMemcpyHostToDevice,
+                               h->stream));
+    return kin_load_resident(h, filter, n_alleles, codes, n_loci, keep_p_minus_1, n_cols_added, "pg_kin_append_counts");
+}
+
+// the same from a line-aligned chunk of sync TEXT: parsed on the device (pg_text.cu) straight into the loader's count
+// slab; pg_kin_text_labels hands out line offsets and positions of the parsed loci for the output rows
+int pg_kin_append_sync_text(pg_kin *h, const pg_filter *filter, const char *text, size_t n_bytes, int64_t max_loci,
+                            int keep_p_minus_1, int64_t *n_loci_out, int64_t *n_cols_added) {
+    if (!h || !filter || (!text && n_bytes > 0) || max_loci < 1) return PG_ERR_ARG;
+    pg_ctx *ctx = h->ctx;
+    if (filter->n_pool_sizes != h->n || !filter->pool_sizes)
+        return kfail(ctx, PG_ERR_ARG, "pg_kin_append_sync_text: %d pool sizes for %d pools", filter->n_pool_sizes, h->n);
+    KCUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_cols_added) *n_cols_added = 0;
+    if (n_loci_out) *n_loci_out = 0;
+    int rc = kin_reserve(h, max_loci, 6);
+    if (rc) return rc;
+    cudaError_t ce = cudaSuccess;
+    uint64_t at = 0;
+    int64_t L = 0;
+    size_t line_cap = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        KCUDA(ctx, pg::text_parse_async(&h->text, text, n_bytes, h->n, (uint32_t *)h->d_counts, max_loci, line_cap,
+                                        ctx->sm_count, h->stream));
+        L = pg::text_parse_finish(h->text, h->stream, &ce, &at);
+        if (L != -5) break;
+        line_cap = (size_t)at + 1;  // more comment / blank lines than the default bound: repeat with the exact number
+    }
+    if (L == -1) return kfail(ctx, PG_ERR_CUDA, "pg_kin_append_sync_text: %s", cudaGetErrorString(ce));
+    if (L == -2) return kfail(ctx, PG_ERR_ARG, "pg_kin_append_sync_text: more loci in the chunk than max_loci %lld", (long long)max_loci);
+    if (L == -3) return kfail(ctx, PG_ERR_ARG, "pg_kin_append_sync_text: the line at byte %llu does not hold %d pools", (unsigned long long)at, h->n);
+    if (L == -4) return kfail(ctx, PG_ERR_ARG, "pg_kin_append_sync_text: malformed pool field at byte %llu", (unsigned long long)at);
+    if (L < 0) return kfail(ctx, PG_ERR_ARG, "pg_kin_append_sync_text: the chunk could not be parsed (%lld)", (long long)L);
+    if (n_loci_out) *n_loci_out = L;
+    if (L == 0) return PG_OK;
+    static const uint8_t sync_codes[6] = {0, 1, 2, 3, 4, 5};
+    return kin_load_resident(h, filter, 6, sync_codes, L, keep_p_minus_1, n_cols_added, "pg_kin_append_sync_text");
+}
+
+int pg_kin_text_labels(pg_kin *h, const uint64_t **line_offsets, const uint64_t **positions) {
+    if (!h) return PG_ERR_ARG;
+    if (!h->text) return kfail(h->ctx, PG_ERR_STATE, "pg_kin_text_labels before pg_kin_append_sync_text");
+    KCUDA(h->ctx, cudaStreamSynchronize(h->stream));  // the label copy was enqueued by the parse
+    if (line_offsets) *line_offsets = pg::text_offsets(h->text);
+    if (positions) *positions = pg::text_positions(h->text);
     return PG_OK;
 }
 

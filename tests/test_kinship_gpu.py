@@ -183,3 +183,31 @@ def test_sync2csv_from_the_device_loader(ctx):
                                    chr_index=c1["chrom_idx"]).decode()
     ocols, olabels = pgo.load_columns(counts.transpose(0, 2, 1).astype(np.uint64), c1["codes"], H.oracle_fs(fs), True)
     assert got == _oracle_sync2csv_rows(ocols, olabels, chroms, pos) and got.count("\n") == len(olabels) > 1000
+
+
+def test_sync2csv_from_sync_text(ctx):
+    """text in -> rows out for sync2csv: chunks of sync text through pg_kin_append_sync_text (device parser + LoadAll),
+    labels from the parsed text, rows equal to those of the count path"""
+    from tests.test_text_gpu import _sync_text
+    c1 = H.load_c1()
+    fs = pb.FilterStats(pool_sizes=c1["pool_sizes"], min_coverage_depth=5, min_allele_frequency=0.01)
+    counts = c1["counts"][:3000]
+    L = counts.shape[0]
+    names = [str(s) for s in c1["chrom_names"]]
+    chroms = [names[i] for i in c1["chrom_idx"][:L]]
+    pos = [int(p) for p in c1["pos"][:L]]
+    text = _sync_text(counts, chroms, pos, extra=[(7, "# a comment"), (11, "Chromosome1\tx\tN\t" + "\t".join(["1:1:1:1:0:0"] * 5))])
+    kin = pb.Kinship(ctx, 5, 5 * L)
+    nl, off, p, loc, alle = kin.append_sync_text(text, fs, L, keep_p_minus_1=False)
+    G = kin.get_columns(0, kin.columns)
+    kin.reset()
+    loc2, alle2 = kin.append_counts(counts, c1["codes"], fs, False)
+    G2 = kin.get_columns(0, kin.columns)
+    kin.close()
+    assert nl == L and list(p) == pos
+    assert np.array_equal(loc, loc2) and np.array_equal(alle, alle2) and np.array_equal(G, G2, equal_nan=True)
+    order = pb.sort_loci(p, text=text, line_offsets=off)
+    got = pb.format_frequency_rows(G, loc, alle, p, locus_order=order, text=text, line_offsets=off)
+    order2 = pb.sort_loci(pos, chr_names=names, chr_index=c1["chrom_idx"][:L])
+    expect = pb.format_frequency_rows(G2, loc2, alle2, pos, locus_order=order2, chr_names=names, chr_index=c1["chrom_idx"][:L])
+    assert got == expect and got.count(b"\n") == len(loc) > 1000
