@@ -272,3 +272,145 @@ class FileSync:
             raise PgError("FileSync::read_analyse_write takes tables::chisq or tables::fisher")
         return _read_analyse_write(ctx, kind, filter_stats, int(np.asarray(filter_stats.pool_sizes).size), None,
                                    self.filename, self.test, out, n_threads, block_bytes)
+
+
+# ---- whole-matrix entries: sync2csv (SaveCsv::write_csv, src/base/sync.rs:1182-1262) and ols_iter_with_kinship
+# (into_genotypes_and_phenotypes + ols_with_covariate, src/base/sync.rs:1106-1179, src/gwas/ols.rs:278-436) ----------
+@dataclass
+class _LoadedColumns:
+    kin: object            # capi.Kinship holding the allele columns on the device, in file order
+    col_locus: np.ndarray  # int64 [P] locus ordinal (over the kept loci of the whole file) of every column
+    col_allele: np.ndarray # uint8 [P]
+    chr_names: list        # distinct chromosome names
+    chr_index: np.ndarray  # uint32 [L]
+    positions: np.ndarray  # uint64 [L]
+
+
+def _load_all(ctx: Context, fname: str, n_pools: int, fs: FilterStats, keep_p_minus_1: bool, max_columns: int,
+              block_bytes: int) -> _LoadedColumns:
+    """LoadAll::load over the whole file, block by block through the device parser and loader"""
+    kin = capi.Kinship(ctx, n_pools, max_columns)
+    max_loci = block_bytes // (12 * n_pools + 5) + 2
+    names, index_of = [], {}
+    chr_index, positions, col_locus, col_allele = [], [], [], []
+    base = 0
+    try:
+        with open(fname, "rb") as fh:
+            carry = b""
+            while True:
+                data = fh.read(block_bytes)
+                if not data and not carry:
+                    break
+                block = carry + data
+                if data:
+                    cut = block.rfind(b"\n") + 1
+                    if cut == 0:
+                        raise PgError(f"a line of {fname} is longer than the block size {block_bytes}")
+                    block, carry = block[:cut], block[cut:]
+                else:
+                    carry = b""
+                L, off, pos, loc, alle = kin.append_sync_text(block, fs, max_loci, keep_p_minus_1)
+                for o in off:  # chromosome = the text up to the first tab of the locus' line
+                    o = int(o)
+                    nm = block[o:block.index(b"\t", o)]
+                    if nm not in index_of:
+                        index_of[nm] = len(names)
+                        names.append(nm)
+                    chr_index.append(index_of[nm])
+                positions.append(pos)
+                col_locus.append(loc + base)
+                col_allele.append(alle)
+                base += L
+                if not data:
+                    break
+    except Exception:
+        kin.close()
+        raise
+    cat = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dt)
+    return _LoadedColumns(kin, cat(col_locus, np.int64), cat(col_allele, np.uint8), names,
+                          np.array(chr_index, dtype=np.uint32), cat(positions, np.uint64))
+
+
+def _count_columns_bound(fname: str) -> int:
+    """an upper bound of the allele columns LoadAll can emit: five per line"""
+    with open(fname, "rb") as fh:
+        lines = sum(chunk.count(b"\n") for chunk in iter(lambda: fh.read(1 << 24), b"")) + 1
+    return 5 * lines
+
+
+def write_csv(self, ctx: Context, filter_stats: FilterStats, keep_p_minus_1: bool, out: str, n_threads: int,
+              block_bytes: int = 32 << 20) -> str:
+    """sync2csv: `SaveCsv::write_csv(&self, &FilterStats, keep_p_minus_1, out, n_threads)` of FileSyncPhen
+    (src/base/sync.rs:1182-1262): header `#chr,pos,allele,<pool names>`, one row per kept allele of every kept locus,
+    loci in LoadAll's order (stable by chromosome, position), frequencies through parse_f64_roundup_and_own(x, 6)"""
+    if out == "":
+        bname = ".".join(self.filename_sync.split(".")[:-1])
+        out = f"{bname}-{time.time()}-allele_frequencies.csv"
+    if os.path.exists(out):
+        raise PgError("Cannot write to output file")
+    ld = _load_all(ctx, self.filename_sync, len(self.pool_names), filter_stats, keep_p_minus_1,
+                   _count_columns_bound(self.filename_sync), block_bytes)
+    try:
+        if ld.col_locus.size == 0:
+            raise PgError("No data passed the filtering variables. Please decrease minimum depth, and/or minimum "
+                          "allele frequency.")  # assert at src/base/sync.rs:1219
+        G = ld.kin.get_columns(0, ld.kin.columns)
+    finally:
+        ld.kin.close()
+    order = capi.sort_loci(ld.positions, chr_names=ld.chr_names, chr_index=ld.chr_index)
+    rows = capi.format_frequency_rows(G, ld.col_locus, ld.col_allele, ld.positions, locus_order=order,
+                                      n_threads=max(1, n_threads), chr_names=ld.chr_names, chr_index=ld.chr_index)
+    with open(out, "xb") as fo:
+        fo.write(capi.format_frequency_header(self.pool_names))
+        fo.write(rows)
+    return out
+
+
+def ols_iter_with_kinship(self, ctx: Context, filter_stats: FilterStats, keep_p_minus_1: bool,
+                          xxt_eigen_variance_explained: float, out: str, n_threads: int,
+                          block_bytes: int = 32 << 20) -> str:
+    """`poolgen ols_iter_with_kinship` (src/main.rs:280-298): into_genotypes_and_phenotypes (src/base/sync.rs:1106-1179)
+    then ols_with_covariate (src/gwas/ols.rs:278-436) and its writer, including the label indexing of
+    src/gwas/ols.rs:421-424 (row i of the allele columns carries entry i of the label vectors, whose entry 0 is the
+    intercept's)"""
+    if out != "" and os.path.exists(out):
+        raise PgError("Cannot write to output file")
+    if np.isnan(self.phen_matrix).any():
+        raise PgError("pools with missing phenotypes: remove them before the scan (the reference's remove_missing, "
+                      "src/gwas/ols.rs:286)")
+    ld = _load_all(ctx, self.filename_sync, len(self.pool_names), filter_stats, keep_p_minus_1,
+                   _count_columns_bound(self.filename_sync), block_bytes)
+    try:
+        P = ld.kin.columns
+        if P == 0:
+            raise PgError("No data passed the filtering variables.")
+        ld.kin.gram()
+        n_eigenvecs = ld.kin.eig_select(P, float(xxt_eigen_variance_explained))
+        beta, _var, pval = ld.kin.covar_scan(self.phen_matrix)   # [k, P] in file order
+    finally:
+        ld.kin.close()
+    # the matrix columns follow the loci sorted by (chromosome, position): permute the records into that order
+    order = capi.sort_loci(ld.positions, chr_names=ld.chr_names, chr_index=ld.chr_index)
+    first = np.full(int(ld.positions.size) + 1, -1, dtype=np.int64)
+    count = np.zeros(int(ld.positions.size) + 1, dtype=np.int64)
+    for c, l in enumerate(ld.col_locus):
+        if first[l] < 0:
+            first[l] = c
+        count[l] += 1
+    seq = np.concatenate([np.arange(first[l], first[l] + count[l]) for l in order if first[l] >= 0]).astype(np.int64)
+    names = [n.decode() for n in ld.chr_names]
+    chromosome = ["intercept"] + [names[ld.chr_index[ld.col_locus[c]]] for c in seq]
+    position = [0] + [int(ld.positions[ld.col_locus[c]]) for c in seq]
+    allele = ["intercept"] + [capi.ALLELE_NAMES[ld.col_allele[c]] for c in seq]
+    rows = capi.format_kinship_rows(chromosome, position, allele, beta[:, seq], pval[:, seq], n_threads=max(1, n_threads))
+    if out == "":  # src/gwas/ols.rs:374-398
+        bname = ".".join(self.filename_sync.split(".")[:-1])
+        out = f"{bname}-ols_iterative_xxt_{n_eigenvecs + 1}_eigens-{time.time()}.csv"
+    with open(out, "xb") as fo:
+        fo.write(capi.format_header(capi.KIND_OLS_KINSHIP))
+        fo.write(rows)
+    return out
+
+
+FileSyncPhen.write_csv = write_csv
+FileSyncPhen.ols_iter_with_kinship = ols_iter_with_kinship

@@ -99,3 +99,78 @@ def test_read_analyse_write_c1(ctx, tmp_path, analysis):
     auto = src.read_analyse_write(ctx, fs, "", 2, fn)
     assert auto.startswith(str(tmp_path / "test-")) and auto.endswith(f"-{analysis}.csv")
     assert open(auto, "rb").read() == expect
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("keep_p_minus_1", [False, True])
+def test_sync2csv_file(ctx, tmp_path, keep_p_minus_1):
+    """`poolgen sync2csv -f test.sync -p test.csv [--keep-p-minus-1]` through FileSyncPhen.write_csv: small blocks, the
+    chromosomes of the file shuffled so that LoadAll's sort matters; against rows built from the oracle's loader"""
+    from oracle import pgo
+    from tests.test_text_gpu import _sync_text
+    from tests.test_writer import _oracle_sync2csv_rows
+    c1 = H.load_c1()
+    L = 2500
+    counts = c1["counts"][:L]
+    names = ["chrB", "chrA", "chr10", "chr9"]
+    chroms = [names[(l // 300) % 4] for l in range(L)]
+    pos = [int(p) for p in c1["pos"][:L]]
+    fsync = str(tmp_path / "t.sync")
+    with open(fsync, "wb") as fh:
+        fh.write(_sync_text(counts, chroms, pos))
+    fphen = str(tmp_path / "t.csv")
+    _write_c1_phen(fphen)
+    phen = pb.FilePhen(fphen, ",", 0, 1, [2, 3]).lparse()
+    fs = pb.FilterStats(pool_sizes=phen.pool_sizes, min_coverage_depth=5, min_allele_frequency=0.01)
+    src = pb.FileSyncPhen(fsync, phen.pool_names, phen.pool_sizes, phen.phen_matrix, "sync2csv")
+    out = src.write_csv(ctx, fs, keep_p_minus_1, str(tmp_path / "freq.csv"), 2, block_bytes=40 << 10)
+    got = open(out, "rb").read().decode()
+    ocols, olabels = pgo.load_columns(counts.transpose(0, 2, 1).astype(np.uint64), c1["codes"], H.oracle_fs(fs),
+                                      keep_p_minus_1)
+    expect = "#chr,pos,allele,G1,G2,G3,G4,G5\n" + _oracle_sync2csv_rows(ocols, olabels, chroms, pos)
+    assert got == expect and got.count("\n") == len(olabels) + 1 > 1000
+
+
+@pytest.mark.gpu
+def test_ols_iter_with_kinship_file(ctx, tmp_path):
+    """`poolgen ols_iter_with_kinship` through FileSyncPhen.ols_iter_with_kinship: rows phenotype-outer / column-inner
+    in LoadAll's locus order with the reference's label indexing (row i carries label i of the vectors that start with
+    the intercept's entry), numbers against the oracle's ols_with_covariate"""
+    from oracle import pgo
+    from tests.test_text_gpu import _sync_text
+    c1 = H.load_c1()
+    L = 1200
+    counts = c1["counts"][:L]
+    names = ["chrB", "chrA"]
+    chroms = [names[(l // 250) % 2] for l in range(L)]
+    pos = [int(p) for p in c1["pos"][:L]]
+    fsync = str(tmp_path / "k.sync")
+    with open(fsync, "wb") as fh:
+        fh.write(_sync_text(counts, chroms, pos))
+    fphen = str(tmp_path / "k.csv")
+    _write_c1_phen(fphen)
+    phen = pb.FilePhen(fphen, ",", 0, 1, [2, 3]).lparse()
+    fs = pb.FilterStats(pool_sizes=phen.pool_sizes, min_coverage_depth=5, min_allele_frequency=0.01)
+    src = pb.FileSyncPhen(fsync, phen.pool_names, phen.pool_sizes, phen.phen_matrix, "ols_iter_with_kinship")
+    out = src.ols_iter_with_kinship(ctx, fs, True, 0.75, str(tmp_path / "kin.csv"), 2, block_bytes=40 << 10)
+    lines = open(out).read().split("\n")
+    assert lines[0] == "#chr,pos,alleles,phenotype,statistic,pvalue" and lines[-1] == ""
+    rows = [ln.split(",") for ln in lines[1:-1]]
+    # oracle: columns in LoadAll's order
+    ocols, olabels = pgo.load_columns(counts.transpose(0, 2, 1).astype(np.uint64), c1["codes"], H.oracle_fs(fs), True)
+    loci = sorted(range(L), key=lambda l: (chroms[l].encode(), pos[l]))
+    by_locus = {}
+    for c, (l, a) in enumerate(olabels):
+        by_locus.setdefault(l, []).append((c, a))
+    seq = [ca for l in loci for ca in by_locus.get(l, [])]
+    P = len(seq)
+    G = ocols[[c for c, _ in seq]]
+    om, ob, ov, op = pgo.ols_with_covariate(G, phen.phen_matrix, 0.75)
+    assert len(rows) == 2 * P
+    labels = [("intercept", "0", "intercept")] + [(chroms[olabels[c][0]], str(pos[olabels[c][0]]), "ATCGND"[a]) for c, a in seq]
+    for j in range(2):
+        for i in range(P):
+            r = rows[j * P + i]
+            assert tuple(r[:3]) == labels[i] and r[3] == f"Pheno_{j}", (r, labels[i])   # the shifted labels of ols.rs:421-424
+            for got, exp, tol in ((float(r[4]), ob[i, j], 1e-7), (float(r[5]), op[i, j], 1e-6)):
+                assert (np.isnan(got) and np.isnan(exp)) or abs(got - exp) <= tol * max(abs(exp), 1e-3), (r, exp)
