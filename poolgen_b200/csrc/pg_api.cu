@@ -367,22 +367,28 @@ static int upload_counts_t(pg_batch *b, const CT *counts, int64_t n_loci) {
     if (n_loci == 0) return PG_OK;
     const size_t bytes = (size_t)n_loci * s->A_in * s->n * sizeof(CT);
     const bool reg = is_regression(s);
-    int rc = ensure_stage(b, (size_t)b->cap * s->A_in * s->n * sizeof(CT));
+    const size_t wide_bytes = (size_t)b->cap * s->A_in * s->n * 4;
+    // the count tests read u32 counts: narrow slabs land behind the u32 area and are widened on the device
+    int rc = ensure_stage(b, reg ? (size_t)b->cap * s->A_in * s->n * sizeof(CT) : wide_bytes + (sizeof(CT) == 4 ? 0 : bytes));
     if (rc) return rc;
     if (reg) {
         PG_CUDA(ctx, cudaMemcpyAsync(b->d_stage, counts, bytes, cudaMemcpyHostToDevice, b->stream));
-        if (sizeof(CT) == 4)
+        if constexpr (sizeof(CT) == 4)
             PG_CUDA(ctx, pg::launch_ingest_u32((const uint32_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
                                                ingest_out(b, 0), b->stream));
-        else if (sizeof(CT) == 1)
+        else if constexpr (sizeof(CT) == 1)
             PG_CUDA(ctx, pg::launch_ingest_u8((const uint8_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
                                               ingest_out(b, 0), b->stream));
         else
             PG_CUDA(ctx, pg::launch_ingest_u16((const uint16_t *)b->d_stage, n_loci, s->n, s->A_in, s->drop_col, s->lay,
                                                ingest_out(b, 0), b->stream));
-    } else {
-        if (sizeof(CT) != 4) return fail(ctx, PG_ERR_UNSUPPORTED, "narrow counts are not wired for the table tests yet");
+    } else if constexpr (sizeof(CT) == 4) {
         PG_CUDA(ctx, cudaMemcpyAsync(b->d_stage, counts, bytes, cudaMemcpyHostToDevice, b->stream));
+    } else {
+        void *narrow = (char *)b->d_stage + wide_bytes;
+        PG_CUDA(ctx, cudaMemcpyAsync(narrow, counts, bytes, cudaMemcpyHostToDevice, b->stream));
+        PG_CUDA(ctx, pg::launch_widen(narrow, (int)sizeof(CT), (uint32_t *)b->d_stage, (size_t)n_loci * s->A_in * s->n,
+                                      b->stream));
     }
     b->input_is_counts = 1;
     return PG_OK;

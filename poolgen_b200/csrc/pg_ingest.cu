@@ -181,6 +181,21 @@ cudaError_t launch_ingest_freq(const double *fin, const uint32_t *din, int64_t n
                                                             o.w, hint_params(o));
     return cudaGetLastError();
 }
+template <typename CT>
+__global__ void __launch_bounds__(256) widen_kernel(const CT *__restrict__ src, uint32_t *__restrict__ dst, size_t count) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (uint32_t)src[i];
+}
+cudaError_t launch_widen(const void *src, int elem_bytes, uint32_t *dst, size_t count, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    if (elem_bytes == 1)
+        widen_kernel<uint8_t><<<grid_for((int64_t)count), 256, 0, s>>>((const uint8_t *)src, dst, count);
+    else if (elem_bytes == 2)
+        widen_kernel<uint16_t><<<grid_for((int64_t)count), 256, 0, s>>>((const uint16_t *)src, dst, count);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
 cudaError_t launch_synth(uint64_t seed, int64_t first_locus, int64_t n_loci, int n, int A_in, uint32_t *counts,
                          cudaStream_t s) {
     if (n_loci <= 0) return cudaSuccess;

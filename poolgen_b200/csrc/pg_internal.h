@@ -135,6 +135,8 @@ cudaError_t launch_ingest_freq(const double *freq_in, const uint32_t *depth_in, 
                                const IngestOut &o, cudaStream_t s);
 cudaError_t launch_synth(uint64_t seed, int64_t first_locus, int64_t n_loci, int n, int A_in,
                          uint32_t *counts, cudaStream_t s);
+// u8 / u16 counts -> u32 (the count tests read u32)
+cudaError_t launch_widen(const void *src, int elem_bytes, uint32_t *dst, size_t count, cudaStream_t s);
 
 // sync text -> counts[locus][6][n_pools] on the device (pg_text.cu)
 struct TextScratch;

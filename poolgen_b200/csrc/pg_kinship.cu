@@ -378,8 +378,6 @@ struct CovarParams {
     double *beta, *var, *pval;  // [k][P]
 };
 
-constexpr int kCovarMaxVec = 12;  // nq + k vectors resident in shared memory (templated on the count)
-
 template <int NV>
 __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
     extern __shared__ __align__(16) double vs[];  // [NV][ldg]

@@ -774,13 +774,14 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
                     fabs(cs[j] - cs[l]) <= tol_rel * fmax(fabs(cs[j]), fabs(cs[l])))
                     tie = true;
         if (tie) {
-            if (DEFER) {  // the streaming kernel leaves exact evaluations to the fix-up kernel
+            if constexpr (DEFER) {  // the streaming kernel leaves exact evaluations to the fix-up kernel
                 redo_mode = REDO_DEFER;
                 return;
-            }
+            } else {
 #pragma unroll
-            for (int j = 0; j < A; j++)
-                if ((kept >> j) & 1u) cs[j] = exact_colsum<A>(p, locus, j, kept);
+                for (int j = 0; j < A; j++)
+                    if ((kept >> j) & 1u) cs[j] = exact_colsum<A>(p, locus, j, kept);
+            }
         }
 #pragma unroll
         for (int j = 0; j < A; j++) {

@@ -438,3 +438,27 @@ def test_chisq_many_pools(ctx, n, A, L, kw):
     st = H.compare_tables(pb.KIND_CHISQ, full, codes, fs, dev, label=f"chisq n={n}")
     assert st["ok"] > 0.5 * L
     print(st)
+
+
+@pytest.mark.parametrize("kind", [pb.KIND_CHISQ, pb.KIND_FISHER])
+def test_tables_narrow_counts(ctx, kind):
+    """u16 / u8 count slabs for the count tests (widened on the device) give the records of the u32 slab, also through
+    the streaming submit"""
+    n, A, L = 3, 4, 5000
+    counts = pb.synth_counts_host(0x7AB1E, 0, L, n, A)
+    assert counts.max() < 256
+    fs = _fs(np.full(n, 1.0 / n))
+    scan = pb.Scan(ctx, kind, fs, n, np.arange(A, dtype=np.uint8))
+    ref = scan.run_counts(counts)
+    for dt in (np.uint16, np.uint8):
+        r = scan.run_counts(counts.astype(dt))
+        assert (r.status == ref.status).all() and np.array_equal(r.stats, ref.stats, equal_nan=True)
+        assert (r.alleles == ref.alleles).all()
+    scan.stream_begin(2048)
+    parts, pend = [], []
+    for l0 in range(0, L, 2048):
+        pend.append(scan.submit_counts(np.ascontiguousarray(counts[l0:l0 + 2048].astype(np.uint8))))
+    for t in pend:
+        parts.append(scan.collect(t))
+    scan.close()
+    assert np.array_equal(np.concatenate([p.stats for p in parts]), ref.stats, equal_nan=True)
