@@ -268,13 +268,16 @@ struct TextScratch {
     int64_t max_loci = 0;
 };
 
+// capacity with headroom: consecutive chunks of a file differ by a few lines, and a reallocation (cudaFree
+// synchronises the device) in the middle of the stream costs more than the memory
 static cudaError_t grow(void **p, size_t *cap, size_t need, size_t elem) {
     if (*cap >= need) return cudaSuccess;
     cudaFree(*p);
     *p = nullptr;
     *cap = 0;
-    cudaError_t e = cudaMalloc(p, need * elem);
-    if (e == cudaSuccess) *cap = need;
+    const size_t want = need + need / 8 + 65536;
+    cudaError_t e = cudaMalloc(p, want * elem);
+    if (e == cudaSuccess) *cap = want;
     return e;
 }
 
