@@ -164,12 +164,20 @@ struct Labels {
     }
 };
 
-void format_range(int kind, const pg_results *res, const pg_row_labels *lab, int64_t lo, int64_t hi, std::string &out) {
+void format_range(int kind, const pg_results *res, const pg_row_labels *lab, int64_t lo, int64_t hi, std::string &dst) {
+    // rows are appended to a string that lives on this thread's stack and handed over once: the std::string headers of
+    // the per-thread pieces sit side by side in one vector, and appending through them would bounce their cache line
+    // between the cores on every row
+    std::string out;
+    struct Handover {
+        std::string &from, &to;
+        ~Handover() { to = std::move(from); }
+    } handover{out, dst};
     const Labels L{lab};
     const int S = res->n_slots, k = res->n_phen;
     const Rounder r6(6), r8(8), r12(12);
     char line[1024];
-    out.reserve((size_t)(hi - lo) * 48);
+    out.reserve((size_t)(hi - lo) * 64 * (size_t)(S * k > 0 ? S * k : 1) / 2 + 4096);
     for (int64_t l = lo; l < hi; l++) {
         const uint64_t mv = res->meta[l];
         if ((mv & 0xffu) != PG_LOCUS_OK) continue;  // None: no row (src/base/sync.rs:864-867)
@@ -293,8 +301,9 @@ int pg_format_kinship_rows(int64_t n_columns, int k, const char *const *chromoso
     if (T < 1) T = 1;
     std::vector<std::string> parts((size_t)T);
     auto work = [&](int t) {
-        std::string &o = parts[(size_t)t];
+        std::string o;  // thread-local, handed over at the end (see format_range)
         const int64_t lo = rows * t / T, hi = rows * (t + 1) / T;
+        o.reserve((size_t)(hi - lo) * 64 + 4096);
         char num[420];
         for (int64_t r = lo; r < hi; r++) {
             const int64_t j = r / n_columns, i = r - j * n_columns;  // phenotype outer, column inner
@@ -311,6 +320,7 @@ int pg_format_kinship_rows(int64_t n_columns, int k, const char *const *chromoso
             o.append(num, (size_t)(put_f64(pval[(size_t)j * n_columns + i], num) - num));
             o.push_back('\n');
         }
+        parts[(size_t)t] = std::move(o);
     };
     if (T == 1) {
         work(0);
@@ -400,7 +410,7 @@ int pg_format_frequency_rows(int64_t n_columns, int n_pools, const double *colum
     std::vector<std::string> parts((size_t)T);
     const Labels L{labels};
     auto work = [&](int t) {
-        std::string &o = parts[(size_t)t];
+        std::string o;  // thread-local, handed over at the end (see format_range)
         const Rounder r6(6);
         const int64_t lo = rows * t / T, hi = rows * (t + 1) / T;
         o.reserve((size_t)(hi - lo) * (size_t)(24 + 9 * n_pools));
@@ -423,6 +433,7 @@ int pg_format_frequency_rows(int64_t n_columns, int n_pools, const double *colum
             }
             o.push_back('\n');
         }
+        parts[(size_t)t] = std::move(o);
     };
     if (T == 1) {
         work(0);
