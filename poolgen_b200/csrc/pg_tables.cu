@@ -119,7 +119,7 @@ __device__ __forceinline__ double ratio_t(const double (&c)[NP][NA], unsigned km
 }
 
 template <int NP, int NA>
-__global__ void __launch_bounds__(kTabThreads) tables_kernel_t(const TableParams p) {
+__global__ void __launch_bounds__(kTabThreads, (NP * NA <= 8) ? 12 : 8) tables_kernel_t(const TableParams p) {
     extern __shared__ __align__(16) uint32_t sm_counts[];
     constexpr int per_locus = NA * NP;
     const int64_t tiles = (p.n_loci + kTabThreads - 1) / kTabThreads;
@@ -362,7 +362,7 @@ static cudaError_t launch_tables_t(const TableParams &p, int sm_count, cudaStrea
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t tiles = (p.n_loci + kTabThreads - 1) / kTabThreads;
-    int64_t grid = tiles < (int64_t)sm_count * 8 ? tiles : (int64_t)sm_count * 8;
+    int64_t grid = tiles < (int64_t)sm_count * 24 ? tiles : (int64_t)sm_count * 24;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, kTabThreads, smem, s>>>(p);
     return cudaGetLastError();
