@@ -462,3 +462,20 @@ def test_tables_narrow_counts(ctx, kind):
         parts.append(scan.collect(t))
     scan.close()
     assert np.array_equal(np.concatenate([p.stats for p in parts]), ref.stats, equal_nan=True)
+
+
+def test_fixup_path_without_ingest_hints():
+    """PG_NOHINT=1 (read once per process by the library) sends every locus whose removed alleles carry reads through
+    the fix-up kernel's renormalising path again: the same parity cases must hold there"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("PG_NOHINT"):
+        pytest.skip("already inside the no-hint run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PG_NOHINT="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_scan_gpu.py"), "-m", "gpu", "-q",
+                          "-x", "-k", "error_reads or hinted_renormalisation or c1_regression"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=root, env=env, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert " passed" in out.stdout
