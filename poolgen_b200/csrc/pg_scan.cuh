@@ -200,10 +200,22 @@ __device__ __forceinline__ void renorm_row_fast(const double (&f)[A], uint32_t d
 }
 
 // the streaming form for loci whose ingest hint names the kept alleles: two rows (row, row + 1) of first-stage
-// frequencies f_ij = c_ij / depth_i become f_ij / sum_kept f_i. -- the depth cancels, so no depth load; within 3 ulp of
+// frequencies f_ij = c_ij / depth_i become f_ij / sum_kept f_i. -- the depth cancels, so no depth load; within 4 ulp of
 // the reference's c_ij / sum_kept c_i. (only the regression sums are formed from it; a tie of column sums or a lost
 // digit still goes to the fix-up kernel).  A pool whose reads all sit on removed alleles gives NaN like the reference
 // (0 / 0), padding rows stay 0.
+// 1 / x for a sum of frequencies (0 < x <= 1 + a few ulp, or exactly 0): hardware seed + two Newton steps, within
+// 1 ulp of the quotient -- a fifth of the instructions of the IEEE division; x = 0 gives NaN (inf seed), which is what
+// the caller wants for 0 / 0
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 template <int A>
 __device__ __forceinline__ void renorm_pair(double2 (&f2)[A], unsigned kept, int row, int n) {
     double sx = 0.0, sy = 0.0;
@@ -213,7 +225,7 @@ __device__ __forceinline__ void renorm_pair(double2 (&f2)[A], unsigned kept, int
             sx += f2[j].x;
             sy += f2[j].y;
         }
-    const double ix = (row < n) ? 1.0 / sx : 0.0, iy = (row + 1 < n) ? 1.0 / sy : 0.0;
+    const double ix = (row < n) ? rcp_fast(sx) : 0.0, iy = (row + 1 < n) ? rcp_fast(sy) : 0.0;
 #pragma unroll
     for (int j = 0; j < A; j++)
         f2[j] = ((kept >> j) & 1u) ? make_double2(f2[j].x * ix, f2[j].y * iy) : make_double2(0.0, 0.0);
@@ -1421,12 +1433,16 @@ cudaError_t launch_scan_p(ScanParams p, int sm_count, cudaStream_t s) {
     }
     if (p.warps_override >= 1 && p.warps_override < nwarps) nwarps = p.warps_override;
     if (nwarps < 1) return cudaErrorInvalidConfiguration;
-    // small slabs (the streaming submit path): shrink the block so that every warp of the grid gets loci -- phase 2
-    // then runs with few lanes, but on all warps at once instead of on a handful of them
-    if (p.g_override < 1) {
-        const int64_t per_warp = p.n_loci / ((int64_t)sm_count * nwarps * 2);
-        const int step = (P == 32) ? 1 : 32 / P;  // whole stages
-        int64_t g = per_warp / step * step;
+    // block size: every warp of the grid should get the same number of blocks.  With r = ceil(L / (warps * 32)) rounds
+    // the block shrinks from 32 loci to ceil(L / (warps * r)) -- a few idle lanes in phase 2 instead of a last round in
+    // which most warps idle (L = 120,000: 2.1 blocks of 32 per warp -> 3 rounds at 70 %; 3 blocks of 23 -> 98 %).  Small
+    // slabs of the streaming submit path fall out of the same rule (one short block per warp).
+    if (p.g_override < 1 && p.n_loci > 0) {
+        const int64_t gw = (int64_t)sm_count * nwarps;  // warps of the grid
+        const int step = (P == 32) ? 1 : 32 / P;        // whole stages
+        const int64_t r = (p.n_loci + gw * G - 1) / (gw * G);
+        int64_t g = (p.n_loci + gw * r - 1) / (gw * r);
+        g = (g + step - 1) / step * step;
         if (g < step) g = step;
         if (g < G) G = (int)g;
     }
