@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Small invocations of every kernel family for `compute-sanitizer --tool memcheck` (run through gpurun)."""
+"""Small invocations of every kernel family in one process (for a debugger or a sanitizer where one is available;
+compute-sanitizer is closed on this pool)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
