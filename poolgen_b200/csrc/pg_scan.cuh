@@ -13,9 +13,11 @@
 //   phase 2  lane = locus, once per block: keep-mask (LocusCounts::filter, src/base/sync.rs:195-303) and allele
 //            order (src/base/sync.rs:478-505) from the totals, centred normal equations, Cholesky, beta, residual
 //            variance, t and the Student-t two-sided p-value, records written straight to global memory.
-// Decisions that land within a rounding bound of a threshold are re-evaluated in the reference's exact sequential
-// order (bit-exact mask); loci that need the renormalised frequencies (a removed allele carries reads, a pool has no
-// coverage) are re-accumulated by the whole warp from global memory.
+// Loci whose MAF-removed alleles carry reads need the frequencies renormalised over the kept alleles: when the ingest
+// hint (pg_ingest.cu) vouches for the keep-mask they are rescaled in registers while they stream; decisions that land
+// within a rounding bound of a threshold are re-evaluated in the reference's exact sequential order (bit-exact mask)
+// and, with the pools without coverage and the cancellation-prone fits, are left to fixup_kernel, where a whole warp
+// re-accumulates the locus from global memory.
 #pragma once
 #include "pg_device.cuh"
 #include "pg_internal.h"
