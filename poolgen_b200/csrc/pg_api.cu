@@ -640,6 +640,25 @@ int pg_batch_time_runs(pg_batch *b, int iters, float *ms_total, int *n_launches)
     PG_CUDA(ctx, cudaEventSynchronize(b->ev1));
     PG_CUDA(ctx, cudaEventElapsedTime(ms_total, b->ev0, b->ev1));
     if (n_launches) *n_launches = launches;
+    static const bool report = getenv("PG_REPORT_DEFER") != nullptr;  // diagnostic: why loci went to the fix-up kernel
+    if (report && b->d_defer && is_regression(b->scan)) {
+        uint32_t count = 0;
+        PG_CUDA(ctx, cudaMemcpy(&count, b->d_defer + b->cap, 4, cudaMemcpyDeviceToHost));
+        std::vector<uint64_t> list(count);
+        if (count) PG_CUDA(ctx, cudaMemcpy(list.data(), b->d_defer, (size_t)count * 8, cudaMemcpyDeviceToHost));
+        uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint64_t e : list) {
+            const unsigned why = (unsigned)(e >> 56);
+            if (why & 1u) h[0]++;
+            if (why & 2u) h[1]++;
+            if (why & 4u) h[2]++;
+            if (why & 8u) h[3]++;
+            if ((why >> 4) >= 1 && (why >> 4) <= 4) h[3 + (why >> 4)]++;
+        }
+        fprintf(stderr, "[pg] deferred %u of %lld loci (last phenotype pass): threshold %u, removed-with-reads %u, no coverage %u, "
+                        "NaN under hint %u, redo ols %u, redo corr %u, corr NaN %u, tie %u\n",
+                count, (long long)b->n_loci, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+    }
     return PG_OK;
 }
 

@@ -1105,9 +1105,17 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool a
     if (act && status == PG_LOCUS_OK && !deferred)
         solve_locus<A, K, W, DEFER>(p, locus, tg, status, kept, m, cb, redo_mode);
     if (DEFER) {
-        if (redo_mode != REDO_NONE) deferred = true;
+        // why (bits 56.., read only by the PG_REPORT_DEFER diagnostic): 1 threshold within rounding, 2 removed allele
+        // with reads and no hint, 4 pool without coverage, 8 NaN under a hint, 16.. the redo mode
+        uint64_t why = (exact_bits != 0u ? 1u : 0u) | ((slow && !slow_decide) ? 2u : 0u) | (slow_decide ? 4u : 0u) |
+                       ((deferred && pre_kept) ? 8u : 0u);
+        if (redo_mode != REDO_NONE) {
+            deferred = true;
+            why |= (uint64_t)redo_mode << 4;
+        }
         if (deferred)
-            p.defer_list[atomicAdd(p.defer_count, 1u)] = (uint64_t)locus | (kept_known ? ((uint64_t)kept << 40) : 0ull);
+            p.defer_list[atomicAdd(p.defer_count, 1u)] =
+                (uint64_t)locus | (kept_known ? ((uint64_t)kept << 40) : 0ull) | (why << 56);
     } else {
         // loci whose single-pass form is not trustworthy: explicit two-pass evaluation by the whole warp
         unsigned need = __ballot_sync(PG_FULL_MASK, redo_mode != REDO_NONE);
@@ -1150,12 +1158,16 @@ __global__ void __launch_bounds__(kFixWarps * 32) fixup_kernel(const __grid_cons
     const int n_pad = p.lay.n_pad;
     const double *ys = p.yc;  // the slow paths index [k * n_pad + pool]: global memory serves as well as shared
     const double *ws = W ? p.w : nullptr;
-    const uint32_t n_blocks = (count + 31) / 32;
+    // loci per block: 32 when the list is long; when it is short the loci are spread over the CTAs of the grid, because
+    // the warp-cooperative exact paths of phase 2 handle the loci of a block one after the other (a handful of loci in
+    // one block would cost their summed latency at the end of every step, with the rest of the GPU idle)
+    const uint32_t per_blk = min(32u, max(1u, (count + gridDim.x - 1) / gridDim.x));
+    const uint32_t n_blocks = (count + per_blk - 1) / per_blk;
     int it = 0;
     for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, it++) {
         double *tot = reinterpret_cast<double *>(fsm) + (size_t)(it & 1) * 32 * AC::NP;
-        const uint32_t e0 = blk * 32;
-        const int cnt = (int)min(32u, count - e0);
+        const uint32_t e0 = blk * per_blk;
+        const int cnt = (int)min(per_blk, count - e0);
         for (int g = warp; g < cnt; g += kFixWarps) {  // the loci of the block are dealt over the warps
             const uint64_t e = p.defer_list[e0 + g];
             const int64_t locus = (int64_t)(e & 0xFFFFFFFFFFull);
