@@ -143,8 +143,10 @@ __device__ __forceinline__ void reduce_to_tot(const double (&acc)[N], double *re
 }
 
 // q_j = sum_i f_ij * (s_i / S), accumulated in pool order with separately rounded multiply and add,
-// NaN frequencies contribute 0 -- the exact arithmetic of src/base/sync.rs:258-271.
-static __device__ __noinline__ double exact_q(const ScanParams &p, int64_t locus, int j, const double *ws) {
+// NaN frequencies contribute 0 -- the exact arithmetic of src/base/sync.rs:258-271.  Called by the whole warp: 32 pools
+// are loaded at once (one coalesced request instead of 32 dependent ones), every lane forms its own product, and the
+// sum runs over the lanes in pool order through shuffles; every lane returns the same q.
+static __device__ __noinline__ double exact_q(const ScanParams &p, int64_t locus, int j, const double *ws, int lane) {
     const Layout &lay = p.lay;
     const double *fl = p.freq + (size_t)locus * lay.freq_stride();
     double q = 0.0;
@@ -153,11 +155,16 @@ static __device__ __noinline__ double exact_q(const ScanParams &p, int64_t locus
         const int rcc = (c == lay.n_chunks - 1) ? lay.rc_last : lay.rc;
         const double *col = fl + (size_t)c * lay.A * lay.rc + (size_t)j * rcc;
         const int rows = min(rcc, lay.n - i0);
-        for (int r = 0; r < rows; r++) {
-            const double f = col[r];
-            const double w = ws ? ws[i0 + r] : p.w_uniform;
-            const double term = (f != f) ? 0.0 : __dmul_rn(f, w);
-            q = __dadd_rn(q, term);
+        for (int r0 = 0; r0 < rows; r0 += 32) {
+            const int r = r0 + lane;
+            double term = 0.0;
+            if (r < rows) {
+                const double f = col[r];
+                const double w = ws ? ws[i0 + r] : p.w_uniform;
+                term = (f != f) ? 0.0 : __dmul_rn(f, w);
+            }
+            const int m = min(32, rows - r0);
+            for (int t = 0; t < m; t++) q = __dadd_rn(q, __shfl_sync(PG_FULL_MASK, term, t));
         }
         i0 += rcc;
     }
@@ -305,12 +312,11 @@ __device__ __noinline__ int slow_locus(const ScanParams &p, int64_t locus, const
     const uint32_t *dl = p.depth + (size_t)locus * lay.depth_stride();
     unsigned kept = kept_out;
     if (decide) {  // a pool without coverage poisoned the fast sums: redo the MAF decision exactly (lane j = column j)
-        bool keep_j = false;
-        if (lane < A) {
-            const double q = exact_q(p, locus, lane, ws);
-            keep_j = !((q < p.maf) | (q > p.one_minus_maf));
+        kept = 0;
+        for (int j = 0; j < A; j++) {
+            const double q = exact_q(p, locus, j, ws, lane);
+            if (!((q < p.maf) | (q > p.one_minus_maf))) kept |= 1u << j;
         }
-        kept = __ballot_sync(PG_FULL_MASK, keep_j) & ((1u << A) - 1u);
         kept_out = kept;
         if (__popc(kept) < 2) return PG_LOCUS_FILTERED;
         // missingness on the first kept column: NaN <=> the pool has no coverage (sync.rs:287-299)
@@ -1058,12 +1064,11 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool a
             need &= need - 1;
             const unsigned bits = __shfl_sync(PG_FULL_MASK, exact_bits, src);
             const int64_t lsrc = __shfl_sync(PG_FULL_MASK, locus, src);
-            double qe = 0.0;
-            if (lane < A && ((bits >> lane) & 1u)) qe = exact_q(p, lsrc, lane, ws);
 #pragma unroll
             for (int j = 0; j < A; j++) {
-                const double v = __shfl_sync(PG_FULL_MASK, qe, j);
-                if (lane == src && ((bits >> j) & 1u)) q[j] = v;
+                if (!((bits >> j) & 1u)) continue;  // warp-uniform: bits was broadcast
+                const double v = exact_q(p, lsrc, j, ws, lane);
+                if (lane == src) q[j] = v;
             }
         }
     }
