@@ -20,14 +20,27 @@ struct HintParams {
     double maf, one_minus_maf, min_depth_f;
     int enabled;
 };
-__device__ __forceinline__ uint8_t locus_hint(const double *q, int A, int n, uint32_t dm, const HintParams &hp) {
+// alleles whose pooled frequency sits within twice the rounding bound of any summation order of a MAF threshold
+__device__ __forceinline__ unsigned ambiguous_alleles(const double *q, int A, int n, const HintParams &hp) {
+    const double tol_rel = 4.0 * ((double)n + 8.0) * kEps;
+    unsigned amb = 0;
+    for (int j = 0; j < A; j++) {
+        const double tl = tol_rel * fmax(fabs(q[j]), 1.0);
+        if (fabs(q[j] - hp.maf) <= tl || fabs(q[j] - hp.one_minus_maf) <= tl) amb |= 1u << j;
+    }
+    return amb;
+}
+
+// `exact` = alleles whose q was re-evaluated in the reference's own order (any distance from a threshold is decisive)
+__device__ __forceinline__ uint8_t locus_hint(const double *q, int A, int n, uint32_t dm, const HintParams &hp,
+                                              unsigned exact) {
     if (!hp.enabled) return 0;
     const double tol_rel = 4.0 * ((double)n + 8.0) * kEps;
     unsigned kept = 0;
     bool removed_with_reads = false, safe = true;
     for (int j = 0; j < A; j++) {
         const double tl = tol_rel * fmax(fabs(q[j]), 1.0);
-        if (fabs(q[j] - hp.maf) <= tl || fabs(q[j] - hp.one_minus_maf) <= tl) safe = false;
+        if (!((exact >> j) & 1u) && (fabs(q[j] - hp.maf) <= tl || fabs(q[j] - hp.one_minus_maf) <= tl)) safe = false;
         if (!((q[j] < hp.maf) | (q[j] > hp.one_minus_maf)))
             kept |= 1u << j;
         else if (q[j] > 0.0)
@@ -42,7 +55,8 @@ __device__ __forceinline__ uint8_t locus_hint(const double *q, int A, int n, uin
 // depth of its pools; a butterfly over the group completes them, its first lane stores dmin and the hint.  No
 // atomics, no scratch, and a locus gets the same bits wherever it lands.
 template <typename RowFn>
-__device__ __forceinline__ void ingest_loci(int64_t n_loci, const Layout &lay, int P, uint32_t *__restrict__ dmin,
+__device__ __forceinline__ void ingest_loci(int64_t n_loci, const Layout &lay, int P, const double *freq,
+                                            const double *__restrict__ w, uint32_t *__restrict__ dmin,
                                             uint8_t *__restrict__ hint, const HintParams &hp, RowFn &&row) {
     const int lane = threadIdx.x & 31, sub = lane / P, q0 = lane % P, lpw = 32 / P;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -57,9 +71,33 @@ __device__ __forceinline__ void ingest_loci(int64_t n_loci, const Layout &lay, i
             for (int j = 0; j < lay.A; j++) q[j] += __shfl_xor_sync(0xFFFFFFFFu, q[j], off);
             dm = min(dm, __shfl_xor_sync(0xFFFFFFFFu, dm, off));
         }
+        // a pooled frequency within rounding of a threshold (one read in one pool of depth 10 among 100 pools IS
+        // 0.001): the group re-evaluates it in the reference's order -- pool by pool, separately rounded multiply and
+        // add, src/base/sync.rs:258-271 -- from the frequencies it has just written, so the hint can still vouch for
+        // the keep-mask and the locus stays out of the fix-up kernel
+        unsigned amb = (hp.enabled && locus < n_loci && dm != 0u) ? ambiguous_alleles(q, lay.A, lay.n, hp) : 0u;
+        if (__any_sync(0xFFFFFFFFu, amb != 0u)) {
+            __syncwarp();  // the group's stores to freq are visible to its lanes
+            const double *fl = freq + (size_t)(locus < n_loci ? locus : 0) * lay.freq_stride();
+            for (int j = 0; j < lay.A; j++) {
+                if (!__any_sync(0xFFFFFFFFu, (amb >> j) & 1u)) continue;
+                double e = 0.0;
+                for (int r0 = 0; r0 < lay.n; r0 += P) {
+                    const int i = r0 + q0;
+                    double term = 0.0;
+                    if (i < lay.n && locus < n_loci) {
+                        const double f = __ldcg(fl + lay.freq_off(i, j));  // written by another lane of this warp
+                        term = (f != f) ? 0.0 : __dmul_rn(f, w[i]);
+                    }
+                    const int m = min(P, lay.n - r0);
+                    for (int t = 0; t < m; t++) e = __dadd_rn(e, __shfl_sync(0xFFFFFFFFu, term, t, P));
+                }
+                if ((amb >> j) & 1u) q[j] = e;
+            }
+        }
         if (locus < n_loci && q0 == 0) {
             dmin[locus] = dm;
-            hint[locus] = locus_hint(q, lay.A, lay.n, dm, hp);
+            hint[locus] = locus_hint(q, lay.A, lay.n, dm, hp, amb);
         }
     }
 }
@@ -70,7 +108,7 @@ __global__ void __launch_bounds__(256) ingest_counts_kernel(const CT *__restrict
                                                             double *__restrict__ freq, uint32_t *__restrict__ depth,
                                                             uint32_t *__restrict__ dmin, uint8_t *__restrict__ hint,
                                                             const double *__restrict__ w, HintParams hp) {
-    ingest_loci(n_loci, lay, P, dmin, hint, hp, [&](int64_t locus, int i, double *q, uint32_t &dm) {
+    ingest_loci(n_loci, lay, P, freq, w, dmin, hint, hp, [&](int64_t locus, int i, double *q, uint32_t &dm) {
         double *fl = freq + (size_t)locus * lay.freq_stride();
         if (i >= n) {  // padding row
             for (int j = 0; j < lay.A; j++) fl[lay.freq_off(i, j)] = 0.0;
@@ -104,7 +142,7 @@ __global__ void __launch_bounds__(256) ingest_freq_kernel(const double *__restri
                                                           double *__restrict__ freq, uint32_t *__restrict__ depth,
                                                           uint32_t *__restrict__ dmin, uint8_t *__restrict__ hint,
                                                           const double *__restrict__ w, HintParams hp) {
-    ingest_loci(n_loci, lay, P, dmin, hint, hp, [&](int64_t locus, int i, double *q, uint32_t &dm) {
+    ingest_loci(n_loci, lay, P, freq, w, dmin, hint, hp, [&](int64_t locus, int i, double *q, uint32_t &dm) {
         double *fl = freq + (size_t)locus * lay.freq_stride();
         const bool pad = i >= n;
         for (int j = 0; j < lay.A; j++) {
