@@ -870,7 +870,7 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
                 const double sxa = tg[AC::S0 + c];
                 const double raw = tg[AC::P0 + c * A - c * (c - 1) / 2];
                 const double sxx = raw - sxa * sxa / nn;
-                if (!(raw <= 1e4 * sxx)) redo = true;
+                if (!(raw <= 1e6 * sxx)) redo = true;  // up to 6 of 16 digits lost by the single-pass form: r keeps 1e-10
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     const double sxy = tg[AC::C0 + c * K + k] - sxa * p.ysum[k] / nn;
