@@ -404,6 +404,15 @@ __device__ __forceinline__ int slot_col(unsigned cb, int s) { return (int)((cb >
 
 enum { REDO_NONE = 0, REDO_OLS = 1, REDO_CORR = 2, REDO_CORR_NAN = 3, REDO_DEFER = 4 };
 
+// the analysis as a compile-time constant in the streaming kernel (KIND = PG_KIND_OLS / PG_KIND_CORR: the other
+// analysis' phase-2 code is not even linked -- the small-locus kernels are sensitive to their instruction footprint),
+// a run-time value in the fix-up kernel (KIND = -1)
+template <int KIND>
+__device__ __forceinline__ bool kind_is_ols(const ScanParams &p) {
+    if constexpr (KIND >= 0) return KIND == PG_KIND_OLS;
+    else return p.kind == PG_KIND_OLS;
+}
+
 // Reference-style two-pass evaluation of one locus straight from global memory by the whole warp (lane = pool):
 // explicit centred moments and explicit residuals e = y - Xb as src/gwas/ols.rs:98-104.  Used when the single-pass
 // Gram form would lose digits to cancellation (near-perfect fits, nearly constant or nearly collinear allele
@@ -766,7 +775,7 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsi
 // ---- phase 2b (one lane per locus): allele order and the single-pass solve, everything in registers ------------
 // in: the totals row tg of the locus.  out: m (rows), cb (allele column of each row, 4 bits per slot), redo (REDO_*)
 // and, in place of the totals, tg[(s*K+k)*2 + {0,1}] = (beta | r, var) and tg[2(A-1)K + s] = mean frequency.
-template <int A, int K, bool W, bool DEFER>
+template <int A, int K, bool W, bool DEFER, int KIND>
 __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, double *tg, int &status, unsigned kept,
                                          int &m, unsigned &cb, int &redo_mode) {
     using AC = Acc<A, K, W>;
@@ -780,7 +789,7 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
     const double tol_rel = 2.0 * (nn + 8.0) * kEps;
     m = __popc(kept) - 1;
     cb = 0;
-    if (p.kind == PG_KIND_OLS) {
+    if (kind_is_ols<KIND>(p)) {
         // stable sort by decreasing column sum, drop the first (major) allele (sync.rs:478-505, ols.rs:227-230)
         double cs[A];
         bool tie = false;
@@ -834,7 +843,7 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
             fmean[a] = (pjj != pjj) ? nan("") : tg[AC::S0 + c] / nn;
         }
     }
-    if (p.kind == PG_KIND_OLS) {
+    if (kind_is_ols<KIND>(p)) {
         if (lay.n < m + 1) {
             status = PG_LOCUS_UNSUPPORTED;
         } else if (!has_nan) {
@@ -930,7 +939,7 @@ __device__ __forceinline__ void student_batch(const ScanParams &p, const PTableD
 }
 
 // ---- phase 2c (one lane per locus): t, p and the records ----------------------------------------------------------
-template <int A, int K>
+template <int A, int K, int KIND>
 __device__ __noinline__ void write_records(const ScanParams &p, const PTableDev &tab, int64_t locus, int status,
                                            int m, unsigned cb, const double *tb) {
     constexpr int T2 = 2 * (A - 1) * K;
@@ -960,7 +969,7 @@ __device__ __noinline__ void write_records(const ScanParams &p, const PTableDev 
             need[k] = false;
             ta[k] = 0.0;
             if (valid) {
-                if (p.kind == PG_KIND_OLS) {
+                if (kind_is_ols<KIND>(p)) {
                     // estimate_significance, src/gwas/ols.rs:139-154
                     const double se = sqrt(v1);
                     const double tt = (fabs(v0) <= kEps) ? 0.0 : v0 / se;
@@ -1013,7 +1022,7 @@ __device__ __noinline__ void write_records(const ScanParams &p, const PTableDev 
 // DEFER = false (the fix-up kernel): the whole warp works on those paths.
 // locus / act / dm are per lane; pre_kept != 0 (fix-up kernel only) says that the row already holds the totals of the
 // renormalised frequencies over that kept set.
-template <int A, int K, bool W, bool DEFER>
+template <int A, int K, bool W, bool DEFER, int KIND>
 __device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool act, double *tot, const double *ys,
                                       const double *ws, int lane, unsigned dm, unsigned pre_kept) {
     using AC = Acc<A, K, W>;
@@ -1108,7 +1117,7 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool a
     int m = 0, redo_mode = REDO_NONE;
     unsigned cb = 0;
     if (act && status == PG_LOCUS_OK && !deferred)
-        solve_locus<A, K, W, DEFER>(p, locus, tg, status, kept, m, cb, redo_mode);
+        solve_locus<A, K, W, DEFER, KIND>(p, locus, tg, status, kept, m, cb, redo_mode);
     if (DEFER) {
         // why (bits 56.., read only by the PG_REPORT_DEFER diagnostic): 1 threshold within rounding, 2 removed allele
         // with reads and no hint, 4 pool without coverage, 8 NaN under a hint, 16.. the redo mode
@@ -1140,7 +1149,7 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool a
         }
         __syncwarp();
     }
-    if (act && !deferred) write_records<A, K>(p, ptab, locus, status, m, cb, tg);
+    if (act && !deferred) write_records<A, K, KIND>(p, ptab, locus, status, m, cb, tg);
     __syncwarp();
 }
 
@@ -1207,13 +1216,13 @@ __global__ void __launch_bounds__(kFixWarps * 32) fixup_kernel(const __grid_cons
             const uint64_t mine = (lane < cnt) ? p.defer_list[e0 + lane] : 0ull;
             const int64_t locus = (int64_t)(mine & 0xFFFFFFFFFFull);
             const unsigned dm = (lane < cnt) ? __ldg(p.dmin + locus) : 0xFFFFFFFFu;
-            epilogue<A, K, W, false>(sp, locus, lane < cnt, tot, ys, ws, lane, dm, (unsigned)(mine >> 40) & 0x3fu);
+            epilogue<A, K, W, false, -1>(sp, locus, lane < cnt, tot, ys, ws, lane, dm, (unsigned)(mine >> 40) & 0x3fu);
         }
     }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
-template <int A, int K, bool W, int P>
+template <int A, int K, bool W, int P, int KIND>
 __global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const __grid_constant__ ScanParams p) {
     using AC = Acc<A, K, W>;
     constexpr int LPS = 32 / P;  // loci per stage
@@ -1411,7 +1420,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const __grid_c
                 }
             }
         }
-        epilogue<A, K, W, true>(sp, l0 + lane, lane < cnt, tot, ys, ws, lane, dm, (hl & 0x80u) ? (hl & 0x3fu) : 0u);
+        epilogue<A, K, W, true, KIND>(sp, l0 + lane, lane < cnt, tot, ys, ws, lane, dm, (hl & 0x80u) ? (hl & 0x3fu) : 0u);
     }
 }
 
@@ -1471,7 +1480,7 @@ cudaError_t launch_scan_p(ScanParams p, int sm_count, cudaStream_t s) {
     p.nbuf = nbuf;
     p.block_loci = G;
     const size_t smem = common + (size_t)nwarps * wbytes;
-    auto kern = scan_kernel<A, K, W, P>;
+    auto kern = (p.kind == PG_KIND_OLS) ? scan_kernel<A, K, W, P, PG_KIND_OLS> : scan_kernel<A, K, W, P, PG_KIND_CORR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t NB = (p.n_loci + G - 1) / G;
