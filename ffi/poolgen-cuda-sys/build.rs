@@ -53,7 +53,7 @@ fn main() {
         ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o"].iter().map(|s| s.to_string()).collect();
     link.push(lib);
     link.extend(objs);
-    link.extend(["-cudart", "static", "-lcusolver", "-lcublas"].iter().map(|s| s.to_string()));
+    link.extend(["-cudart", "static", "-ldl"].iter().map(|s| s.to_string()));
     nvcc(&link);
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=poolgen_cuda");

@@ -13,6 +13,7 @@
 //                 the last coefficient of the reference's normal equations up to rounding
 #include <cub/device/device_scan.cuh>
 #include <cusolverDn.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -949,6 +950,42 @@ int pg_kin_partial_set(pg_kin *h, const double *in) {
 }
 
 // K = (sum of the partial Gram matrices) / P_total; eigen-decomposition; number of PCs by the reference's rule
+// cuSOLVER is loaded on first use: linking it would make every process that opens this library map cuSOLVER, cuSPARSE,
+// cuBLAS, cuBLASLt and nvJitLink (1.5 GB of shared objects, minutes on a cold file system) although only the eigen
+// step of ols_iter_with_kinship calls into it
+namespace {
+struct CusolverApi {
+    cusolverStatus_t (*create)(cusolverDnHandle_t *) = nullptr;
+    cusolverStatus_t (*destroy)(cusolverDnHandle_t) = nullptr;
+    cusolverStatus_t (*set_stream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+    cusolverStatus_t (*syevd_buffer)(cusolverDnHandle_t, cusolverEigMode_t, cublasFillMode_t, int, const double *, int,
+                                     const double *, int *) = nullptr;
+    cusolverStatus_t (*syevd)(cusolverDnHandle_t, cusolverEigMode_t, cublasFillMode_t, int, double *, int, double *,
+                              double *, int, int *) = nullptr;
+    bool ok = false;
+};
+const CusolverApi &cusolver_api() {
+    static const CusolverApi api = [] {
+        CusolverApi a;
+        void *lib = nullptr;
+        for (const char *name : {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so",
+                                 "/usr/local/cuda/lib64/libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (lib) break;
+        }
+        if (!lib) return a;
+        a.create = reinterpret_cast<decltype(a.create)>(dlsym(lib, "cusolverDnCreate"));
+        a.destroy = reinterpret_cast<decltype(a.destroy)>(dlsym(lib, "cusolverDnDestroy"));
+        a.set_stream = reinterpret_cast<decltype(a.set_stream)>(dlsym(lib, "cusolverDnSetStream"));
+        a.syevd_buffer = reinterpret_cast<decltype(a.syevd_buffer)>(dlsym(lib, "cusolverDnDsyevd_bufferSize"));
+        a.syevd = reinterpret_cast<decltype(a.syevd)>(dlsym(lib, "cusolverDnDsyevd"));
+        a.ok = a.create && a.destroy && a.set_stream && a.syevd_buffer && a.syevd;
+        return a;
+    }();
+    return api;
+}
+}  // namespace
+
 int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) {
     if (!h || P_total < 1) return PG_ERR_ARG;
     pg_ctx *ctx = h->ctx;
@@ -960,18 +997,20 @@ int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) 
     cusolverDnHandle_t cs = nullptr;
     int rc = PG_OK;
     std::vector<double> A((size_t)n * n), W(n);
+    const CusolverApi &sol = cusolver_api();
+    if (!sol.ok) return kfail(ctx, PG_ERR_CUDA, "pg_kin_eig_select: libcusolver could not be loaded (%s)", dlerror() ? dlerror() : "missing symbols");
     do {
-        if (cusolverDnCreate(&cs) != CUSOLVER_STATUS_SUCCESS) { rc = kfail(ctx, PG_ERR_CUDA, "cusolverDnCreate failed"); break; }
-        cusolverDnSetStream(cs, h->stream);
+        if (sol.create(&cs) != CUSOLVER_STATUS_SUCCESS) { rc = kfail(ctx, PG_ERR_CUDA, "cusolverDnCreate failed"); break; }
+        sol.set_stream(cs, h->stream);
         if (cudaMalloc(&dA, (size_t)n * n * 8) != cudaSuccess || cudaMalloc(&dW, (size_t)n * 8) != cudaSuccess ||
             cudaMalloc(&dinfo, 4) != cudaSuccess) { rc = kfail(ctx, PG_ERR_CUDA, "pg_kin_eig_select: out of device memory"); break; }
         // scale on the host path is avoided: eigenvectors do not depend on the scale, eigenvalue SHARES neither
         cudaMemcpyAsync(dA, h->d_K, (size_t)n * n * 8, cudaMemcpyDeviceToDevice, h->stream);
         int lwork = 0;
-        if (cusolverDnDsyevd_bufferSize(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dA, n, dW, &lwork) !=
+        if (sol.syevd_buffer(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dA, n, dW, &lwork) !=
             CUSOLVER_STATUS_SUCCESS) { rc = kfail(ctx, PG_ERR_CUDA, "Dsyevd_bufferSize failed"); break; }
         if (cudaMalloc(&dwork, (size_t)lwork * 8) != cudaSuccess) { rc = kfail(ctx, PG_ERR_CUDA, "syevd workspace"); break; }
-        if (cusolverDnDsyevd(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dA, n, dW, dwork, lwork, dinfo) !=
+        if (sol.syevd(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dA, n, dW, dwork, lwork, dinfo) !=
             CUSOLVER_STATUS_SUCCESS) { rc = kfail(ctx, PG_ERR_CUDA, "Dsyevd failed"); break; }
         int info = 0;
         cudaMemcpyAsync(&info, dinfo, 4, cudaMemcpyDeviceToHost, h->stream);
@@ -983,7 +1022,7 @@ int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) 
     cudaFree(dW);
     cudaFree(dwork);
     cudaFree(dinfo);
-    if (cs) cusolverDnDestroy(cs);
+    if (cs) sol.destroy(cs);
     if (rc) return rc;
     // syevd returns ascending eigenvalues, column j of A (column-major) = eigenvector j; the reference walks them
     // "sorted from high to low" (ols.rs:296)
