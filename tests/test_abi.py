@@ -84,3 +84,12 @@ def test_rust_ffi_crate_declares_the_same_functions():
     rs_fns = {m.group(1): arity(m.group(2)) for m in re.finditer(r"pub fn (pg_[a-z0-9_]+)\(([^()]*)\)", ext)}
     assert sorted(c_fns) == _header_functions()
     assert rs_fns == c_fns
+
+
+def test_library_does_not_link_the_cuda_math_libraries():
+    """cuSOLVER is dlopen()ed by the eigen step only: a process that opens libpoolgen_cuda.so for the scans must not
+    map cuSOLVER / cuSPARSE / cuBLAS (1.5 GB, minutes on a cold file system)"""
+    import subprocess
+    out = subprocess.run(["ldd", LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    for name in ("cusolver", "cublas", "cusparse", "nvJitLink"):
+        assert name not in out, out
