@@ -379,7 +379,10 @@ struct CovarParams {
     double *beta, *var, *pval;  // [k][P]
 };
 
-template <int NV>
+// NV = (1 + m) + k vectors in shared memory; a warp streams C allele columns at once so that every shared-memory load
+// of a Q / y~ element feeds C pairs of FMAs (with m = 10 covariates the one-column form spends its time on 12 LDS per
+// element of g: 0.30 of the HBM roofline; C = 4 columns share them)
+template <int NV, int C>
 __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
     extern __shared__ __align__(16) double vs[];  // [NV][ldg]
     const int ldg = p.ldg;
@@ -390,81 +393,102 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
     const int nq = p.nq, k = p.k;
-    for (int64_t c = warp; c < p.P; c += nwarps) {
-        const double *g = p.G + (size_t)c * ldg;
-        double acc[NV], gg = 0.0;
+    for (int64_t c0 = warp * C; c0 < p.P; c0 += nwarps * C) {
+        double accs[C][NV], ggs[C];
 #pragma unroll
-        for (int v = 0; v < NV; v++) acc[v] = 0.0;
-#pragma unroll 4
+        for (int cc = 0; cc < C; cc++) {
+            ggs[cc] = 0.0;
+#pragma unroll
+            for (int v = 0; v < NV; v++) accs[cc][v] = 0.0;
+        }
+        const double *g0 = p.G + (size_t)c0 * ldg;
+#pragma unroll(C == 1 ? 4 : 2)
         for (int r = 2 * lane; r < ldg; r += 64) {
-            const double2 g2 = __ldcs(reinterpret_cast<const double2 *>(g + r));
-            gg = fma(g2.x, g2.x, gg);
-            gg = fma(g2.y, g2.y, gg);
+            double2 g2[C];
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+                g2[cc] = (c0 + cc < p.P) ? __ldcs(reinterpret_cast<const double2 *>(g0 + (size_t)cc * ldg + r))
+                                         : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int cc = 0; cc < C; cc++) {
+                ggs[cc] = fma(g2[cc].x, g2[cc].x, ggs[cc]);
+                ggs[cc] = fma(g2[cc].y, g2[cc].y, ggs[cc]);
+            }
 #pragma unroll
             for (int v = 0; v < NV; v++) {
                 const double2 q2 = *reinterpret_cast<const double2 *>(vs + (size_t)v * ldg + r);
-                acc[v] = fma(g2.x, q2.x, acc[v]);
-                acc[v] = fma(g2.y, q2.y, acc[v]);
+#pragma unroll
+                for (int cc = 0; cc < C; cc++) {
+                    accs[cc][v] = fma(g2[cc].x, q2.x, accs[cc][v]);
+                    accs[cc][v] = fma(g2[cc].y, q2.y, accs[cc][v]);
+                }
             }
         }
-        gg = warp_sum_fixed(gg);
 #pragma unroll
-        for (int v = 0; v < NV; v++) acc[v] = warp_sum_fixed(acc[v]);
-        double uu = 0.0;
+        for (int cc = 0; cc < C; cc++) {
+            const int64_t c = c0 + cc;
+            if (c >= p.P) continue;  // warp-uniform (no break: the loop must unroll so that accs stays in registers)
+            const double *g = g0 + (size_t)cc * ldg;
+            double acc[NV];
+            double gg = warp_sum_fixed(ggs[cc]);
 #pragma unroll
-        for (int v = 0; v < NV; v++)
-            if (v < nq) uu = fma(acc[v], acc[v], uu);
-        double ggc = gg - uu;
-        double gy[NV];
-#pragma unroll
-        for (int v = 0; v < NV; v++) gy[v] = acc[v];
-        if (!(gg <= 1e4 * ggc)) {
-            // cancellation: second pass with explicit residuals g - Q u (the column is still in L2)
-            double s2 = 0.0, sy[NV];
-#pragma unroll
-            for (int v = 0; v < NV; v++) sy[v] = 0.0;
-            for (int r = lane; r < p.n; r += 32) {
-                double e = g[r];
-#pragma unroll
-                for (int v = 0; v < NV; v++)
-                    if (v < nq) e = fma(-acc[v], vs[(size_t)v * ldg + r], e);
-                s2 = fma(e, e, s2);
-#pragma unroll
-                for (int v = 0; v < NV; v++)
-                    if (v >= nq) sy[v] = fma(e, vs[(size_t)v * ldg + r], sy[v]);
-            }
-            ggc = warp_sum_fixed(s2);
+            for (int v = 0; v < NV; v++) acc[v] = warp_sum_fixed(accs[cc][v]);
+            double uu = 0.0;
 #pragma unroll
             for (int v = 0; v < NV; v++)
-                if (v >= nq) gy[v] = warp_sum_fixed(sy[v]);
-        }
-        // lane j < k finishes phenotype j
-        double b = nan(""), vb = nan(""), pv = nan("");
-        double gyj = 0.0, yyj = 0.0;
+                if (v < nq) uu = fma(acc[v], acc[v], uu);
+            double ggc = gg - uu;
+            double gy[NV];
 #pragma unroll
-        for (int v = 0; v < NV; v++)
-            if (v - nq == lane) gyj = gy[v];
+            for (int v = 0; v < NV; v++) gy[v] = acc[v];
+            if (!(gg <= 1e4 * ggc)) {
+                // cancellation: second pass with explicit residuals g - Q u (the column is still in L2)
+                double s2 = 0.0, sy[NV];
 #pragma unroll
-        for (int j = 0; j < kMaxPhenPerPass * 4; j++)
-            if (j == lane) yyj = p.yy[j];
-        if (lane < k) {
-            if (ggc > 0.0 && p.dfe > 0.0) {
-                b = gyj / ggc;
-                double rss = yyj - b * gyj;
-                if (rss < 0.0) rss = 0.0;
-                vb = rss / p.dfe / ggc;
-                // estimate_significance, src/gwas/ols.rs:139-154
-                const double tt = (fabs(b) <= kEps) ? 0.0 : b / sqrt(vb);
-                if (fabs(tt) <= kEps || tt != tt)
-                    pv = 1.0;
-                else
-                    pv = p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab) : student_two_sided(fabs(tt), p.df, p.ln_beta);
-            } else if (gg != gg) {
-                pv = 1.0;  // NaN frequencies: the reference's t is NaN and its p is forced to 1 (ols.rs:150-151)
+                for (int v = 0; v < NV; v++) sy[v] = 0.0;
+                for (int r = lane; r < p.n; r += 32) {
+                    double e = g[r];
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+                        if (v < nq) e = fma(-acc[v], vs[(size_t)v * ldg + r], e);
+                    s2 = fma(e, e, s2);
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+                        if (v >= nq) sy[v] = fma(e, vs[(size_t)v * ldg + r], sy[v]);
+                }
+                ggc = warp_sum_fixed(s2);
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+                    if (v >= nq) gy[v] = warp_sum_fixed(sy[v]);
             }
-            p.beta[(size_t)lane * p.P + c] = b;
-            p.var[(size_t)lane * p.P + c] = vb;
-            p.pval[(size_t)lane * p.P + c] = pv;
+            // lane j < k finishes phenotype j
+            double b = nan(""), vb = nan(""), pv = nan("");
+            double gyj = 0.0, yyj = 0.0;
+#pragma unroll
+            for (int v = 0; v < NV; v++)
+                if (v - nq == lane) gyj = gy[v];
+#pragma unroll
+            for (int j = 0; j < kMaxPhenPerPass * 4; j++)
+                if (j == lane) yyj = p.yy[j];
+            if (lane < k) {
+                if (ggc > 0.0 && p.dfe > 0.0) {
+                    b = gyj / ggc;
+                    double rss = yyj - b * gyj;
+                    if (rss < 0.0) rss = 0.0;
+                    vb = rss / p.dfe / ggc;
+                    // estimate_significance, src/gwas/ols.rs:139-154
+                    const double tt = (fabs(b) <= kEps) ? 0.0 : b / sqrt(vb);
+                    if (fabs(tt) <= kEps || tt != tt)
+                        pv = 1.0;
+                    else
+                        pv = p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab) : student_two_sided(fabs(tt), p.df, p.ln_beta);
+                } else if (gg != gg) {
+                    pv = 1.0;  // NaN frequencies: the reference's t is NaN and its p is forced to 1 (ols.rs:150-151)
+                }
+                p.beta[(size_t)lane * p.P + c] = b;
+                p.var[(size_t)lane * p.P + c] = vb;
+                p.pval[(size_t)lane * p.P + c] = pv;
+            }
         }
     }
 }
@@ -1104,7 +1128,7 @@ int pg_kin_set_covariates(pg_kin *h, const double *cov, int m) {
 template <int NV>
 static cudaError_t covar_launch_nv(const pg::CovarParams &cp, int sm_count, cudaStream_t s) {
     const size_t smem = (size_t)NV * cp.ldg * 8;
-    auto kern = pg::covar_kernel<NV>;
+    auto kern = pg::covar_kernel<NV, (NV >= 9 ? 3 : (NV >= 5 ? 4 : (NV >= 3 ? 2 : 1)))>;  // C * NV accumulators fit the registers
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int ctas_per_sm = (int)std::min<size_t>(4, (227 * 1024) / std::max<size_t>(smem, 1));
