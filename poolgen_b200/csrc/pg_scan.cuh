@@ -676,8 +676,11 @@ __device__ __noinline__ int corr_pairwise_locus(const ScanParams &p, int64_t loc
 
 // Single-pass OLS from the reduced sums for M regressors, fully unrolled so that every matrix lives in registers.
 // Returns false when the centred X'X is not positive definite; sets redo when the single-pass form loses digits.
+// m <= M regressors are present; the slots m..M-1 are an identity block with zero right-hand sides.  They only append
+// exact zeros to the END of every sum, so the m present coefficients come out bit for bit as from the variant with
+// M = m -- a warp whose loci disagree on m runs this once with M = A - 1 instead of one specialised variant per value.
 template <int M, int A, int K, bool W>
-__device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsigned cb, double nn, bool &redo) {
+__device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsigned cb, double nn, bool &redo, int m) {
     using AC = Acc<A, K, W>;
     double tbg[2 * M * K];
     double sx[M], S[M][M], Lm[M][M], Li[M][M], dg[M], rinv[M];
@@ -685,7 +688,7 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsi
 #pragma unroll
     for (int a = 0; a < M; a++) {
         c[a] = slot_col(cb, a);
-        sx[a] = tg[AC::S0 + c[a]];
+        sx[a] = (a < m) ? tg[AC::S0 + c[a]] : 0.0;
     }
     const double inv_n = 1.0 / nn;
     double amp = 1.0;
@@ -695,8 +698,8 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsi
         for (int b = 0; b <= a; b++) {
             const int lo = c[a] < c[b] ? c[a] : c[b], hi = c[a] < c[b] ? c[b] : c[a];
             const double raw = tg[AC::P0 + lo * A - lo * (lo - 1) / 2 + (hi - lo)];
-            S[a][b] = raw - sx[a] * sx[b] * inv_n;
-            if (a == b) amp = fmax(amp, raw / S[a][a]);
+            S[a][b] = (a < m) ? raw - sx[a] * sx[b] * inv_n : (a == b ? 1.0 : 0.0);
+            if (a == b && a < m) amp = fmax(amp, raw / S[a][a]);
         }
     bool ok = true;
 #pragma unroll
@@ -739,8 +742,8 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsi
     }
     redo = !ok || !(amp > 0.0);
     if (!ok) return false;
-    const double inv_dfe = 1.0 / (nn - (double)(M + 1));
-    const bool saturated = !(nn - (double)(M + 1) > 0.0);
+    const double inv_dfe = 1.0 / (nn - (double)(m + 1));
+    const bool saturated = !(nn - (double)(m + 1) > 0.0);
 #pragma unroll
     for (int k = 0; k < K; k++) {
         double z[M], zz = 0.0;
@@ -749,7 +752,7 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsi
         for (int a = 0; a < M; a++) {
             double v = 0.0;
 #pragma unroll
-            for (int b = 0; b <= a; b++) v += Li[a][b] * (tg[AC::C0 + c[b] * K + k] - sx[b] * ys_n);
+            for (int b = 0; b <= a; b++) v += Li[a][b] * ((b < m) ? tg[AC::C0 + c[b] * K + k] - sx[b] * ys_n : 0.0);
             z[a] = v;
             zz += v * v;
         }
@@ -757,7 +760,7 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsi
         // digits lost by the single-pass form: centring (amp), collinearity (vif) and syy - zz
         if (!(64.0 * kEps * (amp * vif * zz + p.syy[k]) <= 1e-10 * rss)) redo = true;
         if (rss < 0.0) rss = 0.0;
-        const double ve = saturated ? rss / (nn - (double)(M + 1)) : rss * inv_dfe;
+        const double ve = saturated ? rss / (nn - (double)(m + 1)) : rss * inv_dfe;
 #pragma unroll
         for (int b = 0; b < M; b++) {
             double v = 0.0;
@@ -848,20 +851,27 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
             status = PG_LOCUS_UNSUPPORTED;
         } else if (!has_nan) {
             bool redo = false;
-            switch (m) {
-                case 1: ols_gram_m<1, A, K, W>(p, tg, cb, nn, redo); break;
-                case 2:
-                    if constexpr (A >= 3) ols_gram_m<2, A, K, W>(p, tg, cb, nn, redo);
-                    break;
-                case 3:
-                    if constexpr (A >= 4) ols_gram_m<3, A, K, W>(p, tg, cb, nn, redo);
-                    break;
-                case 4:
-                    if constexpr (A >= 5) ols_gram_m<4, A, K, W>(p, tg, cb, nn, redo);
-                    break;
-                default:
-                    if constexpr (A >= 6) ols_gram_m<5, A, K, W>(p, tg, cb, nn, redo);
-                    break;
+            // the lanes that got here agree on m (real data: nearly always biallelic) -> the variant of that size;
+            // otherwise ONE pass of the full-size variant with masked slots instead of a pass per distinct m
+            const unsigned here = __activemask();
+            const bool uniform = __match_any_sync(here, m) == here;
+            if (!uniform || m >= A - 1) {
+                ols_gram_m<A - 1, A, K, W>(p, tg, cb, nn, redo, m);
+            } else {
+                switch (m) {  // m < A - 1, every variant is instantiated once
+                    case 1:
+                        if constexpr (A >= 3) ols_gram_m<1, A, K, W>(p, tg, cb, nn, redo, 1);
+                        break;
+                    case 2:
+                        if constexpr (A >= 4) ols_gram_m<2, A, K, W>(p, tg, cb, nn, redo, 2);
+                        break;
+                    case 3:
+                        if constexpr (A >= 5) ols_gram_m<3, A, K, W>(p, tg, cb, nn, redo, 3);
+                        break;
+                    default:
+                        if constexpr (A >= 6) ols_gram_m<4, A, K, W>(p, tg, cb, nn, redo, 4);
+                        break;
+                }
             }
             if (redo) redo_mode = REDO_OLS;
         } else {
