@@ -567,6 +567,7 @@ static int run_once(pg_batch *b, int *launches) {
             p.min_depth_f = (double)s->min_depth;
             p.w_uniform = s->w_uniform;
             p.df = s->df;
+            p.inv_df = 1.0 / s->df;
             p.ln_beta = s->ln_beta;
             p.ptab = s->d_ptab;
             p.ptab_vmax = s->ptab_vmax;

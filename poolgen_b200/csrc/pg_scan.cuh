@@ -714,8 +714,7 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsi
                     ok = false;
                     v = 1.0;
                 }
-                Lm[a][a] = sqrt(v);
-                rinv[a] = 1.0 / Lm[a][a];
+                rinv[a] = rsqrt(v);  // 1 / L_aa in one step (1 ulp): the pivot's sqrt + division left the chain
             } else {
                 Lm[a][b] = v * rinv[b];
             }
@@ -925,7 +924,7 @@ __device__ __forceinline__ void student_batch(const ScanParams &p, const PTableD
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const double ta = need[k] ? t_abs[k] : 0.0;
-        const double v = sqrt(log1p(ta * ta / p.df));
+        const double v = sqrt(log1p(ta * ta * p.inv_df));
         in[k] = need[k] && (v < tab.v_max);
         const double pos = in[k] ? v * tab.inv_h : 0.0;
         int i = (int)pos;
@@ -982,7 +981,7 @@ __device__ __noinline__ void write_records(const ScanParams &p, const PTableDev 
                 if (kind_is_ols<KIND>(p)) {
                     // estimate_significance, src/gwas/ols.rs:139-154
                     const double se = sqrt(v1);
-                    const double tt = (fabs(v0) <= kEps) ? 0.0 : v0 / se;
+                    const double tt = (fabs(v0) <= kEps) ? 0.0 : v0 * rsqrt(v1);  // b / sqrt(var) off the sqrt's chain
                     o0[k] = v0;
                     o1[k] = se;
                     o2[k] = tt;
