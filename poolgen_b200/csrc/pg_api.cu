@@ -568,6 +568,8 @@ static int run_once(pg_batch *b, int *launches) {
             p.w_uniform = s->w_uniform;
             p.df = s->df;
             p.inv_df = 1.0 / s->df;
+            p.inv_n = 1.0 / (double)s->n;
+            p.inv_nm2 = 1.0 / ((double)s->n - 2.0);
             p.ln_beta = s->ln_beta;
             p.ptab = s->d_ptab;
             p.ptab_vmax = s->ptab_vmax;

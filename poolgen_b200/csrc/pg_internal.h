@@ -78,6 +78,7 @@ struct ScanParams {
     double w_uniform;     // s_0 / sum(s) when all weights are equal
     double df;            // Student-t degrees of freedom (n-1 ols, n-2 corr)
     double inv_df;        // 1 / df
+    double inv_n, inv_nm2; // 1 / n, 1 / (n - 2)
     double ln_beta;       // lnG(df/2 + 1/2) - lnG(df/2) - lnG(1/2)
     const void *ptab;     // per-scan table of ln p(v) (double4 per interval), NULL = continued fraction on the device
     double ptab_vmax, ptab_inv_h;

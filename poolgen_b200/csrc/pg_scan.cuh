@@ -690,7 +690,7 @@ __device__ __forceinline__ bool ols_gram_m(const ScanParams &p, double *tg, unsi
         c[a] = slot_col(cb, a);
         sx[a] = (a < m) ? tg[AC::S0 + c[a]] : 0.0;
     }
-    const double inv_n = 1.0 / nn;
+    const double inv_n = p.inv_n;
     double amp = 1.0;
 #pragma unroll
     for (int a = 0; a < M; a++)
@@ -887,11 +887,11 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
                 const int c = slot_col(cb, a);
                 const double sxa = tg[AC::S0 + c];
                 const double raw = tg[AC::P0 + c * A - c * (c - 1) / 2];
-                const double sxx = raw - sxa * sxa / nn;
+                const double sxx = raw - sxa * sxa * p.inv_n;
                 if (!(raw <= 1e6 * sxx)) redo = true;  // up to 6 of 16 digits lost by the single-pass form: r keeps 1e-10
 #pragma unroll
                 for (int k = 0; k < K; k++) {
-                    const double sxy = tg[AC::C0 + c * K + k] - sxa * p.ysum[k] / nn;
+                    const double sxy = tg[AC::C0 + c * K + k] - sxa * (p.ysum[k] * p.inv_n);
                     tb[(a * K + k) * 2 + 0] = sxy / (sqrt(sxx) * sqrt(p.syy[k]));
                     tb[(a * K + k) * 2 + 1] = 0.0;
                 }
@@ -952,7 +952,6 @@ template <int A, int K, int KIND>
 __device__ __noinline__ void write_records(const ScanParams &p, const PTableDev &tab, int64_t locus, int status,
                                            int m, unsigned cb, const double *tb) {
     constexpr int T2 = 2 * (A - 1) * K;
-    const double nn = (double)p.lay.n;
     if (p.write_meta) {
         uint64_t mv = (uint64_t)status;
         if (status == PG_LOCUS_OK) {
@@ -995,13 +994,13 @@ __device__ __noinline__ void write_records(const ScanParams &p, const PTableDev 
                     // pearsons_correlation, src/gwas/correlation_test.rs:52-70
                     const double r = v0;
                     if (r == r) {
-                        const double s2 = (1.0 - r * r) / (nn - 2.0);
+                        const double s2 = (1.0 - r * r) * p.inv_nm2;  // the sign is that of 1 - r^2 either way
                         o1[k] = r;
                         if (s2 <= 0.0) {
                             o0[k] = r;
                             o3[k] = kEps;
                         } else {
-                            const double tt = r / sqrt(s2);
+                            const double tt = r * rsqrt(s2);
                             o2[k] = tt;
                             o0[k] = round(r * 1e7) / 1e7;
                             if (p.lay.n > 2) {
