@@ -310,7 +310,7 @@ def run_cuda(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read + dram__bytes_write of one step (scan + fix-up kernel) from the ncu --set full
                          # capture in profiles/ncu_raw_r1.csv: 33,125 B per locus at the C3 shape
-                         "traffic": (32353.0 * L) if (N_POOLS, N_ALLELES, N_PHEN) == (1000, 4, 3) else None,
+                         "traffic": (32340.0 * L) if (N_POOLS, N_ALLELES, N_PHEN) == (1000, 4, 3) else None,
                          "traffic_unit": "bytes per launch (profiles/README.md)", "peak_source": peak_src,
                          "algorithmic_bytes_per_locus": ALG_BYTES_PER_LOCUS,
                          "resident_input_bytes_per_locus": in_bytes / L, "kernel_ms": per_launch_ms},
