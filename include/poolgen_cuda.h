@@ -9,7 +9,7 @@
  *      gwas::correlation          src/gwas/correlation_test.rs:73-129 PG_KIND_CORR
  *      tables::chisq              src/tables/chisq_test.rs:5-47       PG_KIND_CHISQ
  *      tables::fisher             src/tables/fisher_exact_test.rs:32-130 PG_KIND_FISHER
- * and the whole-matrix entry `ols_with_covariate` (src/gwas/ols.rs:278-436) through the pg_kinship_*
+ * and the whole-matrix entry `ols_with_covariate` (src/gwas/ols.rs:278-436) through the pg_kin_*
  * functions.  The per-locus callback `Fn(&mut T, &FilterStats) -> Option<String>` becomes a
  * per-BATCH call: the reader threads parse their byte range (src/base/sync.rs:827-868) into a slab
  * of counts, hand the slab over, and format the returned numeric records with the reference's own
