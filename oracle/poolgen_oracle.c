@@ -5,6 +5,13 @@
  * file:line it follows (paths relative to the poolgen repository root).  Compile with
  * -ffp-contract=off: Rust never fuses a*b+c, so neither may this file.
  *
+ * Pinning: the reference cannot be built here (no Rust toolchain), so this file is pinned to every known-answer
+ * vector the reference's own unit tests hold for the path (tests/test_oracle_golden.py: pearson r and p, chi-square,
+ * Fisher, factorial_log10, hypergeom_ratio, sync parse / filter / sort / load, phenotype parse, the betas of the stale
+ * ols vector, Rust's f64 Display and rounding).  PARITY UNPINNED where no reference vector exists: the rounding of
+ * MKL's inv / det / eig (an LU restatement stands in) and the ols_iter p-value (df = n - 1 read off
+ * src/gwas/ols.rs:139).
+ *
  * Style note: like the reference, every per-locus step allocates its own temporaries
  * (the reference clones ndarray matrices at each step); this is deliberate so that the
  * timed CPU baseline has the reference's structure, not a hand-optimised one.
