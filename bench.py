@@ -3,9 +3,10 @@
 
 Workload (BASELINE.json configs[2], "C3"): synthetic sync counts, 1,000 pools x 10,000,000 loci x 4 alleles,
 3 phenotypes, sharded over 8 GPUs = 1,250,000 loci per GPU.  The full matrix (323 GB of f64) does not fit one GPU,
-so the bench is WEAK-scaled: every rank holds one 1.25M-locus shard (45 GB resident in HBM, generated on the
+so the bench is WEAK-scaled: every rank holds one 1.25M-locus shard (40 GB resident in HBM, generated on the
 device by the integer-hash generator the CPU oracle can replay); at --gpus 8 the job is exactly C3.
-A step = one pass of the scan kernel over the rank's resident shard (inputs 45 GB >> 126 MB L2, so no flush).
+A step = one pass of the scan kernel over the rank's resident shard (inputs 40 GB >> 126 MB L2, so no flush).
+The other BASELINE configs are reported in the same JSON line under the top-level keys "c2", "c4", "c5" and "text".
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--loci-per-gpu L]
 """
@@ -37,6 +38,42 @@ def measured_peaks():
         with open(p) as fh:
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profile(n_pools: int, n_alleles: int, n_phen: int):
+    """DRAM bytes per locus of one step (dram__bytes_read.sum + dram__bytes_write.sum of the streaming kernel and the
+    fix-up kernel) read from the committed `ncu --set full` capture of this shape: profiles/ncu_raw_r<N>.csv with its
+    sidecar profiles/ncu_raw_r<N>.json ({"shape": [pools, alleles, phenotypes], "loci": L, "kernels": [...]}).
+    Returns (bytes per locus, file) or (None, None) when no capture of this shape is committed."""
+    import csv
+    import glob
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for meta_path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_raw_r*.json")), reverse=True):
+        try:
+            with open(meta_path) as fh:
+                meta = json.load(fh)
+            if list(meta.get("shape", [])) != [n_pools, n_alleles, n_phen]:
+                continue
+            with open(meta_path[:-5] + ".csv", newline="") as fh:
+                rows = list(csv.reader(fh))
+            hdr, units = rows[0], rows[1]
+            kcol = hdr.index("Kernel Name")
+            total = 0.0
+            seen = set()
+            for r in rows[2:]:
+                name = r[kcol]
+                key = next((k for k in meta["kernels"] if k in name), None)
+                if key is None or key in seen:
+                    continue  # one launch of each kernel
+                seen.add(key)
+                for col in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    i = hdr.index(col)
+                    total += float(r[i].replace(",", "")) * unit[units[i]]
+            if seen:
+                return total / float(meta["loci"]), os.path.relpath(meta_path[:-5] + ".csv", ROOT)
+        except (OSError, ValueError, KeyError, IndexError):
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -107,29 +144,38 @@ def dist_env():
     return rank, local, world
 
 
-def cpu_reference_rate(seconds_target: float, n_threads: int, warm: bool = True):
-    """The reference's CPU path restated (oracle/poolgen_oracle.c, per-locus allocation structure and one OS thread
-    per contiguous locus range like src/base/sync.rs:917-939) timed on a bounded sample of the SAME workload."""
+def cpu_reference_rate(seconds_target: float, n_threads: int, tight: bool = False):
+    """The reference's CPU path restated (oracle/poolgen_oracle.c, one OS thread per contiguous locus range like
+    src/base/sync.rs:917-939) timed on a bounded sample of the SAME workload.  tight=False is the faithful structure
+    (per-locus allocations, the pool-size total re-summed per pool and allele as src/base/sync.rs:262-270 does, X'X
+    refactored per phenotype as src/gwas/ols.rs:180); tight=True the same arithmetic without that avoidable work
+    (bit-identical records, tests/test_oracle_golden.py) -- the upper bound of what the CPU path could do.  The inputs
+    come from libpoolgen_synth.so: this leg never maps the product library."""
     from oracle import pgo
-    import poolgen_b200 as pb
-    phen = pb.synth_phen_host(SEED, N_POOLS, N_PHEN)
+    from poolgen_b200 import capi
+    phen = capi.synth_phen_host(SEED, N_POOLS, N_PHEN)
     fs = pgo.FilterStats(pool_sizes=np.full(N_POOLS, 1.0 / N_POOLS))
     codes = np.arange(N_ALLELES, dtype=np.uint8)
-    probe = 256 * n_threads
-    counts = pb.synth_counts_host(SEED, 0, probe, N_POOLS, N_ALLELES)
+    probe = (2048 if tight else 256) * n_threads
+    counts = capi.synth_counts_host(SEED, 0, probe, N_POOLS, N_ALLELES)
     t0 = time.perf_counter()
-    pgo.scan_batch(pgo.SCAN_OLS, counts, codes, phen, fs, n_threads)
+    pgo.scan_batch(pgo.SCAN_OLS, counts, codes, phen, fs, n_threads, tight=tight)
     dt = time.perf_counter() - t0
     rate = probe / dt
     sample = int(max(probe, min(400_000, rate * seconds_target)))
     sample -= sample % n_threads
-    counts = pb.synth_counts_host(SEED, 0, sample, N_POOLS, N_ALLELES)
+    counts = capi.synth_counts_host(SEED, 0, sample, N_POOLS, N_ALLELES)
 
     def step():
         t0 = time.perf_counter()
-        pgo.scan_batch(pgo.SCAN_OLS, counts, codes, phen, fs, n_threads)
+        pgo.scan_batch(pgo.SCAN_OLS, counts, codes, phen, fs, n_threads, tight=tight)
         return time.perf_counter() - t0
     return step, sample
+
+
+def product_library_mapped() -> bool:
+    with open("/proc/self/maps") as fh:
+        return any("libpoolgen_cuda" in line for line in fh)
 
 
 def run_reference(args):
@@ -146,6 +192,11 @@ def run_reference(args):
     print(f"[reference arm] {args.warmup}+{args.steps} steps done after {time.perf_counter() - t_start:.1f} s", file=sys.stderr)
     total = sum(times)
     value = sample * args.steps / total
+    # the "tight" variant next to it: same records without the reference's avoidable work
+    tstep, tsample = cpu_reference_rate(args.cpu_seconds, n_threads, tight=True)
+    tstep()
+    tdt = min(tstep() for _ in range(2))
+    print(f"[reference arm] tight variant: {tsample} loci in {tdt:.2f} s", file=sys.stderr)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -156,9 +207,16 @@ def run_reference(args):
                                     "(in-memory counts, parsing and CSV writing excluded) and scales linearly in loci",
                    "filters": "CLI defaults: min depth 1, MAF 0.001, missingness 0"},
         "cpu_baseline": {"value": value, "unit": "loci/s", "cores": n_threads, "kind": "port",
-                         "sample": f"{sample} loci of the C3 shape per step, {n_threads} OS threads over contiguous locus ranges"},
+                         "sample": f"{sample} loci of the C3 shape per step, {n_threads} OS threads over contiguous locus ranges",
+                         "variant": "faithful (per-locus allocations, pool-size total re-summed per pool and allele, "
+                                    "X'X refactored per phenotype -- what the reference does)",
+                         "tight": {"value": tsample / tdt, "unit": "loci/s", "cores": n_threads,
+                                   "sample": f"{tsample} loci, best of 2",
+                                   "variant": "same arithmetic and records, total hoisted, one inversion per locus, "
+                                              "no per-locus allocation"}},
         "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "maps_product_library": product_library_mapped(),
     }
     print(json.dumps(line))
     return 0
@@ -280,7 +338,7 @@ def run_cuda(args):
     if not args.no_extras:
         if rank == 0:
             extras = c2_numbers(ctx, pb)
-            extras.update(c5_numbers(ctx, pb))
+            extras.update(c5_numbers(ctx, pb, args.c5_loci))
             extras.update(text_numbers(ctx, pb))
         kin = c4_numbers(ctx, pb, dist, rank, world)  # every rank takes part (column shards + all-reduce)
         if rank == 0:
@@ -295,9 +353,18 @@ def run_cuda(args):
             n_threads = os.cpu_count() or 1
             step, sample = cpu_reference_rate(12.0, n_threads)
             dt = step()
+            tstep, tsample = cpu_reference_rate(6.0, n_threads, tight=True)
+            tdt = tstep()
             cpu = {"value": sample / dt, "unit": "loci/s", "cores": n_threads, "kind": "port",
                    "sample": f"{sample} loci of the C3 shape (1000 pools x 4 alleles, 3 phenotypes), in-memory counts, "
-                             f"{n_threads} OS threads over contiguous locus ranges, {dt:.1f} s"}
+                             f"{n_threads} OS threads over contiguous locus ranges, {dt:.1f} s",
+                   "variant": "faithful (per-locus allocations, pool-size total re-summed per pool and allele as "
+                              "src/base/sync.rs:262-270, X'X refactored per phenotype as src/gwas/ols.rs:180)",
+                   "tight": {"value": tsample / tdt, "unit": "loci/s", "cores": n_threads,
+                             "sample": f"{tsample} loci, {tdt:.1f} s",
+                             "variant": "same arithmetic, bit-identical records: total hoisted, one inversion per "
+                                        "locus, no per-locus allocation"}}
+        traffic_per_locus, traffic_file = traffic_from_profile(N_POOLS, N_ALLELES, N_PHEN)
         line = {
             "metric": METRIC, "value": value, "unit": "loci/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -308,18 +375,24 @@ def run_cuda(args):
                        "filters": "CLI defaults: min depth 1, MAF 0.001, missingness 0", "ok_fraction": ok_frac,
                        "e2e_format": f"u8 counts (every count < 256), slabs of {slab} loci, depth-3 pipeline, {n_slabs} slabs"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read + dram__bytes_write of one step (scan + fix-up kernel) from the ncu --set full
-                         # capture in profiles/ncu_raw_r1.csv: 33,125 B per locus at the C3 shape
-                         "traffic": (32340.0 * L) if (N_POOLS, N_ALLELES, N_PHEN) == (1000, 4, 3) else None,
-                         "traffic_unit": "bytes per launch (profiles/README.md)", "peak_source": peak_src,
+                         # dram__bytes_read + dram__bytes_write of one step (streaming + fix-up kernel), read at run time
+                         # from the committed ncu --set full capture of this shape, scaled to the resident batch
+                         "traffic": (traffic_per_locus * L) if traffic_per_locus else None,
+                         "traffic_unit": "bytes per launch", "traffic_source": traffic_file,
+                         "traffic_bytes_per_locus": traffic_per_locus, "peak_source": peak_src,
                          "algorithmic_bytes_per_locus": ALG_BYTES_PER_LOCUS,
                          "resident_input_bytes_per_locus": in_bytes / L, "kernel_ms": per_launch_ms},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "loci/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
-            "extras": extras,
         }
+        # the other BASELINE configs, top level so that they survive the driver's parse of this line
+        for key, names in (("c2", ("c2_ols_iter", "c2_pearson_corr")), ("c5", ("c5_chisq_test", "c5_fisher_exact_test")),
+                           ("c4", ("c4_kinship",)), ("text", ("e2e_sync_text", "e2e_text_to_csv"))):
+            got = {n: extras[n] for n in names if n in extras}
+            if got:
+                line[key] = got[names[0]] if len(names) == 1 else got
         if cpus is not None:
             line["config"]["cpu_affinity"] = f"each rank bound to the {len(cpus)} CPUs next to its GPU (NVML)"
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -355,11 +428,11 @@ def c2_numbers(ctx, pb):
     return out
 
 
-def c5_numbers(ctx, pb):
-    """BASELINE.json configs[4] (C5): chisq_test + fisher_exact_test on 2 pools x L loci of synthetic counts
+def c5_numbers(ctx, pb, L=50_000_000):
+    """BASELINE.json configs[4] (C5): chisq_test + fisher_exact_test on 2 pools x 50M loci of synthetic counts
     (count path: u32 [locus][allele][pool] in, 2 f64 + status out; 4*n*6 + 16 = 64 algorithmic bytes per locus)."""
     out = {}
-    n, A, L = 2, 6, 20_000_000
+    n, A = 2, 6
     fs = pb.FilterStats(pool_sizes=np.full(n, 0.5))
     peak, _ = measured_peaks()
     alg = 4 * n * 6 + 16
@@ -372,7 +445,8 @@ def c5_numbers(ctx, pb):
         per = ms / 5
         out[name] = {"loci_per_s": L / (per * 1e-3), "kernel_ms": per, "loci": L,
                      "roofline_frac": alg * L / (per * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_locus": alg,
-                     "note": "960 MB of counts per pass > L2 (126 MB); Fisher is compute-bound (O((n a)^2 (n+a)) log10/pow per locus)"}
+                     "note": f"{L * n * A * 4 / 1e9:.1f} GB of counts per pass > L2 (126 MB); Fisher is compute-bound "
+                             "(O((n a)^2 (n+a)) log10/pow per locus)"}
         b.close()
         scan.close()
     return out
@@ -468,10 +542,42 @@ def text_numbers(ctx, pb, n_threads=2):
 FP64_DMMA_PEAK_TFLOPS = 37.1  # tools/fp64_probe.cu on this pool's B200 (profiles/fp64_probe_r1.txt): mma.sync m8n8k4 f64
 
 
+def dgemm_peak(torch, seconds: float = 2.0):
+    """cuBLAS Dgemm 8192^3 (torch.matmul on f64 operands) burst = best of 10, sustained = back to back for `seconds`:
+    the FP64 GEMM denominator BASELINE.md 3 names for the kinship Gram matrix, measured in the same process."""
+    n = 8192
+    a = torch.rand((n, n), dtype=torch.float64, device="cuda")
+    b = torch.rand((n, n), dtype=torch.float64, device="cuda")
+    c = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    flops = 2.0 * n * n * n
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    reps = max(3, int(seconds * 1e3 / best))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    e1.synchronize()
+    sustained = e0.elapsed_time(e1) / reps
+    del a, b, c
+    torch.cuda.empty_cache()
+    return flops / best / 1e9, flops / sustained / 1e9
+
+
 def c4_numbers(ctx, pb, dist, rank, world):
     """BASELINE.json configs[3] (C4): ols_iter_with_kinship, 2,000 pools x 5M biallelic loci = 10M allele columns
-    (160 GB of f64) column-sharded over 8 GPUs = 1.25M columns (20 GB) per rank: FP64 DMMA Gram matrix, all-reduce of
-    the n x n partials, eigen step, covariate scan."""
+    (160 GB of f64) column-sharded over 8 GPUs = 1.25M columns (20 GB) per rank: FP64 DMMA Gram matrix, the exchange
+    step (pg_kin_allreduce on the library's own NCCL communicator), eigen step, covariate scan."""
     import torch
     from poolgen_b200 import shard
     n, L_rank, k = 2000, 625_000, 1
@@ -480,20 +586,17 @@ def c4_numbers(ctx, pb, dist, rank, world):
     P = kin.columns
     kin.gram_time(1)
     gram_ms = kin.gram_time(3) / 3
-    if dist is not None:  # communicator warm-up on a scratch tensor, then the 32 MB exchange step timed on the device
-        scratch = torch.zeros(n * n, dtype=torch.float64, device="cuda")
-        dist.all_reduce(scratch)
-        torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    shard.allreduce_partial_gram(kin, dist)
-    ev1.record()
-    torch.cuda.synchronize()
-    ar_ms = ev0.elapsed_time(ev1)
-    P_total = shard.total_columns(P, dist)
+    comm = shard.make_comm(ctx, dist)      # rank 0's id travels over torch.distributed; the data path is the library's
+    kin.gram()
+    comm.kin_allreduce([kin])              # communicator warm-up (the first collective sets up the channels)
+    kin.gram()
+    P_total, ar_ms = comm.kin_allreduce([kin], timed=True)   # the 32 MB exchange step, CUDA events on the kin's stream
     t0 = time.perf_counter()
-    m = kin.eig_select(P_total, 0.75)
+    m = kin.eig_select(0, 0.75)
     eig_ms = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    kin.eig_select(0, 0.75)
+    eig_warm_ms = 1e3 * (time.perf_counter() - t0)
     phen = pb.synth_phen_host(0x5EED0004, n, k)
     kin.covar_scan(phen, 1)
     *_, covar_ms = kin.covar_scan(phen, 5)
@@ -506,26 +609,37 @@ def c4_numbers(ctx, pb, dist, rank, world):
     *_, covar10_ms = kin.covar_scan(phen, 5)
     covar10_ms /= 5
     kin.close()
-    t = torch.tensor([gram_ms, covar_ms, covar10_ms], dtype=torch.float64, device="cuda")
+    comm.close()
+    t = torch.tensor([gram_ms, covar_ms, covar10_ms, ar_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    gram_ms, covar_ms, covar10_ms = (float(v) for v in t.tolist())
+    gram_ms, covar_ms, covar10_ms, ar_ms = (float(v) for v in t.tolist())
+    if rank != 0:
+        return {}
+    dgemm_burst, dgemm_sustained = dgemm_peak(torch)
     peak, _ = measured_peaks()
     nt = (n + 127) // 128
     hw_flops = 2.0 * (nt * (nt + 1) // 2) * 128 * 128 * P       # the upper triangle of 128 x 128 tiles that is computed
     alg_flops = 2.0 * n * n * P                                  # what g.dot(&g.t()) does (ols.rs:295)
     alg_bytes = (8.0 * n + 24 * k) * P
+    fp64_floor_ms = 2.0 * n * 12 * P / (FP64_DMMA_PEAK_TFLOPS * 1e9)   # Q'G with 12 vectors at the FP64 peak
+    bound10_ms = max(alg_bytes / (peak * 1e6), fp64_floor_ms)
     return {"c4_kinship": {
-        "columns_per_gpu": P, "n_pools": n, "n_eigenvecs": m,
+        "columns_per_gpu": P, "columns_total": P_total, "n_pools": n, "n_eigenvecs": m,
         "gram_ms": gram_ms, "gram_algorithmic_tflops_per_gpu": alg_flops / gram_ms / 1e9,
         "gram_hardware_tflops_per_gpu": hw_flops / gram_ms / 1e9,
         "gram_frac_of_fp64_tensor_peak": hw_flops / gram_ms / 1e9 / FP64_DMMA_PEAK_TFLOPS,
         "fp64_tensor_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
-        "allreduce_ms": ar_ms if world > 1 else None, "eig_select_ms": eig_ms,
+        "cublas_dgemm_8192_tflops_burst": dgemm_burst, "cublas_dgemm_8192_tflops_sustained": dgemm_sustained,
+        "gram_hardware_frac_of_dgemm_sustained": hw_flops / gram_ms / 1e9 / dgemm_sustained,
+        "gram_algorithmic_frac_of_dgemm_sustained": alg_flops / gram_ms / 1e9 / dgemm_sustained,
+        "allreduce_ms": ar_ms, "allreduce": "pg_kin_allreduce (library NCCL communicator, %d ranks)" % world,
+        "eig_select_ms": eig_ms, "eig_select_warm_ms": eig_warm_ms,
         "covar_scan_ms": covar_ms, "covar_columns_per_s": world * P / (covar_ms * 1e-3),
         "covar_roofline_frac": alg_bytes / (covar_ms * 1e-3) / 1e9 / peak,
         "covar_scan_10_covariates_ms": covar10_ms,
         "covar_10_covariates_roofline_frac": alg_bytes / (covar10_ms * 1e-3) / 1e9 / peak,
+        "covar_10_covariates_frac_of_min_hbm_fp64": bound10_ms / covar10_ms,
         "note": "symmetric Gram: the algorithmic rate counts 2 n^2 P flops, the hardware rate the DMMA work issued"}}
 
 
@@ -539,6 +653,7 @@ def main():
     ap.add_argument("--e2e-slab", type=int, default=16384)
     ap.add_argument("--e2e-slabs", type=int, default=24)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--c5-loci", type=int, default=50_000_000, help="loci of the C5 leg (BASELINE: 50M)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--cpu-seconds", type=float, default=2.5, help="target seconds per step of the --impl reference arm")
     args = ap.parse_args()

@@ -41,6 +41,11 @@ pub struct pg_batch {
 pub struct pg_kin {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct pg_comm {
+    _private: [u8; 0],
+}
+pub const PG_COMM_ID_BYTES: usize = 128;
 
 /// FilterStats (src/base/structs_and_traits.rs:69-78), sync-path fields
 #[repr(C)]
@@ -138,10 +143,16 @@ extern "C" {
     pub fn pg_format_frequency_header(pool_names: *const *const c_char, n_pools: c_int, out: *mut c_char, capacity: usize, n_bytes: *mut usize) -> c_int;
     pub fn pg_format_frequency_rows(n_columns: i64, n_pools: c_int, columns: *const f64, col_locus: *const i64, col_allele: *const u8, labels: *const pg_row_labels, locus_order: *const i64, n_order: i64, n_threads: c_int, out: *mut c_char, capacity: usize, n_bytes: *mut usize) -> c_int;
     pub fn pg_format_f64(x: f64, n_digits: c_int, out: *mut c_char, capacity: usize) -> c_int;
-    // ---- synthetic workload (bench and tests)
-    pub fn pg_synth_counts_host(seed: u64, first_locus: i64, n_loci: i64, n_pools: c_int, n_alleles: c_int, counts_out: *mut u32) -> c_int;
-    pub fn pg_synth_phen_host(seed: u64, n_pools: c_int, k: c_int, phen_out: *mut f64) -> c_int;
-    pub fn pg_synth_sync_text_host(seed: u64, first_locus: i64, n_loci: i64, n_pools: c_int, n_alleles: c_int, out: *mut c_char, capacity: usize, n_bytes: *mut usize) -> c_int;
+    // ---- several GPUs: shard ranges, the library's NCCL communicator, the kinship exchange step
+    pub fn pg_shard_range(total: i64, rank: c_int, world: c_int, begin: *mut i64, end: *mut i64) -> c_int;
+    pub fn pg_nccl_version(version: *mut c_int) -> c_int;
+    pub fn pg_init_multi(devices: *const c_int, n: c_int, ctxs_out: *mut *mut pg_ctx, comm_out: *mut *mut pg_comm) -> c_int;
+    pub fn pg_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn pg_comm_init_rank(ctx: *mut pg_ctx, id: *const u8, rank: c_int, world: c_int, out: *mut *mut pg_comm) -> c_int;
+    pub fn pg_comm_info(comm: *const pg_comm, world: *mut c_int, n_local: *mut c_int, first_rank: *mut c_int) -> c_int;
+    pub fn pg_comm_destroy(comm: *mut pg_comm) -> c_int;
+    pub fn pg_kin_allreduce(comm: *mut pg_comm, kins: *const *mut pg_kin, n_local: c_int, p_total: *mut i64, ms: *mut f32) -> c_int;
+    pub fn pg_kin_copy_covariates(dst: *mut pg_kin, src: *const pg_kin) -> c_int;
 }
 
 /// `Err(message)` for a negative return code

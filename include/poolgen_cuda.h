@@ -167,7 +167,7 @@ int pg_scan_text_labels(pg_scan *scan, int ticket, const uint64_t **line_offsets
 /* ---- ols_iter_with_kinship: ols_with_covariate (src/gwas/ols.rs:278-436) over a device-resident block of allele
  * columns of GenotypesAndPhenotypes.intercept_and_allele_frequencies[:, 1..] (src/base/sync.rs:1106-1179).
  * One pg_kin per GPU holds that GPU's column shard.  Sequence: append columns -> pg_kin_gram (partial G G') ->
- * [sum the partials over the GPUs: pg_kin_partial hands out the device pointer for an NCCL all-reduce] ->
+ * [sum the partials over the GPUs: pg_kin_allreduce, below] ->
  * pg_kin_eig_select (K = sum / P_total, eigen-decomposition, number of PCs by the reference's rule) ->
  * pg_kin_covar_scan (beta, var(beta), p of the allele coefficient with X = [1 | PCs | g], one record per column
  * and phenotype; the caller writes them phenotype-outer / column-inner like src/gwas/ols.rs:410-433). ----------- */
@@ -200,6 +200,7 @@ int pg_kin_gram_time(pg_kin *kin, int iters, float *ms_total);
 int pg_kin_partial(pg_kin *kin, double **device_ptr, size_t *n_elems); /* n_pools x n_pools, synchronises */
 int pg_kin_partial_get(pg_kin *kin, double *out_host);
 int pg_kin_partial_set(pg_kin *kin, const double *in_host);
+/* P_total = 0: the column count pg_kin_allreduce summed (or, without an all-reduce, the resident columns) */
 int pg_kin_eig_select(pg_kin *kin, int64_t P_total, double variance_explained, int *n_eigenvecs);
 int pg_kin_eigvals(pg_kin *kin, double *out, int count); /* K's eigenvalues, high to low */
 int pg_kin_set_covariates(pg_kin *kin, const double *cov /* n_pools x m row-major */, int m);
@@ -207,6 +208,32 @@ int pg_kin_set_covariates(pg_kin *kin, const double *cov /* n_pools x m row-majo
  * iters > 0 additionally times `iters` back-to-back launches with CUDA events */
 int pg_kin_covar_scan(pg_kin *kin, const double *phen, int k, int iters, float *ms_total, const double **beta,
                       const double **var, const double **pval);
+
+/* ---- several GPUs behind the ABI -----------------------------------------------------------------
+ * The reference runs every analysis in one process (src/main.rs:246-298).  The per-locus scans shard over loci with no
+ * exchange step: pg_shard_range names the contiguous range of a rank (earlier ranks take the larger shards; rank order
+ * = file order, like the reader threads' contiguous byte ranges, src/base/helpers.rs:74-91).  ols_with_covariate has
+ * ONE exchange step: `g.dot(&g.t())` (src/gwas/ols.rs:295) over column shards is the sum of the per-GPU partial Gram
+ * matrices -- pg_kin_allreduce (NCCL all-reduce over NVLink on the handles' own device buffers and streams; the column
+ * counts are summed in the same group).  The communicator is created by the library:
+ *   pg_init_multi        one process drives n GPUs (what the Rust CLI does): n contexts + ncclCommInitAll
+ *   pg_comm_unique_id /  one process per GPU: rank 0 obtains the id, the host ships the PG_COMM_ID_BYTES bytes to the
+ *   pg_comm_init_rank    other ranks however it likes (a file, MPI, torch.distributed), every rank joins
+ * kins[i] belongs to local rank i of the communicator.  After the all-reduce every handle holds the total;
+ * pg_kin_eig_select(kin, 0, ...) then uses the summed column count.  pg_kin_copy_covariates hands the outcome of one
+ * eigen step to the other handles of a process (the step is replicated work).  NCCL is loaded on first use. */
+typedef struct pg_comm pg_comm;
+#define PG_COMM_ID_BYTES 128
+int pg_shard_range(int64_t total, int rank, int world, int64_t *begin, int64_t *end);
+int pg_nccl_version(int *version);
+int pg_init_multi(const int *devices, int n, pg_ctx **ctxs_out /* [n] */, pg_comm **comm_out);
+int pg_comm_unique_id(uint8_t *id /* [PG_COMM_ID_BYTES] */);
+int pg_comm_init_rank(pg_ctx *ctx, const uint8_t *id, int rank, int world, pg_comm **out);
+int pg_comm_info(const pg_comm *comm, int *world, int *n_local, int *first_rank);
+int pg_comm_destroy(pg_comm *comm); /* the contexts of pg_init_multi are destroyed by the caller (pg_destroy) */
+/* ms (optional): device time of the exchange step, CUDA events on kins[0]'s stream */
+int pg_kin_allreduce(pg_comm *comm, pg_kin *const *kins, int n_local, int64_t *P_total, float *ms);
+int pg_kin_copy_covariates(pg_kin *dst, const pg_kin *src);
 
 /* ---- the reference's CSV rows from the numeric records (host code, threads over locus ranges) -------
  * Replaces the string building of the per-locus callbacks (src/gwas/ols.rs:255-275, src/gwas/correlation_test.rs:113-128,
@@ -249,15 +276,6 @@ int pg_format_frequency_rows(int64_t n_columns, int n_pools, const double *colum
                              size_t *n_bytes);
 /* one number: n_digits > 0 = parse_f64_roundup_and_own(x, n_digits), 0 = f64::to_string(); returns the length */
 int pg_format_f64(double x, int n_digits, char *out, size_t capacity);
-
-/* ---- synthetic workload, host side: identical bits to pg_batch_synth ------------ */
-int pg_synth_counts_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int n_pools, int n_alleles,
-                         uint32_t *counts_out);
-int pg_synth_phen_host(uint64_t seed, int n_pools, int k, double *phen_out /* n_pools x k row-major */);
-/* the same counts as sync text (six columns, N = D = 0 beyond n_alleles): chr<1 + locus / 1000000> \t <locus + 1> \t N ...;
- * returns the bytes written (or needed, when capacity is too small) in *n_bytes */
-int pg_synth_sync_text_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int n_pools, int n_alleles,
-                            char *out, size_t capacity, size_t *n_bytes);
 
 #ifdef __cplusplus
 }

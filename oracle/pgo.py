@@ -103,6 +103,8 @@ def lib():
             ("pgo_format_fisher_line", i, [C.c_char_p, C.c_uint64, C.POINTER(_TableResult), C.c_char_p, C.c_size_t]),
             ("pgo_scan_batch", i, [i, C.POINTER(C.c_uint32), C.c_int64, i, i, u8p, dp, i,
                                    C.POINTER(_FilterStats), i, C.POINTER(C.c_int8), u8p, u8p, dp, dp, dp, dp, dp]),
+            ("pgo_scan_batch_tight", i, [i, C.POINTER(C.c_uint32), C.c_int64, i, i, u8p, dp, i,
+                                         C.POINTER(_FilterStats), i, C.POINTER(C.c_int8), u8p, u8p, dp, dp, dp, dp, dp]),
         ]:
             fn = getattr(L, name)
             fn.restype = res
@@ -331,8 +333,9 @@ class BatchResult:
     pval: np.ndarray
 
 
-def scan_batch(kind, counts_packed, allele_codes, phen, fs: FilterStats, n_threads=1) -> BatchResult:
-    """counts_packed: uint32 [L, A, n] (allele-major, pools contiguous)."""
+def scan_batch(kind, counts_packed, allele_codes, phen, fs: FilterStats, n_threads=1, tight=False) -> BatchResult:
+    """counts_packed: uint32 [L, A, n] (allele-major, pools contiguous).  tight=True: the allocation-free ols_iter
+    variant with the pool-size total hoisted and one inversion per locus (bit-identical records)."""
     cp = np.ascontiguousarray(counts_packed, dtype=np.uint32)
     L, A, n = cp.shape
     codes = np.ascontiguousarray(allele_codes, dtype=np.uint8)
@@ -350,7 +353,8 @@ def scan_batch(kind, counts_packed, allele_codes, phen, fs: FilterStats, n_threa
     fm = np.full((L, MAX_ALLELES), np.nan)
     stat, var, t, pval = (np.full((L, MAX_ALLELES, k), np.nan) for _ in range(4))
     fsc = fs.c()
-    rc = lib().pgo_scan_batch(int(kind), cp.ctypes.data_as(C.POINTER(C.c_uint32)), L, n, A, _u8p(codes),
+    fn = lib().pgo_scan_batch_tight if tight else lib().pgo_scan_batch
+    rc = fn(int(kind), cp.ctypes.data_as(C.POINTER(C.c_uint32)), L, n, A, _u8p(codes),
                               _dp(y), k, C.byref(fsc), int(n_threads),
                               status.ctypes.data_as(C.POINTER(C.c_int8)), _u8p(n_out), _u8p(allele),
                               _dp(fm), _dp(stat), _dp(var), _dp(t), _dp(pval))
@@ -393,12 +397,14 @@ def select_eigenvectors(eigvals_desc, threshold):
     return m
 
 
-def ols_with_covariate(G_cols, phen, threshold):
+def ols_with_covariate(G_cols, phen, threshold, columns=None, return_eig=False):
     """G_cols [P, n] allele columns, phen [n, k].  Returns (m, beta [P, k], var [P, k], pval [P, k]) where each entry is
     the LAST coefficient of ols([1 | PCs | g], y) (gwas/ols.rs:340-370); NaN where the regression fails.
     The eigen-decomposition uses numpy's symmetric solver with eigenvalues sorted from high to low; the reference calls
     MKL dgeev and ASSUMES that order (gwas/ols.rs:296) -- parity unpinned for the order, pinned for everything else by
-    the invariance of the last coefficient to the basis of span(PCs)."""
+    the invariance of the last coefficient to the basis of span(PCs).
+    columns: optional subset of column ordinals to regress (the records of the others stay NaN) -- the kinship matrix is
+    always formed from ALL columns.  return_eig: additionally return (eigenvalues high to low, eigenvectors)."""
     G = np.ascontiguousarray(G_cols, dtype=np.float64)
     P, n = G.shape
     y = np.ascontiguousarray(phen, dtype=np.float64)
@@ -411,11 +417,13 @@ def ols_with_covariate(G_cols, phen, threshold):
     m = select_eigenvectors(list(w), threshold)
     cov = V[:, :m]
     beta, var, pval = (np.full((P, k), np.nan) for _ in range(3))
-    for c in range(P):
+    for c in (range(P) if columns is None else columns):
         x = np.ones((n, 2 + m))
         x[:, 1:1 + m] = cov
         x[:, 1 + m] = G[c]
         rc, b, v, p, _ = ols(x, y)
         if rc == 0:
             beta[c], var[c], pval[c] = b[1 + m], v[1 + m], p[1 + m]
+    if return_eig:
+        return m, beta, var, pval, w, V
     return m, beta, var, pval

@@ -233,22 +233,13 @@ static int lu_factor(double *a, int n, int *ipiv) {
     return info;
 }
 
-int pgo_lu_inverse(double *a, int n) {
-    int *ipiv = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
-    double *work = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+/* dgetrf + dgetri with caller-provided scratch (ipiv[n], work[n]) */
+static int lu_inverse_ws(double *a, int n, int *ipiv, double *work) {
     int info = lu_factor(a, n, ipiv);
-    if (info != 0) {
-        free(ipiv);
-        free(work);
-        return info;
-    }
+    if (info != 0) return info;
     /* dtrti2: inverse of the upper triangle, non-unit diagonal */
     for (int j = 0; j < n; j++) {
-        if (a[j + j * n] == 0.0) {
-            free(ipiv);
-            free(work);
-            return j + 1;
-        }
+        if (a[j + j * n] == 0.0) return j + 1;
     }
     for (int j = 0; j < n; j++) {
         a[j + j * n] = 1.0 / a[j + j * n];
@@ -287,14 +278,20 @@ int pgo_lu_inverse(double *a, int n) {
             }
         }
     }
-    free(ipiv);
-    free(work);
     return 0;
 }
 
-double pgo_lu_det(const double *a_in, int n) {
-    double *a = (double *)malloc(sizeof(double) * (size_t)n * (size_t)n);
-    int *ipiv = (int *)malloc(sizeof(int) * (size_t)n);
+int pgo_lu_inverse(double *a, int n) {
+    int *ipiv = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    double *work = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    int info = lu_inverse_ws(a, n, ipiv, work);
+    free(ipiv);
+    free(work);
+    return info;
+}
+
+/* determinant through dgetrf on the scratch copy a[n*n] */
+static double lu_det_ws(const double *a_in, int n, double *a, int *ipiv) {
     memcpy(a, a_in, sizeof(double) * (size_t)n * (size_t)n);
     lu_factor(a, n, ipiv); /* singular => a zero on the diagonal => det 0 */
     double det = 1.0;
@@ -302,6 +299,13 @@ double pgo_lu_det(const double *a_in, int n) {
         det = det * a[j + j * n];
         if (ipiv[j] != j) det = -det;
     }
+    return det;
+}
+
+double pgo_lu_det(const double *a_in, int n) {
+    double *a = (double *)malloc(sizeof(double) * (size_t)n * (size_t)n);
+    int *ipiv = (int *)malloc(sizeof(int) * (size_t)n);
+    double det = lu_det_ws(a_in, n, a, ipiv);
     free(a);
     free(ipiv);
     return det;
@@ -1157,6 +1161,159 @@ int pgo_format_fisher_line(const char *chr, uint64_t pos, const pgo_table_result
 }
 
 /* ====================================================================================== */
+/* "tight" ols_iterate: the SAME arithmetic, operation for operation, as pgo_ols_iterate   */
+/* (results are bit-identical, tests/test_oracle_golden.py), without the reference's       */
+/* avoidable work -- the honest upper bound of what its CPU path could do: */
+/*   - the pool-size total of sync.rs:262-270 is summed once per batch, not per pool and   */
+/*     allele of every locus (the value is the same every time);                          */
+/*   - X'X is inverted (and det(inv) checked) once per locus, not once per phenotype       */
+/*     (ols.rs:180 clones X and refactors it for each trait); (X'X)^-1 X' is formed once;  */
+/*   - no per-locus heap allocation: one workspace per thread.                            */
+/* Loci whose phenotype rows contain NaN take the faithful function.                       */
+/* ====================================================================================== */
+typedef struct {
+    uint64_t *counts; /* n x 6 */
+    double *f1;       /* n x 6 first-stage frequencies */
+    double *freq;     /* n x 6 renormalised, then sorted */
+    double *x;        /* n x 6 */
+    double *tmp;      /* 6 x n  (X'X)^-1 X' */
+    double *e;        /* n */
+    double *wnorm;    /* n: s_i / total */
+} tight_ws;
+
+static size_t tight_ws_doubles(int n) { return (size_t)n * (6 + 6 + 6 + 6 + 1 + 1); }
+
+static int ols_iterate_tight(const uint32_t *packed /* [A][n] */, const uint8_t *alleles_in, int n, int A,
+                             const double *phen, int k, const pgo_filter_stats *fs, tight_ws *ws,
+                             pgo_locus_result *out) {
+    result_fill_nan(out, k);
+    out->status = PGO_FILTERED;
+    /* columns in play, in order (remove_index keeps the order of the others) */
+    int col[PGO_MAX_ALLELES], p = 0;
+    uint8_t alle[PGO_MAX_ALLELES];
+    for (int j = 0; j < A; j++) {
+        if (fs->remove_ns && alleles_in[j] == PGO_N) continue; /* sync.rs:200-213 */
+        col[p] = j;
+        alle[p] = alleles_in[j];
+        p++;
+    }
+    /* coverage (sync.rs:217-229) and first-stage frequencies (sync.rs:242, 166-192) in one pass */
+    double min_cov = 0.0;
+    for (int i = 0; i < n; i++) {
+        double sum = 0.0;
+        for (int j = 0; j < p; j++) sum = sum + (double)packed[(size_t)col[j] * n + i];
+        if (i == 0 || sum < min_cov) min_cov = sum;
+        for (int j = 0; j < p; j++)
+            ws->f1[(size_t)i * 6 + j] = sum == 0.0 ? NAN : (double)packed[(size_t)col[j] * n + i] / sum;
+    }
+    if (min_cov < (double)fs->min_coverage_depth) return PGO_FILTERED;
+    if (n != fs->n_pool_sizes) return out->status = PGO_PANIC;
+    /* MAF (sync.rs:258-282) */
+    int kept[PGO_MAX_ALLELES], pk = 0;
+    for (int j = 0; j < p; j++) {
+        double q = 0.0;
+        for (int i = 0; i < n; i++) {
+            double f = ws->f1[(size_t)i * 6 + j];
+            double term = isnan(f) ? 0.0 : f * ws->wnorm[i];
+            q += term;
+        }
+        if (!((q < fs->min_allele_frequency) | (q > (1.00 - fs->min_allele_frequency)))) kept[pk++] = j;
+    }
+    if (pk < 2) return PGO_FILTERED;
+    {
+        int n_missing = 0; /* sync.rs:287-299 */
+        for (int i = 0; i < n; i++)
+            if (isnan(ws->f1[(size_t)i * 6 + kept[0]])) n_missing += 1;
+        if (n_missing == n) return PGO_FILTERED;
+        if (((double)n_missing / (double)n) > fs->max_missingness_rate) return PGO_FILTERED;
+    }
+    /* to_frequencies over the kept alleles (ols.rs:217-220) and the column sums of the sort (sync.rs:478-505) */
+    double csum[PGO_MAX_ALLELES];
+    for (int a = 0; a < pk; a++) csum[a] = 0.0;
+    for (int i = 0; i < n; i++) {
+        double sum = 0.0;
+        for (int a = 0; a < pk; a++) sum = sum + (double)packed[(size_t)col[kept[a]] * n + i];
+        for (int a = 0; a < pk; a++) {
+            double v = sum == 0.0 ? NAN : (double)packed[(size_t)col[kept[a]] * n + i] / sum;
+            ws->freq[(size_t)i * 6 + a] = v;
+            if (!isnan(v)) csum[a] = csum[a] + v;
+        }
+    }
+    int idx[PGO_MAX_ALLELES];
+    for (int a = 0; a < pk; a++) idx[a] = a;
+    for (int a = 1; a < pk; a++) { /* stable, decreasing */
+        int v = idx[a], b = a - 1;
+        while (b >= 0 && csum[v] > csum[idx[b]]) {
+            idx[b + 1] = idx[b];
+            b--;
+        }
+        idx[b + 1] = v;
+    }
+    /* drop the major allele (ols.rs:227-230), X = [1 | freqs] (ols.rs:240-246) */
+    const int pa = pk - 1, px = pk;
+    for (int i = 0; i < n; i++) {
+        ws->x[(size_t)i * px] = 1.0;
+        for (int j = 1; j < px; j++) ws->x[(size_t)i * px + j] = ws->freq[(size_t)i * 6 + idx[j]];
+    }
+    if (n < px) return -2; /* the n < p branch: the caller takes the faithful function */
+    /* X'X, its inverse and det(inv) once per locus (ols.rs:76-84) */
+    double xtx[36], det_scratch[36], work[6];
+    int ipiv[6];
+    for (int i = 0; i < px; i++)
+        for (int j = 0; j < px; j++) {
+            double s = 0.0;
+            for (int l = 0; l < n; l++) s = s + ws->x[(size_t)l * px + i] * ws->x[(size_t)l * px + j];
+            xtx[i * px + j] = s;
+        }
+    if (lu_inverse_ws(xtx, px, ipiv, work) != 0) return out->status = PGO_FAILED;
+    if (lu_det_ws(xtx, px, det_scratch, ipiv) == 0.0) return out->status = PGO_FAILED;
+    for (int i = 0; i < px; i++)
+        for (int r = 0; r < n; r++) {
+            double s = 0.0;
+            for (int l = 0; l < px; l++) s = s + xtx[i * px + l] * ws->x[(size_t)r * px + l];
+            ws->tmp[(size_t)i * n + r] = s;
+        }
+    const double freedom = (double)n - 1.0;
+    if (!(freedom > 0.0)) return out->status = PGO_PANIC;
+    for (int j = 0; j < k; j++) {
+        double b[6];
+        for (int i = 0; i < px; i++) {
+            double s = 0.0;
+            for (int r = 0; r < n; r++) s = s + ws->tmp[(size_t)i * n + r] * phen[(size_t)r * k + j];
+            b[i] = s;
+        }
+        double ee = 0.0;
+        for (int r = 0; r < n; r++) {
+            double xb = 0.0;
+            for (int l = 0; l < px; l++) xb = xb + ws->x[(size_t)r * px + l] * b[l];
+            ws->e[r] = phen[(size_t)r * k + j] - xb;
+        }
+        for (int r = 0; r < n; r++) ee = ee + ws->e[r] * ws->e[r];
+        const double ve = ee / ((double)n - (double)px);
+        for (int i = 1; i < px; i++) {
+            const double vb = ve * xtx[i * px + i];
+            const double t = fabs(b[i]) <= F64_EPSILON ? 0.0 : b[i] / sqrt(vb);
+            double pv;
+            if (fabs(t) <= F64_EPSILON) pv = 1.0;
+            else if (isnan(t)) pv = 1.0;
+            else pv = 2.00 * (1.00 - pgo_students_t_cdf(fabs(t), freedom));
+            out->stat[(size_t)(i - 1) * k + j] = b[i];
+            out->var[(size_t)(i - 1) * k + j] = vb;
+            out->t[(size_t)(i - 1) * k + j] = t;
+            out->pval[(size_t)(i - 1) * k + j] = pv;
+        }
+    }
+    out->n_alleles_out = pa;
+    for (int i = 1; i < px; i++) {
+        out->allele[i - 1] = alle[kept[idx[i]]];
+        double s = 0.0;
+        for (int r = 0; r < n; r++) s = s + ws->x[(size_t)r * px + i];
+        out->freq_mean[i - 1] = s / (double)n;
+    }
+    return out->status = PGO_OK;
+}
+
+/* ====================================================================================== */
 /* batch driver: contiguous locus ranges, one OS thread each (sync.rs:917-939)             */
 /* ====================================================================================== */
 typedef struct {
@@ -1171,6 +1328,7 @@ typedef struct {
     uint8_t *n_out;
     uint8_t *allele_out;
     double *freq_mean, *stat, *var, *t, *pval;
+    int tight; /* ols_iter only: the allocation-free variant (ols_iterate_tight) */
 } batch_job;
 
 static void *batch_worker(void *arg) {
@@ -1178,6 +1336,50 @@ static void *batch_worker(void *arg) {
     int n = jb->n_pools, A = jb->n_alleles, k = jb->k > 0 ? jb->k : 1;
     size_t cap = (size_t)PGO_MAX_ALLELES * (size_t)k;
     double *scratch = (double *)malloc(sizeof(double) * cap * 4);
+    if (jb->tight && jb->kind == PGO_SCAN_OLS) {
+        int phen_nan = 0;
+        for (size_t i = 0; i < (size_t)n * (size_t)k; i++)
+            if (isnan(jb->phen[i])) phen_nan = 1;
+        double *buf = (double *)malloc(sizeof(double) * tight_ws_doubles(n));
+        tight_ws ws;
+        ws.f1 = buf;
+        ws.freq = buf + (size_t)n * 6;
+        ws.x = buf + (size_t)n * 12;
+        ws.tmp = buf + (size_t)n * 18;
+        ws.e = buf + (size_t)n * 24;
+        ws.wnorm = buf + (size_t)n * 25;
+        ws.counts = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n * (size_t)A);
+        double total = 0.0; /* sync.rs:262-270, once */
+        for (int s_ = 0; s_ < jb->fs->n_pool_sizes; s_++) total = total + jb->fs->pool_sizes[s_];
+        for (int i = 0; i < n && i < jb->fs->n_pool_sizes; i++) ws.wnorm[i] = jb->fs->pool_sizes[i] / total;
+        for (int64_t l = jb->lo; l < jb->hi; l++) {
+            const uint32_t *src = jb->counts_packed + (size_t)l * (size_t)A * (size_t)n;
+            pgo_locus_result r;
+            r.stat = scratch;
+            r.var = scratch + cap;
+            r.t = scratch + 2 * cap;
+            r.pval = scratch + 3 * cap;
+            int status = phen_nan ? -2 : ols_iterate_tight(src, jb->allele_codes, n, A, jb->phen, k, jb->fs, &ws, &r);
+            if (status == -2) { /* NaN phenotypes or n < p: the faithful function */
+                for (int a = 0; a < A; a++)
+                    for (int i = 0; i < n; i++) ws.counts[(size_t)i * A + a] = src[(size_t)a * n + i];
+                status = pgo_ols_iterate(ws.counts, jb->allele_codes, n, A, jb->phen, k, jb->fs, &r);
+            }
+            if (jb->freq_mean)
+                memcpy(jb->freq_mean + (size_t)l * PGO_MAX_ALLELES, r.freq_mean, sizeof(double) * PGO_MAX_ALLELES);
+            if (jb->stat) memcpy(jb->stat + (size_t)l * cap, r.stat, sizeof(double) * cap);
+            if (jb->var) memcpy(jb->var + (size_t)l * cap, r.var, sizeof(double) * cap);
+            if (jb->t) memcpy(jb->t + (size_t)l * cap, r.t, sizeof(double) * cap);
+            if (jb->pval) memcpy(jb->pval + (size_t)l * cap, r.pval, sizeof(double) * cap);
+            if (jb->status) jb->status[l] = (int8_t)status;
+            if (jb->n_out) jb->n_out[l] = (uint8_t)(status == PGO_OK ? r.n_alleles_out : 0);
+            if (jb->allele_out) memcpy(jb->allele_out + (size_t)l * PGO_MAX_ALLELES, r.allele, PGO_MAX_ALLELES);
+        }
+        free(ws.counts);
+        free(buf);
+        free(scratch);
+        return NULL;
+    }
     for (int64_t l = jb->lo; l < jb->hi; l++) {
         /* "parse": build the n x p u64 LocusCounts matrix the callback receives */
         uint64_t *counts = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n * (size_t)A);
@@ -1224,11 +1426,11 @@ static void *batch_worker(void *arg) {
     return NULL;
 }
 
-int pgo_scan_batch(int kind, const uint32_t *counts_packed, int64_t n_loci, int n_pools,
-                   int n_alleles, const uint8_t *allele_codes, const double *phen, int k,
-                   const pgo_filter_stats *fs, int n_threads, int8_t *status, uint8_t *n_out,
-                   uint8_t *allele_out, double *freq_mean, double *stat, double *var, double *t,
-                   double *pval) {
+static int scan_batch_impl(int kind, int tight, const uint32_t *counts_packed, int64_t n_loci, int n_pools,
+                           int n_alleles, const uint8_t *allele_codes, const double *phen, int k,
+                           const pgo_filter_stats *fs, int n_threads, int8_t *status, uint8_t *n_out,
+                           uint8_t *allele_out, double *freq_mean, double *stat, double *var, double *t,
+                           double *pval) {
     if (n_threads < 1) n_threads = 1;
     if ((int64_t)n_threads > n_loci) n_threads = n_loci > 0 ? (int)n_loci : 1;
     if (n_alleles > PGO_MAX_ALLELES || n_alleles < 1) return -1;
@@ -1237,7 +1439,7 @@ int pgo_scan_batch(int kind, const uint32_t *counts_packed, int64_t n_loci, int 
     for (int i = 0; i < n_threads; i++) {
         batch_job jb = {kind, counts_packed, n_loci * i / n_threads, n_loci * (i + 1) / n_threads,
                         n_pools, n_alleles, k, allele_codes, phen, fs, status, n_out, allele_out,
-                        freq_mean, stat, var, t, pval};
+                        freq_mean, stat, var, t, pval, tight};
         jobs[i] = jb;
         if (n_threads == 1) batch_worker(&jobs[i]);
         else pthread_create(&th[i], NULL, batch_worker, &jobs[i]);
@@ -1247,4 +1449,22 @@ int pgo_scan_batch(int kind, const uint32_t *counts_packed, int64_t n_loci, int 
     free(th);
     free(jobs);
     return 0;
+}
+
+int pgo_scan_batch(int kind, const uint32_t *counts_packed, int64_t n_loci, int n_pools,
+                   int n_alleles, const uint8_t *allele_codes, const double *phen, int k,
+                   const pgo_filter_stats *fs, int n_threads, int8_t *status, uint8_t *n_out,
+                   uint8_t *allele_out, double *freq_mean, double *stat, double *var, double *t,
+                   double *pval) {
+    return scan_batch_impl(kind, 0, counts_packed, n_loci, n_pools, n_alleles, allele_codes, phen, k, fs,
+                           n_threads, status, n_out, allele_out, freq_mean, stat, var, t, pval);
+}
+
+int pgo_scan_batch_tight(int kind, const uint32_t *counts_packed, int64_t n_loci, int n_pools,
+                         int n_alleles, const uint8_t *allele_codes, const double *phen, int k,
+                         const pgo_filter_stats *fs, int n_threads, int8_t *status, uint8_t *n_out,
+                         uint8_t *allele_out, double *freq_mean, double *stat, double *var, double *t,
+                         double *pval) {
+    return scan_batch_impl(kind, 1, counts_packed, n_loci, n_pools, n_alleles, allele_codes, phen, k, fs,
+                           n_threads, status, n_out, allele_out, freq_mean, stat, var, t, pval);
 }

@@ -149,6 +149,15 @@ int pgo_scan_batch(int kind, const uint32_t *counts_packed, int64_t n_loci, int 
                    uint8_t *allele_out, double *freq_mean, double *stat, double *var, double *t,
                    double *pval);
 
+/* the same records, bit for bit, for PGO_SCAN_OLS without the reference's avoidable work: the pool-size total summed
+ * once, one inversion of X'X per locus instead of one per phenotype, no per-locus heap allocation ("tight" CPU
+ * baseline of BASELINE.md 2; other kinds run the faithful functions) */
+int pgo_scan_batch_tight(int kind, const uint32_t *counts_packed, int64_t n_loci, int n_pools,
+                         int n_alleles, const uint8_t *allele_codes, const double *phen, int k,
+                         const pgo_filter_stats *fs, int n_threads, int8_t *status, uint8_t *n_out,
+                         uint8_t *allele_out, double *freq_mean, double *stat, double *var, double *t,
+                         double *pval);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,9 +8,9 @@ nothing here computes on the CPU.
 """
 from . import capi  # noqa: F401
 from .capi import (ALLELE_NAMES, KIND_CHISQ, KIND_CORR, KIND_FISHER, KIND_OLS, LOCUS_FAILED, LOCUS_FILTERED,
-                   LOCUS_OK, LOCUS_PANIC, LOCUS_UNSUPPORTED, Batch, Context, FilterStats, Kinship, PgError, Scan,
+                   LOCUS_OK, LOCUS_PANIC, LOCUS_UNSUPPORTED, Batch, Comm, Context, FilterStats, Kinship, PgError, Scan,
                    ScanResults, format_f64, format_frequency_header, format_frequency_rows, format_header, format_kinship_rows,
-                   format_rows, sort_loci, synth_counts_host, synth_phen_host, synth_sync_text_host)
+                   format_rows, nccl_version, shard_range, sort_loci, synth_counts_host, synth_phen_host, synth_sync_text_host)
 
 from .sync_io import FilePhen, FileSync, FileSyncPhen, Phen, find_file_splits  # noqa: E402
 
@@ -18,7 +18,7 @@ __all__ = ["FilePhen", "FileSync", "FileSyncPhen", "Phen", "find_file_splits", "
            "LOCUS_OK", "LOCUS_PANIC", "LOCUS_UNSUPPORTED", "Batch", "Context", "FilterStats", "Kinship", "PgError", "Scan",
            "ScanResults", "synth_counts_host", "synth_phen_host", "synth_sync_text_host", "ols_iterate", "correlation", "chisq", "fisher",
            "ols_with_covariate", "format_f64", "format_header", "format_kinship_rows", "format_rows", "format_frequency_header",
-           "format_frequency_rows", "sort_loci"]
+           "format_frequency_rows", "sort_loci", "Comm", "shard_range", "nccl_version"]
 
 _SYNC_CODES = (0, 1, 2, 3, 4, 5)
 

@@ -7,14 +7,16 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libpoolgen_cuda.so")
+SYNTH_LIB_PATH = os.path.join(_HERE, "lib", "libpoolgen_synth.so")  # host replay of the synthetic workload (no CUDA)
 
 
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(SYNTH_LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     srcs.append(os.path.join(_HERE, "..", "include", "poolgen_cuda.h"))
+    srcs.append(os.path.join(_HERE, "..", "include", "poolgen_synth.h"))
     return any(os.path.getmtime(s) > t for s in srcs if os.path.isfile(s))
 
 

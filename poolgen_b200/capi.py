@@ -14,7 +14,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .build import LIB_PATH
+from .build import LIB_PATH, SYNTH_LIB_PATH
 
 PG_OK = 0
 KIND_OLS, KIND_CORR, KIND_CHISQ, KIND_FISHER = 0, 1, 2, 3
@@ -32,13 +32,18 @@ ABI_SYMBOLS = [
     "pg_scan_submit_sync_text", "pg_batch_synth",
     "pg_batch_run", "pg_batch_download", "pg_batch_sync", "pg_batch_results", "pg_batch_time_runs",
     "pg_batch_bytes", "pg_scan_stream_begin", "pg_scan_submit_counts", "pg_scan_submit_counts_u16",
-    "pg_scan_submit_counts_u8", "pg_scan_submit_freq", "pg_scan_collect", "pg_scan_text_labels", "pg_synth_counts_host", "pg_synth_phen_host", "pg_synth_sync_text_host",
+    "pg_scan_submit_counts_u8", "pg_scan_submit_freq", "pg_scan_collect", "pg_scan_text_labels",
     "pg_kin_open", "pg_kin_close", "pg_kin_reset", "pg_kin_columns", "pg_kin_append_columns", "pg_kin_append_counts",
     "pg_kin_last_labels", "pg_kin_append_sync_text", "pg_kin_text_labels", "pg_kin_synth", "pg_kin_get_columns", "pg_kin_gram", "pg_kin_gram_time", "pg_kin_partial",
     "pg_kin_partial_get", "pg_kin_partial_set", "pg_kin_eig_select", "pg_kin_eigvals", "pg_kin_set_covariates",
     "pg_kin_covar_scan", "pg_format_header", "pg_format_rows", "pg_format_kinship_rows", "pg_format_f64", "pg_sort_loci",
     "pg_format_frequency_header", "pg_format_frequency_rows",
+    "pg_shard_range", "pg_nccl_version", "pg_init_multi", "pg_comm_unique_id", "pg_comm_init_rank", "pg_comm_info",
+    "pg_comm_destroy", "pg_kin_allreduce", "pg_kin_copy_covariates",
 ]
+# include/poolgen_synth.h (libpoolgen_synth.so: host replay of the synthetic workload, no CUDA)
+SYNTH_SYMBOLS = ["pg_synth_counts_host", "pg_synth_phen_host", "pg_synth_sync_text_host"]
+COMM_ID_BYTES = 128
 
 
 class PgError(RuntimeError):
@@ -123,9 +128,6 @@ def lib():
             "pg_scan_submit_freq": (i, [vp, vp, vp, i64, C.POINTER(i)]),
             "pg_scan_collect": (i, [vp, i, C.POINTER(_Results)]),
             "pg_scan_text_labels": (i, [vp, i, pvp, pvp]),
-            "pg_synth_counts_host": (i, [u64, i64, i64, i, i, vp]),
-            "pg_synth_phen_host": (i, [u64, i, i, vp]),
-            "pg_synth_sync_text_host": (i, [u64, i64, i64, i, i, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
             "pg_kin_open": (i, [vp, i, i64, pvp]),
             "pg_kin_close": (i, [vp]),
             "pg_kin_reset": (i, [vp]),
@@ -146,6 +148,15 @@ def lib():
             "pg_kin_eigvals": (i, [vp, vp, i]),
             "pg_kin_set_covariates": (i, [vp, vp, i]),
             "pg_kin_covar_scan": (i, [vp, vp, i, i, C.POINTER(C.c_float), pvp, pvp, pvp]),
+            "pg_shard_range": (i, [i64, i, i, C.POINTER(i64), C.POINTER(i64)]),
+            "pg_nccl_version": (i, [C.POINTER(i)]),
+            "pg_init_multi": (i, [C.POINTER(i), i, pvp, pvp]),
+            "pg_comm_unique_id": (i, [vp]),
+            "pg_comm_init_rank": (i, [vp, vp, i, i, pvp]),
+            "pg_comm_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+            "pg_comm_destroy": (i, [vp]),
+            "pg_kin_allreduce": (i, [vp, pvp, i, C.POINTER(i64), C.POINTER(C.c_float)]),
+            "pg_kin_copy_covariates": (i, [vp, vp]),
             "pg_format_header": (i, [i, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
             "pg_format_rows": (i, [i, C.POINTER(_Results), C.POINTER(_RowLabels), i, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
             "pg_format_kinship_rows": (i, [i64, i, C.POINTER(C.c_char_p), vp, C.POINTER(C.c_char_p), vp, vp, i, vp,
@@ -162,6 +173,25 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+_synth = None
+
+
+def synth_lib():
+    """libpoolgen_synth.so: the host replay of the synthetic workload (plain C++, no CUDA)."""
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise PgError(f"{SYNTH_LIB_PATH} is missing: run `python -m poolgen_b200.build`")
+        L = C.CDLL(SYNTH_LIB_PATH)
+        i, i64, u64, vp = C.c_int, C.c_int64, C.c_uint64, C.c_void_p
+        L.pg_synth_counts_host.restype, L.pg_synth_counts_host.argtypes = i, [u64, i64, i64, i, i, vp]
+        L.pg_synth_phen_host.restype, L.pg_synth_phen_host.argtypes = i, [u64, i, i, vp]
+        L.pg_synth_sync_text_host.restype = i
+        L.pg_synth_sync_text_host.argtypes = [u64, i64, i64, i, i, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        _synth = L
+    return _synth
 
 
 @dataclass
@@ -357,7 +387,11 @@ def _check(rc: int, ctx=None, what: str = ""):
 class Context:
     """One context per GPU (pg_init)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _handle=None):
+        if _handle is not None:  # a context pg_init_multi created
+            self._h = _handle
+            self.device = device
+            return
         self._h = C.c_void_p()
         rc = lib().pg_init(int(device), C.byref(self._h))
         if rc != PG_OK:
@@ -633,6 +667,10 @@ class Kinship:
         assert k.shape == (self.n, self.n)
         self._ck(lib().pg_kin_partial_set(self._h, k.ctypes.data), "pg_kin_partial_set")
 
+    def copy_covariates_from(self, src: "Kinship"):
+        """the outcome of another handle's eigen step (one process, several GPUs: the step is replicated work)"""
+        self._ck(lib().pg_kin_copy_covariates(self._h, src._h), "pg_kin_copy_covariates")
+
     def eig_select(self, P_total: int, variance_explained: float) -> int:
         m = C.c_int()
         self._ck(lib().pg_kin_eig_select(self._h, int(P_total), float(variance_explained), C.byref(m)), "pg_kin_eig_select")
@@ -672,6 +710,68 @@ class Kinship:
             self._h = C.c_void_p()
 
 
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """pg_shard_range: the contiguous [begin, end) of `rank` (earlier ranks take the larger shards)"""
+    b, e = C.c_int64(), C.c_int64()
+    _check(lib().pg_shard_range(int(total), int(rank), int(world), C.byref(b), C.byref(e)), None, "pg_shard_range")
+    return int(b.value), int(e.value)
+
+
+def nccl_version() -> int:
+    v = C.c_int()
+    _check(lib().pg_nccl_version(C.byref(v)), None, "pg_nccl_version")
+    return int(v.value)
+
+
+class Comm:
+    """The library's NCCL communicator (pg_comm): `Comm.init_multi(devices)` for one process driving several GPUs
+    (what the Rust CLI does, src/main.rs:280-298), `Comm.init_rank(ctx, id, rank, world)` for one process per GPU."""
+
+    def __init__(self, handle, contexts):
+        self._h = handle
+        self.contexts = contexts
+
+    @staticmethod
+    def init_multi(devices) -> "Comm":
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        ctxs = (C.c_void_p * len(devices))()
+        h = C.c_void_p()
+        _check(lib().pg_init_multi(devs, len(devices), ctxs, C.byref(h)), None, "pg_init_multi")
+        return Comm(h, [Context(int(d), _handle=C.c_void_p(c)) for d, c in zip(devices, ctxs)])
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        _check(lib().pg_comm_unique_id(buf), None, "pg_comm_unique_id")
+        return buf.raw
+
+    @staticmethod
+    def init_rank(ctx: Context, uid: bytes, rank: int, world: int) -> "Comm":
+        assert len(uid) == COMM_ID_BYTES
+        h = C.c_void_p()
+        _check(lib().pg_comm_init_rank(ctx._h, uid, int(rank), int(world), C.byref(h)), ctx._h, "pg_comm_init_rank")
+        return Comm(h, [ctx])
+
+    def info(self):
+        w, n, f = C.c_int(), C.c_int(), C.c_int()
+        _check(lib().pg_comm_info(self._h, C.byref(w), C.byref(n), C.byref(f)), None, "pg_comm_info")
+        return {"world": w.value, "n_local": n.value, "first_rank": f.value}
+
+    def kin_allreduce(self, kins, timed: bool = False):
+        """sum the partial Gram matrices (and the column counts) of `kins` (one per local rank) over the communicator;
+        returns the total column count (and the device milliseconds of the exchange step when timed)"""
+        arr = (C.c_void_p * len(kins))(*[k._h for k in kins])
+        tot, ms = C.c_int64(), C.c_float()
+        _check(lib().pg_kin_allreduce(self._h, arr, len(kins), C.byref(tot), C.byref(ms) if timed else None),
+               kins[0].ctx._h, "pg_kin_allreduce")
+        return (int(tot.value), float(ms.value)) if timed else int(tot.value)
+
+    def close(self):
+        if self._h:
+            lib().pg_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 def submit_sync_text(scan: "Scan", text: bytes, deferred: bool = False):
     """pg_scan_submit_sync_text: parse + scan + download of one text slab; returns (ticket, n_loci).
     deferred=True passes n_loci = NULL: the call only enqueues the copy and the parse (n_loci comes back as None, the
@@ -699,7 +799,7 @@ def text_labels(scan: "Scan", ticket: int, n_loci: int):
 
 def synth_counts_host(seed: int, first_locus: int, n_loci: int, n_pools: int, n_alleles: int) -> np.ndarray:
     out = np.empty((n_loci, n_alleles, n_pools), dtype=np.uint32)
-    rc = lib().pg_synth_counts_host(int(seed), int(first_locus), int(n_loci), int(n_pools), int(n_alleles), out.ctypes.data)
+    rc = synth_lib().pg_synth_counts_host(int(seed), int(first_locus), int(n_loci), int(n_pools), int(n_alleles), out.ctypes.data)
     if rc != PG_OK:
         raise PgError(f"pg_synth_counts_host failed ({rc})")
     return out
@@ -708,7 +808,7 @@ def synth_counts_host(seed: int, first_locus: int, n_loci: int, n_pools: int, n_
 def synth_sync_text_host(seed: int, first_locus: int, n_loci: int, n_pools: int, n_alleles: int, out: np.ndarray) -> int:
     """writes the synthetic counts as sync text into `out` (uint8 array, e.g. over pinned memory); returns the bytes"""
     nb = C.c_size_t()
-    rc = lib().pg_synth_sync_text_host(int(seed), int(first_locus), int(n_loci), int(n_pools), int(n_alleles),
+    rc = synth_lib().pg_synth_sync_text_host(int(seed), int(first_locus), int(n_loci), int(n_pools), int(n_alleles),
                                        out.ctypes.data, int(out.size), C.byref(nb))
     if rc != PG_OK:
         raise PgError(f"pg_synth_sync_text_host failed ({rc}): needs {nb.value} bytes, has {out.size}")
@@ -717,7 +817,7 @@ def synth_sync_text_host(seed: int, first_locus: int, n_loci: int, n_pools: int,
 
 def synth_phen_host(seed: int, n_pools: int, k: int) -> np.ndarray:
     out = np.empty((n_pools, k), dtype=np.float64)
-    rc = lib().pg_synth_phen_host(int(seed), int(n_pools), int(k), out.ctypes.data)
+    rc = synth_lib().pg_synth_phen_host(int(seed), int(n_pools), int(k), out.ctypes.data)
     if rc != PG_OK:
         raise PgError(f"pg_synth_phen_host failed ({rc})")
     return out

@@ -30,7 +30,11 @@ cudaError_t launch_scan(const ScanParams &p, int sm_count, cudaStream_t s) {
 }
 }  // namespace pg
 
-static thread_local std::string g_init_err;
+// The last error message is per THREAD: reader threads share one pg_ctx (src/base/sync.rs:917-939 runs one reader per
+// file chunk), and the thread that made the failing call is the one that asks for the message.
+static thread_local std::string g_last_err;
+
+void pg::set_error(pg_ctx *, const char *msg) { g_last_err = msg; }
 
 static int fail(pg_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
@@ -38,10 +42,7 @@ static int fail(pg_ctx *ctx, int code, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (ctx)
-        ctx->err = buf;
-    else
-        g_init_err = buf;
+    pg::set_error(ctx, buf);
     return code;
 }
 
@@ -85,7 +86,7 @@ int pg_init(int device, pg_ctx **out) {
 
 void pg_destroy(pg_ctx *ctx) { delete ctx; }
 
-const char *pg_last_error(const pg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
+const char *pg_last_error(const pg_ctx *) { return g_last_err.c_str(); }
 
 int pg_device_info(pg_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
     if (!ctx) return PG_ERR_ARG;
@@ -251,6 +252,15 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
             if (s->d_yc) cudaFree(s->d_yc);
             delete s;
             return fail(ctx, PG_ERR_CUDA, "pg_scan_open: weight upload: %s", cudaGetErrorString(e));
+        }
+    }
+    // pageable-memory copies may return before the DMA has landed and the batches' streams are non-blocking (not
+    // ordered against the legacy stream): the phenotype, weight and p-table uploads are complete when this returns
+    {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            pg_scan_close(s);
+            return fail(ctx, PG_ERR_CUDA, "pg_scan_open: %s", cudaGetErrorString(e));
         }
     }
     *out = s;
@@ -446,8 +456,13 @@ static int text_stage_a(pg_batch *b, const char *text, size_t n_bytes, size_t li
     b->text_bytes = n_bytes;
     int rc = ensure_stage(b, (size_t)b->cap * 6 * s->n * 4);
     if (rc) return rc;
-    PG_CUDA(ctx, pg::text_parse_async(&b->text, text, n_bytes, s->n, (uint32_t *)b->d_stage, b->cap, line_cap,
-                                      ctx->sm_count, b->stream));
+    const cudaError_t pe = pg::text_parse_async(&b->text, text, n_bytes, s->n, (uint32_t *)b->d_stage, b->cap, line_cap,
+                                                ctx->sm_count, b->stream);
+    if (pe != cudaSuccess) {
+        b->have_input = 0;  // nothing usable is resident: a later run / collect must not scan the previous chunk
+        b->n_loci = 0;
+        return fail(ctx, PG_ERR_CUDA, "upload_sync_text: %s", cudaGetErrorString(pe));
+    }
     return PG_OK;
 }
 
@@ -804,55 +819,6 @@ int pg_scan_collect(pg_scan *s, int ticket, pg_results *out) {
     rc = pg_batch_sync(s->slabs[ticket]);
     if (rc) return rc;
     return pg_batch_results(s->slabs[ticket], out);
-}
-
-// ---- synthetic workload, host replay -----------------------------------------------------------
-int pg_synth_counts_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int n_pools, int n_alleles,
-                         uint32_t *out) {
-    if (!out || n_pools < 1 || n_alleles < 1 || n_alleles > PG_MAX_ALLELES || n_loci < 0) return PG_ERR_ARG;
-    for (int64_t l = 0; l < n_loci; l++)
-        for (int i = 0; i < n_pools; i++) {
-            uint32_t c[PG_MAX_ALLELES];
-            pg::synth_counts(seed, first_locus + l, i, n_alleles, c);
-            for (int a = 0; a < n_alleles; a++) out[((size_t)l * n_alleles + a) * n_pools + i] = c[a];
-        }
-    return PG_OK;
-}
-
-int pg_synth_sync_text_host(uint64_t seed, int64_t first_locus, int64_t n_loci, int n_pools, int n_alleles, char *out,
-                            size_t capacity, size_t *n_bytes) {
-    if (!n_bytes || n_pools < 1 || n_alleles < 1 || n_alleles > PG_MAX_ALLELES || n_loci < 0) return PG_ERR_ARG;
-    size_t w = 0;
-    char tmp[64];
-    auto put = [&](const char *p, size_t len) {
-        if (out && w + len <= capacity) memcpy(out + w, p, len);
-        w += len;
-    };
-    for (int64_t l = 0; l < n_loci; l++) {
-        const int64_t locus = first_locus + l;
-        int len = snprintf(tmp, sizeof tmp, "chr%lld\t%lld\tN", (long long)(1 + locus / 1000000), (long long)(locus + 1));
-        put(tmp, (size_t)len);
-        for (int i = 0; i < n_pools; i++) {
-            uint32_t c[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
-            pg::synth_counts(seed, locus, i, n_alleles, c);
-            len = snprintf(tmp, sizeof tmp, "\t%u:%u:%u:%u:%u:%u", c[0], c[1], c[2], c[3], c[4], c[5]);
-            put(tmp, (size_t)len);
-        }
-        put("\n", 1);
-    }
-    *n_bytes = w;
-    return (out && w <= capacity) ? PG_OK : PG_ERR_ARG;
-}
-
-int pg_synth_phen_host(uint64_t seed, int n_pools, int k, double *out) {
-    if (!out || n_pools < 1 || k < 1) return PG_ERR_ARG;
-    for (int i = 0; i < n_pools; i++)
-        for (int j = 0; j < k; j++) {
-            const uint64_t h = pg::splitmix64(seed ^ 0x9E11E5ull ^ ((uint64_t)(i + 1) << 24) ^ (uint64_t)j);
-            // 53 uniform bits -> [-3, 3)
-            out[(size_t)i * k + j] = ((double)(h >> 11) * (1.0 / 9007199254740992.0)) * 6.0 - 3.0;
-        }
-    return PG_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,46 @@
+// pg_kin.h -- the handle of the ols_iter_with_kinship path (shared by pg_kinship.cu and pg_comm.cu; not part of the ABI)
+#pragma once
+#include <vector>
+
+#include "pg_internal.h"
+
+struct pg_kin {
+    pg_ctx *ctx = nullptr;
+    int n = 0, ldg = 0;
+    int64_t cap = 0, P = 0;
+    int64_t P_total = 0;      // columns over all shards (pg_kin_allreduce); 0 = this handle holds them all
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double *d_G = nullptr;
+    double *d_K = nullptr;    // [n][n] partial Gram matrix (sum over the resident columns)
+    double *d_ws = nullptr;   // split-K workspace
+    size_t ws_bytes = 0;
+    int nt = 0, n_slices = 0;
+    // covariates
+    int m = -1;
+    std::vector<double> eigvals;  // descending
+    std::vector<double> Q;        // [1+m][ldg] orthonormal basis of [1 | PCs] (host)
+    double *d_V = nullptr;        // [(1+m) + k][ldg]
+    size_t V_bytes = 0;
+    double *d_ptab = nullptr;
+    double ptab_vmax = 0, ptab_inv_h = 0;
+    int ptab_M = 0;
+    // results
+    int k = 0;
+    double *d_res = nullptr;  // [3][k][P]
+    double *h_res = nullptr;  // pinned
+    size_t res_elems = 0;
+    // loader scratch
+    uint32_t *d_sel = nullptr;
+    int64_t *d_off = nullptr;
+    int64_t *d_col_locus = nullptr;
+    uint8_t *d_col_allele = nullptr;
+    void *d_scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+    int64_t load_cap = 0;
+    void *d_counts = nullptr;
+    size_t counts_bytes = 0;
+    double *d_w = nullptr;
+    pg::TextScratch *text = nullptr;  // sync text parsed on the device (pg_kin_append_sync_text)
+};
+

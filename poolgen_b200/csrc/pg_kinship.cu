@@ -26,6 +26,7 @@
 #include "pg_device.cuh"
 #include "pg_internal.h"
 #include "pg_ptable.h"
+#include "pg_kin.h"
 
 namespace pg {
 
@@ -40,7 +41,8 @@ struct LoadParams {
     double maf, one_minus_maf, max_miss, min_depth_f;
     const double *w;  // [n] s_i / sum(s)
     uint8_t codes[8];
-    uint32_t *sel;      // [locus] number of columns | 4-bit input column index per emitted column << (4 + 4 s)
+    uint32_t *sel;      // [locus] number of columns (bits 0-3) | 3-bit input column index of emitted column s << (4 + 3 s),
+                        // s < 6 (bits 4-21) | kept set << 24 (bits 24-29)
     int64_t *offsets;   // [locus] exclusive scan of the column counts
     double *G;          // [column][ldg]
     int64_t col_base;
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(256) load_decide_kernel(const LoadParams p) {
                 for (int a = 0; a < no; a++) order[a] = sorted[a + 1];
             }
             sel = (uint32_t)no;
-            for (int a = 0; a < no; a++) sel |= (uint32_t)order[a] << (4 + 4 * a);
+            for (int a = 0; a < no; a++) sel |= (uint32_t)order[a] << (4 + 3 * a);
             sel |= kept << 24;
         }
         if (lane == 0) {
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(256) load_emit_kernel(const LoadParams p) {
         const uint32_t sel = p.sel[locus];
         const int no = (int)(sel & 0xf);
         if (no == 0) continue;
-        const unsigned kept = sel >> 24;
+        const unsigned kept = (sel >> 24) & 0x3fu;
         const int64_t c0 = p.col_base + p.offsets[locus];
         const uint32_t *cl = p.counts + (size_t)locus * p.A_in * p.n;
         int col_of[PG_MAX_ALLELES];
@@ -182,14 +184,14 @@ __global__ void __launch_bounds__(256) load_emit_kernel(const LoadParams p) {
                 for (int l = 0; l < A; l++)
                     if ((kept >> l) & 1u) dk += cl[(size_t)col_of[l] * p.n + i];
             for (int a = 0; a < no; a++) {
-                const int j = (int)((sel >> (4 + 4 * a)) & 0xf);
+                const int j = (int)((sel >> (4 + 3 * a)) & 0x7);
                 double v = 0.0;
                 if (i < p.n) v = dk ? (double)cl[(size_t)col_of[j] * p.n + i] / (double)dk : nan("");
                 p.G[(size_t)(c0 + a) * p.ldg + i] = v;
             }
         }
         if (lane < no) {
-            const int j = (int)((sel >> (4 + 4 * lane)) & 0xf);
+            const int j = (int)((sel >> (4 + 3 * lane)) & 0x7);
             p.col_locus[c0 + lane - p.col_base] = locus;
             p.col_allele[c0 + lane - p.col_base] = p.codes[col_of[j]];
         }
@@ -575,52 +577,13 @@ __global__ void __launch_bounds__(256) covar_generic_kernel(const CovarParams p)
 // ================================================================================================================
 // C ABI
 // ================================================================================================================
-struct pg_kin {
-    pg_ctx *ctx = nullptr;
-    int n = 0, ldg = 0;
-    int64_t cap = 0, P = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double *d_G = nullptr;
-    double *d_K = nullptr;    // [n][n] partial Gram matrix (sum over the resident columns)
-    double *d_ws = nullptr;   // split-K workspace
-    size_t ws_bytes = 0;
-    int nt = 0, n_slices = 0;
-    // covariates
-    int m = -1;
-    std::vector<double> eigvals;  // descending
-    std::vector<double> Q;        // [1+m][ldg] orthonormal basis of [1 | PCs] (host)
-    double *d_V = nullptr;        // [(1+m) + k][ldg]
-    size_t V_bytes = 0;
-    double *d_ptab = nullptr;
-    double ptab_vmax = 0, ptab_inv_h = 0;
-    int ptab_M = 0;
-    // results
-    int k = 0;
-    double *d_res = nullptr;  // [3][k][P]
-    double *h_res = nullptr;  // pinned
-    size_t res_elems = 0;
-    // loader scratch
-    uint32_t *d_sel = nullptr;
-    int64_t *d_off = nullptr;
-    int64_t *d_col_locus = nullptr;
-    uint8_t *d_col_allele = nullptr;
-    void *d_scan_tmp = nullptr;
-    size_t scan_tmp_bytes = 0;
-    int64_t load_cap = 0;
-    void *d_counts = nullptr;
-    size_t counts_bytes = 0;
-    double *d_w = nullptr;
-    pg::TextScratch *text = nullptr;  // sync text parsed on the device (pg_kin_append_sync_text)
-};
-
 static int kfail(pg_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (ctx) ctx->err = buf;
+    pg::set_error(ctx, buf);
     return code;
 }
 #define KCUDA(ctx, call)                                                                                  \
@@ -693,6 +656,7 @@ int pg_kin_reset(pg_kin *h) {
     KCUDA(h->ctx, cudaSetDevice(h->ctx->device));
     KCUDA(h->ctx, cudaMemsetAsync(h->d_G, 0, ((size_t)h->cap * h->ldg + pg::kTile) * 8, h->stream));
     h->P = 0;
+    h->P_total = 0;
     return PG_OK;
 }
 
@@ -724,8 +688,8 @@ static int kin_reserve(pg_kin *h, int64_t n_loci, int n_alleles) {
         h->d_sel = nullptr, h->d_off = nullptr, h->d_col_locus = nullptr, h->d_col_allele = nullptr, h->d_scan_tmp = nullptr;
         KCUDA(ctx, cudaMalloc(&h->d_sel, (size_t)n_loci * 4));
         KCUDA(ctx, cudaMalloc(&h->d_off, (size_t)(n_loci + 1) * 8));
-        KCUDA(ctx, cudaMalloc(&h->d_col_locus, (size_t)n_loci * PG_MAX_SLOTS * 8));
-        KCUDA(ctx, cudaMalloc(&h->d_col_allele, (size_t)n_loci * PG_MAX_SLOTS));
+        KCUDA(ctx, cudaMalloc(&h->d_col_locus, (size_t)n_loci * PG_MAX_ALLELES * 8));
+        KCUDA(ctx, cudaMalloc(&h->d_col_allele, (size_t)n_loci * PG_MAX_ALLELES));
         size_t tmp = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp, h->d_off, h->d_off, (int)(n_loci + 1), h->stream);
         KCUDA(ctx, cudaMalloc(&h->d_scan_tmp, tmp));
@@ -1011,7 +975,9 @@ const CusolverApi &cusolver_api() {
 }  // namespace
 
 int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) {
-    if (!h || P_total < 1) return PG_ERR_ARG;
+    if (!h || P_total < 0) return PG_ERR_ARG;
+    if (P_total == 0) P_total = h->P_total > 0 ? h->P_total : h->P;  // the count pg_kin_allreduce summed, else the resident columns
+    if (P_total < 1) return kfail(h->ctx, PG_ERR_STATE, "pg_kin_eig_select: no columns");
     pg_ctx *ctx = h->ctx;
     const int n = h->n;
     KCUDA(ctx, cudaSetDevice(ctx->device));
@@ -1085,6 +1051,19 @@ int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) 
         if (!(nn > 1e-12)) return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_eig_select: covariate %d is collinear with the intercept", c);
         for (int i = 0; i < n; i++) qc[i] /= nn;
     }
+    return PG_OK;
+}
+
+// one process driving several GPUs: the eigen step runs once (it is replicated work) and the other handles take its
+// outcome -- number of PCs, the orthonormal basis of [1 | PCs], the eigenvalues
+int pg_kin_copy_covariates(pg_kin *dst, const pg_kin *src) {
+    if (!dst || !src) return PG_ERR_ARG;
+    if (src->m < 0) return kfail(dst->ctx, PG_ERR_STATE, "pg_kin_copy_covariates: the source has no covariates yet");
+    if (dst->n != src->n) return kfail(dst->ctx, PG_ERR_ARG, "pg_kin_copy_covariates: %d vs %d pools", dst->n, src->n);
+    dst->m = src->m;
+    dst->Q = src->Q;
+    dst->eigvals = src->eigvals;
+    dst->P_total = src->P_total;
     return PG_OK;
 }
 
@@ -1217,7 +1196,8 @@ int pg_kin_covar_scan(pg_kin *h, const double *phen, int k, int iters, float *ms
         pg::PTable tab = pg::build_ptable(df);
         if (tab.max_err < 2e-9) {
             KCUDA(ctx, cudaMalloc(&h->d_ptab, tab.coef.size() * 8));
-            KCUDA(ctx, cudaMemcpy(h->d_ptab, tab.coef.data(), tab.coef.size() * 8, cudaMemcpyHostToDevice));
+            KCUDA(ctx, cudaMemcpyAsync(h->d_ptab, tab.coef.data(), tab.coef.size() * 8, cudaMemcpyHostToDevice, h->stream));
+            KCUDA(ctx, cudaStreamSynchronize(h->stream));
             h->ptab_M = tab.M;
             h->ptab_vmax = tab.v_max;
             h->ptab_inv_h = tab.inv_h;

@@ -655,7 +655,8 @@ cudaError_t launch_tables(const TableParams &p, int sm_count, cudaStream_t s) {
             for (int i = 2; i < x + 1; i++) out = out + log10((double)i);
             lf[x] = out;
         }
-        cudaError_t e = cudaMemcpyToSymbol(c_lf10, lf, sizeof lf);
+        // on the launch stream (pageable source: staged before the call returns), so the kernel below is ordered after it
+        cudaError_t e = cudaMemcpyToSymbolAsync(c_lf10, lf, sizeof lf, 0, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) return e;
         lf_ready[dev & 63] = true;
     }

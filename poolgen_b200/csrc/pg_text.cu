@@ -312,12 +312,9 @@ void text_scratch_free(TextScratch *t) {
 // end) into counts[locus][6][n_pools] (device, capacity max_loci) on stream s and records the `parsed` event.  The
 // per-line arrays hold line_cap lines (0 = a default bound from max_loci); text_parse_finish reports when a chunk has
 // more (comment / blank lines) so that the caller can repeat with the exact bound.
-cudaError_t text_parse_async(TextScratch **scratch, const char *text, size_t n_bytes, int n_pools, uint32_t *d_counts,
-                             int64_t max_loci, size_t line_cap, int sm_count, cudaStream_t s) {
-    if (!*scratch) *scratch = new TextScratch();
-    TextScratch *t = *scratch;
+static cudaError_t text_parse_enqueue(TextScratch *t, const char *text, size_t n_bytes, int n_pools, uint32_t *d_counts,
+                                      int64_t max_loci, size_t line_cap, int sm_count, cudaStream_t s) {
     t->max_loci = max_loci;
-    t->pending = true;
     if (!t->parsed) TCK(cudaEventCreateWithFlags(&t->parsed, cudaEventDisableTiming));
     if (!t->d_info) {
         TCK(cudaMalloc(&t->d_info, 16));
@@ -422,6 +419,18 @@ cudaError_t text_parse_async(TextScratch **scratch, const char *text, size_t n_b
     return cudaEventRecord(t->parsed, s);
 }
 #undef TCK
+
+// a slab is 'pending' only once everything up to the `parsed` event has been enqueued: a failed allocation or launch
+// must not leave text_parse_finish waiting on a stale event and trusting the previous chunk's h_info
+cudaError_t text_parse_async(TextScratch **scratch, const char *text, size_t n_bytes, int n_pools, uint32_t *d_counts,
+                             int64_t max_loci, size_t line_cap, int sm_count, cudaStream_t s) {
+    if (!*scratch) *scratch = new TextScratch();
+    TextScratch *t = *scratch;
+    t->pending = false;
+    const cudaError_t e = text_parse_enqueue(t, text, n_bytes, n_pools, d_counts, max_loci, line_cap, sm_count, s);
+    t->pending = (e == cudaSuccess);
+    return e;
+}
 
 // Waits for the parse and returns the number of loci, or a negative code: -1 CUDA error (*cuda_err), -2 more loci than
 // capacity, -3 pool count mismatch, -4 malformed pool field (*err_offset = byte offset in the chunk), -5 more lines

@@ -35,6 +35,34 @@ def test_library_exports_every_declared_symbol():
     assert capi.lib().pg_abi_version() == 1
 
 
+def test_synth_library_is_separate_and_cuda_free():
+    """include/poolgen_synth.h lives in libpoolgen_synth.so: the host replay of the synthetic workload does not map the
+    product library (bench.py's reference arm generates its inputs there)"""
+    import subprocess
+    from poolgen_b200.build import SYNTH_LIB_PATH
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "poolgen_synth.h")).read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", src)))
+    assert declared == sorted(capi.SYNTH_SYMBOLS)
+    L = ctypes.CDLL(SYNTH_LIB_PATH)
+    P = ctypes.CDLL(LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+        assert not hasattr(P, name), name
+    out = subprocess.run(["ldd", SYNTH_LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    assert "cuda" not in out.lower() and "poolgen" not in out, out
+
+
+def test_shard_range_and_comm_id_without_a_gpu():
+    """the host-callable part of the multi-GPU ABI: contiguous ranges and the communicator id (NCCL loads lazily)"""
+    assert [pb.shard_range(10, r, 3) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
+    assert pb.shard_range(0, 0, 1) == (0, 0)
+    with pytest.raises(pb.PgError):
+        pb.shard_range(10, 3, 3)
+    assert pb.nccl_version() >= 22000
+    a, b = pb.Comm.unique_id(), pb.Comm.unique_id()
+    assert len(a) == len(b) == capi.COMM_ID_BYTES and a != b
+
+
 def test_no_cpu_fallback_without_a_gpu():
     import torch
     if torch.cuda.is_available():
@@ -91,5 +119,5 @@ def test_library_does_not_link_the_cuda_math_libraries():
     map cuSOLVER / cuSPARSE / cuBLAS (1.5 GB, minutes on a cold file system)"""
     import subprocess
     out = subprocess.run(["ldd", LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
-    for name in ("cusolver", "cublas", "cusparse", "nvJitLink"):
+    for name in ("cusolver", "cublas", "cusparse", "nvJitLink", "nccl"):
         assert name not in out, out

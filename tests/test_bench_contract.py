@@ -20,3 +20,18 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    # the reference arm never maps the product library (its inputs come from libpoolgen_synth.so) and reports the
+    # "tight" CPU variant next to the faithful one
+    assert d["maps_product_library"] is False
+    assert d["cpu_baseline"]["tight"]["value"] > d["value"]
+
+
+def test_traffic_is_read_from_the_committed_capture():
+    """roofline.traffic comes from profiles/ncu_raw_r*.csv at run time (dram__bytes_read + dram__bytes_write of the
+    streaming kernel and the fix-up kernel), not from a constant"""
+    sys.path.insert(0, ROOT)
+    import bench
+    per_locus, src = bench.traffic_from_profile(1000, 4, 3)
+    assert src and src.startswith("profiles/ncu_raw_r")
+    assert 32288 <= per_locus <= 1.2 * 32288          # at least the algorithmic bytes, no wasted re-reads
+    assert bench.traffic_from_profile(7, 7, 7) == (None, None)

@@ -74,6 +74,28 @@ def test_loader_c1_bit_exact(ctx, fkw, keep_p_minus_1):
     assert np.array_equal(G, ocols, equal_nan=True)
 
 
+def test_loader_six_columns_keep_ns(ctx):
+    """--keep-ns with MAF 0 and keep_p_minus_1 off: a locus can emit all SIX columns (the selection word holds six
+    column indices next to the kept set; the label arrays hold six entries per locus)"""
+    rng = np.random.default_rng(66)
+    n, L = 7, 400
+    counts = rng.integers(1, 40, size=(L, 6, n)).astype(np.uint32)
+    counts[::5, 4] = 0          # some loci without N reads
+    counts[::7, 2:4] = 0        # some with two empty columns
+    codes = np.arange(6, dtype=np.uint8)
+    for keep_p_minus_1 in (False, True):
+        fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n), remove_ns=False, min_allele_frequency=0.0)
+        kin = pb.Kinship(ctx, n, 6 * L)
+        loc, alle = kin.append_counts(counts, codes, fs, keep_p_minus_1)
+        G = kin.get_columns(0, kin.columns)
+        kin.close()
+        ocols, olabels = pgo.load_columns(counts.transpose(0, 2, 1).astype(np.uint64), codes, H.oracle_fs(fs), keep_p_minus_1)
+        assert len(olabels) == G.shape[0] and (np.bincount(loc).max() == (5 if keep_p_minus_1 else 6))
+        assert [l for l, _ in olabels] == list(loc)
+        assert [a for _, a in olabels] == list(alle)
+        assert np.array_equal(G, ocols, equal_nan=True)
+
+
 @pytest.mark.parametrize("n,P", [(40, 333), (130, 1000), (257, 64)])
 def test_gram_matches_numpy(ctx, n, P):
     rng = np.random.default_rng(n * 1000 + P)
@@ -211,3 +233,47 @@ def test_sync2csv_from_sync_text(ctx):
     order2 = pb.sort_loci(pos, chr_names=names, chr_index=c1["chrom_idx"][:L])
     expect = pb.format_frequency_rows(G2, loc2, alle2, pos, locus_order=order2, chr_names=names, chr_index=c1["chrom_idx"][:L])
     assert got == expect and got.count(b"\n") == len(loc) > 1000
+
+
+def test_c4_shape_gram_and_covariate_scan(ctx):
+    """BASELINE config C4's shape (2,000 pools): 16 x 16 tiles of which 136 are computed, many column slices, the
+    mirrored reduction -- the Gram matrix against fp64 numpy, and the covariate scan against the oracle's normal
+    equations on sampled columns, at the default threshold (no PC selected on frequency data) and at a
+    threshold that selects m = 10 PCs (src/gwas/ols.rs:291-370)."""
+    n, L, k = 2000, 26_000, 2
+    kin = pb.Kinship(ctx, n, 2 * L)
+    kin.synth(0x5EED0004, 0, L)
+    P = kin.columns
+    assert P == 2 * L
+    G = kin.get_columns(0, P)
+    kin.gram()
+    K = kin.partial_get()
+    kin.gram()
+    K2 = kin.partial_get()
+    ref = G.T @ G
+    assert np.array_equal(K, K.T)
+    assert np.array_equal(K, K2)                      # fixed summation order
+    assert np.allclose(K, ref, rtol=1e-12, atol=0.0)
+    phen = pb.synth_phen_host(0x5EED0004, n, k)
+    rng = np.random.default_rng(4)
+    sample = np.sort(rng.choice(P, size=600, replace=False))
+    # default threshold
+    m0 = kin.eig_select(P, 0.75)
+    ev = kin.eigvals(n)
+    beta, var, pval = kin.covar_scan(phen)
+    om, ob, ov, op, w, V = pgo.ols_with_covariate(G, phen, 0.75, columns=sample, return_eig=True)
+    assert m0 == om == 0
+    assert np.allclose(ev, w, rtol=1e-9, atol=1e-12 * w[0])
+    _cmp_records((beta[:, sample], var[:, sample], pval[:, sample]), (ob[sample].T, ov[sample].T, op[sample].T),
+                 "C4 shape m=0", arb=(G[sample], V[:, :0], phen))
+    # a threshold between the cumulative shares of 10 and 11 eigenvalues selects m = 10
+    share = np.cumsum(w / w.sum())
+    thr = 0.5 * (share[9] + share[10])
+    m10 = kin.eig_select(P, thr)
+    beta, var, pval = kin.covar_scan(phen)
+    kin.close()
+    om, ob, ov, op = pgo.ols_with_covariate(G, phen, thr, columns=sample)
+    assert m10 == om == 10
+    n_arb = _cmp_records((beta[:, sample], var[:, sample], pval[:, sample]), (ob[sample].T, ov[sample].T, op[sample].T),
+                         "C4 shape m=10", arb=(G[sample], V[:, :10], phen))
+    print(f"C4 shape: P={P}, m=0 and m=10 records match on {sample.size} sampled columns ({n_arb} arbitrated)")

@@ -106,3 +106,32 @@ def test_statrs_tails_against_scipy():
             assert abs(p - 2 * stats.t.sf(t, df)) <= 1e-9 * p + 1e-15
     for a, x in ((3.5, 2.0), (0.5, 0.1), (12.0, 30.0)):
         assert abs(pgo.gamma_lr(a, x) - special.gammainc(a, x)) < 1e-13
+
+
+def test_tight_cpu_baseline_is_bit_identical_to_the_faithful_one():
+    """bench.py reports two CPU baselines: the faithful restatement and the 'tight' one (pool-size total
+    hoisted, one inversion per locus, no per-locus allocation).  Same arithmetic, so the same bits -- on the synthetic
+    workload, on C1 and with weighted pools."""
+    import poolgen_b200 as pb
+    from tests import helpers as H
+    fields = ("status", "n_out", "allele", "freq_mean", "stat", "var", "t", "pval")
+    for n, A, k, L in [(100, 4, 3, 1500), (12, 6, 2, 800), (3, 4, 1, 300)]:
+        c = pb.synth_counts_host(0x7167 + n, 0, L, n, A)
+        y = pb.synth_phen_host(5, n, k)
+        rng = np.random.default_rng(n)
+        sizes = rng.integers(5, 60, size=n).astype(float)
+        for ps in (np.full(n, 1.0 / n), sizes / sizes.sum()):
+            fs = pgo.FilterStats(pool_sizes=ps, min_allele_frequency=0.01)
+            a = pgo.scan_batch(pgo.SCAN_OLS, c, np.arange(A, dtype=np.uint8), y, fs, 2)
+            b = pgo.scan_batch(pgo.SCAN_OLS, c, np.arange(A, dtype=np.uint8), y, fs, 3, tight=True)
+            assert (a.status == pgo.OK).sum() > 0.3 * L
+            for f in fields:
+                assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), (n, A, f)
+    c1 = H.load_c1()
+    fs = pgo.FilterStats(pool_sizes=c1["pool_sizes"], min_coverage_depth=10, min_allele_frequency=0.01)
+    counts = np.ascontiguousarray(c1["counts"], dtype=np.uint32)
+    a = pgo.scan_batch(pgo.SCAN_OLS, counts, c1["codes"], c1["phen"], fs, 2)
+    b = pgo.scan_batch(pgo.SCAN_OLS, counts, c1["codes"], c1["phen"], fs, 2, tight=True)
+    assert (a.status != pgo.FILTERED).sum() == 2032  # pass the filter (SURVEY 8a F2); a few then fail the regression
+    for f in fields:
+        assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f

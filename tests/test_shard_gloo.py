@@ -1,6 +1,7 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: shard ranges, the partial-Gram all-reduce protocol and
-rank-ordered gathering.  The Kinship handle is replaced by a numpy stand-in with the same partial_get/partial_set
-methods -- no CUDA is touched."""
+"""world_size-2 gloo tests (CPU) of the host side of the multi-GPU path: the shard ranges of the C ABI
+(pg_shard_range), the rendezvous of the library's NCCL communicator id (rank 0 -> every rank) and rank-ordered
+gathering.  No CUDA is touched: the exchange step itself (pg_kin_allreduce) is checked on hardware by
+tests/test_multigpu.py."""
 import os
 import socket
 import sys
@@ -12,7 +13,7 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from poolgen_b200 import shard  # noqa: E402
+from poolgen_b200 import capi, shard  # noqa: E402
 
 
 def test_shard_range_partitions():
@@ -28,17 +29,6 @@ def test_shard_range_partitions():
         shard.shard_range(10, 2, 2)
 
 
-class _FakeKin:
-    def __init__(self, K):
-        self.K = K.copy()
-
-    def partial_get(self):
-        return self.K.copy()
-
-    def partial_set(self, K):
-        self.K = np.array(K, copy=True)
-
-
 def _worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -48,10 +38,18 @@ def _worker(rank, world, port, out_dir):
         rng = np.random.default_rng(5)
         G = rng.random((P, n))                      # every rank builds the same matrix, owns one column shard
         b, e = shard.shard_range(P, rank, world)
-        kin = _FakeKin(G[b:e].T @ G[b:e])
-        shard.allreduce_partial_gram(kin, dist)
-        assert np.allclose(kin.K, G.T @ G, rtol=1e-13)
-        assert shard.total_columns(e - b, dist) == P
+        # the partial Gram matrices of contiguous column shards sum to the whole (what pg_kin_allreduce relies on)
+        partial = G[b:e].T @ G[b:e]
+        import torch
+        t = torch.from_numpy(partial.copy())
+        dist.all_reduce(t)
+        assert np.allclose(t.numpy(), G.T @ G, rtol=1e-13)
+        # communicator rendezvous: the id rank 0 obtained from the library reaches every rank unchanged
+        uid = shard.broadcast_comm_id(dist)
+        assert len(uid) == capi.COMM_ID_BYTES
+        box = [None] * world
+        dist.all_gather_object(box, uid)
+        assert all(u == box[0] for u in box)
         got = shard.gather_in_rank_order(np.arange(b, e), dist)
         if rank == 0:
             assert np.array_equal(got, np.arange(P))
