@@ -130,8 +130,6 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
                     filter->n_pool_sizes, n_pools);
     const bool regression = (kind == PG_KIND_OLS || kind == PG_KIND_CORR);
     if (regression && (!phen || k < 1)) return fail(ctx, PG_ERR_ARG, "pg_scan_open: phenotypes required");
-    if (kind == PG_KIND_FISHER && n_pools > 16)
-        return fail(ctx, PG_ERR_UNSUPPORTED, "pg_scan_open: fisher holds one table per thread and is built for up to 16 pools (got %d); its enumeration grows with (pools x alleles)^2 (src/tables/fisher_exact_test.rs:68-117)", n_pools);
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
 
     pg_scan *s = new (std::nothrow) pg_scan();
@@ -177,6 +175,7 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
         s->yc_host.assign((size_t)k * np, 0.0);
         s->ysum.assign(k, 0.0);
         s->syy.assign(k, 0.0);
+        s->ymean.assign(k, 0.0);
         for (int j = 0; j < k; j++) {
             double sum = 0.0;
             int n_valid = 0;
@@ -198,6 +197,7 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
                 s2 += c * c;
             }
             s->ysum[j] = s1;
+            s->ymean[j] = mean;
             s->syy[j] = s2 - s1 * s1 / n;
         }
         if (s->y_has_nan && kind == PG_KIND_OLS) {
@@ -597,6 +597,7 @@ static int run_once(pg_batch *b, int *launches) {
             for (int j = 0; j < p.K; j++) {
                 p.ysum[j] = s->ysum[base + j];
                 p.syy[j] = s->syy[base + j];
+                p.ymean[j] = s->ymean[base + j];
             }
             for (int j = 0; j < s->A_dev; j++) p.codes[j] = s->codes_dev[j];
             p.meta = b->d_meta;

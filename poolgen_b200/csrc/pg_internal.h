@@ -88,6 +88,7 @@ struct ScanParams {
     const double *w;      // [n_pad] s_i / sum(s) (device)
     double ysum[kMaxPhenPerPass];  // sum of the centred phenotype (rounding residue)
     double syy[kMaxPhenPerPass];   // centred sum of squares
+    double ymean[kMaxPhenPerPass]; // mean of the phenotype (the n < p branch needs the uncentred values)
     int y_has_nan;
     uint8_t codes[8];     // allele code of device column j
     uint64_t *meta;
@@ -184,7 +185,7 @@ struct pg_scan {
     std::vector<double> w_host;
     // phenotypes
     std::vector<double> yc_host;  // [k][n_pad]
-    std::vector<double> ysum, syy;
+    std::vector<double> ysum, syy, ymean;
     int y_has_nan = 0;
     double df = 0, ln_beta = 0;
     double *d_yc = nullptr;

@@ -18,6 +18,7 @@ struct pg_kin {
     int nt = 0, n_slices = 0;
     // covariates
     int m = -1;
+    bool minnorm = false;         // m == n: the reference's n < p branch (pg_kin_eig_select)
     std::vector<double> eigvals;  // descending
     std::vector<double> Q;        // [1+m][ldg] orthonormal basis of [1 | PCs] (host)
     double *d_V = nullptr;        // [(1+m) + k][ldg]

@@ -374,12 +374,32 @@ struct CovarParams {
     double yy[kMaxPhenPerPass * 4];  // y~'y~ per phenotype (k <= 16)
     double dfe;        // n - (2 + m)
     double df;         // n - 1
+    // n < p branch (src/gwas/ols.rs:67-75): the threshold was never reached, so ALL n eigenvectors are covariates
+    // (ols.rs:300-311) and X = [1 | V | g] has n + 2 columns.  With V orthogonal XX' = I + 11' + gg', and the last
+    // coefficient of X'(XX')^-1 y follows from the same sums the kernel forms with Q = [1/sqrt(n)] and the RAW
+    // phenotypes (Woodbury on the rank-2 update); var = (e'e / -2) (...) is rounding noise over a negative number, so
+    // t is NaN and p is forced to 1 (ols.rs:150-151)
+    int minnorm;
+    double nf, sqrt_n;
+    double sy[kMaxPhenPerPass * 4];  // sum of the raw phenotype
     const void *ptab;
     double ptab_vmax, ptab_inv_h;
     int ptab_M;
     double ln_beta;
     double *beta, *var, *pval;  // [k][P]
 };
+
+// last coefficient of the minimum-norm solution with X = [1 | V | g], V orthogonal: b = g'(I + UU')^-1 y, U = [1 g];
+// (I + UU')^-1 = I - U (I_2 + U'U)^-1 U'.  u0 = g'1 / sqrt(n), gy = g'y (raw phenotype j)
+__device__ __forceinline__ void covar_minnorm(const CovarParams &p, double gg, double u0, double gy, int j, double &b,
+                                              double &pv) {
+    const double s = u0 * p.sqrt_n;
+    const double w11 = 1.0 + p.nf, w22 = 1.0 + gg;
+    const double det = w11 * w22 - s * s;  // >= 1 + n + gg > 0 (Cauchy-Schwarz: s^2 <= n gg)
+    const double z0 = (w22 * p.sy[j] - s * gy) / det, z1 = (w11 * gy - s * p.sy[j]) / det;
+    b = gy - (s * z0 + gg * z1);
+    pv = (b == b) ? 1.0 : nan("");
+}
 
 // NV = (1 + m) + k vectors in shared memory; a warp streams C allele columns at once so that every shared-memory load
 // of a Q / y~ element feeds C pairs of FMAs (with m = 10 covariates the one-column form spends its time on 12 LDS per
@@ -443,7 +463,7 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
             double gy[NV];
 #pragma unroll
             for (int v = 0; v < NV; v++) gy[v] = acc[v];
-            if (!(gg <= 1e4 * ggc)) {
+            if (!p.minnorm && !(gg <= 1e4 * ggc)) {
                 // cancellation: second pass with explicit residuals g - Q u (the column is still in L2)
                 double s2 = 0.0, sy[NV];
 #pragma unroll
@@ -473,7 +493,9 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
             for (int j = 0; j < kMaxPhenPerPass * 4; j++)
                 if (j == lane) yyj = p.yy[j];
             if (lane < k) {
-                if (ggc > 0.0 && p.dfe > 0.0) {
+                if (p.minnorm) {
+                    covar_minnorm(p, gg, acc[0], gyj, lane, b, pv);
+                } else if (ggc > 0.0 && p.dfe > 0.0) {
                     b = gyj / ggc;
                     double rss = yyj - b * gyj;
                     if (rss < 0.0) rss = 0.0;
@@ -528,7 +550,7 @@ __global__ void __launch_bounds__(256) covar_generic_kernel(const CovarParams p)
         }
         __syncwarp();
         double ggc = gg - uu;
-        const bool redo = !(gg <= 1e4 * ggc);
+        const bool redo = !p.minnorm && !(gg <= 1e4 * ggc);
         if (redo) {  // explicit residual e = g - Q u, then e'e and e'y~
             for (int r = lane; r < ldg; r += 32) {
                 double e = gcol[r];
@@ -551,7 +573,9 @@ __global__ void __launch_bounds__(256) covar_generic_kernel(const CovarParams p)
         if (lane < k) {
             double b = nan(""), vb = nan(""), pv = nan("");
             const double gyj = u[nq + lane], yyj = p.yy[lane];
-            if (ggc > 0.0 && p.dfe > 0.0) {
+            if (p.minnorm) {
+                covar_minnorm(p, gg, u[0], gyj, lane, b, pv);
+            } else if (ggc > 0.0 && p.dfe > 0.0) {
                 b = gyj / ggc;
                 double rss = yyj - b * gyj;
                 if (rss < 0.0) rss = 0.0;
@@ -1028,8 +1052,17 @@ int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) 
         if (cum[i - 1] >= threshold && (i - 1) < m) m = i - 1;
     }
     h->m = m;
+    h->minnorm = false;
     if (m_out) *m_out = m;
-    if (m + 2 > n) return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_eig_select: %d covariates for %d pools (the reference's n < p branch is not built)", m, n);
+    if (m == n) {
+        // the threshold is never reached (ols.rs:300-311 leaves n_eigenvecs = n): all eigenvectors are covariates and
+        // X = [1 | V | g] has more columns than rows -- the reference's n < p branch (ols.rs:67-75).  span(V) is the
+        // whole space, so only the intercept direction is kept here; covar_kernel forms the minimum-norm coefficient
+        h->minnorm = true;
+        h->Q.assign((size_t)h->ldg, 0.0);
+        for (int i = 0; i < n; i++) h->Q[i] = 1.0 / sqrt((double)n);
+        return PG_OK;
+    }
     // Q = orthonormal basis of [1 | v_1 .. v_m] (modified Gram-Schmidt, twice)
     const int nq = 1 + m, ldg = h->ldg;
     h->Q.assign((size_t)nq * ldg, 0.0);
@@ -1061,6 +1094,7 @@ int pg_kin_copy_covariates(pg_kin *dst, const pg_kin *src) {
     if (src->m < 0) return kfail(dst->ctx, PG_ERR_STATE, "pg_kin_copy_covariates: the source has no covariates yet");
     if (dst->n != src->n) return kfail(dst->ctx, PG_ERR_ARG, "pg_kin_copy_covariates: %d vs %d pools", dst->n, src->n);
     dst->m = src->m;
+    dst->minnorm = src->minnorm;
     dst->Q = src->Q;
     dst->eigvals = src->eigvals;
     dst->P_total = src->P_total;
@@ -1080,6 +1114,7 @@ int pg_kin_set_covariates(pg_kin *h, const double *cov, int m) {
     const int n = h->n, ldg = h->ldg, nq = 1 + m;
     if (m + 2 > n) return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_set_covariates: %d covariates for %d pools", m, n);
     h->m = m;
+    h->minnorm = false;
     h->Q.assign((size_t)nq * ldg, 0.0);
     for (int i = 0; i < n; i++) h->Q[i] = 1.0;
     for (int l = 0; l < m; l++)
@@ -1158,7 +1193,7 @@ int pg_kin_covar_scan(pg_kin *h, const double *phen, int k, int iters, float *ms
     if (!h || !phen || k < 1) return PG_ERR_ARG;
     pg_ctx *ctx = h->ctx;
     if (h->m < 0) return kfail(ctx, PG_ERR_STATE, "pg_kin_covar_scan before pg_kin_eig_select / pg_kin_set_covariates");
-    const int n = h->n, ldg = h->ldg, nq = 1 + h->m;
+    const int n = h->n, ldg = h->ldg, nq = h->minnorm ? 1 : 1 + h->m;
     if (k > pg::kMaxPhenPerPass * 4)
         return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_covar_scan: %d phenotypes > %d per call", k, pg::kMaxPhenPerPass * 4);
     KCUDA(ctx, cudaSetDevice(ctx->device));
@@ -1170,6 +1205,12 @@ int pg_kin_covar_scan(pg_kin *h, const double *phen, int k, int iters, float *ms
     for (int j = 0; j < k; j++) {
         double *yt = &V[(size_t)(nq + j) * ldg];
         for (int i = 0; i < n; i++) yt[i] = phen[(size_t)i * k + j];
+        if (h->minnorm) {  // the n < p branch works on the raw phenotype
+            double sy = 0.0;
+            for (int i = 0; i < n; i++) sy += yt[i];
+            cp.sy[j] = sy;
+            continue;
+        }
         for (int pass = 0; pass < 2; pass++)
             for (int b = 0; b < nq; b++) {
                 const double *qb = &h->Q[(size_t)b * ldg];
@@ -1222,6 +1263,9 @@ int pg_kin_covar_scan(pg_kin *h, const double *phen, int k, int iters, float *ms
     cp.k = k;
     cp.V = h->d_V;
     cp.dfe = (double)n - (double)(2 + h->m);
+    cp.minnorm = h->minnorm ? 1 : 0;
+    cp.nf = (double)n;
+    cp.sqrt_n = sqrt((double)n);
     cp.df = df;
     cp.ptab = h->d_ptab;
     cp.ptab_vmax = h->ptab_vmax;

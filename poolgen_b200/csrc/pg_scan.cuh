@@ -402,7 +402,7 @@ __device__ __forceinline__ double solve_rhs(int m, const double (&Li)[PG_MAX_SLO
 
 __device__ __forceinline__ int slot_col(unsigned cb, int s) { return (int)((cb >> (4 * s)) & 0xfu); }
 
-enum { REDO_NONE = 0, REDO_OLS = 1, REDO_CORR = 2, REDO_CORR_NAN = 3, REDO_DEFER = 4 };
+enum { REDO_NONE = 0, REDO_OLS = 1, REDO_CORR = 2, REDO_CORR_NAN = 3, REDO_DEFER = 4, REDO_MINNORM = 5 };
 
 // the analysis as a compile-time constant in the streaming kernel (KIND = PG_KIND_OLS / PG_KIND_CORR: the other
 // analysis' phase-2 code is not even linked -- the small-locus kernels are sensitive to their instruction footprint),
@@ -674,6 +674,153 @@ __device__ __noinline__ int corr_pairwise_locus(const ScanParams &p, int64_t loc
     return PG_LOCUS_OK;
 }
 
+// Fewer pools than coefficients (n < p_x = 1 + m, i.e. at most 5 pools): the reference's other branch,
+// b = X'(XX')^-1 y and var = ve diag(X'(XX')^-2 X) with ve = e'e / (n - p_x) (src/gwas/ols.rs:67-75, 106-111).  The fit
+// interpolates, so e'e is rounding noise over a NEGATIVE n - p_x: var is a tiny negative number (t = NaN, p forced to 1,
+// ols.rs:150-151) or -0 when every residual is exactly zero (t = +-inf, p = 0) -- both fall out of the same arithmetic
+// in write_records.  LU with partial pivoting in dgetf2's order, so an exactly singular XX' (two pools with the same
+// frequencies) fails like the reference's inv().  Whole warp, every lane computes the same numbers (n <= 5);
+// lane 0 leaves (beta, var) per (slot, phenotype) in out.  ys holds the CENTRED phenotypes; the raw ones are ys + mean.
+template <int A, int K>
+__device__ __noinline__ int minnorm_locus(const ScanParams &p, int64_t locus, unsigned kept, int m, unsigned cb,
+                                          const double *ys, double *out, int lane) {
+    constexpr int MS = A - 1, PX = A, NR = 5;
+    const int n = p.lay.n, n_pad = p.lay.n_pad, px = m + 1;
+    double xrow[PX];
+#pragma unroll
+    for (int c = 0; c < PX; c++) xrow[c] = 0.0;
+    for_rows_coop<A>(p, locus, lane, [&](int i, const double(&f)[A], uint32_t d) {
+        double F[A];
+        renorm_row<A>(f, d, kept, F);
+        xrow[0] = 1.0;
+#pragma unroll
+        for (int a = 0; a < MS; a++) {
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < A; j++)
+                if (a < m && j == slot_col(cb, a)) v = F[j];
+            xrow[1 + a] = v;
+        }
+    });
+    double X[NR][PX], Y[NR][K];
+#pragma unroll
+    for (int i = 0; i < NR; i++) {
+#pragma unroll
+        for (int c = 0; c < PX; c++) X[i][c] = __shfl_sync(PG_FULL_MASK, xrow[c], i);
+#pragma unroll
+        for (int k = 0; k < K; k++) Y[i][k] = (i < n) ? ys[k * n_pad + i] + p.ymean[k] : 0.0;
+    }
+    // M = X X' (n x n); rows / columns >= n form an identity block
+    double M[NR][NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++)
+#pragma unroll
+        for (int j = 0; j < NR; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < PX; c++)
+                if (c < px) s += X[i][c] * X[j][c];
+            M[i][j] = (i < n && j < n) ? s : (i == j ? 1.0 : 0.0);
+        }
+    // right-hand sides: the K phenotypes, then the MS regressor columns of X (for diag(X'(XX')^-2 X))
+    constexpr int NB = K + MS;
+    double B[NR][NB];
+#pragma unroll
+    for (int i = 0; i < NR; i++) {
+#pragma unroll
+        for (int k = 0; k < K; k++) B[i][k] = Y[i][k];
+#pragma unroll
+        for (int a = 0; a < MS; a++) B[i][K + a] = (i < n) ? X[i][1 + a] : 0.0;
+    }
+    // Gaussian elimination with partial pivoting (first largest |a_ij| of the column, like idamax)
+    bool singular = false;
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        int jp = j;
+        double amax = fabs(M[j][j]);
+#pragma unroll
+        for (int i = j + 1; i < NR; i++) {
+            const double v = fabs(M[i][j]);
+            if (v > amax) {
+                amax = v;
+                jp = i;
+            }
+        }
+#pragma unroll
+        for (int i = j + 1; i < NR; i++)
+            if (i == jp) {
+#pragma unroll
+                for (int c = 0; c < NR; c++) {
+                    const double t = M[j][c];
+                    M[j][c] = M[i][c];
+                    M[i][c] = t;
+                }
+#pragma unroll
+                for (int c = 0; c < NB; c++) {
+                    const double t = B[j][c];
+                    B[j][c] = B[i][c];
+                    B[i][c] = t;
+                }
+            }
+        if (!(fabs(M[j][j]) > 0.0)) {
+            singular = true;
+            M[j][j] = 1.0;
+        }
+        const double r = 1.0 / M[j][j];
+#pragma unroll
+        for (int i = j + 1; i < NR; i++) {
+            const double l = M[i][j] * r;
+#pragma unroll
+            for (int c = j + 1; c < NR; c++) M[i][c] -= l * M[j][c];
+#pragma unroll
+            for (int c = 0; c < NB; c++) B[i][c] -= l * B[j][c];
+        }
+    }
+    if (singular) return PG_LOCUS_FAILED;
+#pragma unroll
+    for (int j = NR - 1; j >= 0; j--) {
+#pragma unroll
+        for (int c = 0; c < NB; c++) {
+            double s = B[j][c];
+#pragma unroll
+            for (int i = j + 1; i < NR; i++) s -= M[j][i] * B[i][c];
+            B[j][c] = s / M[j][j];
+        }
+    }
+    // B[:, k] = (XX')^-1 y_k, B[:, K + a] = (XX')^-1 x_a
+    const double dfe = (double)n - (double)px;  // negative
+    if (lane == 0) {
+        for (int k = 0; k < K; k++) {
+            double b[PX];
+            for (int c = 0; c < PX; c++) {
+                double s = 0.0;
+                for (int i = 0; i < NR; i++)
+                    if (i < n && c < px) s += X[i][c] * B[i][k];
+                b[c] = s;
+            }
+            double ee = 0.0;
+            for (int i = 0; i < NR; i++)
+                if (i < n) {
+                    double e = Y[i][k];
+                    for (int c = 0; c < PX; c++)
+                        if (c < px) e -= X[i][c] * b[c];
+                    ee += e * e;
+                }
+            const double ve = ee / dfe;
+            for (int a = 0; a < MS; a++)
+                if (a < m) {
+                    double dd = 0.0;
+                    for (int i = 0; i < NR; i++)
+                        if (i < n) dd += B[i][K + a] * B[i][K + a];
+                    out[(a * K + k) * 2 + 0] = b[1 + a];
+                    out[(a * K + k) * 2 + 1] = ve * dd;
+                }
+        }
+    }
+    __syncwarp();
+    return PG_LOCUS_OK;
+}
+
 // Single-pass OLS from the reduced sums for M regressors, fully unrolled so that every matrix lives in registers.
 // Returns false when the centred X'X is not positive definite; sets redo when the single-pass form loses digits.
 // m <= M regressors are present; the slots m..M-1 are an identity block with zero right-hand sides.  They only append
@@ -846,9 +993,12 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
         }
     }
     if (kind_is_ols<KIND>(p)) {
-        if (lay.n < m + 1) {
-            status = PG_LOCUS_UNSUPPORTED;
-        } else if (!has_nan) {
+        if (has_nan) {
+            for (int i = 0; i < T2; i++) tg[i] = nan("");
+        } else if (lay.n < m + 1) {
+            // fewer pools than coefficients: the minimum-norm branch (src/gwas/ols.rs:67-75), left to the fix-up kernel
+            redo_mode = REDO_MINNORM;
+        } else {
             bool redo = false;
             // the lanes that got here agree on m (real data: nearly always biallelic) -> the variant of that size;
             // otherwise ONE pass of the full-size variant with masked slots instead of a pass per distinct m
@@ -873,8 +1023,6 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
                 }
             }
             if (redo) redo_mode = REDO_OLS;
-        } else {
-            for (int i = 0; i < T2; i++) tg[i] = nan("");
         }
     } else {
         double tb[T2];
@@ -1152,6 +1300,8 @@ __device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool a
             __syncwarp();
             const int st = (md == REDO_CORR_NAN)
                                ? corr_pairwise_locus<A, K>(p, lsrc, kk, mm, cc, ys, tot + (size_t)src * AC::NP, lane)
+                           : (md == REDO_MINNORM)
+                               ? minnorm_locus<A, K>(p, lsrc, kk, mm, cc, ys, tot + (size_t)src * AC::NP, lane)
                                : redo_locus<A, K>(p, lsrc, kk, mm, cc, md, ys, tot + (size_t)src * AC::NP, lane);
             if (lane == src) status = st;
         }

@@ -3,6 +3,8 @@
 // [locus][allele][pool] of a CTA's loci are staged through shared memory with coalesced 128-bit loads;
 // each thread then walks its own locus in the reference's exact sequential order, so the keep-mask
 // needs no rounding analysis here.
+#include <stdlib.h>
+
 #include "pg_device.cuh"
 #include "pg_internal.h"
 
@@ -511,10 +513,61 @@ __global__ void __launch_bounds__(kTabThreads) tables_kernel(const TableParams p
     }
 }
 
-// ---- tables::chisq for more than 16 pools: one warp per locus, lane = pool (stride 32), counts re-read from L1/L2 for
-// each of the three passes (depth + pooled frequencies, column sums, chi-square).  The keep-mask is the reference's:
-// a pooled frequency within the rounding bound of a threshold is re-evaluated by one lane in pool order with separately
-// rounded multiply and add (src/base/sync.rs:258-271).
+// ---- more than 16 pools: one warp per locus, lane = pool (stride 32), counts re-read from L1/L2 ---------------------
+// LocusCounts::filter by the whole warp.  The keep-mask is the reference's: a pooled frequency within the rounding
+// bound of a threshold is re-evaluated by one lane in pool order with separately rounded multiply and add
+// (src/base/sync.rs:258-271).  Every lane returns the same status, kept columns cols[0..pk).
+__device__ __forceinline__ int wide_filter(const TableParams &p, const uint32_t *cnt, const int *col, int pc, int lane,
+                                           int *cols, int &pk) {
+    const int n = p.n;
+    const double tol_rel = 2.0 * ((double)n + 8.0) * kEps;
+    double q[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
+    double dmin = 1.7976931348623157e308;
+    int miss = 0;
+    for (int i = lane; i < n; i += 32) {
+        double d = 0.0;
+        for (int a = 0; a < pc; a++) d += (double)cnt[col[a] * n + i];
+        dmin = fmin(dmin, d);
+        if (d == 0.0) {
+            miss++;
+        } else {
+            const double wi = p.w[i];
+            for (int a = 0; a < pc; a++) q[a] += ((double)cnt[col[a] * n + i] / d) * wi;
+        }
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        dmin = fmin(dmin, __shfl_xor_sync(PG_FULL_MASK, dmin, off));
+        miss += __shfl_xor_sync(PG_FULL_MASK, miss, off);
+        for (int a = 0; a < pc; a++) q[a] += __shfl_xor_sync(PG_FULL_MASK, q[a], off);
+    }
+    pk = 0;
+    if (dmin < p.min_depth_f) return PG_LOCUS_FILTERED;
+    for (int a = 0; a < pc; a++) {
+        double qa = q[a];
+        const double tl = tol_rel * fmax(fabs(qa), 1.0);
+        if (fabs(qa - p.maf) <= tl || fabs(qa - p.one_minus_maf) <= tl) {
+            if (lane == 0) {  // the reference's order decides
+                double e = 0.0;
+                for (int i = 0; i < n; i++) {
+                    double d = 0.0;
+                    for (int b = 0; b < pc; b++) d += (double)cnt[col[b] * n + i];
+                    const double f = (d == 0.0) ? nan("") : (double)cnt[col[a] * n + i] / d;
+                    const double term = (f != f) ? 0.0 : __dmul_rn(f, p.w[i]);
+                    e = __dadd_rn(e, term);
+                }
+                qa = e;
+            }
+            qa = __shfl_sync(PG_FULL_MASK, qa, 0);
+        }
+        if (!((qa < p.maf) | (qa > p.one_minus_maf))) cols[pk++] = col[a];
+    }
+    if (pk < 2) return PG_LOCUS_FILTERED;
+    if (miss == n) return PG_LOCUS_FILTERED;
+    if (((double)miss / (double)n) > p.max_miss) return PG_LOCUS_FILTERED;
+    return PG_LOCUS_OK;
+}
+
+// tables::chisq: three passes (depth + pooled frequencies, column sums, chi-square)
 __global__ void __launch_bounds__(256) chisq_wide_kernel(const TableParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -524,58 +577,11 @@ __global__ void __launch_bounds__(256) chisq_wide_kernel(const TableParams p) {
     int pc = 0;
     for (int j = 0; j < p.A_in; j++)
         if (j != p.drop_col) col[pc++] = j;
-    const double tol_rel = 2.0 * ((double)n + 8.0) * kEps;
     for (int64_t locus = gw; locus < p.n_loci; locus += nw) {
         const uint32_t *cnt = p.counts + (size_t)locus * p.A_in * n;
-        // pass 1: depth per pool, smallest depth, pools without coverage, pooled frequencies
-        double q[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
-        double dmin = 1.7976931348623157e308;
-        int miss = 0;
-        for (int i = lane; i < n; i += 32) {
-            double d = 0.0;
-            for (int a = 0; a < pc; a++) d += (double)cnt[col[a] * n + i];
-            dmin = fmin(dmin, d);
-            if (d == 0.0) {
-                miss++;
-            } else {
-                const double wi = p.w[i];
-                for (int a = 0; a < pc; a++) q[a] += ((double)cnt[col[a] * n + i] / d) * wi;
-            }
-        }
-        for (int off = 16; off >= 1; off >>= 1) {
-            dmin = fmin(dmin, __shfl_xor_sync(PG_FULL_MASK, dmin, off));
-            miss += __shfl_xor_sync(PG_FULL_MASK, miss, off);
-            for (int a = 0; a < pc; a++) q[a] += __shfl_xor_sync(PG_FULL_MASK, q[a], off);
-        }
-        int status = PG_LOCUS_OK;
         int cols[PG_MAX_ALLELES];
         int pk = 0;
-        if (dmin < p.min_depth_f) {
-            status = PG_LOCUS_FILTERED;
-        } else {
-            for (int a = 0; a < pc; a++) {
-                double qa = q[a];
-                const double tl = tol_rel * fmax(fabs(qa), 1.0);
-                if (fabs(qa - p.maf) <= tl || fabs(qa - p.one_minus_maf) <= tl) {
-                    if (lane == 0) {  // the reference's order decides
-                        double e = 0.0;
-                        for (int i = 0; i < n; i++) {
-                            double d = 0.0;
-                            for (int b = 0; b < pc; b++) d += (double)cnt[col[b] * n + i];
-                            const double f = (d == 0.0) ? nan("") : (double)cnt[col[a] * n + i] / d;
-                            const double term = (f != f) ? 0.0 : __dmul_rn(f, p.w[i]);
-                            e = __dadd_rn(e, term);
-                        }
-                        qa = e;
-                    }
-                    qa = __shfl_sync(PG_FULL_MASK, qa, 0);
-                }
-                if (!((qa < p.maf) | (qa > p.one_minus_maf))) cols[pk++] = col[a];
-            }
-            if (pk < 2) status = PG_LOCUS_FILTERED;
-            else if (miss == n) status = PG_LOCUS_FILTERED;
-            else if (((double)miss / (double)n) > p.max_miss) status = PG_LOCUS_FILTERED;
-        }
+        const int status = wide_filter(p, cnt, col, pc, lane, cols, pk);
         double stat = nan(""), pval = nan("");
         if (status == PG_LOCUS_OK) {
             // pass 2: column sums and the total of the frequencies renormalised over the kept alleles (sync.rs:166-192)
@@ -636,15 +642,168 @@ __global__ void __launch_bounds__(256) chisq_wide_kernel(const TableParams p) {
     }
 }
 
-cudaError_t launch_tables(const TableParams &p, int sm_count, cudaStream_t s) {
-    if (p.n > kTabMaxPools) {
-        if (p.kind != PG_KIND_CHISQ) return cudaErrorInvalidConfiguration;
-        int64_t grid = (p.n_loci * 32 + 255) / 256;
-        if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
-        if (grid < 1) grid = 1;
-        chisq_wide_kernel<<<(unsigned)grid, 256, 0, s>>>(p);
-        return cudaGetLastError();
+// tables::fisher (src/tables/fisher_exact_test.rs:32-130) for any number of pools.  The table is rescaled to a total of
+// at most 34 (51-58), so whatever the pool count at most 34 rows are non-zero; a zero row stays zero in every fill
+// (its cells are bounded by its row sum) and adds log10(0!) = 0 to every sum, so only the non-zero rows are kept, with
+// their original index for the two places the enumeration looks at it: `i == n - 1` and `i < max_i` (the latter only
+// through the NUMBER of non-zero rows above max_i -- its "class").  All cell arithmetic is on integers <= 34, hence
+// exact in any form; the floating-point sums (log10-factorials in row-major order, p_extremes over (max_i, max_j) in
+// loop order) keep the reference's order.  The forward fill (78-92) overwrites every cell from cells it has already
+// rewritten, so the (class, max_j) tables are independent: the lanes of the warp take them in parallel, each in its own
+// scratch table, and lane 0 adds the ratios in the reference's loop order.
+constexpr int kFwRows = 34;
+constexpr int kFwWarps = 4;
+constexpr int kFwPitch = 8;  // bytes per scratch row: 6 cells + the running row sum
+
+__global__ void __launch_bounds__(kFwWarps * 32) fisher_wide_kernel(const TableParams p) {
+    __shared__ uint8_t s_obs[kFwWarps][kFwRows * kFwPitch];   // observed (rescaled) non-zero rows | row sum in [6]
+    __shared__ int s_orow[kFwWarps][kFwRows];                 // original row index
+    __shared__ uint8_t s_tab[kFwWarps][32][kFwRows * kFwPitch];
+    __shared__ double s_ratio[kFwWarps][(kFwRows + 1) * PG_MAX_ALLELES];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * kFwWarps + wib;
+    const int64_t nw = (int64_t)gridDim.x * kFwWarps;
+    const int n = p.n;
+    int col[PG_MAX_ALLELES];
+    int pc = 0;
+    for (int j = 0; j < p.A_in; j++)
+        if (j != p.drop_col) col[pc++] = j;
+    uint8_t *obs = s_obs[wib];
+    int *orow = s_orow[wib];
+    uint8_t *T = s_tab[wib][lane];
+    double *ratio = s_ratio[wib];
+    for (int64_t locus = gw; locus < p.n_loci; locus += nw) {
+        const uint32_t *cnt = p.counts + (size_t)locus * p.A_in * n;
+        int cols[PG_MAX_ALLELES];
+        int pk = 0;
+        int status = wide_filter(p, cnt, col, pc, lane, cols, pk);
+        double stat = nan(""), pval = nan("");
+        if (status == PG_LOCUS_OK) {
+            // the table's total (integers: exact in any order), the rescale to <= 34 (fisher_exact_test.rs:50-58)
+            double total = 0.0;
+            for (int i = lane; i < n; i += 32)
+                for (int a = 0; a < pk; a++) total += (double)cnt[cols[a] * n + i];
+            for (int off = 16; off >= 1; off >>= 1) total += __shfl_xor_sync(PG_FULL_MASK, total, off);
+            const bool scale = total > 34.0;
+            const double coef = 34.0 / total;
+            int nz = 0;
+            int cs[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
+            __syncwarp();
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                int cell[PG_MAX_ALLELES], rsum = 0;
+                for (int a = 0; a < pk; a++) {
+                    double c = (i < n) ? (double)cnt[cols[a] * n + i] : 0.0;
+                    if (scale) c = floor(c * coef);
+                    cell[a] = (int)c;
+                    rsum += cell[a];
+                    cs[a] += cell[a];
+                }
+                const unsigned nzm = __ballot_sync(PG_FULL_MASK, rsum > 0);
+                if (rsum > 0) {
+                    const int pos = nz + __popc(nzm & ((1u << lane) - 1u));
+                    if (pos < kFwRows) {  // the total is <= 34, so at most 34 rows carry a count
+                        for (int a = 0; a < pk; a++) obs[pos * kFwPitch + a] = (uint8_t)cell[a];
+                        obs[pos * kFwPitch + 6] = (uint8_t)rsum;
+                        orow[pos] = i;
+                    }
+                }
+                nz += __popc(nzm);
+            }
+            for (int a = 0; a < pk; a++) cs[a] = __reduce_add_sync(PG_FULL_MASK, cs[a]);
+            if (nz > kFwRows) nz = kFwRows;
+            __syncwarp();
+            // log-product of the marginal sums (60-67) and the observed ratio (69), sequential like the reference
+            double lp = 0.0;
+            int tot2 = 0;
+            for (int r = 0; r < nz; r++) {
+                lp = lp + c_lf10[obs[r * kFwPitch + 6]];
+                tot2 += obs[r * kFwPitch + 6];
+            }
+            for (int a = 0; a < pk; a++) lp = lp + c_lf10[cs[a]];
+            double so = 0.0;
+            for (int r = 0; r < nz; r++)
+                for (int a = 0; a < pk; a++) so = so + c_lf10[obs[r * kFwPitch + a]];
+            so = so + c_lf10[tot2];
+            const double p_obs = pow(10.0, lp - so);
+            // the (class, max_j) tables, one per lane at a time
+            const int ntask = (nz + 1) * pk;
+            bool panic = false;
+            for (int t = lane; t < ntask; t += 32) {
+                const int cls = t / pk, mj = t - cls * pk;
+                int S[PG_MAX_ALLELES] = {0, 0, 0, 0, 0, 0};
+                for (int r = 0; r < nz; r++) {  // forward fill (78-92)
+                    const int rsr = obs[r * kFwPitch + 6];
+                    const bool last_row = orow[r] == n - 1;
+                    int rr = 0;
+                    for (int j = 0; j < pk; j++) {
+                        const int a = max(rsr - rr, 0), b = max(cs[j] - S[j], 0);
+                        const int mx = min(a, b);
+                        const int v = (last_row | (j == pk - 1)) ? mx : (((r < cls) | (j < mj)) ? 0 : mx);
+                        T[r * kFwPitch + j] = (uint8_t)v;
+                        rr += v;
+                        S[j] += v;
+                    }
+                    T[r * kFwPitch + 6] = (uint8_t)rr;
+                }
+                for (int j = pk - 1; j >= 0; j--)  // reverse fill (96-111)
+                    for (int r = nz - 1; r >= 0; r--) {
+                        const int R = T[r * kFwPitch + 6];
+                        const int a = max((int)obs[r * kFwPitch + 6] - R, 0), b = max(cs[j] - S[j], 0);
+                        const int mx = min(a, b);
+                        if (mx > 0) {
+                            const int old = T[r * kFwPitch + j];
+                            T[r * kFwPitch + j] = (uint8_t)mx;
+                            T[r * kFwPitch + 6] = (uint8_t)(R + mx - old);
+                            S[j] += mx - old;
+                        }
+                    }
+                int tsum = 0;
+                for (int r = 0; r < nz; r++) {  // the marginal sums must have been kept (113-114)
+                    if (T[r * kFwPitch + 6] != obs[r * kFwPitch + 6]) panic = true;
+                    tsum += T[r * kFwPitch + 6];
+                }
+                for (int j = 0; j < pk; j++)
+                    if (S[j] != cs[j]) panic = true;
+                double sr = 0.0;
+                for (int r = 0; r < nz; r++)
+                    for (int j = 0; j < pk; j++) sr = sr + c_lf10[T[r * kFwPitch + j]];
+                sr = sr + c_lf10[min(tsum, 35)];
+                ratio[t] = pow(10.0, lp - sr);
+            }
+            panic = __any_sync(PG_FULL_MASK, panic);
+            __syncwarp();
+            if (panic) {
+                status = PG_LOCUS_PANIC;  // assert! at fisher_exact_test.rs:113-114
+            } else {
+                double p_ext = 0.0;
+                if (lane == 0) {  // p_extremes in the reference's loop order (max_i outer, max_j inner)
+                    int cls = 0;
+                    for (int mi = 0; mi < n; mi++) {
+                        while (cls < nz && orow[cls] < mi) cls++;
+                        for (int mj = 0; mj < pk; mj++) p_ext += ratio[cls * pk + mj];
+                    }
+                }
+                stat = p_obs;
+                pval = p_obs + p_ext;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            uint64_t mv = (uint64_t)status;
+            if (status == PG_LOCUS_OK) {
+                mv |= (uint64_t)pk << 8;
+                for (int a = 0; a < pk; a++) mv |= (uint64_t)p.codes[cols[a]] << (16 + 8 * a);
+            }
+            p.meta[locus] = mv;
+            double *o = p.stats + (size_t)locus * 4;
+            *reinterpret_cast<double2 *>(o) = make_double2(stat, nan(""));
+            *reinterpret_cast<double2 *>(o + 2) = make_double2(nan(""), pval);
+        }
     }
+}
+
+cudaError_t launch_tables(const TableParams &p, int sm_count, cudaStream_t s) {
     static bool lf_ready[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -659,6 +818,21 @@ cudaError_t launch_tables(const TableParams &p, int sm_count, cudaStream_t s) {
         cudaError_t e = cudaMemcpyToSymbolAsync(c_lf10, lf, sizeof lf, 0, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) return e;
         lf_ready[dev & 63] = true;
+    }
+    static const bool force_wide = getenv("PG_TABLES_WIDE") != nullptr;  // tests: the wide kernels on small tables too
+    if (p.n > kTabMaxPools || force_wide) {
+        if (p.kind == PG_KIND_CHISQ) {
+            int64_t grid = (p.n_loci * 32 + 255) / 256;
+            if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
+            if (grid < 1) grid = 1;
+            chisq_wide_kernel<<<(unsigned)grid, 256, 0, s>>>(p);
+        } else {
+            int64_t grid = (p.n_loci + kFwWarps - 1) / kFwWarps;
+            if (grid > (int64_t)sm_count * 4) grid = (int64_t)sm_count * 4;
+            if (grid < 1) grid = 1;
+            fisher_wide_kernel<<<(unsigned)grid, kFwWarps * 32, 0, s>>>(p);
+        }
+        return cudaGetLastError();
     }
     // register-resident kernels for the common small tables; everything else takes the generic kernel
     if (p.n == 2) {

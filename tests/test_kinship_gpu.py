@@ -277,3 +277,29 @@ def test_c4_shape_gram_and_covariate_scan(ctx):
     n_arb = _cmp_records((beta[:, sample], var[:, sample], pval[:, sample]), (ob[sample].T, ov[sample].T, op[sample].T),
                          "C4 shape m=10", arb=(G[sample], V[:, :10], phen))
     print(f"C4 shape: P={P}, m=0 and m=10 records match on {sample.size} sampled columns ({n_arb} arbitrated)")
+
+
+@pytest.mark.parametrize("n,L,k", [(24, 150, 2), (60, 120, 1)])
+def test_threshold_never_reached_takes_the_n_less_than_p_branch(ctx, n, L, k):
+    """a threshold the cumulative shares never reach leaves n_eigenvecs = n (src/gwas/ols.rs:300-311): X = [1 | V | g]
+    has n + 2 columns for n pools and the reference solves b = X'(XX')^-1 y (ols.rs:67-75); var is rounding noise over
+    a negative n - p, so t is NaN and every p-value is forced to 1 (ols.rs:150-151)"""
+    seed = 0x5EED0004 + 7 * n
+    counts = pb.synth_counts_host(seed, 0, L, n, 4)
+    fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n))
+    phen = pb.synth_phen_host(seed, n, k)
+    kin = pb.Kinship(ctx, n, 4 * L)
+    kin.append_counts(counts, np.arange(4, dtype=np.uint8), fs)
+    P = kin.columns
+    G = kin.get_columns(0, P)
+    kin.gram()
+    m = kin.eig_select(P, 1.5)
+    beta, var, pval = kin.covar_scan(phen)
+    kin.close()
+    om, ob, ov, op = pgo.ols_with_covariate(G, phen, 1.5)
+    assert m == om == n
+    ok = ~np.isnan(ob)
+    assert ok.mean() > 0.9
+    scale = np.maximum(np.abs(ob), np.abs(ob[ok]).mean())
+    assert np.all(np.abs(beta.T - ob)[ok] <= 1e-8 * scale[ok])
+    assert np.all(pval.T[ok] == 1.0) and np.all(op[ok] == 1.0)

@@ -409,10 +409,59 @@ def test_pearson_with_missing_phenotypes(ctx, n, L):
         pb.Scan(ctx, pb.KIND_OLS, fs, n, codes, phen)
 
 
-def test_fisher_refuses_more_than_16_pools(ctx):
-    fs = _fs(np.full(17, 1.0 / 17))
-    with pytest.raises(pb.PgError):
-        pb.Scan(ctx, pb.KIND_FISHER, fs, 17, np.arange(4, dtype=np.uint8))
+def _sparse_counts(rng, L, A, n, mean_total, cover):
+    """count tables for the many-pool Fisher test: a sparse background, a few heavy pools per locus (their rows survive
+    the rescale to a total of 34), optionally one read per pool so that every pool has coverage"""
+    lam = mean_total / (n * min(A, 4))
+    c = np.zeros((L, A, n), dtype=np.uint32)
+    c[:, :min(A, 4)] = rng.poisson(lam, size=(L, min(A, 4), n))
+    heavy = rng.integers(0, n, size=(L, 3))
+    for l in range(0, L, 2):
+        for h in heavy[l]:
+            c[l, :min(A, 4), h] += rng.integers(0, 12 * max(1, n // 10), size=min(A, 4)).astype(np.uint32)
+    if cover:
+        c[:, 0] += 1
+    return c
+
+
+@pytest.mark.parametrize("n,A,L,mean_total,kw", [
+    (17, 4, 1500, 60, {}), (40, 6, 800, 30, {}), (100, 4, 300, 20, {}), (300, 4, 40, 200, {}),
+    (40, 4, 800, 25, dict(min_coverage_depth=0, max_missingness_rate=1.0)),
+    (100, 5, 300, 30, dict(min_coverage_depth=0, max_missingness_rate=1.0))])
+def test_fisher_many_pools(ctx, n, A, L, mean_total, kw):
+    """tables::fisher beyond 16 pools (src/tables/fisher_exact_test.rs:32-130 has no limit): the table is rescaled to a
+    total of at most 34, so only its non-zero rows are enumerated; rescaled (total > 34) and raw tables (pools without
+    coverage allowed), pools whose rescaled row is empty, the last pool empty or not, all-zero rescaled tables"""
+    rng = np.random.default_rng(0xF154 + n + A)
+    full = _sparse_counts(rng, L, A, n, mean_total, cover=not kw)
+    full[::3, :, n - 1] = 0
+    full[::3, 0, n - 1] = 1                                # the last row stays non-zero only through allele A
+    fs = _fs(np.full(n, 1.0 / n), min_allele_frequency=0.0, **kw)
+    codes = np.arange(A, dtype=np.uint8)
+    scan = pb.Scan(ctx, pb.KIND_FISHER, fs, n, codes)
+    dev = scan.run_counts(full)
+    scan.close()
+    st = H.compare_tables(pb.KIND_FISHER, full, codes, fs, dev, label=f"fisher n={n}")
+    assert st["ok"] > 0.5 * L
+    ok = dev.status == pb.LOCUS_OK
+    assert len(np.unique(dev.stats[ok, 0, 0, 3])) > 10     # not only all-zero tables
+    print(st)
+
+
+def test_wide_table_kernels_on_small_tables():
+    """PG_TABLES_WIDE=1 (read once per process) sends tables of up to 16 pools through the many-pool kernels too: the
+    parity cases of the small-table kernels must hold there (C1, the small shapes, C5)"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("PG_TABLES_WIDE"):
+        pytest.skip("already inside the wide-kernel run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PG_TABLES_WIDE="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(root, "tests", "test_scan_gpu.py"),
+                          "-k", "test_c1_tables or test_small_tables or test_c5_tables_synthetic"], env=env, cwd=root,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
+    assert out.returncode == 0, out.stdout[-3000:]
 
 
 @pytest.mark.parametrize("n,A,L,kw", [(17, 4, 3000, {}), (100, 6, 1500, {}), (1000, 4, 300, {}),
@@ -479,3 +528,51 @@ def test_fixup_path_without_ingest_hints():
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=root, env=env, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:]
     assert " passed" in out.stdout
+
+
+@pytest.mark.parametrize("n,A", [(2, 4), (3, 4), (3, 6), (4, 6), (5, 6)])
+def test_fewer_pools_than_coefficients(ctx, n, A):
+    """the reference's n < p branch (src/gwas/ols.rs:67-75, 106-111): b = X'(XX')^-1 y, the minimum-norm interpolating
+    solution; e'e is rounding noise over a negative n - p, so var is a tiny negative number (t = NaN, p forced to 1) or
+    -0 when every residual is exactly zero (p = 0).  beta is checked against the oracle and numpy's pseudo-inverse."""
+    rng = np.random.default_rng(1000 * n + A)
+    L, k = 600, 2
+    counts = rng.integers(1, 60, size=(L, A, n)).astype(np.uint32)
+    counts[rng.random(L) < 0.2, A - 1] = 0                      # some loci with one allele fewer
+    codes = np.arange(A, dtype=np.uint8)
+    fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n), remove_ns=False, min_allele_frequency=0.0)
+    phen = rng.standard_normal((n, k))
+    scan = pb.Scan(ctx, pb.KIND_OLS, fs, n, codes, phen)
+    dev = scan.run_counts(counts)
+    scan.close()
+    ofs = H.oracle_fs(fs)
+    orc = pgo.scan_batch(pgo.SCAN_OLS, counts, codes, phen, ofs, 4)
+    assert ((orc.status == pgo.FILTERED) == (dev.status == pb.LOCUS_FILTERED)).all()
+    assert not (dev.status == pb.LOCUS_UNSUPPORTED).any()
+    under = 0
+    for l in np.nonzero(orc.status == pgo.OK)[0]:
+        m = int(orc.n_out[l])
+        if n >= m + 1:
+            continue
+        under += 1
+        assert dev.status[l] == pb.LOCUS_OK and dev.n_out[l] == m and (dev.alleles[l][:m] == orc.allele[l][:m]).all()
+        X = H._design(counts[l], codes, ofs)
+        cond = np.linalg.cond(X @ X.T)
+        bp = np.linalg.pinv(X) @ phen                             # [p, k] minimum-norm solution
+        for s in range(m):
+            for j in range(k):
+                db, ob, xb = dev.stats[l, s, j, 0], orc.stat[l, s, j], bp[1 + s, j]
+                scale = max(np.abs(bp[:, j]).max(), 1e-300)
+                assert abs(db - xb) <= max(4 * abs(ob - xb), 1e-9 * scale, cond * 1e-15 * scale), (l, s, j, db, ob, xb, cond)
+                dp, op = dev.stats[l, s, j, 3], orc.pval[l, s, j]
+                assert dp in (0.0, 1.0) and op in (0.0, 1.0)
+                dvar = dev.stats[l, s, j, 1]                       # sqrt(var): NaN for var < 0, -0 for var = -0
+                assert np.isnan(dvar) or dvar == 0.0
+                if dp != op:  # only the exact-zero residual case may differ (rounding noise decides e'e == 0)
+                    assert orc.var[l, s, j] == 0.0 or dvar == 0.0, (l, s, j, dp, op)
+    assert under > 100
+    # the loci with n >= p still take the normal equations
+    ge = (orc.status == pgo.OK) & (orc.n_out.astype(int) + 1 < n)
+    if ge.any():
+        sub = np.nonzero(ge)[0]
+        assert np.allclose(dev.stats[sub, 0, 0, 0], orc.stat[sub, 0, 0], rtol=1e-7, atol=1e-9)
