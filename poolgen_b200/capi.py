@@ -710,6 +710,24 @@ class Kinship:
             self._h = C.c_void_p()
 
 
+def _pin_nccl_library():
+    """One libnccl.so.2 per process: the dynamic loader keeps a single object per SONAME, so when this Python process
+    will also import torch (whose bundled NCCL may be newer than the system's), the library must map that same file --
+    PG_NCCL_LIB tells it which (see pg_comm.cu).  A no-op when the variable is set or no bundled NCCL exists."""
+    if os.environ.get("PG_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["PG_NCCL_LIB"] = cand
+                return
+    except (ImportError, ValueError, AttributeError):
+        pass
+
+
 def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
     """pg_shard_range: the contiguous [begin, end) of `rank` (earlier ranks take the larger shards)"""
     b, e = C.c_int64(), C.c_int64()
@@ -718,6 +736,7 @@ def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def nccl_version() -> int:
+    _pin_nccl_library()
     v = C.c_int()
     _check(lib().pg_nccl_version(C.byref(v)), None, "pg_nccl_version")
     return int(v.value)
@@ -733,6 +752,7 @@ class Comm:
 
     @staticmethod
     def init_multi(devices) -> "Comm":
+        _pin_nccl_library()
         devs = (C.c_int * len(devices))(*[int(d) for d in devices])
         ctxs = (C.c_void_p * len(devices))()
         h = C.c_void_p()
@@ -741,6 +761,7 @@ class Comm:
 
     @staticmethod
     def unique_id() -> bytes:
+        _pin_nccl_library()
         buf = C.create_string_buffer(COMM_ID_BYTES)
         _check(lib().pg_comm_unique_id(buf), None, "pg_comm_unique_id")
         return buf.raw
@@ -748,6 +769,7 @@ class Comm:
     @staticmethod
     def init_rank(ctx: Context, uid: bytes, rank: int, world: int) -> "Comm":
         assert len(uid) == COMM_ID_BYTES
+        _pin_nccl_library()
         h = C.c_void_p()
         _check(lib().pg_comm_init_rank(ctx._h, uid, int(rank), int(world), C.byref(h)), ctx._h, "pg_comm_init_rank")
         return Comm(h, [ctx])

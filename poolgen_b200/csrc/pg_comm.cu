@@ -15,6 +15,7 @@
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -41,11 +42,16 @@ struct NcclApi {
 const NcclApi &nccl_api() {
     static const NcclApi api = [] {
         NcclApi a;
+        // PG_NCCL_LIB names the library file explicitly.  A process that will ALSO load another component linked against
+        // a newer libnccl.so.2 (e.g. a Python process importing torch with its bundled NCCL) must point it at that same
+        // file: the dynamic loader keeps one object per SONAME, and whichever copy is mapped first serves both.
         void *lib = nullptr;
-        for (const char *name : {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"}) {
-            lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
-            if (lib) break;
-        }
+        if (const char *forced = getenv("PG_NCCL_LIB")) lib = dlopen(forced, RTLD_NOW | RTLD_LOCAL);
+        if (!lib)
+            for (const char *name : {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"}) {
+                lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+                if (lib) break;
+            }
         if (!lib) {
             a.why = "libnccl.so.2 could not be loaded";
             return a;

@@ -482,6 +482,9 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
 #pragma unroll
                 for (int v = 0; v < NV; v++)
                     if (v >= nq) gy[v] = warp_sum_fixed(sy[v]);
+                // the column lies in span([1 | PCs]) to working precision (a monomorphic locus gives g = 1 or g = 0):
+                // the reference's X'X is singular (exactly so for those two) and inv() fails -> NaN (ols.rs:359-364)
+                if (ggc <= fmax(64.0, p.nf * p.nf) * kEps * kEps * gg) ggc = 0.0;  // below (n eps)^2 the reference's pivot is noise
             }
             // lane j < k finishes phenotype j
             double b = nan(""), vb = nan(""), pv = nan("");
@@ -561,6 +564,7 @@ __global__ void __launch_bounds__(256) covar_generic_kernel(const CovarParams p)
             double s2 = 0.0;
             for (int r = lane; r < p.n; r += 32) s2 = fma(gcol[r], gcol[r], s2);
             ggc = warp_sum_fixed(s2);
+            if (ggc <= fmax(64.0, p.nf * p.nf) * kEps * kEps * gg) ggc = 0.0;  // g in span([1 | PCs]): singular X'X, NaN like the reference
             for (int j = 0; j < k; j++) {
                 const double *yt = p.V + (size_t)(nq + j) * ldg;
                 double a = 0.0;

@@ -248,7 +248,11 @@ def compare_tables(kind, counts, codes, fs, dev, n_threads=8, label=""):
         e_p = np.abs(d_p - o_p) / (np.abs(o_p) + P_FLOOR / PTOL)
     both_nan_s = np.isnan(o_s) & np.isnan(d_s)
     both_nan_p = np.isnan(o_p) & np.isnan(d_p)
-    assert ((e_s <= RTOL) | both_nan_s | ((o_s == 0) & (np.abs(d_s) < 1e-300))).all(), f"{label}: statistic differs, max rel {np.nanmax(e_s)}"
+    # a chi-square of identical rows is 0 in exact arithmetic and rounding noise (~1e-32) in any f64 evaluation: the
+    # one-thread kernels reproduce the reference's noise, the one-warp-per-locus kernels have their own
+    floor = 1e-24 if kind == pb.KIND_CHISQ else 0.0
+    assert ((e_s <= RTOL) | both_nan_s | ((o_s == 0) & (np.abs(d_s) < 1e-300)) |
+            (np.abs(d_s - o_s) <= floor)).all(), f"{label}: statistic differs, max rel {np.nanmax(e_s)}"
     assert ((e_p <= PTOL) | both_nan_p).all(), f"{label}: p differs, max rel {np.nanmax(e_p)}"
     return dict(loci=counts.shape[0], ok=int(o_ok.sum()),
                 max_rel_stat=float(np.nanmax(e_s)) if idx.size else 0.0,

@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 import poolgen_b200 as pb
+from oracle import pgo
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
