@@ -493,7 +493,8 @@ def text_numbers(ctx, pb, n_threads=2):
             lab.text = C.cast(host[i % 2].ctypes.data, C.c_char_p)
             lab.line_offsets = C.cast(po, C.POINTER(C.c_uint64))
             nb = C.c_size_t()
-            rc = lib.pg_format_rows(pb.KIND_OLS, C.byref(r), C.byref(lab), fmt_threads, outs[t], cap, C.byref(nb))
+            rc = lib.pg_format_rows_ex(pb.KIND_OLS, C.byref(r), C.byref(lab), 1 if to_csv == 2 else 0, N_POOLS,
+                                       fmt_threads, outs[t], cap, C.byref(nb))
             assert rc == 0, rc
             rows[t] += nb.value
 
@@ -518,12 +519,15 @@ def text_numbers(ctx, pb, n_threads=2):
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
-    timed(3, True)
-    dt_rec = min(timed(slabs_per_thread, False) for _ in range(2))
-    dt_csv = 1e30
+    timed(3, 1)
+    dt_rec = min(timed(slabs_per_thread, 0) for _ in range(2))
+    dt_csv = dt_exact = 1e30
     for _ in range(2):
         rows[:] = [0] * n_threads
-        dt_csv = min(dt_csv, timed(slabs_per_thread, True))
+        dt_exact = min(dt_exact, timed(slabs_per_thread, 2))
+    for _ in range(2):
+        rows[:] = [0] * n_threads
+        dt_csv = min(dt_csv, timed(slabs_per_thread, 1))
     for sc in scans:
         sc.close()
     ctx.pinned_free(hptr)
@@ -536,7 +540,9 @@ def text_numbers(ctx, pb, n_threads=2):
             "e2e_text_to_csv": {"loci_per_s": n_loci / dt_csv, "text_gb_per_s": text_bytes / dt_csv / 1e9,
                                 "csv_bytes": int(sum(rows)), "csv_gb_per_s": sum(rows) / dt_csv / 1e9,
                                 "format_threads": fmt_threads * n_threads,
-                                "note": note + " -> pg_format_rows (the reference's CSV rows)"}}
+                                "exact_p_loci_per_s": n_loci / dt_exact,
+                                "note": note + " -> pg_format_rows (the reference's CSV rows); exact_p = "
+                                               "PG_FORMAT_EXACT_P, p re-derived on the host with the reference's arithmetic"}}
 
 
 FP64_DMMA_PEAK_TFLOPS = 37.1  # tools/fp64_probe.cu on this pool's B200 (profiles/fp64_probe_r1.txt): mma.sync m8n8k4 f64

@@ -138,6 +138,7 @@ extern "C" {
     // ---- the reference's CSV rows
     pub fn pg_format_header(kind: c_int, out: *mut c_char, capacity: usize, n_bytes: *mut usize) -> c_int;
     pub fn pg_format_rows(kind: c_int, res: *const pg_results, labels: *const pg_row_labels, n_threads: c_int, out: *mut c_char, capacity: usize, n_bytes: *mut usize) -> c_int;
+    pub fn pg_format_rows_ex(kind: c_int, res: *const pg_results, labels: *const pg_row_labels, flags: c_int, n_pools: c_int, n_threads: c_int, out: *mut c_char, capacity: usize, n_bytes: *mut usize) -> c_int;
     pub fn pg_format_kinship_rows(n_columns: i64, k: c_int, chromosome: *const *const c_char, position: *const u64, allele: *const *const c_char, beta: *const f64, pval: *const f64, n_threads: c_int, out: *mut c_char, capacity: usize, n_bytes: *mut usize) -> c_int;
     pub fn pg_sort_loci(labels: *const pg_row_labels, n_loci: i64, order_out: *mut i64) -> c_int;
     pub fn pg_format_frequency_header(pool_names: *const *const c_char, n_pools: c_int, out: *mut c_char, capacity: usize, n_bytes: *mut usize) -> c_int;

@@ -256,6 +256,14 @@ int pg_format_header(int kind, char *out, size_t capacity, size_t *n_bytes);
  * (PG_ERR_ARG, nothing written) */
 int pg_format_rows(int kind, const pg_results *res, const pg_row_labels *labels, int n_threads, char *out,
                    size_t capacity, size_t *n_bytes);
+/* the same with options.  PG_FORMAT_EXACT_P (OLS / CORR): the printed p-value is re-derived on the host from the record's
+ * t statistic with the reference's own arithmetic -- statrs' StudentsT::cdf through its Lentz continued fraction, df =
+ * n_pools - 1 (src/gwas/ols.rs:139,153) or n_pools - 2 (src/gwas/correlation_test.rs:65-66) -- instead of the device's
+ * table value (accurate to ~1e-12, inside the record tolerance of 1e-6 but enough to move a 12th printed decimal).  Rows
+ * then differ from the reference's only where the t statistic itself differs in its last digits.  About 0.3 us per row. */
+#define PG_FORMAT_EXACT_P 1
+int pg_format_rows_ex(int kind, const pg_results *res, const pg_row_labels *labels, int flags, int n_pools,
+                      int n_threads, char *out, size_t capacity, size_t *n_bytes);
 /* rows of ols_iter_with_kinship: phenotype outer, column inner; beta / pval as pg_kin_covar_scan returns them
  * ([k][n_columns]); chromosome / position / allele are indexed by the column ordinal exactly like
  * src/gwas/ols.rs:421-424 indexes the label vectors of GenotypesAndPhenotypes (whose entry 0 is "intercept") */

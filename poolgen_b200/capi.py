@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "pg_kin_open", "pg_kin_close", "pg_kin_reset", "pg_kin_columns", "pg_kin_append_columns", "pg_kin_append_counts",
     "pg_kin_last_labels", "pg_kin_append_sync_text", "pg_kin_text_labels", "pg_kin_synth", "pg_kin_get_columns", "pg_kin_gram", "pg_kin_gram_time", "pg_kin_partial",
     "pg_kin_partial_get", "pg_kin_partial_set", "pg_kin_eig_select", "pg_kin_eigvals", "pg_kin_set_covariates",
-    "pg_kin_covar_scan", "pg_format_header", "pg_format_rows", "pg_format_kinship_rows", "pg_format_f64", "pg_sort_loci",
+    "pg_kin_covar_scan", "pg_format_header", "pg_format_rows", "pg_format_rows_ex", "pg_format_kinship_rows", "pg_format_f64", "pg_sort_loci",
     "pg_format_frequency_header", "pg_format_frequency_rows",
     "pg_shard_range", "pg_nccl_version", "pg_init_multi", "pg_comm_unique_id", "pg_comm_init_rank", "pg_comm_info",
     "pg_comm_destroy", "pg_kin_allreduce", "pg_kin_copy_covariates",
@@ -159,6 +159,8 @@ def lib():
             "pg_kin_copy_covariates": (i, [vp, vp]),
             "pg_format_header": (i, [i, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
             "pg_format_rows": (i, [i, C.POINTER(_Results), C.POINTER(_RowLabels), i, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+            "pg_format_rows_ex": (i, [i, C.POINTER(_Results), C.POINTER(_RowLabels), i, i, i, vp, C.c_size_t,
+                                      C.POINTER(C.c_size_t)]),
             "pg_format_kinship_rows": (i, [i64, i, C.POINTER(C.c_char_p), vp, C.POINTER(C.c_char_p), vp, vp, i, vp,
                                            C.c_size_t, C.POINTER(C.c_size_t)]),
             "pg_format_f64": (i, [C.c_double, i, vp, C.c_size_t]),
@@ -266,11 +268,16 @@ def format_f64(x: float, n_digits: int = 0) -> str:
     return buf.raw[:n].decode()
 
 
+FORMAT_EXACT_P = 1
+
+
 def format_rows(kind: int, results, positions, text: bytes | None = None, line_offsets=None, chr_names=None,
-                chr_index=None, n_threads: int = 0) -> bytes:
+                chr_index=None, n_threads: int = 0, exact_p_pools: int = 0) -> bytes:
     """CSV rows of the per-locus callbacks for a slab of records (`results`: ScanResults or the raw pg_results of
     Scan.collect(copy=False)).  Chromosome names come from the sync text the loci were parsed from (text +
-    line_offsets, as Batch.upload_sync_text returns them) or from chr_names[chr_index[locus]]."""
+    line_offsets, as Batch.upload_sync_text returns them) or from chr_names[chr_index[locus]].
+    exact_p_pools = n_pools > 0: PG_FORMAT_EXACT_P, the printed p-values are re-derived from t with the reference's own
+    arithmetic (ols_iter / pearson_corr)."""
     keep = None
     if isinstance(results, ScanResults):
         results, keep = results.to_c()
@@ -288,14 +295,16 @@ def format_rows(kind: int, results, positions, text: bytes | None = None, line_o
         lab.chr_index = idx.ctypes.data_as(C.POINTER(C.c_uint32))
     n_threads = n_threads or (os.cpu_count() or 1)
     need = C.c_size_t()
-    rc = lib().pg_format_rows(int(kind), C.byref(results), C.byref(lab), n_threads, None, 0, C.byref(need))
+    flags = FORMAT_EXACT_P if exact_p_pools > 0 else 0
+    rc = lib().pg_format_rows_ex(int(kind), C.byref(results), C.byref(lab), flags, int(exact_p_pools), n_threads, None, 0,
+                                 C.byref(need))
     if need.value == 0:
         if rc != PG_OK:
             raise PgError("pg_format_rows: bad arguments")
         return b""
     buf = C.create_string_buffer(need.value)
-    _check(lib().pg_format_rows(int(kind), C.byref(results), C.byref(lab), n_threads, buf, need.value, C.byref(need)),
-           None, "pg_format_rows")
+    _check(lib().pg_format_rows_ex(int(kind), C.byref(results), C.byref(lab), flags, int(exact_p_pools), n_threads, buf,
+                                   need.value, C.byref(need)), None, "pg_format_rows_ex")
     del keep
     return buf.raw[:need.value]
 

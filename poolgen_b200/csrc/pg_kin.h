@@ -1,5 +1,6 @@
 // pg_kin.h -- the handle of the ols_iter_with_kinship path (shared by pg_kinship.cu and pg_comm.cu; not part of the ABI)
 #pragma once
+#include <thread>
 #include <vector>
 
 #include "pg_internal.h"
@@ -43,5 +44,9 @@ struct pg_kin {
     size_t counts_bytes = 0;
     double *d_w = nullptr;
     pg::TextScratch *text = nullptr;  // sync text parsed on the device (pg_kin_append_sync_text)
+    // eigen step: cuSOLVER is mapped and its handle created by a background thread started in pg_kin_open
+    std::thread warm;
+    bool warm_started = false;
+    void *solver = nullptr;  // cusolverDnHandle_t
 };
 

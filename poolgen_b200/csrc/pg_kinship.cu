@@ -605,6 +605,43 @@ __global__ void __launch_bounds__(256) covar_generic_kernel(const CovarParams p)
 // ================================================================================================================
 // C ABI
 // ================================================================================================================
+// cuSOLVER is loaded on first use: linking it would make every process that opens this library map cuSOLVER, cuSPARSE,
+// cuBLAS, cuBLASLt and nvJitLink (1.5 GB of shared objects, minutes on a cold file system) although only the eigen
+// step of ols_iter_with_kinship calls into it
+namespace {
+struct CusolverApi {
+    cusolverStatus_t (*create)(cusolverDnHandle_t *) = nullptr;
+    cusolverStatus_t (*destroy)(cusolverDnHandle_t) = nullptr;
+    cusolverStatus_t (*set_stream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+    cusolverStatus_t (*syevd_buffer)(cusolverDnHandle_t, cusolverEigMode_t, cublasFillMode_t, int, const double *, int,
+                                     const double *, int *) = nullptr;
+    cusolverStatus_t (*syevd)(cusolverDnHandle_t, cusolverEigMode_t, cublasFillMode_t, int, double *, int, double *,
+                              double *, int, int *) = nullptr;
+    bool ok = false;
+};
+const CusolverApi &cusolver_api() {
+    static const CusolverApi api = [] {
+        CusolverApi a;
+        void *lib = nullptr;
+        for (const char *name : {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so",
+                                 "/usr/local/cuda/lib64/libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (lib) break;
+        }
+        if (!lib) return a;
+        a.create = reinterpret_cast<decltype(a.create)>(dlsym(lib, "cusolverDnCreate"));
+        a.destroy = reinterpret_cast<decltype(a.destroy)>(dlsym(lib, "cusolverDnDestroy"));
+        a.set_stream = reinterpret_cast<decltype(a.set_stream)>(dlsym(lib, "cusolverDnSetStream"));
+        a.syevd_buffer = reinterpret_cast<decltype(a.syevd_buffer)>(dlsym(lib, "cusolverDnDsyevd_bufferSize"));
+        a.syevd = reinterpret_cast<decltype(a.syevd)>(dlsym(lib, "cusolverDnDsyevd"));
+        a.ok = a.create && a.destroy && a.set_stream && a.syevd_buffer && a.syevd;
+        return a;
+    }();
+    return api;
+}
+}  // namespace
+
+
 static int kfail(pg_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
@@ -624,6 +661,18 @@ static int kfail(pg_ctx *ctx, int code, const char *fmt, ...) {
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 extern "C" {
+
+// The eigen step's one-off costs -- mapping cuSOLVER and its dependencies (1.5 GB of shared objects) and creating the
+// handle, 0.3-3 s on a cold box -- start in a background thread with the first pg_kin_gram (only ols_iter_with_kinship
+// forms a Gram matrix; the sync2csv loader never pays), so they overlap the Gram kernel and the exchange step instead
+// of sitting in front of the first pg_kin_eig_select.
+static void kin_warm_solver(pg_kin *h) {
+    const CusolverApi &sol = cusolver_api();
+    if (!sol.ok) return;
+    if (cudaSetDevice(h->ctx->device) != cudaSuccess) return;
+    cusolverDnHandle_t cs = nullptr;
+    if (sol.create(&cs) == CUSOLVER_STATUS_SUCCESS) h->solver = cs;
+}
 
 int pg_kin_open(pg_ctx *ctx, int n_pools, int64_t max_columns, pg_kin **out) {
     if (!ctx || !out || n_pools < 2 || max_columns < 1) return kfail(ctx, PG_ERR_ARG, "pg_kin_open: bad argument");
@@ -656,6 +705,8 @@ int pg_kin_open(pg_ctx *ctx, int n_pools, int64_t max_columns, pg_kin **out) {
 
 int pg_kin_close(pg_kin *h) {
     if (!h) return PG_OK;
+    if (h->warm.joinable()) h->warm.join();
+    if (h->solver) cusolver_api().destroy(static_cast<cusolverDnHandle_t>(h->solver));
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_G);
     cudaFree(h->d_K);
@@ -886,6 +937,10 @@ int pg_kin_get_columns(pg_kin *h, int64_t first, int64_t count, double *out) {
 
 static int gram_launch(pg_kin *h) {
     pg_ctx *ctx = h->ctx;
+    if (!h->warm_started) {
+        h->warm_started = true;
+        h->warm = std::thread(kin_warm_solver, h);
+    }
     const int ntiles = h->nt * (h->nt + 1) / 2;
     const int64_t P_pad = round_up(std::max<int64_t>(h->P, 1), pg::kKC);
     // column slices: enough (slice, tile) items for ~8 waves over the SMs, each slice a multiple of kKC columns
@@ -966,42 +1021,6 @@ int pg_kin_partial_set(pg_kin *h, const double *in) {
 }
 
 // K = (sum of the partial Gram matrices) / P_total; eigen-decomposition; number of PCs by the reference's rule
-// cuSOLVER is loaded on first use: linking it would make every process that opens this library map cuSOLVER, cuSPARSE,
-// cuBLAS, cuBLASLt and nvJitLink (1.5 GB of shared objects, minutes on a cold file system) although only the eigen
-// step of ols_iter_with_kinship calls into it
-namespace {
-struct CusolverApi {
-    cusolverStatus_t (*create)(cusolverDnHandle_t *) = nullptr;
-    cusolverStatus_t (*destroy)(cusolverDnHandle_t) = nullptr;
-    cusolverStatus_t (*set_stream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
-    cusolverStatus_t (*syevd_buffer)(cusolverDnHandle_t, cusolverEigMode_t, cublasFillMode_t, int, const double *, int,
-                                     const double *, int *) = nullptr;
-    cusolverStatus_t (*syevd)(cusolverDnHandle_t, cusolverEigMode_t, cublasFillMode_t, int, double *, int, double *,
-                              double *, int, int *) = nullptr;
-    bool ok = false;
-};
-const CusolverApi &cusolver_api() {
-    static const CusolverApi api = [] {
-        CusolverApi a;
-        void *lib = nullptr;
-        for (const char *name : {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so",
-                                 "/usr/local/cuda/lib64/libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so"}) {
-            lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
-            if (lib) break;
-        }
-        if (!lib) return a;
-        a.create = reinterpret_cast<decltype(a.create)>(dlsym(lib, "cusolverDnCreate"));
-        a.destroy = reinterpret_cast<decltype(a.destroy)>(dlsym(lib, "cusolverDnDestroy"));
-        a.set_stream = reinterpret_cast<decltype(a.set_stream)>(dlsym(lib, "cusolverDnSetStream"));
-        a.syevd_buffer = reinterpret_cast<decltype(a.syevd_buffer)>(dlsym(lib, "cusolverDnDsyevd_bufferSize"));
-        a.syevd = reinterpret_cast<decltype(a.syevd)>(dlsym(lib, "cusolverDnDsyevd"));
-        a.ok = a.create && a.destroy && a.set_stream && a.syevd_buffer && a.syevd;
-        return a;
-    }();
-    return api;
-}
-}  // namespace
-
 int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) {
     if (!h || P_total < 0) return PG_ERR_ARG;
     if (P_total == 0) P_total = h->P_total > 0 ? h->P_total : h->P;  // the count pg_kin_allreduce summed, else the resident columns
@@ -1012,13 +1031,18 @@ int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) 
     KCUDA(ctx, cudaStreamSynchronize(h->stream));
     double *dA = nullptr, *dW = nullptr, *dwork = nullptr;
     int *dinfo = nullptr;
-    cusolverDnHandle_t cs = nullptr;
     int rc = PG_OK;
     std::vector<double> A((size_t)n * n), W(n);
+    if (h->warm.joinable()) h->warm.join();  // the handle the background thread of pg_kin_open created
     const CusolverApi &sol = cusolver_api();
     if (!sol.ok) return kfail(ctx, PG_ERR_CUDA, "pg_kin_eig_select: libcusolver could not be loaded (%s)", dlerror() ? dlerror() : "missing symbols");
+    if (!h->solver) {
+        cusolverDnHandle_t made = nullptr;
+        if (sol.create(&made) != CUSOLVER_STATUS_SUCCESS) return kfail(ctx, PG_ERR_CUDA, "cusolverDnCreate failed");
+        h->solver = made;
+    }
+    cusolverDnHandle_t cs = static_cast<cusolverDnHandle_t>(h->solver);
     do {
-        if (sol.create(&cs) != CUSOLVER_STATUS_SUCCESS) { rc = kfail(ctx, PG_ERR_CUDA, "cusolverDnCreate failed"); break; }
         sol.set_stream(cs, h->stream);
         if (cudaMalloc(&dA, (size_t)n * n * 8) != cudaSuccess || cudaMalloc(&dW, (size_t)n * 8) != cudaSuccess ||
             cudaMalloc(&dinfo, 4) != cudaSuccess) { rc = kfail(ctx, PG_ERR_CUDA, "pg_kin_eig_select: out of device memory"); break; }
@@ -1040,7 +1064,6 @@ int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) 
     cudaFree(dW);
     cudaFree(dwork);
     cudaFree(dinfo);
-    if (cs) sol.destroy(cs);
     if (rc) return rc;
     // syevd returns ascending eigenvalues, column j of A (column-major) = eigenvector j; the reference walks them
     // "sorted from high to low" (ols.rs:296)

@@ -18,6 +18,9 @@
 #include <thread>
 #include <vector>
 
+#include <cfloat>
+
+#include "pg_statrs_host.h"
 #include "poolgen_cuda.h"
 
 namespace {
@@ -164,7 +167,8 @@ struct Labels {
     }
 };
 
-void format_range(int kind, const pg_results *res, const pg_row_labels *lab, int64_t lo, int64_t hi, std::string &dst) {
+void format_range(int kind, const pg_results *res, const pg_row_labels *lab, int64_t lo, int64_t hi, std::string &dst,
+                  int flags = 0, int n_pools = 0) {
     // rows are appended to a string that lives on this thread's stack and handed over once: the std::string headers of
     // the per-thread pieces sit side by side in one vector, and appending through them would bounce their cache line
     // between the cores on every row
@@ -176,6 +180,11 @@ void format_range(int kind, const pg_results *res, const pg_row_labels *lab, int
     const Labels L{lab};
     const int S = res->n_slots, k = res->n_phen;
     const Rounder r6(6), r8(8), r12(12);
+    // PG_FORMAT_EXACT_P: the p-value is re-derived on the host from the record's t statistic with the reference's own
+    // arithmetic (statrs' continued fraction, df = n - 1 for ols_iter, n - 2 for pearson_corr)
+    const bool exact_p = (flags & PG_FORMAT_EXACT_P) && (kind == PG_KIND_OLS || kind == PG_KIND_CORR) &&
+                         (double)n_pools - (kind == PG_KIND_OLS ? 1.0 : 2.0) > 0.0;
+    const pg::statrs::TwoSidedT tail(exact_p ? (double)n_pools - (kind == PG_KIND_OLS ? 1.0 : 2.0) : 1.0);
     char line[1024];
     out.reserve((size_t)(hi - lo) * 64 * (size_t)(S * k > 0 ? S * k : 1) / 2 + 4096);
     for (int64_t l = lo; l < hi; l++) {
@@ -212,7 +221,11 @@ void format_range(int kind, const pg_results *res, const pg_row_labels *lab, int
                     *o++ = ',';
                     o = r6.put(st[0], o);
                     *o++ = ',';
-                    o = (kind == PG_KIND_OLS) ? r12.put(st[3], o) : put_f64(st[3], o);
+                    double pv = st[3];
+                    // a finite or infinite t: the reference's formula (ols.rs:148-154, correlation_test.rs:62-66);
+                    // a NaN t marks the special cases the record already carries (p forced to 1, eps or NaN)
+                    if (exact_p && st[2] == st[2] && fabs(st[2]) > DBL_EPSILON) pv = tail(fabs(st[2]));
+                    o = (kind == PG_KIND_OLS) ? r12.put(pv, o) : put_f64(pv, o);
                     *o++ = '\n';
                     out.append(line, (size_t)(o - line));
                 }
@@ -269,6 +282,11 @@ int pg_format_header(int kind, char *out, size_t capacity, size_t *n_bytes) {
 
 int pg_format_rows(int kind, const pg_results *res, const pg_row_labels *labels, int n_threads, char *out,
                    size_t capacity, size_t *n_bytes) {
+    return pg_format_rows_ex(kind, res, labels, 0, 0, n_threads, out, capacity, n_bytes);
+}
+
+int pg_format_rows_ex(int kind, const pg_results *res, const pg_row_labels *labels, int flags, int n_pools,
+                      int n_threads, char *out, size_t capacity, size_t *n_bytes) {
     if (!res || !labels || !labels->positions || kind < PG_KIND_OLS || kind > PG_KIND_FISHER) return PG_ERR_ARG;
     if (labels->text ? !labels->line_offsets : (!labels->chr_names || !labels->chr_index)) return PG_ERR_ARG;
     const int64_t L = res->n_loci;
@@ -278,12 +296,12 @@ int pg_format_rows(int kind, const pg_results *res, const pg_row_labels *labels,
     if (T < 1) T = 1;
     std::vector<std::string> parts((size_t)T);
     if (T == 1) {
-        format_range(kind, res, labels, 0, L, parts[0]);
+        format_range(kind, res, labels, 0, L, parts[0], flags, n_pools);
     } else {
         std::vector<std::thread> th;
         for (int t = 0; t < T; t++) {
             const int64_t lo = L * t / T, hi = L * (t + 1) / T;
-            th.emplace_back([=, &parts] { format_range(kind, res, labels, lo, hi, parts[(size_t)t]); });
+            th.emplace_back([=, &parts] { format_range(kind, res, labels, lo, hi, parts[(size_t)t], flags, n_pools); });
         }
         for (auto &x : th) x.join();
     }

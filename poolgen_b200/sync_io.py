@@ -153,11 +153,14 @@ def _chunk_worker(ctx: Context, kind: int, fs: FilterStats, n_pools: int, phen, 
             lab.text = C.cast(bufs[bi].ctypes.data, C.c_char_p)
             lab.line_offsets = C.cast(po, C.POINTER(C.c_uint64))
             need = C.c_size_t()
-            lib.pg_format_rows(kind, C.byref(res), C.byref(lab), fmt_threads, None, 0, C.byref(need))
+            # the output file carries the reference's own p-value digits (PG_FORMAT_EXACT_P)
+            lib.pg_format_rows_ex(kind, C.byref(res), C.byref(lab), capi.FORMAT_EXACT_P, scan.n_pools, fmt_threads,
+                                  None, 0, C.byref(need))
             if need.value:
                 rows = C.create_string_buffer(need.value)
-                capi._check(lib.pg_format_rows(kind, C.byref(res), C.byref(lab), fmt_threads, rows, need.value,
-                                               C.byref(need)), ctx._h, "pg_format_rows")
+                capi._check(lib.pg_format_rows_ex(kind, C.byref(res), C.byref(lab), capi.FORMAT_EXACT_P, scan.n_pools,
+                                                  fmt_threads, rows, need.value, C.byref(need)), ctx._h,
+                            "pg_format_rows_ex")
                 out.extend(rows.raw[:need.value])
 
         with open(fname, "rb", buffering=0) as fh:

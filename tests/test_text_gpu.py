@@ -193,7 +193,7 @@ def test_c1_text_in_csv_out(ctx, kind):
         expect.append(line)
     assert skipped < 0.02 * L
     expect = "".join(expect)
-    got = pb.format_rows(kind, rec, p, text=text, line_offsets=off, n_threads=4).decode()
+    got = pb.format_rows(kind, rec, p, text=text, line_offsets=off, n_threads=4, exact_p_pools=5).decode()
     gl, el = got.strip().split("\n"), expect.strip().split("\n")
     assert len(gl) == len(el) > 6000
     n_text = 3 if not regression else 3
@@ -221,7 +221,8 @@ def test_c1_text_in_csv_out(ctx, kind):
             ill += 1
     # ols_iter prints rounded numbers (8 / 6 / 12 digits): nearly every row is the same text; the other analyses print
     # 17 significant digits of the mean frequency and of p, where a last-bit difference shows
-    assert ill <= 0.01 * len(el) and (kind != pb.KIND_OLS or same >= 0.9 * len(el)), (same, ill, len(el))
+    # with PG_FORMAT_EXACT_P the p-value digits are the reference's own for the device's t
+    assert ill <= 0.01 * len(el) and (kind != pb.KIND_OLS or same >= 0.95 * len(el)), (same, ill, len(el))
     print(f"kind {kind}: {same} of {len(el)} rows identical text")
 
 

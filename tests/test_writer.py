@@ -213,3 +213,31 @@ def test_sync2csv_rows_c1(keep_p_minus_1):
                                      chr_names=names, chr_index=idx).decode().split("\n")
     assert plain[0].startswith(f"{chroms[labels[0][0]]},{pos[labels[0][0]]},{'ATCGND'[labels[0][1]]},")
     assert pb.format_frequency_header(["Pop1", "Pop2", "Pop3"]) == b"#chr,pos,allele,Pop1,Pop2,Pop3\n"
+
+
+@pytest.mark.parametrize("n,L", [(100, 1200), (1000, 150), (5, 1500)])
+def test_exact_p_option_reprints_the_reference_digits(n, L):
+    """PG_FORMAT_EXACT_P: the writer re-derives p from the record's t statistic with the reference's own arithmetic
+    (statrs' continued fraction, host libm).  Records whose p was deliberately spoiled in the 10th significant digit
+    (the device's table is smooth to ~1e-12) come out with the oracle's lines, text for text."""
+    k = 2
+    counts = pb.synth_counts_host(0xE1AC7 + n, 0, L, n, 4)
+    phen = pb.synth_phen_host(0xE1AC7, n, k)
+    fs = pgo.FilterStats(pool_sizes=np.full(n, 1.0 / n))
+    codes = np.arange(4, dtype=np.uint8)
+    r = pgo.scan_batch(pgo.SCAN_OLS, counts, codes, phen, fs, n_threads=4)
+    S = 3
+    st = np.full((L, S, k, 4), np.nan)
+    st[..., 0] = r.stat[:, :S, :k]
+    st[..., 2] = r.t[:, :S, :k]
+    st[..., 3] = r.pval[:, :S, :k] * (1.0 + 3e-10)
+    status = np.where(r.status < 0, pb.LOCUS_PANIC, r.status).astype(np.uint8)
+    rec = pb.ScanResults(status, r.n_out, r.allele, np.ascontiguousarray(r.freq_mean[:, :S]), st)
+    pos = np.arange(1, L + 1)
+    got = pb.format_rows(pb.KIND_OLS, rec, pos, chr_names=["chr1"], chr_index=np.zeros(L, np.uint32), n_threads=3,
+                         exact_p_pools=n).decode()
+    spoiled = pb.format_rows(pb.KIND_OLS, rec, pos, chr_names=["chr1"], chr_index=np.zeros(L, np.uint32), n_threads=3).decode()
+    expect = "".join(pgo.format_ols_lines("chr1", l + 1, pgo.ols_iterate(counts[l].T.astype(np.uint64), codes, phen, fs))
+                     for l in range(L))
+    assert got == expect and got.count("\n") > L
+    assert spoiled != expect
