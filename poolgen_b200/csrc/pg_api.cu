@@ -214,7 +214,7 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
             delete s;  // StudentsT::new(0,1,0).unwrap() panics (src/gwas/ols.rs:139)
             return fail(ctx, PG_ERR_UNSUPPORTED, "pg_scan_open: ols_iter needs at least 2 pools");
         }
-        s->ln_beta = s->df > 0.0 ? lgamma(s->df / 2.0 + 0.5) - lgamma(s->df / 2.0) - lgamma(0.5) : 0.0;
+        s->ln_beta = s->df > 0.0 ? pg::statrs::ln_gamma(s->df / 2.0 + 0.5) - pg::statrs::ln_gamma(s->df / 2.0) - pg::statrs::ln_gamma(0.5) : 0.0;
         // the phenotype (and weight) vectors of a pass stay resident in shared memory next to the warps' rings: at
         // least one phenotype per pass has to fit beside ~8 warps of 16 KB
         if ((size_t)2 * np * 8 > 96 * 1024) {

@@ -32,6 +32,8 @@ struct pg_kin {
     double *d_res = nullptr;  // [3][k][P]
     double *h_res = nullptr;  // pinned
     size_t res_elems = 0;
+    void *d_defer = nullptr;  // covariate scan: [count | columns left to the two-pass kernel]
+    size_t defer_bytes = 0;
     // loader scratch
     uint32_t *d_sel = nullptr;
     int64_t *d_off = nullptr;

@@ -17,6 +17,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -380,6 +381,9 @@ struct CovarParams {
     // phenotypes (Woodbury on the rank-2 update); var = (e'e / -2) (...) is rounding noise over a negative number, so
     // t is NaN and p is forced to 1 (ols.rs:150-151)
     int minnorm;
+    int y0;            // covar_mma_kernel: first phenotype of this pass (p.k counts the phenotypes of the pass)
+    int64_t *defer_list;     // covar_mma_kernel: columns whose centred g'g is lost to cancellation, finished by
+    unsigned *defer_count;   //   covar_generic_kernel (two-pass form); covar_generic_kernel: the columns to process
     double nf, sqrt_n;
     double sy[kMaxPhenPerPass * 4];  // sum of the raw phenotype
     const void *ptab;
@@ -415,7 +419,10 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
     const int nq = p.nq, k = p.k;
-    for (int64_t c0 = warp * C; c0 < p.P; c0 += nwarps * C) {
+    // C = 1 with a column list: the columns the DMMA kernel left to the two-pass form
+    const int64_t n_items = (C == 1 && p.defer_list) ? (int64_t)*p.defer_count : p.P;
+    for (int64_t i0 = warp * C; i0 < n_items; i0 += nwarps * C) {
+        const int64_t c0 = (C == 1 && p.defer_list) ? p.defer_list[i0] : i0;
         double accs[C][NV], ggs[C];
 #pragma unroll
         for (int cc = 0; cc < C; cc++) {
@@ -520,6 +527,149 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
     }
 }
 
+// ---- covariate scan with selected PCs as a blocked FP64 contraction -----------------------------------------------
+// With m covariates the per-column work is U = V'g for the NV = 1 + m + k vectors (Q columns, then y~): a NV x n by
+// n x P contraction.  As per-warp dot products every element of g costs NV shared-memory operand loads (m = 10: 0.35 of
+// the HBM roofline, shared-memory bandwidth and issue bound).  Here a warp owns 8 allele columns and forms
+// U[v][c] with mma.sync.m8n8k4.f64 (SASS DMMA): M = vectors (MT tiles of 8), N = the 8 columns, K = pools.
+// The sum over pools may take the pools in any order as long as both operands agree: of a 16-pool block lane (g, t)
+// holds pools {2t, 2t+1, 8+2t, 8+2t+1} of its column g -- two 128-bit loads straight from global memory (G is streamed
+// once, no staging: the shared memory belongs to V; the four lanes of a column cover 64 contiguous bytes per request,
+// i.e. whole sectors) -- and the matching elements of vector row g from shared memory (pitch = 8 mod 16 doubles:
+// conflict-free LDS.128); DMMA number s of a block contracts the s-th of those pools.  Two accumulator sets per M tile
+// keep four independent DMMA chains per warp; g'g accumulates beside it.  Every U[v][c] ends up in exactly one lane (no
+// cross-lane reduction); a per-warp scratch hands the 8 columns' sums to the lanes that finish (column, phenotype)
+// pairs.  Columns whose centred g'g is lost to cancellation (nearly constant columns) go to a list that
+// covar_kernel<NV, 1> finishes in its two-pass form -- the streaming kernel carries no slow path.
+// Measured alternatives: a register double buffer (next trip's loads issued before the DMMAs), L2 bulk
+// prefetches ahead of the loads, 16 columns per warp, and a CTA-cooperative form in which the warps split the pools of
+// one column block and hand partial tiles over named barriers -- none beat this one.
+constexpr int kCmMaxWarps = 24;
+constexpr int kCmTrip = 4;  // 16-pool blocks per trip: eight 128-bit loads in flight per lane
+
+template <int MT>
+__global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const CovarParams p, int ldq, int n_warps) {
+    extern __shared__ __align__(16) double cm_sm[];  // V [NV][ldq] | scratch [n_warps][(8 MT + 1) * 8]
+    const int ldg = p.ldg, n = p.n, nq = p.nq, k = p.k, NV = nq + k;
+    double *Vs = cm_sm;
+    for (int i = threadIdx.x; i < NV * ldq; i += blockDim.x) {
+        const int v = i / ldq, r = i - v * ldq;
+        // the Q columns, then the y~ columns of this phenotype pass (p.k of them, starting at p.V's column nq + p.y0)
+        Vs[i] = (r < n) ? p.V[(size_t)(v < nq ? v : v + p.y0) * ldg + r] : 0.0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    constexpr int SCR = (8 * MT + 1) * 8;
+    double *scr = cm_sm + (size_t)NV * ldq + (size_t)wib * SCR;  // U [8 MT][8] | g'g [8]
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
+    const int64_t n_blocks = (p.P + 7) / 8;
+    const int64_t wg = (int64_t)blockIdx.x * n_warps + wib, nwg = (int64_t)gridDim.x * n_warps;
+    // vector rows of this lane in each M tile (rows >= NV are zero: the address is clamped, the value masked)
+    const double *arow[MT];
+    double amask[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+        const int v = 8 * mt + g;
+        amask[mt] = v < NV ? 1.0 : 0.0;
+        arow[mt] = Vs + (size_t)(v < NV ? v : 0) * ldq + 2 * t;
+    }
+    constexpr int TR = 16 * kCmTrip;  // pools per trip
+    const int n_trips = n / TR;       // whole trips; the rest goes through the guarded tail
+    for (int64_t blk = wg; blk < n_blocks; blk += nwg) {
+        const int64_t c0 = blk * 8;
+        const bool cval = c0 + g < p.P;
+        const double zmask = cval ? 1.0 : 0.0;  // a column past the end contributes zeros
+        const double *gb = p.G + (size_t)(cval ? c0 + g : c0) * ldg + 2 * t;
+        double acc[MT][2][2], gg = 0.0;
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) acc[mt][0][0] = acc[mt][0][1] = acc[mt][1][0] = acc[mt][1][1] = 0.0;
+        // one 16-pool block: b0 = pools {2t, 2t+1}, b1 = pools {8+2t, 8+2t+1} of this lane's column
+        auto block16 = [&](const double2 b0, const double2 b1, int i0) {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                double2 a0 = *reinterpret_cast<const double2 *>(arow[mt] + i0);
+                double2 a1 = *reinterpret_cast<const double2 *>(arow[mt] + i0 + 8);
+                if (MT > 1 && mt == MT - 1) {  // the last tile may hold fewer than 8 vectors
+                    a0.x *= amask[mt], a0.y *= amask[mt], a1.x *= amask[mt], a1.y *= amask[mt];
+                }
+                dmma884(acc[mt][0][0], acc[mt][0][1], a0.x, b0.x);
+                dmma884(acc[mt][1][0], acc[mt][1][1], a0.y, b0.y);
+                dmma884(acc[mt][0][0], acc[mt][0][1], a1.x, b1.x);
+                dmma884(acc[mt][1][0], acc[mt][1][1], a1.y, b1.y);
+            }
+            gg = fma(b0.x, b0.x, gg);
+            gg = fma(b0.y, b0.y, gg);
+            gg = fma(b1.x, b1.x, gg);
+            gg = fma(b1.y, b1.y, gg);
+        };
+        for (int tr = 0; tr < n_trips; tr++) {
+            double2 b[kCmTrip][2];
+#pragma unroll
+            for (int u = 0; u < kCmTrip; u++) {
+                b[u][0] = __ldcs(reinterpret_cast<const double2 *>(gb + tr * TR + 16 * u));
+                b[u][1] = __ldcs(reinterpret_cast<const double2 *>(gb + tr * TR + 16 * u + 8));
+            }
+#pragma unroll
+            for (int u = 0; u < kCmTrip; u++)
+                block16(make_double2(b[u][0].x * zmask, b[u][0].y * zmask), make_double2(b[u][1].x * zmask, b[u][1].y * zmask),
+                        tr * TR + 16 * u);
+        }
+        for (int i0 = n_trips * TR; i0 < n; i0 += 16) {  // the tail: pools >= n read as zero (the next column starts there)
+            double2 b[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int r = i0 + 8 * h + 2 * t;
+                b[h].x = (cval && r < n) ? __ldcs(gb + i0 + 8 * h) : 0.0;
+                b[h].y = (cval && r + 1 < n) ? __ldcs(gb + i0 + 8 * h + 1) : 0.0;
+            }
+            block16(b[0], b[1], i0);
+        }
+        // g'g of column g: sum over the four lanes that share it
+        gg += __shfl_xor_sync(PG_FULL_MASK, gg, 1);
+        gg += __shfl_xor_sync(PG_FULL_MASK, gg, 2);
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+            *reinterpret_cast<double2 *>(scr + (8 * mt + g) * 8 + 2 * t) =
+                make_double2(acc[mt][0][0] + acc[mt][1][0], acc[mt][0][1] + acc[mt][1][1]);
+        if (t == 0) scr[8 * MT * 8 + g] = gg;
+        __syncwarp();
+        // lane = (column cc, phenotype group): centred g'g, cancellation check, records
+        const int cc = lane & 7;
+        const int64_t c = c0 + cc;
+        const double ggv = scr[8 * MT * 8 + cc];
+        double uu = 0.0;
+        for (int v = 0; v < nq; v++) uu = fma(scr[v * 8 + cc], scr[v * 8 + cc], uu);
+        const double ggc = ggv - uu;
+        // cancellation: the column goes to the two-pass kernel (explicit residuals g - Q u), which rewrites its records
+        const bool flag = c < p.P && !(ggv <= 1e4 * ggc);
+        if (flag && lane < 8 && p.y0 == 0) p.defer_list[atomicAdd(p.defer_count, 1u)] = c;
+        for (int j = lane >> 3; j < k; j += 4) {
+            if (c >= p.P) break;
+            const double gyj = scr[(nq + j) * 8 + cc], yyj = p.yy[p.y0 + j];
+            double b = nan(""), vb = nan(""), pv = nan("");
+            if (!flag && ggc > 0.0 && p.dfe > 0.0) {
+                b = gyj / ggc;
+                double rss = yyj - b * gyj;
+                if (rss < 0.0) rss = 0.0;
+                vb = rss / p.dfe / ggc;
+                // estimate_significance, src/gwas/ols.rs:139-154
+                const double tt = (fabs(b) <= kEps) ? 0.0 : b / sqrt(vb);
+                if (fabs(tt) <= kEps || tt != tt)
+                    pv = 1.0;
+                else
+                    pv = p.ptab ? student_two_sided_tab(fabs(tt), p.df, ptab) : student_two_sided(fabs(tt), p.df, p.ln_beta);
+            } else if (ggv != ggv) {
+                pv = 1.0;  // NaN frequencies: the reference's t is NaN and its p is forced to 1 (ols.rs:150-151)
+            }
+            p.beta[(size_t)(p.y0 + j) * p.P + c] = b;
+            p.var[(size_t)(p.y0 + j) * p.P + c] = vb;
+            p.pval[(size_t)(p.y0 + j) * p.P + c] = pv;
+        }
+        __syncwarp();
+    }
+}
+
 // Any number of covariates: the column is staged in shared memory (one slot per warp), the 1 + m + k vectors stream
 // from global memory (L2 resident), u = Q'g goes to the warp's shared slot.  O(n (m + k)) per column like the fast
 // kernel, without its register / shared-memory limits.
@@ -532,7 +682,9 @@ __global__ void __launch_bounds__(256) covar_generic_kernel(const CovarParams p)
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
-    for (int64_t c = warp; c < p.P; c += nwarps) {
+    const int64_t n_items = p.defer_list ? (int64_t)*p.defer_count : p.P;
+    for (int64_t item = warp; item < n_items; item += nwarps) {
+        const int64_t c = p.defer_list ? p.defer_list[item] : item;
         const double *g = p.G + (size_t)c * ldg;
         double gg = 0.0;
         for (int r = lane; r < ldg; r += 32) {
@@ -714,6 +866,7 @@ int pg_kin_close(pg_kin *h) {
     cudaFree(h->d_V);
     cudaFree(h->d_ptab);
     cudaFree(h->d_res);
+    cudaFree(h->d_defer);
     if (h->h_res) cudaFreeHost(h->h_res);
     cudaFree(h->d_sel);
     cudaFree(h->d_off);
@@ -1166,6 +1319,17 @@ int pg_kin_set_covariates(pg_kin *h, const double *cov, int m) {
 
 }  // extern "C"
 
+// covar_kernel<NV, 1> over a column list (cp.defer_list / cp.defer_count)
+template <int NV>
+static cudaError_t covar_launch_list(const pg::CovarParams &cp, int sm_count, cudaStream_t s) {
+    const size_t smem = (size_t)NV * cp.ldg * 8;
+    auto kern = pg::covar_kernel<NV, 1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<sm_count, 512, smem, s>>>(cp);
+    return cudaGetLastError();
+}
+
 template <int NV>
 static cudaError_t covar_launch_nv(const pg::CovarParams &cp, int sm_count, cudaStream_t s) {
     const size_t smem = (size_t)NV * cp.ldg * 8;
@@ -1178,10 +1342,92 @@ static cudaError_t covar_launch_nv(const pg::CovarParams &cp, int sm_count, cuda
     return cudaGetLastError();
 }
 
+// the DMMA form: nv <= 16 vectors whose shared-memory copy leaves room for the warps' scratch
+static bool covar_mma_fits(const pg::CovarParams &cp, int nv, int *ldq_out, int *warps_out, size_t *smem_out) {
+    if (cp.minnorm || nv > 16) return false;
+    int ldq = (cp.n + 15) & ~15;  // whole 16-pool blocks, zero padded
+    ldq += 8;                     // pitch = 8 (mod 16) doubles: conflict-free 128-bit fragment loads
+    const int mt = nv <= 8 ? 1 : 2;
+    const size_t vbytes = (size_t)nv * ldq * 8, per_warp = (size_t)(8 * mt + 1) * 8 * 8;
+    const size_t budget = 227 * 1024;
+    if (vbytes + 8 * per_warp > budget) return false;  // V and the warps' partial tiles
+    int warps = (int)std::min<size_t>(pg::kCmMaxWarps, (budget - vbytes) / per_warp);
+    static const int warps_env = getenv("PG_CM_WARPS") ? atoi(getenv("PG_CM_WARPS")) : 0;
+    if (warps_env >= 4 && warps_env < warps) warps = warps_env;
+    *ldq_out = ldq;
+    *warps_out = warps;
+    *smem_out = vbytes + (size_t)warps * per_warp;
+    return true;
+}
+
 static int covar_launch(pg_kin *h, const pg::CovarParams &cp) {
     pg_ctx *ctx = h->ctx;
     const int nv = cp.nq + cp.k;
     cudaError_t e;
+    int ldq = 0, warps = 0;
+    size_t smem_mma = 0;
+    static const bool no_mma = getenv("PG_COVAR_NO_MMA") != nullptr;  // tests: the per-warp dot-product kernels
+    // with covariates (nv >= 5): as many phenotypes per pass as fit beside the Q columns in shared memory, G is
+    // streamed once per pass
+    int kk = cp.k;
+    while (kk > 1 && !covar_mma_fits(cp, cp.nq + kk, &ldq, &warps, &smem_mma)) kk--;
+    if (!no_mma && nv >= 5 && covar_mma_fits(cp, cp.nq + kk, &ldq, &warps, &smem_mma)) {
+        // the list of columns the DMMA passes leave to the two-pass kernel: [count | columns]
+        const size_t need = (size_t)(cp.P + 2) * 8;
+        if (h->defer_bytes < need) {
+            KCUDA(ctx, cudaStreamSynchronize(h->stream));
+            cudaFree(h->d_defer);
+            h->d_defer = nullptr;
+            h->defer_bytes = 0;
+            KCUDA(ctx, cudaMalloc(&h->d_defer, need));
+            h->defer_bytes = need;
+        }
+        KCUDA(ctx, cudaMemsetAsync(h->d_defer, 0, 8, h->stream));
+        for (int y0 = 0; y0 < cp.k; y0 += kk) {
+            pg::CovarParams pp = cp;
+            pp.y0 = y0;
+            pp.k = std::min(kk, cp.k - y0);
+            pp.defer_count = reinterpret_cast<unsigned *>(h->d_defer);
+            pp.defer_list = reinterpret_cast<int64_t *>(h->d_defer) + 1;
+            covar_mma_fits(pp, pp.nq + pp.k, &ldq, &warps, &smem_mma);
+            auto kern = pp.nq + pp.k <= 8 ? pg::covar_mma_kernel<1> : pg::covar_mma_kernel<2>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+            if (e == cudaSuccess) {
+                kern<<<ctx->sm_count, warps * 32, smem_mma, h->stream>>>(pp, ldq, warps);
+                e = cudaGetLastError();
+            }
+            if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covar_mma_kernel: %s", cudaGetErrorString(e));
+        }
+        // the deferred columns (centred g'g lost to cancellation: nearly constant columns): explicit residuals, all phenotypes
+        {
+            pg::CovarParams pp = cp;
+            pp.defer_count = reinterpret_cast<unsigned *>(h->d_defer);
+            pp.defer_list = reinterpret_cast<int64_t *>(h->d_defer) + 1;
+            switch ((size_t)nv * cp.ldg * 8 <= 227 * 1024 ? nv : 0) {
+                case 5: e = covar_launch_list<5>(pp, ctx->sm_count, h->stream); break;
+                case 6: e = covar_launch_list<6>(pp, ctx->sm_count, h->stream); break;
+                case 7: e = covar_launch_list<7>(pp, ctx->sm_count, h->stream); break;
+                case 8: e = covar_launch_list<8>(pp, ctx->sm_count, h->stream); break;
+                case 9: e = covar_launch_list<9>(pp, ctx->sm_count, h->stream); break;
+                case 10: e = covar_launch_list<10>(pp, ctx->sm_count, h->stream); break;
+                case 11: e = covar_launch_list<11>(pp, ctx->sm_count, h->stream); break;
+                case 12: e = covar_launch_list<12>(pp, ctx->sm_count, h->stream); break;
+                default: {
+                    const size_t per_warp = (size_t)(cp.ldg + nv) * 8;
+                    int gw = (int)std::min<size_t>(8, (200 * 1024) / per_warp);
+                    if (gw < 1) return kfail(ctx, PG_ERR_UNSUPPORTED, "covariate scan: %d pools x %d vectors exceed shared memory", cp.n, nv);
+                    const size_t smem = per_warp * gw;
+                    e = cudaFuncSetAttribute(pg::covar_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e == cudaSuccess) {
+                        pg::covar_generic_kernel<<<ctx->sm_count, gw * 32, smem, h->stream>>>(pp);
+                        e = cudaGetLastError();
+                    }
+                }
+            }
+            if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covariate scan (deferred columns): %s", cudaGetErrorString(e));
+        }
+        return PG_OK;
+    }
     switch (nv) {
         case 2: e = covar_launch_nv<2>(cp, ctx->sm_count, h->stream); break;
         case 3: e = covar_launch_nv<3>(cp, ctx->sm_count, h->stream); break;
@@ -1298,7 +1544,7 @@ int pg_kin_covar_scan(pg_kin *h, const double *phen, int k, int iters, float *ms
     cp.ptab_vmax = h->ptab_vmax;
     cp.ptab_inv_h = h->ptab_inv_h;
     cp.ptab_M = h->ptab_M;
-    cp.ln_beta = lgamma(df / 2.0 + 0.5) - lgamma(df / 2.0) - lgamma(0.5);
+    cp.ln_beta = pg::statrs::ln_gamma(df / 2.0 + 0.5) - pg::statrs::ln_gamma(df / 2.0) - pg::statrs::ln_gamma(0.5);
     cp.beta = h->d_res;
     cp.var = h->d_res + (size_t)k * h->P;
     cp.pval = h->d_res + (size_t)2 * k * h->P;

@@ -13,6 +13,8 @@
 
 #include <vector>
 
+#include "pg_statrs_host.h"
+
 namespace pg {
 
 // Lentz continued fraction of statrs 0.16 checked_beta_reg, returning h (the fraction) for already swapped a, b, x
@@ -53,7 +55,9 @@ inline double host_ln_tail(double v, double df) {
     const double x = exp(-u);
     const double omx = -expm1(-u);
     const double a = df / 2.0, b = 0.5;
-    const double lnB = lgamma(a + b) - lgamma(a) - lgamma(b);
+    // statrs' own ln_gamma (Lanczos): the constant the reference's beta_reg uses, not libm's lgamma (they differ by
+    // up to 1e-12 at df ~ 1000, a systematic relative offset of every p-value of the scan)
+    const double lnB = statrs::ln_gamma(a + b) - statrs::ln_gamma(a) - statrs::ln_gamma(b);
     const double lnbt = lnB + a * (-u) + b * log(omx);
     if (x >= (a + 1.0) / (a + b + 2.0)) {
         // symmetric branch: p = 1 - bt * h / a with (x, a, b) -> (1 - x, b, a)

@@ -270,12 +270,22 @@ def test_c4_shape_gram_and_covariate_scan(ctx):
     share = np.cumsum(w / w.sum())
     thr = 0.5 * (share[9] + share[10])
     m10 = kin.eig_select(P, thr)
+    beta_d, var_d, pval_d = kin.covar_scan(phen)         # with the device's own eigenvectors
+    # the covariate scan itself against the oracle, both on the oracle's PCs: the bulk eigenvalues of a 2,000-pool
+    # kinship matrix sit 5e-4 apart (relative), so a 1e-13 difference between two correct Gram matrices turns v_10
+    # into v_11 by ~1e-10 -- the PC SUBSPACE is only defined to that level (eigen step parity unpinned),
+    # and it is checked separately below at the tolerance its conditioning allows
+    kin.set_covariates(V[:, :10])
     beta, var, pval = kin.covar_scan(phen)
     kin.close()
     om, ob, ov, op = pgo.ols_with_covariate(G, phen, thr, columns=sample)
     assert m10 == om == 10
     n_arb = _cmp_records((beta[:, sample], var[:, sample], pval[:, sample]), (ob[sample].T, ov[sample].T, op[sample].T),
                          "C4 shape m=10", arb=(G[sample], V[:, :10], phen))
+    ok = ~np.isnan(ob[sample].T)
+    se = np.sqrt(ov[sample].T[ok])
+    assert np.all(np.abs(beta_d[:, sample][ok] - ob[sample].T[ok]) <= 1e-7 * np.maximum(np.abs(ob[sample].T[ok]), se))
+    assert np.all(np.abs(pval_d[:, sample][ok] - op[sample].T[ok]) <= 1e-6 * op[sample].T[ok] + H.P_FLOOR)
     print(f"C4 shape: P={P}, m=0 and m=10 records match on {sample.size} sampled columns ({n_arb} arbitrated)")
 
 
@@ -303,3 +313,30 @@ def test_threshold_never_reached_takes_the_n_less_than_p_branch(ctx, n, L, k):
     scale = np.maximum(np.abs(ob), np.abs(ob[ok]).mean())
     assert np.all(np.abs(beta.T - ob)[ok] <= 1e-8 * scale[ok])
     assert np.all(pval.T[ok] == 1.0) and np.all(op[ok] == 1.0)
+
+
+@pytest.mark.parametrize("n,P,m,k", [(64, 333, 3, 1), (301, 1001, 6, 3), (130, 50, 12, 4), (97, 7, 9, 2)])
+def test_covariate_scan_dmma_kernel(ctx, n, P, m, k):
+    """the blocked FP64 contraction of the covariate scan (covar_mma_kernel: 5..16 vectors): pool counts that are not
+    multiples of 16, column counts that are not multiples of 16, one and two M tiles, several phenotypes per column,
+    a constant column (singular X'X -> NaN like the reference) -- against the oracle's normal equations"""
+    rng = np.random.default_rng(1000 * n + m)
+    G = np.clip(0.5 + 0.2 * rng.standard_normal((P, n)), 0.0, 1.0)
+    G[P // 2] = 1.0
+    cov = rng.standard_normal((n, m))
+    phen = rng.standard_normal((n, k))
+    kin = pb.Kinship(ctx, n, P)
+    kin.append_columns(G)
+    kin.set_covariates(cov)
+    beta, var, pval = kin.covar_scan(phen)
+    kin.close()
+    ob, ov, op = (np.full((P, k), np.nan) for _ in range(3))
+    for c in range(P):
+        x = np.ones((n, 2 + m))
+        x[:, 1:1 + m] = cov
+        x[:, 1 + m] = G[c]
+        rc, b, v, p_, _ = pgo.ols(x, phen)
+        if rc == 0 and c != P // 2:
+            ob[c], ov[c], op[c] = b[1 + m], v[1 + m], p_[1 + m]
+    assert np.isnan(beta[:, P // 2]).all()
+    _cmp_records((beta, var, pval), (ob.T, ov.T, op.T), f"dmma covar n={n} m={m}", arb=(G, cov, phen))
