@@ -25,7 +25,7 @@ fn main() {
     .chain([format!("-I{}", inc.display()), format!("-I{}", csrc.display())])
     .collect();
     let mut objs: Vec<String> = vec![];
-    for src in ["pg_api.cu", "pg_ingest.cu", "pg_tables.cu", "pg_kinship.cu", "pg_comm.cu", "pg_text.cu", "pg_writer.cpp"] {
+    for src in ["pg_api.cu", "pg_ingest.cu", "pg_tables.cu", "pg_kinship.cu", "pg_nm.cu", "pg_comm.cu", "pg_text.cu", "pg_writer.cpp"] {
         let o = out.join(format!("{src}.o")).display().to_string();
         let mut a = common.clone();
         a.extend(["-c".to_string(), csrc.join(src).display().to_string(), "-o".to_string(), o.clone()]);

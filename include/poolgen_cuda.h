@@ -39,15 +39,23 @@ extern "C" {
 
 enum { PG_OK = 0, PG_ERR_ARG = -1, PG_ERR_CUDA = -2, PG_ERR_STATE = -3, PG_ERR_UNSUPPORTED = -4, PG_ERR_NCCL = -5 };
 
-/* the four per-locus analyses (callbacks) */
-enum { PG_KIND_OLS = 0, PG_KIND_CORR = 1, PG_KIND_CHISQ = 2, PG_KIND_FISHER = 3 };
+/* the per-locus analyses (callbacks); 4 is PG_KIND_OLS_KINSHIP, a header selector of the writer.
+ * PG_KIND_MLE: gwas::mle_iterate (src/gwas/mle.rs:232-305), phenotypes as for PG_KIND_OLS; records: statistic = beta,
+ *   stats[1] = v_b (a variance, mle.rs:150-154), t = beta / v_b (sic, mle.rs:176), p.
+ * PG_KIND_GWALPHA_LS / _ML: gwas::gwalpha_ls / gwalpha_ml (src/gwas/gwalpha.rs:282-386); `phen` of pg_scan_open is the
+ *   gwalpha_fmt matrix (rows x 3 row-major: column 0 bins, column 1 q, column 2 = sig, MIN, MAX then -inf,
+ *   src/base/phen.rs) and `k` its number of rows; records: n_phen = 1, statistic = alpha, stats[1] = p_a.
+ * Both minimise with argmin's Nelder-Mead capped at 1,000 iterations: results agree with the reference to the
+ * solver's convergence, not to 1e-9. */
+enum { PG_KIND_OLS = 0, PG_KIND_CORR = 1, PG_KIND_CHISQ = 2, PG_KIND_FISHER = 3, PG_KIND_MLE = 5, PG_KIND_GWALPHA_LS = 6,
+       PG_KIND_GWALPHA_ML = 7 };
 
 /* per-locus status, = what the reference callback returned */
 enum {
     PG_LOCUS_FILTERED = 0,    /* None: LocusCounts::filter dropped the locus (src/base/sync.rs:195-303) */
     PG_LOCUS_OK = 1,          /* Some(line) */
     PG_LOCUS_FAILED = 2,      /* None: the regression could not be solved (src/gwas/ols.rs:250-253) */
-    PG_LOCUS_UNSUPPORTED = 3, /* shape the device path does not implement (n_pools < n coefficients) */
+    PG_LOCUS_UNSUPPORTED = 3, /* shape the device path does not implement (mle_iter with fewer pools than coefficients) */
     PG_LOCUS_PANIC = 4        /* the reference would panic on this locus (assert / unwrap) */
 };
 

@@ -20,6 +20,7 @@ MAX_ALLELES = 6
 ALLELE_NAMES = "ATCGND"
 FILTERED, OK, FAILED, PANIC = 0, 1, 2, -1
 SCAN_OLS, SCAN_CORR, SCAN_CHISQ, SCAN_FISHER = 0, 1, 2, 3
+SCAN_MLE, SCAN_GWALPHA_LS, SCAN_GWALPHA_ML = 5, 6, 7
 
 
 class _FilterStats(C.Structure):
@@ -101,6 +102,11 @@ def lib():
             ("pgo_format_corr_lines", i, [C.c_char_p, C.c_uint64, C.POINTER(_LocusResult), i, C.c_char_p, C.c_size_t]),
             ("pgo_format_chisq_line", i, [C.c_char_p, C.c_uint64, C.POINTER(_TableResult), C.c_char_p, C.c_size_t]),
             ("pgo_format_fisher_line", i, [C.c_char_p, C.c_uint64, C.POINTER(_TableResult), C.c_char_p, C.c_size_t]),
+            ("pgo_bound_logit", d, [d, d, d]),
+            ("pgo_mle_iterate", i, [u64p, u8p, i, i, dp, i, C.POINTER(_FilterStats), C.POINTER(_LocusResult)]),
+            ("pgo_gwalpha", i, [u64p, u8p, i, i, dp, i, i, C.POINTER(_FilterStats), C.POINTER(_LocusResult)]),
+            ("pgo_format_mle_lines", i, [C.c_char_p, C.c_uint64, C.POINTER(_LocusResult), i, C.c_char_p, C.c_size_t]),
+            ("pgo_format_gwalpha_lines", i, [C.c_char_p, C.c_uint64, C.POINTER(_LocusResult), C.c_char_p, C.c_size_t]),
             ("pgo_scan_batch", i, [i, C.POINTER(C.c_uint32), C.c_int64, i, i, u8p, dp, i,
                                    C.POINTER(_FilterStats), i, C.POINTER(C.c_int8), u8p, u8p, dp, dp, dp, dp, dp]),
             ("pgo_scan_batch_tight", i, [i, C.POINTER(C.c_uint32), C.c_int64, i, i, u8p, dp, i,
@@ -261,6 +267,44 @@ def _locus_call(fn, counts, alleles, phen, fs: FilterStats):
 
 
 def ols_iterate(counts, alleles, phen, fs): return _locus_call(lib().pgo_ols_iterate, counts, alleles, phen, fs)
+def mle_iterate(counts, alleles, phen, fs): return _locus_call(lib().pgo_mle_iterate, counts, alleles, phen, fs)
+
+
+def bound_logit(x, lower, upper): return lib().pgo_bound_logit(float(x), float(lower), float(upper))
+
+
+def gwalpha(counts, alleles, phen_fmt, fs, method="LS"):
+    """gwalpha_ls / gwalpha_ml (gwas/gwalpha.rs:282-386); phen_fmt: the gwalpha_fmt matrix [rows, 3] (column 0 bins,
+    column 1 q, column 2 = sig, min, max, then -inf).  stat[:, 0] = alpha per allele."""
+    c = np.ascontiguousarray(counts, dtype=np.uint64)
+    a = np.ascontiguousarray(alleles, dtype=np.uint8)
+    y = np.ascontiguousarray(phen_fmt, dtype=np.float64)
+    assert y.ndim == 2 and y.shape[1] == 3
+    n, p = c.shape
+    bufs = [np.full(MAX_ALLELES, np.nan) for _ in range(4)]
+    r = _LocusResult()
+    r.stat, r.var, r.t, r.pval = (_dp(b) for b in bufs)
+    fsc = fs.c()
+    st = lib().pgo_gwalpha(_u64p(c), _u8p(a), n, p, _dp(y), int(y.shape[0]), 0 if method == "LS" else 1, C.byref(fsc), C.byref(r))
+    m = r.n_alleles_out
+    out = LocusResult(st, [int(r.allele[i]) for i in range(m)], np.array([r.freq_mean[i] for i in range(m)]),
+                      *(b[:m].reshape(m, 1).copy() for b in bufs))
+    out._raw = (r, bufs, 1)
+    return out
+
+
+def format_mle_lines(chrom, pos, res: LocusResult):
+    r, _, k = res._raw
+    buf = C.create_string_buffer(1 << 14)
+    lib().pgo_format_mle_lines(chrom.encode(), int(pos), C.byref(r), k, buf, 1 << 14)
+    return buf.value.decode()
+
+
+def format_gwalpha_lines(chrom, pos, res: LocusResult):
+    r, _, _ = res._raw
+    buf = C.create_string_buffer(1 << 14)
+    lib().pgo_format_gwalpha_lines(chrom.encode(), int(pos), C.byref(r), buf, 1 << 14)
+    return buf.value.decode()
 def correlation(counts, alleles, phen, fs): return _locus_call(lib().pgo_correlation, counts, alleles, phen, fs)
 
 
@@ -347,6 +391,10 @@ def scan_batch(kind, counts_packed, allele_codes, phen, fs: FilterStats, n_threa
         if y.ndim == 1:
             y = y[:, None].copy()
     k = y.shape[1]
+    k_arg = k
+    if kind in (SCAN_GWALPHA_LS, SCAN_GWALPHA_ML):  # phen = gwalpha_fmt matrix [rows, 3]; one alpha per allele
+        assert y.shape[1] == 3
+        k_arg, k = int(y.shape[0]), 1
     status = np.zeros(L, dtype=np.int8)
     n_out = np.zeros(L, dtype=np.uint8)
     allele = np.full((L, MAX_ALLELES), 0xFF, dtype=np.uint8)
@@ -355,7 +403,7 @@ def scan_batch(kind, counts_packed, allele_codes, phen, fs: FilterStats, n_threa
     fsc = fs.c()
     fn = lib().pgo_scan_batch_tight if tight else lib().pgo_scan_batch
     rc = fn(int(kind), cp.ctypes.data_as(C.POINTER(C.c_uint32)), L, n, A, _u8p(codes),
-                              _dp(y), k, C.byref(fsc), int(n_threads),
+                              _dp(y), k_arg, C.byref(fsc), int(n_threads),
                               status.ctypes.data_as(C.POINTER(C.c_int8)), _u8p(n_out), _u8p(allele),
                               _dp(fm), _dp(stat), _dp(var), _dp(t), _dp(pval))
     assert rc == 0

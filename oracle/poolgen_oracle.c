@@ -1161,6 +1161,503 @@ int pgo_format_fisher_line(const char *chr, uint64_t pos, const pgo_table_result
 }
 
 /* ====================================================================================== */
+/* argmin 0.8.1 Nelder-Mead (solver/neldermead/mod.rs) as the reference drives it:          */
+/* `prepare_solver_neldermead(p, h)` (base/helpers.rs:132-146) builds p + 1 vertices of     */
+/* dimension p -- vertex i is h everywhere and h + 0.5 at coordinate i, the last vertex all  */
+/* h -- and `Executor::new(cost, solver).configure(|s| s.max_iters(1_000)).run()`            */
+/* (gwas/mle.rs:99-113, gwas/gwalpha.rs:127-137).  The crate is not under /root/reference;   */
+/* this restates its published algorithm: alpha = 1, gamma = 2, rho = sigma = 0.5,           */
+/* sd_tolerance = f64::EPSILON; every iteration reflects the worst vertex through the        */
+/* centroid of the others; f_best <= f_r < f_second_worst accepts the reflection, f_r <      */
+/* f_best tries the expansion and keeps the better of the two, f_r >= f_second_worst         */
+/* contracts -- outside (towards the reflected point, accepted when f_c <= f_r) when         */
+/* f_r < f_worst, inside (towards the worst vertex, accepted when f_c < f_worst) otherwise    */
+/* -- and a failed contraction shrinks every vertex half way towards the best one;           */
+/* vertices are kept sorted by cost (stable);                                               */
+/* the run stops after 1,000 iterations or when the sample standard deviation of the         */
+/* vertex costs drops below the tolerance; the result is the best vertex.                   */
+/* PINNED by the reference's own test_gwalpha lines (gwas/gwalpha.rs:392-447), which go      */
+/* through this solver with both cost functions: tests/test_oracle_golden.py.               */
+/* ====================================================================================== */
+#define PGO_NM_MAXD 8
+typedef double (*pgo_cost_fn)(const double *x, int d, void *ctx);
+
+static void nm_sort(double v[][PGO_NM_MAXD], double *c, int nv, int d) {
+    /* stable insertion sort by cost; partial_cmp -> Equal for NaN */
+    for (int a = 1; a < nv; a++) {
+        double ca = c[a], va[PGO_NM_MAXD];
+        memcpy(va, v[a], sizeof(double) * (size_t)d);
+        int b = a - 1;
+        while (b >= 0 && ca < c[b]) {
+            c[b + 1] = c[b];
+            memcpy(v[b + 1], v[b], sizeof(double) * (size_t)d);
+            b--;
+        }
+        c[b + 1] = ca;
+        memcpy(v[b + 1], va, sizeof(double) * (size_t)d);
+    }
+}
+
+/* returns the number of iterations run; x_out = best vertex */
+int pgo_nelder_mead(pgo_cost_fn cost, void *ctx, int d, double h, int max_iters, double *x_out, double *cost_out) {
+    double v[PGO_NM_MAXD + 1][PGO_NM_MAXD], c[PGO_NM_MAXD + 1];
+    const int nv = d + 1;
+    for (int i = 0; i < nv; i++)
+        for (int j = 0; j < d; j++) v[i][j] = (i == j) ? h + 0.5 : h;
+    for (int i = 0; i < nv; i++) c[i] = cost(v[i], d, ctx);
+    nm_sort(v, c, nv, d);
+    int it = 0;
+    for (;;) {
+        /* terminate(): sample standard deviation of the costs */
+        double c0 = 0.0;
+        for (int i = 0; i < nv; i++) c0 = c0 + c[i];
+        c0 = c0 / (double)nv;
+        double ss = 0.0;
+        for (int i = 0; i < nv; i++) ss = ss + (c[i] - c0) * (c[i] - c0);
+        const double sd = sqrt(1.0 / ((double)nv - 1.0) * ss);
+        if (sd < F64_EPSILON) break;
+        if (it >= max_iters) break;
+        double x0[PGO_NM_MAXD], xr[PGO_NM_MAXD], xt[PGO_NM_MAXD];
+        /* centroid of all vertices but the worst */
+        for (int j = 0; j < d; j++) x0[j] = v[0][j];
+        for (int i = 1; i < nv - 1; i++)
+            for (int j = 0; j < d; j++) x0[j] = x0[j] + v[i][j];
+        const double inv = 1.0 / (double)(nv - 1);
+        for (int j = 0; j < d; j++) x0[j] = x0[j] * inv;
+        /* reflection: x0 + alpha (x0 - x_worst) */
+        for (int j = 0; j < d; j++) xr[j] = x0[j] + (x0[j] - v[nv - 1][j]) * 1.0;
+        const double fr = cost(xr, d, ctx);
+        if (fr < c[nv - 2] && fr >= c[0]) {
+            memcpy(v[nv - 1], xr, sizeof(double) * (size_t)d);
+            c[nv - 1] = fr;
+        } else if (fr < c[0]) {
+            for (int j = 0; j < d; j++) xt[j] = x0[j] + (xr[j] - x0[j]) * 2.0; /* expansion */
+            const double fe = cost(xt, d, ctx);
+            if (fe < fr) {
+                memcpy(v[nv - 1], xt, sizeof(double) * (size_t)d);
+                c[nv - 1] = fe;
+            } else {
+                memcpy(v[nv - 1], xr, sizeof(double) * (size_t)d);
+                c[nv - 1] = fr;
+            }
+        } else if (fr >= c[nv - 2]) {
+            int shrink = 0;
+            if (fr < c[nv - 1]) {
+                /* outside contraction: between the centroid and the reflected point */
+                for (int j = 0; j < d; j++) xt[j] = x0[j] + (xr[j] - x0[j]) * 0.5;
+                const double fc = cost(xt, d, ctx);
+                if (fc <= fr) {
+                    memcpy(v[nv - 1], xt, sizeof(double) * (size_t)d);
+                    c[nv - 1] = fc;
+                } else {
+                    shrink = 1;
+                }
+            } else {
+                /* inside contraction: between the centroid and the worst vertex */
+                for (int j = 0; j < d; j++) xt[j] = x0[j] + (v[nv - 1][j] - x0[j]) * 0.5;
+                const double fc = cost(xt, d, ctx);
+                if (fc < c[nv - 1]) {
+                    memcpy(v[nv - 1], xt, sizeof(double) * (size_t)d);
+                    c[nv - 1] = fc;
+                } else {
+                    shrink = 1;
+                }
+            }
+            if (shrink) { /* every vertex moves half way towards the best one */
+                for (int i = 1; i < nv; i++) {
+                    for (int j = 0; j < d; j++) v[i][j] = v[0][j] + (v[i][j] - v[0][j]) * 0.5;
+                    c[i] = cost(v[i], d, ctx);
+                }
+            }
+        } else {
+            /* only reachable with NaN costs */
+            for (int i = 1; i < nv; i++) {
+                for (int j = 0; j < d; j++) v[i][j] = v[0][j] + (v[i][j] - v[0][j]) * 0.5;
+                c[i] = cost(v[i], d, ctx);
+            }
+        }
+        nm_sort(v, c, nv, d);
+        it++;
+    }
+    memcpy(x_out, v[0], sizeof(double) * (size_t)d);
+    if (cost_out) *cost_out = c[0];
+    return it;
+}
+
+/* bound_parameters_with_logit (base/helpers.rs:120-129) */
+double pgo_bound_logit(double x, double lower, double upper) { return lower + ((upper - lower) / (1.00 + exp(-x))); }
+
+/* ndarray 0.15 numeric_util::unrolled_fold with + (what `.sum()` does on contiguous data): eight partial sums */
+static double ndarray_sum_contig(const double *xs, int len) {
+    double acc = 0.0, p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0;
+    while (len >= 8) {
+        p0 = p0 + xs[0]; p1 = p1 + xs[1]; p2 = p2 + xs[2]; p3 = p3 + xs[3];
+        p4 = p4 + xs[4]; p5 = p5 + xs[5]; p6 = p6 + xs[6]; p7 = p7 + xs[7];
+        xs += 8;
+        len -= 8;
+    }
+    acc = acc + (p0 + p4);
+    acc = acc + (p1 + p5);
+    acc = acc + (p2 + p6);
+    acc = acc + (p3 + p7);
+    for (int i = 0; i < len && i < 7; i++) acc = acc + xs[i];
+    return acc;
+}
+/* numeric_util::unrolled_dot */
+static double ndarray_dot_contig(const double *xs, const double *ys, int len) {
+    double sum = 0.0, p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0;
+    while (len >= 8) {
+        p0 = p0 + xs[0] * ys[0]; p1 = p1 + xs[1] * ys[1]; p2 = p2 + xs[2] * ys[2]; p3 = p3 + xs[3] * ys[3];
+        p4 = p4 + xs[4] * ys[4]; p5 = p5 + xs[5] * ys[5]; p6 = p6 + xs[6] * ys[6]; p7 = p7 + xs[7] * ys[7];
+        xs += 8;
+        ys += 8;
+        len -= 8;
+    }
+    sum = sum + (p0 + p4);
+    sum = sum + (p1 + p5);
+    sum = sum + (p2 + p6);
+    sum = sum + (p3 + p7);
+    for (int i = 0; i < len && i < 7; i++) sum = sum + xs[i] * ys[i];
+    return sum;
+}
+
+/* statrs 0.16.0 Beta::cdf */
+static double beta_cdf(double a, double b, double x) {
+    if (x < 0.0) return 0.0;
+    if (x >= 1.0) return 1.0;
+    if (isinf(a)) return x < 1.0 ? 0.0 : 1.0;
+    if (isinf(b)) return 1.0;
+    if (ulps_eq_one(a) && ulps_eq_one(b)) return x;
+    return pgo_beta_reg(a, b, x);
+}
+
+/* ---- gwas/gwalpha.rs ---------------------------------------------------------------------- */
+#define GWALPHA_LO F64_EPSILON
+#define GWALPHA_HI 10.00
+typedef struct {
+    int n;
+    const double *percs_a, *percs_b, *percs_a0, *percs_b0, *q_prime;
+} gwalpha_ctx;
+
+/* least_squares_beta (gwalpha.rs:11-41) */
+static double gwalpha_cost_ls(const double *x, int d, void *vctx) {
+    const gwalpha_ctx *g = (const gwalpha_ctx *)vctx;
+    double sh[4];
+    for (int i = 0; i < 4; i++) sh[i] = pgo_bound_logit(x[i], GWALPHA_LO, GWALPHA_HI);
+    double sa = 0.0, sb = 0.0;
+    for (int i = 0; i < g->n; i++) {
+        const double da = g->percs_a[i] - beta_cdf(sh[0], sh[1], g->q_prime[i]);
+        const double db = g->percs_b[i] - beta_cdf(sh[2], sh[3], g->q_prime[i]);
+        sa += pow(da, 2.0);
+        sb += pow(db, 2.0);
+    }
+    return sa + sb;
+}
+/* maximum_likelihood_beta (gwalpha.rs:43-82) */
+static double gwalpha_cost_ml(const double *x, int d, void *vctx) {
+    const gwalpha_ctx *g = (const gwalpha_ctx *)vctx;
+    double sh[4];
+    for (int i = 0; i < 4; i++) sh[i] = pgo_bound_logit(x[i], GWALPHA_LO, GWALPHA_HI);
+    double la = 0.0, lb = 0.0;
+    for (int i = 0; i < g->n; i++) {
+        double da = beta_cdf(sh[0], sh[1], g->percs_a[i]) - beta_cdf(sh[0], sh[1], g->percs_a0[i]);
+        double db = beta_cdf(sh[2], sh[3], g->percs_b[i]) - beta_cdf(sh[2], sh[3], g->percs_b0[i]);
+        if (da < F64_EPSILON) da = F64_EPSILON;
+        if (db < F64_EPSILON) db = F64_EPSILON;
+        la += log10(da);
+        lb += log10(db);
+    }
+    return -la - lb;
+}
+
+/* gwalpha_ls / gwalpha_ml (gwalpha.rs:282-386).  phen: the gwalpha_fmt matrix, n_rows x 3 row-major (column 0 bins,
+ * column 1 q, column 2 = sig, min, max, then -inf).  Outputs: out->allele / freq_mean (rounded to 6 digits by the line
+ * formatter) and out->stat[j] = alpha of allele j (k = 1).  method 0 = LS, 1 = ML. */
+int pgo_gwalpha(const uint64_t *counts_in, const uint8_t *alleles_in, int n, int p, const double *phen,
+                int n_rows, int method, const pgo_filter_stats *fs, pgo_locus_result *out) {
+    result_fill_nan(out, 1);
+    uint64_t *counts = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n * (size_t)p);
+    uint8_t alleles[PGO_MAX_ALLELES];
+    memcpy(counts, counts_in, sizeof(uint64_t) * (size_t)n * (size_t)p);
+    memcpy(alleles, alleles_in, (size_t)p);
+    int status = pgo_filter(counts, alleles, n, &p, fs);
+    if (status != PGO_OK) {
+        free(counts);
+        return out->status = status;
+    }
+    double *freq = (double *)malloc(sizeof(double) * (size_t)n * (size_t)p);
+    pgo_to_frequencies(counts, n, p, freq);
+    pgo_sort_by_allele_freq(freq, alleles, n, p, 1);
+    if (p >= 2) {
+        remove_col_f64(freq, n, p, 0);
+        memmove(alleles, alleles + 1, (size_t)(p - 1));
+        p -= 1;
+    }
+    /* bins and q without the -inf fillers; sig, min, max (gwalpha.rs:197-216) */
+    double *bins = (double *)malloc(sizeof(double) * (size_t)n_rows * 8);
+    double *q = bins + n_rows, *qp = q + n_rows, *ba = qp + n_rows, *bb = ba + n_rows, *pa = bb + n_rows,
+           *pb = pa + n_rows, *fa = pb + n_rows;
+    int m = 0, mq = 0;
+    for (int i = 0; i < n_rows; i++) {
+        if (phen[(size_t)i * 3 + 0] != -INFINITY) bins[m++] = phen[(size_t)i * 3 + 0];
+        if (phen[(size_t)i * 3 + 1] != -INFINITY) q[mq++] = phen[(size_t)i * 3 + 1];
+    }
+    const double sig = phen[0 * 3 + 2], min = phen[1 * 3 + 2], max = phen[2 * 3 + 2];
+    if (n != m || n_rows < 3) {
+        free(bins);
+        free(freq);
+        free(counts);
+        return out->status = PGO_FILTERED; /* None */
+    }
+    double *pa0 = (double *)malloc(sizeof(double) * (size_t)n * 2), *pb0 = pa0 + n;
+    out->n_alleles_out = p;
+    for (int j = 0; j < p; j++) {
+        /* prepare_freqs_and_qprime (gwalpha.rs:225-280) */
+        for (int i = 0; i < n; i++) fa[i] = freq[(size_t)i * p + j];
+        double p_a;
+        if (p == 1) {
+            p_a = ndarray_dot_contig(fa, bins, n); /* a one-column matrix: the column view is contiguous */
+        } else {
+            p_a = 0.0;
+            for (int i = 0; i < n; i++) p_a += fa[i] * bins[i];
+        }
+        qp[0] = 0.0;
+        for (int i = 1; i < n; i++) qp[i] = (q[i] - min) / (max - min);
+        for (int i = 0; i < n; i++) {
+            ba[i] = (fa[i]) * bins[i] / (p_a);
+            bb[i] = (1.0 - fa[i]) * bins[i] / (1.0 - p_a);
+        }
+        pa[0] = ba[0];
+        pb[0] = bb[0];
+        for (int i = 1; i < n; i++) {
+            pa[i] = ndarray_sum_contig(ba, i + 1);
+            pb[i] = ndarray_sum_contig(bb, i + 1);
+        }
+        pa0[0] = pb0[0] = 0.0;
+        for (int i = 0; i < n - 1; i++) {
+            pa0[i + 1] = pa[i];
+            pb0[i + 1] = pb[i];
+        }
+        gwalpha_ctx g = {n, pa, pb, pa0, pb0, qp};
+        double sol[4];
+        pgo_nelder_mead(method == 0 ? gwalpha_cost_ls : gwalpha_cost_ml, &g, 4, 1.0, 1000, sol, NULL);
+        for (int i = 0; i < 4; i++) sol[i] = pgo_bound_logit(sol[i], GWALPHA_LO, GWALPHA_HI);
+        const double a_mu = min + (max - min) * (sol[0] / (sol[0] + sol[1]));
+        const double b_mu = min + (max - min) * (sol[2] / (sol[2] + sol[3]));
+        const double alpha = (2.00 * sqrt(p_a * (1.0 - p_a))) * (a_mu - b_mu) / sig;
+        out->allele[j] = alleles[j];
+        out->freq_mean[j] = (p == 1 ? ndarray_sum_contig(fa, n) : ({ double s_ = 0.0; for (int i = 0; i < n; i++) s_ = s_ + fa[i]; s_; })) / (double)n;
+        out->stat[j] = alpha;
+    }
+    free(pa0);
+    free(bins);
+    free(freq);
+    free(counts);
+    return out->status = PGO_OK;
+}
+
+/* ---- gwas/mle.rs -------------------------------------------------------------------------- */
+typedef struct {
+    int n, p;
+    const double *x; /* n x p row-major */
+    const double *y; /* n */
+} mle_ctx;
+
+/* negative_likelihood_normal_distribution_sigma_and_beta (mle.rs:13-30); params = [logit sigma2, betas] */
+static double mle_cost(const double *par, int d, void *vctx) {
+    const mle_ctx *m = (const mle_ctx *)vctx;
+    const double sigma2 = pgo_bound_logit(par[0], F64_EPSILON, 1e9);
+    double ss = 0.0;
+    for (int i = 0; i < m->n; i++) {
+        double xb = 0.0; /* x.dot(&betas): rows of fewer than 8 elements, sequential */
+        for (int j = 0; j < m->p; j++) xb = xb + m->x[(size_t)i * m->p + j] * par[1 + j];
+        const double e = m->y[i] - xb;
+        ss = ss + pow(e, 2.0);
+    }
+    return ((double)m->n / 2.00) * log(2.00 * 3.14159265358979323846264338327950288 * sigma2) + (1.00 / sigma2) * ss;
+}
+
+/* remove_collinearities_in_x (mle.rs:56-83), literally: returns the new column count, or -1 where the reference's
+ * `i -= 1` underflows (it would index out of bounds and panic) */
+static int mle_remove_collinear(double *x, int n, int p) {
+    if (p == 2) return p;
+    long i = 1;
+    while (i < p) {
+        long j = i + 1;
+        while (j < p) {
+            if (i < 0) return -1;
+            double *ci = (double *)malloc(sizeof(double) * (size_t)n * 2), *cj = ci + n;
+            for (int r = 0; r < n; r++) {
+                ci[r] = x[(size_t)r * p + i];
+                cj[r] = x[(size_t)r * p + j];
+            }
+            double cor = 0.0, pv = NAN;
+            if (pgo_pearsons_correlation(ci, cj, n, &cor, &pv) != 0) cor = 0.0;
+            free(ci);
+            if (fabs(cor) >= 0.99) {
+                remove_col_f64(x, n, p, (int)j);
+                p -= 1;
+                i -= 1;
+                j -= 1;
+            }
+            j += 1;
+        }
+        i += 1;
+    }
+    return p;
+}
+
+/* mle_iterate (mle.rs:232-305) with mle() (193-230) and the Regression impl (85-191).  out->stat = beta,
+ * out->var = v_b = ve diag((X'X)^-1), out->t = beta / v_b (sic, mle.rs:176), out->pval; rows of removed collinear
+ * columns keep the reference's zeros */
+int pgo_mle_iterate(const uint64_t *counts_in, const uint8_t *alleles_in, int n, int p, const double *phen, int k,
+                    const pgo_filter_stats *fs, pgo_locus_result *out) {
+    result_fill_nan(out, k);
+    uint64_t *counts = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n * (size_t)p);
+    uint8_t alleles[PGO_MAX_ALLELES];
+    memcpy(counts, counts_in, sizeof(uint64_t) * (size_t)n * (size_t)p);
+    memcpy(alleles, alleles_in, (size_t)p);
+    int status = pgo_filter(counts, alleles, n, &p, fs);
+    if (status != PGO_OK) {
+        free(counts);
+        return out->status = status;
+    }
+    double *freq = (double *)malloc(sizeof(double) * (size_t)n * (size_t)p);
+    pgo_to_frequencies(counts, n, p, freq);
+    pgo_sort_by_allele_freq(freq, alleles, n, p, 1);
+    if (p >= 2) {
+        remove_col_f64(freq, n, p, 0);
+        memmove(alleles, alleles + 1, (size_t)(p - 1));
+        p -= 1;
+    }
+    const int px = p + 1;
+    double *x = (double *)malloc(sizeof(double) * (size_t)n * (size_t)px * 2), *xw = x + (size_t)n * px;
+    for (int i = 0; i < n; i++) {
+        x[(size_t)i * px] = 1.0;
+        for (int j = 1; j < px; j++) x[(size_t)i * px + j] = freq[(size_t)i * p + (j - 1)];
+    }
+    double *yj = (double *)malloc(sizeof(double) * (size_t)n);
+    double beta[PGO_MAX_ALLELES + 1][64], vb[PGO_MAX_ALLELES + 1][64], tt[PGO_MAX_ALLELES + 1][64], pv[PGO_MAX_ALLELES + 1][64];
+    int fail = k > 64;
+    for (int i = 0; i < px && !fail; i++)
+        for (int j = 0; j < k; j++) beta[i][j] = vb[i][j] = pv[i][j] = 0.0, tt[i][j] = NAN; /* Array2::zeros */
+    for (int j = 0; j < k && !fail; j++) {
+        memcpy(xw, x, sizeof(double) * (size_t)n * (size_t)px);
+        const int pw = mle_remove_collinear(xw, n, px);
+        if (pw < 0) {
+            fail = 2;
+            break;
+        }
+        for (int i = 0; i < n; i++) yj[i] = phen[(size_t)i * k + j];
+        mle_ctx m = {n, pw, xw, yj};
+        double par[PGO_NM_MAXD];
+        pgo_nelder_mead(mle_cost, &m, pw + 1, 1.0, 1000, par, NULL);
+        const double ve = pgo_bound_logit(par[0], F64_EPSILON, 1e9);
+        /* estimate_variances (mle.rs:116-155) */
+        double *xt = transpose(xw, n, pw), *vcv = NULL;
+        if (n < pw) {
+            double *inv = matmul(xw, n, pw, xt, n);
+            if (pgo_lu_inverse(inv, n) != 0 || pgo_lu_det(inv, n) == 0.0) fail = 1;
+            if (!fail) {
+                double *t1 = matmul(xt, pw, n, inv, n), *t2 = matmul(t1, pw, n, inv, n);
+                vcv = matmul(t2, pw, n, xw, pw);
+                for (int i = 0; i < pw * pw; i++) vcv[i] = ve * vcv[i];
+                free(t1);
+                free(t2);
+            }
+            free(inv);
+        } else {
+            double *inv = matmul(xt, pw, n, xw, pw);
+            if (pgo_lu_inverse(inv, pw) != 0 || pgo_lu_det(inv, pw) == 0.0) fail = 1;
+            if (!fail) {
+                vcv = (double *)malloc(sizeof(double) * (size_t)pw * (size_t)pw);
+                for (int i = 0; i < pw * pw; i++) vcv[i] = ve * inv[i];
+            }
+            free(inv);
+        }
+        free(xt);
+        if (fail) break;
+        const double freedom = (double)n - 1.0;
+        if (!(freedom > 0.0)) {
+            fail = 2;
+            free(vcv);
+            break;
+        }
+        for (int i = 0; i < pw; i++) {
+            const double b = par[1 + i], v = vcv[(size_t)i * pw + i];
+            const double t = b / v; /* mle.rs:176: the variance, not its square root */
+            double pval;
+            if (isinf(t)) pval = 0.0;
+            else if (isnan(t)) pval = 1.0;
+            else pval = 2.00 * (1.00 - pgo_students_t_cdf(fabs(t), freedom));
+            beta[i][j] = b;
+            vb[i][j] = v;
+            tt[i][j] = t;
+            pv[i][j] = pval;
+        }
+        free(vcv);
+    }
+    if (fail) {
+        status = fail == 2 ? PGO_PANIC : PGO_FAILED;
+    } else {
+        out->n_alleles_out = p;
+        for (int i = 1; i < px; i++) {
+            out->allele[i - 1] = alleles[i - 1];
+            double sm = 0.0;
+            for (int r = 0; r < n; r++) sm = sm + x[(size_t)r * px + i];
+            out->freq_mean[i - 1] = sm / (double)n;
+            for (int j = 0; j < k; j++) {
+                out->stat[(size_t)(i - 1) * k + j] = beta[i][j];
+                out->var[(size_t)(i - 1) * k + j] = vb[i][j];
+                out->t[(size_t)(i - 1) * k + j] = tt[i][j];
+                out->pval[(size_t)(i - 1) * k + j] = pv[i][j];
+            }
+        }
+    }
+    free(yj);
+    free(x);
+    free(freq);
+    free(counts);
+    return out->status = status;
+}
+
+/* output lines of mle_iterate (mle.rs:283-303): beta rounded to 6 digits, p-value unrounded */
+int pgo_format_mle_lines(const char *chr, uint64_t pos, const pgo_locus_result *r, int k, char *buf, size_t cap) {
+    size_t w = 0;
+    buf[0] = 0;
+    if (r->status != PGO_OK) return 0;
+    for (int i = 0; i < r->n_alleles_out; i++)
+        for (int j = 0; j < k; j++) {
+            char f[420], b[420], pvs[420];
+            pgo_round_to_string(r->freq_mean[i], 8, f, sizeof f);
+            pgo_round_to_string(r->stat[(size_t)i * k + j], 6, b, sizeof b);
+            pgo_f64_to_string(r->pval[(size_t)i * k + j], pvs, sizeof pvs);
+            int len = snprintf(buf + w, cap - w, "%s,%llu,%c,%s,Pheno_%d,%s,%s\n", chr, (unsigned long long)pos,
+                               "ATCGND"[r->allele[i]], f, j, b, pvs);
+            if (len < 0 || (size_t)len >= cap - w) return -1;
+            w += (size_t)len;
+        }
+    return (int)w;
+}
+
+/* output lines of gwalpha_ls / gwalpha_ml (gwalpha.rs:320-331): chr,pos,allele,freq r6,Pheno_0,alpha r6,Unknown */
+int pgo_format_gwalpha_lines(const char *chr, uint64_t pos, const pgo_locus_result *r, char *buf, size_t cap) {
+    size_t w = 0;
+    buf[0] = 0;
+    if (r->status != PGO_OK) return 0;
+    for (int j = 0; j < r->n_alleles_out; j++) {
+        char f[420], a[420];
+        pgo_round_to_string(r->freq_mean[j], 6, f, sizeof f);
+        pgo_round_to_string(r->stat[j], 6, a, sizeof a);
+        int len = snprintf(buf + w, cap - w, "%s,%llu,%c,%s,Pheno_0,%s,Unknown\n", chr, (unsigned long long)pos,
+                           "ATCGND"[r->allele[j]], f, a);
+        if (len < 0 || (size_t)len >= cap - w) return -1;
+        w += (size_t)len;
+    }
+    return (int)w;
+}
+
+/* ====================================================================================== */
 /* "tight" ols_iterate: the SAME arithmetic, operation for operation, as pgo_ols_iterate   */
 /* (results are bit-identical, tests/test_oracle_golden.py), without the reference's       */
 /* avoidable work -- the honest upper bound of what its CPU path could do: */
@@ -1329,11 +1826,13 @@ typedef struct {
     uint8_t *allele_out;
     double *freq_mean, *stat, *var, *t, *pval;
     int tight; /* ols_iter only: the allocation-free variant (ols_iterate_tight) */
+    int phen_rows; /* gwalpha: rows of the gwalpha_fmt matrix */
 } batch_job;
 
 static void *batch_worker(void *arg) {
     batch_job *jb = (batch_job *)arg;
     int n = jb->n_pools, A = jb->n_alleles, k = jb->k > 0 ? jb->k : 1;
+    if (jb->phen_rows) k = 1; /* gwalpha: one alpha per allele; jb->k carried the rows of the gwalpha_fmt matrix */
     size_t cap = (size_t)PGO_MAX_ALLELES * (size_t)k;
     double *scratch = (double *)malloc(sizeof(double) * cap * 4);
     if (jb->tight && jb->kind == PGO_SCAN_OLS) {
@@ -1389,7 +1888,7 @@ static void *batch_worker(void *arg) {
         int status, nout = 0;
         uint8_t alle[PGO_MAX_ALLELES];
         memset(alle, 0xff, sizeof alle);
-        if (jb->kind == PGO_SCAN_OLS || jb->kind == PGO_SCAN_CORR) {
+        if (jb->kind == PGO_SCAN_OLS || jb->kind == PGO_SCAN_CORR || jb->kind >= PGO_SCAN_MLE) {
             pgo_locus_result r;
             r.stat = scratch;
             r.var = scratch + cap;
@@ -1397,6 +1896,11 @@ static void *batch_worker(void *arg) {
             r.pval = scratch + 3 * cap;
             if (jb->kind == PGO_SCAN_OLS)
                 status = pgo_ols_iterate(counts, jb->allele_codes, n, A, jb->phen, k, jb->fs, &r);
+            else if (jb->kind == PGO_SCAN_MLE)
+                status = pgo_mle_iterate(counts, jb->allele_codes, n, A, jb->phen, k, jb->fs, &r);
+            else if (jb->kind == PGO_SCAN_GWALPHA_LS || jb->kind == PGO_SCAN_GWALPHA_ML)
+                status = pgo_gwalpha(counts, jb->allele_codes, n, A, jb->phen, jb->phen_rows,
+                                     jb->kind == PGO_SCAN_GWALPHA_ML, jb->fs, &r);
             else
                 status = pgo_correlation(counts, jb->allele_codes, n, A, jb->phen, k, jb->fs, &r);
             nout = r.n_alleles_out;
@@ -1439,7 +1943,7 @@ static int scan_batch_impl(int kind, int tight, const uint32_t *counts_packed, i
     for (int i = 0; i < n_threads; i++) {
         batch_job jb = {kind, counts_packed, n_loci * i / n_threads, n_loci * (i + 1) / n_threads,
                         n_pools, n_alleles, k, allele_codes, phen, fs, status, n_out, allele_out,
-                        freq_mean, stat, var, t, pval, tight};
+                        freq_mean, stat, var, t, pval, tight, (kind == PGO_SCAN_GWALPHA_LS || kind == PGO_SCAN_GWALPHA_ML) ? k : 0};
         jobs[i] = jb;
         if (n_threads == 1) batch_worker(&jobs[i]);
         else pthread_create(&th[i], NULL, batch_worker, &jobs[i]);

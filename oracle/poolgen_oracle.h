@@ -125,6 +125,21 @@ double pgo_hypergeom_ratio(const double *counts, int n_cells, double log_prod_fa
 int pgo_fisher(const uint64_t *counts, const uint8_t *alleles, int n, int p,
                const pgo_filter_stats *fs, pgo_table_result *out);
 
+/* ---- argmin 0.8.1 Nelder-Mead as prepare_solver_neldermead + Executor drive it (base/helpers.rs:132-146,
+ *      gwas/mle.rs:99-113, gwas/gwalpha.rs:127-137); pinned by the reference's test_gwalpha lines ------------ */
+typedef double (*pgo_cost_fn)(const double *x, int d, void *ctx);
+int pgo_nelder_mead(pgo_cost_fn cost, void *ctx, int d, double h, int max_iters, double *x_out, double *cost_out);
+double pgo_bound_logit(double x, double lower, double upper); /* base/helpers.rs:120-129 */
+/* gwalpha_ls (method 0) / gwalpha_ml (method 1), gwas/gwalpha.rs:282-386; phen = gwalpha_fmt matrix n_rows x 3 row-major;
+ * out->stat[j] = alpha of allele j */
+int pgo_gwalpha(const uint64_t *counts, const uint8_t *alleles, int n, int p, const double *phen, int n_rows,
+                int method, const pgo_filter_stats *fs, pgo_locus_result *out);
+int pgo_format_gwalpha_lines(const char *chr, uint64_t pos, const pgo_locus_result *r, char *buf, size_t cap);
+/* mle_iterate (gwas/mle.rs:232-305): out->stat = beta, var = v_b, t = beta / v_b (sic), pval */
+int pgo_mle_iterate(const uint64_t *counts, const uint8_t *alleles, int n, int p, const double *phen, int k,
+                    const pgo_filter_stats *fs, pgo_locus_result *out);
+int pgo_format_mle_lines(const char *chr, uint64_t pos, const pgo_locus_result *r, int k, char *buf, size_t cap);
+
 /* ---- output lines (ols.rs:255-275, correlation_test.rs:113-128, chisq_test.rs:37-46,
  *      fisher_exact_test.rs:119-129).  Return bytes written (excluding NUL). -------------- */
 int pgo_format_ols_lines(const char *chr, uint64_t pos, const pgo_locus_result *r, int k,
@@ -137,7 +152,8 @@ int pgo_format_fisher_line(const char *chr, uint64_t pos, const pgo_table_result
                            size_t cap);
 
 /* ---- batch drivers: one OS thread per contiguous locus range (sync.rs:917-939) -------- */
-enum { PGO_SCAN_OLS = 0, PGO_SCAN_CORR = 1, PGO_SCAN_CHISQ = 2, PGO_SCAN_FISHER = 3 };
+enum { PGO_SCAN_OLS = 0, PGO_SCAN_CORR = 1, PGO_SCAN_CHISQ = 2, PGO_SCAN_FISHER = 3, PGO_SCAN_MLE = 5, PGO_SCAN_GWALPHA_LS = 6,
+       PGO_SCAN_GWALPHA_ML = 7 /* gwalpha kinds: phen = gwalpha_fmt matrix, k = its row count, one alpha per allele */ };
 /* counts_packed: u32 [locus][allele][pool] (the layout the CUDA library ingests), n_alleles
  * columns named by allele_codes.  Outputs (caller allocated, may be NULL when not wanted):
  *   status[L] (int8), n_out[L] (u8), allele_out[L*6] (u8), freq_mean[L*6],

@@ -7,7 +7,7 @@ BATCH of parsed loci instead of one.  All arithmetic runs in libpoolgen_cuda.so 
 nothing here computes on the CPU.
 """
 from . import capi  # noqa: F401
-from .capi import (ALLELE_NAMES, KIND_CHISQ, KIND_CORR, KIND_FISHER, KIND_OLS, LOCUS_FAILED, LOCUS_FILTERED,
+from .capi import (ALLELE_NAMES, KIND_CHISQ, KIND_CORR, KIND_FISHER, KIND_GWALPHA_LS, KIND_GWALPHA_ML, KIND_MLE, KIND_OLS, LOCUS_FAILED, LOCUS_FILTERED,
                    LOCUS_OK, LOCUS_PANIC, LOCUS_UNSUPPORTED, Batch, Comm, Context, FilterStats, Kinship, PgError, Scan,
                    ScanResults, format_f64, format_frequency_header, format_frequency_rows, format_header, format_kinship_rows,
                    format_rows, nccl_version, shard_range, sort_loci, synth_counts_host, synth_phen_host, synth_sync_text_host)
@@ -18,7 +18,8 @@ __all__ = ["FilePhen", "FileSync", "FileSyncPhen", "Phen", "find_file_splits", "
            "LOCUS_OK", "LOCUS_PANIC", "LOCUS_UNSUPPORTED", "Batch", "Context", "FilterStats", "Kinship", "PgError", "Scan",
            "ScanResults", "synth_counts_host", "synth_phen_host", "synth_sync_text_host", "ols_iterate", "correlation", "chisq", "fisher",
            "ols_with_covariate", "format_f64", "format_header", "format_kinship_rows", "format_rows", "format_frequency_header",
-           "format_frequency_rows", "sort_loci", "Comm", "shard_range", "nccl_version"]
+           "format_frequency_rows", "sort_loci", "Comm", "shard_range", "nccl_version", "KIND_MLE", "KIND_GWALPHA_LS",
+           "KIND_GWALPHA_ML", "mle_iterate", "gwalpha"]
 
 _SYNC_CODES = (0, 1, 2, 3, 4, 5)
 
@@ -49,6 +50,17 @@ def chisq(ctx, counts, filter_stats, allele_codes=_SYNC_CODES):
 def fisher(ctx, counts, filter_stats, allele_codes=_SYNC_CODES):
     """tables::fisher over a batch."""
     return _run(KIND_FISHER, ctx, counts, filter_stats, None, allele_codes)
+
+
+def mle_iterate(ctx, counts, phen, filter_stats, allele_codes=_SYNC_CODES):
+    """gwas::mle_iterate over a batch (src/gwas/mle.rs:232-305): stats[..., 0] = beta, 1 = v_b, 2 = beta / v_b, 3 = p."""
+    return _run(KIND_MLE, ctx, counts, filter_stats, phen, allele_codes)
+
+
+def gwalpha(ctx, counts, gwalpha_fmt, filter_stats, method="LS", allele_codes=_SYNC_CODES):
+    """gwas::gwalpha_ls / gwalpha_ml over a batch (src/gwas/gwalpha.rs:282-386); gwalpha_fmt [rows, 3]: column 0 bins,
+    column 1 q, column 2 = sig, MIN, MAX, then -inf.  stats[..., 0, 0] = alpha."""
+    return _run(KIND_GWALPHA_LS if method == "LS" else KIND_GWALPHA_ML, ctx, counts, filter_stats, gwalpha_fmt, allele_codes)
 
 
 def ols_with_covariate(ctx, columns, phen, xxt_eigen_variance_explained=0.75):

@@ -19,6 +19,7 @@ from .build import LIB_PATH, SYNTH_LIB_PATH
 PG_OK = 0
 KIND_OLS, KIND_CORR, KIND_CHISQ, KIND_FISHER = 0, 1, 2, 3
 KIND_OLS_KINSHIP = 4  # header selector of the writer only
+KIND_MLE, KIND_GWALPHA_LS, KIND_GWALPHA_ML = 5, 6, 7  # Nelder-Mead analyses (mle_iter, gwalpha)
 LOCUS_FILTERED, LOCUS_OK, LOCUS_FAILED, LOCUS_UNSUPPORTED, LOCUS_PANIC = 0, 1, 2, 3, 4
 MAX_ALLELES = 6
 MAX_SLOTS = 5
@@ -447,10 +448,15 @@ class Scan:
             if y.ndim == 1:
                 y = y[:, None].copy()
             k = y.shape[1]
+            if kind in (KIND_GWALPHA_LS, KIND_GWALPHA_ML):
+                # the gwalpha_fmt matrix [rows, 3]: column 0 bins, column 1 q, column 2 = sig, MIN, MAX, then -inf
+                assert y.shape[1] == 3, y.shape
+                k = y.shape[0]
             yp = y.ctypes.data_as(C.POINTER(C.c_double))
         else:
             y, k, yp = None, 0, None
-        self.n_pools, self.n_alleles, self.k = int(n_pools), int(codes.size), k
+        self.n_pools, self.n_alleles = int(n_pools), int(codes.size)
+        self.k = 1 if kind in (KIND_GWALPHA_LS, KIND_GWALPHA_ML) else k
         self._h = C.c_void_p()
         _check(lib().pg_scan_open(ctx._h, int(kind), C.byref(f), int(n_pools), int(codes.size),
                                   codes.ctypes.data_as(C.POINTER(C.c_uint8)), yp, int(k), C.byref(self._h)),

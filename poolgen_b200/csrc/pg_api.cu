@@ -115,7 +115,9 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
                  const uint8_t *allele_codes, const double *phen, int k, pg_scan **out) {
     if (!ctx || !out || !filter || !allele_codes) return fail(ctx, PG_ERR_ARG, "pg_scan_open: NULL argument");
     *out = nullptr;
-    if (kind < PG_KIND_OLS || kind > PG_KIND_FISHER) return fail(ctx, PG_ERR_ARG, "pg_scan_open: kind %d", kind);
+    const bool gwalpha = (kind == PG_KIND_GWALPHA_LS || kind == PG_KIND_GWALPHA_ML);
+    if (!((kind >= PG_KIND_OLS && kind <= PG_KIND_FISHER) || kind == PG_KIND_MLE || gwalpha))
+        return fail(ctx, PG_ERR_ARG, "pg_scan_open: kind %d", kind);
     if (n_pools < 1) return fail(ctx, PG_ERR_ARG, "pg_scan_open: n_pools %d", n_pools);
     if (n_alleles < 1 || n_alleles > PG_MAX_ALLELES)
         return fail(ctx, PG_ERR_ARG, "pg_scan_open: n_alleles %d not in 1..6", n_alleles);
@@ -128,8 +130,28 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
     if (filter->n_pool_sizes != n_pools || !filter->pool_sizes)
         return fail(ctx, PG_ERR_ARG, "pg_scan_open: %d pool sizes for %d pools (the reference asserts equality)",
                     filter->n_pool_sizes, n_pools);
-    const bool regression = (kind == PG_KIND_OLS || kind == PG_KIND_CORR);
+    const bool regression = (kind == PG_KIND_OLS || kind == PG_KIND_CORR || kind == PG_KIND_MLE || gwalpha);
     if (regression && (!phen || k < 1)) return fail(ctx, PG_ERR_ARG, "pg_scan_open: phenotypes required");
+    // gwalpha: `phen` is the gwalpha_fmt matrix, k rows x 3 (column 0 bins, column 1 q, column 2 = sig, MIN, MAX, then
+    // -inf fillers, src/gwas/gwalpha.rs:197-216); the scan's own "phenotype" is only a stand-in for the filter-only pass
+    std::vector<double> gw_bins, gw_q, gw_stand_in;
+    const int gw_rows = k;
+    if (gwalpha) {
+        if (k < 3) return fail(ctx, PG_ERR_ARG, "pg_scan_open: the gwalpha_fmt matrix needs at least 3 rows (sig, MIN, MAX)");
+        for (int i = 0; i < k; i++) {
+            if (phen[(size_t)i * 3 + 0] != -INFINITY) gw_bins.push_back(phen[(size_t)i * 3 + 0]);
+            if (phen[(size_t)i * 3 + 1] != -INFINITY) gw_q.push_back(phen[(size_t)i * 3 + 1]);
+        }
+        if ((int)gw_bins.size() != n_pools || (int)gw_q.size() < n_pools)
+            return fail(ctx, PG_ERR_ARG, "pg_scan_open: %d bins for %d pools (the reference returns None for every locus, "
+                                         "src/gwas/gwalpha.rs:218-223)", (int)gw_bins.size(), n_pools);
+        if (n_pools > 64) return fail(ctx, PG_ERR_UNSUPPORTED, "pg_scan_open: gwalpha is built for up to 64 pools (got %d)", n_pools);
+        gw_stand_in.assign(n_pools, 0.0);
+        for (int i = 0; i < n_pools; i++) gw_stand_in[i] = (double)(i % 7) - 3.0;
+        k = 1;
+    }
+    const double *gw_fmt = phen;
+    if (gwalpha) phen = gw_stand_in.data();
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
 
     pg_scan *s = new (std::nothrow) pg_scan();
@@ -200,7 +222,7 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
             s->ymean[j] = mean;
             s->syy[j] = s2 - s1 * s1 / n;
         }
-        if (s->y_has_nan && kind == PG_KIND_OLS) {
+        if (s->y_has_nan && (kind == PG_KIND_OLS || kind == PG_KIND_MLE)) {
             // ols_iterate: remove_missing() shrinks the pools but not FilterStats.pool_sizes, so the reference
             // panics at src/base/sync.rs:254-257.  pearson_corr drops NaN pairs per phenotype
             // (correlation_test.rs:21-31): every locus of such a scan takes the pairwise path of the fix-up kernel.
@@ -209,8 +231,8 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
                         "pg_scan_open: missing phenotype values (the reference's ols_iter panics on them, "
                         "src/base/sync.rs:254-257)");
         }
-        s->df = (kind == PG_KIND_OLS) ? (double)n - 1.0 : (double)n - 2.0;
-        if (kind == PG_KIND_OLS && !(s->df > 0.0)) {
+        s->df = (kind != PG_KIND_CORR) ? (double)n - 1.0 : (double)n - 2.0;
+        if (kind != PG_KIND_CORR && !(s->df > 0.0)) {
             delete s;  // StudentsT::new(0,1,0).unwrap() panics (src/gwas/ols.rs:139)
             return fail(ctx, PG_ERR_UNSUPPORTED, "pg_scan_open: ols_iter needs at least 2 pools");
         }
@@ -254,6 +276,30 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
             return fail(ctx, PG_ERR_CUDA, "pg_scan_open: weight upload: %s", cudaGetErrorString(e));
         }
     }
+    if (kind == PG_KIND_MLE || gwalpha) {
+        // what the Nelder-Mead kernels read: raw phenotypes [k][n_pad] (mle_iter) | bins [n_pad], q [n_pad] (gwalpha)
+        const int np = s->lay.n_pad;
+        std::vector<double> raw((size_t)(gwalpha ? 2 : k) * np, 0.0);
+        if (gwalpha) {
+            for (int i = 0; i < n_pools; i++) {
+                raw[i] = gw_bins[i];
+                raw[(size_t)np + i] = gw_q[i];
+            }
+            s->gw_sig = gw_fmt[0 * 3 + 2];
+            s->gw_min = gw_fmt[1 * 3 + 2];
+            s->gw_max = gw_fmt[2 * 3 + 2];
+            (void)gw_rows;
+        } else {
+            for (int j = 0; j < k; j++)
+                for (int i = 0; i < n_pools; i++) raw[(size_t)j * np + i] = phen[(size_t)i * k + j];
+        }
+        cudaError_t e = cudaMalloc(&s->d_yraw, raw.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(s->d_yraw, raw.data(), raw.size() * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            pg_scan_close(s);
+            return fail(ctx, PG_ERR_CUDA, "pg_scan_open: phenotype upload: %s", cudaGetErrorString(e));
+        }
+    }
     // pageable-memory copies may return before the DMA has landed and the batches' streams are non-blocking (not
     // ordered against the legacy stream): the phenotype, weight and p-table uploads are complete when this returns
     {
@@ -274,12 +320,14 @@ int pg_scan_close(pg_scan *s) {
     if (s->d_yc) cudaFree(s->d_yc);
     if (s->d_w) cudaFree(s->d_w);
     if (s->d_ptab) cudaFree(s->d_ptab);
+    if (s->d_yraw) cudaFree(s->d_yraw);
     delete s;
     return PG_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-static bool is_regression(const pg_scan *s) { return s->kind == PG_KIND_OLS || s->kind == PG_KIND_CORR; }
+static bool is_nm(const pg_scan *s) { return s->kind == PG_KIND_MLE || s->kind == PG_KIND_GWALPHA_LS || s->kind == PG_KIND_GWALPHA_ML; }
+static bool is_regression(const pg_scan *s) { return s->kind == PG_KIND_OLS || s->kind == PG_KIND_CORR || is_nm(s); }
 
 int pg_batch_create(pg_scan *s, int64_t cap, pg_batch **out) {
     if (!s || !out || cap < 1 || cap > 0x7FFFFFFFLL) return fail(s ? s->ctx : nullptr, PG_ERR_ARG, "pg_batch_create: bad argument (1 <= capacity < 2^31 loci)");
@@ -565,7 +613,8 @@ static int run_once(pg_batch *b, int *launches) {
         static const int warps_env = getenv("PG_WARPS") ? atoi(getenv("PG_WARPS")) : 0;
         static const int g_env = getenv("PG_G") ? atoi(getenv("PG_G")) : 0;
         static const int p_env = getenv("PG_P") ? atoi(getenv("PG_P")) : 0;
-        for (int base = 0; base < s->k; base += kpass) {
+        if (is_nm(s)) kpass = 1;  // one filter-only pass: keep-mask, allele order, mean frequencies
+        for (int base = 0; base < (is_nm(s) ? 1 : s->k); base += kpass) {
             pg::ScanParams p;
             memset(&p, 0, sizeof p);
             p.lay = s->lay;
@@ -574,7 +623,8 @@ static int run_once(pg_batch *b, int *launches) {
             p.dmin = b->d_dmin;
             p.hint = b->d_hint;
             p.n_loci = b->n_loci;
-            p.kind = s->kind;
+            p.kind = is_nm(s) ? PG_KIND_OLS : s->kind;
+            p.filter_only = is_nm(s) ? 1 : 0;
             p.weighted = s->weighted;
             p.maf = s->maf;
             p.one_minus_maf = 1.00 - s->maf;
@@ -614,6 +664,31 @@ static int run_once(pg_batch *b, int *launches) {
             p.p_override = p_env;
             PG_CUDA(ctx, pg::launch_scan(p, ctx->sm_count, b->stream));
             if (launches) (*launches) += 2;  // streaming kernel + fix-up kernel
+        }
+        if (is_nm(s)) {
+            pg::NmParams q;
+            memset(&q, 0, sizeof q);
+            q.lay = s->lay;
+            q.freq = b->d_freq;
+            q.depth = b->d_depth;
+            q.n_loci = b->n_loci;
+            q.kind = s->kind;
+            q.k = s->k;
+            q.yraw = s->d_yraw;
+            q.gw_sig = s->gw_sig;
+            q.gw_min = s->gw_min;
+            q.gw_max = s->gw_max;
+            q.df = s->df;
+            q.ln_beta = s->ln_beta;
+            q.ptab = s->d_ptab;
+            q.ptab_vmax = s->ptab_vmax;
+            q.ptab_inv_h = s->ptab_inv_h;
+            q.ptab_M = s->ptab_M;
+            for (int j = 0; j < s->A_dev; j++) q.codes[j] = s->codes_dev[j];
+            q.meta = b->d_meta;
+            q.stats = b->d_stats;
+            PG_CUDA(ctx, pg::launch_nm(q, ctx->sm_count, b->stream));
+            if (launches) (*launches)++;
         }
     } else {
         pg::TableParams p;

@@ -90,6 +90,7 @@ struct ScanParams {
     double syy[kMaxPhenPerPass];   // centred sum of squares
     double ymean[kMaxPhenPerPass]; // mean of the phenotype (the n < p branch needs the uncentred values)
     int y_has_nan;
+    int filter_only;      // mle_iter / gwalpha: phase 2 stops after the keep-mask, the allele order and the means
     uint8_t codes[8];     // allele code of device column j
     uint64_t *meta;
     double *freq_mean;
@@ -116,6 +117,26 @@ struct TableParams {
     uint64_t *meta;
     double *stats;
 };
+
+// parameters of the Nelder-Mead analyses (pg_nm.cu): mle_iter and gwalpha run after the scan kernel's filter-only pass
+struct NmParams {
+    Layout lay;
+    const double *freq;
+    const uint32_t *depth;
+    int64_t n_loci;
+    int kind;
+    int k;                 // phenotypes (mle) | 1 (gwalpha)
+    const double *yraw;    // mle: [k][n_pad] raw phenotypes; gwalpha: bins [n_pad] then q [n_pad]
+    double gw_sig, gw_min, gw_max;
+    double df, ln_beta;    // Student-t(n - 1)
+    const void *ptab;
+    double ptab_vmax, ptab_inv_h;
+    int ptab_M;
+    uint8_t codes[8];      // allele code of device column j
+    uint64_t *meta;
+    double *stats;         // [locus][A-1][k][4]
+};
+cudaError_t launch_nm(const NmParams &p, int sm_count, cudaStream_t s);
 
 // launchers implemented in the kernel translation units
 cudaError_t launch_scan(const ScanParams &p, int sm_count, cudaStream_t s);
@@ -190,6 +211,8 @@ struct pg_scan {
     double df = 0, ln_beta = 0;
     double *d_yc = nullptr;
     double *d_w = nullptr;
+    double *d_yraw = nullptr;   // mle_iter: raw phenotypes [k][n_pad]; gwalpha: bins [n_pad], q [n_pad]
+    double gw_sig = 0, gw_min = 0, gw_max = 0;  // gwalpha_fmt: sig, MIN, MAX
     double *d_ptab = nullptr;
     double ptab_vmax = 0, ptab_inv_h = 0, ptab_err = 0;
     int ptab_M = 0;

@@ -1,0 +1,486 @@
+// pg_nm.cu -- the Nelder-Mead analyses of the per-locus scan:
+//   mle_iter   gwas::mle_iterate  (src/gwas/mle.rs:232-305)    PG_KIND_MLE
+//   gwalpha    gwas::gwalpha_ls / gwalpha_ml (src/gwas/gwalpha.rs:282-386)   PG_KIND_GWALPHA_LS / _ML
+// Both start like ols_iter -- LocusCounts::filter, to_frequencies, sort_by_allele_freq, drop the major allele -- so the
+// streaming scan kernel runs first in its filter-only mode and leaves status, allele order (plus the major allele's
+// code) and mean frequencies; the kernels here read that, rebuild the renormalised frequency columns from the resident
+// frequency matrix, and minimise the reference's cost functions with argmin 0.8.1's Nelder-Mead as
+// `prepare_solver_neldermead` + `Executor::max_iters(1_000)` drive it (src/base/helpers.rs:132-146): the simplex steps
+// (reflection, expansion, outside / inside contraction, shrink; stable sort by cost; standard-deviation stop) are
+// those the CPU checker of this repository pins against the reference's own test_gwalpha lines, statement for statement.  A capped simplex search returns wherever its path ends, and the path turns on comparisons
+// of nearly equal costs, so agreement with the reference is to the solver's own convergence (declared in the tests),
+// not 1e-9 -- DESIGN.md 11.
+//   mle_iter: a warp per locus forms the centred moments of [x | y] once (lane = pool); the cost
+//       (n/2) ln(2 pi s2) + RSS(beta) / s2   (mle.rs:13-30, sic: no 1/2 on the second term)
+//   is then a quadratic form in beta -- O(p^2) per evaluation instead of O(n p) -- and lane j minimises phenotype j.
+//   gwalpha: a thread per (locus, allele); the cost sums squared differences (LS) or log10 differences (ML) of Beta
+//   cdfs, statrs' continued fraction with the shapes of the current vertex.
+#include "pg_device.cuh"
+#include "pg_internal.h"
+
+namespace pg {
+
+constexpr int kNmMaxD = 8;  // parameters: sigma2 + intercept + up to 5 alleles (mle), 4 shapes (gwalpha)
+
+__device__ __forceinline__ double bound_logit(double x, double lo, double hi) { return lo + ((hi - lo) / (1.00 + exp(-x))); }
+
+// argmin 0.8.1 Nelder-Mead: alpha 1, gamma 2, rho = sigma =
+// 0.5, sd_tolerance = f64::EPSILON, initial simplex h everywhere and h + 0.5 on the diagonal, stable sort by cost.
+template <typename Cost>
+__device__ void nelder_mead(const Cost &cost, int d, double h, int max_iters, double *best) {
+    double v[kNmMaxD + 1][kNmMaxD], c[kNmMaxD + 1];
+    const int nv = d + 1;
+    for (int i = 0; i < nv; i++)
+        for (int j = 0; j < d; j++) v[i][j] = (i == j) ? h + 0.5 : h;
+    for (int i = 0; i < nv; i++) c[i] = cost(v[i]);
+    auto sort = [&]() {
+        for (int a = 1; a < nv; a++) {
+            const double ca = c[a];
+            double va[kNmMaxD];
+            for (int j = 0; j < d; j++) va[j] = v[a][j];
+            int b = a - 1;
+            while (b >= 0 && ca < c[b]) {
+                c[b + 1] = c[b];
+                for (int j = 0; j < d; j++) v[b + 1][j] = v[b][j];
+                b--;
+            }
+            c[b + 1] = ca;
+            for (int j = 0; j < d; j++) v[b + 1][j] = va[j];
+        }
+    };
+    auto shrink = [&]() {
+        for (int i = 1; i < nv; i++) {
+            for (int j = 0; j < d; j++) v[i][j] = v[0][j] + (v[i][j] - v[0][j]) * 0.5;
+            c[i] = cost(v[i]);
+        }
+    };
+    sort();
+    for (int it = 0;; it++) {
+        double c0 = 0.0;
+        for (int i = 0; i < nv; i++) c0 = c0 + c[i];
+        c0 = c0 / (double)nv;
+        double ss = 0.0;
+        for (int i = 0; i < nv; i++) ss = ss + (c[i] - c0) * (c[i] - c0);
+        const double sd = sqrt(1.0 / ((double)nv - 1.0) * ss);
+        if (sd < kEps) break;
+        if (it >= max_iters) break;
+        double x0[kNmMaxD], xr[kNmMaxD], xt[kNmMaxD];
+        for (int j = 0; j < d; j++) x0[j] = v[0][j];
+        for (int i = 1; i < nv - 1; i++)
+            for (int j = 0; j < d; j++) x0[j] = x0[j] + v[i][j];
+        const double inv = 1.0 / (double)(nv - 1);
+        for (int j = 0; j < d; j++) x0[j] = x0[j] * inv;
+        for (int j = 0; j < d; j++) xr[j] = x0[j] + (x0[j] - v[nv - 1][j]) * 1.0;
+        const double fr = cost(xr);
+        if (fr < c[nv - 2] && fr >= c[0]) {
+            for (int j = 0; j < d; j++) v[nv - 1][j] = xr[j];
+            c[nv - 1] = fr;
+        } else if (fr < c[0]) {
+            for (int j = 0; j < d; j++) xt[j] = x0[j] + (xr[j] - x0[j]) * 2.0;
+            const double fe = cost(xt);
+            const bool take_e = fe < fr;
+            for (int j = 0; j < d; j++) v[nv - 1][j] = take_e ? xt[j] : xr[j];
+            c[nv - 1] = take_e ? fe : fr;
+        } else if (fr >= c[nv - 2]) {
+            if (fr < c[nv - 1]) {  // outside contraction
+                for (int j = 0; j < d; j++) xt[j] = x0[j] + (xr[j] - x0[j]) * 0.5;
+                const double fc = cost(xt);
+                if (fc <= fr) {
+                    for (int j = 0; j < d; j++) v[nv - 1][j] = xt[j];
+                    c[nv - 1] = fc;
+                } else {
+                    shrink();
+                }
+            } else {  // inside contraction
+                for (int j = 0; j < d; j++) xt[j] = x0[j] + (v[nv - 1][j] - x0[j]) * 0.5;
+                const double fc = cost(xt);
+                if (fc < c[nv - 1]) {
+                    for (int j = 0; j < d; j++) v[nv - 1][j] = xt[j];
+                    c[nv - 1] = fc;
+                } else {
+                    shrink();
+                }
+            }
+        } else {
+            shrink();  // only reachable with NaN costs
+        }
+        sort();
+    }
+    for (int j = 0; j < d; j++) best[j] = v[0][j];
+}
+
+// the renormalised frequency of (pool i, device column j) over the kept columns, as the scan forms it
+__device__ __forceinline__ void renorm_generic(const NmParams &p, const double *fl, const uint32_t *dl, int i, unsigned kept,
+                                               double *F) {
+    const int A = p.lay.A;
+    const uint32_t d = dl[i];
+    double c[PG_MAX_ALLELES], dk = 0.0;
+    for (int j = 0; j < A; j++) {
+        c[j] = (d == 0u) ? 0.0 : rint(fl[p.lay.freq_off(i, j)] * (double)d);
+        if ((kept >> j) & 1u) dk += c[j];
+    }
+    for (int j = 0; j < A; j++) F[j] = ((kept >> j) & 1u) ? ((dk == 0.0) ? nan("") : c[j] / dk) : 0.0;
+}
+
+// device column of an allele code
+__device__ __forceinline__ int col_of_code(const NmParams &p, unsigned code) {
+    for (int j = 0; j < p.lay.A; j++)
+        if (p.codes[j] == code) return j;
+    return 0;
+}
+
+// ---- mle_iter: one warp per locus ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mle_kernel(const NmParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int n = p.lay.n, n_pad = p.lay.n_pad, S = p.lay.A - 1, k = p.k;
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
+    for (int64_t locus = warp; locus < p.n_loci; locus += nwarps) {
+        const uint64_t mv = p.meta[locus];
+        if ((mv & 0xffu) != PG_LOCUS_OK) continue;
+        const int m = (int)((mv >> 8) & 0xffu);  // allele columns of X (the intercept comes on top)
+        int col[PG_MAX_SLOTS];
+        unsigned kept = 0;
+        for (int s = 0; s < m; s++) {
+            col[s] = col_of_code(p, (unsigned)((mv >> (16 + 8 * s)) & 0xffu));
+            kept |= 1u << col[s];
+        }
+        kept |= 1u << col_of_code(p, (unsigned)((mv >> (16 + 8 * m)) & 0xffu));  // the major allele
+        const double *fl = p.freq + (size_t)locus * p.lay.freq_stride();
+        const uint32_t *dl = p.depth + (size_t)locus * p.lay.depth_stride();
+        // means of the allele columns, then centred second moments (lane = pool)
+        double sx[PG_MAX_SLOTS];
+        for (int a = 0; a < PG_MAX_SLOTS; a++) sx[a] = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            double F[PG_MAX_ALLELES];
+            renorm_generic(p, fl, dl, i, kept, F);
+            for (int a = 0; a < m; a++) sx[a] += F[col[a]];
+        }
+        double xbar[PG_MAX_SLOTS];
+        for (int a = 0; a < PG_MAX_SLOTS; a++) xbar[a] = (a < m) ? warp_sum_fixed(sx[a]) / (double)n : 0.0;
+        double Sxx[PG_MAX_SLOTS][PG_MAX_SLOTS];
+        for (int a = 0; a < PG_MAX_SLOTS; a++)
+            for (int b = 0; b < PG_MAX_SLOTS; b++) Sxx[a][b] = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            double F[PG_MAX_ALLELES];
+            renorm_generic(p, fl, dl, i, kept, F);
+            for (int a = 0; a < m; a++)
+                for (int b = 0; b <= a; b++) Sxx[a][b] = fma(F[col[a]] - xbar[a], F[col[b]] - xbar[b], Sxx[a][b]);
+        }
+        for (int a = 0; a < m; a++)
+            for (int b = 0; b <= a; b++) {
+                Sxx[a][b] = warp_sum_fixed(Sxx[a][b]);
+                Sxx[b][a] = Sxx[a][b];
+            }
+        // remove_collinearities_in_x (mle.rs:56-83), literally, on |r| rounded to 7 digits like pearsons_correlation.
+        // X column c >= 1 is allele column c - 1; column 0 is the intercept (its correlation is NaN: never removed).
+        int xc[PG_MAX_SLOTS + 1], pw = m + 1;
+        for (int c = 0; c <= m; c++) xc[c] = c;
+        bool panic = false;
+        if (pw != 2) {
+            long i = 1;
+            while (i < pw && !panic) {
+                long j = i + 1;
+                while (j < pw) {
+                    if (i < 0) {
+                        panic = true;  // the reference's `i -= 1` underflows and its next column() call panics
+                        break;
+                    }
+                    double cor = nan("");
+                    if (xc[i] >= 1 && xc[j] >= 1) {
+                        const int a = xc[i] - 1, b = xc[j] - 1;
+                        const double r = Sxx[a][b] / (sqrt(Sxx[a][a]) * sqrt(Sxx[b][b]));
+                        cor = round(r * 1e7) / 1e7;
+                    }
+                    if (fabs(cor) >= 0.99) {
+                        for (int c = (int)j; c + 1 < pw; c++) xc[c] = xc[c + 1];
+                        pw -= 1;
+                        i -= 1;
+                        j -= 1;
+                    }
+                    j += 1;
+                }
+                i += 1;
+            }
+        }
+        int status = panic ? PG_LOCUS_PANIC : PG_LOCUS_OK;
+        if (status == PG_LOCUS_OK && n < pw) status = PG_LOCUS_UNSUPPORTED;  // the X X' form of the variances (mle.rs:130-140)
+        // (X'X)^-1 of the remaining columns through the centred moments: the allele block is Sxx^-1, the intercept's
+        // diagonal entry 1/n + xbar' Sxx^-1 xbar
+        const int q = pw - 1;  // allele columns left
+        double Si[PG_MAX_SLOTS][PG_MAX_SLOTS], dgi[PG_MAX_SLOTS + 1];
+        if (status == PG_LOCUS_OK) {
+            double M[PG_MAX_SLOTS][2 * PG_MAX_SLOTS];
+            for (int a = 0; a < q; a++)
+                for (int b = 0; b < q; b++) {
+                    M[a][b] = Sxx[xc[a + 1] - 1][xc[b + 1] - 1];
+                    M[a][q + b] = a == b ? 1.0 : 0.0;
+                }
+            for (int c = 0; c < q && status == PG_LOCUS_OK; c++) {  // Gauss-Jordan with partial pivoting
+                int pr = c;
+                for (int r = c + 1; r < q; r++)
+                    if (fabs(M[r][c]) > fabs(M[pr][c])) pr = r;
+                if (!(fabs(M[pr][c]) > 0.0)) {
+                    status = PG_LOCUS_FAILED;  // Non-invertible x_matrix (mle.rs:143-148)
+                    break;
+                }
+                for (int e = 0; e < 2 * q; e++) {
+                    const double tmp = M[c][e];
+                    M[c][e] = M[pr][e];
+                    M[pr][e] = tmp;
+                }
+                const double piv = 1.0 / M[c][c];
+                for (int e = 0; e < 2 * q; e++) M[c][e] *= piv;
+                for (int r = 0; r < q; r++) {
+                    if (r == c) continue;
+                    const double f = M[r][c];
+                    for (int e = 0; e < 2 * q; e++) M[r][e] -= f * M[c][e];
+                }
+            }
+            if (status == PG_LOCUS_OK) {
+                double quad = 0.0;
+                for (int a = 0; a < q; a++)
+                    for (int b = 0; b < q; b++) {
+                        Si[a][b] = M[a][q + b];
+                        quad += xbar[xc[a + 1] - 1] * Si[a][b] * xbar[xc[b + 1] - 1];
+                    }
+                dgi[0] = 1.0 / (double)n + quad;
+                for (int a = 0; a < q; a++) dgi[1 + a] = Si[a][a];
+            }
+        }
+        // phenotypes: lane j takes phenotype j (centred cross moments by the whole warp first)
+        for (int j0 = 0; j0 < k; j0 += 32) {
+            const int jn = min(32, k - j0);
+            double ybar_l = 0.0, syy_l = 0.0, sxy_l[PG_MAX_SLOTS];
+            for (int a = 0; a < PG_MAX_SLOTS; a++) sxy_l[a] = 0.0;
+            for (int jj = 0; jj < jn; jj++) {
+                const double *y = p.yraw + (size_t)(j0 + jj) * n_pad;
+                double sy = 0.0;
+                for (int i = lane; i < n; i += 32) sy += y[i];
+                const double ybar = warp_sum_fixed(sy) / (double)n;
+                double syy = 0.0, sxy[PG_MAX_SLOTS];
+                for (int a = 0; a < PG_MAX_SLOTS; a++) sxy[a] = 0.0;
+                for (int i = lane; i < n; i += 32) {
+                    double F[PG_MAX_ALLELES];
+                    renorm_generic(p, fl, dl, i, kept, F);
+                    const double dy = y[i] - ybar;
+                    syy = fma(dy, dy, syy);
+                    for (int a = 0; a < m; a++) sxy[a] = fma(F[col[a]] - xbar[a], dy, sxy[a]);
+                }
+                syy = warp_sum_fixed(syy);
+                for (int a = 0; a < PG_MAX_SLOTS; a++) sxy[a] = (a < m) ? warp_sum_fixed(sxy[a]) : 0.0;
+                if (lane == jj) {
+                    ybar_l = ybar;
+                    syy_l = syy;
+                    for (int a = 0; a < PG_MAX_SLOTS; a++) sxy_l[a] = sxy[a];
+                }
+            }
+            if (lane < jn) {
+                const int j = j0 + lane;
+                double b[PG_MAX_SLOTS + 1], vb[PG_MAX_SLOTS + 1];
+                for (int c = 0; c <= PG_MAX_SLOTS; c++) b[c] = vb[c] = 0.0;  // Array2::zeros: rows of removed columns
+                if (status == PG_LOCUS_OK) {
+                    const double nn = (double)n;
+                    // cost(par): par[0] = logit of sigma2, par[1] = intercept, par[2..] = remaining allele columns
+                    auto cost = [&](const double *par) {
+                        const double s2 = bound_logit(par[0], kEps, 1e9);
+                        double quad = 0.0, lin = 0.0, off = ybar_l - par[1];
+                        for (int a = 0; a < q; a++) {
+                            const int ia = xc[a + 1] - 1;
+                            lin += par[2 + a] * sxy_l[ia];
+                            off -= xbar[ia] * par[2 + a];
+                            for (int c = 0; c < q; c++) quad += par[2 + a] * Sxx[ia][xc[c + 1] - 1] * par[2 + c];
+                        }
+                        const double rss = (syy_l - 2.0 * lin + quad) + nn * off * off;
+                        return (nn / 2.00) * log(2.00 * 3.14159265358979323846264338327950288 * s2) + (1.00 / s2) * rss;
+                    };
+                    double par[kNmMaxD];
+                    nelder_mead(cost, pw + 1, 1.0, 1000, par);
+                    const double ve = bound_logit(par[0], kEps, 1e9);
+                    for (int c = 0; c < pw; c++) {
+                        b[c] = par[1 + c];
+                        vb[c] = ve * dgi[c];
+                    }
+                }
+                for (int s = 0; s < S; s++) {
+                    double o0 = nan(""), o1 = nan(""), o2 = nan(""), o3 = nan("");
+                    if (status == PG_LOCUS_OK && s < m) {
+                        // output row s is X column s + 1 of the UNREDUCED matrix: the reference fills rows 0..pw of a zero
+                        // matrix and never maps them back (mle.rs:218-226: "does not account for the identities of the
+                        // removed columns")
+                        const int c = s + 1;
+                        const bool filled = c < pw;
+                        o0 = filled ? b[c] : 0.0;
+                        o1 = filled ? vb[c] : 0.0;
+                        if (filled) {
+                            o2 = o0 / o1;  // mle.rs:176: the variance, not its square root
+                            if (isinf(o2))
+                                o3 = 0.0;
+                            else if (o2 != o2)
+                                o3 = 1.0;
+                            else
+                                o3 = p.ptab ? student_two_sided_tab(fabs(o2), p.df, ptab) : student_two_sided(fabs(o2), p.df, p.ln_beta);
+                        } else {
+                            o3 = 0.0;
+                        }
+                    }
+                    double *o = p.stats + (((size_t)locus * S + s) * k + j) * 4;
+                    o[0] = o0, o[1] = o1, o[2] = o2, o[3] = o3;
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && status != PG_LOCUS_OK) p.meta[locus] = (mv & ~0xffull) | (uint64_t)status;
+    }
+}
+
+// ---- gwalpha: one thread per (locus, allele) ------------------------------------------------------------------------
+constexpr int kGwMaxPools = 64;
+
+__device__ double nd_sum(const double *xs, int len) {  // ndarray 0.15 unrolled_fold (what `.sum()` does on a slice)
+    double acc = 0.0, p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0;
+    while (len >= 8) {
+        p0 = p0 + xs[0], p1 = p1 + xs[1], p2 = p2 + xs[2], p3 = p3 + xs[3];
+        p4 = p4 + xs[4], p5 = p5 + xs[5], p6 = p6 + xs[6], p7 = p7 + xs[7];
+        xs += 8;
+        len -= 8;
+    }
+    acc = acc + (p0 + p4);
+    acc = acc + (p1 + p5);
+    acc = acc + (p2 + p6);
+    acc = acc + (p3 + p7);
+    for (int i = 0; i < len && i < 7; i++) acc = acc + xs[i];
+    return acc;
+}
+
+// statrs Beta::cdf with the shapes' ln B precomputed
+__device__ __forceinline__ double beta_cdf_dev(double a, double b, double lnb, double x) {
+    if (x < 0.0) return 0.0;
+    if (x >= 1.0) return 1.0;
+    if (fabs(a - 1.0) <= 4.0 * 1.1102230246251565e-16 && fabs(b - 1.0) <= 4.0 * 1.1102230246251565e-16) return x;
+    return beta_reg_dev(a, b, x, lnb);
+}
+
+__global__ void __launch_bounds__(128) gwalpha_kernel(const NmParams p) {
+    const int S = p.lay.A - 1, n = p.lay.n, n_pad = p.lay.n_pad;
+    const int64_t total = p.n_loci * S;
+    const double *bins = p.yraw, *q = p.yraw + n_pad;
+    for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
+         item += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t locus = item / S;
+        const int s = (int)(item - locus * S);
+        const uint64_t mv = p.meta[locus];
+        double *o = p.stats + ((size_t)locus * S + s) * 4;
+        const int m = (int)((mv >> 8) & 0xffu);
+        if ((mv & 0xffu) != PG_LOCUS_OK || s >= m) {
+            o[0] = o[1] = o[2] = o[3] = nan("");
+            continue;
+        }
+        unsigned kept = 0;
+        for (int a = 0; a <= m; a++) kept |= 1u << col_of_code(p, (unsigned)((mv >> (16 + 8 * a)) & 0xffu));
+        const int cj = col_of_code(p, (unsigned)((mv >> (16 + 8 * s)) & 0xffu));
+        const double *fl = p.freq + (size_t)locus * p.lay.freq_stride();
+        const uint32_t *dl = p.depth + (size_t)locus * p.lay.depth_stride();
+        // prepare_freqs_and_qprime (gwalpha.rs:225-280)
+        double fa[kGwMaxPools], qp[kGwMaxPools], pa[kGwMaxPools], pb[kGwMaxPools], pa0[kGwMaxPools], pb0[kGwMaxPools];
+        double p_a = 0.0;
+        for (int i = 0; i < n; i++) {
+            double F[PG_MAX_ALLELES];
+            renorm_generic(p, fl, dl, i, kept, F);
+            fa[i] = F[cj];
+        }
+        if (m == 1) {  // a one-column matrix: the column view is contiguous and ndarray takes its unrolled dot
+            double prod[kGwMaxPools];
+            double s0 = 0.0, ps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int len = n, at = 0;
+            while (len >= 8) {
+                for (int e = 0; e < 8; e++) ps[e] = ps[e] + fa[at + e] * bins[at + e];
+                at += 8;
+                len -= 8;
+            }
+            s0 = s0 + (ps[0] + ps[4]);
+            s0 = s0 + (ps[1] + ps[5]);
+            s0 = s0 + (ps[2] + ps[6]);
+            s0 = s0 + (ps[3] + ps[7]);
+            for (int i = 0; i < len && i < 7; i++) s0 = s0 + fa[at + i] * bins[at + i];
+            p_a = s0;
+            (void)prod;
+        } else {
+            for (int i = 0; i < n; i++) p_a += fa[i] * bins[i];
+        }
+        qp[0] = 0.0;
+        for (int i = 1; i < n; i++) qp[i] = (q[i] - p.gw_min) / (p.gw_max - p.gw_min);
+        {
+            double ba[kGwMaxPools], bb[kGwMaxPools];
+            for (int i = 0; i < n; i++) {
+                ba[i] = (fa[i]) * bins[i] / (p_a);
+                bb[i] = (1.0 - fa[i]) * bins[i] / (1.0 - p_a);
+            }
+            pa[0] = ba[0];
+            pb[0] = bb[0];
+            for (int i = 1; i < n; i++) {
+                pa[i] = nd_sum(ba, i + 1);
+                pb[i] = nd_sum(bb, i + 1);
+            }
+        }
+        pa0[0] = pb0[0] = 0.0;
+        for (int i = 0; i < n - 1; i++) {
+            pa0[i + 1] = pa[i];
+            pb0[i + 1] = pb[i];
+        }
+        const bool ml = p.kind == PG_KIND_GWALPHA_ML;
+        auto cost = [&](const double *par) {
+            double sh[4];
+            for (int e = 0; e < 4; e++) sh[e] = bound_logit(par[e], kEps, 10.00);
+            const double lna = ln_gamma_dev(sh[0] + sh[1]) - ln_gamma_dev(sh[0]) - ln_gamma_dev(sh[1]);
+            const double lnb = ln_gamma_dev(sh[2] + sh[3]) - ln_gamma_dev(sh[2]) - ln_gamma_dev(sh[3]);
+            double ra = 0.0, rb = 0.0;
+            if (!ml) {  // least_squares_beta (gwalpha.rs:11-41)
+                for (int i = 0; i < n; i++) {
+                    const double da = pa[i] - beta_cdf_dev(sh[0], sh[1], lna, qp[i]);
+                    const double db = pb[i] - beta_cdf_dev(sh[2], sh[3], lnb, qp[i]);
+                    ra += da * da;
+                    rb += db * db;
+                }
+                return ra + rb;
+            }
+            for (int i = 0; i < n; i++) {  // maximum_likelihood_beta (gwalpha.rs:43-82)
+                double da = beta_cdf_dev(sh[0], sh[1], lna, pa[i]) - beta_cdf_dev(sh[0], sh[1], lna, pa0[i]);
+                double db = beta_cdf_dev(sh[2], sh[3], lnb, pb[i]) - beta_cdf_dev(sh[2], sh[3], lnb, pb0[i]);
+                if (da < kEps) da = kEps;
+                if (db < kEps) db = kEps;
+                ra += log10(da);
+                rb += log10(db);
+            }
+            return -ra - rb;
+        };
+        double par[kNmMaxD];
+        nelder_mead(cost, 4, 1.0, 1000, par);
+        double sol[4];
+        for (int e = 0; e < 4; e++) sol[e] = bound_logit(par[e], kEps, 10.00);
+        const double a_mu = p.gw_min + (p.gw_max - p.gw_min) * (sol[0] / (sol[0] + sol[1]));
+        const double b_mu = p.gw_min + (p.gw_max - p.gw_min) * (sol[2] / (sol[2] + sol[3]));
+        const double alpha = (2.00 * sqrt(p_a * (1.0 - p_a))) * (a_mu - b_mu) / p.gw_sig;
+        o[0] = alpha;
+        o[1] = p_a;
+        o[2] = nan("");
+        o[3] = nan("");
+    }
+}
+
+cudaError_t launch_nm(const NmParams &p, int sm_count, cudaStream_t s) {
+    if (p.n_loci == 0) return cudaSuccess;
+    if (p.kind == PG_KIND_MLE) {
+        int64_t grid = (p.n_loci * 32 + 127) / 128;
+        if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
+        mle_kernel<<<(unsigned)grid, 128, 0, s>>>(p);
+    } else {
+        int64_t grid = (p.n_loci * (p.lay.A - 1) + 127) / 128;
+        if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
+        gwalpha_kernel<<<(unsigned)grid, 128, 0, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace pg

@@ -971,6 +971,7 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
                 if (cs[l] > cs[j] || (cs[l] == cs[j] && l < j)) rank++;
             }
             if (rank >= 1) cb |= (unsigned)j << (4 * (rank - 1));
+            else cb |= (unsigned)j << 20;  // the major allele (dropped from the regressors; mle_iter / gwalpha need it)
         }
     } else {
         // kept columns in file order, the last one is dropped (correlation_test.rs:94-98)
@@ -993,7 +994,10 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
         }
     }
     if (kind_is_ols<KIND>(p)) {
-        if (has_nan) {
+        if (p.filter_only) {
+            // mle_iter / gwalpha: only the keep-mask, the allele order and the mean frequencies are wanted here; the
+            // statistics come from the Nelder-Mead kernels (pg_nm.cu)
+        } else if (has_nan) {
             for (int i = 0; i < T2; i++) tg[i] = nan("");
         } else if (lay.n < m + 1) {
             // fewer pools than coefficients: the minimum-norm branch (src/gwas/ols.rs:67-75), left to the fix-up kernel
@@ -1107,6 +1111,8 @@ __device__ __noinline__ void write_records(const ScanParams &p, const PTableDev 
 #pragma unroll
             for (int s = 0; s < A - 1; s++)
                 if (s < m) mv |= (uint64_t)p.codes[slot_col(cb, s)] << (16 + 8 * s);
+            // the byte after the output rows' codes: the major allele (ols_iter; read by the Nelder-Mead kernels only)
+            if (kind_is_ols<KIND>(p) && m < 6) mv |= (uint64_t)p.codes[(cb >> 20) & 0xfu] << (16 + 8 * m);
         }
         p.meta[locus] = mv;
 #pragma unroll

@@ -182,9 +182,9 @@ void format_range(int kind, const pg_results *res, const pg_row_labels *lab, int
     const Rounder r6(6), r8(8), r12(12);
     // PG_FORMAT_EXACT_P: the p-value is re-derived on the host from the record's t statistic with the reference's own
     // arithmetic (statrs' continued fraction, df = n - 1 for ols_iter, n - 2 for pearson_corr)
-    const bool exact_p = (flags & PG_FORMAT_EXACT_P) && (kind == PG_KIND_OLS || kind == PG_KIND_CORR) &&
-                         (double)n_pools - (kind == PG_KIND_OLS ? 1.0 : 2.0) > 0.0;
-    const pg::statrs::TwoSidedT tail(exact_p ? (double)n_pools - (kind == PG_KIND_OLS ? 1.0 : 2.0) : 1.0);
+    const bool exact_p = (flags & PG_FORMAT_EXACT_P) && (kind == PG_KIND_OLS || kind == PG_KIND_CORR || kind == PG_KIND_MLE) &&
+                         (double)n_pools - (kind != PG_KIND_CORR ? 1.0 : 2.0) > 0.0;
+    const pg::statrs::TwoSidedT tail(exact_p ? (double)n_pools - (kind != PG_KIND_CORR ? 1.0 : 2.0) : 1.0);
     char line[1024];
     out.reserve((size_t)(hi - lo) * 64 * (size_t)(S * k > 0 ? S * k : 1) / 2 + 4096);
     for (int64_t l = lo; l < hi; l++) {
@@ -203,7 +203,24 @@ void format_range(int kind, const pg_results *res, const pg_row_labels *lab, int
         h = put_u64(lab->positions[l], h);
         *h++ = ',';
         const size_t hn = (size_t)(h - head);
-        if (kind == PG_KIND_OLS || kind == PG_KIND_CORR) {
+        if (kind == PG_KIND_GWALPHA_LS || kind == PG_KIND_GWALPHA_ML) {
+            // gwalpha_ls / gwalpha_ml (src/gwas/gwalpha.rs:320-331): chr,pos,allele,freq r6,Pheno_0,alpha r6,Unknown
+            for (int s = 0; s < n_out && s < S; s++) {
+                const double *st = res->stats + ((size_t)l * S + s) * (size_t)k * 4;
+                char *o = line;
+                memcpy(o, head, hn);
+                o += hn;
+                *o++ = kAlleleNames[(mv >> (16 + 8 * s)) & 0xffu];
+                *o++ = ',';
+                o = r6.put(res->freq_mean[(size_t)l * S + s], o);
+                memcpy(o, ",Pheno_0,", 9);
+                o += 9;
+                o = r6.put(st[0], o);
+                memcpy(o, ",Unknown\n", 9);
+                o += 9;
+                out.append(line, (size_t)(o - line));
+            }
+        } else if (kind == PG_KIND_OLS || kind == PG_KIND_CORR || kind == PG_KIND_MLE) {
             for (int s = 0; s < n_out && s < S; s++) {
                 const double fm = res->freq_mean[(size_t)l * S + s];
                 const char an = kAlleleNames[(mv >> (16 + 8 * s)) & 0xffu];
@@ -214,7 +231,7 @@ void format_range(int kind, const pg_results *res, const pg_row_labels *lab, int
                     o += hn;
                     *o++ = an;
                     *o++ = ',';
-                    o = (kind == PG_KIND_OLS) ? r8.put(fm, o) : put_f64(fm, o);
+                    o = (kind != PG_KIND_CORR) ? r8.put(fm, o) : put_f64(fm, o);
                     memcpy(o, ",Pheno_", 7);
                     o += 7;
                     o = put_u64((uint64_t)j, o);
@@ -267,6 +284,9 @@ int pg_format_header(int kind, char *out, size_t capacity, size_t *n_bytes) {
     const char *h;
     switch (kind) {
         case PG_KIND_OLS:
+        case PG_KIND_MLE:
+        case PG_KIND_GWALPHA_LS:
+        case PG_KIND_GWALPHA_ML:
         case PG_KIND_CORR: h = "#chr,pos,alleles,freq,phenotype,statistic,pvalue\n"; break;  // src/base/sync.rs:950
         case PG_KIND_CHISQ:
         case PG_KIND_FISHER: h = "#chr,pos,alleles,statistic,pvalue\n"; break;               // src/base/sync.rs:766
@@ -287,7 +307,8 @@ int pg_format_rows(int kind, const pg_results *res, const pg_row_labels *labels,
 
 int pg_format_rows_ex(int kind, const pg_results *res, const pg_row_labels *labels, int flags, int n_pools,
                       int n_threads, char *out, size_t capacity, size_t *n_bytes) {
-    if (!res || !labels || !labels->positions || kind < PG_KIND_OLS || kind > PG_KIND_FISHER) return PG_ERR_ARG;
+    if (!res || !labels || !labels->positions) return PG_ERR_ARG;
+    if (!((kind >= PG_KIND_OLS && kind <= PG_KIND_FISHER) || (kind >= PG_KIND_MLE && kind <= PG_KIND_GWALPHA_ML))) return PG_ERR_ARG;
     if (labels->text ? !labels->line_offsets : (!labels->chr_names || !labels->chr_index)) return PG_ERR_ARG;
     const int64_t L = res->n_loci;
     if (L > 0 && (!res->meta || !res->stats)) return PG_ERR_ARG;

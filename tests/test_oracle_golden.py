@@ -135,3 +135,57 @@ def test_tight_cpu_baseline_is_bit_identical_to_the_faithful_one():
     assert (a.status != pgo.FILTERED).sum() == 2032  # pass the filter; a few then fail the regression
     for f in fields:
         assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
+
+
+def _gwalpha_example():
+    """the inputs of the reference's test_gwalpha (src/gwas/gwalpha.rs:399-441)"""
+    counts = np.array([5, 2, 6, 2, 2, 7, 3, 2, 5, 4, 3, 3, 5, 5, 0], dtype=np.uint64).reshape(5, 3)
+    fmt = np.array([0.2, 0.2, 0.2, 0.2, 0.2, 0.0, 0.1, 0.4, 0.7, 0.9, 0.02, 0.0, 0.9, -np.inf, -np.inf]).reshape(3, 5).T.copy()
+    fs = pgo.FilterStats(pool_sizes=np.array([20.0] * 5), remove_ns=True, min_coverage_depth=1,
+                         min_allele_frequency=0.005, max_missingness_rate=0.0)
+    return counts, np.array([0, 1, 5], dtype=np.uint8), fmt, fs
+
+
+def test_gwalpha_lines_pin_the_nelder_mead_restatement():
+    """src/gwas/gwalpha.rs:392-447 (test_gwalpha): the two output lines of gwalpha_ls and of gwalpha_ml.  They go through
+    argmin's Nelder-Mead (1,000-iteration cap), statrs' Beta::cdf and bound_parameters_with_logit, so they pin the
+    oracle's restatement of the solver (reflection / expansion / outside and inside contraction / shrink, stable sort,
+    standard-deviation stop) to the six printed digits -- for BOTH cost functions and all four searches."""
+    counts, alleles, fmt, fs = _gwalpha_example()
+    ls = pgo.format_gwalpha_lines("Chromosome1", 12345, pgo.gwalpha(counts, alleles, fmt, fs, "LS"))
+    ml = pgo.format_gwalpha_lines("Chromosome1", 12345, pgo.gwalpha(counts, alleles, fmt, fs, "ML"))
+    assert ls == "Chromosome1,12345,A,0.353287,Pheno_0,5.816067,Unknown\nChromosome1,12345,T,0.267133,Pheno_0,9.176892,Unknown\n"
+    assert ml == "Chromosome1,12345,A,0.353287,Pheno_0,-3.293261,Unknown\nChromosome1,12345,T,0.267133,Pheno_0,-7.098985,Unknown\n"
+
+
+def test_bound_parameters_with_logit():
+    """src/base/helpers.rs:120-129"""
+    eps = np.finfo(float).eps
+    assert pgo.bound_logit(0.0, eps, 1e9) == eps + (1e9 - eps) / 2.0
+    assert pgo.bound_logit(-800.0, eps, 10.0) == eps          # exp(800) = inf: the lower limit
+    assert abs(pgo.bound_logit(40.0, eps, 10.0) - 10.0) < 1e-14
+
+
+def test_mle_iterate_converges_to_the_closed_form():
+    """mle_iterate (src/gwas/mle.rs:232-305) minimises (n/2) ln(2 pi s2) + RSS(beta) / s2: at the optimum beta is the OLS
+    solution and s2 = 2 RSS / n (the reference's cost has no 1/2 on its second term).  The simplex search is capped at
+    1,000 iterations, so the restatement is held to the solver's own convergence, not to 1e-9."""
+    import poolgen_b200 as pb
+    n, A, k, L = 30, 4, 2, 150
+    counts = pb.synth_counts_host(0x31E, 0, L, n, A)
+    phen = pb.synth_phen_host(0x31E, n, k)
+    fs = pgo.FilterStats(pool_sizes=np.full(n, 1.0 / n))
+    codes = np.arange(A, dtype=np.uint8)
+    m = pgo.scan_batch(pgo.SCAN_MLE, counts, codes, phen, fs, 4)
+    o = pgo.scan_batch(pgo.SCAN_OLS, counts, codes, phen, fs, 4)
+    ok = (m.status == pgo.OK) & (o.status == pgo.OK)
+    assert ok.sum() > 100 and ((m.status == pgo.FILTERED) == (o.status == pgo.FILTERED)).all()
+    assert (m.n_out[ok] == o.n_out[ok]).all() and (m.allele[ok] == o.allele[ok]).all()
+    sel = ~np.isnan(o.stat[ok])
+    rel = np.abs(m.stat[ok] - o.stat[ok])[sel] / np.maximum(np.abs(o.stat[ok])[sel], np.sqrt(o.var[ok])[sel])
+    assert np.median(rel) < 1e-6 and np.quantile(rel, 0.9) < 1e-3
+    # v_b = s2 diag((X'X)^-1) with s2 = 2 RSS / n = 2 (n - p) / n times the OLS residual variance
+    p_x = m.n_out[ok].astype(float)[:, None, None] + 1.0
+    ratio = (m.var[ok] / o.var[ok])[sel]
+    expect = np.broadcast_to(2.0 * (n - p_x) / n, m.var[ok].shape)[sel]
+    assert np.median(np.abs(ratio / expect - 1.0)) < 1e-5
