@@ -340,6 +340,7 @@ def run_cuda(args):
             extras = c2_numbers(ctx, pb)
             extras.update(c5_numbers(ctx, pb, args.c5_loci))
             extras.update(text_numbers(ctx, pb))
+            extras.update(nm_numbers(ctx, pb))
         kin = c4_numbers(ctx, pb, dist, rank, world)  # every rank takes part (column shards + all-reduce)
         if rank == 0:
             extras.update(kin)
@@ -389,7 +390,8 @@ def run_cuda(args):
         }
         # the other BASELINE configs, top level so that they survive the driver's parse of this line
         for key, names in (("c2", ("c2_ols_iter", "c2_pearson_corr")), ("c5", ("c5_chisq_test", "c5_fisher_exact_test")),
-                           ("c4", ("c4_kinship",)), ("text", ("e2e_sync_text", "e2e_text_to_csv"))):
+                           ("c4", ("c4_kinship",)), ("text", ("e2e_sync_text", "e2e_text_to_csv")),
+                           ("nelder_mead", ("nelder_mead",))):
             got = {n: extras[n] for n in names if n in extras}
             if got:
                 line[key] = got[names[0]] if len(names) == 1 else got
@@ -450,6 +452,40 @@ def c5_numbers(ctx, pb, L=50_000_000):
         b.close()
         scan.close()
     return out
+
+
+def nm_numbers(ctx, pb):
+    """the Nelder-Mead analyses.  mle_iter on the C2 shape (100 pools, 1 phenotype) and gwalpha (LS,
+    ML) on 5 pools: filter-only scan pass + simplex kernel (1,000-iteration cap per search).  Compute-bound by design
+    (the reference's own algorithm): reported as loci/s, no roofline claim."""
+    out = {}
+    n, A, k, L = 100, 4, 1, 200_000
+    phen = pb.synth_phen_host(0x5EED0002, n, k)
+    fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n))
+    scan = pb.Scan(ctx, pb.KIND_MLE, fs, n, np.arange(A, dtype=np.uint8), phen)
+    b = scan.batch(L)
+    b.synth(0x5EED0002, 0, L)
+    b.time_runs(1)
+    ms, _ = b.time_runs(2)
+    out["mle_iter_c2_shape"] = {"loci_per_s": L / (ms / 2 * 1e-3), "ms": ms / 2, "loci": L, "n_pools": n, "n_phen": k}
+    b.close()
+    scan.close()
+    n, L = 5, 200_000
+    fmt = np.full((5, 3), -np.inf)
+    fmt[:, 0] = 0.2
+    fmt[:, 1] = (0.0, 0.1, 0.4, 0.7, 0.9)
+    fmt[:3, 2] = (0.02, 0.0, 0.9)
+    fs = pb.FilterStats(pool_sizes=np.full(n, 0.2))
+    for name, kind in (("gwalpha_ls_5_pools", pb.KIND_GWALPHA_LS), ("gwalpha_ml_5_pools", pb.KIND_GWALPHA_ML)):
+        scan = pb.Scan(ctx, kind, fs, n, np.arange(A, dtype=np.uint8), fmt)
+        b = scan.batch(L)
+        b.synth(0x5EED0005, 0, L)
+        b.time_runs(1)
+        ms, _ = b.time_runs(2)
+        out[name] = {"loci_per_s": L / (ms / 2 * 1e-3), "ms": ms / 2, "loci": L, "n_pools": n}
+        b.close()
+        scan.close()
+    return {"nelder_mead": out}
 
 
 def text_numbers(ctx, pb, n_threads=2):

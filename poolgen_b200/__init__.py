@@ -19,7 +19,7 @@ __all__ = ["FilePhen", "FileSync", "FileSyncPhen", "Phen", "find_file_splits", "
            "ScanResults", "synth_counts_host", "synth_phen_host", "synth_sync_text_host", "ols_iterate", "correlation", "chisq", "fisher",
            "ols_with_covariate", "format_f64", "format_header", "format_kinship_rows", "format_rows", "format_frequency_header",
            "format_frequency_rows", "sort_loci", "Comm", "shard_range", "nccl_version", "KIND_MLE", "KIND_GWALPHA_LS",
-           "KIND_GWALPHA_ML", "mle_iterate", "gwalpha"]
+           "KIND_GWALPHA_ML", "mle_iterate", "gwalpha", "gwalpha_ls", "gwalpha_ml"]
 
 _SYNC_CODES = (0, 1, 2, 3, 4, 5)
 
@@ -61,6 +61,14 @@ def gwalpha(ctx, counts, gwalpha_fmt, filter_stats, method="LS", allele_codes=_S
     """gwas::gwalpha_ls / gwalpha_ml over a batch (src/gwas/gwalpha.rs:282-386); gwalpha_fmt [rows, 3]: column 0 bins,
     column 1 q, column 2 = sig, MIN, MAX, then -inf.  stats[..., 0, 0] = alpha."""
     return _run(KIND_GWALPHA_LS if method == "LS" else KIND_GWALPHA_ML, ctx, counts, filter_stats, gwalpha_fmt, allele_codes)
+
+
+def gwalpha_ls(ctx, counts, gwalpha_fmt, filter_stats, allele_codes=_SYNC_CODES):
+    return gwalpha(ctx, counts, gwalpha_fmt, filter_stats, "LS", allele_codes)
+
+
+def gwalpha_ml(ctx, counts, gwalpha_fmt, filter_stats, allele_codes=_SYNC_CODES):
+    return gwalpha(ctx, counts, gwalpha_fmt, filter_stats, "ML", allele_codes)
 
 
 def ols_with_covariate(ctx, columns, phen, xxt_eigen_variance_explained=0.75):

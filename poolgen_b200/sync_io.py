@@ -17,7 +17,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import capi
-from .capi import KIND_CHISQ, KIND_CORR, KIND_FISHER, KIND_OLS, Context, FilterStats, PgError, Scan
+from .capi import (KIND_CHISQ, KIND_CORR, KIND_FISHER, KIND_GWALPHA_LS, KIND_GWALPHA_ML, KIND_MLE, KIND_OLS, Context,
+                   FilterStats, PgError, Scan)
 
 _MISSING = {"", "NA", "NAN", "NaN", "na", "nan"}  # src/base/phen.rs:66-72
 
@@ -101,7 +102,8 @@ def find_file_splits(fname: str, n_threads: int) -> list:
     return dedup
 
 
-_KIND_NAMES = {KIND_OLS: "ols_iter", KIND_CORR: "pearson_corr", KIND_CHISQ: "chisq_test", KIND_FISHER: "fisher_exact_test"}
+_KIND_NAMES = {KIND_OLS: "ols_iter", KIND_CORR: "pearson_corr", KIND_CHISQ: "chisq_test", KIND_FISHER: "fisher_exact_test",
+               KIND_MLE: "mle_iter", KIND_GWALPHA_LS: "gwalpha", KIND_GWALPHA_ML: "gwalpha"}
 
 
 def _kind_of(function) -> int:
@@ -109,7 +111,8 @@ def _kind_of(function) -> int:
     if isinstance(function, int):
         return function
     name = getattr(function, "__name__", str(function))
-    table = {"ols_iterate": KIND_OLS, "correlation": KIND_CORR, "chisq": KIND_CHISQ, "fisher": KIND_FISHER}
+    table = {"ols_iterate": KIND_OLS, "correlation": KIND_CORR, "chisq": KIND_CHISQ, "fisher": KIND_FISHER,
+             "mle_iterate": KIND_MLE, "gwalpha_ls": KIND_GWALPHA_LS, "gwalpha_ml": KIND_GWALPHA_ML}
     if name not in table:
         raise PgError(f"unknown per-locus function {name!r}")
     return table[name]
@@ -252,10 +255,11 @@ class FileSyncPhen:
     def read_analyse_write(self, ctx: Context, filter_stats: FilterStats, out: str, n_threads: int, function,
                            block_bytes: int = 32 << 20) -> str:
         """`read_analyse_write(&self, &FilterStats, out, n_threads, function)` (src/base/sync.rs:872-970) for
-        function = ols_iterate | correlation: returns the output file name"""
+        function = ols_iterate | correlation | mle_iterate | gwalpha_ls | gwalpha_ml (for the last two phen_matrix is
+        the gwalpha_fmt matrix, src/main.rs:335-358): returns the output file name"""
         kind = _kind_of(function)
-        if kind not in (KIND_OLS, KIND_CORR):
-            raise PgError("FileSyncPhen::read_analyse_write takes gwas::ols_iterate or gwas::correlation")
+        if kind not in (KIND_OLS, KIND_CORR, KIND_MLE, KIND_GWALPHA_LS, KIND_GWALPHA_ML):
+            raise PgError("FileSyncPhen::read_analyse_write takes gwas::ols_iterate, correlation, mle_iterate or gwalpha_ls / _ml")
         return _read_analyse_write(ctx, kind, filter_stats, len(self.pool_names), self.phen_matrix, self.filename_sync,
                                    self.test, out, n_threads, block_bytes)
 

@@ -6,8 +6,8 @@ Tolerance, declared up front: both sides run the same capped simplex search (1,0
 comparisons of nearly equal costs; the device evaluates the mle_iter cost as a quadratic form of centred moments
 (O(p^2) per evaluation) where the reference walks the residuals (O(n p)), and its libm differs from the host's in the
 last bit.  A path that splits ends at a different point of the flat valley around the optimum, so agreement is to the
-solver's convergence: medians at 1e-6, every locus within a few 1e-3 of the coefficient's own standard error -- not
-the 1e-9 of the closed-form analyses.  The keep-mask, the allele order and the mean frequencies are bit-exact."""
+solver's convergence: medians at 1e-6 or better, every value within 1e-3 (relative to the coefficient or its standard
+error; measured maxima 4e-6) -- not the 1e-9 of the closed-form analyses.  The keep-mask, the allele order and the mean frequencies are bit-exact."""
 import numpy as np
 import pytest
 
@@ -74,10 +74,8 @@ def test_gwalpha_synthetic(ctx, method, n, A, L):
     a_o, a_d = orc.stat[ok][:, :S, 0][slot], dev.stats[ok][:, :, 0, 0][slot]
     err = np.abs(a_d - a_o) / np.maximum(np.abs(a_o), 1.0)
     print(f"gwalpha {method} n={n}: {slot.sum()} alphas, median err {np.median(err):.2e}, 99% {np.quantile(err, 0.99):.2e}, max {err.max():.2e}")
-    assert np.median(err) < 1e-5 and np.quantile(err, 0.9) < 1e-3
-    # both sides stop at the same kind of point: the device's cost is not worse than the oracle's by more than the
-    # solver's own resolution -- checked through alpha's spread only where the searches visibly split
-    assert (err < 0.5).mean() > 0.97
+    # measured on B200 (profiles/README.md): medians 1e-8, maxima 2e-7
+    assert np.median(err) < 1e-6 and err.max() < 1e-4
 
 
 @pytest.mark.parametrize("n,A,k,L", [(30, 4, 2, 400), (100, 4, 1, 300), (6, 6, 3, 400), (1000, 4, 3, 60)])
@@ -106,10 +104,41 @@ def test_mle_iter_synthetic(ctx, n, A, k, L):
     ep = np.abs(p_d - p_o) / np.maximum(p_o, 1e-12)
     print(f"mle_iter n={n} k={k}: {slot.sum()} coefficients, beta err median {np.median(eb):.2e} max {eb.max():.2e}; "
           f"v_b err median {np.median(ev):.2e} max {ev.max():.2e}; p err median {np.median(ep):.2e} max {ep.max():.2e}")
-    assert np.median(eb) < 1e-5 and np.quantile(eb, 0.95) < 5e-3
-    assert np.median(ev) < 1e-5 and np.quantile(ev, 0.95) < 5e-3
-    assert np.median(ep) < 1e-4
+    # measured on B200 (profiles/README.md): beta medians 1e-8 .. 3e-7, maxima 4e-6; p maxima 2.4e-6
+    assert np.median(eb) < 5e-6 and eb.max() < 1e-3
+    assert np.median(ev) < 1e-6 and ev.max() < 1e-3
+    assert np.median(ep) < 5e-6 and ep.max() < 1e-3
     # rows text: beta rounded to 6 digits, p printed in full
     rows = pb.format_rows(pb.KIND_MLE, dev, np.arange(1, L + 1), chr_names=["chr1"], chr_index=np.zeros(L, np.uint32)).decode()
     first = rows.split("\n")[0].split(",")
     assert len(first) == 7 and first[4] == "Pheno_0"
+
+
+def test_file_level_mle_iter_and_gwalpha(ctx, tmp_path):
+    """`poolgen mle_iter` / `poolgen gwalpha` from a sync file (src/main.rs:299-358): FileSyncPhen::read_analyse_write with
+    the new callbacks over the reference's tests/test.sync (5 pools), rows in file order"""
+    from tests.test_text_gpu import _sync_text
+    c1 = H.load_c1()
+    L = 600
+    counts = c1["counts"][:L]
+    names = [str(s) for s in c1["chrom_names"]]
+    chroms = [names[i] for i in c1["chrom_idx"][:L]]
+    pos = [int(p) for p in c1["pos"][:L]]
+    fsync = tmp_path / "t.sync"
+    fsync.write_bytes(_sync_text(counts, chroms, pos))
+    fs = pb.FilterStats(pool_sizes=c1["pool_sizes"], min_coverage_depth=10, min_allele_frequency=0.01)
+    src = pb.FileSyncPhen(str(fsync), [f"p{i}" for i in range(5)], c1["pool_sizes"], c1["phen"], "mle_iter")
+    out = src.read_analyse_write(ctx, fs, str(tmp_path / "mle.csv"), 2, pb.mle_iterate, block_bytes=16 << 10)
+    lines = open(out).read().strip().split("\n")
+    assert lines[0] == "#chr,pos,alleles,freq,phenotype,statistic,pvalue" and len(lines) > 100
+    dev = pb.mle_iterate(ctx, counts, c1["phen"], fs, c1["codes"])
+    expect = pb.format_rows(pb.KIND_MLE, dev, pos, chr_names=names, chr_index=c1["chrom_idx"][:L], exact_p_pools=5).decode()
+    assert "\n".join(lines[1:]) + "\n" == expect
+    rng = np.random.default_rng(5)
+    fmt = _gwalpha_fmt(5, rng)
+    srcg = pb.FileSyncPhen(str(fsync), [f"p{i}" for i in range(5)], c1["pool_sizes"], fmt, "gwalpha")
+    outg = srcg.read_analyse_write(ctx, fs, str(tmp_path / "gw.csv"), 2, pb.gwalpha_ml, block_bytes=16 << 10)
+    gl = open(outg).read().strip().split("\n")
+    assert len(gl) > 100 and all(l.endswith(",Unknown") for l in gl[1:])
+    devg = pb.gwalpha(ctx, counts, fmt, fs, "ML", c1["codes"])
+    assert "\n".join(gl[1:]) + "\n" == pb.format_rows(pb.KIND_GWALPHA_ML, devg, pos, chr_names=names, chr_index=c1["chrom_idx"][:L]).decode()
