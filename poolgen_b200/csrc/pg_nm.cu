@@ -129,56 +129,83 @@ __device__ __forceinline__ int col_of_code(const NmParams &p, unsigned code) {
     return 0;
 }
 
-// ---- mle_iter: one warp per locus ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) mle_kernel(const NmParams p) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+// ---- mle_iter: a warp takes 32 loci; moments by the whole warp (lane = pool), simplex searches with lane = locus ------
+constexpr int kMlePhen = 4;                                   // phenotypes per pass over the loci of a block
+constexpr int kMleMom = 20 + kMlePhen * 7;                    // xbar[5] | Sxx lower triangle [15] | per phenotype ybar, syy, sxy[5]
+constexpr int kMleWarps = 4;
+
+__global__ void __launch_bounds__(kMleWarps * 32) mle_kernel(const NmParams p) {
+    extern __shared__ __align__(16) double mle_sm[];  // [warps][32][kMleMom]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *mom = mle_sm + (size_t)wib * 32 * kMleMom;
+    const int64_t warp = (int64_t)blockIdx.x * kMleWarps + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * kMleWarps;
     const int n = p.lay.n, n_pad = p.lay.n_pad, S = p.lay.A - 1, k = p.k;
     const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
-    for (int64_t locus = warp; locus < p.n_loci; locus += nwarps) {
-        const uint64_t mv = p.meta[locus];
-        if ((mv & 0xffu) != PG_LOCUS_OK) continue;
-        const int m = (int)((mv >> 8) & 0xffu);  // allele columns of X (the intercept comes on top)
-        int col[PG_MAX_SLOTS];
-        unsigned kept = 0;
-        for (int s = 0; s < m; s++) {
-            col[s] = col_of_code(p, (unsigned)((mv >> (16 + 8 * s)) & 0xffu));
-            kept |= 1u << col[s];
-        }
-        kept |= 1u << col_of_code(p, (unsigned)((mv >> (16 + 8 * m)) & 0xffu));  // the major allele
-        const double *fl = p.freq + (size_t)locus * p.lay.freq_stride();
-        const uint32_t *dl = p.depth + (size_t)locus * p.lay.depth_stride();
-        // means of the allele columns, then centred second moments (lane = pool)
-        double sx[PG_MAX_SLOTS];
-        for (int a = 0; a < PG_MAX_SLOTS; a++) sx[a] = 0.0;
-        for (int i = lane; i < n; i += 32) {
-            double F[PG_MAX_ALLELES];
-            renorm_generic(p, fl, dl, i, kept, F);
-            for (int a = 0; a < m; a++) sx[a] += F[col[a]];
-        }
-        double xbar[PG_MAX_SLOTS];
-        for (int a = 0; a < PG_MAX_SLOTS; a++) xbar[a] = (a < m) ? warp_sum_fixed(sx[a]) / (double)n : 0.0;
-        double Sxx[PG_MAX_SLOTS][PG_MAX_SLOTS];
-        for (int a = 0; a < PG_MAX_SLOTS; a++)
-            for (int b = 0; b < PG_MAX_SLOTS; b++) Sxx[a][b] = 0.0;
-        for (int i = lane; i < n; i += 32) {
-            double F[PG_MAX_ALLELES];
-            renorm_generic(p, fl, dl, i, kept, F);
-            for (int a = 0; a < m; a++)
-                for (int b = 0; b <= a; b++) Sxx[a][b] = fma(F[col[a]] - xbar[a], F[col[b]] - xbar[b], Sxx[a][b]);
-        }
-        for (int a = 0; a < m; a++)
-            for (int b = 0; b <= a; b++) {
-                Sxx[a][b] = warp_sum_fixed(Sxx[a][b]);
-                Sxx[b][a] = Sxx[a][b];
+    const int64_t n_blocks = (p.n_loci + 31) / 32;
+    for (int64_t blk = warp; blk < n_blocks; blk += nwarps) {
+        const int64_t l0 = blk * 32;
+        const int cnt = (int)min((int64_t)32, p.n_loci - l0);
+        // this lane's locus: status, allele columns of X (the intercept comes on top), kept set
+        const uint64_t mv = (lane < cnt) ? p.meta[l0 + lane] : 0ull;
+        const bool act = (mv & 0xffu) == PG_LOCUS_OK;
+        const int m = (int)((mv >> 8) & 0xffu);
+        unsigned colw = 0, kept = 0;  // 4 bits per output slot: device column
+        if (act) {
+            for (int s = 0; s < m; s++) {
+                const int c = col_of_code(p, (unsigned)((mv >> (16 + 8 * s)) & 0xffu));
+                colw |= (unsigned)c << (4 * s);
+                kept |= 1u << c;
             }
+            kept |= 1u << col_of_code(p, (unsigned)((mv >> (16 + 8 * m)) & 0xffu));  // the major allele
+        }
+        // ---- moments of the allele columns, one locus after the other, lane = pool
+        for (int g = 0; g < cnt; g++) {
+            if (!__shfl_sync(PG_FULL_MASK, (int)act, g)) continue;  // warp-uniform
+            const int mg = __shfl_sync(PG_FULL_MASK, m, g);
+            const unsigned cg = __shfl_sync(PG_FULL_MASK, colw, g), kg = __shfl_sync(PG_FULL_MASK, kept, g);
+            const double *fl = p.freq + (size_t)(l0 + g) * p.lay.freq_stride();
+            const uint32_t *dl = p.depth + (size_t)(l0 + g) * p.lay.depth_stride();
+            double sx[PG_MAX_SLOTS];
+            for (int a = 0; a < PG_MAX_SLOTS; a++) sx[a] = 0.0;
+            for (int i = lane; i < n; i += 32) {
+                double F[PG_MAX_ALLELES];
+                renorm_generic(p, fl, dl, i, kg, F);
+                for (int a = 0; a < mg; a++) sx[a] += F[(cg >> (4 * a)) & 0xfu];
+            }
+            double xb[PG_MAX_SLOTS];
+            for (int a = 0; a < PG_MAX_SLOTS; a++) xb[a] = (a < mg) ? warp_sum_fixed(sx[a]) / (double)n : 0.0;
+            double sxx[15];
+            for (int e = 0; e < 15; e++) sxx[e] = 0.0;
+            for (int i = lane; i < n; i += 32) {
+                double F[PG_MAX_ALLELES];
+                renorm_generic(p, fl, dl, i, kg, F);
+                for (int a = 0; a < mg; a++)
+                    for (int b = 0; b <= a; b++)
+                        sxx[a * (a + 1) / 2 + b] = fma(F[(cg >> (4 * a)) & 0xfu] - xb[a], F[(cg >> (4 * b)) & 0xfu] - xb[b], sxx[a * (a + 1) / 2 + b]);
+            }
+            for (int e = 0; e < 15; e++) sxx[e] = (e < mg * (mg + 1) / 2) ? warp_sum_fixed(sxx[e]) : 0.0;
+            if (lane == 0) {
+                double *mo = mom + (size_t)g * kMleMom;
+                for (int a = 0; a < PG_MAX_SLOTS; a++) mo[a] = xb[a];
+                for (int e = 0; e < 15; e++) mo[5 + e] = sxx[e];
+            }
+        }
+        __syncwarp();
+        // ---- lane = locus: collinear columns, (X'X)^-1
+        double xbar[PG_MAX_SLOTS], Sxx[PG_MAX_SLOTS][PG_MAX_SLOTS];
+        {
+            const double *mo = mom + (size_t)lane * kMleMom;
+            for (int a = 0; a < PG_MAX_SLOTS; a++) xbar[a] = act ? mo[a] : 0.0;
+            for (int a = 0; a < PG_MAX_SLOTS; a++)
+                for (int b = 0; b <= a; b++) Sxx[a][b] = Sxx[b][a] = act ? mo[5 + a * (a + 1) / 2 + b] : 0.0;
+        }
         // remove_collinearities_in_x (mle.rs:56-83), literally, on |r| rounded to 7 digits like pearsons_correlation.
         // X column c >= 1 is allele column c - 1; column 0 is the intercept (its correlation is NaN: never removed).
         int xc[PG_MAX_SLOTS + 1], pw = m + 1;
-        for (int c = 0; c <= m; c++) xc[c] = c;
+        for (int c = 0; c <= PG_MAX_SLOTS; c++) xc[c] = c;
         bool panic = false;
-        if (pw != 2) {
+        if (act && pw != 2) {
             long i = 1;
             while (i < pw && !panic) {
                 long j = i + 1;
@@ -204,13 +231,14 @@ __global__ void __launch_bounds__(128) mle_kernel(const NmParams p) {
                 i += 1;
             }
         }
-        int status = panic ? PG_LOCUS_PANIC : PG_LOCUS_OK;
-        if (status == PG_LOCUS_OK && n < pw) status = PG_LOCUS_UNSUPPORTED;  // the X X' form of the variances (mle.rs:130-140)
+        int status = !act ? (int)(mv & 0xffu) : (panic ? PG_LOCUS_PANIC : PG_LOCUS_OK);
+        if (act && status == PG_LOCUS_OK && n < pw) status = PG_LOCUS_UNSUPPORTED;  // the X X' form of the variances (mle.rs:130-140)
         // (X'X)^-1 of the remaining columns through the centred moments: the allele block is Sxx^-1, the intercept's
         // diagonal entry 1/n + xbar' Sxx^-1 xbar
         const int q = pw - 1;  // allele columns left
-        double Si[PG_MAX_SLOTS][PG_MAX_SLOTS], dgi[PG_MAX_SLOTS + 1];
-        if (status == PG_LOCUS_OK) {
+        double dgi[PG_MAX_SLOTS + 1];
+        for (int c = 0; c <= PG_MAX_SLOTS; c++) dgi[c] = 0.0;
+        if (act && status == PG_LOCUS_OK) {
             double M[PG_MAX_SLOTS][2 * PG_MAX_SLOTS];
             for (int a = 0; a < q; a++)
                 for (int b = 0; b < q; b++) {
@@ -241,97 +269,112 @@ __global__ void __launch_bounds__(128) mle_kernel(const NmParams p) {
             if (status == PG_LOCUS_OK) {
                 double quad = 0.0;
                 for (int a = 0; a < q; a++)
-                    for (int b = 0; b < q; b++) {
-                        Si[a][b] = M[a][q + b];
-                        quad += xbar[xc[a + 1] - 1] * Si[a][b] * xbar[xc[b + 1] - 1];
-                    }
+                    for (int b = 0; b < q; b++) quad += xbar[xc[a + 1] - 1] * M[a][q + b] * xbar[xc[b + 1] - 1];
                 dgi[0] = 1.0 / (double)n + quad;
-                for (int a = 0; a < q; a++) dgi[1 + a] = Si[a][a];
+                for (int a = 0; a < q; a++) dgi[1 + a] = M[a][q + a];
             }
         }
-        // phenotypes: lane j takes phenotype j (centred cross moments by the whole warp first)
-        for (int j0 = 0; j0 < k; j0 += 32) {
-            const int jn = min(32, k - j0);
-            double ybar_l = 0.0, syy_l = 0.0, sxy_l[PG_MAX_SLOTS];
-            for (int a = 0; a < PG_MAX_SLOTS; a++) sxy_l[a] = 0.0;
-            for (int jj = 0; jj < jn; jj++) {
-                const double *y = p.yraw + (size_t)(j0 + jj) * n_pad;
-                double sy = 0.0;
-                for (int i = lane; i < n; i += 32) sy += y[i];
-                const double ybar = warp_sum_fixed(sy) / (double)n;
-                double syy = 0.0, sxy[PG_MAX_SLOTS];
-                for (int a = 0; a < PG_MAX_SLOTS; a++) sxy[a] = 0.0;
-                for (int i = lane; i < n; i += 32) {
-                    double F[PG_MAX_ALLELES];
-                    renorm_generic(p, fl, dl, i, kept, F);
-                    const double dy = y[i] - ybar;
-                    syy = fma(dy, dy, syy);
-                    for (int a = 0; a < m; a++) sxy[a] = fma(F[col[a]] - xbar[a], dy, sxy[a]);
-                }
-                syy = warp_sum_fixed(syy);
-                for (int a = 0; a < PG_MAX_SLOTS; a++) sxy[a] = (a < m) ? warp_sum_fixed(sxy[a]) : 0.0;
-                if (lane == jj) {
-                    ybar_l = ybar;
-                    syy_l = syy;
-                    for (int a = 0; a < PG_MAX_SLOTS; a++) sxy_l[a] = sxy[a];
-                }
-            }
-            if (lane < jn) {
-                const int j = j0 + lane;
-                double b[PG_MAX_SLOTS + 1], vb[PG_MAX_SLOTS + 1];
-                for (int c = 0; c <= PG_MAX_SLOTS; c++) b[c] = vb[c] = 0.0;  // Array2::zeros: rows of removed columns
-                if (status == PG_LOCUS_OK) {
-                    const double nn = (double)n;
-                    // cost(par): par[0] = logit of sigma2, par[1] = intercept, par[2..] = remaining allele columns
-                    auto cost = [&](const double *par) {
-                        const double s2 = bound_logit(par[0], kEps, 1e9);
-                        double quad = 0.0, lin = 0.0, off = ybar_l - par[1];
-                        for (int a = 0; a < q; a++) {
-                            const int ia = xc[a + 1] - 1;
-                            lin += par[2 + a] * sxy_l[ia];
-                            off -= xbar[ia] * par[2 + a];
-                            for (int c = 0; c < q; c++) quad += par[2 + a] * Sxx[ia][xc[c + 1] - 1] * par[2 + c];
-                        }
-                        const double rss = (syy_l - 2.0 * lin + quad) + nn * off * off;
-                        return (nn / 2.00) * log(2.00 * 3.14159265358979323846264338327950288 * s2) + (1.00 / s2) * rss;
-                    };
-                    double par[kNmMaxD];
-                    nelder_mead(cost, pw + 1, 1.0, 1000, par);
-                    const double ve = bound_logit(par[0], kEps, 1e9);
-                    for (int c = 0; c < pw; c++) {
-                        b[c] = par[1 + c];
-                        vb[c] = ve * dgi[c];
+        // ---- phenotypes, kMlePhen at a time: centred cross moments by the whole warp, then lane = locus again
+        for (int j0 = 0; j0 < k; j0 += kMlePhen) {
+            const int jn = min(kMlePhen, k - j0);
+            __syncwarp();
+            for (int g = 0; g < cnt; g++) {
+                if (!__shfl_sync(PG_FULL_MASK, (int)act, g)) continue;
+                const int mg = __shfl_sync(PG_FULL_MASK, m, g);
+                const unsigned cg = __shfl_sync(PG_FULL_MASK, colw, g), kg = __shfl_sync(PG_FULL_MASK, kept, g);
+                const double *fl = p.freq + (size_t)(l0 + g) * p.lay.freq_stride();
+                const uint32_t *dl = p.depth + (size_t)(l0 + g) * p.lay.depth_stride();
+                const double *mo = mom + (size_t)g * kMleMom;
+                double xb[PG_MAX_SLOTS];
+                for (int a = 0; a < PG_MAX_SLOTS; a++) xb[a] = mo[a];
+                for (int jj = 0; jj < jn; jj++) {
+                    const double *y = p.yraw + (size_t)(j0 + jj) * n_pad;
+                    double sy = 0.0;
+                    for (int i = lane; i < n; i += 32) sy += y[i];
+                    const double ybar = warp_sum_fixed(sy) / (double)n;
+                    double syy = 0.0, sxy[PG_MAX_SLOTS];
+                    for (int a = 0; a < PG_MAX_SLOTS; a++) sxy[a] = 0.0;
+                    for (int i = lane; i < n; i += 32) {
+                        double F[PG_MAX_ALLELES];
+                        renorm_generic(p, fl, dl, i, kg, F);
+                        const double dy = y[i] - ybar;
+                        syy = fma(dy, dy, syy);
+                        for (int a = 0; a < mg; a++) sxy[a] = fma(F[(cg >> (4 * a)) & 0xfu] - xb[a], dy, sxy[a]);
                     }
-                }
-                for (int s = 0; s < S; s++) {
-                    double o0 = nan(""), o1 = nan(""), o2 = nan(""), o3 = nan("");
-                    if (status == PG_LOCUS_OK && s < m) {
-                        // output row s is X column s + 1 of the UNREDUCED matrix: the reference fills rows 0..pw of a zero
-                        // matrix and never maps them back (mle.rs:218-226: "does not account for the identities of the
-                        // removed columns")
-                        const int c = s + 1;
-                        const bool filled = c < pw;
-                        o0 = filled ? b[c] : 0.0;
-                        o1 = filled ? vb[c] : 0.0;
-                        if (filled) {
-                            o2 = o0 / o1;  // mle.rs:176: the variance, not its square root
-                            if (isinf(o2))
-                                o3 = 0.0;
-                            else if (o2 != o2)
-                                o3 = 1.0;
-                            else
-                                o3 = p.ptab ? student_two_sided_tab(fabs(o2), p.df, ptab) : student_two_sided(fabs(o2), p.df, p.ln_beta);
-                        } else {
-                            o3 = 0.0;
-                        }
+                    syy = warp_sum_fixed(syy);
+                    for (int a = 0; a < PG_MAX_SLOTS; a++) sxy[a] = (a < mg) ? warp_sum_fixed(sxy[a]) : 0.0;
+                    if (lane == 0) {
+                        double *o = mom + (size_t)g * kMleMom + 20 + jj * 7;
+                        o[0] = ybar;
+                        o[1] = syy;
+                        for (int a = 0; a < PG_MAX_SLOTS; a++) o[2 + a] = sxy[a];
                     }
-                    double *o = p.stats + (((size_t)locus * S + s) * k + j) * 4;
-                    o[0] = o0, o[1] = o1, o[2] = o2, o[3] = o3;
                 }
             }
             __syncwarp();
+            if (lane < cnt && (act || true)) {
+                for (int jj = 0; jj < jn; jj++) {
+                    const int j = j0 + jj;
+                    const double *mo = mom + (size_t)lane * kMleMom + 20 + jj * 7;
+                    const double ybar_l = mo[0], syy_l = mo[1];
+                    double sxy_l[PG_MAX_SLOTS];
+                    for (int a = 0; a < PG_MAX_SLOTS; a++) sxy_l[a] = mo[2 + a];
+                    double b[PG_MAX_SLOTS + 1], vb[PG_MAX_SLOTS + 1];
+                    for (int c = 0; c <= PG_MAX_SLOTS; c++) b[c] = vb[c] = 0.0;  // Array2::zeros: rows of removed columns
+                    if (act && status == PG_LOCUS_OK) {
+                        const double nn = (double)n;
+                        // cost(par): par[0] = logit of sigma2, par[1] = intercept, par[2..] = remaining allele columns
+                        auto cost = [&](const double *par) {
+                            const double s2 = bound_logit(par[0], kEps, 1e9);
+                            double quad = 0.0, lin = 0.0, off = ybar_l - par[1];
+                            for (int a = 0; a < q; a++) {
+                                const int ia = xc[a + 1] - 1;
+                                lin += par[2 + a] * sxy_l[ia];
+                                off -= xbar[ia] * par[2 + a];
+                                for (int c = 0; c < q; c++) quad += par[2 + a] * Sxx[ia][xc[c + 1] - 1] * par[2 + c];
+                            }
+                            const double rss = (syy_l - 2.0 * lin + quad) + nn * off * off;
+                            return (nn / 2.00) * log(2.00 * 3.14159265358979323846264338327950288 * s2) + (1.00 / s2) * rss;
+                        };
+                        double par[kNmMaxD];
+                        nelder_mead(cost, pw + 1, 1.0, 1000, par);
+                        const double ve = bound_logit(par[0], kEps, 1e9);
+                        for (int c = 0; c < pw; c++) {
+                            b[c] = par[1 + c];
+                            vb[c] = ve * dgi[c];
+                        }
+                    }
+                    if (!act) continue;
+                    for (int s = 0; s < S; s++) {
+                        double o0 = nan(""), o1 = nan(""), o2 = nan(""), o3 = nan("");
+                        if (status == PG_LOCUS_OK && s < m) {
+                            // output row s is X column s + 1 of the UNREDUCED matrix: the reference fills rows 0..pw of a
+                            // zero matrix and never maps them back (mle.rs:218-226: "does not account for the identities
+                            // of the removed columns")
+                            const int c = s + 1;
+                            const bool filled = c < pw;
+                            o0 = filled ? b[c] : 0.0;
+                            o1 = filled ? vb[c] : 0.0;
+                            if (filled) {
+                                o2 = o0 / o1;  // mle.rs:176: the variance, not its square root
+                                if (isinf(o2))
+                                    o3 = 0.0;
+                                else if (o2 != o2)
+                                    o3 = 1.0;
+                                else
+                                    o3 = p.ptab ? student_two_sided_tab(fabs(o2), p.df, ptab) : student_two_sided(fabs(o2), p.df, p.ln_beta);
+                            } else {
+                                o3 = 0.0;
+                            }
+                        }
+                        double *o = p.stats + (((size_t)(l0 + lane) * S + s) * k + j) * 4;
+                        o[0] = o0, o[1] = o1, o[2] = o2, o[3] = o3;
+                    }
+                }
+            }
         }
-        if (lane == 0 && status != PG_LOCUS_OK) p.meta[locus] = (mv & ~0xffull) | (uint64_t)status;
+        if (act && status != PG_LOCUS_OK) p.meta[l0 + lane] = (mv & ~0xffull) | (uint64_t)status;
+        __syncwarp();
     }
 }
 
@@ -472,9 +515,12 @@ __global__ void __launch_bounds__(128) gwalpha_kernel(const NmParams p) {
 cudaError_t launch_nm(const NmParams &p, int sm_count, cudaStream_t s) {
     if (p.n_loci == 0) return cudaSuccess;
     if (p.kind == PG_KIND_MLE) {
-        int64_t grid = (p.n_loci * 32 + 127) / 128;
-        if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
-        mle_kernel<<<(unsigned)grid, 128, 0, s>>>(p);
+        const size_t smem = (size_t)kMleWarps * 32 * kMleMom * 8;
+        cudaError_t e = cudaFuncSetAttribute(mle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int64_t grid = ((p.n_loci + 31) / 32 + kMleWarps - 1) / kMleWarps;
+        if (grid > (int64_t)sm_count * 4) grid = (int64_t)sm_count * 4;
+        mle_kernel<<<(unsigned)grid, kMleWarps * 32, smem, s>>>(p);
     } else {
         int64_t grid = (p.n_loci * (p.lay.A - 1) + 127) / 128;
         if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
