@@ -255,8 +255,8 @@ int pg_scan_open(pg_ctx *ctx, int kind, const pg_filter *filter, int n_pools, in
                     return fail(ctx, PG_ERR_CUDA, "pg_scan_open: p-value table upload: %s", cudaGetErrorString(et));
                 }
                 s->ptab_M = tab.M;
-                s->ptab_vmax = tab.v_max;
-                s->ptab_inv_h = tab.inv_h;
+                s->ptab_isd = tab.inv_sqrt_df;
+                s->ptab_bits = tab.bits;
                 s->ptab_err = tab.max_err;
             }
         }
@@ -637,8 +637,8 @@ static int run_once(pg_batch *b, int *launches) {
             p.inv_nm2 = 1.0 / ((double)s->n - 2.0);
             p.ln_beta = s->ln_beta;
             p.ptab = s->d_ptab;
-            p.ptab_vmax = s->ptab_vmax;
-            p.ptab_inv_h = s->ptab_inv_h;
+            p.ptab_isd = s->ptab_isd;
+            p.ptab_bits = s->ptab_bits;
             p.ptab_M = s->ptab_M;
             p.K = std::min(kpass, s->k - base);
             p.y_has_nan = s->y_has_nan;
@@ -681,8 +681,8 @@ static int run_once(pg_batch *b, int *launches) {
             q.df = s->df;
             q.ln_beta = s->ln_beta;
             q.ptab = s->d_ptab;
-            q.ptab_vmax = s->ptab_vmax;
-            q.ptab_inv_h = s->ptab_inv_h;
+            q.ptab_isd = s->ptab_isd;
+            q.ptab_bits = s->ptab_bits;
             q.ptab_M = s->ptab_M;
             for (int j = 0; j < s->A_dev; j++) q.codes[j] = s->codes_dev[j];
             q.meta = b->d_meta;

@@ -129,25 +129,34 @@ static __device__ __noinline__ double student_two_sided(double t_abs, double df,
     return 2.0 * (1.0 - cdf);
 }
 
-// Same quantity through the per-scan table of ln p(v), v = sqrt(log1p(t^2/df)) (pg_ptable.h).  The final
+// Same quantity through the per-scan table of ln p indexed by the bits of 1 + |t| / sqrt(df) (pg_ptable.h).  The final
 // 2 * (1 - (1 - ib)) reproduces the reference's quantisation of small p-values.
 struct PTableDev {
     const double4 *coef;
-    double v_max, inv_h;
+    double inv_sqrt_df, bits;  // bits: intervals per octave of w = 1 + |t| / sqrt(df) as a power of two
     int M;
 };
+// interval and fraction of w = 1 + x from the bits of the double: idx = octave * 2^B + the top B mantissa bits
+__device__ __forceinline__ int ptab_locate(double w, int B, double &s) {
+    const int hi = __double2hiint(w);
+    const int sh = 20 - B;
+    const int idx = (hi >> sh) - (1023 << B);
+    const double w0 = __hiloint2double(hi & ~((1 << sh) - 1), 0);
+    const double scale = __hiloint2double((2046 + B - (hi >> 20)) << 20, 0);  // 2^(B - e), e = (hi >> 20) - 1023
+    s = (w - w0) * scale;
+    return idx;
+}
 __device__ __forceinline__ double student_two_sided_tab(double t_abs, double df, const PTableDev &tb) {
-    const double z = t_abs * t_abs / df;
-    const double v = sqrt(log1p(z));
+    const double w = fma(t_abs, tb.inv_sqrt_df, 1.0);
     double ptrue = 0.0;
-    if (v < tb.v_max) {
-        const double pos = v * tb.inv_h;
-        int i = (int)pos;
-        if (i > tb.M - 1) i = tb.M - 1;
-        const double s = pos - (double)i;
-        const double2 *cp = reinterpret_cast<const double2 *>(tb.coef + i);
-        const double2 c01 = __ldg(cp), c23 = __ldg(cp + 1);
-        ptrue = exp(fma(s, fma(s, fma(s, c23.y, c23.x), c01.y), c01.x));
+    if (w < 1.7e308) {
+        double s;
+        const int i = ptab_locate(w, (int)tb.bits, s);
+        if (i < tb.M) {
+            const double2 *cp = reinterpret_cast<const double2 *>(tb.coef + i);
+            const double2 c01 = __ldg(cp), c23 = __ldg(cp + 1);
+            ptrue = exp(fma(s, fma(s, fma(s, c23.y, c23.x), c01.y), c01.x));
+        }
     }
     const double ib = 0.5 * ptrue;
     const double cdf = t_abs <= 0.0 ? ib : 1.0 - ib;

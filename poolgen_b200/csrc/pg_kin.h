@@ -1,5 +1,8 @@
 // pg_kin.h -- the handle of the ols_iter_with_kinship path (shared by pg_kinship.cu and pg_comm.cu; not part of the ABI)
 #pragma once
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -25,7 +28,7 @@ struct pg_kin {
     double *d_V = nullptr;        // [(1+m) + k][ldg]
     size_t V_bytes = 0;
     double *d_ptab = nullptr;
-    double ptab_vmax = 0, ptab_inv_h = 0;
+    double ptab_isd = 0, ptab_bits = 0;
     int ptab_M = 0;
     // results
     int k = 0;
@@ -46,9 +49,16 @@ struct pg_kin {
     size_t counts_bytes = 0;
     double *d_w = nullptr;
     pg::TextScratch *text = nullptr;  // sync text parsed on the device (pg_kin_append_sync_text)
-    // eigen step: cuSOLVER is mapped and its handle created by a background thread started in pg_kin_open
-    std::thread warm;
-    bool warm_started = false;
-    void *solver = nullptr;  // cusolverDnHandle_t
+    // eigen step: cuSOLVER is mapped and its handle created by a detached background thread started in pg_kin_open;
+    // the state outlives the handle so that pg_kin_close never waits for a cold dlopen (the loader / sync2csv never
+    // reaches the eigen step)
+    struct Warm {
+        std::mutex m;
+        std::condition_variable cv;
+        void *solver = nullptr;  // cusolverDnHandle_t
+        bool done = false, abandoned = false;
+        int device = 0;
+    };
+    std::shared_ptr<Warm> warm;
 };
 

@@ -387,7 +387,7 @@ struct CovarParams {
     double nf, sqrt_n;
     double sy[kMaxPhenPerPass * 4];  // sum of the raw phenotype
     const void *ptab;
-    double ptab_vmax, ptab_inv_h;
+    double ptab_isd, ptab_bits;
     int ptab_M;
     double ln_beta;
     double *beta, *var, *pval;  // [k][P]
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_isd, p.ptab_bits, p.ptab_M};
     const int nq = p.nq, k = p.k;
     // C = 1 with a column list: the columns the DMMA kernel left to the two-pass form
     const int64_t n_items = (C == 1 && p.defer_list) ? (int64_t)*p.defer_count : p.P;
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     constexpr int SCR = (8 * MT + 1) * 8;
     double *scr = cm_sm + (size_t)NV * ldq + (size_t)wib * SCR;  // U [8 MT][8] | g'g [8]
-    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_isd, p.ptab_bits, p.ptab_M};
     const int64_t n_blocks = (p.P + 7) / 8;
     const int64_t wg = (int64_t)blockIdx.x * n_warps + wib, nwg = (int64_t)gridDim.x * n_warps;
     // vector rows of this lane in each M tile (rows >= NV are zero: the address is clamped, the value masked)
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(256) covar_generic_kernel(const CovarParams p)
     double *u = gcol + ldg;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_isd, p.ptab_bits, p.ptab_M};
     const int64_t n_items = p.defer_list ? (int64_t)*p.defer_count : p.P;
     for (int64_t item = warp; item < n_items; item += nwarps) {
         const int64_t c = p.defer_list ? p.defer_list[item] : item;
@@ -815,15 +815,29 @@ static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 extern "C" {
 
 // The eigen step's one-off costs -- mapping cuSOLVER and its dependencies (1.5 GB of shared objects) and creating the
-// handle, 0.3-3 s on a cold box -- start in a background thread with the first pg_kin_gram (only ols_iter_with_kinship
-// forms a Gram matrix; the sync2csv loader never pays), so they overlap the Gram kernel and the exchange step instead
-// of sitting in front of the first pg_kin_eig_select.
-static void kin_warm_solver(pg_kin *h) {
-    const CusolverApi &sol = cusolver_api();
-    if (!sol.ok) return;
-    if (cudaSetDevice(h->ctx->device) != cudaSuccess) return;
+// handle, 0.3-3 s on a cold box, more when eight ranks do it at once -- start in a detached background thread when the
+// kinship handle is opened, so they overlap the column loading, the Gram kernel and the exchange step instead of
+// sitting in front of the first pg_kin_eig_select.  The thread owns a reference to its state: a handle that is closed
+// before the thread finishes (the sync2csv loader never reaches the eigen step) abandons it without waiting.
+static void kin_warm_solver(std::shared_ptr<pg_kin::Warm> w) {
+    const CusolverApi &sol = cusolver_api();  // the dlopen: the slow part
     cusolverDnHandle_t cs = nullptr;
-    if (sol.create(&cs) == CUSOLVER_STATUS_SUCCESS) h->solver = cs;
+    {
+        std::unique_lock<std::mutex> lk(w->m);
+        if (w->abandoned) {  // closed meanwhile: do not touch CUDA any more (the process may be on its way out)
+            w->done = true;
+            return;
+        }
+    }
+    if (sol.ok && cudaSetDevice(w->device) == cudaSuccess && sol.create(&cs) != CUSOLVER_STATUS_SUCCESS) cs = nullptr;
+    std::unique_lock<std::mutex> lk(w->m);
+    if (w->abandoned) {
+        if (cs) sol.destroy(cs);
+    } else {
+        w->solver = cs;
+    }
+    w->done = true;
+    w->cv.notify_all();
 }
 
 int pg_kin_open(pg_ctx *ctx, int n_pools, int64_t max_columns, pg_kin **out) {
@@ -851,14 +865,24 @@ int pg_kin_open(pg_ctx *ctx, int n_pools, int64_t max_columns, pg_kin **out) {
         return kfail(ctx, PG_ERR_CUDA, "pg_kin_open(%d pools, %lld columns): %s", n_pools, (long long)max_columns,
                      cudaGetErrorString(e));
     }
+    h->warm = std::make_shared<pg_kin::Warm>();
+    h->warm->device = ctx->device;
+    std::thread(kin_warm_solver, h->warm).detach();
     *out = h;
     return PG_OK;
 }
 
 int pg_kin_close(pg_kin *h) {
     if (!h) return PG_OK;
-    if (h->warm.joinable()) h->warm.join();
-    if (h->solver) cusolver_api().destroy(static_cast<cusolverDnHandle_t>(h->solver));
+    if (h->warm) {
+        std::unique_lock<std::mutex> lk(h->warm->m);
+        if (h->warm->done) {
+            if (h->warm->solver) cusolver_api().destroy(static_cast<cusolverDnHandle_t>(h->warm->solver));
+            h->warm->solver = nullptr;
+        } else {
+            h->warm->abandoned = true;  // the thread disposes of what it creates
+        }
+    }
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_G);
     cudaFree(h->d_K);
@@ -1090,10 +1114,6 @@ int pg_kin_get_columns(pg_kin *h, int64_t first, int64_t count, double *out) {
 
 static int gram_launch(pg_kin *h) {
     pg_ctx *ctx = h->ctx;
-    if (!h->warm_started) {
-        h->warm_started = true;
-        h->warm = std::thread(kin_warm_solver, h);
-    }
     const int ntiles = h->nt * (h->nt + 1) / 2;
     const int64_t P_pad = round_up(std::max<int64_t>(h->P, 1), pg::kKC);
     // column slices: enough (slice, tile) items for ~8 waves over the SMs, each slice a multiple of kKC columns
@@ -1186,15 +1206,18 @@ int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) 
     int *dinfo = nullptr;
     int rc = PG_OK;
     std::vector<double> A((size_t)n * n), W(n);
-    if (h->warm.joinable()) h->warm.join();  // the handle the background thread of pg_kin_open created
+    {  // the handle the background thread of pg_kin_open creates
+        std::unique_lock<std::mutex> lk(h->warm->m);
+        h->warm->cv.wait(lk, [&] { return h->warm->done; });
+    }
     const CusolverApi &sol = cusolver_api();
     if (!sol.ok) return kfail(ctx, PG_ERR_CUDA, "pg_kin_eig_select: libcusolver could not be loaded (%s)", dlerror() ? dlerror() : "missing symbols");
-    if (!h->solver) {
+    if (!h->warm->solver) {
         cusolverDnHandle_t made = nullptr;
         if (sol.create(&made) != CUSOLVER_STATUS_SUCCESS) return kfail(ctx, PG_ERR_CUDA, "cusolverDnCreate failed");
-        h->solver = made;
+        h->warm->solver = made;
     }
-    cusolverDnHandle_t cs = static_cast<cusolverDnHandle_t>(h->solver);
+    cusolverDnHandle_t cs = static_cast<cusolverDnHandle_t>(h->warm->solver);
     do {
         sol.set_stream(cs, h->stream);
         if (cudaMalloc(&dA, (size_t)n * n * 8) != cudaSuccess || cudaMalloc(&dW, (size_t)n * 8) != cudaSuccess ||
@@ -1513,8 +1536,8 @@ int pg_kin_covar_scan(pg_kin *h, const double *phen, int k, int iters, float *ms
             KCUDA(ctx, cudaMemcpyAsync(h->d_ptab, tab.coef.data(), tab.coef.size() * 8, cudaMemcpyHostToDevice, h->stream));
             KCUDA(ctx, cudaStreamSynchronize(h->stream));
             h->ptab_M = tab.M;
-            h->ptab_vmax = tab.v_max;
-            h->ptab_inv_h = tab.inv_h;
+            h->ptab_isd = tab.inv_sqrt_df;
+            h->ptab_bits = tab.bits;
         }
     }
     const size_t elems = (size_t)3 * k * std::max<int64_t>(h->P, 1);
@@ -1541,8 +1564,8 @@ int pg_kin_covar_scan(pg_kin *h, const double *phen, int k, int iters, float *ms
     cp.sqrt_n = sqrt((double)n);
     cp.df = df;
     cp.ptab = h->d_ptab;
-    cp.ptab_vmax = h->ptab_vmax;
-    cp.ptab_inv_h = h->ptab_inv_h;
+    cp.ptab_isd = h->ptab_isd;
+    cp.ptab_bits = h->ptab_bits;
     cp.ptab_M = h->ptab_M;
     cp.ln_beta = pg::statrs::ln_gamma(df / 2.0 + 0.5) - pg::statrs::ln_gamma(df / 2.0) - pg::statrs::ln_gamma(0.5);
     cp.beta = h->d_res;

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kMleWarps * 32) mle_kernel(const NmParams p) {
     const int64_t warp = (int64_t)blockIdx.x * kMleWarps + wib;
     const int64_t nwarps = (int64_t)gridDim.x * kMleWarps;
     const int n = p.lay.n, n_pad = p.lay.n_pad, S = p.lay.A - 1, k = p.k;
-    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_isd, p.ptab_bits, p.ptab_M};
     const int64_t n_blocks = (p.n_loci + 31) / 32;
     for (int64_t blk = warp; blk < n_blocks; blk += nwarps) {
         const int64_t l0 = blk * 32;

@@ -1073,15 +1073,14 @@ __device__ __forceinline__ void student_batch(const ScanParams &p, const PTableD
     double s[K];
     const double2 *cp[K];
     bool in[K];
+    const int B = (int)tab.bits;
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const double ta = need[k] ? t_abs[k] : 0.0;
-        const double v = sqrt(log1p(ta * ta * p.inv_df));
-        in[k] = need[k] && (v < tab.v_max);
-        const double pos = in[k] ? v * tab.inv_h : 0.0;
-        int i = (int)pos;
-        if (i > tab.M - 1) i = tab.M - 1;
-        s[k] = pos - (double)i;
+        const double w = fma(ta, tab.inv_sqrt_df, 1.0);
+        int i = ptab_locate(w, B, s[k]);
+        in[k] = need[k] && (w < 1.7e308) && (i < tab.M);
+        if (!in[k]) i = 0;
         cp[k] = reinterpret_cast<const double2 *>(tab.coef + i);
     }
     double2 c01[K], c23[K];
@@ -1188,7 +1187,7 @@ template <int A, int K, bool W, bool DEFER, int KIND>
 __device__ __noinline__ void epilogue(const ScanParams &p, int64_t locus, bool act, double *tot, const double *ys,
                                       const double *ws, int lane, unsigned dm, unsigned pre_kept) {
     using AC = Acc<A, K, W>;
-    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_vmax, p.ptab_inv_h, p.ptab_M};
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_isd, p.ptab_bits, p.ptab_M};
     double *tg = tot + (size_t)lane * AC::NP;
     const double tol_rel = 2.0 * ((double)p.lay.n + 8.0) * kEps;
     int status = PG_LOCUS_FILTERED;
