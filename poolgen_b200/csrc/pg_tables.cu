@@ -103,26 +103,46 @@ __device__ __forceinline__ double gamma_q_halfint(int df, double x) {
     return ex * sum;
 }
 
+// lf: the log10-factorial table in SHARED memory -- the lookups are indexed by the cell values, which differ from lane
+// to lane, and a divergent index serialises constant-cache reads
 template <int NP, int NA>
-__device__ __forceinline__ double ratio_t(const double (&c)[NP][NA], unsigned km, double lp) {
+__device__ __forceinline__ double ratio_t(const double (&c)[NP][NA], unsigned km, double lp, const double *lf) {
     double s = 0.0, total = 0.0;
 #pragma unroll
     for (int i = 0; i < NP; i++)
 #pragma unroll
         for (int j = 0; j < NA; j++)
-            if ((km >> j) & 1u) s = s + c_lf10[(int)c[i][j]];
+            if ((km >> j) & 1u) s = s + lf[(int)c[i][j]];
 #pragma unroll
     for (int i = 0; i < NP; i++)
 #pragma unroll
         for (int j = 0; j < NA; j++)
             if ((km >> j) & 1u) total = total + c[i][j];
-    s = s + c_lf10[(int)total];
+    s = s + lf[(int)total];
+    return exp10(lp - s);
+}
+
+template <int NP, int NA>
+__device__ __forceinline__ double ratio_i(const int (&c)[NP][NA], unsigned km, double lp, const double *lf) {
+    double s = 0.0;
+    int total = 0;
+#pragma unroll
+    for (int i = 0; i < NP; i++)
+#pragma unroll
+        for (int j = 0; j < NA; j++)
+            if ((km >> j) & 1u) {
+                s = s + lf[c[i][j]];
+                total += c[i][j];
+            }
+    s = s + lf[min(total, 35)];
     return exp10(lp - s);
 }
 
 template <int NP, int NA>
 __global__ void __launch_bounds__(kTabThreads, (NP * NA <= 8) ? 12 : 8) tables_kernel_t(const TableParams p) {
     extern __shared__ __align__(16) uint32_t sm_counts[];
+    __shared__ double s_lf[36];
+    if (threadIdx.x < 36) s_lf[threadIdx.x] = c_lf10[threadIdx.x];
     constexpr int per_locus = NA * NP;
     const int64_t tiles = (p.n_loci + kTabThreads - 1) / kTabThreads;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -255,81 +275,90 @@ __global__ void __launch_bounds__(kTabThreads, (NP * NA <= 8) ? 12 : 8) tables_k
                         for (int j = 0; j < NA; j++)
                             if ((km >> j) & 1u) c[i][j] = floor(c[i][j] * coef);
                 }
+                // from here on every cell is an integer <= 34 (the rescale, fisher_exact_test.rs:51-58): the fills, the
+                // marginal sums and the comparisons are exact in integer arithmetic, which leaves the FP64 pipe to the
+                // log-factorial sums and 10^x
+                int ci[NP][NA], ri[NP], cj[NA];
+#pragma unroll
+                for (int i = 0; i < NP; i++)
+#pragma unroll
+                    for (int j = 0; j < NA; j++) ci[i][j] = (int)fmin(c[i][j], 35.0);  // > 34 only without the rescale: never
 #pragma unroll
                 for (int i = 0; i < NP; i++) {
-                    rs[i] = 0.0;
+                    ri[i] = 0;
 #pragma unroll
-                    for (int j = 0; j < NA; j++) rs[i] = rs[i] + c[i][j];
+                    for (int j = 0; j < NA; j++) ri[i] += ci[i][j];
                 }
 #pragma unroll
                 for (int j = 0; j < NA; j++) {
-                    cs[j] = 0.0;
+                    cj[j] = 0;
 #pragma unroll
-                    for (int i = 0; i < NP; i++) cs[j] = cs[j] + c[i][j];
+                    for (int i = 0; i < NP; i++) cj[j] += ci[i][j];
                 }
                 double lp = 0.0;
 #pragma unroll
-                for (int i = 0; i < NP; i++) lp = lp + c_lf10[(int)rs[i]];
+                for (int i = 0; i < NP; i++) lp = lp + s_lf[ri[i]];
 #pragma unroll
                 for (int j = 0; j < NA; j++)
-                    if ((km >> j) & 1u) lp = lp + c_lf10[(int)cs[j]];
-                const double p_obs = ratio_t<NP, NA>(c, km, lp);
+                    if ((km >> j) & 1u) lp = lp + s_lf[cj[j]];
+                const double p_obs = ratio_i<NP, NA>(ci, km, lp, s_lf);
                 const int jlast = 31 - __clz(km);  // the last kept column
                 double p_ext = 0.0;
                 bool panic = false;
                 for (int mi = 0; mi < NP && !panic; mi++)
                     for (int mj = 0; mj < NA && !panic; mj++) {
                         if (!((km >> mj) & 1u)) continue;
-                        // forward fill (fisher_exact_test.rs:78-92)
+                        // forward fill (fisher_exact_test.rs:78-92); `as usize` saturates negatives to 0
+                        int cdown[NA];
 #pragma unroll
-                        for (int i = 0; i < NP; i++)
+                        for (int j = 0; j < NA; j++) cdown[j] = 0;
+#pragma unroll
+                        for (int i = 0; i < NP; i++) {
+                            int r = 0;
 #pragma unroll
                             for (int j = 0; j < NA; j++) {
                                 if (!((km >> j) & 1u)) continue;
-                                double r = 0.0, sdown = 0.0;
-#pragma unroll
-                                for (int jj = 0; jj < j; jj++) r = r + c[i][jj];
-#pragma unroll
-                                for (int ii = 0; ii < i; ii++) sdown = sdown + c[ii][j];
-                                const double a = as_usize_f64(rs[i] - r), b = as_usize_f64(cs[j] - sdown);
-                                const double mx = a < b ? a : b;
+                                const int mx = min(max(ri[i] - r, 0), max(cj[j] - cdown[j], 0));
+                                int v;
                                 if ((i == NP - 1) | (j == jlast))
-                                    c[i][j] = mx;
+                                    v = mx;
                                 else if ((i < mi) | (j < mj))
-                                    c[i][j] = 0.0;
+                                    v = 0;
                                 else
-                                    c[i][j] = mx;
+                                    v = mx;
+                                ci[i][j] = v;
+                                r += v;
+                                cdown[j] += v;
                             }
-                        // reverse fill (fisher_exact_test.rs:96-111)
+                        }
+                        // reverse fill (fisher_exact_test.rs:96-111): the full row / column sums of the CURRENT table
+                        int rfull[NP];
+#pragma unroll
+                        for (int i = 0; i < NP; i++) {
+                            rfull[i] = 0;
+#pragma unroll
+                            for (int j = 0; j < NA; j++) rfull[i] += ci[i][j];
+                        }
 #pragma unroll
                         for (int j = NA - 1; j >= 0; j--)
 #pragma unroll
                             for (int i = NP - 1; i >= 0; i--) {
                                 if (!((km >> j) & 1u)) continue;
-                                double r = 0.0, sdown = 0.0;
-#pragma unroll
-                                for (int jj = 0; jj < NA; jj++) r = r + c[i][jj];
-#pragma unroll
-                                for (int ii = 0; ii < NP; ii++) sdown = sdown + c[ii][j];
-                                const double a = as_usize_f64(rs[i] - r), b = as_usize_f64(cs[j] - sdown);
-                                const double mx = a < b ? a : b;
-                                if (mx > 0.0) c[i][j] = mx;
+                                const int mx = min(max(ri[i] - rfull[i], 0), max(cj[j] - cdown[j], 0));
+                                if (mx > 0) {
+                                    const int d = mx - ci[i][j];
+                                    ci[i][j] = mx;
+                                    rfull[i] += d;
+                                    cdown[j] += d;
+                                }
                             }
 #pragma unroll
-                        for (int i = 0; i < NP; i++) {
-                            double r = 0.0;
+                        for (int i = 0; i < NP; i++)
+                            if (rfull[i] != ri[i]) panic = true;
 #pragma unroll
-                            for (int j = 0; j < NA; j++) r = r + c[i][j];
-                            if (r != rs[i]) panic = true;
-                        }
-#pragma unroll
-                        for (int j = 0; j < NA; j++) {
-                            double sdown = 0.0;
-#pragma unroll
-                            for (int i = 0; i < NP; i++) sdown = sdown + c[i][j];
-                            if (sdown != cs[j]) panic = true;
-                        }
-                        if (!panic) p_ext += ratio_t<NP, NA>(c, km, lp);
+                        for (int j = 0; j < NA; j++)
+                            if (cdown[j] != cj[j]) panic = true;
+                        if (!panic) p_ext += ratio_i<NP, NA>(ci, km, lp, s_lf);
                     }
                 if (panic) {
                     status = PG_LOCUS_PANIC;  // assert! at fisher_exact_test.rs:113-114

@@ -66,5 +66,42 @@ kin.gram()
 kin.eig_select(kin.columns, 0.75)
 kin.covar_scan(phen)
 kin.close()
+# round 2: Fisher beyond 16 pools, fewer pools than coefficients, the Nelder-Mead analyses, the DMMA covariate scan,
+# the kinship n < p branch, the library's communicator with one rank
+n, A, L = 20, 4, 200
+full = (rng.poisson(0.6, size=(L, A, n)) + (rng.random((L, A, n)) < 0.02) * 40).astype(np.uint32)
+full[:, 0] += 1
+fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n), min_allele_frequency=0.0)
+scan = pb.Scan(ctx, pb.KIND_FISHER, fs, n, np.arange(A, dtype=np.uint8))
+scan.run_counts(full)
+scan.close()
+n, A, L = 3, 6, 300
+full = rng.integers(1, 40, size=(L, A, n)).astype(np.uint32)
+fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n), remove_ns=False, min_allele_frequency=0.0)
+pb.ols_iterate(ctx, full, rng.standard_normal((n, 2)), fs, np.arange(A, dtype=np.uint8))
+n, A, L = 9, 4, 200
+full = pb.synth_counts_host(3, 0, L, n, A)
+fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n))
+pb.mle_iterate(ctx, full, pb.synth_phen_host(3, n, 5), fs, np.arange(A, dtype=np.uint8))
+fmt = np.full((n, 3), -np.inf)
+fmt[:, 0] = 1.0 / n
+fmt[:, 1] = np.linspace(0.0, 0.9, n)
+fmt[:3, 2] = (0.1, 0.0, 1.0)
+for m in ("LS", "ML"):
+    pb.gwalpha(ctx, full[:40], fmt, fs, m, np.arange(A, dtype=np.uint8))
+n, P = 37, 203
+G = np.clip(0.5 + 0.2 * rng.standard_normal((P, n)), 0, 1)
+kin = pb.Kinship(ctx, n, P)
+kin.append_columns(G)
+kin.set_covariates(rng.standard_normal((n, 6)))
+kin.covar_scan(rng.standard_normal((n, 3)))
+kin.gram()
+from poolgen_b200 import shard
+comm = shard.make_comm(ctx)
+comm.kin_allreduce([kin])
+kin.eig_select(0, 1.5)      # never reached: n_eigenvecs = n, the n < p branch
+kin.covar_scan(rng.standard_normal((n, 2)))
+kin.close()
+comm.close()
 ctx.close()
 print("sanitize_small: done", len(rows))
