@@ -15,12 +15,23 @@
  *   src/tables/fisher_exact_test.rs:139-142 log10(5!), hypergeometric ratio, output line
  *   src/base/sync.rs:1557-1632             parse -> counts -> freqs -> filter -> sort
  *   src/gwas/ols.rs:534                    the four betas of the (commented) vector
+ *   src/gwas/gwalpha.rs:392-447            the two output lines of gwalpha_ls and of gwalpha_ml: four
+ *                                          Nelder-Mead searches over two cost functions, six printed
+ *                                          digits each -- they pin the restatement of argmin's solver,
+ *                                          statrs' Beta::cdf and bound_parameters_with_logit
  * "parity unpinned" for: MKL inv/det rounding and the ols_iter p-values (no live
- * reference vector exists; df = n-1 per src/gwas/ols.rs:139).
+ * reference vector exists; df = n-1 per src/gwas/ols.rs:139); mle_iterate (gwas/mle.rs has
+ * no known-answer test: its solver is the one test_gwalpha pins, its cost function is
+ * checked against the closed-form optimum, tests/test_oracle_golden.py).
  *
  * Third-party arithmetic that is not under /root/reference is restated from the
  * published algorithms: statrs 0.16.0 (ln_gamma, beta_reg, gamma_lr, StudentsT,
- * ChiSquared), LAPACK dgetrf/dgetri as called by ndarray-linalg 0.16.0.
+ * ChiSquared, Beta), LAPACK dgetrf/dgetri as called by ndarray-linalg 0.16.0, argmin
+ * 0.8.1 (NelderMead as prepare_solver_neldermead + Executor::max_iters(1_000) drive it),
+ * ndarray 0.15.6 (the summation order of `sum()` / `dot()` on contiguous data).
+ *
+ * pgo_scan_batch_tight is the "tight" CPU baseline of bench.py: the same arithmetic as
+ * the faithful functions (bit-identical records) without the reference's avoidable work.
  */
 #ifndef POOLGEN_ORACLE_H
 #define POOLGEN_ORACLE_H
