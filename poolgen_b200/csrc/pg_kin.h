@@ -49,16 +49,9 @@ struct pg_kin {
     size_t counts_bytes = 0;
     double *d_w = nullptr;
     pg::TextScratch *text = nullptr;  // sync text parsed on the device (pg_kin_append_sync_text)
-    // eigen step: cuSOLVER is mapped and its handle created by a detached background thread started in pg_kin_open;
-    // the state outlives the handle so that pg_kin_close never waits for a cold dlopen (the loader / sync2csv never
-    // reaches the eigen step)
-    struct Warm {
-        std::mutex m;
-        std::condition_variable cv;
-        void *solver = nullptr;  // cusolverDnHandle_t
-        bool done = false, abandoned = false;
-        int device = 0;
-    };
-    std::shared_ptr<Warm> warm;
+    // eigen step: cuSOLVER is mapped and its handle created by a background thread started in pg_kin_open and joined
+    // by pg_kin_eig_select / pg_kin_close
+    std::thread warm;
+    void *solver = nullptr;  // cusolverDnHandle_t
 };
 

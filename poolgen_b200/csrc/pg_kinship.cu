@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <vector>
 
@@ -536,16 +537,19 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
 // holds pools {2t, 2t+1, 8+2t, 8+2t+1} of its column g -- two 128-bit loads straight from global memory (G is streamed
 // once, no staging: the shared memory belongs to V; the four lanes of a column cover 64 contiguous bytes per request,
 // i.e. whole sectors) -- and the matching elements of vector row g from shared memory (pitch = 8 mod 16 doubles:
-// conflict-free LDS.128); DMMA number s of a block contracts the s-th of those pools.  Two accumulator sets per M tile
-// keep four independent DMMA chains per warp; g'g accumulates beside it.  Every U[v][c] ends up in exactly one lane (no
+// conflict-free LDS.128); DMMA number s of a block contracts the s-th of those pools.  HBM wants ~110 KB in flight per
+// SM and the shared memory is taken, so the in-flight data lives in REGISTERS: a lane holds a ring of eight blocks and
+// reloads a slot the moment its block has been consumed (across the boundary to the warp's next column block), which
+// keeps 224 bytes per lane = 115 KB per SM in flight with 16 warps.  Two accumulator sets per M tile keep four
+// independent DMMA chains per warp; g'g accumulates beside it.  Every U[v][c] ends up in exactly one lane (no
 // cross-lane reduction); a per-warp scratch hands the 8 columns' sums to the lanes that finish (column, phenotype)
 // pairs.  Columns whose centred g'g is lost to cancellation (nearly constant columns) go to a list that
 // covar_kernel<NV, 1> finishes in its two-pass form -- the streaming kernel carries no slow path.
-// Measured alternatives: a register double buffer (next trip's loads issued before the DMMAs), L2 bulk
-// prefetches ahead of the loads, 16 columns per warp, and a CTA-cooperative form in which the warps split the pools of
-// one column block and hand partial tiles over named barriers -- none beat this one.
-constexpr int kCmMaxWarps = 24;
-constexpr int kCmTrip = 4;  // 16-pool blocks per trip: eight 128-bit loads in flight per lane
+// Measured alternatives: loads and DMMAs in alternating trips (24 warps), a two-trip register double
+// buffer, L2 bulk prefetches ahead of the loads, 16 columns per warp, and a CTA-cooperative form in which the warps
+// split the pools of one column block and hand partial tiles over named barriers.
+constexpr int kCmMaxWarps = 16;
+constexpr int kCmRing = 8;  // 16-pool blocks a lane holds in registers (256 bytes)
 
 template <int MT>
 __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const CovarParams p, int ldq, int n_warps) {
@@ -573,13 +577,27 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
         amask[mt] = v < NV ? 1.0 : 0.0;
         arow[mt] = Vs + (size_t)(v < NV ? v : 0) * ldq + 2 * t;
     }
-    constexpr int TR = 16 * kCmTrip;  // pools per trip
-    const int n_trips = n / TR;       // whole trips; the rest goes through the guarded tail
+    const int nb_ring = (n / 16) / kCmRing * kCmRing;  // 16-pool blocks that go through the register ring
+    auto col_ptr = [&](int64_t blk) {
+        const int64_t c0 = blk * 8;
+        return p.G + (size_t)(c0 + g < p.P ? c0 + g : c0) * ldg + 2 * t;
+    };
+    double2 ring[kCmRing][2];
+    if (wg < n_blocks && nb_ring > 0) {
+        const double *g0 = col_ptr(wg);
+#pragma unroll
+        for (int u = 0; u < kCmRing; u++) {
+            ring[u][0] = __ldcs(reinterpret_cast<const double2 *>(g0 + u * 16));
+            ring[u][1] = __ldcs(reinterpret_cast<const double2 *>(g0 + u * 16 + 8));
+        }
+    }
     for (int64_t blk = wg; blk < n_blocks; blk += nwg) {
         const int64_t c0 = blk * 8;
         const bool cval = c0 + g < p.P;
         const double zmask = cval ? 1.0 : 0.0;  // a column past the end contributes zeros
-        const double *gb = p.G + (size_t)(cval ? c0 + g : c0) * ldg + 2 * t;
+        const double *gb = col_ptr(blk);
+        const bool has_next = blk + nwg < n_blocks;
+        const double *gb_next = has_next ? col_ptr(blk + nwg) : gb;
         double acc[MT][2][2], gg = 0.0;
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) acc[mt][0][0] = acc[mt][0][1] = acc[mt][1][0] = acc[mt][1][1] = 0.0;
@@ -602,19 +620,24 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
             gg = fma(b1.x, b1.x, gg);
             gg = fma(b1.y, b1.y, gg);
         };
-        for (int tr = 0; tr < n_trips; tr++) {
-            double2 b[kCmTrip][2];
+        // the ring: slot u holds 16-pool block rb (rb % kCmRing == u) of this column block; as soon as a block has been
+        // consumed its registers take the block kCmRing further on -- of this column block or, near its end, of the
+        // warp's next one -- so kCmRing - 1 blocks (224 bytes per lane) are in flight at any time
+        for (int rb0 = 0; rb0 < nb_ring; rb0 += kCmRing) {
 #pragma unroll
-            for (int u = 0; u < kCmTrip; u++) {
-                b[u][0] = __ldcs(reinterpret_cast<const double2 *>(gb + tr * TR + 16 * u));
-                b[u][1] = __ldcs(reinterpret_cast<const double2 *>(gb + tr * TR + 16 * u + 8));
+            for (int u = 0; u < kCmRing; u++) {
+                const int rb = rb0 + u;
+                block16(make_double2(ring[u][0].x * zmask, ring[u][0].y * zmask),
+                        make_double2(ring[u][1].x * zmask, ring[u][1].y * zmask), rb * 16);
+                const bool here = rb + kCmRing < nb_ring;
+                const double *src = here ? gb + (rb + kCmRing) * 16 : gb_next + (rb + kCmRing - nb_ring) * 16;
+                if (here || has_next) {
+                    ring[u][0] = __ldcs(reinterpret_cast<const double2 *>(src));
+                    ring[u][1] = __ldcs(reinterpret_cast<const double2 *>(src + 8));
+                }
             }
-#pragma unroll
-            for (int u = 0; u < kCmTrip; u++)
-                block16(make_double2(b[u][0].x * zmask, b[u][0].y * zmask), make_double2(b[u][1].x * zmask, b[u][1].y * zmask),
-                        tr * TR + 16 * u);
         }
-        for (int i0 = n_trips * TR; i0 < n; i0 += 16) {  // the tail: pools >= n read as zero (the next column starts there)
+        for (int i0 = nb_ring * 16; i0 < n; i0 += 16) {  // what the ring does not cover: pools >= n read as zero
             double2 b[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -815,29 +838,17 @@ static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 extern "C" {
 
 // The eigen step's one-off costs -- mapping cuSOLVER and its dependencies (1.5 GB of shared objects) and creating the
-// handle, 0.3-3 s on a cold box, more when eight ranks do it at once -- start in a detached background thread when the
-// kinship handle is opened, so they overlap the column loading, the Gram kernel and the exchange step instead of
-// sitting in front of the first pg_kin_eig_select.  The thread owns a reference to its state: a handle that is closed
-// before the thread finishes (the sync2csv loader never reaches the eigen step) abandons it without waiting.
-static void kin_warm_solver(std::shared_ptr<pg_kin::Warm> w) {
-    const CusolverApi &sol = cusolver_api();  // the dlopen: the slow part
+// handle, 0.3-3 s on a cold box, more when eight ranks do it at once -- start in a background thread when the kinship
+// handle is opened, so they overlap the column loading, the Gram kernel and the exchange step instead of sitting in
+// front of the first pg_kin_eig_select.  The thread is joined by pg_kin_eig_select and by pg_kin_close (a detached
+// thread that is still inside dlopen when the process runs its exit handlers corrupts the heap -- measured): a caller
+// that only loads columns (sync2csv) waits for the mapping once per process, at its first close.
+static void kin_warm_solver(pg_kin *h) {
+    const CusolverApi &sol = cusolver_api();
+    if (!sol.ok) return;
+    if (cudaSetDevice(h->ctx->device) != cudaSuccess) return;
     cusolverDnHandle_t cs = nullptr;
-    {
-        std::unique_lock<std::mutex> lk(w->m);
-        if (w->abandoned) {  // closed meanwhile: do not touch CUDA any more (the process may be on its way out)
-            w->done = true;
-            return;
-        }
-    }
-    if (sol.ok && cudaSetDevice(w->device) == cudaSuccess && sol.create(&cs) != CUSOLVER_STATUS_SUCCESS) cs = nullptr;
-    std::unique_lock<std::mutex> lk(w->m);
-    if (w->abandoned) {
-        if (cs) sol.destroy(cs);
-    } else {
-        w->solver = cs;
-    }
-    w->done = true;
-    w->cv.notify_all();
+    if (sol.create(&cs) == CUSOLVER_STATUS_SUCCESS) h->solver = cs;
 }
 
 int pg_kin_open(pg_ctx *ctx, int n_pools, int64_t max_columns, pg_kin **out) {
@@ -865,24 +876,15 @@ int pg_kin_open(pg_ctx *ctx, int n_pools, int64_t max_columns, pg_kin **out) {
         return kfail(ctx, PG_ERR_CUDA, "pg_kin_open(%d pools, %lld columns): %s", n_pools, (long long)max_columns,
                      cudaGetErrorString(e));
     }
-    h->warm = std::make_shared<pg_kin::Warm>();
-    h->warm->device = ctx->device;
-    std::thread(kin_warm_solver, h->warm).detach();
+    h->warm = std::thread(kin_warm_solver, h);
     *out = h;
     return PG_OK;
 }
 
 int pg_kin_close(pg_kin *h) {
     if (!h) return PG_OK;
-    if (h->warm) {
-        std::unique_lock<std::mutex> lk(h->warm->m);
-        if (h->warm->done) {
-            if (h->warm->solver) cusolver_api().destroy(static_cast<cusolverDnHandle_t>(h->warm->solver));
-            h->warm->solver = nullptr;
-        } else {
-            h->warm->abandoned = true;  // the thread disposes of what it creates
-        }
-    }
+    if (h->warm.joinable()) h->warm.join();
+    if (h->solver) cusolver_api().destroy(static_cast<cusolverDnHandle_t>(h->solver));
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_G);
     cudaFree(h->d_K);
@@ -1206,18 +1208,15 @@ int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) 
     int *dinfo = nullptr;
     int rc = PG_OK;
     std::vector<double> A((size_t)n * n), W(n);
-    {  // the handle the background thread of pg_kin_open creates
-        std::unique_lock<std::mutex> lk(h->warm->m);
-        h->warm->cv.wait(lk, [&] { return h->warm->done; });
-    }
+    if (h->warm.joinable()) h->warm.join();  // the handle the background thread of pg_kin_open creates
     const CusolverApi &sol = cusolver_api();
     if (!sol.ok) return kfail(ctx, PG_ERR_CUDA, "pg_kin_eig_select: libcusolver could not be loaded (%s)", dlerror() ? dlerror() : "missing symbols");
-    if (!h->warm->solver) {
+    if (!h->solver) {
         cusolverDnHandle_t made = nullptr;
         if (sol.create(&made) != CUSOLVER_STATUS_SUCCESS) return kfail(ctx, PG_ERR_CUDA, "cusolverDnCreate failed");
-        h->warm->solver = made;
+        h->solver = made;
     }
-    cusolverDnHandle_t cs = static_cast<cusolverDnHandle_t>(h->warm->solver);
+    cusolverDnHandle_t cs = static_cast<cusolverDnHandle_t>(h->solver);
     do {
         sol.set_stream(cs, h->stream);
         if (cudaMalloc(&dA, (size_t)n * n * 8) != cudaSuccess || cudaMalloc(&dW, (size_t)n * 8) != cudaSuccess ||
