@@ -484,6 +484,18 @@ def nm_numbers(ctx, pb):
         out[name] = {"loci_per_s": L / (ms * 1e-3), "ms": ms, "loci": L, "n_pools": n}
         b.close()
         scan.close()
+    # mle_iter_with_kinship (mle_with_covariate, gwas/mle.rs:307-463): C4's pool count, no PCs (what raw frequencies
+    # select), one search over [sigma2, b_0, b_g] per column
+    n, P = 2000, 200_000
+    kin = pb.Kinship(ctx, n, P)
+    kin.synth(0x5EED0004, 0, P // 2)
+    kin.set_covariates(np.zeros((n, 0)))
+    y = pb.synth_phen_host(0x5EED0004, n, 1)
+    kin.mle_scan(y)
+    ms = kin.mle_scan(y, timed=True)[3]
+    out["mle_iter_with_kinship_c4_pools"] = {"columns_per_s": kin.columns / (ms * 1e-3), "ms": ms, "columns": int(kin.columns),
+                                             "n_pools": n, "n_covariates": 0}
+    kin.close()
     return {"nelder_mead": out}
 
 

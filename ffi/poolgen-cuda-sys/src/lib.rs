@@ -135,6 +135,8 @@ extern "C" {
     pub fn pg_kin_eigvals(kin: *mut pg_kin, out: *mut f64, count: c_int) -> c_int;
     pub fn pg_kin_set_covariates(kin: *mut pg_kin, cov: *const f64, m: c_int) -> c_int;
     pub fn pg_kin_covar_scan(kin: *mut pg_kin, phen: *const f64, k: c_int, iters: c_int, ms_total: *mut f32, beta: *mut *const f64, var: *mut *const f64, pval: *mut *const f64) -> c_int;
+    /// mle_iter_with_kinship: gwas::mle_with_covariate (src/gwas/mle.rs:307-463) over the same columns and covariates
+    pub fn pg_kin_mle_scan(kin: *mut pg_kin, phen: *const f64, k: c_int, ms: *mut f32, beta: *mut *const f64, var: *mut *const f64, pval: *mut *const f64) -> c_int;
     // ---- the reference's CSV rows
     pub fn pg_format_header(kind: c_int, out: *mut c_char, capacity: usize, n_bytes: *mut usize) -> c_int;
     pub fn pg_format_rows(kind: c_int, res: *const pg_results, labels: *const pg_row_labels, n_threads: c_int, out: *mut c_char, capacity: usize, n_bytes: *mut usize) -> c_int;

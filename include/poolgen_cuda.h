@@ -216,6 +216,14 @@ int pg_kin_set_covariates(pg_kin *kin, const double *cov /* n_pools x m row-majo
  * iters > 0 additionally times `iters` back-to-back launches with CUDA events */
 int pg_kin_covar_scan(pg_kin *kin, const double *phen, int k, int iters, float *ms_total, const double **beta,
                       const double **var, const double **pval);
+/* mle_iter_with_kinship: mle_with_covariate (src/gwas/mle.rs:307-463; call site src/main.rs:316-326) over the same
+ * resident columns and covariates -- per (column, phenotype) the maximum-likelihood fit of y on [1 | PCs | g] by the
+ * reference's Nelder-Mead search (mle.rs:85-114), v_b = sigma2 [(X'X)^-1]_gg, t = beta / v_b (sic, mle.rs:176),
+ * p from Student-t(n - 1); NaN where X'X has no inverse.  Same result layout as pg_kin_covar_scan, same rows
+ * (pg_format_kinship_rows).  At most 13 covariates (a simplex of 16 parameters) and 16 phenotypes per call;
+ * PG_ERR_UNSUPPORTED for the n < 2 + m form.  ms: kernel time of the scan. */
+int pg_kin_mle_scan(pg_kin *kin, const double *phen, int k, float *ms, const double **beta, const double **var,
+                    const double **pval);
 
 /* ---- several GPUs behind the ABI -----------------------------------------------------------------
  * The reference runs every analysis in one process (src/main.rs:246-298).  The per-locus scans shard over loci with no

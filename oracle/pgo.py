@@ -104,6 +104,7 @@ def lib():
             ("pgo_format_fisher_line", i, [C.c_char_p, C.c_uint64, C.POINTER(_TableResult), C.c_char_p, C.c_size_t]),
             ("pgo_bound_logit", d, [d, d, d]),
             ("pgo_mle_iterate", i, [u64p, u8p, i, i, dp, i, C.POINTER(_FilterStats), C.POINTER(_LocusResult)]),
+            ("pgo_mle_regress", i, [dp, i, i, dp, dp, dp, dp]),
             ("pgo_gwalpha", i, [u64p, u8p, i, i, dp, i, i, C.POINTER(_FilterStats), C.POINTER(_LocusResult)]),
             ("pgo_format_mle_lines", i, [C.c_char_p, C.c_uint64, C.POINTER(_LocusResult), i, C.c_char_p, C.c_size_t]),
             ("pgo_format_gwalpha_lines", i, [C.c_char_p, C.c_uint64, C.POINTER(_LocusResult), C.c_char_p, C.c_size_t]),
@@ -268,6 +269,16 @@ def _locus_call(fn, counts, alleles, phen, fs: FilterStats):
 
 def ols_iterate(counts, alleles, phen, fs): return _locus_call(lib().pgo_ols_iterate, counts, alleles, phen, fs)
 def mle_iterate(counts, alleles, phen, fs): return _locus_call(lib().pgo_mle_iterate, counts, alleles, phen, fs)
+
+
+def mle_regress(x, y):
+    """mle(x, y, false) for one phenotype (gwas/mle.rs:193-230): (rc, beta [p], var [p], pval [p])."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+    n, p = x.shape
+    beta, var, pval = (np.full(p, np.nan) for _ in range(3))
+    rc = lib().pgo_mle_regress(_dp(x), n, p, _dp(y), _dp(beta), _dp(var), _dp(pval))
+    return rc, beta, var, pval
 
 
 def bound_logit(x, lower, upper): return lib().pgo_bound_logit(float(x), float(lower), float(upper))
@@ -474,4 +485,37 @@ def ols_with_covariate(G_cols, phen, threshold, columns=None, return_eig=False):
             beta[c], var[c], pval[c] = b[1 + m], v[1 + m], p[1 + m]
     if return_eig:
         return m, beta, var, pval, w, V
+    return m, beta, var, pval
+
+
+def mle_with_covariate(G_cols, phen, threshold, columns=None, covariates=None):
+    """mle_with_covariate (gwas/mle.rs:307-463): like ols_with_covariate above with mle() in place of ols() -- each entry
+    the last coefficient of the maximum-likelihood fit of y on [1 | PCs | g] (Nelder-Mead on sigma2 and the betas), its
+    v_b and p (t = beta / v_b, df n - 1, mle.rs:160-185); NaN where the regression fails.  covariates: use these columns
+    [n, m] instead of the eigenvectors (the simplex search is NOT invariant to the basis of span(PCs), so a parity test
+    hands both sides the same columns).  Returns (m, beta [P, k], var, pval)."""
+    G = np.ascontiguousarray(G_cols, dtype=np.float64)
+    P, n = G.shape
+    y = np.ascontiguousarray(phen, dtype=np.float64)
+    if y.ndim == 1:
+        y = y[:, None].copy()
+    k = y.shape[1]
+    if covariates is None:
+        K = (G.T @ G) / float(P)
+        w, V = np.linalg.eigh(K)
+        w, V = w[::-1], V[:, ::-1]
+        m = select_eigenvectors(list(w), threshold)
+        cov = V[:, :m]
+    else:
+        cov = np.ascontiguousarray(covariates, dtype=np.float64).reshape(n, -1)
+        m = cov.shape[1]
+    beta, var, pval = (np.full((P, k), np.nan) for _ in range(3))
+    for c in (range(P) if columns is None else columns):
+        x = np.ones((n, 2 + m))
+        x[:, 1:1 + m] = cov
+        x[:, 1 + m] = G[c]
+        for j in range(k):
+            rc, b, v, p = mle_regress(x, y[:, j])
+            if rc == 0:
+                beta[c, j], var[c, j], pval[c, j] = b[1 + m], v[1 + m], p[1 + m]
     return m, beta, var, pval

@@ -1179,7 +1179,7 @@ int pgo_format_fisher_line(const char *chr, uint64_t pos, const pgo_table_result
 /* PINNED by the reference's own test_gwalpha lines (gwas/gwalpha.rs:392-447), which go      */
 /* through this solver with both cost functions: tests/test_oracle_golden.py.               */
 /* ====================================================================================== */
-#define PGO_NM_MAXD 8
+#define PGO_NM_MAXD 16
 typedef double (*pgo_cost_fn)(const double *x, int d, void *ctx);
 
 static void nm_sort(double v[][PGO_NM_MAXD], double *c, int nv, int d) {
@@ -1469,8 +1469,8 @@ static double mle_cost(const double *par, int d, void *vctx) {
     const double sigma2 = pgo_bound_logit(par[0], F64_EPSILON, 1e9);
     double ss = 0.0;
     for (int i = 0; i < m->n; i++) {
-        double xb = 0.0; /* x.dot(&betas): rows of fewer than 8 elements, sequential */
-        for (int j = 0; j < m->p; j++) xb = xb + m->x[(size_t)i * m->p + j] * par[1 + j];
+        /* x.dot(&betas): one contiguous row.dot per element (sequential below 8 columns, ndarray's 8 partial sums from there) */
+        const double xb = ndarray_dot_contig(m->x + (size_t)i * m->p, par + 1, m->p);
         const double e = m->y[i] - xb;
         ss = ss + pow(e, 2.0);
     }
@@ -1619,6 +1619,59 @@ int pgo_mle_iterate(const uint64_t *counts_in, const uint8_t *alleles_in, int n,
     free(freq);
     free(counts);
     return out->status = status;
+}
+
+/* mle() with remove_collinearities = false and one phenotype, as mle_with_covariate calls it for X = [1 | PCs | g]
+ * (mle.rs:193-230 through the Regression impl 85-191; call site 370-392): beta / var / pval of all p columns; nonzero
+ * where the reference returns Err (the caller then records NaN) */
+int pgo_mle_regress(const double *x, int n, int p, const double *y, double *beta, double *var, double *pval) {
+    if (p + 1 > PGO_NM_MAXD) return -2;
+    mle_ctx m = {n, p, x, y};
+    double par[PGO_NM_MAXD];
+    pgo_nelder_mead(mle_cost, &m, p + 1, 1.0, 1000, par, NULL);
+    const double ve = pgo_bound_logit(par[0], F64_EPSILON, 1e9);
+    double *xt = transpose(x, n, p), *vcv = NULL;
+    int fail = 0;
+    if (n < p) {
+        double *inv = matmul(x, n, p, xt, n);
+        if (pgo_lu_inverse(inv, n) != 0 || pgo_lu_det(inv, n) == 0.0) fail = 1;
+        if (!fail) {
+            double *t1 = matmul(xt, p, n, inv, n), *t2 = matmul(t1, p, n, inv, n);
+            vcv = matmul(t2, p, n, x, p);
+            for (int i = 0; i < p * p; i++) vcv[i] = ve * vcv[i];
+            free(t1);
+            free(t2);
+        }
+        free(inv);
+    } else {
+        double *inv = matmul(xt, p, n, x, p);
+        if (pgo_lu_inverse(inv, p) != 0 || pgo_lu_det(inv, p) == 0.0) fail = 1;
+        if (!fail) {
+            vcv = (double *)malloc(sizeof(double) * (size_t)p * (size_t)p);
+            for (int i = 0; i < p * p; i++) vcv[i] = ve * inv[i];
+        }
+        free(inv);
+    }
+    free(xt);
+    if (fail) return 1;
+    const double freedom = (double)n - 1.0;
+    if (!(freedom > 0.0)) { /* StudentsT::new(..).unwrap() panics */
+        free(vcv);
+        return 2;
+    }
+    for (int i = 0; i < p; i++) {
+        const double b = par[1 + i], v = vcv[(size_t)i * p + i];
+        const double t = b / v; /* mle.rs:176 */
+        double pv;
+        if (isinf(t)) pv = 0.0;
+        else if (isnan(t)) pv = 1.0;
+        else pv = 2.00 * (1.00 - pgo_students_t_cdf(fabs(t), freedom));
+        beta[i] = b;
+        var[i] = v;
+        pval[i] = pv;
+    }
+    free(vcv);
+    return 0;
 }
 
 /* output lines of mle_iterate (mle.rs:283-303): beta rounded to 6 digits, p-value unrounded */

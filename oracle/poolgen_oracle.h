@@ -149,6 +149,8 @@ int pgo_format_gwalpha_lines(const char *chr, uint64_t pos, const pgo_locus_resu
 /* mle_iterate (gwas/mle.rs:232-305): out->stat = beta, var = v_b, t = beta / v_b (sic), pval */
 int pgo_mle_iterate(const uint64_t *counts, const uint8_t *alleles, int n, int p, const double *phen, int k,
                     const pgo_filter_stats *fs, pgo_locus_result *out);
+/* one regression of mle_with_covariate (gwas/mle.rs:307-463): mle(x, y, false) for one phenotype; x n x p row-major */
+int pgo_mle_regress(const double *x, int n, int p, const double *y, double *beta, double *var, double *pval);
 int pgo_format_mle_lines(const char *chr, uint64_t pos, const pgo_locus_result *r, int k, char *buf, size_t cap);
 
 /* ---- output lines (ols.rs:255-275, correlation_test.rs:113-128, chisq_test.rs:37-46,

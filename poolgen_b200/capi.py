@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "pg_kin_open", "pg_kin_close", "pg_kin_reset", "pg_kin_columns", "pg_kin_append_columns", "pg_kin_append_counts",
     "pg_kin_last_labels", "pg_kin_append_sync_text", "pg_kin_text_labels", "pg_kin_synth", "pg_kin_get_columns", "pg_kin_gram", "pg_kin_gram_time", "pg_kin_partial",
     "pg_kin_partial_get", "pg_kin_partial_set", "pg_kin_eig_select", "pg_kin_eigvals", "pg_kin_set_covariates",
-    "pg_kin_covar_scan", "pg_format_header", "pg_format_rows", "pg_format_rows_ex", "pg_format_kinship_rows", "pg_format_f64", "pg_sort_loci",
+    "pg_kin_covar_scan", "pg_kin_mle_scan", "pg_format_header", "pg_format_rows", "pg_format_rows_ex", "pg_format_kinship_rows", "pg_format_f64", "pg_sort_loci",
     "pg_format_frequency_header", "pg_format_frequency_rows",
     "pg_shard_range", "pg_nccl_version", "pg_init_multi", "pg_comm_unique_id", "pg_comm_init_rank", "pg_comm_info",
     "pg_comm_destroy", "pg_kin_allreduce", "pg_kin_copy_covariates",
@@ -149,6 +149,7 @@ def lib():
             "pg_kin_eigvals": (i, [vp, vp, i]),
             "pg_kin_set_covariates": (i, [vp, vp, i]),
             "pg_kin_covar_scan": (i, [vp, vp, i, i, C.POINTER(C.c_float), pvp, pvp, pvp]),
+            "pg_kin_mle_scan": (i, [vp, vp, i, C.POINTER(C.c_float), pvp, pvp, pvp]),
             "pg_shard_range": (i, [i64, i, i, C.POINTER(i64), C.POINTER(i64)]),
             "pg_nccl_version": (i, [C.POINTER(i)]),
             "pg_init_multi": (i, [C.POINTER(i), i, pvp, pvp]),
@@ -718,6 +719,26 @@ class Kinship:
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(k, P)).copy()
         out = (arr(pb), arr(pv), arr(pp))
         return out + (float(ms.value),) if iters > 0 else out
+
+    def mle_scan(self, phen, timed: bool = False):
+        """mle_with_covariate (gwas/mle.rs:307-463): phen [n_pools, k] -> (beta, var, pval) each [k, columns]
+        (+ kernel milliseconds if timed)."""
+        y = np.ascontiguousarray(phen, dtype=np.float64)
+        if y.ndim == 1:
+            y = y[:, None].copy()
+        k = y.shape[1]
+        ms = C.c_float()
+        pb, pv, pp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(lib().pg_kin_mle_scan(self._h, y.ctypes.data, int(k), C.byref(ms), C.byref(pb), C.byref(pv), C.byref(pp)),
+                 "pg_kin_mle_scan")
+        P = self.columns
+
+        def arr(p):
+            if P == 0:
+                return np.zeros((k, 0))
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(k, P)).copy()
+        out = (arr(pb), arr(pv), arr(pp))
+        return out + (float(ms.value),) if timed else out
 
     def close(self):
         if self._h:

@@ -138,6 +138,22 @@ struct NmParams {
 };
 cudaError_t launch_nm(const NmParams &p, int sm_count, cudaStream_t s);
 
+// mle_with_covariate (src/gwas/mle.rs:307-463) over the resident allele columns of a pg_kin (pg_nm.cu): X = [1 | PCs | g]
+constexpr int kKinMleMaxM = 13;  // covariates: the simplex search runs over sigma2 + (2 + m) coefficients <= 16 parameters
+struct KinMleParams {
+    const double *G;     // [P][ldg] allele columns
+    int64_t P;
+    int n, ldg, m, k;
+    const double *Z;     // [m + k][ldg]: centred covariates, then centred phenotypes
+    const double *fix;   // zbar[m] | Szz[m][m] | Szz^-1 [m][m] | per phenotype: ybar, Syy, Szy[m]
+    double df, ln_beta;  // Student-t(n - 1)
+    const void *ptab;
+    double ptab_isd, ptab_bits;
+    int ptab_M;
+    double *beta, *var, *pval;  // [k][P]
+};
+cudaError_t launch_kin_mle(const KinMleParams &p, int sm_count, cudaStream_t s);
+
 // launchers implemented in the kernel translation units
 cudaError_t launch_scan(const ScanParams &p, int sm_count, cudaStream_t s);
 cudaError_t launch_tables(const TableParams &p, int sm_count, cudaStream_t s);

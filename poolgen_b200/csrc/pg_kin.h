@@ -25,6 +25,9 @@ struct pg_kin {
     bool minnorm = false;         // m == n: the reference's n < p branch (pg_kin_eig_select)
     std::vector<double> eigvals;  // descending
     std::vector<double> Q;        // [1+m][ldg] orthonormal basis of [1 | PCs] (host)
+    std::vector<double> C;        // [m][ldg] the covariates themselves (pg_kin_mle_scan: the simplex search is not basis-invariant)
+    double *d_mle = nullptr;      // pg_kin_mle_scan: centred covariates and phenotypes, then the fixed moments
+    size_t mle_bytes = 0;
     double *d_V = nullptr;        // [(1+m) + k][ldg]
     size_t V_bytes = 0;
     double *d_ptab = nullptr;

@@ -893,6 +893,7 @@ int pg_kin_close(pg_kin *h) {
     cudaFree(h->d_ptab);
     cudaFree(h->d_res);
     cudaFree(h->d_defer);
+    cudaFree(h->d_mle);
     if (h->h_res) cudaFreeHost(h->h_res);
     cudaFree(h->d_sel);
     cudaFree(h->d_off);
@@ -1261,6 +1262,7 @@ int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) 
         // X = [1 | V | g] has more columns than rows -- the reference's n < p branch (ols.rs:67-75).  span(V) is the
         // whole space, so only the intercept direction is kept here; covar_kernel forms the minimum-norm coefficient
         h->minnorm = true;
+        h->C.clear();
         h->Q.assign((size_t)h->ldg, 0.0);
         for (int i = 0; i < n; i++) h->Q[i] = 1.0 / sqrt((double)n);
         return PG_OK;
@@ -1271,6 +1273,7 @@ int pg_kin_eig_select(pg_kin *h, int64_t P_total, double threshold, int *m_out) 
     for (int i = 0; i < n; i++) h->Q[i] = 1.0;
     for (int l = 0; l < m; l++)
         for (int i = 0; i < n; i++) h->Q[(size_t)(1 + l) * ldg + i] = A[(size_t)(n - 1 - l) * n + i];
+    h->C.assign(h->Q.begin() + ldg, h->Q.end());
     for (int c = 0; c < nq; c++) {
         double *qc = &h->Q[(size_t)c * ldg];
         for (int pass = 0; pass < 2; pass++)
@@ -1298,6 +1301,7 @@ int pg_kin_copy_covariates(pg_kin *dst, const pg_kin *src) {
     dst->m = src->m;
     dst->minnorm = src->minnorm;
     dst->Q = src->Q;
+    dst->C = src->C;
     dst->eigvals = src->eigvals;
     dst->P_total = src->P_total;
     return PG_OK;
@@ -1321,6 +1325,7 @@ int pg_kin_set_covariates(pg_kin *h, const double *cov, int m) {
     for (int i = 0; i < n; i++) h->Q[i] = 1.0;
     for (int l = 0; l < m; l++)
         for (int i = 0; i < n; i++) h->Q[(size_t)(1 + l) * ldg + i] = cov[(size_t)i * m + l];
+    h->C.assign(h->Q.begin() + ldg, h->Q.end());
     for (int c = 0; c < nq; c++) {
         double *qc = &h->Q[(size_t)c * ldg];
         for (int pass = 0; pass < 2; pass++)
@@ -1479,6 +1484,35 @@ static int covar_launch(pg_kin *h, const pg::CovarParams &cp) {
     return PG_OK;
 }
 
+// the Student-t(n - 1) table and the [3][k][P] record buffers shared by pg_kin_covar_scan and pg_kin_mle_scan
+static int kin_prepare_records(pg_kin *h, int k) {
+    pg_ctx *ctx = h->ctx;
+    const double df = (double)h->n - 1.0;
+    if (!h->d_ptab) {
+        pg::PTable tab = pg::build_ptable(df);
+        if (tab.max_err < 2e-9) {
+            KCUDA(ctx, cudaMalloc(&h->d_ptab, tab.coef.size() * 8));
+            KCUDA(ctx, cudaMemcpyAsync(h->d_ptab, tab.coef.data(), tab.coef.size() * 8, cudaMemcpyHostToDevice, h->stream));
+            KCUDA(ctx, cudaStreamSynchronize(h->stream));
+            h->ptab_M = tab.M;
+            h->ptab_isd = tab.inv_sqrt_df;
+            h->ptab_bits = tab.bits;
+        }
+    }
+    const size_t elems = (size_t)3 * k * std::max<int64_t>(h->P, 1);
+    if (h->res_elems < elems) {
+        KCUDA(ctx, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_res);
+        if (h->h_res) cudaFreeHost(h->h_res);
+        h->d_res = nullptr, h->h_res = nullptr;
+        KCUDA(ctx, cudaMalloc(&h->d_res, elems * 8));
+        KCUDA(ctx, cudaHostAlloc((void **)&h->h_res, elems * 8, cudaHostAllocDefault));
+        h->res_elems = elems;
+    }
+    h->k = k;
+    return PG_OK;
+}
+
 extern "C" {
 
 // per-column regression; phen n x k row-major.  Results (host, pinned, valid until the next call / close):
@@ -1528,28 +1562,7 @@ int pg_kin_covar_scan(pg_kin *h, const double *phen, int k, int iters, float *ms
     KCUDA(ctx, cudaMemcpyAsync(h->d_V, V.data(), vb, cudaMemcpyHostToDevice, h->stream));
     KCUDA(ctx, cudaStreamSynchronize(h->stream));
     const double df = (double)n - 1.0;
-    if (!h->d_ptab) {
-        pg::PTable tab = pg::build_ptable(df);
-        if (tab.max_err < 2e-9) {
-            KCUDA(ctx, cudaMalloc(&h->d_ptab, tab.coef.size() * 8));
-            KCUDA(ctx, cudaMemcpyAsync(h->d_ptab, tab.coef.data(), tab.coef.size() * 8, cudaMemcpyHostToDevice, h->stream));
-            KCUDA(ctx, cudaStreamSynchronize(h->stream));
-            h->ptab_M = tab.M;
-            h->ptab_isd = tab.inv_sqrt_df;
-            h->ptab_bits = tab.bits;
-        }
-    }
-    const size_t elems = (size_t)3 * k * std::max<int64_t>(h->P, 1);
-    if (h->res_elems < elems) {
-        KCUDA(ctx, cudaStreamSynchronize(h->stream));
-        cudaFree(h->d_res);
-        if (h->h_res) cudaFreeHost(h->h_res);
-        h->d_res = nullptr, h->h_res = nullptr;
-        KCUDA(ctx, cudaMalloc(&h->d_res, elems * 8));
-        KCUDA(ctx, cudaHostAlloc((void **)&h->h_res, elems * 8, cudaHostAllocDefault));
-        h->res_elems = elems;
-    }
-    h->k = k;
+    if (int rc = kin_prepare_records(h, k)) return rc;
     cp.G = h->d_G;
     cp.P = h->P;
     cp.ldg = ldg;
@@ -1580,6 +1593,125 @@ int pg_kin_covar_scan(pg_kin *h, const double *phen, int k, int iters, float *ms
     KCUDA(ctx, cudaMemcpyAsync(h->h_res, h->d_res, (size_t)3 * k * h->P * 8, cudaMemcpyDeviceToHost, h->stream));
     KCUDA(ctx, cudaStreamSynchronize(h->stream));
     if (iters > 0 && ms_total) KCUDA(ctx, cudaEventElapsedTime(ms_total, h->ev0, h->ev1));
+    if (beta) *beta = h->h_res;
+    if (var) *var = h->h_res + (size_t)k * h->P;
+    if (pval) *pval = h->h_res + (size_t)2 * k * h->P;
+    return PG_OK;
+}
+
+// mle_iter_with_kinship: mle_with_covariate (src/gwas/mle.rs:307-463) over the resident columns, with the covariates
+// pg_kin_eig_select / pg_kin_set_covariates left.  Everything that does not involve the allele column -- the centred
+// covariates and phenotypes and their moments, Szz^-1 -- is formed here on the host (n x (m + k), tiny)
+int pg_kin_mle_scan(pg_kin *h, const double *phen, int k, float *ms, const double **beta, const double **var,
+                    const double **pval) {
+    if (!h || !phen || k < 1) return PG_ERR_ARG;
+    pg_ctx *ctx = h->ctx;
+    if (h->m < 0) return kfail(ctx, PG_ERR_STATE, "pg_kin_mle_scan before pg_kin_eig_select / pg_kin_set_covariates");
+    const int n = h->n, ldg = h->ldg, m = h->m;
+    if (h->minnorm || m + 2 > n)
+        return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_mle_scan: %d covariates for %d pools (the n < p form of mle.rs:130-140)", m, n);
+    if (m > pg::kKinMleMaxM)
+        return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_mle_scan: %d covariates > %d (simplex of at most 16 parameters)", m, pg::kKinMleMaxM);
+    if (k > 16) return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_mle_scan: %d phenotypes > 16 per call", k);
+    if ((int)h->C.size() != m * ldg) return kfail(ctx, PG_ERR_STATE, "pg_kin_mle_scan: covariates missing");
+    KCUDA(ctx, cudaSetDevice(ctx->device));
+    const int nfix = m + 2 * m * m + k * (2 + m);
+    std::vector<double> Z((size_t)(m + k) * ldg + nfix, 0.0);
+    double *fix = Z.data() + (size_t)(m + k) * ldg;
+    double *zbar = fix, *Szz = fix + m, *Wzz = Szz + m * m, *phf = Wzz + m * m;
+    for (int l = 0; l < m; l++) {
+        const double *c = &h->C[(size_t)l * ldg];
+        double s = 0.0;
+        for (int i = 0; i < n; i++) s += c[i];
+        zbar[l] = s / (double)n;
+        for (int i = 0; i < n; i++) Z[(size_t)l * ldg + i] = c[i] - zbar[l];
+    }
+    for (int a = 0; a < m; a++)
+        for (int b = 0; b <= a; b++) {
+            double s = 0.0;
+            for (int i = 0; i < n; i++) s += Z[(size_t)a * ldg + i] * Z[(size_t)b * ldg + i];
+            Szz[a * m + b] = Szz[b * m + a] = s;
+        }
+    if (m > 0) {  // Szz^-1 by Gauss-Jordan with partial pivoting
+        std::vector<double> M((size_t)m * 2 * m, 0.0);
+        for (int a = 0; a < m; a++) {
+            for (int b = 0; b < m; b++) M[(size_t)a * 2 * m + b] = Szz[a * m + b];
+            M[(size_t)a * 2 * m + m + a] = 1.0;
+        }
+        for (int c = 0; c < m; c++) {
+            int pr = c;
+            for (int r = c + 1; r < m; r++)
+                if (fabs(M[(size_t)r * 2 * m + c]) > fabs(M[(size_t)pr * 2 * m + c])) pr = r;
+            if (!(fabs(M[(size_t)pr * 2 * m + c]) > 1e-12 * fabs(Szz[c * m + c])))
+                return kfail(ctx, PG_ERR_UNSUPPORTED, "pg_kin_mle_scan: covariate %d is collinear with the others", c);
+            for (int e = 0; e < 2 * m; e++) std::swap(M[(size_t)c * 2 * m + e], M[(size_t)pr * 2 * m + e]);
+            const double piv = 1.0 / M[(size_t)c * 2 * m + c];
+            for (int e = 0; e < 2 * m; e++) M[(size_t)c * 2 * m + e] *= piv;
+            for (int r = 0; r < m; r++) {
+                if (r == c) continue;
+                const double f = M[(size_t)r * 2 * m + c];
+                for (int e = 0; e < 2 * m; e++) M[(size_t)r * 2 * m + e] -= f * M[(size_t)c * 2 * m + e];
+            }
+        }
+        for (int a = 0; a < m; a++)
+            for (int b = 0; b < m; b++) Wzz[a * m + b] = M[(size_t)a * 2 * m + m + b];
+    }
+    for (int j = 0; j < k; j++) {
+        double *yt = &Z[(size_t)(m + j) * ldg], *pf = phf + (size_t)j * (2 + m);
+        double s = 0.0;
+        for (int i = 0; i < n; i++) s += phen[(size_t)i * k + j];
+        const double ybar = s / (double)n;
+        double syy = 0.0;
+        for (int i = 0; i < n; i++) {
+            yt[i] = phen[(size_t)i * k + j] - ybar;
+            syy += yt[i] * yt[i];
+        }
+        pf[0] = ybar;
+        pf[1] = syy;
+        for (int l = 0; l < m; l++) {
+            double c = 0.0;
+            for (int i = 0; i < n; i++) c += Z[(size_t)l * ldg + i] * yt[i];
+            pf[2 + l] = c;
+        }
+    }
+    const size_t zb = Z.size() * 8;
+    if (h->mle_bytes < zb) {
+        KCUDA(ctx, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_mle);
+        h->d_mle = nullptr;
+        h->mle_bytes = 0;
+        KCUDA(ctx, cudaMalloc(&h->d_mle, zb));
+        h->mle_bytes = zb;
+    }
+    KCUDA(ctx, cudaMemcpyAsync(h->d_mle, Z.data(), zb, cudaMemcpyHostToDevice, h->stream));
+    KCUDA(ctx, cudaStreamSynchronize(h->stream));
+    if (int rc = kin_prepare_records(h, k)) return rc;
+    const double df = (double)n - 1.0;
+    pg::KinMleParams mp;
+    memset(&mp, 0, sizeof mp);
+    mp.G = h->d_G;
+    mp.P = h->P;
+    mp.n = n;
+    mp.ldg = ldg;
+    mp.m = m;
+    mp.k = k;
+    mp.Z = h->d_mle;
+    mp.fix = h->d_mle + (size_t)(m + k) * ldg;
+    mp.df = df;
+    mp.ln_beta = pg::statrs::ln_gamma(df / 2.0 + 0.5) - pg::statrs::ln_gamma(df / 2.0) - pg::statrs::ln_gamma(0.5);
+    mp.ptab = h->d_ptab;
+    mp.ptab_isd = h->ptab_isd;
+    mp.ptab_bits = h->ptab_bits;
+    mp.ptab_M = h->ptab_M;
+    mp.beta = h->d_res;
+    mp.var = h->d_res + (size_t)k * h->P;
+    mp.pval = h->d_res + (size_t)2 * k * h->P;
+    KCUDA(ctx, cudaEventRecord(h->ev0, h->stream));
+    KCUDA(ctx, pg::launch_kin_mle(mp, ctx->sm_count, h->stream));
+    KCUDA(ctx, cudaEventRecord(h->ev1, h->stream));
+    KCUDA(ctx, cudaMemcpyAsync(h->h_res, h->d_res, (size_t)3 * k * h->P * 8, cudaMemcpyDeviceToHost, h->stream));
+    KCUDA(ctx, cudaStreamSynchronize(h->stream));
+    if (ms) KCUDA(ctx, cudaEventElapsedTime(ms, h->ev0, h->ev1));
     if (beta) *beta = h->h_res;
     if (var) *var = h->h_res + (size_t)k * h->P;
     if (pval) *pval = h->h_res + (size_t)2 * k * h->P;

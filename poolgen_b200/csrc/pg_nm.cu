@@ -15,6 +15,7 @@
 //   is then a quadratic form in beta -- O(p^2) per evaluation instead of O(n p) -- and lane j minimises phenotype j.
 //   gwalpha: a thread per (locus, allele); the cost sums squared differences (LS) or log10 differences (ML) of Beta
 //   cdfs, statrs' continued fraction with the shapes of the current vertex.
+//   mle_iter_with_kinship  gwas::mle_with_covariate (src/gwas/mle.rs:307-463): kin_mle_kernel over a pg_kin's columns.
 #include "pg_device.cuh"
 #include "pg_internal.h"
 
@@ -26,9 +27,9 @@ __device__ __forceinline__ double bound_logit(double x, double lo, double hi) { 
 
 // argmin 0.8.1 Nelder-Mead: alpha 1, gamma 2, rho = sigma =
 // 0.5, sd_tolerance = f64::EPSILON, initial simplex h everywhere and h + 0.5 on the diagonal, stable sort by cost.
-template <typename Cost>
+template <int MAXD, typename Cost>
 __device__ void nelder_mead(const Cost &cost, int d, double h, int max_iters, double *best) {
-    double v[kNmMaxD + 1][kNmMaxD], c[kNmMaxD + 1];
+    double v[MAXD + 1][MAXD], c[MAXD + 1];
     const int nv = d + 1;
     for (int i = 0; i < nv; i++)
         for (int j = 0; j < d; j++) v[i][j] = (i == j) ? h + 0.5 : h;
@@ -36,7 +37,7 @@ __device__ void nelder_mead(const Cost &cost, int d, double h, int max_iters, do
     auto sort = [&]() {
         for (int a = 1; a < nv; a++) {
             const double ca = c[a];
-            double va[kNmMaxD];
+            double va[MAXD];
             for (int j = 0; j < d; j++) va[j] = v[a][j];
             int b = a - 1;
             while (b >= 0 && ca < c[b]) {
@@ -64,7 +65,7 @@ __device__ void nelder_mead(const Cost &cost, int d, double h, int max_iters, do
         const double sd = sqrt(1.0 / ((double)nv - 1.0) * ss);
         if (sd < kEps) break;
         if (it >= max_iters) break;
-        double x0[kNmMaxD], xr[kNmMaxD], xt[kNmMaxD];
+        double x0[MAXD], xr[MAXD], xt[MAXD];
         for (int j = 0; j < d; j++) x0[j] = v[0][j];
         for (int i = 1; i < nv - 1; i++)
             for (int j = 0; j < d; j++) x0[j] = x0[j] + v[i][j];
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kMleWarps * 32) mle_kernel(const NmParams p) {
                             return (nn / 2.00) * log(2.00 * 3.14159265358979323846264338327950288 * s2) + (1.00 / s2) * rss;
                         };
                         double par[kNmMaxD];
-                        nelder_mead(cost, pw + 1, 1.0, 1000, par);
+                        nelder_mead<kNmMaxD>(cost, pw + 1, 1.0, 1000, par);
                         const double ve = bound_logit(par[0], kEps, 1e9);
                         for (int c = 0; c < pw; c++) {
                             b[c] = par[1 + c];
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(128) gwalpha_kernel(const NmParams p) {
             return -ra - rb;
         };
         double par[kNmMaxD];
-        nelder_mead(cost, 4, 1.0, 1000, par);
+        nelder_mead<kNmMaxD>(cost, 4, 1.0, 1000, par);
         double sol[4];
         for (int e = 0; e < 4; e++) sol[e] = bound_logit(par[e], kEps, 10.00);
         const double a_mu = p.gw_min + (p.gw_max - p.gw_min) * (sol[0] / (sol[0] + sol[1]));
@@ -510,6 +511,131 @@ __global__ void __launch_bounds__(128) gwalpha_kernel(const NmParams p) {
         o[2] = nan("");
         o[3] = nan("");
     }
+}
+
+// ---- mle_iter_with_kinship: mle_with_covariate (mle.rs:307-463) over the resident allele columns --------------------
+// One regression per (column, phenotype) with X = [1 | PCs | g] (mle.rs:370-392) and mle(x, y, false): Nelder-Mead over
+// [logit sigma2, b_0, b_PC.., b_g] from the all-ones simplex, v_b = sigma2 [(X'X)^-1]_gg, t = b / v_b (sic, mle.rs:176),
+// p from Student-t(n - 1).  A warp takes 32 columns: the whole warp forms the centred moments of a column against the
+// covariates and phenotypes (lane = pool; everything that does not involve g is formed once on the host), then lane =
+// column runs the searches on the quadratic form
+//   RSS(b) = Syy - 2 (b_z'Szy + b_g Sgy) + b_z'Szz b_z + 2 b_g b_z'Szg + b_g^2 Sgg + n (ybar - b_0 - b_z'zbar - b_g gbar)^2
+constexpr int kKmWarps = 4;
+constexpr int kKmMaxD = kKinMleMaxM + 3;
+
+__global__ void __launch_bounds__(kKmWarps * 32) kin_mle_kernel(const KinMleParams p, int fix_pad) {
+    extern __shared__ __align__(16) double km_sm[];  // fix | [warps][32][2 + m + k]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int m = p.m, k = p.k, n = p.n;
+    const int nfix = m + 2 * m * m + k * (2 + m);
+    for (int i = threadIdx.x; i < nfix; i += blockDim.x) km_sm[i] = p.fix[i];
+    __syncthreads();
+    const double *zbar = km_sm, *Szz = zbar + m, *Wzz = Szz + m * m, *phf = Wzz + m * m;
+    const int mw = 2 + m + k;  // gbar, Sgg, Szg[m], Sgy[k]
+    double *mom = km_sm + fix_pad + (size_t)wib * 32 * mw;
+    const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_isd, p.ptab_bits, p.ptab_M};
+    const double nn = (double)n;
+    const int64_t n_blocks = (p.P + 31) / 32;
+    for (int64_t blk = (int64_t)blockIdx.x * kKmWarps + wib; blk < n_blocks; blk += (int64_t)gridDim.x * kKmWarps) {
+        const int64_t c0 = blk * 32;
+        const int cnt = (int)min((int64_t)32, p.P - c0);
+        for (int g = 0; g < cnt; g++) {
+            const double *col = p.G + (size_t)(c0 + g) * p.ldg;
+            double *mo = mom + (size_t)g * mw;
+            double s = 0.0;
+            for (int i = lane; i < n; i += 32) s += col[i];
+            const double gbar = warp_sum_fixed(s) / nn;
+            double sgg = 0.0;
+            for (int i = lane; i < n; i += 32) {
+                const double d = col[i] - gbar;
+                sgg = fma(d, d, sgg);
+            }
+            sgg = warp_sum_fixed(sgg);
+            if (lane == 0) mo[0] = gbar, mo[1] = sgg;
+            for (int v0 = 0; v0 < m + k; v0 += 4) {
+                const int nv = min(4, m + k - v0);
+                double a[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int i = lane; i < n; i += 32) {
+                    const double d = col[i] - gbar;
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if (e < nv) a[e] = fma(p.Z[(size_t)(v0 + e) * p.ldg + i], d, a[e]);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const double t = warp_sum_fixed(a[e]);
+                    if (lane == 0 && e < nv) mo[2 + v0 + e] = t;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < cnt) {
+            const double *mo = mom + (size_t)lane * mw;
+            const double gbar = mo[0], Sgg = mo[1];
+            double Szg[kKinMleMaxM];
+            for (int l = 0; l < kKinMleMaxM; l++) Szg[l] = l < m ? mo[2 + l] : 0.0;
+            // [(X'X)^-1]_gg = 1 / (Sgg - Szg' Szz^-1 Szg); a column inside span[1 | PCs] has no inverse (mle.rs:143-148: Err -> NaN)
+            double proj = 0.0;
+            for (int a = 0; a < m; a++)
+                for (int b = 0; b < m; b++) proj += Szg[a] * Wzz[a * m + b] * Szg[b];
+            const double den = Sgg - proj;
+            const bool singular = !(den > fmax(64.0, nn * nn) * kEps * kEps * (Sgg + nn * gbar * gbar));
+            const double dgi = 1.0 / den;
+            for (int j = 0; j < k; j++) {
+                const double *pf = phf + (size_t)j * (2 + m);
+                const double ybar = pf[0], Syy = pf[1], Sgy = mo[2 + m + j];
+                const double *Szy = pf + 2;
+                double o0 = nan(""), o1 = nan(""), o3 = nan("");
+                if (!singular) {
+                    auto cost = [&](const double *par) {
+                        const double s2 = bound_logit(par[0], kEps, 1e9);
+                        const double *bz = par + 2, bg = par[2 + m];
+                        double lin = bg * Sgy, quad = bg * bg * Sgg, off = ybar - par[1] - bg * gbar, cross = 0.0;
+                        for (int a = 0; a < m; a++) {
+                            lin += bz[a] * Szy[a];
+                            off -= bz[a] * zbar[a];
+                            cross += bz[a] * Szg[a];
+                            double r = 0.0;
+                            for (int b = 0; b < m; b++) r += Szz[a * m + b] * bz[b];
+                            quad += bz[a] * r;
+                        }
+                        const double rss = (Syy - 2.0 * lin + (quad + 2.0 * bg * cross)) + nn * off * off;
+                        return (nn / 2.00) * log(2.00 * 3.14159265358979323846264338327950288 * s2) + (1.00 / s2) * rss;
+                    };
+                    double par[kKmMaxD];
+                    nelder_mead<kKmMaxD>(cost, m + 3, 1.0, 1000, par);
+                    const double ve = bound_logit(par[0], kEps, 1e9);
+                    o0 = par[2 + m];
+                    o1 = ve * dgi;
+                    const double t = o0 / o1;
+                    if (isinf(t))
+                        o3 = 0.0;
+                    else if (t != t)
+                        o3 = 1.0;
+                    else
+                        o3 = p.ptab ? student_two_sided_tab(fabs(t), p.df, ptab) : student_two_sided(fabs(t), p.df, p.ln_beta);
+                }
+                const size_t at = (size_t)j * p.P + (size_t)(c0 + lane);
+                p.beta[at] = o0;
+                p.var[at] = o1;
+                p.pval[at] = o3;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_kin_mle(const KinMleParams &p, int sm_count, cudaStream_t s) {
+    if (p.P == 0) return cudaSuccess;
+    const int nfix = p.m + 2 * p.m * p.m + p.k * (2 + p.m);
+    const int fix_pad = (nfix + 1) & ~1;
+    const size_t smem = ((size_t)fix_pad + (size_t)kKmWarps * 32 * (2 + p.m + p.k)) * 8;
+    cudaError_t e = cudaFuncSetAttribute(kin_mle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t grid = ((p.P + 31) / 32 + kKmWarps - 1) / kKmWarps;
+    if (grid > (int64_t)sm_count * 4) grid = (int64_t)sm_count * 4;
+    kin_mle_kernel<<<(unsigned)grid, kKmWarps * 32, smem, s>>>(p, fix_pad);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_nm(const NmParams &p, int sm_count, cudaStream_t s) {

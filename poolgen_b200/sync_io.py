@@ -373,13 +373,8 @@ def write_csv(self, ctx: Context, filter_stats: FilterStats, keep_p_minus_1: boo
     return out
 
 
-def ols_iter_with_kinship(self, ctx: Context, filter_stats: FilterStats, keep_p_minus_1: bool,
-                          xxt_eigen_variance_explained: float, out: str, n_threads: int,
-                          block_bytes: int = 32 << 20) -> str:
-    """`poolgen ols_iter_with_kinship` (src/main.rs:280-298): into_genotypes_and_phenotypes (src/base/sync.rs:1106-1179)
-    then ols_with_covariate (src/gwas/ols.rs:278-436) and its writer, including the label indexing of
-    src/gwas/ols.rs:421-424 (row i of the allele columns carries entry i of the label vectors, whose entry 0 is the
-    intercept's)"""
+def _iter_with_kinship(self, ctx: Context, filter_stats: FilterStats, keep_p_minus_1: bool,
+                       xxt_eigen_variance_explained: float, out: str, n_threads: int, block_bytes: int, method: str) -> str:
     if out != "" and os.path.exists(out):
         raise PgError("Cannot write to output file")
     if np.isnan(self.phen_matrix).any():
@@ -393,7 +388,8 @@ def ols_iter_with_kinship(self, ctx: Context, filter_stats: FilterStats, keep_p_
             raise PgError("No data passed the filtering variables.")
         ld.kin.gram()
         n_eigenvecs = ld.kin.eig_select(P, float(xxt_eigen_variance_explained))
-        beta, _var, pval = ld.kin.covar_scan(self.phen_matrix)   # [k, P] in file order
+        scan = ld.kin.covar_scan if method == "ols" else ld.kin.mle_scan
+        beta, _var, pval = scan(self.phen_matrix)   # [k, P] in file order
     finally:
         ld.kin.close()
     # the matrix columns follow the loci sorted by (chromosome, position): permute the records into that order
@@ -410,14 +406,36 @@ def ols_iter_with_kinship(self, ctx: Context, filter_stats: FilterStats, keep_p_
     position = [0] + [int(ld.positions[ld.col_locus[c]]) for c in seq]
     allele = ["intercept"] + [capi.ALLELE_NAMES[ld.col_allele[c]] for c in seq]
     rows = capi.format_kinship_rows(chromosome, position, allele, beta[:, seq], pval[:, seq], n_threads=max(1, n_threads))
-    if out == "":  # src/gwas/ols.rs:374-398
+    if out == "":  # src/gwas/ols.rs:374-398, src/gwas/mle.rs:409-433
         bname = ".".join(self.filename_sync.split(".")[:-1])
-        out = f"{bname}-ols_iterative_xxt_{n_eigenvecs + 1}_eigens-{time.time()}.csv"
+        out = f"{bname}-{method}_iterative_xxt_{n_eigenvecs + 1}_eigens-{time.time()}.csv"
     with open(out, "xb") as fo:
         fo.write(capi.format_header(capi.KIND_OLS_KINSHIP))
         fo.write(rows)
     return out
 
 
+def ols_iter_with_kinship(self, ctx: Context, filter_stats: FilterStats, keep_p_minus_1: bool,
+                          xxt_eigen_variance_explained: float, out: str, n_threads: int,
+                          block_bytes: int = 32 << 20) -> str:
+    """`poolgen ols_iter_with_kinship` (src/main.rs:280-298): into_genotypes_and_phenotypes (src/base/sync.rs:1106-1179)
+    then ols_with_covariate (src/gwas/ols.rs:278-436) and its writer, including the label indexing of
+    src/gwas/ols.rs:421-424 (row i of the allele columns carries entry i of the label vectors, whose entry 0 is the
+    intercept's)"""
+    return _iter_with_kinship(self, ctx, filter_stats, keep_p_minus_1, xxt_eigen_variance_explained, out, n_threads,
+                              block_bytes, "ols")
+
+
+def mle_iter_with_kinship(self, ctx: Context, filter_stats: FilterStats, keep_p_minus_1: bool,
+                          xxt_eigen_variance_explained: float, out: str, n_threads: int,
+                          block_bytes: int = 32 << 20) -> str:
+    """`poolgen mle_iter_with_kinship` (src/main.rs:316-326): the same loader, then mle_with_covariate
+    (src/gwas/mle.rs:307-463) -- kinship matrix, PCs by the same rule, one maximum-likelihood fit per column and
+    phenotype -- and its writer (same header and row layout, labels indexed the same way, mle.rs:449-460)"""
+    return _iter_with_kinship(self, ctx, filter_stats, keep_p_minus_1, xxt_eigen_variance_explained, out, n_threads,
+                              block_bytes, "mle")
+
+
 FileSyncPhen.write_csv = write_csv
 FileSyncPhen.ols_iter_with_kinship = ols_iter_with_kinship
+FileSyncPhen.mle_iter_with_kinship = mle_iter_with_kinship

@@ -142,3 +142,59 @@ def test_file_level_mle_iter_and_gwalpha(ctx, tmp_path):
     assert len(gl) > 100 and all(l.endswith(",Unknown") for l in gl[1:])
     devg = pb.gwalpha(ctx, counts, fmt, fs, "ML", c1["codes"])
     assert "\n".join(gl[1:]) + "\n" == pb.format_rows(pb.KIND_GWALPHA_ML, devg, pos, chr_names=names, chr_index=c1["chrom_idx"][:L]).decode()
+
+
+@pytest.mark.parametrize("n,P,m,k", [(40, 300, 0, 2), (25, 200, 1, 1), (60, 150, 3, 2), (300, 70, 2, 1), (2000, 40, 0, 1)])
+def test_mle_with_covariate(ctx, n, P, m, k):
+    """mle_iter_with_kinship's scan (pg_kin_mle_scan vs the oracle's mle_with_covariate, gwas/mle.rs:307-463): per
+    (column, phenotype) the last coefficient of the maximum-likelihood fit of y on [1 | covariates | g].  Both sides get
+    the SAME covariate columns -- unlike the OLS scan the simplex search depends on the basis, not only on the span.
+    Up to four covariates the reference's 1,000 iterations converge and the declared tolerance of this file applies;
+    beyond that its own result is the end of a capped, unconverged path (test_mle_with_covariate_capped_path)."""
+    rng = np.random.default_rng(n * 7 + m)
+    G = np.clip(0.45 + 0.2 * rng.standard_normal((P, n)), 0.0, 1.0)
+    G[3] = 0.25                                             # a constant column: X'X has no inverse -> NaN
+    cov = rng.standard_normal((n, m)) / np.sqrt(n)          # the scale of unit eigenvectors
+    phen = rng.standard_normal((n, k)) + 3.0 * G[5][:, None]
+    kin = pb.Kinship(ctx, n, P)
+    kin.append_columns(G)
+    kin.set_covariates(cov)
+    b_d, v_d, p_d = kin.mle_scan(phen)
+    kin.close()
+    _, b_o, v_o, p_o = pgo.mle_with_covariate(G, phen, 0.5, covariates=cov)
+    b_o, v_o, p_o = b_o.T, v_o.T, p_o.T
+    assert np.isnan(b_d[:, 3]).all() and np.isnan(b_o[:, 3]).all() and np.isnan(p_d[:, 3]).all()
+    ok = ~np.isnan(b_o)
+    assert (ok == ~np.isnan(b_d)).all() and ok.sum() == k * (P - 1)
+    # v_b = sigma2 [(X'X)^-1]_gg is the squared standard error up to (n - p) / n
+    eb = np.abs(b_d[ok] - b_o[ok]) / np.maximum(np.abs(b_o[ok]), np.sqrt(v_o[ok]))
+    ev = np.abs(v_d[ok] - v_o[ok]) / v_o[ok]
+    ep = np.abs(p_d[ok] - p_o[ok]) / np.maximum(p_o[ok], 1e-12)
+    print(f"mle_with_covariate n={n} m={m} k={k}: beta err median {np.median(eb):.2e} max {eb.max():.2e}; "
+          f"v_b median {np.median(ev):.2e} max {ev.max():.2e}; p median {np.median(ep):.2e} max {ep.max():.2e}")
+    assert np.median(eb) < 5e-6 and eb.max() < 1e-3
+    assert np.median(ev) < 1e-6 and ev.max() < 1e-3
+    assert np.median(ep) < 5e-6 and ep.max() < 1e-3
+
+
+def test_mle_with_covariate_capped_path(ctx):
+    """Six covariates = nine parameters: the reference's 1,000 simplex iterations end far from the optimum (the oracle's
+    coefficients are tens of standard errors from the least-squares ones), so the records are whatever the capped path
+    reaches -- parity unpinned.  What holds on both sides: the search runs, every record is finite, and v_b follows
+    sigma2 [(X'X)^-1]_gg with the sigma2 the path ended at.  More than 13 covariates are refused."""
+    n, P, m = 50, 64, 6
+    rng = np.random.default_rng(11)
+    G = np.clip(0.45 + 0.2 * rng.standard_normal((P, n)), 0.0, 1.0)
+    cov = rng.standard_normal((n, m)) / np.sqrt(n)
+    phen = rng.standard_normal((n, 1))
+    kin = pb.Kinship(ctx, n, P)
+    kin.append_columns(G)
+    kin.set_covariates(cov)
+    b_d, v_d, p_d = kin.mle_scan(phen)
+    assert np.isfinite(b_d).all() and (v_d > 0).all() and ((p_d >= 0) & (p_d <= 1)).all()
+    _, b_o, v_o, p_o = pgo.mle_with_covariate(G, phen, 0.5, covariates=cov, columns=range(8))
+    assert np.isfinite(b_o[:8]).all() and (v_o[:8] > 0).all()
+    kin.set_covariates(rng.standard_normal((n, 14)))
+    with pytest.raises(pb.PgError):
+        kin.mle_scan(phen)
+    kin.close()

@@ -189,3 +189,27 @@ def test_mle_iterate_converges_to_the_closed_form():
     ratio = (m.var[ok] / o.var[ok])[sel]
     expect = np.broadcast_to(2.0 * (n - p_x) / n, m.var[ok].shape)[sel]
     assert np.median(np.abs(ratio / expect - 1.0)) < 1e-5
+
+
+def test_mle_with_covariate_converges_to_the_closed_form():
+    """mle_with_covariate (src/gwas/mle.rs:307-463): with a few covariates the capped simplex search reaches the
+    optimum, where the last coefficient is the least-squares one and v_b = (2 RSS / n) [(X'X)^-1]_gg = 2 (n - p) / n
+    times the OLS variance.  A constant column has no inverse: NaN, like the reference's Err branch (mle.rs:377-383)."""
+    rng = np.random.default_rng(3)
+    n, P = 50, 40
+    G = np.clip(0.45 + 0.2 * rng.standard_normal((P, n)), 0.0, 1.0)
+    G[7] = 0.5
+    y = rng.standard_normal((n, 2)) + 2.0 * G[1][:, None]
+    for m in (0, 1, 2):
+        cov = rng.standard_normal((n, m)) / np.sqrt(n)
+        _, b, v, p = pgo.mle_with_covariate(G, y, 0.5, covariates=cov)
+        assert np.isnan(b[7]).all() and np.isnan(p[7]).all()
+        for c in (0, 1, 5, 30):
+            x = np.ones((n, 2 + m))
+            x[:, 1:1 + m] = cov
+            x[:, 1 + m] = G[c]
+            rc, bo, vo, po, _ = pgo.ols(x, y)
+            assert rc == 0
+            assert np.all(np.abs(b[c] - bo[1 + m]) < 1e-5 * np.sqrt(vo[1 + m]))
+            assert np.allclose(v[c] / vo[1 + m], 2.0 * (n - (2 + m)) / n, rtol=1e-5)
+            assert np.all((p[c] >= 0) & (p[c] <= 1))

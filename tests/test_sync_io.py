@@ -175,3 +175,53 @@ def test_ols_iter_with_kinship_file(ctx, tmp_path):
             assert tuple(r[:3]) == labels[i] and r[3] == f"Pheno_{j}", (r, labels[i])   # the shifted labels of ols.rs:421-424
             for got, exp, tol in ((float(r[4]), ob[i, j], 1e-7), (float(r[5]), op[i, j], 1e-6)):
                 assert (np.isnan(got) and np.isnan(exp)) or abs(got - exp) <= tol * max(abs(exp), 1e-3), (r, exp)
+
+
+@pytest.mark.gpu
+def test_mle_iter_with_kinship_file(ctx, tmp_path):
+    """`poolgen mle_iter_with_kinship` (src/main.rs:316-326) through FileSyncPhen.mle_iter_with_kinship: the loader and
+    the rows of the OLS entry, numbers against the oracle's mle_with_covariate (gwas/mle.rs:307-463) to the simplex
+    search's convergence (tests/test_nm_gpu.py states the tolerance)"""
+    from oracle import pgo
+    from tests.test_text_gpu import _sync_text
+    c1 = H.load_c1()
+    L = 500
+    counts = c1["counts"][:L]
+    chroms = ["chr1"] * L
+    pos = [int(p) for p in c1["pos"][:L]]
+    fsync = str(tmp_path / "m.sync")
+    with open(fsync, "wb") as fh:
+        fh.write(_sync_text(counts, chroms, pos))
+    fphen = str(tmp_path / "m.csv")
+    _write_c1_phen(fphen)
+    phen = pb.FilePhen(fphen, ",", 0, 1, [2, 3]).lparse()
+    fs = pb.FilterStats(pool_sizes=phen.pool_sizes, min_coverage_depth=5, min_allele_frequency=0.01)
+    src = pb.FileSyncPhen(fsync, phen.pool_names, phen.pool_sizes, phen.phen_matrix, "mle_iter_with_kinship")
+    out = src.mle_iter_with_kinship(ctx, fs, True, 0.75, str(tmp_path / "kin_mle.csv"), 2, block_bytes=40 << 10)
+    lines = open(out).read().split("\n")
+    assert lines[0] == "#chr,pos,alleles,phenotype,statistic,pvalue" and lines[-1] == ""
+    rows = [ln.split(",") for ln in lines[1:-1]]
+    ocols, olabels = pgo.load_columns(counts.transpose(0, 2, 1).astype(np.uint64), c1["codes"], H.oracle_fs(fs), True)
+    loci = sorted(range(L), key=lambda l: (chroms[l].encode(), pos[l]))
+    by_locus = {}
+    for c, (l, a) in enumerate(olabels):
+        by_locus.setdefault(l, []).append((c, a))
+    seq = [ca for l in loci for ca in by_locus.get(l, [])]
+    P = len(seq)
+    G = ocols[[c for c, _ in seq]]
+    om, ob, ov, op = pgo.mle_with_covariate(G, phen.phen_matrix, 0.75)
+    assert om == 0 and len(rows) == 2 * P and P > 150     # raw frequencies: the first eigenvalue alone crosses 0.75
+    labels = [("intercept", "0", "intercept")] + [(chroms[olabels[c][0]], str(pos[olabels[c][0]]), "ATCGND"[a]) for c, a in seq]
+    worst = 0.0
+    for j in range(2):
+        for i in range(P):
+            r = rows[j * P + i]
+            assert tuple(r[:3]) == labels[i] and r[3] == f"Pheno_{j}", (r, labels[i])
+            got_b, got_p = float(r[4]), float(r[5])
+            if np.isnan(ob[i, j]):
+                assert np.isnan(got_b) and np.isnan(got_p), r
+                continue
+            eb = abs(got_b - ob[i, j]) / max(abs(ob[i, j]), np.sqrt(ov[i, j]))
+            ep = abs(got_p - op[i, j]) / max(op[i, j], 1e-12)
+            worst = max(worst, eb, ep)
+    assert worst < 1e-3, worst

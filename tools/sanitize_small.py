@@ -95,6 +95,7 @@ kin = pb.Kinship(ctx, n, P)
 kin.append_columns(G)
 kin.set_covariates(rng.standard_normal((n, 6)))
 kin.covar_scan(rng.standard_normal((n, 3)))
+kin.mle_scan(rng.standard_normal((n, 2)))
 kin.gram()
 from poolgen_b200 import shard
 comm = shard.make_comm(ctx)
