@@ -1044,8 +1044,12 @@ __device__ __noinline__ void solve_locus(const ScanParams &p, int64_t locus, dou
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     const double sxy = tg[AC::C0 + c * K + k] - sxa * (p.ysum[k] * p.inv_n);
-                    tb[(a * K + k) * 2 + 0] = sxy / (sqrt(sxx) * sqrt(p.syy[k]));
+                    const double r = sxy / (sqrt(sxx) * sqrt(p.syy[k]));
+                    tb[(a * K + k) * 2 + 0] = r;
                     tb[(a * K + k) * 2 + 1] = 0.0;
+                    // t = r / sqrt((1 - r^2) / (n - 2)) carries the error of r times r^2 / (1 - r^2): near a perfect
+                    // correlation (a handful of pools) the digits the single-pass form loses reach the p-value
+                    if (!(16.0 * kEps * raw <= 1e-8 * (1.0 - r * r) * sxx)) redo = true;
                 }
             }
         }
@@ -1408,7 +1412,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan_kernel(const __grid_c
     unsigned char *stage0 = wb + 64;
     double *tot = reinterpret_cast<double *>(stage0 + (size_t)p.nbuf * p.stage_bytes);
     const int nbuf = p.nbuf;
-    const int red_rows = min((int)(p.stage_bytes / (kRedPitch * 8)), AC::N);
+    const int red_rows = max(1, min((int)(p.stage_bytes / (kRedPitch * 8)), AC::N));  // launch_scan_p keeps a stage >= one row
 
     for (int i = threadIdx.x; i < K * n_pad; i += blockDim.x) ys[i] = p.yc[i];
     if (W)
@@ -1596,6 +1600,8 @@ cudaError_t launch_scan_p(ScanParams p, int sm_count, cudaStream_t s) {
     common = (common + 127) / 128 * 128;
     size_t stage = (P == 32) ? (size_t)A * lay.rc * 8 : (size_t)(32 / P) * lay.freq_stride() * 8;
     stage = (stage + 127) / 128 * 128;
+    // a stage doubles as the scratch of reduce_to_tot: at least one row of it (two alleles x four pools is a 256-byte stage)
+    if (stage < (size_t)kRedPitch * 8) stage = ((size_t)kRedPitch * 8 + 127) / 128 * 128;
     // loci per epilogue block (= lanes busy in phase 2) and ring depth: prefer 32 loci and 3 stages, give way in
     // that order until the full set of warps fits (the scan is bound by the number of resident warps)
     int G = 32, nbuf = 3, nwarps = 0;

@@ -577,3 +577,28 @@ def test_fewer_pools_than_coefficients(ctx, n, A):
     if ge.any():
         sub = np.nonzero(ge)[0]
         assert np.allclose(dev.stats[sub, 0, 0, 0], orc.stat[sub, 0, 0], rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("n,A,k", [(2, 2, 1), (3, 2, 2), (4, 2, 4), (4, 2, 1), (2, 3, 3), (4, 3, 4)])
+@pytest.mark.parametrize("kind", [pb.KIND_OLS, pb.KIND_CORR])
+def test_tiny_stage(ctx, kind, n, A, k):
+    """two alleles over at most four pools: a ring stage of 256 bytes is smaller than one row of the reduction scratch
+    it doubles as (found by tools/fuzz_parity.py: the reduction then never advanced).  Biallelic loci over a handful
+    of pools are an everyday input."""
+    L = 3000
+    rng = np.random.default_rng(n * 10 + A)
+    depth = rng.integers(20, 120, (L, n))
+    minor = rng.binomial(depth, rng.uniform(0.02, 0.5, (L, 1)))
+    counts = np.zeros((L, A, n), dtype=np.uint32)
+    counts[:, 0], counts[:, 1] = depth - minor, minor
+    if A == 3:
+        counts[:, 2] = rng.integers(0, 5, (L, n))
+    phen = rng.standard_normal((n, k)) * 3.0 + 10.0
+    fs = _fs(np.full(n, 1.0 / n), min_coverage_depth=10, min_allele_frequency=0.01)
+    codes = np.array([1, 3, 5][:A], dtype=np.uint8)
+    scan = pb.Scan(ctx, kind, fs, n, codes, phen)
+    dev = scan.run_counts(counts)
+    scan.close()
+    st = H.compare_regression(kind, counts, codes, phen, fs, dev, label=f"tiny n={n} A={A} k={k}")
+    assert st["kept"] > 0.5 * L
+    print(st)

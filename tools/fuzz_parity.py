@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Randomised differential test of the per-locus scans against the CPU checker (tests/helpers.py does the comparing):
+random pool counts, allele columns, phenotypes, count distributions (sparse, deep, zero-depth pools, monomorphic loci,
+near-threshold minor alleles), storage widths and filter settings.  Every case prints one line; a violation prints the
+case's seed so that `--only SEED` replays it.
+
+    python tools/fuzz_parity.py --seconds 240 [--seed 1] [--only CASE_SEED]
+"""
+import argparse
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import poolgen_b200 as pb  # noqa: E402
+from tests import helpers as H  # noqa: E402
+
+POOLS = [2, 3, 4, 5, 6, 7, 8, 9, 12, 15, 16, 17, 20, 31, 32, 33, 40, 63, 64, 65, 100, 127, 128, 129, 130, 200, 255, 256, 257,
+         300, 511, 512, 513, 1000, 1023, 1025]
+
+
+def make_counts(rng, L, A, n, style):
+    if style == "poisson":
+        lam = rng.uniform(0.3, 30.0)
+        w = rng.dirichlet(np.full(A, rng.uniform(0.2, 3.0)), size=L)            # allele weights per locus
+        c = rng.poisson(lam * A * w[:, :, None] * np.ones((1, 1, n)))
+    elif style == "sparse":
+        c = (rng.random((L, A, n)) < rng.uniform(0.05, 0.5)) * rng.integers(1, 6, (L, A, n))
+        c[:, 0] += rng.integers(0, 3, (L, n))
+    elif style == "deep":
+        depth = rng.integers(50, 60000, (L, 1, n))
+        w = rng.dirichlet(np.full(A, 0.7), size=L)
+        c = np.floor(depth * w[:, :, None] * rng.uniform(0.7, 1.3, (L, A, n)))
+    else:  # "biallelic": two alleles carry the reads, the minor one near the MAF thresholds
+        c = np.zeros((L, A, n))
+        a0 = rng.integers(0, A, L)
+        a1 = (a0 + rng.integers(1, A, L)) % A
+        depth = rng.integers(10, 120, (L, n))
+        f = rng.choice([0.0005, 0.001, 0.005, 0.01, 0.05, 0.2, 0.5], size=L)[:, None] * rng.uniform(0.5, 1.5, (L, n))
+        minor = rng.binomial(depth, np.clip(f, 0, 1))
+        c[np.arange(L), a0] = depth - minor
+        c[np.arange(L), a1] = minor
+    c = np.asarray(c, dtype=np.int64)
+    # zero-depth pools, monomorphic loci
+    z = rng.random((L, n)) < rng.choice([0.0, 0.0, 0.002, 0.05])
+    c[np.broadcast_to(z[:, None, :], c.shape)] = 0
+    mono = rng.random(L) < 0.03
+    c[mono, 1:] = 0
+    return np.clip(c, 0, 2**31 - 1).astype(np.uint32)
+
+
+def build_case(seed):
+    rng = np.random.default_rng(seed)
+    kind = [pb.KIND_OLS, pb.KIND_CORR, pb.KIND_CHISQ, pb.KIND_FISHER][rng.integers(0, 4)]
+    n = int(rng.choice(POOLS))
+    if kind == pb.KIND_FISHER and n > 40:
+        n = int(rng.choice([2, 3, 4, 5, 8, 16, 17, 24, 40]))
+    A = int(rng.integers(2, 7))
+    codes = np.sort(rng.choice(6, size=A, replace=False)).astype(np.uint8)
+    k = int(rng.integers(1, 5))
+    if A >= 6 and k > 2:
+        k = 2
+    if A == 5 and k > 3:
+        k = 3
+    L = int(np.clip(rng.integers(100, 3000) * 60 // (n + 20), 40, 3000))
+    style = str(rng.choice(["poisson", "sparse", "deep", "biallelic"]))
+    if kind == pb.KIND_FISHER and style == "deep":
+        style = "poisson"
+    counts = make_counts(rng, L, A, n, style)
+    width = rng.choice([8, 16, 32])
+    if width == 8 and counts.max() > 255 or width == 16 and counts.max() > 65535:
+        width = 32
+    ps = rng.uniform(1.0, 50.0, n) if rng.random() < 0.5 else np.ones(n)
+    tot = 0.0
+    for v in ps:
+        tot = tot + v
+    ps = np.array([v / tot for v in ps])
+    fs = pb.FilterStats(pool_sizes=ps, remove_ns=bool(rng.random() < 0.7),
+                        min_coverage_depth=int(rng.choice([1, 1, 2, 5, 10, 20])),
+                        min_allele_frequency=float(rng.choice([0.0, 0.0005, 0.001, 0.01, 0.05, 0.2])),
+                        max_missingness_rate=float(rng.choice([0.0, 0.1, 0.5, 1.0])))
+    phen = rng.standard_normal((n, k)) * rng.uniform(0.1, 100.0) + rng.uniform(-50, 50)
+    if rng.random() < 0.3:
+        phen[:, 0] += 5.0 * counts[min(7, L - 1), 0] / np.maximum(counts[min(7, L - 1)].sum(axis=0), 1)
+    if kind == pb.KIND_CORR and n > 6 and rng.random() < 0.3:
+        phen[rng.integers(0, n, 2), rng.integers(0, k)] = np.nan
+    label = (f"seed={seed} kind={kind} n={n} codes={codes.tolist()} k={k} L={L} {style} u{width} ns={fs.remove_ns} "
+             f"depth={fs.min_coverage_depth} maf={fs.min_allele_frequency} miss={fs.max_missingness_rate} "
+             f"weighted={bool(ps.max() > ps.min())}")
+    return kind, n, codes, k, counts, int(width), fs, phen, label
+
+
+def one_case(ctx, seed, verbose=True):
+    kind, n, codes, k, counts, width, fs, phen, label = build_case(seed)
+    up = counts.astype({8: np.uint8, 16: np.uint16, 32: np.uint32}[int(width)])
+    print(f"run {label}", flush=True)   # a kernel that never returns leaves this as the last line
+    try:
+        if kind in (pb.KIND_OLS, pb.KIND_CORR):
+            scan = pb.Scan(ctx, kind, fs, n, codes, phen)
+            dev = scan.run_counts(up)
+            scan.close()
+            st = H.compare_regression(kind, counts, codes, phen, fs, dev, label=label)
+        else:
+            scan = pb.Scan(ctx, kind, fs, n, codes)
+            dev = scan.run_counts(up)
+            scan.close()
+            st = H.compare_tables(kind, counts, codes, fs, dev, label=label)
+    except pb.PgError as e:
+        if verbose:
+            print(f"REFUSED {label}: {e}", flush=True)
+        return "refused"
+    except AssertionError as e:
+        print(f"VIOLATION {label}\n    {e}", flush=True)
+        return "violation"
+    except Exception:
+        print(f"ERROR {label}", flush=True)
+        traceback.print_exc()
+        return "error"
+    if verbose:
+        print(f"ok {label} -> {st}", flush=True)
+    return "ok"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=120.0)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--only", type=int, default=None)
+    ap.add_argument("--quiet", action="store_true")
+    a = ap.parse_args()
+    ctx = pb.Context(0)
+    if a.only is not None:
+        print(one_case(ctx, a.only))
+        return 0
+    t0 = time.time()
+    tally = {}
+    i = 0
+    while time.time() - t0 < a.seconds:
+        r = one_case(ctx, a.seed * 1_000_003 + i, verbose=not a.quiet)
+        tally[r] = tally.get(r, 0) + 1
+        i += 1
+    print("fuzz_parity:", tally, flush=True)
+    ctx.close()
+    return 1 if tally.get("violation", 0) or tally.get("error", 0) else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
