@@ -406,11 +406,16 @@ __device__ __forceinline__ void covar_minnorm(const CovarParams &p, double gg, d
     pv = (b == b) ? 1.0 : nan("");
 }
 
+// the residual sum of squares y~'y~ - b g~'y~ carries the digits the centred g'g lost times y~'y~ / rss: beyond this
+// product it is re-formed from explicit residuals (4 eps x 1e5 keeps 1e-10)
+constexpr double kCovarRssRedo = 1e-5;  // (g'g / g~'g~) (y~'y~ / rss) above 1e5
+
 // NV = (1 + m) + k vectors in shared memory; a warp streams C allele columns at once so that every shared-memory load
 // of a Q / y~ element feeds C pairs of FMAs (with m = 10 covariates the one-column form spends its time on 12 LDS per
 // element of g: 0.30 of the HBM roofline; C = 4 columns share them)
-template <int NV, int C>
+template <int NV, int C, bool LIST>
 __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
+    static_assert(!LIST || C == 1, "the column list is walked one column at a time");
     extern __shared__ __align__(16) double vs[];  // [NV][ldg]
     const int ldg = p.ldg;
     for (int i = threadIdx.x; i < NV * ldg; i += blockDim.x) vs[i] = p.V[i];
@@ -420,10 +425,11 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_isd, p.ptab_bits, p.ptab_M};
     const int nq = p.nq, k = p.k;
-    // C = 1 with a column list: the columns the DMMA kernel left to the two-pass form
-    const int64_t n_items = (C == 1 && p.defer_list) ? (int64_t)*p.defer_count : p.P;
+    // LIST: the columns a streaming kernel (this one with LIST = false, or the DMMA form) left to the explicit-residual
+    // forms; the streaming instantiations carry none of that code
+    const int64_t n_items = LIST ? (int64_t)*p.defer_count : p.P;
     for (int64_t i0 = warp * C; i0 < n_items; i0 += nwarps * C) {
-        const int64_t c0 = (C == 1 && p.defer_list) ? p.defer_list[i0] : i0;
+        const int64_t c0 = LIST ? p.defer_list[i0] : i0;
         double accs[C][NV], ggs[C];
 #pragma unroll
         for (int cc = 0; cc < C; cc++) {
@@ -471,7 +477,8 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
             double gy[NV];
 #pragma unroll
             for (int v = 0; v < NV; v++) gy[v] = acc[v];
-            if (!p.minnorm && !(gg <= 1e4 * ggc)) {
+            const bool redone = !p.minnorm && !(gg <= 1e4 * ggc);
+            if (redone) {
                 // cancellation: second pass with explicit residuals g - Q u (the column is still in L2)
                 double s2 = 0.0, sy[NV];
 #pragma unroll
@@ -503,12 +510,40 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
 #pragma unroll
             for (int j = 0; j < kMaxPhenPerPass * 4; j++)
                 if (j == lane) yyj = p.yy[j];
+            const bool solve = lane < k && !p.minnorm && ggc > 0.0 && p.dfe > 0.0;
+            double rss = 0.0;
+            if (solve) {
+                b = gyj / ggc;
+                rss = yyj - b * gyj;
+            }
+            // a near-perfect fit (everyday with a handful of pools: 1 - r^2 of three points piles up at 0) leaves
+            // y~'y~ - b g~'y~ to cancellation, on top of what the centred g'g lost: explicit residuals
+            // y~ - b (g - Q u) like the reference (ols.rs:102).  The streaming form only names the column.
+            unsigned small = __ballot_sync(PG_FULL_MASK, solve && !(kCovarRssRedo * (redone ? ggc : gg) * yyj <= rss * ggc));
+            if (!LIST) {
+                if (small && lane == 0) p.defer_list[atomicAdd(p.defer_count, 1u)] = c;
+            } else {
+                while (small) {
+                    const int j = __ffs(small) - 1;
+                    small &= small - 1;
+                    const double bj = __shfl_sync(PG_FULL_MASK, b, j);
+                    double s2 = 0.0;
+                    for (int r = lane; r < p.n; r += 32) {
+                        double e = g[r];
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+                            if (v < nq) e = fma(-acc[v], vs[(size_t)v * ldg + r], e);
+                        e = fma(-bj, e, vs[(size_t)(nq + j) * ldg + r]);
+                        s2 = fma(e, e, s2);
+                    }
+                    s2 = warp_sum_fixed(s2);
+                    if (lane == j) rss = s2;
+                }
+            }
             if (lane < k) {
                 if (p.minnorm) {
                     covar_minnorm(p, gg, acc[0], gyj, lane, b, pv);
-                } else if (ggc > 0.0 && p.dfe > 0.0) {
-                    b = gyj / ggc;
-                    double rss = yyj - b * gyj;
+                } else if (solve) {
                     if (rss < 0.0) rss = 0.0;
                     vb = rss / p.dfe / ggc;
                     // estimate_significance, src/gwas/ols.rs:139-154
@@ -666,7 +701,7 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
         const double ggc = ggv - uu;
         // cancellation: the column goes to the two-pass kernel (explicit residuals g - Q u), which rewrites its records
         const bool flag = c < p.P && !(ggv <= 1e4 * ggc);
-        if (flag && lane < 8 && p.y0 == 0) p.defer_list[atomicAdd(p.defer_count, 1u)] = c;
+        bool small = false;  // a near-perfect fit of some phenotype: the residual sum of squares wants explicit residuals
         for (int j = lane >> 3; j < k; j += 4) {
             if (c >= p.P) break;
             const double gyj = scr[(nq + j) * 8 + cc], yyj = p.yy[p.y0 + j];
@@ -674,6 +709,7 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
             if (!flag && ggc > 0.0 && p.dfe > 0.0) {
                 b = gyj / ggc;
                 double rss = yyj - b * gyj;
+                if (!(kCovarRssRedo * ggv * yyj <= rss * ggc)) small = true;
                 if (rss < 0.0) rss = 0.0;
                 vb = rss / p.dfe / ggc;
                 // estimate_significance, src/gwas/ols.rs:139-154
@@ -689,6 +725,10 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
             p.var[(size_t)(p.y0 + j) * p.P + c] = vb;
             p.pval[(size_t)(p.y0 + j) * p.P + c] = pv;
         }
+        // the four lanes of a column agree; one entry per column and pass (the list kernel redoes every phenotype)
+        small |= __shfl_xor_sync(PG_FULL_MASK, (int)small, 8) != 0;
+        small |= __shfl_xor_sync(PG_FULL_MASK, (int)small, 16) != 0;
+        if (lane < 8 && ((flag && p.y0 == 0) || (!flag && small))) p.defer_list[atomicAdd(p.defer_count, 1u)] = c;
         __syncwarp();
     }
 }
@@ -749,14 +789,35 @@ __global__ void __launch_bounds__(256) covar_generic_kernel(const CovarParams p)
             }
             __syncwarp();
         }
+        const bool solve = lane < k && !p.minnorm && ggc > 0.0 && p.dfe > 0.0;
+        double b = nan(""), rss = 0.0;
+        const double gyj = lane < k ? u[nq + lane] : 0.0, yyj = lane < k ? p.yy[lane] : 0.0;
+        if (solve) {
+            b = gyj / ggc;
+            rss = yyj - b * gyj;
+        }
+        unsigned small = __ballot_sync(PG_FULL_MASK, solve && !(kCovarRssRedo * (redo ? ggc : gg) * yyj <= rss * ggc));  // see covar_kernel
+        while (small) {
+            const int j = __ffs(small) - 1;
+            small &= small - 1;
+            const double bj = __shfl_sync(PG_FULL_MASK, b, j);
+            const double *yt = p.V + (size_t)(nq + j) * ldg;
+            double s2 = 0.0;
+            for (int r = lane; r < p.n; r += 32) {
+                double e = gcol[r];  // already g - Q u after the cancellation branch above
+                if (!redo)
+                    for (int v = 0; v < nq; v++) e = fma(-u[v], p.V[(size_t)v * ldg + r], e);
+                e = fma(-bj, e, yt[r]);
+                s2 = fma(e, e, s2);
+            }
+            s2 = warp_sum_fixed(s2);
+            if (lane == j) rss = s2;
+        }
         if (lane < k) {
-            double b = nan(""), vb = nan(""), pv = nan("");
-            const double gyj = u[nq + lane], yyj = p.yy[lane];
+            double vb = nan(""), pv = nan("");
             if (p.minnorm) {
                 covar_minnorm(p, gg, u[0], gyj, lane, b, pv);
-            } else if (ggc > 0.0 && p.dfe > 0.0) {
-                b = gyj / ggc;
-                double rss = yyj - b * gyj;
+            } else if (solve) {
                 if (rss < 0.0) rss = 0.0;
                 vb = rss / p.dfe / ggc;
                 const double tt = (fabs(b) <= kEps) ? 0.0 : b / sqrt(vb);
@@ -1346,11 +1407,11 @@ int pg_kin_set_covariates(pg_kin *h, const double *cov, int m) {
 
 }  // extern "C"
 
-// covar_kernel<NV, 1> over a column list (cp.defer_list / cp.defer_count)
+// covar_kernel<NV, 1, true> over a column list (cp.defer_list / cp.defer_count)
 template <int NV>
 static cudaError_t covar_launch_list(const pg::CovarParams &cp, int sm_count, cudaStream_t s) {
     const size_t smem = (size_t)NV * cp.ldg * 8;
-    auto kern = pg::covar_kernel<NV, 1>;
+    auto kern = pg::covar_kernel<NV, 1, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<sm_count, 512, smem, s>>>(cp);
@@ -1360,7 +1421,7 @@ static cudaError_t covar_launch_list(const pg::CovarParams &cp, int sm_count, cu
 template <int NV>
 static cudaError_t covar_launch_nv(const pg::CovarParams &cp, int sm_count, cudaStream_t s) {
     const size_t smem = (size_t)NV * cp.ldg * 8;
-    auto kern = pg::covar_kernel<NV, (NV >= 9 ? 3 : (NV >= 5 ? 4 : (NV >= 3 ? 2 : 1)))>;  // C * NV accumulators fit the registers
+    auto kern = pg::covar_kernel<NV, (NV >= 9 ? 3 : (NV >= 5 ? 4 : (NV >= 3 ? 2 : 1))), false>;  // C * NV accumulators fit the registers
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int ctas_per_sm = (int)std::min<size_t>(4, (227 * 1024) / std::max<size_t>(smem, 1));
@@ -1387,35 +1448,56 @@ static bool covar_mma_fits(const pg::CovarParams &cp, int nv, int *ldq_out, int 
     return true;
 }
 
-static int covar_launch(pg_kin *h, const pg::CovarParams &cp) {
+// covar_generic_kernel over all columns (list = false) or over the deferred list
+static int covar_launch_generic(pg_kin *h, const pg::CovarParams &cp) {
     pg_ctx *ctx = h->ctx;
     const int nv = cp.nq + cp.k;
-    cudaError_t e;
+    const size_t per_warp = (size_t)(cp.ldg + nv) * 8;
+    const int warps = (int)std::min<size_t>(8, (200 * 1024) / per_warp);
+    if (warps < 1) return kfail(ctx, PG_ERR_UNSUPPORTED, "covariate scan: %d pools x %d vectors exceed shared memory", cp.n, nv);
+    const size_t smem = per_warp * warps;
+    cudaError_t e = cudaFuncSetAttribute(pg::covar_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        pg::covar_generic_kernel<<<ctx->sm_count, warps * 32, smem, h->stream>>>(cp);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covar_generic_kernel: %s", cudaGetErrorString(e));
+    return PG_OK;
+}
+
+static int covar_launch(pg_kin *h, const pg::CovarParams &cp_in) {
+    pg_ctx *ctx = h->ctx;
+    const int nv = cp_in.nq + cp_in.k;
+    cudaError_t e = cudaSuccess;
     int ldq = 0, warps = 0;
     size_t smem_mma = 0;
     static const bool no_mma = getenv("PG_COVAR_NO_MMA") != nullptr;  // tests: the per-warp dot-product kernels
     // with covariates (nv >= 5): as many phenotypes per pass as fit beside the Q columns in shared memory, G is
     // streamed once per pass
-    int kk = cp.k;
-    while (kk > 1 && !covar_mma_fits(cp, cp.nq + kk, &ldq, &warps, &smem_mma)) kk--;
-    if (!no_mma && nv >= 5 && covar_mma_fits(cp, cp.nq + kk, &ldq, &warps, &smem_mma)) {
-        // the list of columns the DMMA passes leave to the two-pass kernel: [count | columns]
-        const size_t need = (size_t)(cp.P + 2) * 8;
-        if (h->defer_bytes < need) {
-            KCUDA(ctx, cudaStreamSynchronize(h->stream));
-            cudaFree(h->d_defer);
-            h->d_defer = nullptr;
-            h->defer_bytes = 0;
-            KCUDA(ctx, cudaMalloc(&h->d_defer, need));
-            h->defer_bytes = need;
-        }
-        KCUDA(ctx, cudaMemsetAsync(h->d_defer, 0, 8, h->stream));
+    int kk = cp_in.k;
+    while (kk > 1 && !covar_mma_fits(cp_in, cp_in.nq + kk, &ldq, &warps, &smem_mma)) kk--;
+    const bool mma = !no_mma && nv >= 5 && covar_mma_fits(cp_in, cp_in.nq + kk, &ldq, &warps, &smem_mma);
+    // the list of columns the streaming kernels leave to the explicit-residual forms: [count | columns], at most one
+    // entry per column and pass
+    const size_t need = ((size_t)cp_in.P * (size_t)(mma ? (cp_in.k + kk - 1) / kk : 1) + 2) * 8;
+    if (h->defer_bytes < need) {
+        KCUDA(ctx, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_defer);
+        h->d_defer = nullptr;
+        h->defer_bytes = 0;
+        KCUDA(ctx, cudaMalloc(&h->d_defer, need));
+        h->defer_bytes = need;
+    }
+    KCUDA(ctx, cudaMemsetAsync(h->d_defer, 0, 8, h->stream));
+    pg::CovarParams cp = cp_in;
+    cp.defer_count = reinterpret_cast<unsigned *>(h->d_defer);
+    cp.defer_list = reinterpret_cast<int64_t *>(h->d_defer) + 1;
+    const bool fits = (size_t)nv * cp.ldg * 8 <= 227 * 1024;  // the vectors in shared memory (covar_kernel)
+    if (mma) {
         for (int y0 = 0; y0 < cp.k; y0 += kk) {
             pg::CovarParams pp = cp;
             pp.y0 = y0;
             pp.k = std::min(kk, cp.k - y0);
-            pp.defer_count = reinterpret_cast<unsigned *>(h->d_defer);
-            pp.defer_list = reinterpret_cast<int64_t *>(h->d_defer) + 1;
             covar_mma_fits(pp, pp.nq + pp.k, &ldq, &warps, &smem_mma);
             auto kern = pp.nq + pp.k <= 8 ? pg::covar_mma_kernel<1> : pg::covar_mma_kernel<2>;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
@@ -1425,62 +1507,46 @@ static int covar_launch(pg_kin *h, const pg::CovarParams &cp) {
             }
             if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covar_mma_kernel: %s", cudaGetErrorString(e));
         }
-        // the deferred columns (centred g'g lost to cancellation: nearly constant columns): explicit residuals, all phenotypes
-        {
-            pg::CovarParams pp = cp;
-            pp.defer_count = reinterpret_cast<unsigned *>(h->d_defer);
-            pp.defer_list = reinterpret_cast<int64_t *>(h->d_defer) + 1;
-            switch ((size_t)nv * cp.ldg * 8 <= 227 * 1024 ? nv : 0) {
-                case 5: e = covar_launch_list<5>(pp, ctx->sm_count, h->stream); break;
-                case 6: e = covar_launch_list<6>(pp, ctx->sm_count, h->stream); break;
-                case 7: e = covar_launch_list<7>(pp, ctx->sm_count, h->stream); break;
-                case 8: e = covar_launch_list<8>(pp, ctx->sm_count, h->stream); break;
-                case 9: e = covar_launch_list<9>(pp, ctx->sm_count, h->stream); break;
-                case 10: e = covar_launch_list<10>(pp, ctx->sm_count, h->stream); break;
-                case 11: e = covar_launch_list<11>(pp, ctx->sm_count, h->stream); break;
-                case 12: e = covar_launch_list<12>(pp, ctx->sm_count, h->stream); break;
-                default: {
-                    const size_t per_warp = (size_t)(cp.ldg + nv) * 8;
-                    int gw = (int)std::min<size_t>(8, (200 * 1024) / per_warp);
-                    if (gw < 1) return kfail(ctx, PG_ERR_UNSUPPORTED, "covariate scan: %d pools x %d vectors exceed shared memory", cp.n, nv);
-                    const size_t smem = per_warp * gw;
-                    e = cudaFuncSetAttribute(pg::covar_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (e == cudaSuccess) {
-                        pg::covar_generic_kernel<<<ctx->sm_count, gw * 32, smem, h->stream>>>(pp);
-                        e = cudaGetLastError();
-                    }
-                }
+    } else {
+        switch (fits ? nv : 0) {
+            case 2: e = covar_launch_nv<2>(cp, ctx->sm_count, h->stream); break;
+            case 3: e = covar_launch_nv<3>(cp, ctx->sm_count, h->stream); break;
+            case 4: e = covar_launch_nv<4>(cp, ctx->sm_count, h->stream); break;
+            case 5: e = covar_launch_nv<5>(cp, ctx->sm_count, h->stream); break;
+            case 6: e = covar_launch_nv<6>(cp, ctx->sm_count, h->stream); break;
+            case 7: e = covar_launch_nv<7>(cp, ctx->sm_count, h->stream); break;
+            case 8: e = covar_launch_nv<8>(cp, ctx->sm_count, h->stream); break;
+            case 9: e = covar_launch_nv<9>(cp, ctx->sm_count, h->stream); break;
+            case 10: e = covar_launch_nv<10>(cp, ctx->sm_count, h->stream); break;
+            case 11: e = covar_launch_nv<11>(cp, ctx->sm_count, h->stream); break;
+            case 12: e = covar_launch_nv<12>(cp, ctx->sm_count, h->stream); break;
+            default: {
+                // every column through the generic kernel, which carries the explicit-residual forms itself
+                pg::CovarParams pp = cp;
+                pp.defer_list = nullptr;
+                pp.defer_count = nullptr;
+                return covar_launch_generic(h, pp);
             }
-            if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covariate scan (deferred columns): %s", cudaGetErrorString(e));
         }
-        return PG_OK;
+        if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covar_kernel: %s", cudaGetErrorString(e));
     }
-    switch (nv) {
-        case 2: e = covar_launch_nv<2>(cp, ctx->sm_count, h->stream); break;
-        case 3: e = covar_launch_nv<3>(cp, ctx->sm_count, h->stream); break;
-        case 4: e = covar_launch_nv<4>(cp, ctx->sm_count, h->stream); break;
-        case 5: e = covar_launch_nv<5>(cp, ctx->sm_count, h->stream); break;
-        case 6: e = covar_launch_nv<6>(cp, ctx->sm_count, h->stream); break;
-        case 7: e = covar_launch_nv<7>(cp, ctx->sm_count, h->stream); break;
-        case 8: e = covar_launch_nv<8>(cp, ctx->sm_count, h->stream); break;
-        case 9: e = covar_launch_nv<9>(cp, ctx->sm_count, h->stream); break;
-        case 10: e = covar_launch_nv<10>(cp, ctx->sm_count, h->stream); break;
-        case 11: e = covar_launch_nv<11>(cp, ctx->sm_count, h->stream); break;
-        case 12: e = covar_launch_nv<12>(cp, ctx->sm_count, h->stream); break;
-        default: {
-            const size_t per_warp = (size_t)(cp.ldg + nv) * 8;
-            int warps = (int)std::min<size_t>(8, (200 * 1024) / per_warp);
-            if (warps < 1) return kfail(ctx, PG_ERR_UNSUPPORTED, "covariate scan: %d pools x %d vectors exceed shared memory", cp.n, nv);
-            const size_t smem = per_warp * warps;
-            e = cudaFuncSetAttribute(pg::covar_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) {
-                pg::covar_generic_kernel<<<ctx->sm_count, warps * 32, smem, h->stream>>>(cp);
-                e = cudaGetLastError();
-            }
-            break;
-        }
+    // the deferred columns (a centred g'g or a residual sum of squares lost to cancellation): explicit residuals, every
+    // phenotype; an empty list costs one tiny launch
+    switch (fits ? nv : 0) {
+        case 2: e = covar_launch_list<2>(cp, ctx->sm_count, h->stream); break;
+        case 3: e = covar_launch_list<3>(cp, ctx->sm_count, h->stream); break;
+        case 4: e = covar_launch_list<4>(cp, ctx->sm_count, h->stream); break;
+        case 5: e = covar_launch_list<5>(cp, ctx->sm_count, h->stream); break;
+        case 6: e = covar_launch_list<6>(cp, ctx->sm_count, h->stream); break;
+        case 7: e = covar_launch_list<7>(cp, ctx->sm_count, h->stream); break;
+        case 8: e = covar_launch_list<8>(cp, ctx->sm_count, h->stream); break;
+        case 9: e = covar_launch_list<9>(cp, ctx->sm_count, h->stream); break;
+        case 10: e = covar_launch_list<10>(cp, ctx->sm_count, h->stream); break;
+        case 11: e = covar_launch_list<11>(cp, ctx->sm_count, h->stream); break;
+        case 12: e = covar_launch_list<12>(cp, ctx->sm_count, h->stream); break;
+        default: return covar_launch_generic(h, cp);
     }
-    if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covar_kernel: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covariate scan (deferred columns): %s", cudaGetErrorString(e));
     return PG_OK;
 }
 
@@ -1593,6 +1659,12 @@ int pg_kin_covar_scan(pg_kin *h, const double *phen, int k, int iters, float *ms
     KCUDA(ctx, cudaMemcpyAsync(h->h_res, h->d_res, (size_t)3 * k * h->P * 8, cudaMemcpyDeviceToHost, h->stream));
     KCUDA(ctx, cudaStreamSynchronize(h->stream));
     if (iters > 0 && ms_total) KCUDA(ctx, cudaEventElapsedTime(ms_total, h->ev0, h->ev1));
+    static const bool debug = getenv("PG_COVAR_DEBUG") != nullptr;  // how many columns took the explicit-residual forms
+    if (debug && h->d_defer) {
+        unsigned cnt = 0;
+        cudaMemcpy(&cnt, h->d_defer, 4, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "pg_kin_covar_scan: %u of %lld columns deferred to the explicit-residual kernel\n", cnt, (long long)h->P);
+    }
     if (beta) *beta = h->h_res;
     if (var) *var = h->h_res + (size_t)k * h->P;
     if (pval) *pval = h->h_res + (size_t)2 * k * h->P;

@@ -340,3 +340,34 @@ def test_covariate_scan_dmma_kernel(ctx, n, P, m, k):
             ob[c], ov[c], op[c] = b[1 + m], v[1 + m], p_[1 + m]
     assert np.isnan(beta[:, P // 2]).all()
     _cmp_records((beta, var, pval), (ob.T, ov.T, op.T), f"dmma covar n={n} m={m}", arb=(G, cov, phen))
+
+
+@pytest.mark.parametrize("n,m,k", [(3, 0, 3), (4, 1, 2), (5, 2, 2), (6, 3, 1), (7, 4, 3), (9, 2, 4)])
+def test_covariate_scan_few_pools(ctx, n, m, k):
+    """a handful of pools: near-perfect fits are the rule (1 - r^2 of three points piles up at 0) and the columns of a
+    deeply covered locus are nearly constant, so y~'y~ - b g~'y~ loses the digits the centred g'g lost times
+    y~'y~ / rss -- those columns take the explicit-residual kernel (found by tools/fuzz_parity.py --mode kin: the
+    variance was off by 1e-8 .. 1e-6 where the oracle's explicit residuals keep 1e-13)"""
+    rng = np.random.default_rng(100 * n + m)
+    P = 4000
+    base = rng.uniform(0.05, 0.95, (P, 1))
+    G = np.clip(base + rng.uniform(1e-4, 0.2, (P, 1)) * rng.standard_normal((P, n)), 0.0, 1.0)
+    cov = rng.standard_normal((n, m))
+    phen = rng.standard_normal((n, k)) * 5.0 + 20.0
+    kin = pb.Kinship(ctx, n, P)
+    kin.append_columns(G)
+    kin.set_covariates(cov)
+    beta, var, pval = kin.covar_scan(phen)
+    kin.close()
+    ob, ov, op = (np.full((P, k), np.nan) for _ in range(3))
+    for c in range(P):
+        x = np.ones((n, 2 + m))
+        x[:, 1:1 + m] = cov
+        x[:, 1 + m] = G[c]
+        rc, b, v, p_, _ = pgo.ols(x, phen)
+        if rc == 0 and np.ptp(G[c]) > 0:
+            ob[c], ov[c], op[c] = b[1 + m], v[1 + m], p_[1 + m]
+    flat = np.ptp(G, axis=1) == 0
+    beta[:, flat], var[:, flat], pval[:, flat] = np.nan, np.nan, np.nan
+    n_arb = _cmp_records((beta, var, pval), (ob.T, ov.T, op.T), f"few pools n={n} m={m}", arb=(G, cov, phen))
+    print(f"few pools n={n} m={m} k={k}: {n_arb} of {P * k} records arbitrated")

@@ -4,7 +4,10 @@ random pool counts, allele columns, phenotypes, count distributions (sparse, dee
 near-threshold minor alleles), storage widths and filter settings.  Every case prints one line; a violation prints the
 case's seed so that `--only SEED` replays it.
 
-    python tools/fuzz_parity.py --seconds 240 [--seed 1] [--only CASE_SEED]
+    python tools/fuzz_parity.py --seconds 240 [--seed 1] [--only CASE_SEED] [--mode scan|kin|text]
+
+--mode kin: the column loader (bit-exact columns and labels) and the covariate scan; --mode text: sync text through the
+device parser in slabs against the same loci as counts (identical records).
 """
 import argparse
 import os
@@ -124,22 +127,157 @@ def one_case(ctx, seed, verbose=True):
     return "ok"
 
 
+def kin_case(ctx, seed, verbose=True):
+    """LoadAll on the device (columns and labels bit-exact) and the covariate scan with 0..4 explicit covariates"""
+    from oracle import pgo
+    from tests.test_kinship_gpu import _cmp_records
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([3, 4, 5, 6, 7, 9, 15, 16, 17, 24, 31, 33, 48, 64, 65, 100, 130, 300]))
+    A = int(rng.integers(2, 7))
+    codes = np.sort(rng.choice(6, size=A, replace=False)).astype(np.uint8)
+    L = int(np.clip(rng.integers(30, 400) * 40 // (n + 20), 10, 300))
+    style = str(rng.choice(["poisson", "sparse", "deep", "biallelic"]))
+    counts = make_counts(rng, L, A, n, style)
+    ps = rng.uniform(1.0, 50.0, n) if rng.random() < 0.5 else np.ones(n)
+    tot = 0.0
+    for v in ps:
+        tot = tot + v
+    ps = np.array([v / tot for v in ps])
+    fs = pb.FilterStats(pool_sizes=ps, remove_ns=bool(rng.random() < 0.7),
+                        min_coverage_depth=int(rng.choice([1, 1, 2, 5, 10])),
+                        min_allele_frequency=float(rng.choice([0.0, 0.0005, 0.001, 0.01, 0.05])),
+                        max_missingness_rate=float(rng.choice([0.0, 0.1, 1.0])))
+    keep = bool(rng.random() < 0.5)
+    m = int(rng.integers(0, min(5, n - 2)))
+    k = int(rng.integers(1, 4))
+    cov = rng.standard_normal((n, m))
+    phen = rng.standard_normal((n, k)) * rng.uniform(0.1, 30.0) + rng.uniform(-20, 20)
+    label = (f"kin seed={seed} n={n} codes={codes.tolist()} L={L} {style} ns={fs.remove_ns} depth={fs.min_coverage_depth} "
+             f"maf={fs.min_allele_frequency} miss={fs.max_missingness_rate} keep_p_minus_1={keep} m={m} k={k}")
+    print(f"run {label}", flush=True)
+    try:
+        kin = pb.Kinship(ctx, n, 6 * L)
+        loc, alle = kin.append_counts(counts, codes, fs, keep)
+        P = kin.columns
+        G = kin.get_columns(0, P) if P else np.zeros((0, n))
+        ocols, olabels = pgo.load_columns(counts.transpose(0, 2, 1).astype(np.uint64), codes, H.oracle_fs(fs), keep)
+        assert len(olabels) == P, f"{label}: {P} columns, oracle {len(olabels)}"
+        assert [l for l, _ in olabels] == list(loc) and [a for _, a in olabels] == list(alle), f"{label}: labels differ"
+        assert P == 0 or np.array_equal(G, ocols, equal_nan=True), f"{label}: columns differ"
+        narb = 0
+        if P and not np.isnan(G).any():
+            kin.set_covariates(cov)
+            beta, var, pval = kin.covar_scan(phen)
+            ob, ov, op = (np.full((P, k), np.nan) for _ in range(3))
+            for c in range(P):
+                x = np.ones((n, 2 + m))
+                x[:, 1:1 + m] = cov
+                x[:, 1 + m] = G[c]
+                rc, b, v, p_, _ = pgo.ols(x, phen)
+                if rc == 0:
+                    ob[c], ov[c], op[c] = b[1 + m], v[1 + m], p_[1 + m]
+            # columns inside span[1 | covariates] (constant over the pools): NaN on the device, rounding noise in the oracle
+            flat = np.ptp(G, axis=1) == 0
+            ob[flat], ov[flat], op[flat] = np.nan, np.nan, np.nan
+            beta[:, flat], var[:, flat], pval[:, flat] = np.nan, np.nan, np.nan
+            narb = _cmp_records((beta, var, pval), (ob.T, ov.T, op.T), label, arb=(G, cov, phen))
+        kin.close()
+    except pb.PgError as e:
+        if verbose:
+            print(f"REFUSED {label}: {e}", flush=True)
+        return "refused"
+    except AssertionError as e:
+        print(f"VIOLATION {label}\n    {str(e)[:600]}", flush=True)
+        return "violation"
+    except Exception:
+        print(f"ERROR {label}", flush=True)
+        traceback.print_exc()
+        return "error"
+    if verbose:
+        print(f"ok {label} -> {P} columns, {narb} arbitrated", flush=True)
+    return "ok"
+
+
+def text_case(ctx, seed, verbose=True):
+    """the same loci as sync text through the device parser (one submit per slab, random slab sizes) and as counts:
+    identical records"""
+    from tests.test_text_gpu import _sync_text
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([2, 3, 5, 8, 16, 17, 40, 100, 130, 300]))
+    L = int(np.clip(rng.integers(50, 1500) * 40 // (n + 20), 20, 1500))
+    k = int(rng.integers(1, 4))
+    kind = [pb.KIND_OLS, pb.KIND_CORR, pb.KIND_CHISQ, pb.KIND_FISHER][rng.integers(0, 4)]
+    if kind == pb.KIND_FISHER and n > 40:
+        n = 17
+    style = str(rng.choice(["poisson", "sparse", "deep", "biallelic"]))
+    if kind == pb.KIND_FISHER and style == "deep":
+        style = "poisson"
+    counts = make_counts(rng, L, 6, n, style)
+    fs = pb.FilterStats(pool_sizes=np.full(n, 1.0 / n), remove_ns=bool(rng.random() < 0.7),
+                        min_coverage_depth=int(rng.choice([1, 2, 10])),
+                        min_allele_frequency=float(rng.choice([0.0, 0.001, 0.01, 0.05])),
+                        max_missingness_rate=float(rng.choice([0.0, 0.1, 1.0])))
+    phen = rng.standard_normal((n, k)) if kind in (pb.KIND_OLS, pb.KIND_CORR) else None
+    codes = np.arange(6, dtype=np.uint8)
+    slab = int(rng.choice([7, 64, 333, 1000, 4096]))
+    crlf = bool(rng.random() < 0.3)
+    label = f"text seed={seed} kind={kind} n={n} L={L} k={k} {style} slab={slab} crlf={crlf} ns={fs.remove_ns}"
+    print(f"run {label}", flush=True)
+    try:
+        scan = pb.Scan(ctx, kind, fs, n, codes, phen)
+        whole = scan.run_counts(counts)
+        scan.stream_begin(slab)
+        chroms = ["chr%d" % (1 + l // 400) for l in range(L)]
+        pos = [10 + 3 * l for l in range(L)]
+        pending, parts = [], []
+        for l0 in range(0, L, slab):
+            text = _sync_text(counts[l0:l0 + slab], chroms[l0:l0 + slab], pos[l0:l0 + slab], crlf)
+            t, nl = pb.capi.submit_sync_text(scan, text)
+            assert nl == min(slab, L - l0), f"{label}: parsed {nl} loci"
+            pending.append(t)
+            if len(pending) == 2:
+                parts.append(scan.collect(pending.pop(0)))
+        while pending:
+            parts.append(scan.collect(pending.pop(0)))
+        scan.close()
+        status = np.concatenate([p.status for p in parts])
+        stats = np.concatenate([p.stats for p in parts])
+        assert (status == whole.status).all(), f"{label}: status differs"
+        assert np.array_equal(stats, whole.stats, equal_nan=True), f"{label}: records differ"
+    except pb.PgError as e:
+        if verbose:
+            print(f"REFUSED {label}: {e}", flush=True)
+        return "refused"
+    except AssertionError as e:
+        print(f"VIOLATION {label}\n    {str(e)[:600]}", flush=True)
+        return "violation"
+    except Exception:
+        print(f"ERROR {label}", flush=True)
+        traceback.print_exc()
+        return "error"
+    if verbose:
+        print(f"ok {label}", flush=True)
+    return "ok"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--only", type=int, default=None)
     ap.add_argument("--quiet", action="store_true")
+    ap.add_argument("--mode", choices=["scan", "kin", "text"], default="scan")
     a = ap.parse_args()
     ctx = pb.Context(0)
+    case = {"scan": one_case, "kin": kin_case, "text": text_case}[a.mode]
     if a.only is not None:
-        print(one_case(ctx, a.only))
+        print(case(ctx, a.only))
         return 0
     t0 = time.time()
     tally = {}
     i = 0
     while time.time() - t0 < a.seconds:
-        r = one_case(ctx, a.seed * 1_000_003 + i, verbose=not a.quiet)
+        r = case(ctx, a.seed * 1_000_003 + i, verbose=not a.quiet)
         tally[r] = tally.get(r, 0) + 1
         i += 1
     print("fuzz_parity:", tally, flush=True)
