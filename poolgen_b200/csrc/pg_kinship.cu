@@ -603,33 +603,35 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
     const PTableDev ptab = {reinterpret_cast<const double4 *>(p.ptab), p.ptab_isd, p.ptab_bits, p.ptab_M};
     const int64_t n_blocks = (p.P + 7) / 8;
     const int64_t wg = (int64_t)blockIdx.x * n_warps + wib, nwg = (int64_t)gridDim.x * n_warps;
-    // vector rows of this lane in each M tile (rows >= NV are zero: the address is clamped, the value masked)
+    // vector rows of this lane in each M tile.  A row of D depends on its own row of A only and a column on its own
+    // column of B, so rows >= NV (address clamped to row 0) and columns past the end (clamped to the block's first
+    // column) simply produce sums nobody reads -- no masking multiplies on the FP64 pipe the DMMAs need
     const double *arow[MT];
-    double amask[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) {
         const int v = 8 * mt + g;
-        amask[mt] = v < NV ? 1.0 : 0.0;
         arow[mt] = Vs + (size_t)(v < NV ? v : 0) * ldq + 2 * t;
     }
-    const int nb_ring = (n / 16) / kCmRing * kCmRing;  // 16-pool blocks that go through the register ring
+    const int nbf = n / 16;                       // whole 16-pool blocks: all of them go through the register ring
+    const int nbm = nbf / kCmRing * kCmRing;      // blocks of the full ring rounds; a last partial round takes the rest
     auto col_ptr = [&](int64_t blk) {
         const int64_t c0 = blk * 8;
         return p.G + (size_t)(c0 + g < p.P ? c0 + g : c0) * ldg + 2 * t;
     };
     double2 ring[kCmRing][2];
-    if (wg < n_blocks && nb_ring > 0) {
+    if (wg < n_blocks) {
         const double *g0 = col_ptr(wg);
 #pragma unroll
         for (int u = 0; u < kCmRing; u++) {
-            ring[u][0] = __ldcs(reinterpret_cast<const double2 *>(g0 + u * 16));
-            ring[u][1] = __ldcs(reinterpret_cast<const double2 *>(g0 + u * 16 + 8));
+            if (u < nbf) {
+                ring[u][0] = __ldcs(reinterpret_cast<const double2 *>(g0 + u * 16));
+                ring[u][1] = __ldcs(reinterpret_cast<const double2 *>(g0 + u * 16 + 8));
+            }
         }
     }
     for (int64_t blk = wg; blk < n_blocks; blk += nwg) {
         const int64_t c0 = blk * 8;
         const bool cval = c0 + g < p.P;
-        const double zmask = cval ? 1.0 : 0.0;  // a column past the end contributes zeros
         const double *gb = col_ptr(blk);
         const bool has_next = blk + nwg < n_blocks;
         const double *gb_next = has_next ? col_ptr(blk + nwg) : gb;
@@ -640,11 +642,8 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
         auto block16 = [&](const double2 b0, const double2 b1, int i0) {
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
-                double2 a0 = *reinterpret_cast<const double2 *>(arow[mt] + i0);
-                double2 a1 = *reinterpret_cast<const double2 *>(arow[mt] + i0 + 8);
-                if (MT > 1 && mt == MT - 1) {  // the last tile may hold fewer than 8 vectors
-                    a0.x *= amask[mt], a0.y *= amask[mt], a1.x *= amask[mt], a1.y *= amask[mt];
-                }
+                const double2 a0 = *reinterpret_cast<const double2 *>(arow[mt] + i0);
+                const double2 a1 = *reinterpret_cast<const double2 *>(arow[mt] + i0 + 8);
                 dmma884(acc[mt][0][0], acc[mt][0][1], a0.x, b0.x);
                 dmma884(acc[mt][1][0], acc[mt][1][1], a0.y, b0.y);
                 dmma884(acc[mt][0][0], acc[mt][0][1], a1.x, b1.x);
@@ -658,21 +657,33 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
         // the ring: slot u holds 16-pool block rb (rb % kCmRing == u) of this column block; as soon as a block has been
         // consumed its registers take the block kCmRing further on -- of this column block or, near its end, of the
         // warp's next one -- so kCmRing - 1 blocks (224 bytes per lane) are in flight at any time
-        for (int rb0 = 0; rb0 < nb_ring; rb0 += kCmRing) {
+        for (int rb0 = 0; rb0 < nbm; rb0 += kCmRing) {
 #pragma unroll
             for (int u = 0; u < kCmRing; u++) {
                 const int rb = rb0 + u;
-                block16(make_double2(ring[u][0].x * zmask, ring[u][0].y * zmask),
-                        make_double2(ring[u][1].x * zmask, ring[u][1].y * zmask), rb * 16);
-                const bool here = rb + kCmRing < nb_ring;
-                const double *src = here ? gb + (rb + kCmRing) * 16 : gb_next + (rb + kCmRing - nb_ring) * 16;
+                block16(ring[u][0], ring[u][1], rb * 16);
+                // the slot's next block: kCmRing further on in this column block, else block u of the warp's next one
+                const bool here = rb + kCmRing < nbf;
+                const double *src = here ? gb + (rb + kCmRing) * 16 : gb_next + u * 16;
                 if (here || has_next) {
                     ring[u][0] = __ldcs(reinterpret_cast<const double2 *>(src));
                     ring[u][1] = __ldcs(reinterpret_cast<const double2 *>(src + 8));
                 }
             }
         }
-        for (int i0 = nb_ring * 16; i0 < n; i0 += 16) {  // what the ring does not cover: pools >= n read as zero
+        if (nbm < nbf) {  // the last, partial round (slots past it already hold the next column block's data)
+#pragma unroll
+            for (int u = 0; u < kCmRing; u++) {
+                if (nbm + u < nbf) {
+                    block16(ring[u][0], ring[u][1], (nbm + u) * 16);
+                    if (has_next) {
+                        ring[u][0] = __ldcs(reinterpret_cast<const double2 *>(gb_next + u * 16));
+                        ring[u][1] = __ldcs(reinterpret_cast<const double2 *>(gb_next + u * 16 + 8));
+                    }
+                }
+            }
+        }
+        for (int i0 = nbf * 16; i0 < n; i0 += 16) {  // the partial block, if any: pools >= n read as zero
             double2 b[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
