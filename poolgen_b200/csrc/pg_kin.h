@@ -40,6 +40,8 @@ struct pg_kin {
     size_t res_elems = 0;
     void *d_defer = nullptr;  // covariate scan: [count | columns left to the two-pass kernel]
     size_t defer_bytes = 0;
+    double *d_part = nullptr;  // covariate scan (DMMA form in pool passes): partial sums per column block
+    size_t part_bytes = 0;
     // loader scratch
     uint32_t *d_sel = nullptr;
     int64_t *d_off = nullptr;

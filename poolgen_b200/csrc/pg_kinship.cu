@@ -383,6 +383,12 @@ struct CovarParams {
     // t is NaN and p is forced to 1 (ols.rs:150-151)
     int minnorm;
     int y0;            // covar_mma_kernel: first phenotype of this pass (p.k counts the phenotypes of the pass)
+    // covar_mma_kernel over a pool range [pr0, pr0 + pn): with V of all pools in shared memory little L1 is left for the
+    // loads in flight, so wide V is taken in pool passes -- a pass that is not the last leaves its partial U and g'g per
+    // column block in `part` (part_mode bit 0), a pass that is not the first adds them to its own (bit 1) and the last
+    // one finishes; 0 = all pools at once
+    int pr0, pn, part_mode;
+    double *part;      // [column block][(8 MT + 1) * 8]
     int64_t *defer_list;     // covar_mma_kernel: columns whose centred g'g is lost to cancellation, finished by
     unsigned *defer_count;   //   covar_generic_kernel (two-pass form); covar_generic_kernel: the columns to process
     double nf, sqrt_n;
@@ -483,17 +489,30 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
                 double s2 = 0.0, sy[NV];
 #pragma unroll
                 for (int v = 0; v < NV; v++) sy[v] = 0.0;
-                for (int r = lane; r < p.n; r += 32) {
-                    double e = g[r];
+                // (pool pairs, two of them in flight per lane: the chain over the Q columns is latency bound; rows
+                // n..ldg hold zeros in G and in V)
+                double s2b = 0.0;
+#pragma unroll 2
+                for (int r = 2 * lane; r < ldg; r += 64) {
+                    double2 e = *reinterpret_cast<const double2 *>(g + r);
 #pragma unroll
                     for (int v = 0; v < NV; v++)
-                        if (v < nq) e = fma(-acc[v], vs[(size_t)v * ldg + r], e);
-                    s2 = fma(e, e, s2);
+                        if (v < nq) {
+                            const double2 q2 = *reinterpret_cast<const double2 *>(vs + (size_t)v * ldg + r);
+                            e.x = fma(-acc[v], q2.x, e.x);
+                            e.y = fma(-acc[v], q2.y, e.y);
+                        }
+                    s2 = fma(e.x, e.x, s2);
+                    s2b = fma(e.y, e.y, s2b);
 #pragma unroll
                     for (int v = 0; v < NV; v++)
-                        if (v >= nq) sy[v] = fma(e, vs[(size_t)v * ldg + r], sy[v]);
+                        if (v >= nq) {
+                            const double2 q2 = *reinterpret_cast<const double2 *>(vs + (size_t)v * ldg + r);
+                            sy[v] = fma(e.x, q2.x, sy[v]);
+                            sy[v] = fma(e.y, q2.y, sy[v]);
+                        }
                 }
-                ggc = warp_sum_fixed(s2);
+                ggc = warp_sum_fixed(s2 + s2b);
 #pragma unroll
                 for (int v = 0; v < NV; v++)
                     if (v >= nq) gy[v] = warp_sum_fixed(sy[v]);
@@ -527,16 +546,24 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
                     const int j = __ffs(small) - 1;
                     small &= small - 1;
                     const double bj = __shfl_sync(PG_FULL_MASK, b, j);
-                    double s2 = 0.0;
-                    for (int r = lane; r < p.n; r += 32) {
-                        double e = g[r];
+                    double s2 = 0.0, s2b = 0.0;
+#pragma unroll 2
+                    for (int r = 2 * lane; r < ldg; r += 64) {
+                        double2 e = *reinterpret_cast<const double2 *>(g + r);
 #pragma unroll
                         for (int v = 0; v < NV; v++)
-                            if (v < nq) e = fma(-acc[v], vs[(size_t)v * ldg + r], e);
-                        e = fma(-bj, e, vs[(size_t)(nq + j) * ldg + r]);
-                        s2 = fma(e, e, s2);
+                            if (v < nq) {
+                                const double2 q2 = *reinterpret_cast<const double2 *>(vs + (size_t)v * ldg + r);
+                                e.x = fma(-acc[v], q2.x, e.x);
+                                e.y = fma(-acc[v], q2.y, e.y);
+                            }
+                        const double2 y2 = *reinterpret_cast<const double2 *>(vs + (size_t)(nq + j) * ldg + r);
+                        e.x = fma(-bj, e.x, y2.x);
+                        e.y = fma(-bj, e.y, y2.y);
+                        s2 = fma(e.x, e.x, s2);
+                        s2b = fma(e.y, e.y, s2b);
                     }
-                    s2 = warp_sum_fixed(s2);
+                    s2 = warp_sum_fixed(s2 + s2b);
                     if (lane == j) rss = s2;
                 }
             }
@@ -589,12 +616,12 @@ constexpr int kCmRing = 8;  // 16-pool blocks a lane holds in registers (256 byt
 template <int MT>
 __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const CovarParams p, int ldq, int n_warps) {
     extern __shared__ __align__(16) double cm_sm[];  // V [NV][ldq] | scratch [n_warps][(8 MT + 1) * 8]
-    const int ldg = p.ldg, n = p.n, nq = p.nq, k = p.k, NV = nq + k;
+    const int ldg = p.ldg, n = p.pn, nq = p.nq, k = p.k, NV = nq + k;  // n: the pools of this pass
     double *Vs = cm_sm;
     for (int i = threadIdx.x; i < NV * ldq; i += blockDim.x) {
         const int v = i / ldq, r = i - v * ldq;
         // the Q columns, then the y~ columns of this phenotype pass (p.k of them, starting at p.V's column nq + p.y0)
-        Vs[i] = (r < n) ? p.V[(size_t)(v < nq ? v : v + p.y0) * ldg + r] : 0.0;
+        Vs[i] = (r < n) ? p.V[(size_t)(v < nq ? v : v + p.y0) * ldg + p.pr0 + r] : 0.0;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -616,7 +643,7 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
     const int nbm = nbf / kCmRing * kCmRing;      // blocks of the full ring rounds; a last partial round takes the rest
     auto col_ptr = [&](int64_t blk) {
         const int64_t c0 = blk * 8;
-        return p.G + (size_t)(c0 + g < p.P ? c0 + g : c0) * ldg + 2 * t;
+        return p.G + (size_t)(c0 + g < p.P ? c0 + g : c0) * ldg + p.pr0 + 2 * t;
     };
     double2 ring[kCmRing][2];
     if (wg < n_blocks) {
@@ -703,6 +730,17 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
                 make_double2(acc[mt][0][0] + acc[mt][1][0], acc[mt][0][1] + acc[mt][1][1]);
         if (t == 0) scr[8 * MT * 8 + g] = gg;
         __syncwarp();
+        if (p.part_mode & 2) {  // not the first pool pass: add what the earlier ones parked
+            const double *src = p.part + (size_t)blk * SCR;
+            for (int i = lane; i < SCR; i += 32) scr[i] += src[i];
+            __syncwarp();
+        }
+        if (p.part_mode & 1) {  // not the last pool pass: park the partial sums of this column block
+            double *dst = p.part + (size_t)blk * SCR;
+            for (int i = lane; i < SCR; i += 32) dst[i] = scr[i];
+            __syncwarp();
+            continue;
+        }
         // lane = (column cc, phenotype group): centred g'g, cancellation check, records
         const int cc = lane & 7;
         const int64_t c = c0 + cc;
@@ -966,6 +1004,7 @@ int pg_kin_close(pg_kin *h) {
     cudaFree(h->d_res);
     cudaFree(h->d_defer);
     cudaFree(h->d_mle);
+    cudaFree(h->d_part);
     if (h->h_res) cudaFreeHost(h->h_res);
     cudaFree(h->d_sel);
     cudaFree(h->d_off);
@@ -1442,9 +1481,11 @@ static cudaError_t covar_launch_nv(const pg::CovarParams &cp, int sm_count, cuda
 }
 
 // the DMMA form: nv <= 16 vectors whose shared-memory copy leaves room for the warps' scratch
-static bool covar_mma_fits(const pg::CovarParams &cp, int nv, int *ldq_out, int *warps_out, size_t *smem_out) {
+static bool covar_mma_fits(const pg::CovarParams &cp, int nv, int *ldq_out, int *warps_out, size_t *smem_out,
+                           int pools = 0) {
     if (cp.minnorm || nv > 16) return false;
-    int ldq = (cp.n + 15) & ~15;  // whole 16-pool blocks, zero padded
+    if (pools <= 0) pools = cp.n;
+    int ldq = (pools + 15) & ~15;  // whole 16-pool blocks, zero padded
     ldq += 8;                     // pitch = 8 (mod 16) doubles: conflict-free 128-bit fragment loads
     const int mt = nv <= 8 ? 1 : 2;
     const size_t vbytes = (size_t)nv * ldq * 8, per_warp = (size_t)(8 * mt + 1) * 8 * 8;
@@ -1485,9 +1526,33 @@ static int covar_launch(pg_kin *h, const pg::CovarParams &cp_in) {
     static const bool no_mma = getenv("PG_COVAR_NO_MMA") != nullptr;  // tests: the per-warp dot-product kernels
     // with covariates (nv >= 5): as many phenotypes per pass as fit beside the Q columns in shared memory, G is
     // streamed once per pass
+    // pool passes of the DMMA form: shared memory beyond the 196 KB carve-out leaves 28 KB of L1 for the loads in flight
+    // (n = 2,000 with 12 vectors: V = 193 KB, 0.58 of the roofline; the same kernel runs each half of the pools at 0.90)
+    // -- then the pools are taken in the fewest passes that stay within that carve-out, the partial sums parked in
+    // global memory in between (1.7 % of the column traffic per extra pass)
+    static const int passes_env = getenv("PG_CM_POOL_PASSES") ? atoi(getenv("PG_CM_POOL_PASSES")) : 0;
+    auto pool_plan = [&](int nvp, int *per_out) {
+        const size_t scratch = (size_t)pg::kCmMaxWarps * (size_t)(8 * (nvp <= 8 ? 1 : 2) + 1) * 8 * 8;
+        int np = 1, per = cp_in.n;
+        for (; np <= 16; np++) {
+            per = (((cp_in.n + np - 1) / np) + 15) & ~15;  // pools per pass, whole 16-pool blocks
+            if ((size_t)nvp * (per + 8) * 8 + scratch <= 196 * 1024) break;
+        }
+        if (passes_env >= 1) {
+            np = passes_env;
+            per = (((cp_in.n + np - 1) / np) + 15) & ~15;
+        }
+        *per_out = per;
+        return (cp_in.n + per - 1) / per;
+    };
+    auto fits_nv = [&](int nvp) {
+        int per = 0;
+        pool_plan(nvp, &per);
+        return covar_mma_fits(cp_in, nvp, &ldq, &warps, &smem_mma, per);
+    };
     int kk = cp_in.k;
-    while (kk > 1 && !covar_mma_fits(cp_in, cp_in.nq + kk, &ldq, &warps, &smem_mma)) kk--;
-    const bool mma = !no_mma && nv >= 5 && covar_mma_fits(cp_in, cp_in.nq + kk, &ldq, &warps, &smem_mma);
+    while (kk > 1 && !fits_nv(cp_in.nq + kk)) kk--;
+    const bool mma = !no_mma && nv >= 5 && fits_nv(cp_in.nq + kk);
     // the list of columns the streaming kernels leave to the explicit-residual forms: [count | columns], at most one
     // entry per column and pass
     const size_t need = ((size_t)cp_in.P * (size_t)(mma ? (cp_in.k + kk - 1) / kk : 1) + 2) * 8;
@@ -1509,14 +1574,35 @@ static int covar_launch(pg_kin *h, const pg::CovarParams &cp_in) {
             pg::CovarParams pp = cp;
             pp.y0 = y0;
             pp.k = std::min(kk, cp.k - y0);
-            covar_mma_fits(pp, pp.nq + pp.k, &ldq, &warps, &smem_mma);
-            auto kern = pp.nq + pp.k <= 8 ? pg::covar_mma_kernel<1> : pg::covar_mma_kernel<2>;
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
-            if (e == cudaSuccess) {
-                kern<<<ctx->sm_count, warps * 32, smem_mma, h->stream>>>(pp, ldq, warps);
-                e = cudaGetLastError();
+            const int nvp = pp.nq + pp.k, mt = nvp <= 8 ? 1 : 2;
+            int per = 0;
+            const int np = pool_plan(nvp, &per);
+            if (np > 1) {
+                const size_t need_part = (size_t)((cp.P + 7) / 8) * (size_t)(8 * mt + 1) * 8 * 8;
+                if (h->part_bytes < need_part) {
+                    KCUDA(ctx, cudaStreamSynchronize(h->stream));
+                    cudaFree(h->d_part);
+                    h->d_part = nullptr;
+                    h->part_bytes = 0;
+                    KCUDA(ctx, cudaMalloc(&h->d_part, need_part));
+                    h->part_bytes = need_part;
+                }
             }
-            if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covar_mma_kernel: %s", cudaGetErrorString(e));
+            auto kern = mt == 1 ? pg::covar_mma_kernel<1> : pg::covar_mma_kernel<2>;
+            for (int ip = 0; ip < np; ip++) {
+                pp.pr0 = ip * per;
+                pp.pn = std::min(per, cp.n - pp.pr0);
+                pp.part_mode = (ip + 1 < np ? 1 : 0) | (ip > 0 ? 2 : 0);
+                pp.part = h->d_part;
+                if (!covar_mma_fits(pp, nvp, &ldq, &warps, &smem_mma, pp.pn))
+                    return kfail(ctx, PG_ERR_UNSUPPORTED, "covariate scan: %d vectors x %d pools do not fit a pool pass", nvp, pp.pn);
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+                if (e == cudaSuccess) {
+                    kern<<<ctx->sm_count, warps * 32, smem_mma, h->stream>>>(pp, ldq, warps);
+                    e = cudaGetLastError();
+                }
+                if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covar_mma_kernel: %s", cudaGetErrorString(e));
+            }
         }
     } else {
         switch (fits ? nv : 0) {
@@ -1531,6 +1617,10 @@ static int covar_launch(pg_kin *h, const pg::CovarParams &cp_in) {
             case 10: e = covar_launch_nv<10>(cp, ctx->sm_count, h->stream); break;
             case 11: e = covar_launch_nv<11>(cp, ctx->sm_count, h->stream); break;
             case 12: e = covar_launch_nv<12>(cp, ctx->sm_count, h->stream); break;
+            case 13: e = covar_launch_nv<13>(cp, ctx->sm_count, h->stream); break;
+            case 14: e = covar_launch_nv<14>(cp, ctx->sm_count, h->stream); break;
+            case 15: e = covar_launch_nv<15>(cp, ctx->sm_count, h->stream); break;
+            case 16: e = covar_launch_nv<16>(cp, ctx->sm_count, h->stream); break;
             default: {
                 // every column through the generic kernel, which carries the explicit-residual forms itself
                 pg::CovarParams pp = cp;
@@ -1555,6 +1645,10 @@ static int covar_launch(pg_kin *h, const pg::CovarParams &cp_in) {
         case 10: e = covar_launch_list<10>(cp, ctx->sm_count, h->stream); break;
         case 11: e = covar_launch_list<11>(cp, ctx->sm_count, h->stream); break;
         case 12: e = covar_launch_list<12>(cp, ctx->sm_count, h->stream); break;
+        case 13: e = covar_launch_list<13>(cp, ctx->sm_count, h->stream); break;
+        case 14: e = covar_launch_list<14>(cp, ctx->sm_count, h->stream); break;
+        case 15: e = covar_launch_list<15>(cp, ctx->sm_count, h->stream); break;
+        case 16: e = covar_launch_list<16>(cp, ctx->sm_count, h->stream); break;
         default: return covar_launch_generic(h, cp);
     }
     if (e != cudaSuccess) return kfail(ctx, PG_ERR_CUDA, "covariate scan (deferred columns): %s", cudaGetErrorString(e));
