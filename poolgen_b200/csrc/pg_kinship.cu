@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(512) covar_kernel(const CovarParams p) {
             double gy[NV];
 #pragma unroll
             for (int v = 0; v < NV; v++) gy[v] = acc[v];
-            const bool redone = !p.minnorm && !(gg <= 1e4 * ggc);
+            const bool redone = !p.minnorm && gg == gg && !(gg <= 1e4 * ggc);  // NaN frequencies: nothing to redo
             if (redone) {
                 // cancellation: second pass with explicit residuals g - Q u (the column is still in L2)
                 double s2 = 0.0, sy[NV];
@@ -749,7 +749,8 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
         for (int v = 0; v < nq; v++) uu = fma(scr[v * 8 + cc], scr[v * 8 + cc], uu);
         const double ggc = ggv - uu;
         // cancellation: the column goes to the two-pass kernel (explicit residuals g - Q u), which rewrites its records
-        const bool flag = c < p.P && !(ggv <= 1e4 * ggc);
+        // (a column with a NaN frequency -- a pool without coverage -- is finished below: NaN, NaN, p = 1; nothing to redo)
+        const bool flag = c < p.P && ggv == ggv && !(ggv <= 1e4 * ggc);
         bool small = false;  // a near-perfect fit of some phenotype: the residual sum of squares wants explicit residuals
         for (int j = lane >> 3; j < k; j += 4) {
             if (c >= p.P) break;
@@ -817,7 +818,7 @@ __global__ void __launch_bounds__(256) covar_generic_kernel(const CovarParams p)
         }
         __syncwarp();
         double ggc = gg - uu;
-        const bool redo = !p.minnorm && !(gg <= 1e4 * ggc);
+        const bool redo = !p.minnorm && gg == gg && !(gg <= 1e4 * ggc);
         if (redo) {  // explicit residual e = g - Q u, then e'e and e'y~
             for (int r = lane; r < ldg; r += 32) {
                 double e = gcol[r];
