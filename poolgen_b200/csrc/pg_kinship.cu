@@ -750,13 +750,32 @@ __global__ void __launch_bounds__(kCmMaxWarps * 32, 1) covar_mma_kernel(const Co
         const double ggc = ggv - uu;
         // cancellation: the column goes to the two-pass kernel (explicit residuals g - Q u), which rewrites its records
         // (a column with a NaN frequency -- a pool without coverage -- is finished below: NaN, NaN, p = 1; nothing to redo)
-        const bool flag = c < p.P && ggv == ggv && !(ggv <= 1e4 * ggc);
+        bool flag = c < p.P && ggv == ggv && !(ggv <= 1e4 * ggc);
+        // most flagged columns of real data are CONSTANT over the pools (a monomorphic locus gives g = 1): X'X is singular
+        // like the reference's (NaN records) and the explicit-residual kernel has nothing to find out.  The warp looks at
+        // such a column once more -- bit for bit against its first pool, from L2 -- here, outside the streaming loop
+        bool constant = false;
+        {
+            unsigned todo = __ballot_sync(PG_FULL_MASK, flag && lane < 8);
+            while (todo) {
+                const int cf = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const double *gc = p.G + (size_t)(c0 + cf) * ldg;
+                const unsigned long long first = __double_as_longlong(__ldg(gc));
+                unsigned long long differs = 0ull;
+#pragma unroll 4
+                for (int r = lane; r < p.n; r += 32) differs |= __double_as_longlong(__ldg(gc + r)) ^ first;
+                const bool same = !__any_sync(PG_FULL_MASK, differs != 0ull);
+                if (cc == cf && same) constant = true;
+            }
+            if (constant) flag = false;
+        }
         bool small = false;  // a near-perfect fit of some phenotype: the residual sum of squares wants explicit residuals
         for (int j = lane >> 3; j < k; j += 4) {
             if (c >= p.P) break;
             const double gyj = scr[(nq + j) * 8 + cc], yyj = p.yy[p.y0 + j];
             double b = nan(""), vb = nan(""), pv = nan("");
-            if (!flag && ggc > 0.0 && p.dfe > 0.0) {
+            if (!flag && !constant && ggc > 0.0 && p.dfe > 0.0) {
                 b = gyj / ggc;
                 double rss = yyj - b * gyj;
                 if (!(kCovarRssRedo * ggv * yyj <= rss * ggc)) small = true;
