@@ -315,7 +315,10 @@ def test_threshold_never_reached_takes_the_n_less_than_p_branch(ctx, n, L, k):
     assert np.all(pval.T[ok] == 1.0) and np.all(op[ok] == 1.0)
 
 
-@pytest.mark.parametrize("n,P,m,k", [(64, 333, 3, 1), (301, 1001, 6, 3), (130, 50, 12, 4), (97, 7, 9, 2)])
+@pytest.mark.parametrize("n,P,m,k", [(64, 333, 3, 1), (301, 1001, 6, 3), (130, 50, 12, 4), (97, 7, 9, 2),
+                                     (2000, 260, 10, 1),    # V = 193 KB: two pool passes (1,008 + 992 pools)
+                                     (2900, 150, 12, 3),    # 16 vectors: three pool passes, a middle pass that adds AND parks
+                                     (1000, 200, 13, 1)])   # 15 vectors: the list kernel's 13..16-vector instantiations
 def test_covariate_scan_dmma_kernel(ctx, n, P, m, k):
     """the blocked FP64 contraction of the covariate scan (covar_mma_kernel: 5..16 vectors): pool counts that are not
     multiples of 16, column counts that are not multiples of 16, one and two M tiles, several phenotypes per column,
@@ -323,6 +326,9 @@ def test_covariate_scan_dmma_kernel(ctx, n, P, m, k):
     rng = np.random.default_rng(1000 * n + m)
     G = np.clip(0.5 + 0.2 * rng.standard_normal((P, n)), 0.0, 1.0)
     G[P // 2] = 1.0
+    # nearly constant columns (a rare allele): the centred g'g loses its digits -> the explicit-residual list kernel
+    for c in (1, P // 3, P - 2):
+        G[c] = 0.999 + 1e-4 * rng.standard_normal(n)
     cov = rng.standard_normal((n, m))
     phen = rng.standard_normal((n, k))
     kin = pb.Kinship(ctx, n, P)
