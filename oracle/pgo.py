@@ -103,6 +103,7 @@ def lib():
             ("pgo_format_chisq_line", i, [C.c_char_p, C.c_uint64, C.POINTER(_TableResult), C.c_char_p, C.c_size_t]),
             ("pgo_format_fisher_line", i, [C.c_char_p, C.c_uint64, C.POINTER(_TableResult), C.c_char_p, C.c_size_t]),
             ("pgo_bound_logit", d, [d, d, d]),
+            ("pgo_check_reciprocal_division", C.c_long, [C.c_uint, C.c_long]),
             ("pgo_mle_iterate", i, [u64p, u8p, i, i, dp, i, C.POINTER(_FilterStats), C.POINTER(_LocusResult)]),
             ("pgo_mle_regress", i, [dp, i, i, dp, dp, dp, dp]),
             ("pgo_gwalpha", i, [u64p, u8p, i, i, dp, i, i, C.POINTER(_FilterStats), C.POINTER(_LocusResult)]),
@@ -279,6 +280,11 @@ def mle_regress(x, y):
     beta, var, pval = (np.full(p, np.nan) for _ in range(3))
     rc = lib().pgo_mle_regress(_dp(x), n, p, _dp(y), _dp(beta), _dp(var), _dp(pval))
     return rc, beta, var, pval
+
+
+def check_reciprocal_division(d_max, n_random):
+    """mismatches between RN(q + (c - q d) r), r = RN(1 / d), q = RN(c r) and the IEEE quotient c / d"""
+    return int(lib().pgo_check_reciprocal_division(int(d_max), int(n_random)))
 
 
 def bound_logit(x, lower, upper): return lib().pgo_bound_logit(float(x), float(lower), float(upper))

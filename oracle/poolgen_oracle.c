@@ -2025,3 +2025,35 @@ int pgo_scan_batch_tight(int kind, const uint32_t *counts_packed, int64_t n_loci
     return scan_batch_impl(kind, 1, counts_packed, n_loci, n_pools, n_alleles, allele_codes, phen, k, fs,
                            n_threads, status, n_out, allele_out, freq_mean, stat, var, t, pval);
 }
+
+
+/* ====================================================================================== */
+/* Checker for one device-side shortcut (not a restatement of the reference): the ingest   */
+/* kernel forms c / d as RN(q + (c - q d) r) with r = RN(1 / d), q = RN(c r) -- Markstein's */
+/* correction step -- instead of one IEEE division per allele.  Every operation is an      */
+/* IEEE-754 round-to-nearest operation, so the host's fma() reproduces the device bit for   */
+/* bit: returns how many (c, d) pairs differ from the plain quotient -- all c <= d <= d_max, */
+/* then n_random pairs of 32-bit operands.                                                 */
+/* ====================================================================================== */
+long pgo_check_reciprocal_division(unsigned d_max, long n_random) {
+    long bad = 0;
+    for (uint32_t d = 1; d <= d_max; d++) {
+        const double dd = (double)d, r = 1.0 / dd;
+        for (uint32_t c = 0; c <= d; c++) {
+            const double q = (double)c * r;
+            if (fma(fma(-q, dd, (double)c), r, q) != (double)c / dd) bad++;
+        }
+    }
+    uint64_t s = 88172645463325252ull;
+    for (long i = 0; i < n_random; i++) {
+        s ^= s << 13;
+        s ^= s >> 7;
+        s ^= s << 17;
+        uint32_t d = (uint32_t)(s >> 32), c = (uint32_t)s;
+        if (!d) d = 1;
+        if (i & 1) c %= d;
+        const double dd = (double)d, r = 1.0 / dd, q = (double)c * r;
+        if (fma(fma(-q, dd, (double)c), r, q) != (double)c / dd) bad++;
+    }
+    return bad;
+}

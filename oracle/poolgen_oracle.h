@@ -190,4 +190,7 @@ int pgo_scan_batch_tight(int kind, const uint32_t *counts_packed, int64_t n_loci
 #ifdef __cplusplus
 }
 #endif
+/* checker for the ingest kernel's reciprocal-based quotient (see the definition): number of mismatching pairs */
+long pgo_check_reciprocal_division(unsigned d_max, long n_random);
+
 #endif

@@ -126,9 +126,16 @@ __global__ void __launch_bounds__(256) ingest_counts_kernel(const CT *__restrict
             jj++;
         }
         if (d > 0xFFFFFFFEull) d = 0xFFFFFFFEull;  // documented limit: per-pool depth < 2^32 - 1
+        // f = c / d, correctly rounded like the reference's division, at one reciprocal per pool instead of one division
+        // per allele: with r = RN(1 / d), q = RN(c r) and the exact remainder c - q d, RN(q + rem r) IS RN(c / d)
+        // (Markstein's correction step; bit-identical for all 32-bit operands -- a host-side test under tests/ checks
+        // the same sequence on the host exhaustively for d <= 4096 and on random pairs)
         const double dd = (double)d, wi = w[i];
+        const double rd = __drcp_rn(dd);
         for (int j = 0; j < lay.A; j++) {
-            const double f = (d == 0) ? nan("") : (double)c[j] / dd;
+            const double cj = (double)c[j];
+            const double q0 = __dmul_rn(cj, rd);
+            const double f = (d == 0) ? nan("") : __fma_rn(__fma_rn(-q0, dd, cj), rd, q0);
             fl[lay.freq_off(i, j)] = f;
             if (d != 0) q[j] = fma(f, wi, q[j]);
         }

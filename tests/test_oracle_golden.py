@@ -213,3 +213,11 @@ def test_mle_with_covariate_converges_to_the_closed_form():
             assert np.all(np.abs(b[c] - bo[1 + m]) < 1e-5 * np.sqrt(vo[1 + m]))
             assert np.allclose(v[c] / vo[1 + m], 2.0 * (n - (2 + m)) / n, rtol=1e-5)
             assert np.all((p[c] >= 0) & (p[c] <= 1))
+
+
+def test_reciprocal_division_is_the_ieee_quotient():
+    """The ingest kernel forms the first-stage frequency c / depth with one reciprocal per pool and a correction step
+    per allele (pg_ingest.cu); the keep-mask is bit-exact only if that IS the correctly rounded quotient the reference
+    computes (src/base/sync.rs:166-192).  The sequence consists of IEEE operations only, so the host reproduces it:
+    every c <= d <= 4096 and 2e7 random pairs of 32-bit operands."""
+    assert pgo.check_reciprocal_division(4096, 20_000_000) == 0
