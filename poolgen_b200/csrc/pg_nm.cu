@@ -110,6 +110,117 @@ __device__ void nelder_mead(const Cost &cost, int d, double h, int max_iters, do
     for (int j = 0; j < d; j++) best[j] = v[0][j];
 }
 
+// The same search as a state machine with ONE call site of the cost function, for costs that dwarf the bookkeeping
+// (gwalpha: 4.7 x; mle_iter's quadratic form is so cheap that the indexed state costs 3 x -- it keeps the loop
+// above): the lanes of a warp run independent searches
+// and take different steps in the same iteration (one reflects, one expands, one shrinks); with a call per step the
+// warp would walk through every call site in turn, each time with a few lanes active.  Here every lane names the
+// point it needs next, all evaluate together, and each then advances its own state.  The sequence of points, costs
+// and comparisons of a search is exactly the textbook loop's.
+template <int MAXD, typename Cost>
+__device__ void nelder_mead_one_site(const Cost &cost, int d, double h, int max_iters, double *best) {
+    double v[MAXD + 1][MAXD], c[MAXD + 1];
+    const int nv = d + 1;
+    for (int i = 0; i < nv; i++)
+        for (int j = 0; j < d; j++) v[i][j] = (i == j) ? h + 0.5 : h;
+    auto sort = [&]() {
+        for (int a = 1; a < nv; a++) {
+            const double ca = c[a];
+            double va[MAXD];
+            for (int j = 0; j < d; j++) va[j] = v[a][j];
+            int b = a - 1;
+            while (b >= 0 && ca < c[b]) {
+                c[b + 1] = c[b];
+                for (int j = 0; j < d; j++) v[b + 1][j] = v[b][j];
+                b--;
+            }
+            c[b + 1] = ca;
+            for (int j = 0; j < d; j++) v[b + 1][j] = va[j];
+        }
+    };
+    enum { kInit, kReflect, kExpand, kOutside, kInside, kShrink, kDone };
+    int state = kInit, idx = 0, it = 0;
+    double x0[MAXD], xr[MAXD], xt[MAXD], fr = 0.0;
+    // the vertices are sorted: stop, or set up the next iteration (centroid of all but the worst, reflected point)
+    auto next_iteration = [&]() {
+        double c0 = 0.0;
+        for (int i = 0; i < nv; i++) c0 = c0 + c[i];
+        c0 = c0 / (double)nv;
+        double ss = 0.0;
+        for (int i = 0; i < nv; i++) ss = ss + (c[i] - c0) * (c[i] - c0);
+        const double sd = sqrt(1.0 / ((double)nv - 1.0) * ss);
+        if (sd < kEps || it >= max_iters) {
+            state = kDone;
+            return;
+        }
+        it++;
+        for (int j = 0; j < d; j++) x0[j] = v[0][j];
+        for (int i = 1; i < nv - 1; i++)
+            for (int j = 0; j < d; j++) x0[j] = x0[j] + v[i][j];
+        const double inv = 1.0 / (double)(nv - 1);
+        for (int j = 0; j < d; j++) x0[j] = x0[j] * inv;
+        for (int j = 0; j < d; j++) xr[j] = x0[j] + (x0[j] - v[nv - 1][j]) * 1.0;
+        state = kReflect;
+    };
+    auto accept = [&](const double *x, double f) {  // replaces the worst vertex
+        for (int j = 0; j < d; j++) v[nv - 1][j] = x[j];
+        c[nv - 1] = f;
+        sort();
+        next_iteration();
+    };
+    auto begin_shrink = [&]() {  // every vertex half way towards the best one, then their costs one by one
+        for (int i = 1; i < nv; i++)
+            for (int j = 0; j < d; j++) v[i][j] = v[0][j] + (v[i][j] - v[0][j]) * 0.5;
+        idx = 1;
+        state = kShrink;
+    };
+    while (state != kDone) {
+        const double *x = (state == kInit || state == kShrink) ? v[idx] : (state == kReflect ? xr : xt);
+        const double f = cost(x);
+        if (state == kInit || state == kShrink) {
+            c[idx] = f;
+            if (++idx == nv) {
+                sort();
+                next_iteration();
+            }
+        } else if (state == kReflect) {
+            fr = f;
+            if (fr < c[nv - 2] && fr >= c[0]) {
+                accept(xr, fr);
+            } else if (fr < c[0]) {
+                for (int j = 0; j < d; j++) xt[j] = x0[j] + (xr[j] - x0[j]) * 2.0;
+                state = kExpand;
+            } else if (fr >= c[nv - 2]) {
+                if (fr < c[nv - 1]) {  // outside contraction
+                    for (int j = 0; j < d; j++) xt[j] = x0[j] + (xr[j] - x0[j]) * 0.5;
+                    state = kOutside;
+                } else {  // inside contraction
+                    for (int j = 0; j < d; j++) xt[j] = x0[j] + (v[nv - 1][j] - x0[j]) * 0.5;
+                    state = kInside;
+                }
+            } else {
+                begin_shrink();  // only reachable with NaN costs
+            }
+        } else if (state == kExpand) {
+            if (f < fr)
+                accept(xt, f);
+            else
+                accept(xr, fr);
+        } else if (state == kOutside) {
+            if (f <= fr)
+                accept(xt, f);
+            else
+                begin_shrink();
+        } else {  // kInside
+            if (f < c[nv - 1])
+                accept(xt, f);
+            else
+                begin_shrink();
+        }
+    }
+    for (int j = 0; j < d; j++) best[j] = v[0][j];
+}
+
 // the renormalised frequency of (pool i, device column j) over the kept columns, as the scan forms it
 __device__ __forceinline__ void renorm_generic(const NmParams &p, const double *fl, const uint32_t *dl, int i, unsigned kept,
                                                double *F) {
@@ -500,7 +611,7 @@ __global__ void __launch_bounds__(128) gwalpha_kernel(const NmParams p) {
             return -ra - rb;
         };
         double par[kNmMaxD];
-        nelder_mead<kNmMaxD>(cost, 4, 1.0, 1000, par);
+        nelder_mead_one_site<kNmMaxD>(cost, 4, 1.0, 1000, par);
         double sol[4];
         for (int e = 0; e < 4; e++) sol[e] = bound_logit(par[e], kEps, 10.00);
         const double a_mu = p.gw_min + (p.gw_max - p.gw_min) * (sol[0] / (sol[0] + sol[1]));
