@@ -508,7 +508,7 @@ def text_numbers(ctx, pb, n_threads=2):
     import ctypes as C
     import threading
     import torch
-    slab, slabs_per_thread = 4096, 8
+    slab, slabs_per_thread = 4096, 24   # long enough that the three formats of the pipeline drain weigh little
     per_locus_cap = 16 + N_POOLS * 24
     host, hptr = ctx.pinned_empty((2, slab * per_locus_cap), np.uint8)
     nbytes = [pb.synth_sync_text_host(SEED, i * slab, slab, N_POOLS, N_ALLELES, host[i]) for i in range(2)]
