@@ -600,9 +600,16 @@ __global__ void __launch_bounds__(128) gwalpha_kernel(const NmParams p) {
                 }
                 return ra + rb;
             }
-            for (int i = 0; i < n; i++) {  // maximum_likelihood_beta (gwalpha.rs:43-82)
-                double da = beta_cdf_dev(sh[0], sh[1], lna, pa[i]) - beta_cdf_dev(sh[0], sh[1], lna, pa0[i]);
-                double db = beta_cdf_dev(sh[2], sh[3], lnb, pb[i]) - beta_cdf_dev(sh[2], sh[3], lnb, pb0[i]);
+            // maximum_likelihood_beta (gwalpha.rs:43-82).  The lower percentile of bin i is the upper one of bin i - 1
+            // (pa0[i] = pa[i - 1], bit for bit), so its cdf is the value the previous turn computed: the same
+            // numbers as the reference's two evaluations per bin at half the continued fractions
+            double lo_a = beta_cdf_dev(sh[0], sh[1], lna, pa0[0]), lo_b = beta_cdf_dev(sh[2], sh[3], lnb, pb0[0]);
+            for (int i = 0; i < n; i++) {
+                const double hi_a = beta_cdf_dev(sh[0], sh[1], lna, pa[i]), hi_b = beta_cdf_dev(sh[2], sh[3], lnb, pb[i]);
+                double da = hi_a - lo_a;
+                double db = hi_b - lo_b;
+                lo_a = hi_a;
+                lo_b = hi_b;
                 if (da < kEps) da = kEps;
                 if (db < kEps) db = kEps;
                 ra += log10(da);
