@@ -243,13 +243,17 @@ __device__ __forceinline__ int col_of_code(const NmParams &p, unsigned code) {
 
 // ---- mle_iter: a warp takes 32 loci; moments by the whole warp (lane = pool), simplex searches with lane = locus ------
 constexpr int kMlePhen = 4;                                   // phenotypes per pass over the loci of a block
-constexpr int kMleMom = 20 + kMlePhen * 7;                    // xbar[5] | Sxx lower triangle [15] | per phenotype ybar, syy, sxy[5]
+// a locus' row of moments: xbar[5] | Sxx lower triangle [15] | per phenotype of the pass: ybar, syy, sxy[5]
+// the per-locus row a launch actually uses: with fewer than kMlePhen phenotypes the rows shrink, and with them the
+// shared memory per warp -- the searches are latency bound, so every resident warp counts (16 -> 20 per SM at k = 1)
+__host__ __device__ inline int mle_mom_stride(int k) { return 20 + (k < kMlePhen ? k : kMlePhen) * 7; }
 constexpr int kMleWarps = 4;
 
 __global__ void __launch_bounds__(kMleWarps * 32) mle_kernel(const NmParams p) {
-    extern __shared__ __align__(16) double mle_sm[];  // [warps][32][kMleMom]
+    extern __shared__ __align__(16) double mle_sm[];  // [warps][32][stride]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *mom = mle_sm + (size_t)wib * 32 * kMleMom;
+    const int stride = mle_mom_stride(p.k);
+    double *mom = mle_sm + (size_t)wib * 32 * stride;
     const int64_t warp = (int64_t)blockIdx.x * kMleWarps + wib;
     const int64_t nwarps = (int64_t)gridDim.x * kMleWarps;
     const int n = p.lay.n, n_pad = p.lay.n_pad, S = p.lay.A - 1, k = p.k;
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(kMleWarps * 32) mle_kernel(const NmParams p) {
             }
             for (int e = 0; e < 15; e++) sxx[e] = (e < mg * (mg + 1) / 2) ? warp_sum_fixed(sxx[e]) : 0.0;
             if (lane == 0) {
-                double *mo = mom + (size_t)g * kMleMom;
+                double *mo = mom + (size_t)g * stride;
                 for (int a = 0; a < PG_MAX_SLOTS; a++) mo[a] = xb[a];
                 for (int e = 0; e < 15; e++) mo[5 + e] = sxx[e];
             }
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(kMleWarps * 32) mle_kernel(const NmParams p) {
         // ---- lane = locus: collinear columns, (X'X)^-1
         double xbar[PG_MAX_SLOTS], Sxx[PG_MAX_SLOTS][PG_MAX_SLOTS];
         {
-            const double *mo = mom + (size_t)lane * kMleMom;
+            const double *mo = mom + (size_t)lane * stride;
             for (int a = 0; a < PG_MAX_SLOTS; a++) xbar[a] = act ? mo[a] : 0.0;
             for (int a = 0; a < PG_MAX_SLOTS; a++)
                 for (int b = 0; b <= a; b++) Sxx[a][b] = Sxx[b][a] = act ? mo[5 + a * (a + 1) / 2 + b] : 0.0;
@@ -396,7 +400,7 @@ __global__ void __launch_bounds__(kMleWarps * 32) mle_kernel(const NmParams p) {
                 const unsigned cg = __shfl_sync(PG_FULL_MASK, colw, g), kg = __shfl_sync(PG_FULL_MASK, kept, g);
                 const double *fl = p.freq + (size_t)(l0 + g) * p.lay.freq_stride();
                 const uint32_t *dl = p.depth + (size_t)(l0 + g) * p.lay.depth_stride();
-                const double *mo = mom + (size_t)g * kMleMom;
+                const double *mo = mom + (size_t)g * stride;
                 double xb[PG_MAX_SLOTS];
                 for (int a = 0; a < PG_MAX_SLOTS; a++) xb[a] = mo[a];
                 for (int jj = 0; jj < jn; jj++) {
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(kMleWarps * 32) mle_kernel(const NmParams p) {
                     syy = warp_sum_fixed(syy);
                     for (int a = 0; a < PG_MAX_SLOTS; a++) sxy[a] = (a < mg) ? warp_sum_fixed(sxy[a]) : 0.0;
                     if (lane == 0) {
-                        double *o = mom + (size_t)g * kMleMom + 20 + jj * 7;
+                        double *o = mom + (size_t)g * stride + 20 + jj * 7;
                         o[0] = ybar;
                         o[1] = syy;
                         for (int a = 0; a < PG_MAX_SLOTS; a++) o[2 + a] = sxy[a];
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(kMleWarps * 32) mle_kernel(const NmParams p) {
             if (lane < cnt && (act || true)) {
                 for (int jj = 0; jj < jn; jj++) {
                     const int j = j0 + jj;
-                    const double *mo = mom + (size_t)lane * kMleMom + 20 + jj * 7;
+                    const double *mo = mom + (size_t)lane * stride + 20 + jj * 7;
                     const double ybar_l = mo[0], syy_l = mo[1];
                     double sxy_l[PG_MAX_SLOTS];
                     for (int a = 0; a < PG_MAX_SLOTS; a++) sxy_l[a] = mo[2 + a];
@@ -759,11 +763,15 @@ cudaError_t launch_kin_mle(const KinMleParams &p, int sm_count, cudaStream_t s) 
 cudaError_t launch_nm(const NmParams &p, int sm_count, cudaStream_t s) {
     if (p.n_loci == 0) return cudaSuccess;
     if (p.kind == PG_KIND_MLE) {
-        const size_t smem = (size_t)kMleWarps * 32 * kMleMom * 8;
+        const size_t smem = (size_t)kMleWarps * 32 * mle_mom_stride(p.k) * 8;
         cudaError_t e = cudaFuncSetAttribute(mle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        int per_sm = 0;  // resident CTAs per SM as registers and shared memory allow: whole waves of them
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mle_kernel, kMleWarps * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
         int64_t grid = ((p.n_loci + 31) / 32 + kMleWarps - 1) / kMleWarps;
-        if (grid > (int64_t)sm_count * 4) grid = (int64_t)sm_count * 4;
+        if (grid > (int64_t)sm_count * per_sm) grid = (int64_t)sm_count * per_sm;
         mle_kernel<<<(unsigned)grid, kMleWarps * 32, smem, s>>>(p);
     } else {
         int64_t grid = (p.n_loci * (p.lay.A - 1) + 127) / 128;
